@@ -1,0 +1,203 @@
+"""Caller-side finite-element helpers: Lagrange function spaces and functions.
+
+The reference takes its level set as a `dolfinx.fem.Function` (reference
+src/phifem/mesh_scripts.py:571-577, tests/test_compute_meshtags.py:153-158).  dolfinx and
+basix are not part of this framework, so this module is the stand-in the drop-in API
+accepts: `functionspace(mesh, ("Lagrange", k))`, `Function(V)`, `Function.interpolate(f)`,
+`Function.x.array`.  It is host-side numpy bookkeeping (dof numbering, node sets,
+tabulation of the basis at the detection points); the hot path consumes its arrays on the
+GPU.
+
+Element definition (matches basix 0.9 defaults [dep-knowledge, SURVEY.md A.2/C.7]):
+Lagrange with GLL-warped nodes (differs from equispaced from degree 3), cell-local dof order
+= vertices, then edges in dolfinx local edge order, then faces, then interior.  Global dof
+numbering is ours (vertices, then edges, faces, cells); the hot path takes the dofmap as an
+input array, so any numbering works.
+"""
+import itertools
+import math
+
+import numpy as np
+
+from .mesh import Mesh
+
+_GLL = {
+    1: np.array([0.0, 1.0]),
+    2: np.array([0.0, 0.5, 1.0]),
+    3: np.array([0.0, (1.0 - 1.0 / math.sqrt(5.0)) / 2.0, (1.0 + 1.0 / math.sqrt(5.0)) / 2.0, 1.0]),
+}
+
+# dolfinx local edge order [dep-knowledge, SURVEY.md C.7]
+LOCAL_EDGES = {
+    "triangle": ((1, 2), (0, 2), (0, 1)),
+    "quadrilateral": ((0, 1), (0, 2), (1, 3), (2, 3)),
+    "tetrahedron": ((2, 3), (1, 3), (1, 2), (0, 3), (0, 2), (0, 1)),
+}
+LOCAL_FACES = {"tetrahedron": ((1, 2, 3), (0, 2, 3), (0, 1, 3), (0, 1, 2))}
+REF_VERTICES = {
+    "triangle": np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]]),
+    "quadrilateral": np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [1.0, 1.0]]),
+    "tetrahedron": np.array([[0.0, 0, 0], [1.0, 0, 0], [0, 1.0, 0], [0, 0, 1.0]]),
+}
+
+
+def _monomial_exponents(cell_type, k):
+    if cell_type == "quadrilateral":
+        return [(i, j) for i in range(k + 1) for j in range(k + 1)]
+    tdim = 2 if cell_type == "triangle" else 3
+    return [e for e in itertools.product(range(k + 1), repeat=tdim) if sum(e) <= k]
+
+
+def _monomials(exps, pts):
+    pts = np.asarray(pts, dtype=np.float64)
+    out = np.ones((len(pts), len(exps)))
+    for m, e in enumerate(exps):
+        for d, p in enumerate(e):
+            if p:
+                out[:, m] *= pts[:, d] ** p
+    return out
+
+
+class LagrangeElement:
+    """Reference Lagrange element of degree 1..3 on triangle / quadrilateral / tetrahedron."""
+
+    def __init__(self, cell_type, degree):
+        if cell_type not in REF_VERTICES:
+            raise NotImplementedError(cell_type)
+        if degree not in (1, 2, 3):
+            raise NotImplementedError("Lagrange degree %d" % degree)
+        self.cell_type, self.degree = cell_type, degree
+        rv = REF_VERTICES[cell_type]
+        k = degree
+        inner = _GLL[k][1:-1]
+        nodes = [v for v in rv]
+        # entity bookkeeping: list of (kind, local entity, position)
+        ents = [("v", i, 0) for i in range(len(rv))]
+        for e, (a, b) in enumerate(LOCAL_EDGES[cell_type]):
+            for j, s in enumerate(inner):
+                nodes.append((1 - s) * rv[a] + s * rv[b])
+                ents.append(("e", e, j))
+        if cell_type == "tetrahedron" and k == 3:
+            for f, face in enumerate(LOCAL_FACES[cell_type]):
+                nodes.append(rv[list(face)].mean(axis=0))
+                ents.append(("f", f, 0))
+        if cell_type == "triangle" and k == 3:
+            nodes.append(rv.mean(axis=0))
+            ents.append(("c", 0, 0))
+        if cell_type == "quadrilateral":
+            for j, (sy, sx) in enumerate(itertools.product(inner, inner)):
+                nodes.append(np.array([sx, sy]))
+                ents.append(("c", 0, j))
+        self.nodes = np.array(nodes)
+        self.entities = ents
+        self.exps = _monomial_exponents(cell_type, k)
+        assert len(self.exps) == len(self.nodes)
+        self.coef = np.linalg.inv(_monomials(self.exps, self.nodes))  # [monomial, basis]
+        self.ndofs = len(self.nodes)
+
+    def tabulate(self, pts, snap=True):
+        """Basis values [..., npts, ndofs] at reference points [..., npts, tdim]; entries within
+        1e-9 of 0 / +-1 are snapped like FFCx does with its tables [dep-knowledge]."""
+        pts = np.asarray(pts, dtype=np.float64)
+        lead = pts.shape[:-1]
+        tab = _monomials(self.exps, pts.reshape(-1, pts.shape[-1])) @ self.coef
+        if snap:
+            for target in (0.0, 1.0, -1.0):
+                tab[np.abs(tab - target) < 1e-9] = target
+        return tab.reshape(lead + (self.ndofs,))
+
+
+def _unique_rows(keys):
+    uniq, inv = np.unique(keys, axis=0, return_inverse=True)
+    return uniq, inv.reshape(-1)
+
+
+class FunctionSpace:
+    def __init__(self, mesh, degree):
+        self.mesh = mesh
+        self.element = LagrangeElement(mesh.cell_type, degree)
+        self.degree = degree
+        cells = mesh.cells_host.astype(np.int64)
+        nc = len(cells)
+        nv = mesh.num_vertices
+        k = degree
+        cols = [cells]
+        offset = nv
+        if k > 1:
+            edges = LOCAL_EDGES[mesh.cell_type]
+            pairs = np.stack([cells[:, list(e)] for e in edges], axis=1)      # [Nc, ne, 2]
+            flip = pairs[:, :, 0] > pairs[:, :, 1]
+            _, inv = _unique_rows(np.sort(pairs, axis=2).reshape(-1, 2))
+            eid = inv.reshape(nc, len(edges))
+            n_edges = int(eid.max()) + 1
+            for e in range(len(edges)):
+                for j in range(k - 1):
+                    pos = np.where(flip[:, e], k - 2 - j, j)
+                    cols.append((offset + eid[:, e] * (k - 1) + pos)[:, None])
+            offset += n_edges * (k - 1)
+        kinds = [ent[0] for ent in self.element.entities]
+        if "f" in kinds:
+            faces = LOCAL_FACES[mesh.cell_type]
+            tri = np.sort(np.stack([cells[:, list(f)] for f in faces], axis=1), axis=2)
+            _, inv = _unique_rows(tri.reshape(-1, 3))
+            fid = inv.reshape(nc, len(faces))
+            for f in range(len(faces)):
+                cols.append((offset + fid[:, f])[:, None])
+            offset += int(fid.max()) + 1
+        n_int = kinds.count("c")
+        if n_int:
+            base = offset + np.arange(nc)[:, None] * n_int
+            cols.append(base + np.arange(n_int)[None, :])
+            offset += nc * n_int
+        self.dofmap = np.ascontiguousarray(np.concatenate(cols, axis=1).astype(np.int32))
+        self.num_dofs = int(offset)
+        assert self.dofmap.shape[1] == self.element.ndofs
+
+    def tabulate_dof_coordinates(self):
+        """Physical coordinates of the dofs [num_dofs, gdim] (affine / bilinear push-forward of the
+        reference nodes, accumulated vertex by vertex)."""
+        from . import _geometry
+        mesh = self.mesh
+        shape = _geometry.coordinate_basis(mesh.cell_type, self.element.nodes)  # [nd, nvpc]
+        xc = mesh.x_host[mesh.cells_host]                                        # [Nc, nvpc, gdim]
+        out = np.zeros((self.num_dofs, mesh.gdim))
+        for i in range(self.element.ndofs):
+            acc = None
+            for v in range(xc.shape[1]):
+                w = shape[i, v]
+                if w == 0.0:
+                    continue
+                term = xc[:, v, :] if w == 1.0 else w * xc[:, v, :]
+                acc = term if acc is None else acc + term
+            out[self.dofmap[:, i]] = acc
+        return out
+
+
+class _Vector:
+    def __init__(self, n):
+        self.array = np.zeros(n, dtype=np.float64)
+
+
+class Function:
+    """A finite-element function: `function_space`, `x.array` (dof values)."""
+
+    def __init__(self, V, values=None):
+        self.function_space = V
+        self.x = _Vector(V.num_dofs)
+        if values is not None:
+            self.x.array[:] = values
+
+    def interpolate(self, f):
+        """f receives coordinates as an array of shape (3, npoints), like dolfinx."""
+        X = self.function_space.tabulate_dof_coordinates()
+        x3 = np.zeros((3, len(X)))
+        x3[:X.shape[1]] = X.T
+        with np.errstate(all="ignore"):
+            self.x.array[:] = np.asarray(f(x3), dtype=np.float64)
+        return self
+
+
+def functionspace(mesh: Mesh, element):
+    """`element` = ("Lagrange", degree) or an int degree."""
+    degree = element[1] if isinstance(element, (tuple, list)) else int(element)
+    return FunctionSpace(mesh, degree)

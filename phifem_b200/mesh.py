@@ -1,0 +1,292 @@
+"""Mesh, topology and mesh tags: the data model of the hot path.
+
+Stand-ins for the dolfinx objects the reference API exchanges (`dolfinx.mesh.Mesh`,
+`MeshTags`, `AdjacencyList_int32`; reference src/phifem/mesh_scripts.py:12-15,151-153,386).
+A `Mesh` owns its arrays on ONE device (HBM-resident for the whole life of the mesh, like a
+dolfinx mesh lives in host memory); host copies are made lazily and only for the
+duck-typed dolfinx-style accessors.
+
+Layout in HBM (row-major, int32 indices, fp64 coordinates):
+    x      [Nv, gdim]   vertex coordinates
+    cells  [Nc, nvpc]   cell -> vertex (dolfinx local order)
+    c2f    [Nc, nfpc]   cell -> facet, local facet i opposite local vertex i on simplices
+    f2c    [Nf, 2]      facet -> cells ascending, -1 pad on the mesh boundary
+    fverts [Nf, nvpf]   facet -> sorted vertex tuple
+
+Facet numbering = lexicographic rank of the sorted vertex tuple (what dolfinx 0.9 produces in
+serial [probed on the reference's golden tag files, SURVEY.md C.2]).  The topology builder
+is sort/unique plumbing written with torch ops so it runs where the mesh lives.
+"""
+import numpy as np
+import torch
+
+from . import _geometry as G
+
+
+def default_device():
+    return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() \
+        else torch.device("cpu")
+
+
+class AdjacencyList:
+    """Minimal `dolfinx.graph.AdjacencyList_int32` look-alike (host arrays)."""
+
+    def __init__(self, array, offsets):
+        self.array = np.ascontiguousarray(array, dtype=np.int32)
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+
+    def links(self, i):
+        return self.array[self.offsets[i]:self.offsets[i + 1]]
+
+    @property
+    def num_nodes(self):
+        return len(self.offsets) - 1
+
+
+class _CellType:
+    def __init__(self, name):
+        self.name = name
+
+
+class Topology:
+    def __init__(self, mesh):
+        self._mesh = mesh
+        self.dim = G.TDIM[mesh.cell_type]
+        self.cell_type = _CellType(mesh.cell_type)
+        self._conn = {}
+
+    def cell_name(self):
+        return self._mesh.cell_type
+
+    def create_connectivity(self, d0, d1):
+        if (d0, d1) in self._conn:
+            return
+        m, tdim = self._mesh, self.dim
+        if (d0, d1) == (tdim, 0):
+            c = m.cells_host
+            adj = AdjacencyList(c.ravel(), np.arange(0, c.size + 1, c.shape[1]))
+        elif (d0, d1) == (tdim, tdim - 1):
+            c2f = m.c2f.cpu().numpy()
+            adj = AdjacencyList(c2f.ravel(), np.arange(0, c2f.size + 1, c2f.shape[1]))
+        elif (d0, d1) == (tdim - 1, tdim):
+            f2c = m.f2c.cpu().numpy()
+            cnt = (f2c >= 0).sum(axis=1)
+            adj = AdjacencyList(f2c[f2c >= 0], np.r_[0, np.cumsum(cnt)])
+        elif (d0, d1) == (tdim - 1, 0):
+            fv = m.facet_vertices.cpu().numpy()
+            adj = AdjacencyList(fv.ravel(), np.arange(0, fv.size + 1, fv.shape[1]))
+        elif (d0, d1) == (0, tdim):
+            c = m.cells_host
+            order = np.argsort(c.ravel(), kind="stable")
+            cnt = np.bincount(c.ravel(), minlength=m.num_vertices)
+            adj = AdjacencyList((order // c.shape[1]), np.r_[0, np.cumsum(cnt)])
+        else:
+            raise NotImplementedError("connectivity (%d, %d)" % (d0, d1))
+        self._conn[(d0, d1)] = adj
+
+    def connectivity(self, d0, d1):
+        return self._conn.get((d0, d1))
+
+
+class _Geometry:
+    def __init__(self, mesh):
+        self._mesh = mesh
+
+    @property
+    def x(self):
+        x = self._mesh.x_host
+        out = np.zeros((len(x), 3))
+        out[:, :x.shape[1]] = x
+        return out
+
+
+class Mesh:
+    """Unstructured mesh of triangles, quadrilaterals or tetrahedra on one device."""
+
+    def __init__(self, x, cells, cell_type, device=None):
+        if cell_type not in G.CELL_TYPES:
+            raise NotImplementedError("unsupported cell type '%s'" % cell_type)
+        self.cell_type = cell_type
+        self.device = torch.device(device) if device is not None else default_device()
+        self.x = torch.as_tensor(x, dtype=torch.float64).to(self.device).contiguous()
+        self.cells = torch.as_tensor(cells).to(torch.int32).to(self.device).contiguous()
+        if self.cells.ndim != 2 or self.cells.shape[1] != G.NVPC[cell_type]:
+            raise ValueError("cells must have shape [Nc, %d]" % G.NVPC[cell_type])
+        self.gdim = int(self.x.shape[1])
+        self.num_vertices = int(self.x.shape[0])
+        self.num_cells = int(self.cells.shape[0])
+        self._topo = None
+        self._host = {}
+        self.topology = Topology(self)
+        self.geometry = _Geometry(self)
+
+    @staticmethod
+    def from_xdmf(x, cells_file_order, cell_type, device=None):
+        """XDMF stores quadrilaterals cyclically; dolfinx uses tensor order [a,b,d,c]
+        [probed, SURVEY.md A.1]."""
+        cells = np.asarray(cells_file_order)
+        if cell_type == "quadrilateral":
+            cells = cells[:, [0, 1, 3, 2]]
+        return Mesh(x, cells, cell_type, device)
+
+    # ---- host mirrors (lazy) -------------------------------------------------------------
+    @property
+    def x_host(self):
+        if "x" not in self._host:
+            self._host["x"] = self.x.cpu().numpy()
+        return self._host["x"]
+
+    @property
+    def cells_host(self):
+        if "cells" not in self._host:
+            self._host["cells"] = self.cells.cpu().numpy()
+        return self._host["cells"]
+
+    # ---- facet topology (lazy, on the mesh's device) ----------------------------------------
+    def _build(self):
+        if self._topo is None:
+            self._topo = build_facet_topology(self.cells, self.cell_type, self.num_vertices)
+        return self._topo
+
+    @property
+    def c2f(self):
+        return self._build()[0]
+
+    @property
+    def f2c(self):
+        return self._build()[1]
+
+    @property
+    def facet_vertices(self):
+        return self._build()[2]
+
+    @property
+    def num_facets(self):
+        return int(self.f2c.shape[0])
+
+
+def _unique_inverse(keys):
+    uniq, inv = torch.unique(keys, sorted=True, return_inverse=True)
+    return uniq, inv
+
+
+def build_facet_topology(cells, cell_type, num_vertices):
+    """Number the facets and build c2f / f2c / facet->vertices with sort-unique passes.
+
+    Replaces `mesh.topology.create_connectivity(tdim, tdim-1)` / `(tdim-1, tdim)` as used at
+    reference mesh_scripts.py:151-153,419-422.  Works on any torch device.
+    """
+    lfs = G.LOCAL_FACETS[cell_type]
+    nc, nfpc, nvpf = cells.shape[0], len(lfs), len(lfs[0])
+    c64 = cells.to(torch.int64)
+    nv = int(num_vertices)
+    # sorted vertex tuples of every (cell, local facet) instance, cell-major
+    cols = []
+    for lf in lfs:
+        t, _ = torch.sort(c64[:, list(lf)], dim=1)
+        cols.append(t)
+    inst = torch.stack(cols, dim=1).reshape(nc * nfpc, nvpf)
+    del cols
+    key = inst[:, 0] * nv + inst[:, 1]
+    if nvpf == 2:
+        uniq, inv = _unique_inverse(key)
+        fverts = torch.stack([uniq // nv, uniq % nv], dim=1)
+    else:
+        upair, pinv = _unique_inverse(key)          # rank of the leading pair keeps lexicographic order
+        key = pinv * nv + inst[:, 2]
+        del pinv
+        uniq, inv = _unique_inverse(key)
+        pair = upair[uniq // nv]
+        fverts = torch.stack([pair // nv, pair % nv, uniq % nv], dim=1)
+        del upair, pair
+    del inst, key
+    nf = int(uniq.shape[0])
+    c2f = inv.reshape(nc, nfpc).to(torch.int32)
+    owner = torch.arange(nc, device=cells.device, dtype=torch.int32).repeat_interleave(nfpc)
+    lo = torch.full((nf,), nc, dtype=torch.int32, device=cells.device)
+    hi = torch.full((nf,), -1, dtype=torch.int32, device=cells.device)
+    lo.scatter_reduce_(0, inv, owner, reduce="amin")
+    hi.scatter_reduce_(0, inv, owner, reduce="amax")
+    hi = torch.where(hi == lo, torch.full_like(hi, -1), hi)
+    f2c = torch.stack([lo, hi], dim=1).contiguous()
+    return c2f.contiguous(), f2c, fverts.to(torch.int32).contiguous()
+
+
+class MeshTags:
+    """`dolfinx.mesh.MeshTags` look-alike: `dim`, sorted int32 `indices`, int32 `values`, `find`.
+
+    Tags live on the device (`values_dev` holds one entry per entity, 0 = untagged); the host
+    views `indices` / `values` are materialised on first access (one D2H copy)."""
+
+    def __init__(self, mesh, dim, values_dev=None, indices=None, values=None):
+        self.mesh = mesh
+        self.dim = dim
+        self.values_dev = values_dev
+        self._indices = None if indices is None else np.ascontiguousarray(indices, dtype=np.int32)
+        self._values = None if values is None else np.ascontiguousarray(values, dtype=np.int32)
+
+    @staticmethod
+    def from_lists(mesh, dim, indices, values):
+        """Like `dolfinx.mesh.meshtags(mesh, dim, indices, values)`."""
+        indices = np.asarray(indices, dtype=np.int32)
+        values = np.asarray(values, dtype=np.int32)
+        n = mesh.num_cells if dim == mesh.topology.dim else mesh.num_facets
+        dense = torch.zeros(n, dtype=torch.int32)
+        dense[torch.from_numpy(indices.astype(np.int64))] = torch.from_numpy(values)
+        return MeshTags(mesh, dim, dense.to(mesh.device), indices, values)
+
+    def _materialise(self):
+        if self._indices is None:
+            dense = self.values_dev.cpu().numpy()
+            idx = np.nonzero(dense)[0].astype(np.int32)
+            self._indices, self._values = idx, dense[idx].astype(np.int32)
+
+    @property
+    def indices(self):
+        self._materialise()
+        return self._indices
+
+    @property
+    def values(self):
+        self._materialise()
+        return self._values
+
+    def find(self, value):
+        self._materialise()
+        return self._indices[self._values == value]
+
+
+class Measure:
+    """What the reference returns as `ufl.Measure("ds", subdomain_data=[(100, e), (101, e)])`
+    (mesh_scripts.py:631-633): calling it with an id selects the flat `[cell, local_facet, ...]`
+    entity list of that id."""
+
+    def __init__(self, integral_type, domain, subdomain_data=None):
+        self.integral_type = integral_type
+        self.domain = domain
+        self.subdomain_data = subdomain_data
+
+    def __call__(self, subdomain_id):
+        return MeasureRestriction(self, subdomain_id)
+
+    def entities(self, subdomain_id, device=False):
+        if self.subdomain_data is None:
+            raise ValueError("measure without subdomain data")
+        for sid, ents in self.subdomain_data:
+            if sid == subdomain_id:
+                return ents if device else ents.cpu().numpy()
+        raise KeyError(subdomain_id)
+
+
+class MeasureRestriction:
+    def __init__(self, measure, subdomain_id):
+        self.measure = measure
+        self.subdomain_id = subdomain_id
+
+    @property
+    def integration_entities(self):
+        return self.measure.entities(self.subdomain_id)
+
+    @property
+    def integration_entities_dev(self):
+        return self.measure.entities(self.subdomain_id, device=True)
