@@ -1,0 +1,94 @@
+"""Synthetic meshes and level sets of the benchmark configurations.
+
+S-2D(n): n x n squares split by the "right" diagonal -> 2 n^2 triangles (what
+`dolfinx.mesh.create_rectangle` gives the reference demos,
+demo/strong-dirichlet/flower/main.py:48-49).  S-3D(n): n^3 cubes x 6 Kuhn tetrahedra.
+Vertices are numbered lexicographically; generated directly on the target device.
+"""
+import itertools
+import math
+
+import numpy as np
+import torch
+
+from .mesh import Mesh, default_device
+
+
+def _grid_vertices(lo, hi, n, device):
+    axes = [torch.linspace(float(a), float(b), n + 1, dtype=torch.float64, device=device)
+            for a, b in zip(lo, hi)]
+    grids = torch.meshgrid(*axes, indexing="ij")
+    return torch.stack([g.reshape(-1) for g in grids], dim=1).contiguous()
+
+
+def rectangle_mesh(n, lo=(-1.0, -1.0), hi=(1.0, 1.0), device=None):
+    """2 n^2 triangles; vertex id = i*(n+1)+j for the point (x_i, y_j)."""
+    device = torch.device(device) if device is not None else default_device()
+    x = _grid_vertices(lo, hi, n, device)
+    i = torch.arange(n, device=device, dtype=torch.int64)
+    I, J = torch.meshgrid(i, i, indexing="ij")
+    v00 = (I * (n + 1) + J).reshape(-1)
+    v10, v01, v11 = v00 + (n + 1), v00 + 1, v00 + (n + 1) + 1
+    t0 = torch.stack([v00, v10, v11], dim=1)
+    t1 = torch.stack([v00, v01, v11], dim=1)
+    cells = torch.stack([t0, t1], dim=1).reshape(-1, 3).to(torch.int32)
+    return Mesh(x, cells, "triangle", device)
+
+
+def box_mesh(n, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0), device=None):
+    """6 n^3 Kuhn tetrahedra: each cube is split along the 6 monotone edge paths from its low
+    corner to its high corner; vertex id = (i*(n+1)+j)*(n+1)+k."""
+    device = torch.device(device) if device is not None else default_device()
+    x = _grid_vertices(lo, hi, n, device)
+    i = torch.arange(n, device=device, dtype=torch.int64)
+    I, J, K = torch.meshgrid(i, i, i, indexing="ij")
+    base = ((I * (n + 1) + J) * (n + 1) + K).reshape(-1)
+    stride = [(n + 1) * (n + 1), n + 1, 1]
+    tets = []
+    for perm in itertools.permutations(range(3)):
+        offs, acc = [0], 0
+        for a in perm:
+            acc += stride[a]
+            offs.append(acc)
+        tets.append(base[:, None] + torch.tensor(offs, device=device, dtype=torch.int64)[None, :])
+    cells = torch.stack(tets, dim=1).reshape(-1, 4).to(torch.int32)
+    return Mesh(x, cells, "tetrahedron", device)
+
+
+def unstructured_variant(mesh, jitter=0.2, seed=0):
+    """Interior-vertex jitter (uniform in +-jitter*h), random cell permutation and random vertex
+    relabelling: the "unstructured" stress variant of SURVEY.md section 8d."""
+    rng = np.random.default_rng(seed)
+    x = mesh.x.cpu().numpy().copy()
+    cells = mesh.cells.cpu().numpy().astype(np.int64)
+    lo, hi = x.min(axis=0), x.max(axis=0)
+    nv = len(x)
+    n = round(nv ** (1.0 / x.shape[1])) - 1
+    h = (hi - lo) / n
+    interior = np.all((x > lo + 1e-12) & (x < hi - 1e-12), axis=1)
+    x[interior] += rng.uniform(-jitter, jitter, size=(int(interior.sum()), x.shape[1])) * h
+    cells = cells[rng.permutation(len(cells))]
+    relabel = rng.permutation(nv)
+    xn = np.empty_like(x)
+    xn[relabel] = x
+    return Mesh(xn, relabel[cells].astype(np.int32), mesh.cell_type, mesh.device)
+
+
+SPHERE_CENTER = (0.5 + math.pi / 1000.0, 0.5 + math.e / 1000.0, 0.5 + math.sqrt(2.0) / 1000.0)
+SPHERE_RADIUS = 0.45
+
+
+def sphere_levelset(x, center=SPHERE_CENTER, radius=SPHERE_RADIUS):
+    """phi = |x - c|^2 - r^2 at the rows of x (torch tensor [N, gdim]); the offsets keep every
+    vertex value away from zero."""
+    c = torch.tensor(center[:x.shape[1]], dtype=torch.float64, device=x.device)
+    d = x - c
+    return (d * d).sum(dim=1) - radius * radius
+
+
+def ball_source(x, center=SPHERE_CENTER, radius=0.2, value=10.0):
+    """Nodal values of 10 * 1[ball], the analogue of the demos' source term
+    (demo/strong-dirichlet/flower/data.py:54-62)."""
+    c = torch.tensor(center[:x.shape[1]], dtype=torch.float64, device=x.device)
+    d = x - c
+    return torch.where((d * d).sum(dim=1) <= radius * radius, value, 0.0).to(torch.float64)
