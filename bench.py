@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""Benchmark of the phi-FEM hot path: cut-cell tags + CSR assembly, cells/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--n 204] [--impl ours|reference]
+
+One "step" = one pass of the hot path over the synthetic 3D P1 configuration of BASELINE.json
+(config E): classify all cells and facets of a 6 n^3 Kuhn-tetrahedra unit cube
+against a sphere level set, then assemble the strong-Dirichlet phi-FEM operator and load vector into
+CSR (pattern / slot maps are the precomputed symbolic phase, timed separately as `symbolic_ms`).
+Prints ONE JSON line (rank 0).  `value` times the device-resident pass with CUDA events; `e2e` times
+the public API with pinned host buffers for the level set, the source term and all results.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "phi-FEM cells assembled/s (tags+CSR)"
+UNIT = "cells/s"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {}
+        for key in dir(nv):
+            if key.startswith("nvmlClocksEventReason") or key.startswith("nvmlClocksThrottleReason"):
+                val = getattr(nv, key)
+                if isinstance(val, int) and val and "All" not in key and "None" not in key:
+                    names.setdefault(val, key.replace("nvmlClocksEventReason", "")
+                                     .replace("nvmlClocksThrottleReason", ""))
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if bits & bit and name not in ("GpuIdle", "ApplicationsClocksSetting"):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=1.0)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def algorithmic_bytes(counts):
+    """compulsory traffic, each input read once / each output written once."""
+    nc, nv, nf, gdim, nvpc = counts["Nc"], counts["Nv"], counts["Nf"], counts["gdim"], counts["nvpc"]
+    na, nva, ng, nnz = counts["Na"], counts["Nv_active"], counts["Ng"], counts["nnz"]
+    b_tags_cells = 4 * nvpc * nc + 8 * nv + 4 * nc
+    b_tags_facets = 4 * nvpc * nc + 4 * nf            # c2f (== f2c in size) + facet tags out
+    b_asm = (4 * nvpc * na + 8 * gdim * nva + 8 * nva + 8 * nva + 4 * na + 8 * ng + 12 * nnz
+             + 4 * (nv + 1) + 8 * nv)
+    # the numeric cell kernel alone: no column indices / indptr (they belong to the symbolic phase)
+    b_cells_kernel = 4 * nvpc * na + 8 * gdim * nva + 16 * nva + 4 * na + 8 * nnz + 8 * nva
+    return {"tags_cells": b_tags_cells, "tags_facets": b_tags_facets, "assembly": b_asm,
+            "cells_kernel": b_cells_kernel, "total": b_tags_cells + b_tags_facets + b_asm}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores (cpu_baseline of our line, and --impl reference)
+# ------------------------------------------------------------------------------------------------
+class CpuWorkload:
+    def __init__(self, n):
+        import torch
+        from oracle import native as ON
+        from phifem_b200 import assemble, synthetic
+        from phifem_b200.mesh import MeshTags
+        self.ON, self.n = ON, n
+        mesh = synthetic.box_mesh(n, device="cpu")
+        self.x = mesh.x.numpy()
+        self.cells = np.ascontiguousarray(mesh.cells.numpy())
+        self.c2f = np.ascontiguousarray(mesh.c2f.numpy())
+        self.f2c = np.ascontiguousarray(mesh.f2c.numpy())
+        self.phi = synthetic.sphere_levelset(mesh.x).numpy()
+        self.f = synthetic.ball_source(mesh.x).numpy()
+        ct = ON.tag_cells_p1(self.x, self.cells, self.phi)
+        ft = ON.tag_facets_p1(self.x, self.cells, self.c2f, self.f2c, self.phi, ct)
+        # ds(100) entities + symbolic phase through the product's host plumbing on CPU tensors
+        from oracle import tags as OT
+        ents = OT.integration_entities(self.c2f, self.f2c, (ct == 1) | (ct == 2), ft == 4)
+        plan = assemble.build_plan(mesh, MeshTags(mesh, 3, torch.from_numpy(ct)),
+                                   MeshTags(mesh, 2, torch.from_numpy(ft)), ents)
+        self.plan = {k: np.ascontiguousarray(getattr(plan, k).numpy())
+                     for k in ("active", "slots_cells", "entities", "slots_boundary", "ghost", "slots_ghost")}
+        self.nnz = plan.nnz
+        self.num_cells = mesh.num_cells
+
+    def step(self):
+        ON, p = self.ON, self.plan
+        ct = ON.tag_cells_p1(self.x, self.cells, self.phi)
+        ON.tag_facets_p1(self.x, self.cells, self.c2f, self.f2c, self.phi, ct)
+        ON.assemble_p1(self.x, self.cells, self.c2f, self.f2c, self.phi, self.f, ct, p["active"],
+                       p["slots_cells"], p["entities"], p["slots_boundary"], p["ghost"],
+                       p["slots_ghost"], 1.0, self.nnz)
+
+
+def cpu_measure(n, steps, warmup):
+    from oracle import native as ON
+    w = CpuWorkload(n)
+    for _ in range(warmup):
+        w.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        w.step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": w.num_cells / dt, "unit": UNIT, "cores": ON.num_threads(), "kind": "port",
+            "sample": "n=%d Kuhn unit cube (%d tetrahedra), sphere level set, tags + CSR assembly, "
+                      "C/OpenMP oracle port; dolfinx/PETSc is not installable here" % (n, w.num_cells),
+            "ms_per_step": dt * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cpu_measure(args.cpu_n, max(1, args.steps), max(1, args.warmup))
+    line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": max(1, args.steps), "warmup": max(1, args.warmup), "ms_per_step": res["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": "synthetic 3D P1 phi-FEM Poisson, Kuhn tetrahedra, sphere level set "
+                                   "(bounded sample n=%d of the n=%d configuration)" % (args.cpu_n, args.n)},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from phifem_b200 import _lib, assemble, fem, mesh_scripts, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.n
+    t_setup = time.perf_counter()
+    if world > 1:
+        from phifem_b200 import dist as pdist
+        problem = pdist.SlabProblem(n, rank, world, dev)
+        mesh, phi, f = problem.mesh, problem.phi, problem.f
+    else:
+        problem = None
+        mesh = synthetic.box_mesh(n, device=dev)
+        phi = synthetic.sphere_levelset(mesh.x)
+        f = synthetic.ball_source(mesh.x)
+    mesh.c2f  # build the facet topology (mesh-level symbolic, once per mesh)
+    mesh.detj_bounds()
+    torch.cuda.synchronize()
+    topo_s = time.perf_counter() - t_setup
+
+    V = fem.functionspace_p1_device(mesh)
+    fn = fem.Function(V, phi)
+    dls = mesh_scripts._DeviceLevelset(mesh, fn, 1)
+    ws = mesh_scripts.classify(mesh, dls)
+    torch.cuda.synchronize()
+    counters = ws.counters.cpu().numpy()
+
+    t0 = time.perf_counter()
+    tdim = mesh.topology.dim
+    from phifem_b200.mesh import MeshTags
+    ctags, ftags = MeshTags(mesh, tdim, ws.cell_tags), MeshTags(mesh, tdim - 1, ws.facet_tags)
+    ctags.tags8, ftags.tags8 = ws.cell_tags8, ws.facet_tags8
+    ents = mesh_scripts._integration_entities_dev(mesh, ws.cell_tags8, ws.facet_tags8, 4, (1, 2))
+    plan = assemble.build_plan(mesh, ctags, ftags, ents)
+    if problem is not None:
+        problem.attach_plan(plan)
+    torch.cuda.synchronize()
+    symbolic_ms = (time.perf_counter() - t0) * 1e3
+    data, b = plan.new_outputs()
+
+    def step(events=None):
+        k = 0
+
+        def mark():
+            nonlocal k
+            if events is not None:
+                events[k].record()
+                k += 1
+        mark()
+        mesh_scripts.classify_cells(mesh, dls, ws)
+        mark()
+        mesh_scripts.classify_facets(mesh, dls, ws)
+        mark()
+        assemble.assemble_into(plan, phi, f, 1.0, data, b, marks=mark)
+        if problem is not None:
+            problem.exchange(data, b)
+        mark()
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    n_marks = 8
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(n_marks)] for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(args.steps):
+        step(evs[i])
+    stop.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    total_ms = start.elapsed_time(stop)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+
+    # per-kernel durations from the events recorded inside the timed region
+    names = ["tag_cells", "tag_facets", "zero", "assemble_cells", "assemble_boundary", "assemble_ghost",
+             "exchange"]
+    per = {nm: statistics.mean(evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(args.steps))
+           for j, nm in enumerate(names)}
+
+    n_cells_local = mesh.num_cells
+    n_cells_total = n_cells_local
+    if world > 1:
+        t = torch.tensor([n_cells_local], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        n_cells_total = int(t.item())
+    value = n_cells_total / (ms_per_step * 1e-3)
+
+    counts = {"Nc": mesh.num_cells, "Nv": mesh.num_vertices, "Nf": mesh.num_facets, "gdim": mesh.gdim,
+              "nvpc": mesh.cells.shape[1], "Na": int(plan.active.numel()), "Ng": int(plan.ghost.numel()),
+              "Nv_active": int((plan.indptr[1:] > plan.indptr[:-1]).sum()), "nnz": plan.nnz,
+              "Ne_ds100": int(plan.entities.shape[0]),
+              "interior": int(counters[0]), "cut": int(counters[1]), "exterior": int(counters[2])}
+    ab = algorithmic_bytes(counts)
+    peak, peak_src = _peaks()
+    dominant = max(("tag_cells", "tag_facets", "assemble_cells"), key=lambda k_: per[k_])
+    kbytes = {"tag_cells": ab["tags_cells"], "tag_facets": ab["tags_facets"],
+              "assemble_cells": ab["cells_kernel"]}[dominant]
+    achieved = kbytes / (per[dominant] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": kbytes,
+                "step_achieved_gbs": ab["total"] / (ms_per_step * 1e-3) / 1e9,
+                "step_frac": ab["total"] / (ms_per_step * 1e-3) / 1e9 / peak,
+                "kernels_ms": per,
+                "kernels_gbs": {"tag_cells": ab["tags_cells"] / per["tag_cells"] / 1e6,
+                                "tag_facets": ab["tags_facets"] / per["tag_facets"] / 1e6,
+                                "assemble_cells": ab["cells_kernel"] / per["assemble_cells"] / 1e6}}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        with open(traffic_file) as fh:
+            roofline["traffic"] = json.load(fh).get(dominant)
+
+    # ---- e2e: public API, pinned host buffers in, pinned host buffers out ---------------------------
+    e2e = None
+    if world == 1:
+        phi_h = phi.cpu().pin_memory()
+        f_h = f.cpu().pin_memory()
+        out_h = {"ct": torch.empty(mesh.num_cells, dtype=torch.int32).pin_memory(),
+                 "ft": torch.empty(mesh.num_facets, dtype=torch.int32).pin_memory(),
+                 "data": torch.empty(plan.nnz, dtype=torch.float64).pin_memory(),
+                 "b": torch.empty(mesh.num_vertices, dtype=torch.float64).pin_memory()}
+        import warnings
+
+        def e2e_step():
+            fn_h = fem.Function(V, phi_h)                                   # host level set
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", RuntimeWarning)
+                ct_, ft_, _, ds_, _ = mesh_scripts.compute_tags_measures(mesh, fn_h, 1, box_mode=True)
+            A_, b_ = assemble.assemble_strong_dirichlet(plan, phi_h, f_h, stab_coef=1.0)
+            out_h["ct"].copy_(ct_.values_dev, non_blocking=True)
+            out_h["ft"].copy_(ft_.values_dev, non_blocking=True)
+            out_h["data"].copy_(A_.data, non_blocking=True)
+            out_h["b"].copy_(b_, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_steps = max(2, min(args.steps, 5))
+        for _ in range(2):
+            e2e_step()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        e2e = {"value": mesh.num_cells / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
+               "h2d_bytes_per_step": int(phi_h.numel() * 8 * 2 + f_h.numel() * 8),
+               "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in out_h.values())),
+               "api": "compute_tags_measures(box_mode=True) + assemble_strong_dirichlet(plan, ...) with "
+                      "pinned host level set / source in and pinned host tags + CSR values + b out; "
+                      "assembly plan (symbolic phase) reused"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_measure(args.cpu_n, 3, 1)
+        cpu.pop("ms_per_step")
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "synthetic 3D P1 phi-FEM Poisson (BASELINE.json configs[4]): "
+                                       "%d Kuhn tetrahedra per GPU (n=%d), sphere level set, tags + "
+                                       "strong-Dirichlet CSR assembly" % (n_cells_local, n),
+                           "cells_total": n_cells_total, "counts": counts,
+                           "l2_policy": "inputs larger than L2 (%.1f GB streamed per step)"
+                                        % (ab["total"] / 1e9),
+                           "partition": "1 slab of the global box per rank, owned CSR rows, NCCL halo "
+                                        "exchange" if world > 1 else "single GPU",
+                           "timed": "tag kernels + zeroing + assembly kernels; symbolic phase excluded"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+                "gpu_launches": 5 * args.steps, "symbolic_ms": symbolic_ms, "topology_s": topo_s}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--n", type=int, default=204, help="cubes per edge (6 n^3 tetrahedra per GPU)")
+    ap.add_argument("--cpu-n", type=int, default=80, help="size of the bounded CPU sample")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

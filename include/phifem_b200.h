@@ -1,0 +1,149 @@
+/*
+ * phifem_b200 -- C ABI of the B200-native phi-FEM hot path.
+ *
+ * The reference (PhiFEM/phiFEM) is pure Python on top of dolfinx; it has NO native FFI for this
+ * path.  The functions below are the device-side replacements of the Python/dolfinx calls named in
+ * each comment (paths relative to the reference tree).  INTEGRATION.md shows the ctypes binding a
+ * maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - every `const T*` / `T*` is a DEVICE pointer unless the comment says HOST;
+ *   - indices are int32, values fp64, row-major arrays;
+ *   - the last argument is the CUDA stream (cudaStream_t passed as void*); calls are asynchronous;
+ *   - return value: 0 on success, negative `phifem_status` otherwise; `phifem_last_error()` returns
+ *     a thread-local message for the last failure on the calling thread.
+ */
+#ifndef PHIFEM_B200_H
+#define PHIFEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHIFEM_B200_ABI_VERSION 1
+
+typedef enum phifem_status {
+  PHIFEM_OK = 0,
+  PHIFEM_ERR_ARGUMENT = -1,    /* bad argument (null pointer, unsupported size) */
+  PHIFEM_ERR_CUDA = -2,        /* CUDA runtime error, see phifem_last_error() */
+  PHIFEM_ERR_UNSUPPORTED = -3  /* cell type / degree outside the implemented path */
+} phifem_status;
+
+typedef enum phifem_cell_type {
+  PHIFEM_TRIANGLE = 0,
+  PHIFEM_QUADRILATERAL = 1,
+  PHIFEM_TETRAHEDRON = 2
+} phifem_cell_type;
+
+/* Mesh arrays resident in HBM (what a dolfinx `Mesh` + its topology connectivities hold;
+ * src/phifem/mesh_scripts.py:151-153,308-315,419-422). */
+typedef struct phifem_mesh {
+  int32_t cell_type;      /* phifem_cell_type */
+  int32_t gdim;           /* 2 or 3 */
+  int64_t n_vertices;
+  int64_t n_cells;
+  int64_t n_facets;
+  const double* x;        /* [n_vertices, gdim] */
+  const int32_t* cells;   /* [n_cells, nvpc] cell -> vertex, dolfinx local order */
+  const int32_t* c2f;     /* [n_cells, nfpc] cell -> facet (local facet i opposite vertex i) */
+  const int32_t* f2c;     /* [n_facets, 2]   facet -> cells ascending, -1 pad */
+  double detj_min;        /* optional bounds of |det J| over the mesh (0,0 = unknown): */
+  double detj_max;        /* lets the P1 classifier skip the coordinate gather on uncut cells */
+} phifem_mesh;
+
+/* Discrete level set as seen by the detection forms (src/phifem/mesh_scripts.py:95-134).
+ * mode 0: P_k coefficients + dofmap + basis tabulated at the detection points;
+ * mode 1: values already evaluated at the detection points (UFL-expression mode of
+ *         tests/test_compute_meshtags.py:160-161). */
+typedef struct phifem_levelset {
+  int32_t mode;
+  int32_t n_dofs_per_cell;      /* nd (mode 0) */
+  int32_t n_cell_points;        /* npts */
+  int32_t n_facet_points;       /* nq */
+  const double* coeffs;         /* [n_dofs]              (mode 0) */
+  const int32_t* dofmap;        /* [n_cells, nd]; NULL => mesh.cells (P1)   (mode 0) */
+  const double* cell_table;     /* [npts, nd] basis at the cell detection points   (mode 0) */
+  const double* facet_table;    /* [nfpc, nq, nd] basis at the facet detection points (mode 0) */
+  const double* cell_values;    /* [n_cells, npts]       (mode 1) */
+  const double* facet_values;   /* [n_cells, nfpc, nq]   (mode 1) */
+  const double* coord_grad;     /* [npts, 4, 2] reference gradients of the Q1 coordinate element at
+                                   the cell detection points (quadrilaterals only) */
+} phifem_levelset;
+
+/* Slots of the int64 counter block written by the tag kernels. */
+enum {
+  PHIFEM_CNT_INTERIOR = 0,     /* cells tagged 1 */
+  PHIFEM_CNT_CUT = 1,          /* cells tagged 2 */
+  PHIFEM_CNT_EXTERIOR = 2,     /* cells tagged 3 */
+  PHIFEM_CNT_UNTAGGED = 3,     /* cells with NaN ratio */
+  PHIFEM_CNT_ZERO_DEN = 4,     /* cells whose dx-denominator is ~0 (RuntimeWarning, :129-133) */
+  PHIFEM_CNT_FACET_TAG1 = 5,   /* ... 5..10: facets tagged 1..6 */
+  PHIFEM_CNT_FACET_ZERO_DEN = 11, /* cells whose ds-denominator is ~0 */
+  PHIFEM_CNT_FACET_CONFLICT = 12, /* facets the reference algebra would emit twice */
+  PHIFEM_CNT_BOUNDARY_OWNERS = 13, /* cells owning at least one mesh-boundary facet */
+  PHIFEM_N_COUNTERS = 16
+};
+
+const char* phifem_last_error(void);
+int phifem_abi_version(void);
+
+/* Physical coordinates of reference points in every cell: out[n_cells, n_points, gdim].
+ * `shape` [n_points, nvpc] = coordinate-element basis at the points.  Used to evaluate an
+ * expression level set where the reference evaluates a UFL expression of SpatialCoordinate. */
+int phifem_cell_points(const phifem_mesh* mesh, const double* shape, int32_t n_points,
+                       double* out, void* stream);
+
+/* Replaces `_compute_detection_vector` (:95-134) + `_tag_cells` (:284-390) for the `dx` detection
+ * measure: cell_tags[n_cells] in {1 interior, 2 cut, 3 exterior, 0 untagged}; cell_tags8 is the
+ * same as int8 (consumed by the facet / assembly kernels).  `counters` (int64[PHIFEM_N_COUNTERS])
+ * must be zeroed by the caller; slots 0..4 are accumulated.  single_layer_cut != 0 applies
+ * :349-358 and needs `vertex_scratch` (uint8[n_vertices], any content). */
+int phifem_tag_cells(const phifem_mesh* mesh, const phifem_levelset* ls, int32_t single_layer_cut,
+                     int32_t* cell_tags, int8_t* cell_tags8, uint8_t* vertex_scratch,
+                     int64_t* counters, void* stream);
+
+/* Replaces `_tag_facets` (:393-558) including its `ds` detection pass (:434-452):
+ * facet_tags[n_facets] in 1..6.  Reads counters[PHIFEM_CNT_EXTERIOR] on the device (the "no exterior
+ * cell" branch :469-470), accumulates slots 5..13. */
+int phifem_tag_facets(const phifem_mesh* mesh, const phifem_levelset* ls, const int8_t* cell_tags8,
+                      int32_t* facet_tags, int8_t* facet_tags8, int64_t* counters, void* stream);
+
+/* Candidate records of `_compute_integration_entities` (:137-192): for every facet with
+ * facet_tags == facet_tag and every adjacent cell whose tag bit is set in cell_mask
+ * (bit t set => cells tagged t allowed), append (key = 2*facet + column, cell, local facet) to
+ * records[capacity, 3] (int64) in unspecified order; *n_records counts all candidates (may exceed
+ * capacity => caller retries).  Column = position of the cell in the reversed facet->cell list. */
+int phifem_entity_records(const phifem_mesh* mesh, const int8_t* cell_tags8,
+                          const int8_t* facet_tags8, int32_t facet_tag, uint32_t cell_mask,
+                          int64_t* records, int64_t capacity, int64_t* n_records, void* stream);
+
+/* ---- strong-Dirichlet phi-FEM operator, P1 on triangles / tetrahedra --------------------------
+ * Forms: demo/strong-dirichlet/flower/main.py:104-128.  dof = vertex.  `data` (CSR values) and `b`
+ * must be zeroed by the caller; contributions are ADDED (PETSc ADD_VALUES semantics, :121-123). */
+
+/* dx((1,2)) stiffness + dx(2) stabilisation (:105,107-112) and the load vector (:126-128).
+ * active[n_active] = cells tagged 1 or 2; slots[n_active, nv*nv] = CSR position of entry
+ * (row = local test vertex i, col = local trial vertex j) at slots[e*nv*nv + i*nv + j]. */
+int phifem_assemble_cells_p1(const phifem_mesh* mesh, const double* phi, const double* f,
+                             const int8_t* cell_tags8, const int32_t* active, int64_t n_active,
+                             const int32_t* slots, double sigma, double* data, double* b,
+                             void* stream);
+
+/* -int_{ds(100)} (grad(phi w).n) phi v (:106): entities[n_entities, 2] = (cell, local facet),
+ * slots[n_entities, nv*nv]. */
+int phifem_assemble_boundary_p1(const phifem_mesh* mesh, const double* phi, const int32_t* entities,
+                                int64_t n_entities, const int32_t* slots, double* data,
+                                void* stream);
+
+/* sigma avg(h_T) jump.jump over dS((2,3)) (:113-118): facets[n_facets] interior facets tagged 2/3,
+ * slots[n_facets, (2nv)^2] over macro dofs [cell+ vertices, cell- vertices], cell+ = f2c[f][0]. */
+int phifem_assemble_ghost_p1(const phifem_mesh* mesh, const double* phi, const int32_t* facets,
+                             int64_t n_facets, const int32_t* slots, double sigma, double* data,
+                             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHIFEM_B200_H */

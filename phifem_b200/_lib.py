@@ -1,0 +1,117 @@
+"""ctypes binding of libphifem_b200.so (the C ABI declared in include/phifem_b200.h).
+
+There is no fallback: if the shared library is missing or no CUDA device is present the hot
+path raises.  Build the library with `python -m phifem_b200.build` (or `__graft_entry__.build()`).
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libphifem_b200.so")
+
+CELL_TYPE_ID = {"triangle": 0, "quadrilateral": 1, "tetrahedron": 2}
+N_COUNTERS = 16
+CNT_INTERIOR, CNT_CUT, CNT_EXTERIOR, CNT_UNTAGGED, CNT_ZERO_DEN = 0, 1, 2, 3, 4
+CNT_FACET_TAG1 = 5
+CNT_FACET_ZERO_DEN, CNT_FACET_CONFLICT, CNT_BOUNDARY_OWNERS = 11, 12, 13
+
+_vp = ctypes.c_void_p
+
+
+class CMesh(ctypes.Structure):
+    _fields_ = [("cell_type", ctypes.c_int32), ("gdim", ctypes.c_int32),
+                ("n_vertices", ctypes.c_int64), ("n_cells", ctypes.c_int64),
+                ("n_facets", ctypes.c_int64),
+                ("x", _vp), ("cells", _vp), ("c2f", _vp), ("f2c", _vp),
+                ("detj_min", ctypes.c_double), ("detj_max", ctypes.c_double)]
+
+
+class CLevelset(ctypes.Structure):
+    _fields_ = [("mode", ctypes.c_int32), ("n_dofs_per_cell", ctypes.c_int32),
+                ("n_cell_points", ctypes.c_int32), ("n_facet_points", ctypes.c_int32),
+                ("coeffs", _vp), ("dofmap", _vp), ("cell_table", _vp), ("facet_table", _vp),
+                ("cell_values", _vp), ("facet_values", _vp), ("coord_grad", _vp)]
+
+
+_SIGNATURES = {
+    "phifem_last_error": (ctypes.c_char_p, []),
+    "phifem_abi_version": (ctypes.c_int, []),
+    "phifem_cell_points": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, ctypes.c_int32, _vp, _vp]),
+    "phifem_tag_cells": (ctypes.c_int, [ctypes.POINTER(CMesh), ctypes.POINTER(CLevelset),
+                                        ctypes.c_int32, _vp, _vp, _vp, _vp, _vp]),
+    "phifem_tag_facets": (ctypes.c_int, [ctypes.POINTER(CMesh), ctypes.POINTER(CLevelset), _vp, _vp,
+                                         _vp, _vp, _vp]),
+    "phifem_entity_records": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, ctypes.c_int32,
+                                             ctypes.c_uint32, _vp, ctypes.c_int64, _vp, _vp]),
+    "phifem_assemble_cells_p1": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, _vp, _vp,
+                                                ctypes.c_int64, _vp, ctypes.c_double, _vp, _vp, _vp]),
+    "phifem_assemble_boundary_p1": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, ctypes.c_int64,
+                                                   _vp, _vp, _vp]),
+    "phifem_assemble_ghost_p1": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, ctypes.c_int64, _vp,
+                                                ctypes.c_double, _vp, _vp]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load():
+    """dlopen the C-ABI library (no GPU needed for this step)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "phifem_b200: %s is missing -- build it with `python -m phifem_b200.build`; "
+                "there is no CPU fallback for the hot path" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        if lib.phifem_abi_version() != 1:
+            raise RuntimeError("phifem_b200: ABI version mismatch")
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().phifem_last_error().decode()
+        if rc == -3:
+            raise NotImplementedError(msg)
+        if rc == -1:
+            raise ValueError(msg)
+        raise RuntimeError("phifem_b200 (%d): %s" % (rc, msg))
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("phifem_b200: expected a CUDA tensor; the hot path has no CPU fallback")
+    if not t.is_contiguous():
+        raise ValueError("phifem_b200: tensor must be contiguous")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(mesh):
+    if mesh.device.type != "cuda":
+        raise RuntimeError(
+            "phifem_b200: the mesh lives on '%s'; cut-cell classification and assembly run on a CUDA "
+            "device only (no CPU fallback)" % mesh.device)
+    load()
+
+
+def c_mesh(mesh, with_facets=True):
+    require_cuda(mesh)
+    lo, hi = mesh.detj_bounds() if mesh.cell_type != "quadrilateral" else (0.0, 0.0)
+    return CMesh(CELL_TYPE_ID[mesh.cell_type], mesh.gdim, mesh.num_vertices, mesh.num_cells,
+                 mesh.num_facets if with_facets else 0, ptr(mesh.x), ptr(mesh.cells),
+                 ptr(mesh.c2f) if with_facets else None, ptr(mesh.f2c) if with_facets else None,
+                 lo, hi)

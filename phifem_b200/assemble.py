@@ -1,0 +1,148 @@
+"""Assembly of the strong-Dirichlet phi-FEM operator into CSR on the GPU.
+
+What the reference demo does with UFL + `dolfinx.fem.petsc.assemble_matrix / assemble_vector`
+(reference demo/strong-dirichlet/flower/main.py:92-131), for P1 on triangles and tetrahedra:
+
+    plan = build_plan(mesh, cells_tags, facets_tags, ds_bdy(100))          # symbolic, per tag set
+    A, b = assemble_strong_dirichlet(plan, phi_h, f_h, stab_coef=1.0)      # numeric, hot path
+
+Symbolic phase (sort/unique plumbing, torch ops on the device): CSR pattern = union over the
+integral domains -- all vertex pairs of every cell tagged 1/2, all pairs among the two cells of
+every interior facet tagged 2/3 -- with structural zeros kept and rows without contributions
+empty (dolfinx create_sparsity_pattern [dep-knowledge, SURVEY.md C.3]); plus the entity ->
+CSR-slot maps the kernels scatter through.  Numeric phase: three hand-written kernels
+(csrc/assemble.cu) adding into zeroed `data` / `b`.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .fem import Function
+
+
+class CSRMatrix:
+    """Assembled operator: `indptr` int32 [n+1], `indices` int32 [nnz], `data` float64 [nnz] on the
+    device; `.to_scipy()` copies to the host."""
+
+    def __init__(self, indptr, indices, data, shape):
+        self.indptr, self.indices, self.data, self.shape = indptr, indices, data, shape
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.data.cpu().numpy(), self.indices.cpu().numpy(),
+                              self.indptr.cpu().numpy()), shape=self.shape)
+
+
+class AssemblyPlan:
+    """Tag-dependent symbolic data of one operator (reused for every assembly with the same tags)."""
+
+    def __init__(self, mesh, cell_tags8, facet_tags8, entities):
+        if mesh.cell_type not in ("triangle", "tetrahedron"):
+            raise NotImplementedError("P1 assembly supports triangles and tetrahedra")
+        dev = mesh.device
+        self.mesh = mesh
+        self.cell_tags8 = cell_tags8
+        n = mesh.num_vertices
+        nv = mesh.cells.shape[1]
+        self.n_rows = n
+        self.active = torch.nonzero((cell_tags8 == 1) | (cell_tags8 == 2)).reshape(-1).to(torch.int32)
+        interior = mesh.f2c[:, 1] >= 0
+        self.ghost = torch.nonzero(((facet_tags8 == 2) | (facet_tags8 == 3)) & interior) \
+            .reshape(-1).to(torch.int32)
+        self.entities = entities.reshape(-1, 2).to(torch.int32).contiguous()
+
+        def pair_keys(dm):  # [m, k] dofs -> [m, k*k] keys row*n+col, row-major (row = test)
+            return (dm[:, :, None] * n + dm[:, None, :]).reshape(dm.shape[0], -1)
+
+        dm = mesh.cells[self.active.long()].long()
+        keys_c = pair_keys(dm)
+        g = self.ghost.long()
+        mac = torch.cat([mesh.cells[mesh.f2c[g, 0].long()], mesh.cells[mesh.f2c[g, 1].long()]], dim=1).long()
+        keys_g = pair_keys(mac)
+        n_c = keys_c.numel()
+        uniq, inv = torch.unique(torch.cat([keys_c.reshape(-1), keys_g.reshape(-1)]), sorted=True,
+                                 return_inverse=True)
+        del keys_c, keys_g
+        self.slots_cells = inv[:n_c].reshape(-1, nv * nv).to(torch.int32).contiguous()
+        self.slots_ghost = inv[n_c:].reshape(-1, 4 * nv * nv).to(torch.int32).contiguous()
+        del inv
+        keys_b = pair_keys(mesh.cells[self.entities[:, 0].long()].long())
+        self.slots_boundary = torch.searchsorted(uniq, keys_b.reshape(-1)).reshape(-1, nv * nv) \
+            .to(torch.int32).contiguous()
+        rows = uniq // n
+        self.indices = (uniq - rows * n).to(torch.int32).contiguous()
+        counts = torch.bincount(rows, minlength=n)
+        self.indptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        self.indptr[1:] = torch.cumsum(counts, dim=0)
+        self.indptr = self.indptr.to(torch.int32).contiguous()
+        self.nnz = int(uniq.numel())
+
+    def new_outputs(self):
+        dev = self.mesh.device
+        return (torch.zeros(self.nnz, dtype=torch.float64, device=dev),
+                torch.zeros(self.n_rows, dtype=torch.float64, device=dev))
+
+
+def build_plan(mesh, cells_tags, facets_tags, ds=None):
+    """Symbolic phase for `a` and `L` of the strong-Dirichlet demo.  `ds` is what the demo passes as
+    `ds_bdy(100)` (main.py:64): a MeasureRestriction, a flat entity array, or None (no boundary term)."""
+    c8 = getattr(cells_tags, "tags8", None)
+    c8 = c8 if c8 is not None else cells_tags.values_dev.to(torch.int8)
+    f8 = getattr(facets_tags, "tags8", None)
+    f8 = f8 if f8 is not None else facets_tags.values_dev.to(torch.int8)
+    if ds is None:
+        ents = torch.zeros(0, dtype=torch.int32, device=mesh.device)
+    elif hasattr(ds, "integration_entities_dev"):
+        ents = ds.integration_entities_dev
+    else:
+        ents = torch.as_tensor(np.asarray(ds, dtype=np.int32), device=mesh.device)
+    return AssemblyPlan(mesh, c8.contiguous(), f8.contiguous(), ents)
+
+
+def _device_vector(mesh, v):
+    if isinstance(v, Function):
+        if v.function_space.degree != 1:
+            raise NotImplementedError("the CUDA assembly path implements P1 (vertex dofs)")
+        v = v.x.array
+    t = v if torch.is_tensor(v) else torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64))
+    t = t.to(mesh.device, dtype=torch.float64, non_blocking=True).contiguous()
+    if t.numel() != mesh.num_vertices:
+        raise ValueError("expected one value per vertex")
+    return t
+
+
+def assemble_into(plan, phi, f, sigma, data, b, marks=None):
+    """Numeric phase on the current stream: zero `data`/`b`, run the cell, boundary and ghost-penalty
+    kernels.  All arguments are device tensors; nothing synchronises.  `marks` (optional callable) is
+    invoked after the zeroing and after each kernel (bench.py records CUDA events there)."""
+    marks = marks or (lambda: None)
+    _lib.require_cuda(plan.mesh)
+    lib = _lib.load()
+    cm = _lib.c_mesh(plan.mesh)
+    st = _lib.stream()
+    data.zero_()
+    b.zero_()
+    marks()
+    _lib.check(lib.phifem_assemble_cells_p1(
+        cm, _lib.ptr(phi), _lib.ptr(f), _lib.ptr(plan.cell_tags8), _lib.ptr(plan.active),
+        plan.active.numel(), _lib.ptr(plan.slots_cells), float(sigma), _lib.ptr(data), _lib.ptr(b), st))
+    marks()
+    _lib.check(lib.phifem_assemble_boundary_p1(
+        cm, _lib.ptr(phi), _lib.ptr(plan.entities), plan.entities.shape[0],
+        _lib.ptr(plan.slots_boundary), _lib.ptr(data), st))
+    marks()
+    _lib.check(lib.phifem_assemble_ghost_p1(
+        cm, _lib.ptr(phi), _lib.ptr(plan.ghost), plan.ghost.numel(), _lib.ptr(plan.slots_ghost),
+        float(sigma), _lib.ptr(data), st))
+    marks()
+    return data, b
+
+
+def assemble_strong_dirichlet(plan, phi_h, f_h, stab_coef=1.0):
+    """A (CSR) and b of reference demo/strong-dirichlet/flower/main.py:104-131."""
+    mesh = plan.mesh
+    phi = _device_vector(mesh, phi_h)
+    f = _device_vector(mesh, f_h)
+    data, b = plan.new_outputs()
+    assemble_into(plan, phi, f, stab_coef, data, b)
+    return CSRMatrix(plan.indptr, plan.indices, data, (plan.n_rows, plan.n_rows)), b

@@ -1,0 +1,64 @@
+// Shared device/host helpers of the phifem_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/phifem_b200.h"
+
+namespace phifem {
+
+void set_error(const char* fmt, ...);
+
+#define PHIFEM_CHECK_ARG(cond, msg)                         \
+  do {                                                      \
+    if (!(cond)) {                                          \
+      ::phifem::set_error("%s: %s", __func__, msg);         \
+      return PHIFEM_ERR_ARGUMENT;                           \
+    }                                                       \
+  } while (0)
+
+#define PHIFEM_CHECK_LAUNCH()                                                         \
+  do {                                                                                \
+    cudaError_t err__ = cudaGetLastError();                                           \
+    if (err__ != cudaSuccess) {                                                       \
+      ::phifem::set_error("%s: CUDA error: %s", __func__, cudaGetErrorString(err__)); \
+      return PHIFEM_ERR_CUDA;                                                         \
+    }                                                                                 \
+  } while (0)
+
+// Reference-cell traits (dolfinx conventions): simplex local facet i is opposite
+// local vertex i, its vertices listed in ascending local order; quadrilateral facets in tensor order.
+template <int CT> struct CellTraits;
+template <> struct CellTraits<PHIFEM_TRIANGLE> {
+  static constexpr int nv = 3, nf = 3, nvf = 2, gdim = 2;
+  __host__ __device__ static constexpr int fv(int f, int k) {
+    constexpr int t[3][2] = {{1, 2}, {0, 2}, {0, 1}};
+    return t[f][k];
+  }
+};
+template <> struct CellTraits<PHIFEM_QUADRILATERAL> {
+  static constexpr int nv = 4, nf = 4, nvf = 2, gdim = 2;
+  __host__ __device__ static constexpr int fv(int f, int k) {
+    constexpr int t[4][2] = {{0, 1}, {0, 2}, {1, 3}, {2, 3}};
+    return t[f][k];
+  }
+};
+template <> struct CellTraits<PHIFEM_TETRAHEDRON> {
+  static constexpr int nv = 4, nf = 4, nvf = 3, gdim = 3;
+  __host__ __device__ static constexpr int fv(int f, int k) {
+    constexpr int t[4][3] = {{1, 2, 3}, {0, 2, 3}, {0, 1, 3}, {0, 1, 2}};
+    return t[f][k];
+  }
+};
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+inline int grid_for(int64_t n, int block, int ctas_per_sm) {
+  int64_t need = (n + block - 1) / block;
+  int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+}  // namespace phifem

@@ -1,0 +1,577 @@
+// K1: level-set cut-cell classification on sm_100a.
+//
+// Replaces reference src/phifem/mesh_scripts.py `_compute_detection_vector` (:95-134),
+// `_tag_cells` (:284-390), `_tag_facets` (:393-558) and the candidate search of
+// `_compute_integration_entities` (:137-192).
+//
+// Bit-exactness: the detection ratio is compared with ==1.0 / ==-1.0 in the reference
+// (:343-347), so this file restates the FFCx arithmetic literally -- sequential sums of
+// fl(phi_q * |detJ|), no FMA contraction (the file is compiled with -fmad=false), IEEE
+// division and sqrt.  Everything here is HBM/L2-bound integer + fp64 streaming work: one
+// thread per cell / facet, coalesced index loads, gathers that hit L2, warp-ballot counters.
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace phifem {
+namespace {
+
+constexpr int kMaxDofs = 20;  // P3 tetrahedron
+constexpr int kBlock = 256;
+
+__device__ __forceinline__ double seq_dot(const double* __restrict__ w, int wstride,
+                                          const double* v, int vstride, int n) {
+  // sum_k w[k] v[k], left to right, exact-zero weights skipped, unit weights not multiplied
+  double acc = 0.0;
+  bool first = true;
+  for (int k = 0; k < n; ++k) {
+    const double wk = __ldg(w + k * wstride);
+    if (wk == 0.0) continue;
+    const double term = (wk == 1.0) ? v[k * vstride] : wk * v[k * vstride];
+    acc = first ? term : acc + term;
+    first = false;
+  }
+  return acc;
+}
+
+__device__ __forceinline__ int classify(double num, double den) {
+  // mesh_scripts.py:124-128 then :343-347
+  const double d = (den > 0.0) ? num / den : 0.5;
+  if (d > -1.0 && d < 1.0) return 2;
+  if (d == 1.0) return 3;
+  if (d == -1.0) return 1;
+  return 0;
+}
+
+__device__ __forceinline__ bool is_close_to_zero(double den) { return fabs(den) <= 1e-8; }
+
+template <int CT>
+__device__ __forceinline__ void load_cell(const phifem_mesh& m, int64_t c, int (&v)[4],
+                                          double (&xc)[4][3]) {
+  using T = CellTraits<CT>;
+#pragma unroll
+  for (int k = 0; k < T::nv; ++k) v[k] = __ldg(m.cells + c * T::nv + k);
+#pragma unroll
+  for (int k = 0; k < T::nv; ++k)
+#pragma unroll
+    for (int d = 0; d < T::gdim; ++d) xc[k][d] = __ldg(m.x + (int64_t)v[k] * T::gdim + d);
+}
+
+// |det J| of a simplex, same operation order as oracle/tags.py cell_scale
+template <int CT>
+__device__ __forceinline__ double simplex_detj(const double (&xc)[4][3]) {
+  if (CT == PHIFEM_TRIANGLE) {
+    const double j00 = xc[1][0] - xc[0][0], j01 = xc[2][0] - xc[0][0];
+    const double j10 = xc[1][1] - xc[0][1], j11 = xc[2][1] - xc[0][1];
+    return fabs(j00 * j11 - j01 * j10);
+  } else {
+    double a[3], b[3], c[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      a[d] = xc[1][d] - xc[0][d];
+      b[d] = xc[2][d] - xc[0][d];
+      c[d] = xc[3][d] - xc[0][d];
+    }
+    const double det = (a[0] * (b[1] * c[2] - c[1] * b[2]) - b[0] * (a[1] * c[2] - c[1] * a[2])) +
+                       c[0] * (a[1] * b[2] - b[1] * a[2]);
+    return fabs(det);
+  }
+}
+
+// facet integral scale: edge length (2D) or |e1 x e2| (3D); oracle/tags.py facet_scale
+template <int CT>
+__device__ __forceinline__ double facet_scale(const double (&xc)[4][3], int lf) {
+  using T = CellTraits<CT>;
+  int a = 0, b = 0, c = 0;
+#pragma unroll
+  for (int f = 0; f < T::nf; ++f)
+    if (f == lf) {
+      a = T::fv(f, 0);
+      b = T::fv(f, 1);
+      c = T::nvf == 3 ? T::fv(f, T::nvf - 1) : 0;
+    }
+  if constexpr (T::nvf == 2) {
+    const double d0 = xc[b][0] - xc[a][0], d1 = xc[b][1] - xc[a][1];
+    return sqrt(d0 * d0 + d1 * d1);
+  } else {
+    double e1[3], e2[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      e1[d] = xc[b][d] - xc[a][d];
+      e2[d] = xc[c][d] - xc[a][d];
+    }
+    const double cx = e1[1] * e2[2] - e1[2] * e2[1];
+    const double cy = e1[2] * e2[0] - e1[0] * e2[2];
+    const double cz = e1[0] * e2[1] - e1[1] * e2[0];
+    return sqrt((cx * cx + cy * cy) + cz * cz);
+  }
+}
+
+__device__ __forceinline__ void load_coeffs(const phifem_mesh& m, const phifem_levelset& ls, int nvpc,
+                                            int64_t c, const int (&v)[4], double* cd) {
+  const int nd = ls.n_dofs_per_cell;
+  if (ls.dofmap == nullptr) {
+    for (int i = 0; i < nvpc; ++i) cd[i] = __ldg(ls.coeffs + v[i]);
+  } else {
+    for (int i = 0; i < nd; ++i) cd[i] = __ldg(ls.coeffs + __ldg(ls.dofmap + c * nd + i));
+  }
+}
+
+// ---- block-level tag counters (warp ballot -> shared -> one global atomic per block) --------
+struct BlockCounters {
+  unsigned int* s;
+  __device__ BlockCounters(unsigned int* smem, int n) : s(smem) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s[i] = 0u;
+    __syncthreads();
+  }
+  __device__ __forceinline__ void vote(bool pred, int slot) {
+    const unsigned int b = __ballot_sync(0xffffffffu, pred);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&s[slot], __popc(b));
+  }
+  __device__ void flush(int64_t* counters, int base, int n) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      if (s[i]) atomicAdd(reinterpret_cast<unsigned long long*>(counters + base + i),
+                          (unsigned long long)s[i]);
+  }
+};
+
+// ---- K1a: P1 level set, detection degree 1, simplices: the headline kernel ------------------
+// Per cell: 4 (3) vertex ids (coalesced 16 B / 12 B), 4 (3) fp64 gathers of phi (L2-resident:
+// 8 B x Nv), and -- only where the sign test cannot decide -- the vertex coordinates for |det J|.
+// Uncut cells whose products phi*|detJ| can neither vanish, overflow nor land near the
+// RuntimeWarning threshold are decided from the signs alone, which is bit-identical to the
+// sequential sum (all terms share a sign => num == +-den exactly).
+template <int CT>
+__global__ void __launch_bounds__(kBlock) k_tag_cells_p1(phifem_mesh m, const double* __restrict__ phi,
+                                                         bool have_bounds, int32_t* __restrict__ tags,
+                                                         int8_t* __restrict__ tags8,
+                                                         int64_t* counters) {
+  using T = CellTraits<CT>;
+  __shared__ unsigned int scnt[5];
+  BlockCounters cnt(scnt, 5);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < m.n_cells; base += stride) {
+    const int64_t c = base + threadIdx.x;
+    const bool valid = c < m.n_cells;
+    int tag = -1;
+    bool zden = false;
+    if (valid) {
+      int v[4];
+      if (T::nv == 4) {
+        const int4 q = __ldg(reinterpret_cast<const int4*>(m.cells) + c);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < T::nv; ++k) v[k] = __ldg(m.cells + c * T::nv + k);
+      }
+      double p[4];
+#pragma unroll
+      for (int k = 0; k < T::nv; ++k) p[k] = __ldg(phi + v[k]);
+      bool allpos = true, allneg = true, sane = true;
+      double sumabs = 0.0;
+#pragma unroll
+      for (int k = 0; k < T::nv; ++k) {
+        allpos &= p[k] > 0.0;
+        allneg &= p[k] < 0.0;
+        const double ap = fabs(p[k]);
+        sane &= (ap >= 1e-150) & (ap <= 1e150);
+        sumabs += ap;
+      }
+      bool fast = have_bounds && sane && (allpos || allneg);
+      if (fast) {
+        // den = sum |p| s lies in [sumabs*detj_min, sumabs*detj_max] up to rounding: decide the
+        // isclose(den, 0) flag (atol 1e-8, mesh_scripts.py:129) only when it is unambiguous
+        if (sumabs * m.detj_min > 2e-8) zden = false;
+        else if (sumabs * m.detj_max < 0.5e-8) zden = true;
+        else fast = false;
+      }
+      if (fast) {
+        tag = allpos ? 3 : 1;
+      } else {
+        double xc[4][3];
+#pragma unroll
+        for (int k = 0; k < T::nv; ++k)
+#pragma unroll
+          for (int d = 0; d < T::gdim; ++d) xc[k][d] = __ldg(m.x + (int64_t)v[k] * T::gdim + d);
+        const double s = simplex_detj<CT>(xc);
+        double num = 0.0, den = 0.0;
+#pragma unroll
+        for (int k = 0; k < T::nv; ++k) {
+          const double t = p[k] * s;
+          num = num + t;
+          den = den + fabs(t);
+        }
+        tag = classify(num, den);
+        zden = is_close_to_zero(den);
+      }
+      tags[c] = tag;
+      tags8[c] = (int8_t)tag;
+    }
+    cnt.vote(tag == 1, 0);
+    cnt.vote(tag == 2, 1);
+    cnt.vote(tag == 3, 2);
+    cnt.vote(tag == 0, 3);
+    cnt.vote(zden, 4);
+  }
+  cnt.flush(counters, PHIFEM_CNT_INTERIOR, 5);
+}
+
+// ---- K1b: generic table-driven cell classification (P1..P3 / Q1..Q3, any detection degree) ----
+template <int CT>
+__global__ void __launch_bounds__(kBlock) k_tag_cells_generic(phifem_mesh m, phifem_levelset ls,
+                                                              int32_t* __restrict__ tags,
+                                                              int8_t* __restrict__ tags8,
+                                                              int64_t* counters) {
+  using T = CellTraits<CT>;
+  __shared__ unsigned int scnt[5];
+  BlockCounters cnt(scnt, 5);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int npts = ls.n_cell_points, nd = ls.n_dofs_per_cell;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < m.n_cells; base += stride) {
+    const int64_t c = base + threadIdx.x;
+    int tag = -1;
+    bool zden = false;
+    if (c < m.n_cells) {
+      int v[4];
+      double xc[4][3];
+      load_cell<CT>(m, c, v, xc);
+      double cd[kMaxDofs];
+      if (ls.mode == 0) load_coeffs(m, ls, T::nv, c, v, cd);
+      double s = 0.0;
+      if (CT != PHIFEM_QUADRILATERAL) s = simplex_detj<CT>(xc);
+      double num = 0.0, den = 0.0;
+      for (int q = 0; q < npts; ++q) {
+        if (CT == PHIFEM_QUADRILATERAL) {
+          const double* g = ls.coord_grad + q * 8;  // [4 vertices][2]
+          const double j00 = seq_dot(g + 0, 2, &xc[0][0], 3, 4);
+          const double j01 = seq_dot(g + 1, 2, &xc[0][0], 3, 4);
+          const double j10 = seq_dot(g + 0, 2, &xc[0][1], 3, 4);
+          const double j11 = seq_dot(g + 1, 2, &xc[0][1], 3, 4);
+          s = fabs(j00 * j11 - j01 * j10);
+        }
+        const double ph = ls.mode == 0 ? seq_dot(ls.cell_table + q * nd, 1, cd, 1, nd)
+                                       : __ldg(ls.cell_values + c * npts + q);
+        const double t = ph * s;
+        num = num + t;
+        den = den + fabs(t);
+      }
+      tag = classify(num, den);
+      zden = is_close_to_zero(den);
+      tags[c] = tag;
+      tags8[c] = (int8_t)tag;
+    }
+    cnt.vote(tag == 1, 0);
+    cnt.vote(tag == 2, 1);
+    cnt.vote(tag == 3, 2);
+    cnt.vote(tag == 0, 3);
+    cnt.vote(zden, 4);
+  }
+  cnt.flush(counters, PHIFEM_CNT_INTERIOR, 5);
+}
+
+// ---- single_layer_cut (mesh_scripts.py:349-358) --------------------------------------------------
+__global__ void k_single_layer_mark(const int32_t* __restrict__ cells, int nv, int64_t n_cells,
+                                    const int8_t* __restrict__ tags8, uint8_t* vflag) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cells || tags8[c] != 1) return;
+  for (int k = 0; k < nv; ++k) vflag[cells[c * nv + k]] = 1;  // benign race: everybody stores 1
+}
+
+__global__ void k_single_layer_apply(const int32_t* __restrict__ cells, int nv, int64_t n_cells,
+                                     int32_t* tags, int8_t* tags8, const uint8_t* __restrict__ vflag,
+                                     int64_t* counters) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cells || tags8[c] != 2) return;
+  bool touches = false;
+  for (int k = 0; k < nv; ++k) touches |= vflag[cells[c * nv + k]] != 0;
+  if (!touches) {  // isolated cut cell -> exterior
+    tags[c] = 3;
+    tags8[c] = 3;
+    atomicAdd(reinterpret_cast<unsigned long long*>(counters + PHIFEM_CNT_EXTERIOR), 1ull);
+    atomicAdd(reinterpret_cast<unsigned long long*>(counters + PHIFEM_CNT_CUT), ~0ull);  // -1
+  }
+}
+
+// ---- K1c: facet tags ------------------------------------------------------------------------------
+// ds-detection of the owner cell of a mesh-boundary facet (mesh_scripts.py:434-452): per exterior
+// facet sum_q phi_q*s_f, added into the cell entry in ascending facet index.
+template <int CT>
+__device__ bool owner_is_ds_cut(const phifem_mesh& m, const phifem_levelset& ls, int64_t c,
+                                int32_t this_facet, bool* first_of_cell, bool* zden) {
+  using T = CellTraits<CT>;
+  int v[4];
+  double xc[4][3];
+  load_cell<CT>(m, c, v, xc);
+  double cd[kMaxDofs];
+  if (ls.mode == 0) load_coeffs(m, ls, T::nv, c, v, cd);
+  int32_t fid[4];
+  bool isb[4];
+  int32_t smallest = INT32_MAX;
+#pragma unroll
+  for (int i = 0; i < T::nf; ++i) {
+    fid[i] = __ldg(m.c2f + c * T::nf + i);
+    isb[i] = __ldg(m.f2c + 2 * (int64_t)fid[i] + 1) < 0;
+    if (isb[i] && fid[i] < smallest) smallest = fid[i];
+  }
+  *first_of_cell = (smallest == this_facet);
+  const int nq = ls.n_facet_points, nd = ls.n_dofs_per_cell;
+  double num = 0.0, den = 0.0;
+  int32_t last = -1;
+  for (int round = 0; round < T::nf; ++round) {
+    int lf = -1;
+    int32_t best = INT32_MAX;
+#pragma unroll
+    for (int i = 0; i < T::nf; ++i)
+      if (isb[i] && fid[i] > last && fid[i] < best) {
+        best = fid[i];
+        lf = i;
+      }
+    if (lf < 0) break;
+    last = best;
+    const double sc = facet_scale<CT>(xc, lf);
+    double fn = 0.0, fd = 0.0;
+    for (int q = 0; q < nq; ++q) {
+      const double ph = ls.mode == 0
+                            ? seq_dot(ls.facet_table + ((int64_t)lf * nq + q) * nd, 1, cd, 1, nd)
+                            : __ldg(ls.facet_values + (c * T::nf + lf) * nq + q);
+      const double t = ph * sc;
+      fn = fn + t;
+      fd = fd + fabs(t);
+    }
+    num = num + fn;
+    den = den + fd;
+  }
+  *zden = is_close_to_zero(den);
+  const double d = (den > 0.0) ? num / den : 0.5;
+  return d > -1.0 && d < 1.0;
+}
+
+template <int CT>
+__global__ void __launch_bounds__(kBlock) k_tag_facets(phifem_mesh m, phifem_levelset ls,
+                                                       const int8_t* __restrict__ ctags,
+                                                       int32_t* __restrict__ ftags,
+                                                       int8_t* __restrict__ ftags8, int64_t* counters) {
+  __shared__ unsigned int scnt[10];
+  BlockCounters cnt(scnt, 10);
+  // "no exterior cell at all" switches the meaning of mesh-boundary facets (:469-474)
+  const bool anyE = *reinterpret_cast<volatile int64_t*>(counters + PHIFEM_CNT_EXTERIOR) > 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < m.n_facets; base += stride) {
+    const int64_t f = base + threadIdx.x;
+    int tag = -1;
+    bool zden = false, owner_first = false, conflict = false;
+    if (f < m.n_facets) {
+      const int2 cc = __ldg(reinterpret_cast<const int2*>(m.f2c) + f);
+      const int t0 = ctags[cc.x];
+      const bool bnd = cc.y < 0;
+      const int t1 = bnd ? 0 : ctags[cc.y];
+      const bool inI = (t0 == 1) | (t1 == 1), inC = (t0 == 2) | (t1 == 2), inE = (t0 == 3) | (t1 == 3);
+      bool k = false;
+      if (bnd) k = owner_is_ds_cut<CT>(m, ls, cc.x, (int32_t)f, &owner_first, &zden);
+      const bool cut_bnd = bnd && k;                                  // :454-456
+      const bool uncut_bnd = bnd && !k && !inE && !inI;               // :457-461
+      const bool int_bnd = inI && inC;                                // :464-466
+      bool boundary = anyE ? ((inE && inC) || uncut_bnd) : bnd;       // :469-474
+      const bool direct = inE && inI;                                 // :476-478
+      const bool cutf = (inC && !(boundary || int_bnd || direct || uncut_bnd)) || cut_bnd;  // :480-485
+      const bool rem = int_bnd || boundary || direct;
+      const bool interior = inI && !rem;                              // :488-490
+      const bool exterior = inE && !rem;                              // :493-495
+      boundary = boundary && !cutf;                                   // :497
+      // stacking order [5,1,3,2,4,6] of :524-552; the last writer wins when the algebra is inconsistent
+      tag = 0;
+      if (exterior) tag = 5;
+      if (interior) tag = 1;
+      if (int_bnd) tag = 3;
+      if (cutf) tag = 2;
+      if (boundary) tag = 4;
+      if (direct) tag = 6;
+      conflict = (int)exterior + (int)interior + (int)int_bnd + (int)cutf + (int)boundary + (int)direct > 1;
+      ftags[f] = tag;
+      ftags8[f] = (int8_t)tag;
+    }
+#pragma unroll
+    for (int t = 1; t <= 6; ++t) cnt.vote(tag == t, t - 1);
+    cnt.vote(owner_first && zden, 6);   // PHIFEM_CNT_FACET_ZERO_DEN
+    cnt.vote(conflict, 7);              // PHIFEM_CNT_FACET_CONFLICT
+    cnt.vote(owner_first, 8);           // slot 13: number of cells owning a mesh-boundary facet
+  }
+  cnt.flush(counters, PHIFEM_CNT_FACET_TAG1, 9);
+}
+
+// ---- candidate records of the one-sided measures (mesh_scripts.py:137-192) -------------------------
+__global__ void k_entity_records(phifem_mesh m, int nf_per_cell, const int8_t* __restrict__ ctags,
+                                 const int8_t* __restrict__ ftags, int facet_tag, unsigned int cell_mask,
+                                 int64_t* records, int64_t capacity, unsigned long long* n_records) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= m.n_facets || ftags[f] != facet_tag) return;
+  const int2 cc = __ldg(reinterpret_cast<const int2*>(m.f2c) + f);
+  // `_reshape_map` (:195-214) lists the cells of a facet in reverse link order
+  const int cell_of_col[2] = {cc.y >= 0 ? cc.y : cc.x, cc.y >= 0 ? cc.x : -1};
+  for (int col = 0; col < 2; ++col) {
+    const int c = cell_of_col[col];
+    if (c < 0) continue;
+    if (!((cell_mask >> ctags[c]) & 1u)) continue;
+    int lf = 0;
+    for (int i = 0; i < nf_per_cell; ++i)
+      if (m.c2f[(int64_t)c * nf_per_cell + i] == (int32_t)f) lf = i;
+    const unsigned long long slot = atomicAdd(n_records, 1ull);
+    if ((int64_t)slot < capacity) {
+      records[3 * slot + 0] = 2 * f + col;
+      records[3 * slot + 1] = c;
+      records[3 * slot + 2] = lf;
+    }
+  }
+}
+
+template <int CT>
+__global__ void k_cell_points(phifem_mesh m, const double* __restrict__ shape, int npts,
+                              double* __restrict__ out) {
+  using T = CellTraits<CT>;
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m.n_cells) return;
+  int v[4];
+  double xc[4][3];
+  load_cell<CT>(m, c, v, xc);
+  for (int q = 0; q < npts; ++q)
+    for (int d = 0; d < T::gdim; ++d)
+      out[(c * npts + q) * T::gdim + d] = seq_dot(shape + q * T::nv, 1, &xc[0][d], 3, T::nv);
+}
+
+template <typename F>
+int dispatch_cell_type(int ct, F&& fn) {
+  switch (ct) {
+    case PHIFEM_TRIANGLE: fn(std::integral_constant<int, PHIFEM_TRIANGLE>()); return 0;
+    case PHIFEM_QUADRILATERAL: fn(std::integral_constant<int, PHIFEM_QUADRILATERAL>()); return 0;
+    case PHIFEM_TETRAHEDRON: fn(std::integral_constant<int, PHIFEM_TETRAHEDRON>()); return 0;
+  }
+  return -1;
+}
+
+int check_mesh(const phifem_mesh* m, bool need_facets) {
+  PHIFEM_CHECK_ARG(m != nullptr, "mesh is null");
+  PHIFEM_CHECK_ARG(m->x && m->cells, "mesh.x / mesh.cells is null");
+  PHIFEM_CHECK_ARG(m->n_cells >= 0 && m->n_vertices >= 0, "negative sizes");
+  PHIFEM_CHECK_ARG(!need_facets || (m->c2f && m->f2c), "mesh.c2f / mesh.f2c is null");
+  const int want = m->cell_type == PHIFEM_TETRAHEDRON ? 3 : 2;
+  if (m->cell_type < 0 || m->cell_type > 2) {
+    set_error("unsupported cell type %d", m->cell_type);
+    return PHIFEM_ERR_UNSUPPORTED;
+  }
+  PHIFEM_CHECK_ARG(m->gdim == want, "gdim does not match the cell type");
+  return PHIFEM_OK;
+}
+
+int check_levelset(const phifem_mesh* m, const phifem_levelset* ls, bool facets) {
+  PHIFEM_CHECK_ARG(ls != nullptr, "levelset is null");
+  if (ls->mode == 0) {
+    PHIFEM_CHECK_ARG(ls->coeffs != nullptr, "levelset.coeffs is null");
+    PHIFEM_CHECK_ARG(ls->n_dofs_per_cell >= 1 && ls->n_dofs_per_cell <= kMaxDofs,
+                     "levelset.n_dofs_per_cell out of range");
+    PHIFEM_CHECK_ARG(facets ? ls->facet_table != nullptr : ls->cell_table != nullptr,
+                     "levelset basis table is null");
+  } else if (ls->mode == 1) {
+    PHIFEM_CHECK_ARG(facets ? ls->facet_values != nullptr : ls->cell_values != nullptr,
+                     "levelset point values are null");
+  } else {
+    PHIFEM_CHECK_ARG(false, "levelset.mode must be 0 or 1");
+  }
+  PHIFEM_CHECK_ARG(facets || m->cell_type != PHIFEM_QUADRILATERAL || ls->coord_grad != nullptr,
+                   "levelset.coord_grad is required for quadrilaterals");
+  return PHIFEM_OK;
+}
+
+}  // namespace
+}  // namespace phifem
+
+using namespace phifem;
+
+extern "C" int phifem_cell_points(const phifem_mesh* mesh, const double* shape, int32_t n_points,
+                                  double* out, void* stream) {
+  if (int rc = check_mesh(mesh, false)) return rc;
+  PHIFEM_CHECK_ARG(shape && out && n_points > 0, "null pointer / no points");
+  if (mesh->n_cells == 0) return PHIFEM_OK;
+  const int grid = (int)((mesh->n_cells + kBlock - 1) / kBlock);
+  dispatch_cell_type(mesh->cell_type, [&](auto ct) {
+    k_cell_points<decltype(ct)::value><<<grid, kBlock, 0, (cudaStream_t)stream>>>(*mesh, shape, n_points, out);
+  });
+  PHIFEM_CHECK_LAUNCH();
+  return PHIFEM_OK;
+}
+
+extern "C" int phifem_tag_cells(const phifem_mesh* mesh, const phifem_levelset* ls,
+                                int32_t single_layer_cut, int32_t* cell_tags, int8_t* cell_tags8,
+                                uint8_t* vertex_scratch, int64_t* counters, void* stream) {
+  if (int rc = check_mesh(mesh, false)) return rc;
+  if (int rc = check_levelset(mesh, ls, false)) return rc;
+  PHIFEM_CHECK_ARG(cell_tags && cell_tags8 && counters, "output pointer is null");
+  PHIFEM_CHECK_ARG(!single_layer_cut || vertex_scratch, "single_layer_cut needs vertex_scratch");
+  if (mesh->n_cells == 0) return PHIFEM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ct = mesh->cell_type;
+  const int nv = ct == PHIFEM_TRIANGLE ? 3 : 4;
+  const bool simplex = ct != PHIFEM_QUADRILATERAL;
+  // P1 fast kernel: vertex dofs, identity table (detection degree 1 puts the points on the vertices)
+  const bool p1 = simplex && ls->mode == 0 && ls->dofmap == nullptr && ls->n_dofs_per_cell == nv &&
+                  ls->n_cell_points == nv && ls->cell_table == nullptr;
+  const int grid = grid_for(mesh->n_cells, kBlock, 8);
+  if (p1) {
+    const bool have_bounds = mesh->detj_min >= 1e-150 && mesh->detj_max <= 1e150 &&
+                             mesh->detj_min <= mesh->detj_max;
+    if (ct == PHIFEM_TRIANGLE)
+      k_tag_cells_p1<PHIFEM_TRIANGLE><<<grid, kBlock, 0, st>>>(*mesh, ls->coeffs, have_bounds, cell_tags,
+                                                              cell_tags8, counters);
+    else
+      k_tag_cells_p1<PHIFEM_TETRAHEDRON><<<grid, kBlock, 0, st>>>(*mesh, ls->coeffs, have_bounds,
+                                                                 cell_tags, cell_tags8, counters);
+  } else {
+    PHIFEM_CHECK_ARG(ls->mode != 0 || ls->cell_table != nullptr, "levelset.cell_table is null");
+    dispatch_cell_type(ct, [&](auto c) {
+      k_tag_cells_generic<decltype(c)::value><<<grid, kBlock, 0, st>>>(*mesh, *ls, cell_tags, cell_tags8,
+                                                                      counters);
+    });
+  }
+  PHIFEM_CHECK_LAUNCH();
+  if (single_layer_cut) {
+    cudaMemsetAsync(vertex_scratch, 0, (size_t)mesh->n_vertices, st);
+    const int g = (int)((mesh->n_cells + kBlock - 1) / kBlock);
+    k_single_layer_mark<<<g, kBlock, 0, st>>>(mesh->cells, nv, mesh->n_cells, cell_tags8, vertex_scratch);
+    k_single_layer_apply<<<g, kBlock, 0, st>>>(mesh->cells, nv, mesh->n_cells, cell_tags, cell_tags8,
+                                               vertex_scratch, counters);
+    PHIFEM_CHECK_LAUNCH();
+  }
+  return PHIFEM_OK;
+}
+
+extern "C" int phifem_tag_facets(const phifem_mesh* mesh, const phifem_levelset* ls,
+                                 const int8_t* cell_tags8, int32_t* facet_tags, int8_t* facet_tags8,
+                                 int64_t* counters, void* stream) {
+  if (int rc = check_mesh(mesh, true)) return rc;
+  if (int rc = check_levelset(mesh, ls, true)) return rc;
+  PHIFEM_CHECK_ARG(cell_tags8 && facet_tags && facet_tags8 && counters, "null pointer");
+  if (mesh->n_facets == 0) return PHIFEM_OK;
+  const int grid = grid_for(mesh->n_facets, kBlock, 8);
+  dispatch_cell_type(mesh->cell_type, [&](auto c) {
+    k_tag_facets<decltype(c)::value><<<grid, kBlock, 0, (cudaStream_t)stream>>>(
+        *mesh, *ls, cell_tags8, facet_tags, facet_tags8, counters);
+  });
+  PHIFEM_CHECK_LAUNCH();
+  return PHIFEM_OK;
+}
+
+extern "C" int phifem_entity_records(const phifem_mesh* mesh, const int8_t* cell_tags8,
+                                     const int8_t* facet_tags8, int32_t facet_tag, uint32_t cell_mask,
+                                     int64_t* records, int64_t capacity, int64_t* n_records,
+                                     void* stream) {
+  if (int rc = check_mesh(mesh, true)) return rc;
+  PHIFEM_CHECK_ARG(cell_tags8 && facet_tags8 && n_records && (records || capacity == 0), "null pointer");
+  if (mesh->n_facets == 0) return PHIFEM_OK;
+  const int nf = mesh->cell_type == PHIFEM_TRIANGLE ? 3 : 4;
+  const int grid = (int)((mesh->n_facets + kBlock - 1) / kBlock);
+  k_entity_records<<<grid, kBlock, 0, (cudaStream_t)stream>>>(
+      *mesh, nf, cell_tags8, facet_tags8, facet_tag, cell_mask, records, capacity,
+      reinterpret_cast<unsigned long long*>(n_records));
+  PHIFEM_CHECK_LAUNCH();
+  return PHIFEM_OK;
+}

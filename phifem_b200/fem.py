@@ -174,15 +174,21 @@ class FunctionSpace:
 
 
 class _Vector:
-    def __init__(self, n):
-        self.array = np.zeros(n, dtype=np.float64)
+    def __init__(self, n, array=None):
+        self.array = np.zeros(n, dtype=np.float64) if array is None else array
 
 
 class Function:
-    """A finite-element function: `function_space`, `x.array` (dof values)."""
+    """A finite-element function: `function_space`, `x.array` (dof values).  `values` may be a numpy
+    array (copied) or a torch tensor on any device (kept as is: device-resident coefficients)."""
 
     def __init__(self, V, values=None):
         self.function_space = V
+        if values is not None and not isinstance(values, np.ndarray) and hasattr(values, "device"):
+            if values.numel() != V.num_dofs:
+                raise ValueError("expected %d dof values" % V.num_dofs)
+            self.x = _Vector(V.num_dofs, values)
+            return
         self.x = _Vector(V.num_dofs)
         if values is not None:
             self.x.array[:] = values
@@ -195,6 +201,24 @@ class Function:
         with np.errstate(all="ignore"):
             self.x.array[:] = np.asarray(f(x3), dtype=np.float64)
         return self
+
+
+class P1Space:
+    """P1 space with vertex dofs and dofmap == mesh.cells, without any host-side copies (what the
+    large configurations use; `functionspace(mesh, 1)` builds the same numbering)."""
+
+    def __init__(self, mesh):
+        self.mesh, self.degree = mesh, 1
+        self.element = LagrangeElement(mesh.cell_type, 1)
+        self.num_dofs = mesh.num_vertices
+
+    @property
+    def dofmap(self):
+        return self.mesh.cells_host
+
+
+def functionspace_p1_device(mesh: Mesh):
+    return P1Space(mesh)
 
 
 def functionspace(mesh: Mesh, element):

@@ -164,6 +164,29 @@ class Mesh:
     def num_facets(self):
         return int(self.f2c.shape[0])
 
+    def detj_bounds(self):
+        """(min, max) of |det J| over the simplices of the mesh, cached.  A property of the mesh
+        alone: lets the P1 classifier decide uncut cells from the signs of phi without gathering
+        coordinates (csrc/tags.cu, k_tag_cells_p1)."""
+        if "detj" not in self._host:
+            if self.cell_type == "quadrilateral" or self.num_cells == 0:
+                self._host["detj"] = (0.0, 0.0)
+            else:
+                lo, hi = float("inf"), 0.0
+                step = 1 << 24
+                for s in range(0, self.num_cells, step):
+                    xc = self.x[self.cells[s:s + step].long()]
+                    e = xc[:, 1:, :] - xc[:, :1, :]
+                    if e.shape[1] == 2:
+                        det = e[:, 0, 0] * e[:, 1, 1] - e[:, 0, 1] * e[:, 1, 0]
+                    else:
+                        det = (e[:, 0] * torch.linalg.cross(e[:, 1], e[:, 2], dim=1)).sum(dim=1)
+                    det = det.abs()
+                    lo, hi = min(lo, float(det.min())), max(hi, float(det.max()))
+                # widen: the kernel's own |det J| may differ from this one in the last bits
+                self._host["detj"] = (lo * (1 - 1e-9), hi * (1 + 1e-9))
+        return self._host["detj"]
+
 
 def _unique_inverse(keys):
     uniq, inv = torch.unique(keys, sorted=True, return_inverse=True)

@@ -1,0 +1,325 @@
+"""Drop-in for `phifem.mesh_scripts` (reference src/phifem/mesh_scripts.py) on B200.
+
+Same public function, argument meaning, tag values, measure ids and error behaviour as the
+reference; underneath, the classification runs as hand-written CUDA kernels (csrc/tags.cu)
+called through the C ABI of include/phifem_b200.h.  There is no CPU path: a mesh that does
+not live on a CUDA device raises.
+
+Public API (reference :571-653):
+
+    cells_tags, facets_tags, submesh, boundaries_measure, submesh_maps = compute_tags_measures(
+        mesh, discrete_levelset, detection_degree, box_mode=False, single_layer_cut=False,
+        overwrite_tags={})
+
+`mesh` is a `phifem_b200.mesh.Mesh`; `discrete_levelset` is a `phifem_b200.fem.Function`
+(P1..P3) or a callable of the physical coordinates `f(x)` with `x` of shape (gdim, npoints)
+(the stand-in for the reference's UFL expression of `SpatialCoordinate`).
+"""
+import os
+import warnings
+
+import numpy as np
+import torch
+
+from . import _geometry as G
+from . import _lib
+from .fem import Function
+from .mesh import Measure, Mesh, MeshTags
+
+debug_mode = os.environ.get("MODE") == "debug"  # reference :22-25
+
+_reference_segment_points = G.reference_segment_points
+_reference_triangle_boundary_points = G.reference_triangle_boundary_points
+_reference_square_boundary_points = G.reference_square_boundary_points
+
+_ZERO_WARNING = ("The detection function is zero everywhere on a cell. We mark it as 'cut' but this "
+                 "can be incorrect and should be carefully checked.")
+
+
+class _DeviceLevelset:
+    """Level set staged for the kernels: owns the device buffers the C struct points to."""
+
+    def __init__(self, mesh, levelset, detection_degree):
+        ct, dev = mesh.cell_type, mesh.device
+        pts = G.cell_detection_points(ct, detection_degree)       # raises NotImplementedError like :326-329
+        fpts = G.facet_detection_points(ct, detection_degree)     # [nfpc, nq, tdim]
+        self.npts, self.nq = len(pts), fpts.shape[1]
+        self.keep = []
+        f64 = dict(dtype=torch.float64, device=dev)
+        coord_grad = None
+        if ct == "quadrilateral":
+            coord_grad = torch.as_tensor(G.coordinate_basis_grad(ct, pts), **f64).contiguous()
+        self.c = _lib.CLevelset()
+        self.c.n_cell_points, self.c.n_facet_points = self.npts, self.nq
+        self.c.coord_grad = _lib.ptr(coord_grad)
+        self.keep.append(coord_grad)
+        if isinstance(levelset, Function):
+            V = levelset.function_space
+            if V.mesh is not mesh:
+                raise ValueError("the level set is defined on another mesh")
+            coeffs = levelset.x.array
+            coeffs = coeffs if torch.is_tensor(coeffs) else torch.from_numpy(np.ascontiguousarray(coeffs))
+            coeffs = coeffs.to(dev, dtype=torch.float64, non_blocking=True).contiguous()
+            nd = V.element.ndofs
+            simplex_p1 = (V.degree == 1 and detection_degree == 1 and ct != "quadrilateral")
+            self.c.mode, self.c.n_dofs_per_cell = 0, nd
+            self.c.coeffs = _lib.ptr(coeffs)
+            ftab = torch.as_tensor(V.element.tabulate(fpts), **f64).contiguous()
+            self.c.facet_table = _lib.ptr(ftab)
+            self.keep += [coeffs, ftab]
+            if simplex_p1:
+                # vertex dofs, points on the vertices: identity table => fast kernel (dofmap = cells)
+                self.c.dofmap, self.c.cell_table = None, None
+            else:
+                if not hasattr(V, "_dofmap_dev") or V._dofmap_dev.device != dev:
+                    V._dofmap_dev = torch.from_numpy(V.dofmap).to(dev)
+                ctab = torch.as_tensor(V.element.tabulate(pts), **f64).contiguous()
+                self.c.dofmap, self.c.cell_table = _lib.ptr(V._dofmap_dev), _lib.ptr(ctab)
+                self.keep += [ctab]
+        elif callable(levelset):
+            vals = self._evaluate(mesh, levelset, pts)
+            fvals = self._evaluate(mesh, levelset, fpts.reshape(-1, fpts.shape[-1]))
+            self.c.mode = 1
+            self.c.cell_values, self.c.facet_values = _lib.ptr(vals), _lib.ptr(fvals)
+            self.keep += [vals, fvals]
+        else:
+            raise TypeError("discrete_levelset must be a phifem_b200.fem.Function or a callable f(x)")
+
+    @staticmethod
+    def _evaluate(mesh, func, ref_pts):
+        """phi at the push-forward of reference points: the points are computed on the device
+        (phifem_cell_points), the user's Python expression is evaluated on the host."""
+        shape = torch.as_tensor(G.coordinate_basis(mesh.cell_type, ref_pts), dtype=torch.float64,
+                                device=mesh.device).contiguous()
+        npts = len(ref_pts)
+        xq = torch.empty((mesh.num_cells, npts, mesh.gdim), dtype=torch.float64, device=mesh.device)
+        cm = _lib.c_mesh(mesh, with_facets=False)
+        _lib.check(_lib.load().phifem_cell_points(cm, _lib.ptr(shape), npts, _lib.ptr(xq), _lib.stream()))
+        pts = xq.reshape(-1, mesh.gdim).T.cpu().numpy()
+        with np.errstate(all="ignore"):
+            vals = np.asarray(func(pts), dtype=np.float64).reshape(mesh.num_cells, npts)
+        return torch.from_numpy(np.ascontiguousarray(vals)).to(mesh.device)
+
+
+class TagWorkspace:
+    """Device buffers of one classification (reused across calls on the same mesh)."""
+
+    def __init__(self, mesh):
+        dev = mesh.device
+        self.cell_tags = torch.empty(mesh.num_cells, dtype=torch.int32, device=dev)
+        self.cell_tags8 = torch.empty(mesh.num_cells, dtype=torch.int8, device=dev)
+        self.facet_tags = torch.empty(mesh.num_facets, dtype=torch.int32, device=dev)
+        self.facet_tags8 = torch.empty(mesh.num_facets, dtype=torch.int8, device=dev)
+        self.counters = torch.zeros(_lib.N_COUNTERS, dtype=torch.int64, device=dev)
+        self.vertex_scratch = None
+
+
+def classify_cells(mesh, dls, ws, single_layer_cut=False):
+    """K1 on the current stream: zero the counters, tag the cells (no host synchronisation)."""
+    ws.counters.zero_()
+    if single_layer_cut and ws.vertex_scratch is None:
+        ws.vertex_scratch = torch.empty(mesh.num_vertices, dtype=torch.uint8, device=mesh.device)
+    _lib.check(_lib.load().phifem_tag_cells(
+        _lib.c_mesh(mesh), dls.c, int(bool(single_layer_cut)), _lib.ptr(ws.cell_tags),
+        _lib.ptr(ws.cell_tags8), _lib.ptr(ws.vertex_scratch), _lib.ptr(ws.counters), _lib.stream()))
+
+
+def classify_facets(mesh, dls, ws):
+    """Facet tags from the cell tags of `ws` on the current stream (no host synchronisation)."""
+    _lib.check(_lib.load().phifem_tag_facets(
+        _lib.c_mesh(mesh), dls.c, _lib.ptr(ws.cell_tags8), _lib.ptr(ws.facet_tags),
+        _lib.ptr(ws.facet_tags8), _lib.ptr(ws.counters), _lib.stream()))
+
+
+def classify(mesh, dls, single_layer_cut=False, ws=None):
+    """Run the tag kernels (cells, then facets) on the current stream; returns the workspace."""
+    ws = ws or TagWorkspace(mesh)
+    classify_cells(mesh, dls, ws, single_layer_cut)
+    classify_facets(mesh, dls, ws)
+    return ws
+
+
+def _integration_entities_dev(mesh, cell_tags8, facet_tags8, facet_tag, cell_tag_values):
+    """Device version of `_compute_integration_entities` (reference :137-192): flat int32
+    [cell, local_facet, ...] tensor, cells in first-appearance order, local facets ascending."""
+    lib = _lib.load()
+    cm = _lib.c_mesh(mesh)
+    mask = 0
+    for t in cell_tag_values:
+        mask |= 1 << int(t)
+    n_dev = torch.zeros(1, dtype=torch.int64, device=mesh.device)
+    capacity = max(1024, int(4 * mesh.num_facets ** (1 - 1.0 / mesh.topology.dim)))
+    while True:
+        rec = torch.empty((capacity, 3), dtype=torch.int64, device=mesh.device)
+        n_dev.zero_()
+        _lib.check(lib.phifem_entity_records(cm, _lib.ptr(cell_tags8), _lib.ptr(facet_tags8), facet_tag,
+                                             mask, _lib.ptr(rec), capacity, _lib.ptr(n_dev), _lib.stream()))
+        n = int(n_dev.item())
+        if n <= capacity:
+            break
+        capacity = n
+    rec = rec[:n]
+    if n == 0:
+        return torch.zeros(0, dtype=torch.int32, device=mesh.device)
+    key, cell, lf = rec[:, 0], rec[:, 1], rec[:, 2]
+    ucell, inv = torch.unique(cell, return_inverse=True)
+    first = torch.full((len(ucell),), torch.iinfo(torch.int64).max, dtype=torch.int64, device=mesh.device)
+    first.scatter_reduce_(0, inv, key, reduce="amin")          # first appearance of each cell
+    order = torch.argsort(first[inv] * 8 + lf)                  # then local facets ascending
+    return torch.stack([cell[order], lf[order]], dim=1).reshape(-1).to(torch.int32)
+
+
+def _tags_from_workspace(mesh, ws):
+    tdim = mesh.topology.dim
+    return (MeshTags(mesh, tdim, ws.cell_tags), MeshTags(mesh, tdim - 1, ws.facet_tags))
+
+
+def _overwrite_tags(mesh, tags_to_overwrite, new_tags):
+    """Reference :561-568: the user's tags win where both are defined."""
+    dense = tags_to_overwrite.values_dev.clone()
+    idx = torch.from_numpy(np.asarray(new_tags.indices, dtype=np.int64)).to(dense.device)
+    dense[idx] = torch.from_numpy(np.asarray(new_tags.values, dtype=np.int32)).to(dense.device)
+    return MeshTags(mesh, tags_to_overwrite.dim, dense)
+
+
+def _check_debug(counters):
+    """MODE=debug assertions of reference :360-374 and :499-521 that apply to dense tag arrays."""
+    if counters[_lib.CNT_INTERIOR] == 0:
+        raise ValueError("No interior cells (1)!")
+    if counters[_lib.CNT_CUT] == 0:
+        print("WARNING: no cut cells computed in the partition.")
+    ft = counters[_lib.CNT_FACET_TAG1:_lib.CNT_FACET_TAG1 + 6]
+    if ft[0] == 0:
+        raise ValueError("No interior facets (1)!")
+    if ft[1] == 0:
+        print("WARNING: no cut facet computed in the partition.")
+    if ft[3] == 0:
+        raise ValueError("No boundary facets (4)!")
+    if counters[_lib.CNT_FACET_CONFLICT] != 0:
+        raise ValueError("facet sets have a non-empty intersection!")
+
+
+def compute_tags_measures(mesh, discrete_levelset, detection_degree, box_mode=False,
+                          single_layer_cut=False, overwrite_tags={}):
+    """Compute the mesh (cells and facets) tags as well as the discrete boundary measures.
+
+    Same contract as reference src/phifem/mesh_scripts.py:571-653.  Cells: 1 inside, 2 cut,
+    3 outside (:290-293).  Facets: 1 interior, 2 cut, 3 inside/cut interface, 4 Gamma_h,
+    5 exterior, 6 direct inside/outside interface (:399-405).  box_mode=True returns tags on the
+    input mesh and a `ds` measure whose id 100 / 101 hold the one-sided entities (:617-634);
+    box_mode=False returns the submesh of Omega_h, tags re-indexed on it and its maps (:635-645).
+    """
+    if not isinstance(mesh, Mesh):
+        raise TypeError("mesh must be a phifem_b200.mesh.Mesh")
+    _lib.require_cuda(mesh)
+    dls = _DeviceLevelset(mesh, discrete_levelset, detection_degree)
+    ws = classify(mesh, dls, single_layer_cut)
+    counters = ws.counters.cpu().numpy()          # one small D2H: warnings, debug checks
+    if counters[_lib.CNT_ZERO_DEN] > 0:           # :129-133 for the dx detection
+        warnings.warn(_ZERO_WARNING, RuntimeWarning)
+    if counters[_lib.CNT_FACET_ZERO_DEN] > 0 or counters[_lib.CNT_BOUNDARY_OWNERS] < mesh.num_cells:
+        # the ds detection vector is zero on every cell without a mesh-boundary facet: the
+        # reference warns here on essentially every mesh
+        warnings.warn(_ZERO_WARNING, RuntimeWarning)
+    if debug_mode:
+        _check_debug(counters)
+    cells_tags, facets_tags = _tags_from_workspace(mesh, ws)
+    cell_tags8, facet_tags8 = ws.cell_tags8, ws.facet_tags8
+
+    if "cells" in overwrite_tags.keys():          # :606-610
+        ow = overwrite_tags["cells"]
+        if np.any(np.isin([1, 2, 3], ow.values)):
+            raise ValueError("Cannot overwrite cells tags with values 1, 2 or 3.")
+        cells_tags = _overwrite_tags(mesh, cells_tags, ow)
+        cell_tags8 = cells_tags.values_dev.to(torch.int8)
+    if "facets" in overwrite_tags.keys():         # :611-615
+        ow = overwrite_tags["facets"]
+        if np.any(np.isin([1, 2, 3, 4, 5, 6, 100, 101], ow.values)):
+            raise ValueError("Cannot overwrite facets tags with values 1, 2, 3, 4, 5, 6, 100 or 101.")
+        facets_tags = _overwrite_tags(mesh, facets_tags, ow)
+        facet_tags8 = facets_tags.values_dev.to(torch.int8)
+
+    if box_mode:                                   # :617-634
+        ents_out = _integration_entities_dev(mesh, cell_tags8, facet_tags8, 4, (1, 2))
+        ents_in = _integration_entities_dev(mesh, cell_tags8, facet_tags8, 3, (2, 3))
+        measure = Measure("ds", mesh, subdomain_data=[(100, ents_out), (101, ents_in)])
+        cells_tags.tags8, facets_tags.tags8 = cell_tags8, facet_tags8
+        return cells_tags, facets_tags, None, measure, None
+
+    # submesh of Omega_h = cells tagged 1 or 2 (:635-645)
+    keep = torch.nonzero((cell_tags8 == 1) | (cell_tags8 == 2)).reshape(-1)
+    sub_parent = mesh.cells[keep].long()
+    v_map = torch.unique(sub_parent)
+    renum = torch.full((mesh.num_vertices,), -1, dtype=torch.int64, device=mesh.device)
+    renum[v_map] = torch.arange(len(v_map), device=mesh.device)
+    submesh = Mesh(mesh.x[v_map], renum[sub_parent].to(torch.int32), mesh.cell_type, mesh.device)
+    sub_cell = cells_tags.values_dev[keep].contiguous()
+    parent_facet = torch.empty(submesh.num_facets, dtype=torch.int64, device=mesh.device)
+    parent_facet[submesh.c2f.reshape(-1).long()] = mesh.c2f[keep].reshape(-1).long()   # :244-260
+    sub_facet = facets_tags.values_dev[parent_facet].contiguous()
+    tdim = mesh.topology.dim
+    c_map = keep.to(torch.int32).cpu().numpy()
+    v_map_h = v_map.to(torch.int32).cpu().numpy()
+    return (MeshTags(submesh, tdim, sub_cell), MeshTags(submesh, tdim - 1, sub_facet), submesh,
+            Measure("ds", submesh), [c_map, v_map_h, v_map_h.copy()])
+
+
+# the reference's test file calls the function by this name (tests/test_compute_meshtags.py:122)
+compute_meshtags = compute_tags_measures
+
+
+def _tag_cells(mesh, discrete_levelset, detection_degree, single_layer_cut=False):
+    """Reference :284-390 (cells only)."""
+    return compute_tags_measures(mesh, discrete_levelset, detection_degree, box_mode=True,
+                                 single_layer_cut=single_layer_cut)[0]
+
+
+def _tag_facets(mesh, cells_tags, discrete_levelset, detection_degree):
+    """Reference :393-558 for given cell tags."""
+    _lib.require_cuda(mesh)
+    dls = _DeviceLevelset(mesh, discrete_levelset, detection_degree)
+    ws = TagWorkspace(mesh)
+    ws.cell_tags8 = cells_tags.values_dev.to(torch.int8).contiguous()
+    ws.counters[_lib.CNT_EXTERIOR] = int((ws.cell_tags8 == 3).sum())
+    _lib.check(_lib.load().phifem_tag_facets(_lib.c_mesh(mesh), dls.c, _lib.ptr(ws.cell_tags8),
+                                             _lib.ptr(ws.facet_tags), _lib.ptr(ws.facet_tags8),
+                                             _lib.ptr(ws.counters), _lib.stream()))
+    return MeshTags(mesh, mesh.topology.dim - 1, ws.facet_tags)
+
+
+def _compute_integration_entities(mesh, integration_cells, integration_facets, ind):
+    """Reference :137-192, for explicit index lists (host arrays)."""
+    _lib.require_cuda(mesh)
+    ct8 = torch.zeros(mesh.num_cells, dtype=torch.int8, device=mesh.device)
+    ct8[torch.as_tensor(np.asarray(integration_cells, dtype=np.int64), device=mesh.device)] = 1
+    ft8 = torch.zeros(mesh.num_facets, dtype=torch.int8, device=mesh.device)
+    ft8[torch.as_tensor(np.asarray(integration_facets, dtype=np.int64), device=mesh.device)] = 1
+    ents = _integration_entities_dev(mesh, ct8, ft8, 1, (1,))
+    return [(ind, ents.cpu().numpy())]
+
+
+def _reshape_map(connect):
+    """Reference :195-214: padded dense map, columns in reverse link order."""
+    counts = np.diff(connect.offsets)
+    width = int(counts.max())
+    out = -np.ones((len(counts), width), dtype=int)
+    ends = connect.offsets[1:]
+    for col in range(width):
+        has = counts > col
+        out[has, col] = connect.array[ends[has] - col - 1]
+    return out, width
+
+
+def _transfer_tags(source_mesh_tags, dest_mesh, cmap, source_mesh=None):
+    """Reference :217-281: re-index cell or facet tags onto a submesh."""
+    cdim = dest_mesh.topology.dim
+    cmap_d = torch.as_tensor(np.asarray(cmap, dtype=np.int64), device=dest_mesh.device)
+    if source_mesh_tags.dim == cdim:
+        return MeshTags(dest_mesh, cdim, source_mesh_tags.values_dev[cmap_d].contiguous())
+    if source_mesh_tags.dim == cdim - 1:
+        if source_mesh is None:
+            raise ValueError("You must pass a source_mesh to transfer facets tags.")
+        parent = torch.empty(dest_mesh.num_facets, dtype=torch.int64, device=dest_mesh.device)
+        parent[dest_mesh.c2f.reshape(-1).long()] = source_mesh.c2f[cmap_d].reshape(-1).long()
+        return MeshTags(dest_mesh, cdim - 1, source_mesh_tags.values_dev[parent].contiguous())
+    raise ValueError("The source_mesh_tags can only be cells tags or facets tags.")
