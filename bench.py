@@ -39,7 +39,7 @@ def _peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.02):
+    def __init__(self, index, period=0.004):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -311,7 +311,7 @@ def run_ours(args):
 
     # ---- e2e: public API, pinned host buffers in, pinned host buffers out ---------------------------
     e2e = None
-    if world == 1:
+    if world == 1 and not args.no_e2e:
         phi_h = phi.cpu().pin_memory()
         f_h = f.cpu().pin_memory()
         out_h = {"ct": torch.empty(mesh.num_cells, dtype=torch.int32).pin_memory(),
@@ -380,6 +380,7 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=80, help="size of the bounded CPU sample")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

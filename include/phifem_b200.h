@@ -51,6 +51,8 @@ typedef struct phifem_mesh {
   const int32_t* f2c;     /* [n_facets, 2]   facet -> cells ascending, -1 pad */
   double detj_min;        /* optional bounds of |det J| over the mesh (0,0 = unknown): */
   double detj_max;        /* lets the P1 classifier skip the coordinate gather on uncut cells */
+  const int32_t* boundary_facets; /* optional [n_boundary_facets]: facets with one cell, ascending; */
+  int64_t n_boundary_facets;      /* lets the facet classifier run its ds detection as a second pass */
 } phifem_mesh;
 
 /* Discrete level set as seen by the detection forms (src/phifem/mesh_scripts.py:95-134).
@@ -79,7 +81,6 @@ enum {
   PHIFEM_CNT_EXTERIOR = 2,     /* cells tagged 3 */
   PHIFEM_CNT_UNTAGGED = 3,     /* cells with NaN ratio */
   PHIFEM_CNT_ZERO_DEN = 4,     /* cells whose dx-denominator is ~0 (RuntimeWarning, :129-133) */
-  PHIFEM_CNT_FACET_TAG1 = 5,   /* ... 5..10: facets tagged 1..6 */
   PHIFEM_CNT_FACET_ZERO_DEN = 11, /* cells whose ds-denominator is ~0 */
   PHIFEM_CNT_FACET_CONFLICT = 12, /* facets the reference algebra would emit twice */
   PHIFEM_CNT_BOUNDARY_OWNERS = 13, /* cells owning at least one mesh-boundary facet */
@@ -106,7 +107,7 @@ int phifem_tag_cells(const phifem_mesh* mesh, const phifem_levelset* ls, int32_t
 
 /* Replaces `_tag_facets` (:393-558) including its `ds` detection pass (:434-452):
  * facet_tags[n_facets] in 1..6.  Reads counters[PHIFEM_CNT_EXTERIOR] on the device (the "no exterior
- * cell" branch :469-470), accumulates slots 5..13. */
+ * cell" branch :469-470), accumulates slots 11..13. */
 int phifem_tag_facets(const phifem_mesh* mesh, const phifem_levelset* ls, const int8_t* cell_tags8,
                       int32_t* facet_tags, int8_t* facet_tags8, int64_t* counters, void* stream);
 

@@ -14,7 +14,6 @@ LIB_PATH = os.path.join(_HERE, "libphifem_b200.so")
 CELL_TYPE_ID = {"triangle": 0, "quadrilateral": 1, "tetrahedron": 2}
 N_COUNTERS = 16
 CNT_INTERIOR, CNT_CUT, CNT_EXTERIOR, CNT_UNTAGGED, CNT_ZERO_DEN = 0, 1, 2, 3, 4
-CNT_FACET_TAG1 = 5
 CNT_FACET_ZERO_DEN, CNT_FACET_CONFLICT, CNT_BOUNDARY_OWNERS = 11, 12, 13
 
 _vp = ctypes.c_void_p
@@ -25,7 +24,8 @@ class CMesh(ctypes.Structure):
                 ("n_vertices", ctypes.c_int64), ("n_cells", ctypes.c_int64),
                 ("n_facets", ctypes.c_int64),
                 ("x", _vp), ("cells", _vp), ("c2f", _vp), ("f2c", _vp),
-                ("detj_min", ctypes.c_double), ("detj_max", ctypes.c_double)]
+                ("detj_min", ctypes.c_double), ("detj_max", ctypes.c_double),
+                ("boundary_facets", _vp), ("n_boundary_facets", ctypes.c_int64)]
 
 
 class CLevelset(ctypes.Structure):
@@ -114,4 +114,5 @@ def c_mesh(mesh, with_facets=True):
     return CMesh(CELL_TYPE_ID[mesh.cell_type], mesh.gdim, mesh.num_vertices, mesh.num_cells,
                  mesh.num_facets if with_facets else 0, ptr(mesh.x), ptr(mesh.cells),
                  ptr(mesh.c2f) if with_facets else None, ptr(mesh.f2c) if with_facets else None,
-                 lo, hi)
+                 lo, hi, ptr(mesh.boundary_facets) if with_facets else None,
+                 mesh.boundary_facets.numel() if with_facets else 0)

@@ -52,7 +52,7 @@ class AssemblyPlan:
         self.entities = entities.reshape(-1, 2).to(torch.int32).contiguous()
 
         def pair_keys(dm):  # [m, k] dofs -> [m, k*k] keys row*n+col, row-major (row = test)
-            return (dm[:, :, None] * n + dm[:, None, :]).reshape(dm.shape[0], -1)
+            return (dm[:, :, None] * n + dm[:, None, :]).reshape(dm.shape[0], dm.shape[1] * dm.shape[1])
 
         dm = mesh.cells[self.active.long()].long()
         keys_c = pair_keys(dm)
@@ -94,6 +94,8 @@ def build_plan(mesh, cells_tags, facets_tags, ds=None):
         ents = torch.zeros(0, dtype=torch.int32, device=mesh.device)
     elif hasattr(ds, "integration_entities_dev"):
         ents = ds.integration_entities_dev
+    elif torch.is_tensor(ds):
+        ents = ds.to(mesh.device)
     else:
         ents = torch.as_tensor(np.asarray(ds, dtype=np.int32), device=mesh.device)
     return AssemblyPlan(mesh, c8.contiguous(), f8.contiguous(), ents)

@@ -54,6 +54,19 @@ template <> struct CellTraits<PHIFEM_TETRAHEDRON> {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// Persistent grid-stride kernels: exactly one resident wave (SMs x occupancy), never more CTAs than tiles.
+template <typename K>
+inline int persistent_grid(K kernel, int block, int64_t n_tiles) {
+  int per_sm = 0, dev = 0, sms = kNumSMs;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  int64_t cap = (int64_t)sms * per_sm;
+  if (n_tiles < 1) n_tiles = 1;
+  return (int)(n_tiles < cap ? n_tiles : cap);
+}
+
 inline int grid_for(int64_t n, int block, int ctas_per_sm) {
   int64_t need = (n + block - 1) / block;
   int64_t cap = (int64_t)kNumSMs * ctas_per_sm;

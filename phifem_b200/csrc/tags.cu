@@ -117,7 +117,7 @@ __device__ __forceinline__ void load_coeffs(const phifem_mesh& m, const phifem_l
   }
 }
 
-// ---- block-level tag counters (warp ballot -> shared -> one global atomic per block) --------
+// ---- tag counters: per-thread registers -> warp redux -> shared -> one global atomic per block --------
 struct BlockCounters {
   unsigned int* s;
   __device__ BlockCounters(unsigned int* smem, int n) : s(smem) {
@@ -128,6 +128,10 @@ struct BlockCounters {
     const unsigned int b = __ballot_sync(0xffffffffu, pred);
     if ((threadIdx.x & 31) == 0 && b) atomicAdd(&s[slot], __popc(b));
   }
+  __device__ __forceinline__ void add(unsigned int local, int slot) {  // all 32 lanes must call
+    const unsigned int w = __reduce_add_sync(0xffffffffu, local);
+    if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s[slot], w);
+  }
   __device__ void flush(int64_t* counters, int base, int n) {
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x)
@@ -137,48 +141,84 @@ struct BlockCounters {
 };
 
 // ---- K1a: P1 level set, detection degree 1, simplices: the headline kernel ------------------
-// Per cell: 4 (3) vertex ids (coalesced 16 B / 12 B), 4 (3) fp64 gathers of phi (L2-resident:
-// 8 B x Nv), and -- only where the sign test cannot decide -- the vertex coordinates for |det J|.
+// Per cell: 4 (3) vertex ids (coalesced 16 B / 12 B), 4 (3) fp64 gathers of phi (8 B x Nv, mostly
+// L1/L2 hits), and -- only where the sign test cannot decide -- the vertex coordinates for |det J|.
 // Uncut cells whose products phi*|detJ| can neither vanish, overflow nor land near the
 // RuntimeWarning threshold are decided from the signs alone, which is bit-identical to the
 // sequential sum (all terms share a sign => num == +-den exactly).
+// HBM-latency bound: every thread keeps kUnroll independent cells in flight (index loads first, then
+// all gathers), counters stay in registers until the end of the grid-stride loop.
+constexpr int kUnroll = 4;
+
+// exact path for cells the sign test cannot decide; scalars in / packed (tag | zden << 8) out so
+// that the call does not force the caller's arrays into local memory
 template <int CT>
-__global__ void __launch_bounds__(kBlock) k_tag_cells_p1(phifem_mesh m, const double* __restrict__ phi,
-                                                         bool have_bounds, int32_t* __restrict__ tags,
-                                                         int8_t* __restrict__ tags8,
-                                                         int64_t* counters) {
+__device__ __noinline__ int tag_cell_exact(const double* __restrict__ x, int v0, int v1, int v2, int v3,
+                                           double p0, double p1, double p2, double p3) {
+  using T = CellTraits<CT>;
+  const int v[4] = {v0, v1, v2, v3};
+  const double p[4] = {p0, p1, p2, p3};
+  double xc[4][3];
+#pragma unroll
+  for (int k = 0; k < T::nv; ++k)
+#pragma unroll
+    for (int d = 0; d < T::gdim; ++d) xc[k][d] = __ldg(x + (int64_t)v[k] * T::gdim + d);
+  const double s = simplex_detj<CT>(xc);
+  double num = 0.0, den = 0.0;
+#pragma unroll
+  for (int k = 0; k < T::nv; ++k) {
+    const double t = p[k] * s;
+    num = num + t;
+    den = den + fabs(t);
+  }
+  return classify(num, den) | ((int)is_close_to_zero(den) << 8);
+}
+
+template <int CT>
+__global__ void __launch_bounds__(kBlock, 3) k_tag_cells_p1(phifem_mesh m, const double* __restrict__ phi,
+                                                            bool have_bounds, int32_t* __restrict__ tags,
+                                                            int8_t* __restrict__ tags8,
+                                                            int64_t* counters) {
   using T = CellTraits<CT>;
   __shared__ unsigned int scnt[5];
   BlockCounters cnt(scnt, 5);
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < m.n_cells; base += stride) {
-    const int64_t c = base + threadIdx.x;
-    const bool valid = c < m.n_cells;
-    int tag = -1;
-    bool zden = false;
-    if (valid) {
-      int v[4];
+  unsigned int local[5] = {0u, 0u, 0u, 0u, 0u};
+  const int64_t tile = (int64_t)blockDim.x * kUnroll;
+  for (int64_t base = (int64_t)blockIdx.x * tile; base < m.n_cells; base += (int64_t)gridDim.x * tile) {
+    int v[kUnroll][4];
+    bool valid[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t c = base + (int64_t)u * blockDim.x + threadIdx.x;
+      valid[u] = c < m.n_cells;
+      const int64_t cc = valid[u] ? c : 0;
       if (T::nv == 4) {
-        const int4 q = __ldg(reinterpret_cast<const int4*>(m.cells) + c);
-        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        const int4 q = __ldg(reinterpret_cast<const int4*>(m.cells) + cc);
+        v[u][0] = q.x; v[u][1] = q.y; v[u][2] = q.z; v[u][3] = q.w;
       } else {
 #pragma unroll
-        for (int k = 0; k < T::nv; ++k) v[k] = __ldg(m.cells + c * T::nv + k);
+        for (int k = 0; k < T::nv; ++k) v[u][k] = __ldg(m.cells + cc * T::nv + k);
       }
-      double p[4];
+    }
+    double p[kUnroll][4];
 #pragma unroll
-      for (int k = 0; k < T::nv; ++k) p[k] = __ldg(phi + v[k]);
+    for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+      for (int k = 0; k < T::nv; ++k) p[u][k] = __ldg(phi + v[u][k]);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
       bool allpos = true, allneg = true, sane = true;
       double sumabs = 0.0;
 #pragma unroll
       for (int k = 0; k < T::nv; ++k) {
-        allpos &= p[k] > 0.0;
-        allneg &= p[k] < 0.0;
-        const double ap = fabs(p[k]);
+        allpos &= p[u][k] > 0.0;
+        allneg &= p[u][k] < 0.0;
+        const double ap = fabs(p[u][k]);
         sane &= (ap >= 1e-150) & (ap <= 1e150);
         sumabs += ap;
       }
       bool fast = have_bounds && sane && (allpos || allneg);
+      bool zden = false;
       if (fast) {
         // den = sum |p| s lies in [sumabs*detj_min, sumabs*detj_max] up to rounding: decide the
         // isclose(den, 0) flag (atol 1e-8, mesh_scripts.py:129) only when it is unambiguous
@@ -186,34 +226,27 @@ __global__ void __launch_bounds__(kBlock) k_tag_cells_p1(phifem_mesh m, const do
         else if (sumabs * m.detj_max < 0.5e-8) zden = true;
         else fast = false;
       }
-      if (fast) {
-        tag = allpos ? 3 : 1;
-      } else {
-        double xc[4][3];
-#pragma unroll
-        for (int k = 0; k < T::nv; ++k)
-#pragma unroll
-          for (int d = 0; d < T::gdim; ++d) xc[k][d] = __ldg(m.x + (int64_t)v[k] * T::gdim + d);
-        const double s = simplex_detj<CT>(xc);
-        double num = 0.0, den = 0.0;
-#pragma unroll
-        for (int k = 0; k < T::nv; ++k) {
-          const double t = p[k] * s;
-          num = num + t;
-          den = den + fabs(t);
-        }
-        tag = classify(num, den);
-        zden = is_close_to_zero(den);
+      int tag = allpos ? 3 : 1;
+      if (!fast && valid[u]) {
+        const int r = tag_cell_exact<CT>(m.x, v[u][0], v[u][1], v[u][2], T::nv == 4 ? v[u][3] : 0,
+                                         p[u][0], p[u][1], p[u][2], T::nv == 4 ? p[u][3] : 0.0);
+        tag = r & 0xff;
+        zden = (r >> 8) != 0;
       }
-      tags[c] = tag;
-      tags8[c] = (int8_t)tag;
+      if (valid[u]) {
+        const int64_t c = base + (int64_t)u * blockDim.x + threadIdx.x;
+        tags[c] = tag;
+        tags8[c] = (int8_t)tag;
+        local[0] += tag == 1;
+        local[1] += tag == 2;
+        local[2] += tag == 3;
+        local[3] += tag == 0;
+        local[4] += zden;
+      }
     }
-    cnt.vote(tag == 1, 0);
-    cnt.vote(tag == 2, 1);
-    cnt.vote(tag == 3, 2);
-    cnt.vote(tag == 0, 3);
-    cnt.vote(zden, 4);
   }
+#pragma unroll
+  for (int i = 0; i < 5; ++i) cnt.add(local[i], i);
   cnt.flush(counters, PHIFEM_CNT_INTERIOR, 5);
 }
 
@@ -297,7 +330,7 @@ __global__ void k_single_layer_apply(const int32_t* __restrict__ cells, int nv, 
 // ds-detection of the owner cell of a mesh-boundary facet (mesh_scripts.py:434-452): per exterior
 // facet sum_q phi_q*s_f, added into the cell entry in ascending facet index.
 template <int CT>
-__device__ bool owner_is_ds_cut(const phifem_mesh& m, const phifem_levelset& ls, int64_t c,
+__device__ __noinline__ bool owner_is_ds_cut(const phifem_mesh& m, const phifem_levelset& ls, int64_t c,
                                 int32_t this_facet, bool* first_of_cell, bool* zden) {
   using T = CellTraits<CT>;
   int v[4];
@@ -347,57 +380,135 @@ __device__ bool owner_is_ds_cut(const phifem_mesh& m, const phifem_levelset& ls,
   return d > -1.0 && d < 1.0;
 }
 
+// The facet algebra of mesh_scripts.py:454-497 for ONE facet: membership flags in, tag out (bit 8 = the
+// reference would emit the facet twice).  Evaluated at compile time into a lookup table for interior
+// facets and at run time for the (rare) mesh-boundary facets.
+__host__ __device__ constexpr int facet_algebra(int t0, int t1, bool bnd, bool k, bool anyE) {
+  const bool inI = (t0 == 1) | (t1 == 1), inC = (t0 == 2) | (t1 == 2), inE = (t0 == 3) | (t1 == 3);
+  const bool cut_bnd = bnd && k;                                  // :454-456
+  const bool uncut_bnd = bnd && !k && !inE && !inI;               // :457-461
+  const bool int_bnd = inI && inC;                                // :464-466
+  bool boundary = anyE ? ((inE && inC) || uncut_bnd) : bnd;       // :469-474
+  const bool direct = inE && inI;                                 // :476-478
+  const bool cutf = (inC && !(boundary || int_bnd || direct || uncut_bnd)) || cut_bnd;  // :480-485
+  const bool rem = int_bnd || boundary || direct;
+  const bool interior = inI && !rem;                              // :488-490
+  const bool exterior = inE && !rem;                              // :493-495
+  boundary = boundary && !cutf;                                   // :497
+  // stacking order [5,1,3,2,4,6] of :524-552; the last writer wins when the algebra is inconsistent
+  int tag = 0;
+  if (exterior) tag = 5;
+  if (interior) tag = 1;
+  if (int_bnd) tag = 3;
+  if (cutf) tag = 2;
+  if (boundary) tag = 4;
+  if (direct) tag = 6;
+  const int n = (int)exterior + (int)interior + (int)int_bnd + (int)cutf + (int)boundary + (int)direct;
+  return tag | (n > 1 ? 0x100 : 0);
+}
+
+// interior facets: 4 bits per (t0, t1) pair, t in 0..3 (for them `anyE` cannot change the outcome: it
+// only matters when a tag-3 cell exists, and then anyE is true)
+__host__ __device__ constexpr unsigned long long interior_facet_lut(bool conflicts) {
+  unsigned long long lut = 0;
+  for (int t0 = 0; t0 < 4; ++t0)
+    for (int t1 = 0; t1 < 4; ++t1) {
+      const int r = facet_algebra(t0, t1, false, false, true);
+      const unsigned long long v = conflicts ? (unsigned long long)(r >> 8) : (unsigned long long)(r & 0xf);
+      lut |= v << (4 * (t0 * 4 + t1));
+    }
+  return lut;
+}
+
+// mesh-boundary facet: needs the ds detection of its owner cell; returns the tag, updates counters
 template <int CT>
-__global__ void __launch_bounds__(kBlock) k_tag_facets(phifem_mesh m, phifem_levelset ls,
-                                                       const int8_t* __restrict__ ctags,
-                                                       int32_t* __restrict__ ftags,
-                                                       int8_t* __restrict__ ftags8, int64_t* counters) {
-  __shared__ unsigned int scnt[10];
-  BlockCounters cnt(scnt, 10);
+__device__ __forceinline__ int tag_boundary_facet(const phifem_mesh& m, const phifem_levelset& ls,
+                                                  int owner, int t0, int32_t f, bool anyE,
+                                                  unsigned int& n_zden, unsigned int& n_conflict,
+                                                  unsigned int& n_owner) {
+  bool zden = false, owner_first = false;
+  const bool k = owner_is_ds_cut<CT>(m, ls, owner, f, &owner_first, &zden);
+  const int r = facet_algebra(t0, 0, true, k, anyE);
+  n_conflict += r >> 8;
+  n_zden += owner_first && zden;
+  n_owner += owner_first;
+  return r & 0xf;
+}
+
+// second pass over the (precomputed, mesh-level) list of mesh-boundary facets: keeps the heavy
+// table-driven ds detection out of the streaming kernel
+template <int CT>
+__global__ void __launch_bounds__(kBlock) k_tag_boundary_facets(phifem_mesh m, phifem_levelset ls,
+                                                                const int8_t* __restrict__ ctags,
+                                                                int32_t* __restrict__ ftags,
+                                                                int8_t* __restrict__ ftags8,
+                                                                int64_t* counters) {
+  __shared__ unsigned int scnt[4];
+  BlockCounters cnt(scnt, 3);
+  unsigned int n_zden = 0, n_conflict = 0, n_owner = 0;
+  const bool anyE = *reinterpret_cast<volatile int64_t*>(counters + PHIFEM_CNT_EXTERIOR) > 0;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m.n_boundary_facets) {
+    const int32_t f = __ldg(m.boundary_facets + i);
+    const int owner = __ldg(m.f2c + 2 * (int64_t)f);
+    const int tag = tag_boundary_facet<CT>(m, ls, owner, __ldg(ctags + owner) & 3, f, anyE, n_zden,
+                                           n_conflict, n_owner);
+    ftags[f] = tag;
+    ftags8[f] = (int8_t)tag;
+  }
+  cnt.add(n_zden, 0);
+  cnt.add(n_conflict, 1);
+  cnt.add(n_owner, 2);
+  cnt.flush(counters, PHIFEM_CNT_FACET_ZERO_DEN, 3);
+}
+
+template <int CT, bool kInlineBoundary>
+__global__ void __launch_bounds__(kBlock, 4) k_tag_facets(phifem_mesh m, phifem_levelset ls,
+                                                          const int8_t* __restrict__ ctags,
+                                                          int32_t* __restrict__ ftags,
+                                                          int8_t* __restrict__ ftags8, int64_t* counters) {
+  constexpr unsigned long long kTagLut = interior_facet_lut(false);
+  constexpr unsigned long long kConflictLut = interior_facet_lut(true);
+  __shared__ unsigned int scnt[4];
+  BlockCounters cnt(scnt, 3);
+  unsigned int n_zden = 0, n_conflict = 0, n_owner = 0;
   // "no exterior cell at all" switches the meaning of mesh-boundary facets (:469-474)
   const bool anyE = *reinterpret_cast<volatile int64_t*>(counters + PHIFEM_CNT_EXTERIOR) > 0;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < m.n_facets; base += stride) {
-    const int64_t f = base + threadIdx.x;
-    int tag = -1;
-    bool zden = false, owner_first = false, conflict = false;
-    if (f < m.n_facets) {
-      const int2 cc = __ldg(reinterpret_cast<const int2*>(m.f2c) + f);
-      const int t0 = ctags[cc.x];
-      const bool bnd = cc.y < 0;
-      const int t1 = bnd ? 0 : ctags[cc.y];
-      const bool inI = (t0 == 1) | (t1 == 1), inC = (t0 == 2) | (t1 == 2), inE = (t0 == 3) | (t1 == 3);
-      bool k = false;
-      if (bnd) k = owner_is_ds_cut<CT>(m, ls, cc.x, (int32_t)f, &owner_first, &zden);
-      const bool cut_bnd = bnd && k;                                  // :454-456
-      const bool uncut_bnd = bnd && !k && !inE && !inI;               // :457-461
-      const bool int_bnd = inI && inC;                                // :464-466
-      bool boundary = anyE ? ((inE && inC) || uncut_bnd) : bnd;       // :469-474
-      const bool direct = inE && inI;                                 // :476-478
-      const bool cutf = (inC && !(boundary || int_bnd || direct || uncut_bnd)) || cut_bnd;  // :480-485
-      const bool rem = int_bnd || boundary || direct;
-      const bool interior = inI && !rem;                              // :488-490
-      const bool exterior = inE && !rem;                              // :493-495
-      boundary = boundary && !cutf;                                   // :497
-      // stacking order [5,1,3,2,4,6] of :524-552; the last writer wins when the algebra is inconsistent
-      tag = 0;
-      if (exterior) tag = 5;
-      if (interior) tag = 1;
-      if (int_bnd) tag = 3;
-      if (cutf) tag = 2;
-      if (boundary) tag = 4;
-      if (direct) tag = 6;
-      conflict = (int)exterior + (int)interior + (int)int_bnd + (int)cutf + (int)boundary + (int)direct > 1;
+  const int64_t tile = (int64_t)blockDim.x * kUnroll;
+  for (int64_t base = (int64_t)blockIdx.x * tile; base < m.n_facets; base += (int64_t)gridDim.x * tile) {
+    int2 cc[kUnroll];
+    bool valid[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t f = base + (int64_t)u * blockDim.x + threadIdx.x;
+      valid[u] = f < m.n_facets;
+      cc[u] = __ldg(reinterpret_cast<const int2*>(m.f2c) + (valid[u] ? f : 0));
+    }
+    int t0[kUnroll], t1[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      t0[u] = __ldg(ctags + cc[u].x) & 3;
+      t1[u] = cc[u].y < 0 ? 0 : (__ldg(ctags + cc[u].y) & 3);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      if (!valid[u]) continue;
+      const int64_t f = base + (int64_t)u * blockDim.x + threadIdx.x;
+      const int sh = 4 * (t0[u] * 4 + t1[u]);
+      int tag = (int)((kTagLut >> sh) & 0xfull);
+      n_conflict += (unsigned int)((kConflictLut >> sh) & 1ull);
+      if (cc[u].y < 0) {
+        if (!kInlineBoundary) continue;  // tagged by k_tag_boundary_facets
+        tag = tag_boundary_facet<CT>(m, ls, cc[u].x, t0[u], (int32_t)f, anyE, n_zden, n_conflict, n_owner);
+      }
       ftags[f] = tag;
       ftags8[f] = (int8_t)tag;
     }
-#pragma unroll
-    for (int t = 1; t <= 6; ++t) cnt.vote(tag == t, t - 1);
-    cnt.vote(owner_first && zden, 6);   // PHIFEM_CNT_FACET_ZERO_DEN
-    cnt.vote(conflict, 7);              // PHIFEM_CNT_FACET_CONFLICT
-    cnt.vote(owner_first, 8);           // slot 13: number of cells owning a mesh-boundary facet
   }
-  cnt.flush(counters, PHIFEM_CNT_FACET_TAG1, 9);
+  cnt.add(n_zden, 0);
+  cnt.add(n_conflict, 1);
+  cnt.add(n_owner, 2);
+  cnt.flush(counters, PHIFEM_CNT_FACET_ZERO_DEN, 3);
 }
 
 // ---- candidate records of the one-sided measures (mesh_scripts.py:137-192) -------------------------
@@ -469,8 +580,8 @@ int check_levelset(const phifem_mesh* m, const phifem_levelset* ls, bool facets)
     PHIFEM_CHECK_ARG(ls->coeffs != nullptr, "levelset.coeffs is null");
     PHIFEM_CHECK_ARG(ls->n_dofs_per_cell >= 1 && ls->n_dofs_per_cell <= kMaxDofs,
                      "levelset.n_dofs_per_cell out of range");
-    PHIFEM_CHECK_ARG(facets ? ls->facet_table != nullptr : ls->cell_table != nullptr,
-                     "levelset basis table is null");
+    // a null cell_table selects the P1 vertex-dof kernel (checked again by the caller)
+    PHIFEM_CHECK_ARG(!facets || ls->facet_table != nullptr, "levelset.facet_table is null");
   } else if (ls->mode == 1) {
     PHIFEM_CHECK_ARG(facets ? ls->facet_values != nullptr : ls->cell_values != nullptr,
                      "levelset point values are null");
@@ -519,12 +630,15 @@ extern "C" int phifem_tag_cells(const phifem_mesh* mesh, const phifem_levelset* 
   if (p1) {
     const bool have_bounds = mesh->detj_min >= 1e-150 && mesh->detj_max <= 1e150 &&
                              mesh->detj_min <= mesh->detj_max;
+    const int64_t tiles = (mesh->n_cells + kBlock * kUnroll - 1) / (kBlock * kUnroll);
     if (ct == PHIFEM_TRIANGLE)
-      k_tag_cells_p1<PHIFEM_TRIANGLE><<<grid, kBlock, 0, st>>>(*mesh, ls->coeffs, have_bounds, cell_tags,
-                                                              cell_tags8, counters);
+      k_tag_cells_p1<PHIFEM_TRIANGLE><<<persistent_grid(k_tag_cells_p1<PHIFEM_TRIANGLE>, kBlock, tiles),
+                                        kBlock, 0, st>>>(*mesh, ls->coeffs, have_bounds, cell_tags,
+                                                         cell_tags8, counters);
     else
-      k_tag_cells_p1<PHIFEM_TETRAHEDRON><<<grid, kBlock, 0, st>>>(*mesh, ls->coeffs, have_bounds,
-                                                                 cell_tags, cell_tags8, counters);
+      k_tag_cells_p1<PHIFEM_TETRAHEDRON><<<persistent_grid(k_tag_cells_p1<PHIFEM_TETRAHEDRON>, kBlock, tiles),
+                                           kBlock, 0, st>>>(*mesh, ls->coeffs, have_bounds, cell_tags,
+                                                            cell_tags8, counters);
   } else {
     PHIFEM_CHECK_ARG(ls->mode != 0 || ls->cell_table != nullptr, "levelset.cell_table is null");
     dispatch_cell_type(ct, [&](auto c) {
@@ -551,10 +665,25 @@ extern "C" int phifem_tag_facets(const phifem_mesh* mesh, const phifem_levelset*
   if (int rc = check_levelset(mesh, ls, true)) return rc;
   PHIFEM_CHECK_ARG(cell_tags8 && facet_tags && facet_tags8 && counters, "null pointer");
   if (mesh->n_facets == 0) return PHIFEM_OK;
-  const int grid = grid_for(mesh->n_facets, kBlock, 8);
+  const int64_t tiles = (mesh->n_facets + kBlock * kUnroll - 1) / (kBlock * kUnroll);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool two_pass = mesh->boundary_facets != nullptr;
   dispatch_cell_type(mesh->cell_type, [&](auto c) {
-    k_tag_facets<decltype(c)::value><<<grid, kBlock, 0, (cudaStream_t)stream>>>(
-        *mesh, *ls, cell_tags8, facet_tags, facet_tags8, counters);
+    constexpr int CT = decltype(c)::value;
+    if (two_pass) {
+      const int grid = persistent_grid(k_tag_facets<CT, false>, kBlock, tiles);
+      k_tag_facets<CT, false><<<grid, kBlock, 0, st>>>(*mesh, *ls, cell_tags8, facet_tags, facet_tags8,
+                                                       counters);
+      if (mesh->n_boundary_facets > 0) {
+        const int g2 = (int)((mesh->n_boundary_facets + kBlock - 1) / kBlock);
+        k_tag_boundary_facets<CT><<<g2, kBlock, 0, st>>>(*mesh, *ls, cell_tags8, facet_tags, facet_tags8,
+                                                         counters);
+      }
+    } else {
+      const int grid = persistent_grid(k_tag_facets<CT, true>, kBlock, tiles);
+      k_tag_facets<CT, true><<<grid, kBlock, 0, st>>>(*mesh, *ls, cell_tags8, facet_tags, facet_tags8,
+                                                      counters);
+    }
   });
   PHIFEM_CHECK_LAUNCH();
   return PHIFEM_OK;

@@ -164,6 +164,13 @@ class Mesh:
     def num_facets(self):
         return int(self.f2c.shape[0])
 
+    @property
+    def boundary_facets(self):
+        """Facets with a single cell (ascending int32 list), cached: a property of the mesh."""
+        if "bfacets" not in self._host:
+            self._host["bfacets"] = torch.nonzero(self.f2c[:, 1] < 0).reshape(-1).to(torch.int32).contiguous()
+        return self._host["bfacets"]
+
     def detj_bounds(self):
         """(min, max) of |det J| over the simplices of the mesh, cached.  A property of the mesh
         alone: lets the P1 classifier decide uncut cells from the signs of phi without gathering

@@ -182,13 +182,13 @@ def _overwrite_tags(mesh, tags_to_overwrite, new_tags):
     return MeshTags(mesh, tags_to_overwrite.dim, dense)
 
 
-def _check_debug(counters):
+def _check_debug(counters, facet_tags8):
     """MODE=debug assertions of reference :360-374 and :499-521 that apply to dense tag arrays."""
     if counters[_lib.CNT_INTERIOR] == 0:
         raise ValueError("No interior cells (1)!")
     if counters[_lib.CNT_CUT] == 0:
         print("WARNING: no cut cells computed in the partition.")
-    ft = counters[_lib.CNT_FACET_TAG1:_lib.CNT_FACET_TAG1 + 6]
+    ft = torch.bincount(facet_tags8.to(torch.int64), minlength=7)[1:7].cpu().numpy()
     if ft[0] == 0:
         raise ValueError("No interior facets (1)!")
     if ft[1] == 0:
@@ -222,7 +222,7 @@ def compute_tags_measures(mesh, discrete_levelset, detection_degree, box_mode=Fa
         # reference warns here on essentially every mesh
         warnings.warn(_ZERO_WARNING, RuntimeWarning)
     if debug_mode:
-        _check_debug(counters)
+        _check_debug(counters, ws.facet_tags8)
     cells_tags, facets_tags = _tags_from_workspace(mesh, ws)
     cell_tags8, facet_tags8 = ws.cell_tags8, ws.facet_tags8
 

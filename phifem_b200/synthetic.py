@@ -36,14 +36,19 @@ def rectangle_mesh(n, lo=(-1.0, -1.0), hi=(1.0, 1.0), device=None):
 
 
 def box_mesh(n, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0), device=None):
-    """6 n^3 Kuhn tetrahedra: each cube is split along the 6 monotone edge paths from its low
-    corner to its high corner; vertex id = (i*(n+1)+j)*(n+1)+k."""
+    """6 nx ny nz Kuhn tetrahedra (n = int or (nx, ny, nz)): each cube is split along the 6 monotone
+    edge paths from its low corner to its high corner; vertex id = (i*(ny+1)+j)*(nz+1)+k; the 6
+    tetrahedra of a cube are consecutive and cubes are ordered x-major."""
     device = torch.device(device) if device is not None else default_device()
-    x = _grid_vertices(lo, hi, n, device)
-    i = torch.arange(n, device=device, dtype=torch.int64)
-    I, J, K = torch.meshgrid(i, i, i, indexing="ij")
-    base = ((I * (n + 1) + J) * (n + 1) + K).reshape(-1)
-    stride = [(n + 1) * (n + 1), n + 1, 1]
+    nx, ny, nz = (n, n, n) if isinstance(n, int) else n
+    axes = [torch.linspace(float(a), float(b), m + 1, dtype=torch.float64, device=device)
+            for a, b, m in zip(lo, hi, (nx, ny, nz))]
+    grids = torch.meshgrid(*axes, indexing="ij")
+    x = torch.stack([g.reshape(-1) for g in grids], dim=1).contiguous()
+    I, J, K = torch.meshgrid(*[torch.arange(m, device=device, dtype=torch.int64) for m in (nx, ny, nz)],
+                             indexing="ij")
+    base = ((I * (ny + 1) + J) * (nz + 1) + K).reshape(-1)
+    stride = [(ny + 1) * (nz + 1), nz + 1, 1]
     tets = []
     for perm in itertools.permutations(range(3)):
         offs, acc = [0], 0

@@ -29,7 +29,7 @@ def test_argument_errors_do_not_need_a_gpu():
     lib = _lib.load()
     rc = lib.phifem_tag_cells(None, None, 0, None, None, None, None, None)
     assert rc == -1 and b"mesh" in lib.phifem_last_error()
-    m = _lib.CMesh(7, 2, 0, 0, 0, 1, 1, 1, 1, 0.0, 0.0)
+    m = _lib.CMesh(7, 2, 0, 0, 0, 1, 1, 1, 1, 0.0, 0.0, None, 0)
     ls = _lib.CLevelset()
     rc = lib.phifem_tag_cells(ctypes.byref(m), ctypes.byref(ls), 0, 1, 1, None, 1, None)
     assert rc == -3 and b"unsupported cell type" in lib.phifem_last_error()
