@@ -219,7 +219,7 @@ def run_ours(args):
     ctags, ftags = MeshTags(mesh, tdim, ws.cell_tags), MeshTags(mesh, tdim - 1, ws.facet_tags)
     ctags.tags8, ftags.tags8 = ws.cell_tags8, ws.facet_tags8
     ents = mesh_scripts._integration_entities_dev(mesh, ws.cell_tags8, ws.facet_tags8, 4, (1, 2))
-    plan = assemble.build_plan(mesh, ctags, ftags, ents)
+    plan = assemble.build_plan(mesh, ctags, ftags, ents, method=args.scatter, capacity=args.capacity)
     if problem is not None:
         problem.attach_plan(plan)
     torch.cuda.synchronize()
@@ -365,7 +365,13 @@ def run_ours(args):
                                         "exchange" if world > 1 else "single GPU",
                            "timed": "tag kernels + zeroing + assembly kernels; symbolic phase excluded"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-                "gpu_launches": 5 * args.steps, "symbolic_ms": symbolic_ms, "topology_s": topo_s}
+                "gpu_launches": (4 if plan.method == "blocked" else 6) * args.steps,
+                "symbolic_ms": symbolic_ms, "topology_s": topo_s,
+                "scatter": {"method": plan.method,
+                            **({"blocks": plan.blocked.n_blocks, "capacity": plan.blocked.capacity,
+                                "bin_shape": plan.blocked.bin_shape,
+                                "recompute_factor": plan.blocked.redundancy,
+                                "plan_bytes": plan.blocked.index_bytes()} if plan.blocked else {})}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -379,6 +385,9 @@ def main():
     ap.add_argument("--n", type=int, default=204, help="cubes per edge (6 n^3 tetrahedra per GPU)")
     ap.add_argument("--cpu-n", type=int, default=80, help="size of the bounded CPU sample")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scatter", default="blocked", choices=["blocked", "atomic"],
+                    help="assembly scatter strategy (owner-computes blocks / fp64 reductions)")
+    ap.add_argument("--capacity", type=int, default=None, help="contributions per block (blocked scatter)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     args = ap.parse_args()

@@ -144,6 +144,45 @@ int phifem_assemble_ghost_p1(const phifem_mesh* mesh, const double* phi, const i
                              int64_t n_facets, const int32_t* slots, double sigma, double* data,
                              void* stream);
 
+/* ---- owner-computes assembly (no atomics, no zero-fill, bitwise reproducible) ---------------------
+ * Rows are grouped into spatially compact blocks; one CTA per block evaluates every cell / ghost facet /
+ * one-sided entity touching the block's rows (an entity is listed once per block it touches: an
+ * "instance"), parks each entry whose row the block owns in shared memory at a precomputed position,
+ * then one thread per CSR entry (or load-vector row) sums its contiguous segment and stores it.
+ * All arrays are built by the symbolic phase (phifem_b200/blocked.py). */
+#define PHIFEM_BLOCK_DESC_INTS 12
+typedef struct phifem_blocked_plan {
+  int32_t n_blocks;
+  int32_t capacity;            /* max contributions of any block = shared-memory doubles, <= 32767 */
+  int32_t max_segments;        /* max padded segment count of any block (multiple of 8) */
+  int32_t reserved;
+  const int32_t* block_desc;   /* [n_blocks, 12]: n_contrib, seg_begin (multiple of 8), n_seg_padded
+                                  (multiple of 8, > number of segments), cell_begin, cell_end,
+                                  ghost_begin, ghost_end, bnd_begin, bnd_end, 0, 0, 0 */
+  const int16_t* seg_start;    /* per block, at seg_begin: first buffer position of each segment
+                                  (block-local), then pad entries equal to n_contrib */
+  const int32_t* seg_dest;     /* same indexing: >= 0: CSR slot in `data`; < 0: row (dest & 0x7fffffff)
+                                  of b; pads: 0 */
+  int64_t n_cell_inst;
+  const int32_t* cell_verts;   /* [n_cell_inst, 4] vertex ids (triangles: 4th unused); sign bit of the
+                                  first id = cell is cut (tag 2) */
+  const int16_t* cell_pos;     /* column-major words: entry e of instance i is the int16 at
+                                  ((e/2) * n_cell_inst + i) * 2 + e%2; entries: nv*nv matrix (row-major,
+                                  row = test) then nv load-vector entries; < 0 = row not owned */
+  int64_t n_ghost_inst;
+  const int32_t* ghost_facet;  /* [n_ghost_inst] facet id */
+  const int16_t* ghost_pos;    /* same layout, (2nv)^2 entries over [cell+ vertices, cell- vertices] */
+  int64_t n_bnd_inst;
+  const int32_t* bnd_entity;   /* [n_bnd_inst, 2] (cell, local facet) */
+  const int16_t* bnd_pos;      /* same layout, nv*nv entries */
+} phifem_blocked_plan;
+
+/* Replaces phifem_assemble_{cells,boundary,ghost}_p1 in one launch; `data` and `b` need NOT be zeroed
+ * (every CSR entry of the pattern and every active row of b is written exactly once; rows of b without
+ * contributions are left untouched). */
+int phifem_assemble_blocked_p1(const phifem_mesh* mesh, const double* phi, const double* f, double sigma,
+                               const phifem_blocked_plan* plan, double* data, double* b, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

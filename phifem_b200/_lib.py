@@ -35,6 +35,15 @@ class CLevelset(ctypes.Structure):
                 ("cell_values", _vp), ("facet_values", _vp), ("coord_grad", _vp)]
 
 
+class CBlockedPlan(ctypes.Structure):
+    _fields_ = [("n_blocks", ctypes.c_int32), ("capacity", ctypes.c_int32),
+                ("max_segments", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("block_desc", _vp), ("seg_start", _vp), ("seg_dest", _vp),
+                ("n_cell_inst", ctypes.c_int64), ("cell_verts", _vp), ("cell_pos", _vp),
+                ("n_ghost_inst", ctypes.c_int64), ("ghost_facet", _vp), ("ghost_pos", _vp),
+                ("n_bnd_inst", ctypes.c_int64), ("bnd_entity", _vp), ("bnd_pos", _vp)]
+
+
 _SIGNATURES = {
     "phifem_last_error": (ctypes.c_char_p, []),
     "phifem_abi_version": (ctypes.c_int, []),
@@ -51,6 +60,8 @@ _SIGNATURES = {
                                                    _vp, _vp, _vp]),
     "phifem_assemble_ghost_p1": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, ctypes.c_int64, _vp,
                                                 ctypes.c_double, _vp, _vp]),
+    "phifem_assemble_blocked_p1": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, ctypes.c_double,
+                                                  ctypes.POINTER(CBlockedPlan), _vp, _vp, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -34,9 +34,13 @@ class CSRMatrix:
 
 
 class AssemblyPlan:
-    """Tag-dependent symbolic data of one operator (reused for every assembly with the same tags)."""
+    """Tag-dependent symbolic data of one operator (reused for every assembly with the same tags).
 
-    def __init__(self, mesh, cell_tags8, facet_tags8, entities):
+    method = "blocked": owner-computes kernel (no atomics; phifem_b200/blocked.py), the default;
+    method = "atomic" : fp64 reductions through the slot maps (also the fall-back when a row gathers more
+    contributions than a shared-memory block can hold)."""
+
+    def __init__(self, mesh, cell_tags8, facet_tags8, entities, method="blocked", capacity=None):
         if mesh.cell_type not in ("triangle", "tetrahedron"):
             raise NotImplementedError("P1 assembly supports triangles and tetrahedra")
         dev = mesh.device
@@ -76,6 +80,16 @@ class AssemblyPlan:
         self.indptr[1:] = torch.cumsum(counts, dim=0)
         self.indptr = self.indptr.to(torch.int32).contiguous()
         self.nnz = int(uniq.numel())
+        self.blocked, self.method = None, "atomic"
+        if method == "blocked" and self.active.numel() > 0:
+            from . import blocked
+            try:
+                self.blocked = blocked.BlockedPlan(self, capacity or blocked.DEFAULT_CAPACITY)
+                self.method = "blocked"
+            except NotImplementedError:
+                self.blocked = None
+        elif method not in ("blocked", "atomic"):
+            raise ValueError("method must be 'blocked' or 'atomic'")
 
     def new_outputs(self):
         dev = self.mesh.device
@@ -83,7 +97,7 @@ class AssemblyPlan:
                 torch.zeros(self.n_rows, dtype=torch.float64, device=dev))
 
 
-def build_plan(mesh, cells_tags, facets_tags, ds=None):
+def build_plan(mesh, cells_tags, facets_tags, ds=None, method="blocked", capacity=None):
     """Symbolic phase for `a` and `L` of the strong-Dirichlet demo.  `ds` is what the demo passes as
     `ds_bdy(100)` (main.py:64): a MeasureRestriction, a flat entity array, or None (no boundary term)."""
     c8 = getattr(cells_tags, "tags8", None)
@@ -98,7 +112,7 @@ def build_plan(mesh, cells_tags, facets_tags, ds=None):
         ents = ds.to(mesh.device)
     else:
         ents = torch.as_tensor(np.asarray(ds, dtype=np.int32), device=mesh.device)
-    return AssemblyPlan(mesh, c8.contiguous(), f8.contiguous(), ents)
+    return AssemblyPlan(mesh, c8.contiguous(), f8.contiguous(), ents, method=method, capacity=capacity)
 
 
 def _device_vector(mesh, v):
@@ -119,6 +133,14 @@ def assemble_into(plan, phi, f, sigma, data, b, marks=None):
     invoked after the zeroing and after each kernel (bench.py records CUDA events there)."""
     marks = marks or (lambda: None)
     _lib.require_cuda(plan.mesh)
+    if getattr(plan, "blocked", None) is not None:
+        from . import blocked
+        marks()
+        blocked.assemble_blocked_into(plan.blocked, phi, f, sigma, data, b)
+        marks()
+        marks()
+        marks()
+        return data, b
     lib = _lib.load()
     cm = _lib.c_mesh(plan.mesh)
     st = _lib.stream()

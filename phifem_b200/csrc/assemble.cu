@@ -3,9 +3,20 @@
 // Forms of reference demo/strong-dirichlet/flower/main.py:104-128; closed-form element tensors of
 // SURVEY.md Appendix B (exact for P1 phi, P1 w/v, P1 f), so the kernels stay near the fp64/HBM
 // ridge instead of looping over quadrature points.  What dolfinx does per entity with one FFCx
-// `tabulate_tensor` call plus a `MatSetValuesLocal(ADD_VALUES)` binary search is one thread here:
-// gather geometry + phi + f, evaluate the tensor in registers, scatter through a precomputed
-// cell -> CSR-slot map with fp64 reductions (REDG.E.ADD.F64) that resolve in L2.
+// `tabulate_tensor` call plus a `MatSetValuesLocal(ADD_VALUES)` binary search is one thread here.
+//
+// Two scatter strategies share the same element math (the `emit` functors below):
+//   * atomic   -- one thread per entity, fp64 reductions (REDG.E.ADD.F64) through a precomputed
+//                 entity -> CSR-slot map.  Simple, but ~8 reductions land on every CSR entry and the
+//                 SM issues < 1 reduction lane per clock: 410 M reductions = 2.5 ms at 50.9 M tets.
+//   * blocked  -- owner-computes.  Rows are grouped into spatially compact blocks; one CTA per block
+//                 evaluates every entity touching its rows (halo entities are recomputed by each
+//                 block they touch), drops each contribution into a shared-memory buffer at a position
+//                 precomputed so that contributions to the same CSR entry are adjacent, then one
+//                 thread per CSR entry sums its segment and stores it.  No atomics, no zero-fill, plain
+//                 coalesced row stores, bitwise reproducible.
+#include <cuda_pipeline.h>
+
 #include "common.cuh"
 
 namespace phifem {
@@ -14,12 +25,12 @@ namespace {
 constexpr int kBlock = 128;
 
 template <int D>
-struct Simplex {
-  double G[D + 1][D];  // grad(lambda_i)
-  double vol;          // |K|
-  double p[D + 1];     // phi at the vertices
-  int v[D + 1];
-};
+__device__ __forceinline__ void load_xc(const phifem_mesh& m, const int (&v)[D + 1], double (&xc)[D + 1][D]) {
+#pragma unroll
+  for (int k = 0; k <= D; ++k)
+#pragma unroll
+    for (int d = 0; d < D; ++d) xc[k][d] = __ldg(m.x + (int64_t)v[k] * D + d);
+}
 
 template <int D>
 __device__ __forceinline__ void load_vertices(const phifem_mesh& m, int64_t c, int (&v)[D + 1],
@@ -31,10 +42,7 @@ __device__ __forceinline__ void load_vertices(const phifem_mesh& m, int64_t c, i
 #pragma unroll
     for (int k = 0; k <= D; ++k) v[k] = __ldg(m.cells + c * (D + 1) + k);
   }
-#pragma unroll
-  for (int k = 0; k <= D; ++k)
-#pragma unroll
-    for (int d = 0; d < D; ++d) xc[k][d] = __ldg(m.x + (int64_t)v[k] * D + d);
+  load_xc<D>(m, v, xc);
 }
 
 template <int D>
@@ -104,37 +112,14 @@ __device__ __forceinline__ double dot(const double (&a)[D], const double (&b)[D]
   return s;
 }
 
-// ---- K2 + K4: cells of dx((1,2)) and dx(2) -----------------------------------------------------------
-template <int D>
-__global__ void __launch_bounds__(kBlock) k_assemble_cells_p1(
-    phifem_mesh m, const double* __restrict__ phi, const double* __restrict__ f,
-    const int8_t* __restrict__ ctags, const int32_t* __restrict__ active, int64_t n_active,
-    const int32_t* __restrict__ slots, double sigma, double* __restrict__ data, double* __restrict__ b) {
+// ---- element tensors; `emit.mat(i, j, value)` / `emit.vec(i, value)` receive the entries -------------
+
+// dx((1,2)) stiffness + dx(2) stabilisation (main.py:105,107-112), load vector (:126-128)
+template <int D, typename Emit>
+__device__ __forceinline__ void cell_tensor(const double (&xc)[D + 1][D], const double (&p)[D + 1],
+                                            const double (&fv)[D + 1], bool is_cut, double sigma,
+                                            Emit& emit) {
   constexpr int NV = D + 1;
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_active) return;
-  const int64_t c = __ldg(active + e);
-  int v[NV];
-  double xc[NV][D];
-  load_vertices<D>(m, c, v, xc);
-  double p[NV], fv[NV];
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    p[k] = __ldg(phi + v[k]);
-    fv[k] = __ldg(f + v[k]);
-  }
-  // slot loads issued early: they do not depend on the arithmetic below
-  int sl[NV * NV];
-  if (NV * NV % 4 == 0) {
-#pragma unroll
-    for (int q = 0; q < NV * NV / 4; ++q) {
-      const int4 s4 = __ldg(reinterpret_cast<const int4*>(slots + e * NV * NV) + q);
-      sl[4 * q] = s4.x; sl[4 * q + 1] = s4.y; sl[4 * q + 2] = s4.z; sl[4 * q + 3] = s4.w;
-    }
-  } else {
-#pragma unroll
-    for (int q = 0; q < NV * NV; ++q) sl[q] = __ldg(slots + e * NV * NV + q);
-  }
   double G[NV][D], vol;
   gradients<D>(xc, G, vol);
   double g[D];
@@ -164,7 +149,7 @@ __global__ void __launch_bounds__(kBlock) k_assemble_cells_p1(
     mu += p[i] * mm[i];
   }
   double stab = 0.0;
-  if (ctags[c] == 2) stab = sigma * diameter2<D>(xc) * vol;  // sigma h_T^2 |K| on cut cells
+  if (is_cut) stab = sigma * diameter2<D>(xc) * vol;  // sigma h_T^2 |K| on cut cells
   const double ggM = gg * cM, stab4 = 4.0 * stab;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -172,40 +157,27 @@ __global__ void __launch_bounds__(kBlock) k_assemble_cells_p1(
     for (int j = i; j < NV; ++j) {
       const double val = ggM * (i == j ? 2.0 : 1.0) + a[i] * mm[j] + mm[i] * a[j] +
                          dot<D>(G[i], G[j]) * mu + stab4 * a[i] * a[j];
-      atomicAdd(data + sl[i * NV + j], val);
-      if (j != i) atomicAdd(data + sl[j * NV + i], val);
+      emit.mat(i, j, val);
+      if (j != i) emit.mat(j, i, val);
     }
   }
   constexpr double fact_d = D == 2 ? 2.0 : 6.0, fact_d3 = D == 2 ? 120.0 : 720.0;
   const double c3 = vol * (fact_d / fact_d3);
   const double fmean2 = 2.0 * stab * F * (1.0 / NV);
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const double bi = c3 * ((F * P + FP) + fv[i] * P + F * p[i] + 2.0 * fv[i] * p[i]) - fmean2 * a[i];
-    atomicAdd(b + v[i], bi);
-  }
+  for (int i = 0; i < NV; ++i)
+    emit.vec(i, c3 * ((F * P + FP) + fv[i] * P + F * p[i] + 2.0 * fv[i] * p[i]) - fmean2 * a[i]);
 }
 
 __device__ __forceinline__ double alpha3(int a, int b, int c) {
   return (double)((1 + (a == b)) * (1 + (a == c) + (b == c)));
 }
 
-// ---- one-sided boundary term over ds(100) entities ----------------------------------------------------
-template <int D>
-__global__ void __launch_bounds__(kBlock) k_assemble_boundary_p1(
-    phifem_mesh m, const double* __restrict__ phi, const int32_t* __restrict__ entities,
-    int64_t n_entities, const int32_t* __restrict__ slots, double* __restrict__ data) {
+// -int_F (grad(phi w).n) phi v on local facet o of a cell (main.py:106), row = test
+template <int D, typename Emit>
+__device__ __forceinline__ void boundary_tensor(const double (&xc)[D + 1][D], const double (&p)[D + 1],
+                                                int o, Emit& emit) {
   constexpr int NV = D + 1;
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_entities) return;
-  const int64_t c = __ldg(entities + 2 * e);
-  const int o = __ldg(entities + 2 * e + 1);
-  int v[NV];
-  double xc[NV][D];
-  load_vertices<D>(m, c, v, xc);
-  double p[NV];
-#pragma unroll
-  for (int k = 0; k < NV; ++k) p[k] = __ldg(phi + v[k]);
   double G[NV][D], vol;
   gradients<D>(xc, G, vol);
   double Go[D];
@@ -244,21 +216,16 @@ __global__ void __launch_bounds__(kBlock) k_assemble_boundary_p1(
         const double tjki = (j != o) ? alpha3(j, k, i) : 0.0;
         acc += p[k] * (gn * tjki + Gnj * s);
       }
-      const double val = (i == o) ? 0.0 : -cF * acc;
-      atomicAdd(data + __ldg(slots + e * NV * NV + i * NV + j), val);
+      emit.mat(i, j, (i == o) ? 0.0 : -cF * acc);
     }
   }
 }
 
-// ---- K3: ghost penalty over interior facets tagged 2 / 3 ------------------------------------------------
-template <int D>
-__global__ void __launch_bounds__(kBlock) k_assemble_ghost_p1(
-    phifem_mesh m, const double* __restrict__ phi, const int32_t* __restrict__ facets, int64_t n_facets,
-    const int32_t* __restrict__ slots, double sigma, double* __restrict__ data) {
+// sigma avg(h_T) int_F jump.jump (main.py:113-118) over macro dofs [cell+ vertices, cell- vertices]
+template <int D, typename Emit>
+__device__ __forceinline__ void ghost_tensor(const phifem_mesh& m, const double* __restrict__ phi,
+                                             int32_t fct, double sigma, Emit& emit) {
   constexpr int NV = D + 1, NM = 2 * NV;
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_facets) return;
-  const int32_t fct = __ldg(facets + e);
   const int2 cc = __ldg(reinterpret_cast<const int2*>(m.f2c) + fct);
   int fvert[D];            // global vertices of the facet, ordered as in cell +
   double Jv[NM][D];        // jump integrand of macro dof a at facet vertex k (affine on the facet)
@@ -335,9 +302,229 @@ __global__ void __launch_bounds__(kBlock) k_assemble_ghost_p1(
 #pragma unroll
       for (int k = 0; k < D; ++k) s += Jv[a][k] * Jv[bb][k];
       const double val = coef * s;
-      atomicAdd(data + __ldg(slots + e * NM * NM + a * NM + bb), val);
-      if (bb != a) atomicAdd(data + __ldg(slots + e * NM * NM + bb * NM + a), val);
+      emit.mat(a, bb, val);
+      if (bb != a) emit.mat(bb, a, val);
     }
+  }
+}
+
+// ---- scatter strategy 1: fp64 reductions through an entity -> CSR-slot map -------------------------------
+template <int N>
+struct AtomicEmit {
+  double* data;
+  double* b;
+  const int32_t* slots;  // [N*N] of this entity
+  const int* verts;
+  __device__ __forceinline__ void mat(int i, int j, double v) const { atomicAdd(data + __ldg(slots + i * N + j), v); }
+  __device__ __forceinline__ void vec(int i, double v) const { atomicAdd(b + verts[i], v); }
+};
+
+template <int D>
+__global__ void __launch_bounds__(kBlock) k_assemble_cells_p1(
+    phifem_mesh m, const double* __restrict__ phi, const double* __restrict__ f,
+    const int8_t* __restrict__ ctags, const int32_t* __restrict__ active, int64_t n_active,
+    const int32_t* __restrict__ slots, double sigma, double* __restrict__ data, double* __restrict__ b) {
+  constexpr int NV = D + 1;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_active) return;
+  const int64_t c = __ldg(active + e);
+  int v[NV];
+  double xc[NV][D];
+  load_vertices<D>(m, c, v, xc);
+  double p[NV], fv[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    p[k] = __ldg(phi + v[k]);
+    fv[k] = __ldg(f + v[k]);
+  }
+  AtomicEmit<NV> emit{data, b, slots + e * NV * NV, v};
+  cell_tensor<D>(xc, p, fv, ctags[c] == 2, sigma, emit);
+}
+
+template <int D>
+__global__ void __launch_bounds__(kBlock) k_assemble_boundary_p1(
+    phifem_mesh m, const double* __restrict__ phi, const int32_t* __restrict__ entities,
+    int64_t n_entities, const int32_t* __restrict__ slots, double* __restrict__ data) {
+  constexpr int NV = D + 1;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_entities) return;
+  const int64_t c = __ldg(entities + 2 * e);
+  const int o = __ldg(entities + 2 * e + 1);
+  int v[NV];
+  double xc[NV][D];
+  load_vertices<D>(m, c, v, xc);
+  double p[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) p[k] = __ldg(phi + v[k]);
+  AtomicEmit<NV> emit{data, nullptr, slots + e * NV * NV, v};
+  boundary_tensor<D>(xc, p, o, emit);
+}
+
+template <int D>
+__global__ void __launch_bounds__(kBlock) k_assemble_ghost_p1(
+    phifem_mesh m, const double* __restrict__ phi, const int32_t* __restrict__ facets, int64_t n_facets,
+    const int32_t* __restrict__ slots, double sigma, double* __restrict__ data) {
+  constexpr int NM = 2 * (D + 1);
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_facets) return;
+  AtomicEmit<NM> emit{data, nullptr, slots + e * NM * NM, nullptr};
+  ghost_tensor<D>(m, phi, __ldg(facets + e), sigma, emit);
+}
+
+// ---- scatter strategy 2: owner-computes row blocks, shared-memory segmented reduction -----------------------
+constexpr int kBlockedThreads = 512;   // one CTA per SM with the full shared-memory buffer
+constexpr int kBlockedThreadsHalf = 256;  // two co-resident CTAs per SM with half-size buffers
+
+// positions are int16 pairs packed in 32-bit words, column-major over the instances of a kind:
+// word q of instance i at pos[q * n_instances + i]; entry e sits in word e/2, half e%2; < 0 = not ours
+template <int NWORDS>
+struct BufferEmit {
+  double* buf;
+  int nmat;      // entries per row of the local tensor (mat(i,j) -> entry i*nmat+j)
+  int vec_base;  // first entry of the vector part
+  unsigned int w[NWORDS];
+  __device__ __forceinline__ void put(int e, double v) const {
+    const int pos = (int)(short)(w[e >> 1] >> (16 * (e & 1)));
+    if (pos >= 0) buf[pos] = v;
+  }
+  __device__ __forceinline__ void mat(int i, int j, double v) const { put(i * nmat + j, v); }
+  __device__ __forceinline__ void vec(int i, double v) const { put(vec_base + i, v); }
+};
+
+struct BlockDesc {
+  int n_contrib, s_begin, n_seg_pad, c_begin, c_end, g_begin, g_end, b_begin, b_end;
+};
+__device__ __forceinline__ BlockDesc load_desc(const phifem_blocked_plan& pl, int blk) {
+  const int4* p = reinterpret_cast<const int4*>(pl.block_desc + (int64_t)blk * PHIFEM_BLOCK_DESC_INTS);
+  const int4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+  return BlockDesc{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x};
+}
+
+template <int CW>
+struct CellRecord {
+  unsigned int w[CW];
+  int4 v;
+};
+template <int CW>
+__device__ __forceinline__ void load_record(const phifem_blocked_plan& pl, int i, CellRecord<CW>& r) {
+#pragma unroll
+  for (int q = 0; q < CW; ++q)
+    r.w[q] = __ldg(reinterpret_cast<const unsigned int*>(pl.cell_pos) + (int64_t)q * pl.n_cell_inst + i);
+  r.v = __ldg(reinterpret_cast<const int4*>(pl.cell_verts) + i);
+}
+
+// Latency plan (16 warps per SM is all the register file allows for the fp64 element math):
+//  * the instance record a thread needs next -- also across the block boundary -- is loaded into
+//    registers before the current instance is evaluated, so only the L2-resident vertex gathers sit
+//    on the critical path of phase 1;
+//  * the segment tables of the block are copied global -> shared with cp.async (LDGSTS) while
+//    phase 1 runs, so phase 2 touches shared memory only, with 4 loads in flight per thread.
+template <int D, int THREADS>
+__global__ void __launch_bounds__(THREADS, kBlockedThreads / THREADS) k_assemble_blocked_p1(
+    phifem_mesh m, const double* __restrict__ phi, const double* __restrict__ f, double sigma,
+    phifem_blocked_plan pl, double* __restrict__ data, double* __restrict__ b) {
+  constexpr int NV = D + 1, NM = 2 * NV;
+  constexpr int CW = (NV * NV + NV + 1) / 2, GW = (NM * NM + 1) / 2, BW = (NV * NV + 1) / 2;
+  extern __shared__ __align__(16) double buf[];
+  int32_t* s_dest = reinterpret_cast<int32_t*>(buf + ((pl.capacity + 1) & ~1));
+  int16_t* s_start = reinterpret_cast<int16_t*>(s_dest + pl.max_segments);
+  const int tid = threadIdx.x;
+  int blk = blockIdx.x;
+  if (blk >= pl.n_blocks) return;
+  BlockDesc d = load_desc(pl, blk);
+  CellRecord<CW> cur;
+  int have = -1;  // instance whose record sits in `cur`
+  if (d.c_begin + tid < d.c_end) {
+    have = d.c_begin + tid;
+    load_record<CW>(pl, have, cur);
+  }
+  for (; blk < pl.n_blocks; blk += gridDim.x) {
+    const bool more = blk + (int)gridDim.x < pl.n_blocks;
+    BlockDesc nd = d;
+    if (more) nd = load_desc(pl, blk + gridDim.x);
+    // stage this block's segment tables (16-byte chunks; ranges are padded to 8 entries by the plan)
+    {
+      const int4* g_start = reinterpret_cast<const int4*>(pl.seg_start + d.s_begin);
+      const int4* g_dest = reinterpret_cast<const int4*>(pl.seg_dest + d.s_begin);
+      for (int q = tid; q < d.n_seg_pad / 8; q += THREADS)
+        __pipeline_memcpy_async(reinterpret_cast<int4*>(s_start) + q, g_start + q, 16);
+      for (int q = tid; q < d.n_seg_pad / 4; q += THREADS)
+        __pipeline_memcpy_async(reinterpret_cast<int4*>(s_dest) + q, g_dest + q, 16);
+      __pipeline_commit();
+    }
+    // phase 1: evaluate every entity touching the block's rows, park the entries we own in shared memory
+    for (int i = d.c_begin + tid; i < d.c_end;) {
+      BufferEmit<CW> emit{buf, NV, NV * NV};
+#pragma unroll
+      for (int q = 0; q < CW; ++q) emit.w[q] = cur.w[q];
+      const int4 vq = cur.v;
+      const int ni = i + THREADS;
+      if (ni < d.c_end) {
+        have = ni;
+        load_record<CW>(pl, ni, cur);
+      } else if (more && nd.c_begin + tid < nd.c_end) {
+        have = nd.c_begin + tid;
+        load_record<CW>(pl, have, cur);
+      }
+      const bool is_cut = vq.x < 0;  // tag-2 flag rides in the sign bit of the first vertex id
+      int v[NV];
+      v[0] = vq.x & 0x7fffffff; v[1] = vq.y; v[2] = vq.z;
+      if (NV == 4) v[NV - 1] = vq.w;
+      double xc[NV][D], p[NV], fv[NV];
+      load_xc<D>(m, v, xc);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        p[k] = __ldg(phi + v[k]);
+        fv[k] = __ldg(f + v[k]);
+      }
+      cell_tensor<D>(xc, p, fv, is_cut, sigma, emit);
+      i = ni;
+    }
+    if (more && nd.c_begin + tid < nd.c_end && have != nd.c_begin + tid) {
+      have = nd.c_begin + tid;  // threads idle in this block still prefetch for the next one
+      load_record<CW>(pl, have, cur);
+    }
+    for (int i = d.g_begin + tid; i < d.g_end; i += THREADS) {
+      BufferEmit<GW> emit{buf, NM, 0};
+#pragma unroll
+      for (int q = 0; q < GW; ++q)
+        emit.w[q] = __ldg(reinterpret_cast<const unsigned int*>(pl.ghost_pos) + (int64_t)q * pl.n_ghost_inst + i);
+      ghost_tensor<D>(m, phi, __ldg(pl.ghost_facet + i), sigma, emit);
+    }
+    for (int i = d.b_begin + tid; i < d.b_end; i += THREADS) {
+      BufferEmit<BW> emit{buf, NV, 0};
+#pragma unroll
+      for (int q = 0; q < BW; ++q)
+        emit.w[q] = __ldg(reinterpret_cast<const unsigned int*>(pl.bnd_pos) + (int64_t)q * pl.n_bnd_inst + i);
+      const int64_t c = __ldg(pl.bnd_entity + 2 * (int64_t)i);
+      const int o = __ldg(pl.bnd_entity + 2 * (int64_t)i + 1);
+      int v[NV];
+      double xc[NV][D], p[NV];
+      load_vertices<D>(m, c, v, xc);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) p[k] = __ldg(phi + v[k]);
+      boundary_tensor<D>(xc, p, o, emit);
+    }
+    __pipeline_wait_prior(0);
+    __syncthreads();
+    // phase 2: one thread per CSR entry / load-vector row sums its segment in a fixed order and stores it
+    // (pad entries carry start == n_contrib, so they are empty and the last real segment ends there)
+    for (int s = tid; s < d.n_seg_pad - 1; s += THREADS) {
+      const int lo = s_start[s], hi = s_start[s + 1];
+      if (hi <= lo) continue;
+      double acc = 0.0;
+      int k = lo;
+      for (; k + 4 <= hi; k += 4) {
+        const double v0 = buf[k], v1 = buf[k + 1], v2 = buf[k + 2], v3 = buf[k + 3];
+        acc = (((acc + v0) + v1) + v2) + v3;
+      }
+      for (; k < hi; ++k) acc += buf[k];
+      const int32_t dst = s_dest[s];
+      if (dst >= 0) data[dst] = acc;
+      else b[dst & 0x7fffffff] = acc;
+    }
+    __syncthreads();
+    d = nd;
   }
 }
 
@@ -406,6 +593,48 @@ extern "C" int phifem_assemble_ghost_p1(const phifem_mesh* mesh, const double* p
     k_assemble_ghost_p1<2><<<grid, kBlock, 0, st>>>(*mesh, phi, facets, n_facets, slots, sigma, data);
   else
     k_assemble_ghost_p1<3><<<grid, kBlock, 0, st>>>(*mesh, phi, facets, n_facets, slots, sigma, data);
+  PHIFEM_CHECK_LAUNCH();
+  return PHIFEM_OK;
+}
+
+extern "C" int phifem_assemble_blocked_p1(const phifem_mesh* mesh, const double* phi, const double* f,
+                                          double sigma, const phifem_blocked_plan* plan, double* data,
+                                          double* b, void* stream) {
+  if (int rc = check_simplex_mesh(mesh)) return rc;
+  PHIFEM_CHECK_ARG(phi && f && plan && data && b, "null pointer");
+  PHIFEM_CHECK_ARG(plan->n_blocks == 0 || (plan->block_desc && plan->seg_start && plan->seg_dest),
+                   "plan arrays are null");
+  PHIFEM_CHECK_ARG(plan->n_ghost_inst == 0 || (mesh->c2f && mesh->f2c), "ghost facets need c2f / f2c");
+  PHIFEM_CHECK_ARG(plan->capacity > 0 && plan->capacity <= 32767, "plan.capacity out of range");
+  if (plan->n_blocks == 0) return PHIFEM_OK;
+  PHIFEM_CHECK_ARG(plan->max_segments > 0 && plan->max_segments % 8 == 0, "plan.max_segments");
+  const size_t smem = (size_t)((plan->capacity + 1) & ~1) * sizeof(double) +
+                      (size_t)plan->max_segments * (sizeof(int32_t) + sizeof(int16_t)) + 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, sms = kNumSMs;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // buffers up to ~110 KB: two CTAs of 256 threads share an SM (one reduces while the other computes)
+  const bool half = smem <= 110 * 1024;
+  const int per_sm = half ? 2 : 1;
+  const int grid = plan->n_blocks < sms * per_sm ? plan->n_blocks : sms * per_sm;
+  cudaError_t err = cudaSuccess;
+  auto launch = [&](auto kernel, int threads) {
+    err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err == cudaSuccess) kernel<<<grid, threads, smem, st>>>(*mesh, phi, f, sigma, *plan, data, b);
+  };
+  if (mesh->cell_type == PHIFEM_TRIANGLE) {
+    if (half) launch(k_assemble_blocked_p1<2, kBlockedThreadsHalf>, kBlockedThreadsHalf);
+    else launch(k_assemble_blocked_p1<2, kBlockedThreads>, kBlockedThreads);
+  } else {
+    if (half) launch(k_assemble_blocked_p1<3, kBlockedThreadsHalf>, kBlockedThreadsHalf);
+    else launch(k_assemble_blocked_p1<3, kBlockedThreads>, kBlockedThreads);
+  }
+  if (err != cudaSuccess) {
+    set_error("phifem_assemble_blocked_p1: cannot reserve %zu bytes of shared memory: %s", smem,
+              cudaGetErrorString(err));
+    return PHIFEM_ERR_CUDA;
+  }
   PHIFEM_CHECK_LAUNCH();
   return PHIFEM_OK;
 }

@@ -38,16 +38,27 @@ def _row_scale(indptr, data):
     return scale, rows
 
 
+@pytest.mark.parametrize("method,capacity", [("blocked", None), ("blocked", 2500), ("atomic", None)])
 @pytest.mark.parametrize("kind,n", [("tri", 40), ("tri-unstructured", 24), ("tet", 10),
                                     ("tet-unstructured", 8)])
-def test_cuda_operator_matches_oracle(kind, n):
+def test_cuda_operator_matches_oracle(kind, n, method, capacity):
     mesh, phi, f = _setup(kind, n)
     fn = fem.Function(fem.functionspace(mesh, 1), phi.cpu().numpy())
     with warnings.catch_warnings():
         warnings.simplefilter("ignore", RuntimeWarning)
         ctags, ftags, _, ds, _ = mesh_scripts.compute_tags_measures(mesh, fn, 1, box_mode=True)
-    plan = assemble.build_plan(mesh, ctags, ftags, ds(100))
+    plan = assemble.build_plan(mesh, ctags, ftags, ds(100), method=method, capacity=capacity)
+    assert plan.method == method
     A, b = assemble.assemble_strong_dirichlet(plan, phi, f, stab_coef=1.0)
+    if method == "blocked":
+        # owner-computes sums in a fixed order: bitwise reproducible, and independent of what the
+        # output buffers held before (no zero-fill needed for the matrix)
+        data2 = torch.full_like(A.data, float("nan"))
+        b2 = torch.zeros_like(b)
+        assemble.assemble_into(plan, phi, f, 1.0, data2, b2)
+        assert torch.equal(data2, A.data) and torch.equal(b2, b)
+        if capacity:
+            assert plan.blocked.n_blocks > 4
 
     x = mesh.x.cpu().numpy()
     cells = mesh.cells.cpu().numpy().astype(np.int64)
@@ -89,7 +100,7 @@ def test_cuda_each_integral_separately():
 
     from phifem_b200 import _lib
     lib = _lib.load()
-    plan = assemble.build_plan(mesh, ctags, ftags, ds(100))
+    plan = assemble.build_plan(mesh, ctags, ftags, ds(100), method="atomic")
     cm = _lib.c_mesh(mesh)
     st = _lib.stream()
 
@@ -140,6 +151,7 @@ def test_cuda_assembly_properties_at_scale():
         warnings.simplefilter("ignore", RuntimeWarning)
         ctags, ftags, _, ds, _ = mesh_scripts.compute_tags_measures(mesh, fn, 1, box_mode=True)
     plan = assemble.build_plan(mesh, ctags, ftags, None)          # no one-sided term
+    assert plan.method == "blocked" and plan.blocked.n_blocks > 148
     one = torch.ones(mesh.num_vertices, dtype=torch.float64, device="cuda")
     A, b = assemble.assemble_strong_dirichlet(plan, one, one, stab_coef=1.0)
     M = A.to_scipy()
