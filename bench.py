@@ -385,7 +385,7 @@ def main():
     ap.add_argument("--n", type=int, default=204, help="cubes per edge (6 n^3 tetrahedra per GPU)")
     ap.add_argument("--cpu-n", type=int, default=80, help="size of the bounded CPU sample")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scatter", default="blocked", choices=["blocked", "atomic"],
+    ap.add_argument("--scatter", default="atomic", choices=["blocked", "atomic"],
                     help="assembly scatter strategy (owner-computes blocks / fp64 reductions)")
     ap.add_argument("--capacity", type=int, default=None, help="contributions per block (blocked scatter)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

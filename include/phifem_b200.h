@@ -138,8 +138,11 @@ int phifem_assemble_boundary_p1(const phifem_mesh* mesh, const double* phi, cons
                                 int64_t n_entities, const int32_t* slots, double* data,
                                 void* stream);
 
-/* sigma avg(h_T) jump.jump over dS((2,3)) (:113-118): facets[n_facets] interior facets tagged 2/3,
- * slots[n_facets, (2nv)^2] over macro dofs [cell+ vertices, cell- vertices], cell+ = f2c[f][0]. */
+/* sigma avg(h_T) jump.jump over dS((2,3)) (:113-118): facets[n_facets] interior facets tagged 2/3.
+ * The 2nv macro dofs [cell+ vertices, cell- vertices] (cell+ = f2c[f][0]) hold nv+1 distinct vertices;
+ * the two halves of a shared vertex are summed before the scatter, so slots[n_facets, (nv+1)^2] runs
+ * over the vertex list [facet vertices in the local order of cell+, opposite vertex of cell+, opposite
+ * vertex of cell-] (row-major, row = test).  Same sparsity as the (2nv)^2 macro block of dolfinx. */
 int phifem_assemble_ghost_p1(const phifem_mesh* mesh, const double* phi, const int32_t* facets,
                              int64_t n_facets, const int32_t* slots, double sigma, double* data,
                              void* stream);
@@ -171,7 +174,7 @@ typedef struct phifem_blocked_plan {
                                   row = test) then nv load-vector entries; < 0 = row not owned */
   int64_t n_ghost_inst;
   const int32_t* ghost_facet;  /* [n_ghost_inst] facet id */
-  const int16_t* ghost_pos;    /* same layout, (2nv)^2 entries over [cell+ vertices, cell- vertices] */
+  const int16_t* ghost_pos;    /* same layout, (nv+1)^2 entries over the distinct vertices of the macro element */
   int64_t n_bnd_inst;
   const int32_t* bnd_entity;   /* [n_bnd_inst, 2] (cell, local facet) */
   const int16_t* bnd_pos;      /* same layout, nv*nv entries */

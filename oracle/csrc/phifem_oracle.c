@@ -311,15 +311,19 @@ void oracle_assemble_boundary_p1(const double* x, int D, const int32_t* cells, c
   }
 }
 
+/* slots[n_facets, (nv+1)^2] runs over the DISTINCT vertices of the macro element: facet vertices as
+ * ordered in cell +, opposite vertex of cell +, opposite vertex of cell - (include/phifem_b200.h).  The
+ * (2nv)^2 macro entries of the reference are still computed and added one by one. */
 void oracle_assemble_ghost_p1(const double* x, int D, const int32_t* cells, const int32_t* c2f,
                               const int32_t* f2c, const double* phi, const int32_t* facets,
                               int64_t n_facets, const int32_t* slots, double sigma, double* data) {
-  const int nv = D + 1, nm = 2 * nv;
+  const int nv = D + 1, nm = 2 * nv, ng = D + 2;
 #pragma omp parallel for schedule(static)
   for (int64_t e = 0; e < n_facets; ++e) {
     const int32_t fct = facets[e];
     double Jv[8][3], Js[8], hsum = 0.0, area = 0.0;
     int32_t fvert[3] = {0, 0, 0};
+    int target[8];
     for (int side = 0; side < 2; ++side) {
       const int64_t c = f2c[2 * (int64_t)fct + side];
       simplex_t s;
@@ -343,8 +347,11 @@ void oracle_assemble_ghost_p1(const double* x, int D, const int32_t* cells, cons
       }
       for (int a = 0; a < nv; ++a) {
         double Gna = dotD(s.G[a], n, D);
-        for (int k = 0; k < D; ++k)
+        target[side * nv + a] = D + side;
+        for (int k = 0; k < D; ++k) {
           Jv[side * nv + a][k] = (s.v[a] == fvert[k] ? gn : 0.0) + Gna * phi[fvert[k]];
+          if (s.v[a] == fvert[k]) target[side * nv + a] = k;
+        }
       }
     }
     const double coef = sigma * 0.5 * hsum * area / (D * (D + 1));
@@ -356,7 +363,7 @@ void oracle_assemble_ghost_p1(const double* x, int D, const int32_t* cells, cons
       for (int bb = 0; bb < nm; ++bb) {
         double t = Js[a] * Js[bb];
         for (int k = 0; k < D; ++k) t += Jv[a][k] * Jv[bb][k];
-        atomic_add(data + slots[e * nm * nm + a * nm + bb], coef * t);
+        atomic_add(data + slots[e * ng * ng + target[a] * ng + target[bb]], coef * t);
       }
   }
 }

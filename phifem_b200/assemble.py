@@ -33,14 +33,34 @@ class CSRMatrix:
                               self.indptr.cpu().numpy()), shape=self.shape)
 
 
+def ghost_macro_vertices(mesh, facets):
+    """[n, nv+1] distinct vertices of the macro element of interior facets, in the order the ghost-penalty
+    kernel emits its tensor: facet vertices as ordered in cell + (= f2c[f][0]), opposite vertex of cell +,
+    opposite vertex of cell -."""
+    g = facets.long()
+    nv = mesh.cells.shape[1]
+    out = []
+    for side in (0, 1):
+        c = mesh.f2c[g, side].long()
+        cv = mesh.cells[c].long()
+        lf = (mesh.c2f[c].long() == g[:, None]).long().argmax(dim=1)
+        if side == 0:
+            keep = torch.arange(nv, device=g.device)[None, :] != lf[:, None]
+            out.append(cv[keep].reshape(-1, nv - 1))
+        out.append(cv.gather(1, lf[:, None]))
+    return torch.cat(out, dim=1)
+
+
 class AssemblyPlan:
     """Tag-dependent symbolic data of one operator (reused for every assembly with the same tags).
 
-    method = "blocked": owner-computes kernel (no atomics; phifem_b200/blocked.py), the default;
-    method = "atomic" : fp64 reductions through the slot maps (also the fall-back when a row gathers more
-    contributions than a shared-memory block can hold)."""
+    method = "atomic" : fp64 reductions through the slot maps (the default: fastest at present, see
+    DESIGN.md / profiles/);
+    method = "blocked": owner-computes kernel (no atomics, no zero-fill, bitwise reproducible;
+    phifem_b200/blocked.py); falls back to "atomic" when a single row gathers more contributions than a
+    shared-memory block can hold."""
 
-    def __init__(self, mesh, cell_tags8, facet_tags8, entities, method="blocked", capacity=None):
+    def __init__(self, mesh, cell_tags8, facet_tags8, entities, method="atomic", capacity=None):
         if mesh.cell_type not in ("triangle", "tetrahedron"):
             raise NotImplementedError("P1 assembly supports triangles and tetrahedra")
         dev = mesh.device
@@ -60,15 +80,14 @@ class AssemblyPlan:
 
         dm = mesh.cells[self.active.long()].long()
         keys_c = pair_keys(dm)
-        g = self.ghost.long()
-        mac = torch.cat([mesh.cells[mesh.f2c[g, 0].long()], mesh.cells[mesh.f2c[g, 1].long()]], dim=1).long()
+        mac = ghost_macro_vertices(mesh, self.ghost)
         keys_g = pair_keys(mac)
         n_c = keys_c.numel()
         uniq, inv = torch.unique(torch.cat([keys_c.reshape(-1), keys_g.reshape(-1)]), sorted=True,
                                  return_inverse=True)
         del keys_c, keys_g
         self.slots_cells = inv[:n_c].reshape(-1, nv * nv).to(torch.int32).contiguous()
-        self.slots_ghost = inv[n_c:].reshape(-1, 4 * nv * nv).to(torch.int32).contiguous()
+        self.slots_ghost = inv[n_c:].reshape(-1, (nv + 1) ** 2).to(torch.int32).contiguous()
         del inv
         keys_b = pair_keys(mesh.cells[self.entities[:, 0].long()].long())
         self.slots_boundary = torch.searchsorted(uniq, keys_b.reshape(-1)).reshape(-1, nv * nv) \
@@ -97,7 +116,7 @@ class AssemblyPlan:
                 torch.zeros(self.n_rows, dtype=torch.float64, device=dev))
 
 
-def build_plan(mesh, cells_tags, facets_tags, ds=None, method="blocked", capacity=None):
+def build_plan(mesh, cells_tags, facets_tags, ds=None, method="atomic", capacity=None):
     """Symbolic phase for `a` and `L` of the strong-Dirichlet demo.  `ds` is what the demo passes as
     `ds_bdy(100)` (main.py:64): a MeasureRestriction, a flat entity array, or None (no boundary term)."""
     c8 = getattr(cells_tags, "tags8", None)

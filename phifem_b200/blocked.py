@@ -24,7 +24,7 @@ import torch
 from . import _lib
 
 DESC_INTS = 12
-DEFAULT_CAPACITY = 27000     # doubles: 216 KB of the 227 KB a CTA may use on sm_100a
+DEFAULT_CAPACITY = 25000     # doubles: 200 KB buffer + ~20 KB segment tables of the 227 KB a CTA may use on sm_100a
 _KEY_SHIFT = 33              # key = block << 33 | is_b << 32 | index
 
 
@@ -167,7 +167,7 @@ class BlockedPlan:
             o = torch.argsort(inst_blk, stable=True)
             return inst_ent[o], p[o], torch.searchsorted(inst_blk[o].contiguous(), torch.arange(NB + 1, **i64))
 
-        m_c, m_g, m_b = nv * nv + nv, 4 * nv * nv, nv * nv
+        m_c, m_g, m_b = nv * nv + nv, (nv + 1) ** 2, nv * nv
         ce, cp, c_rng = instances(blk_cell, pos_cell, m_c)
         ge, gp, g_rng = instances(blk_g, pos_g, m_g)
         be, bp, b_rng = instances(blk_b, pos_b, m_b)

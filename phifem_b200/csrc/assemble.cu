@@ -221,14 +221,24 @@ __device__ __forceinline__ void boundary_tensor(const double (&xc)[D + 1][D], co
   }
 }
 
-// sigma avg(h_T) int_F jump.jump (main.py:113-118) over macro dofs [cell+ vertices, cell- vertices]
+// sigma avg(h_T) int_F jump.jump (main.py:113-118).  The macro element [cell+ vertices, cell- vertices]
+// has 2(D+1) dofs but only D+2 distinct vertices (the D facet vertices appear in both halves); the jump
+// integrand is linear in the basis function, so the two halves of a shared vertex are summed first and
+// (D+2)^2 entries are emitted instead of (2D+2)^2 -- 25 instead of 64 scatter operations per tetrahedron
+// facet.  Vertex order of the emitted tensor: facet vertices as ordered in cell +, opposite vertex of
+// cell +, opposite vertex of cell -.
 template <int D, typename Emit>
 __device__ __forceinline__ void ghost_tensor(const phifem_mesh& m, const double* __restrict__ phi,
                                              int32_t fct, double sigma, Emit& emit) {
-  constexpr int NV = D + 1, NM = 2 * NV;
+  constexpr int NV = D + 1, NG = D + 2;
   const int2 cc = __ldg(reinterpret_cast<const int2*>(m.f2c) + fct);
   int fvert[D];            // global vertices of the facet, ordered as in cell +
-  double Jv[NM][D];        // jump integrand of macro dof a at facet vertex k (affine on the facet)
+  double pf[D];            // phi at the facet vertices
+  double Jg[NG][D];        // jump integrand of each distinct vertex at facet vertex k (affine on the facet)
+#pragma unroll
+  for (int a = 0; a < NG; ++a)
+#pragma unroll
+    for (int k = 0; k < D; ++k) Jg[a][k] = 0.0;
   double hsum = 0.0, area = 0.0;
 #pragma unroll
   for (int side = 0; side < 2; ++side) {
@@ -271,36 +281,44 @@ __device__ __forceinline__ void ghost_tensor(const phifem_mesh& m, const double*
         if (k != o) {
 #pragma unroll
           for (int t = 0; t < D; ++t)
-            if (t == q) fvert[t] = v[k];
+            if (t == q) {
+              fvert[t] = v[k];
+              pf[t] = p[k];
+            }
           ++q;
         }
     }
 #pragma unroll
     for (int a = 0; a < NV; ++a) {
       const double Gna = dot<D>(G[a], n);
+      // destination: the facet vertex this dof sits on, or this side's opposite vertex
+      int t = D + side;
 #pragma unroll
-      for (int k = 0; k < D; ++k) {
-        const double pk = __ldg(phi + fvert[k]);
-        Jv[side * NV + a][k] = (v[a] == fvert[k] ? gn : 0.0) + Gna * pk;
-      }
+      for (int k = 0; k < D; ++k)
+        if (a != o && v[a] == fvert[k]) t = k;
+#pragma unroll
+      for (int tt = 0; tt < NG; ++tt)
+        if (tt == t)
+#pragma unroll
+          for (int k = 0; k < D; ++k) Jg[tt][k] += (tt == k && t < D ? gn : 0.0) + Gna * pf[k];
     }
   }
   const double coef = sigma * 0.5 * hsum * area * (1.0 / (D * (D + 1)));
-  double Js[NM];
+  double Js[NG];
 #pragma unroll
-  for (int a = 0; a < NM; ++a) {
+  for (int a = 0; a < NG; ++a) {
     double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < D; ++k) s += Jv[a][k];
+    for (int k = 0; k < D; ++k) s += Jg[a][k];
     Js[a] = s;
   }
 #pragma unroll
-  for (int a = 0; a < NM; ++a) {
+  for (int a = 0; a < NG; ++a) {
 #pragma unroll
-    for (int bb = a; bb < NM; ++bb) {
+    for (int bb = a; bb < NG; ++bb) {
       double s = Js[a] * Js[bb];
 #pragma unroll
-      for (int k = 0; k < D; ++k) s += Jv[a][k] * Jv[bb][k];
+      for (int k = 0; k < D; ++k) s += Jg[a][k] * Jg[bb][k];
       const double val = coef * s;
       emit.mat(a, bb, val);
       if (bb != a) emit.mat(bb, a, val);
@@ -313,9 +331,21 @@ template <int N>
 struct AtomicEmit {
   double* data;
   double* b;
-  const int32_t* slots;  // [N*N] of this entity
   const int* verts;
-  __device__ __forceinline__ void mat(int i, int j, double v) const { atomicAdd(data + __ldg(slots + i * N + j), v); }
+  int sl[N * N];  // CSR slots of this entity, fetched before the arithmetic starts (independent loads)
+  __device__ __forceinline__ void load_slots(const int32_t* __restrict__ slots) {
+    if (N * N % 4 == 0) {
+#pragma unroll
+      for (int q = 0; q < N * N / 4; ++q) {
+        const int4 s4 = __ldg(reinterpret_cast<const int4*>(slots) + q);
+        sl[4 * q] = s4.x; sl[4 * q + 1] = s4.y; sl[4 * q + 2] = s4.z; sl[4 * q + 3] = s4.w;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < N * N; ++q) sl[q] = __ldg(slots + q);
+    }
+  }
+  __device__ __forceinline__ void mat(int i, int j, double v) const { atomicAdd(data + sl[i * N + j], v); }
   __device__ __forceinline__ void vec(int i, double v) const { atomicAdd(b + verts[i], v); }
 };
 
@@ -337,7 +367,8 @@ __global__ void __launch_bounds__(kBlock) k_assemble_cells_p1(
     p[k] = __ldg(phi + v[k]);
     fv[k] = __ldg(f + v[k]);
   }
-  AtomicEmit<NV> emit{data, b, slots + e * NV * NV, v};
+  AtomicEmit<NV> emit{data, b, v};
+  emit.load_slots(slots + e * NV * NV);
   cell_tensor<D>(xc, p, fv, ctags[c] == 2, sigma, emit);
 }
 
@@ -356,7 +387,8 @@ __global__ void __launch_bounds__(kBlock) k_assemble_boundary_p1(
   double p[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) p[k] = __ldg(phi + v[k]);
-  AtomicEmit<NV> emit{data, nullptr, slots + e * NV * NV, v};
+  AtomicEmit<NV> emit{data, nullptr, v};
+  emit.load_slots(slots + e * NV * NV);
   boundary_tensor<D>(xc, p, o, emit);
 }
 
@@ -364,10 +396,11 @@ template <int D>
 __global__ void __launch_bounds__(kBlock) k_assemble_ghost_p1(
     phifem_mesh m, const double* __restrict__ phi, const int32_t* __restrict__ facets, int64_t n_facets,
     const int32_t* __restrict__ slots, double sigma, double* __restrict__ data) {
-  constexpr int NM = 2 * (D + 1);
+  constexpr int NM = D + 2;
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_facets) return;
-  AtomicEmit<NM> emit{data, nullptr, slots + e * NM * NM, nullptr};
+  AtomicEmit<NM> emit{data, nullptr, nullptr};
+  emit.load_slots(slots + e * NM * NM);
   ghost_tensor<D>(m, phi, __ldg(facets + e), sigma, emit);
 }
 
@@ -423,7 +456,7 @@ template <int D, int THREADS>
 __global__ void __launch_bounds__(THREADS, kBlockedThreads / THREADS) k_assemble_blocked_p1(
     phifem_mesh m, const double* __restrict__ phi, const double* __restrict__ f, double sigma,
     phifem_blocked_plan pl, double* __restrict__ data, double* __restrict__ b) {
-  constexpr int NV = D + 1, NM = 2 * NV;
+  constexpr int NV = D + 1, NM = D + 2;  // NM: distinct vertices of a facet macro element
   constexpr int CW = (NV * NV + NV + 1) / 2, GW = (NM * NM + 1) / 2, BW = (NV * NV + 1) / 2;
   extern __shared__ __align__(16) double buf[];
   int32_t* s_dest = reinterpret_cast<int32_t*>(buf + ((pl.capacity + 1) & ~1));

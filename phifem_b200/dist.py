@@ -141,7 +141,7 @@ class SlabProblem:
             return (g[:, :, None] * NG + g[:, None, :]).reshape(dm.shape[0], dm.shape[1] ** 2)
 
         dm_c = mesh.cells[active].long()
-        mac = torch.cat([mesh.cells[mesh.f2c[ghost, 0].long()], mesh.cells[mesh.f2c[ghost, 1].long()]], dim=1).long()
+        mac = assemble.ghost_macro_vertices(mesh, ghost)
         dm_b = mesh.cells[ents[:, 0].long()].long()
         keys = [pair_keys(dm_c), pair_keys(mac), pair_keys(dm_b)]
         flat = torch.cat([k.reshape(-1) for k in keys])
@@ -182,7 +182,7 @@ class SlabProblem:
         self.plan = SimpleNamespace(
             mesh=mesh, cell_tags8=cell_tags8, active=active.to(torch.int32).contiguous(),
             ghost=ghost.to(torch.int32).contiguous(), entities=ents.to(torch.int32).contiguous(),
-            slots_cells=s_c.reshape(-1, nv * nv).contiguous(), slots_ghost=s_g.reshape(-1, 4 * nv * nv).contiguous(),
+            slots_cells=s_c.reshape(-1, nv * nv).contiguous(), slots_ghost=s_g.reshape(-1, (nv + 1) ** 2).contiguous(),
             slots_boundary=s_b.reshape(-1, nv * nv).contiguous(), nnz=nnz, total=total, n_rows=n_rows,
             indptr=indptr.to(torch.int64), indices=(own - rows * NG).contiguous(),
             send_ranges=[(send_off[q], send_off[q] + int(send_keys[q].numel())) for q in range(world)],

@@ -80,7 +80,14 @@ def test_blocked_plan_reproduces_the_oracle_operator(d, n, cap):
     cut = cv[:, 0] < 0
     cv[:, 0] &= 0x7FFFFFFF
     At, bt = OA.cell_tensors_closed_form(x, cv[:, :d + 1], phi, f, cut, 1.0)
-    Gt, _ = OA.ghost_tensors_closed_form(x, cells, phi, out["c2f"], out["f2c"], bp.ghost_facet.numpy(), 1.0)
+    G8, macro = OA.ghost_tensors_closed_form(x, cells, phi, out["c2f"], out["f2c"], bp.ghost_facet.numpy(), 1.0)
+    # fold the (2nv)^2 macro tensors onto the nv+1 distinct vertices, in the kernel's vertex order
+    from phifem_b200.assemble import ghost_macro_vertices
+    mv = ghost_macro_vertices(m, bp.ghost_facet).numpy()
+    Gt = np.zeros((len(mv), d + 2, d + 2))
+    for e in range(len(mv)):
+        t = [int(np.nonzero(mv[e] == v)[0][0]) for v in macro[e]]
+        np.add.at(Gt[e], (np.repeat(t, len(t)), np.tile(t, len(t))), G8[e].ravel())
     Bt = OA.boundary_tensors_closed_form(x, cells, phi, bp.bnd_entity.numpy())
     data, b = _emulate(bp, At, bt, Gt, Bt, plan.nnz, len(x))
     ip, ix, want, wb = OA.assemble_strong_dirichlet(x, cells, cells, len(x), phi, f, out["cell_tags"],

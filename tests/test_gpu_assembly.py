@@ -150,7 +150,7 @@ def test_cuda_assembly_properties_at_scale():
     with warnings.catch_warnings():
         warnings.simplefilter("ignore", RuntimeWarning)
         ctags, ftags, _, ds, _ = mesh_scripts.compute_tags_measures(mesh, fn, 1, box_mode=True)
-    plan = assemble.build_plan(mesh, ctags, ftags, None)          # no one-sided term
+    plan = assemble.build_plan(mesh, ctags, ftags, None, method="blocked")   # no one-sided term
     assert plan.method == "blocked" and plan.blocked.n_blocks > 148
     one = torch.ones(mesh.num_vertices, dtype=torch.float64, device="cuda")
     A, b = assemble.assemble_strong_dirichlet(plan, one, one, stab_coef=1.0)

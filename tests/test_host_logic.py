@@ -81,10 +81,14 @@ def test_symbolic_phase_matches_oracle_pattern(d):
     dm = cells[active]
     assert np.array_equal(rows[sl], np.repeat(dm, nv, axis=1))
     assert np.array_equal(ix[sl], np.tile(dm, (1, nv)))
-    mac = np.concatenate([cells[out["f2c"][ghost, 0]], cells[out["f2c"][ghost, 1]]], axis=1)
+    mac = assemble.ghost_macro_vertices(m, plan.ghost).numpy()
+    for e, fct in enumerate(ghost):                      # distinct vertices of the two cells, cell + first
+        cp, cm = out["f2c"][fct]
+        assert set(mac[e]) == set(cells[cp]) | set(cells[cm]) and len(set(mac[e])) == nv + 1
+        assert list(mac[e][:nv - 1]) == [v for v in cells[cp] if v in cells[cm]]
     sg = plan.slots_ghost.numpy()
-    assert np.array_equal(rows[sg], np.repeat(mac, 2 * nv, axis=1))
-    assert np.array_equal(ix[sg], np.tile(mac, (1, 2 * nv)))
+    assert np.array_equal(rows[sg], np.repeat(mac, nv + 1, axis=1))
+    assert np.array_equal(ix[sg], np.tile(mac, (1, nv + 1)))
     ents = out["ds100"].reshape(-1, 2)
     sb = plan.slots_boundary.numpy()
     assert np.array_equal(ix[sb], np.tile(cells[ents[:, 0]], (1, nv)))
