@@ -85,6 +85,15 @@ class SlabProblem:
         self.f = self._source(self.mesh.x)
         self.plan = None
 
+    @classmethod
+    def global_reference(cls, n, world, device="cpu"):
+        """(mesh, phi, f) of the WHOLE box on one device: what the ranks' results are checked against.
+        Vertex / cell numbering equals the ranks' global numbering."""
+        self = cls.__new__(cls)
+        self.n, self.rank, self.world, self.group, self.device = n, 0, world, None, torch.device(device)
+        mesh = self._slab_mesh(world * n, n, 0)
+        return mesh, self._levelset(mesh.x), self._source(mesh.x)
+
     def _slab_mesh(self, nx, n, i0):
         base = synthetic.box_mesh((nx, n, n), device=self.device)
         x = base.x.clone()

@@ -1,0 +1,21 @@
+"""Multi-GPU parity (needs >= 2 GPUs: run with `gpurun --gpus 2 -- python -m pytest tests -m gpu`):
+the gathered N-GPU tags and CSR operator equal the single-GPU ones."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpus_match_single_gpu():
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29611",
+                          os.path.join(HERE, "dist_gpu_worker.py"), "12"], capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert "DIST-OK world=2" in out.stdout
