@@ -174,7 +174,8 @@ class SlabProblem:
                 sel = owner == q
                 slot[sel] = send_off[q] + torch.searchsorted(send_keys[q], flat[sel])
         sizes = [k.numel() for k in keys]
-        s_c, s_g, s_b = torch.split(slot.to(torch.int32), sizes)
+        # clone: the kernels read slot rows with 16-byte vector loads, split() views may start unaligned
+        s_c, s_g, s_b = (t.clone() for t in torch.split(slot.to(torch.int32), sizes))
         rows = own // NG
         n_rows = self.row_hi - self.row_lo
         counts = torch.bincount(rows - self.row_lo, minlength=n_rows)
