@@ -303,10 +303,16 @@ def run_ours(args):
     ab = algorithmic_bytes(counts)
     peak, peak_src = _peaks()
     dominant = max(("tag_cells", "tag_facets", "assemble_cells"), key=lambda k_: per[k_])
+    # the row-gather kernel is the whole assembly (cells + ghost + one-sided terms, pattern read, CSR
+    # values and b written): SURVEY.md 8(d) B_asm; the atomic cell kernel alone moves less
+    asm_bytes = ab["assembly"] if plan.method in ("rows", "blocked") else ab["cells_kernel"]
     kbytes = {"tag_cells": ab["tags_cells"], "tag_facets": ab["tags_facets"],
-              "assemble_cells": ab["cells_kernel"]}[dominant]
+              "assemble_cells": asm_bytes}[dominant]
     achieved = kbytes / (per[dominant] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+    kernel_names = {"tag_cells": "k_tag_cells_p1", "tag_facets": "k_tag_facets",
+                    "assemble_cells": {"rows": "k_assemble_rows_p1", "blocked": "k_assemble_blocked_p1",
+                                       "atomic": "k_assemble_cells_p1"}[plan.method]}
+    roofline = {"bound": "hbm", "kernel": kernel_names[dominant], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": kbytes,
                 "step_achieved_gbs": ab["total"] / (ms_per_step * 1e-3) / 1e9,
@@ -314,7 +320,7 @@ def run_ours(args):
                 "kernels_ms": per,
                 "kernels_gbs": {"tag_cells": ab["tags_cells"] / per["tag_cells"] / 1e6,
                                 "tag_facets": ab["tags_facets"] / per["tag_facets"] / 1e6,
-                                "assemble_cells": ab["cells_kernel"] / per["assemble_cells"] / 1e6}}
+                                "assemble_cells": asm_bytes / per["assemble_cells"] / 1e6}}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         with open(traffic_file) as fh:
@@ -378,13 +384,22 @@ def run_ours(args):
                                         "exchange" if world > 1 else "single GPU",
                            "timed": "tag kernels + zeroing + assembly kernels; symbolic phase excluded"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-                "gpu_launches": (4 if plan.method == "blocked" else 6) * args.steps,
+                "gpu_launches": {"rows": 6, "blocked": 4, "atomic": 6}[plan.method] * args.steps,
                 "symbolic_ms": symbolic_ms, "topology_s": topo_s,
                 "scatter": {"method": plan.method,
                             **({"blocks": plan.blocked.n_blocks, "capacity": plan.blocked.capacity,
                                 "bin_shape": plan.blocked.bin_shape,
                                 "recompute_factor": plan.blocked.redundancy,
-                                "plan_bytes": plan.blocked.index_bytes()} if plan.blocked else {})}}
+                                "plan_bytes": plan.blocked.index_bytes()} if plan.blocked else {}),
+                            **({"order": plan.rowsplan.order, "max_row_nnz": plan.rowsplan.max_row_nnz,
+                                "rows_cells_ghost_boundary": [plan.rowsplan.cells.n_listed,
+                                                              plan.rowsplan.ghost.n_listed,
+                                                              plan.rowsplan.boundary.n_listed],
+                                "records": [plan.rowsplan.cells.n_records, plan.rowsplan.ghost.n_records,
+                                            plan.rowsplan.boundary.n_records],
+                                "lane_padding": [plan.rowsplan.cells.padding(), plan.rowsplan.ghost.padding(),
+                                                 plan.rowsplan.boundary.padding()],
+                                "plan_bytes": plan.rowsplan.index_bytes()} if plan.rowsplan else {})}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -398,8 +413,8 @@ def main():
     ap.add_argument("--n", type=int, default=204, help="cubes per edge (6 n^3 tetrahedra per GPU)")
     ap.add_argument("--cpu-n", type=int, default=80, help="size of the bounded CPU sample")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scatter", default="atomic", choices=["blocked", "atomic"],
-                    help="assembly scatter strategy (owner-computes blocks / fp64 reductions)")
+    ap.add_argument("--scatter", default="rows", choices=["rows", "blocked", "atomic"],
+                    help="assembly strategy (row-gather / owner-computes blocks / fp64 reductions)")
     ap.add_argument("--capacity", type=int, default=None, help="contributions per block (blocked scatter)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")

@@ -186,6 +186,52 @@ typedef struct phifem_blocked_plan {
 int phifem_assemble_blocked_p1(const phifem_mesh* mesh, const double* phi, const double* f, double sigma,
                                const phifem_blocked_plan* plan, double* data, double* b, void* stream);
 
+/* ---- row-gather assembly: one thread per CSR row (owner computes; no atomics, no zero-fill of `data`,
+ * bitwise reproducible) ---------------------------------------------------------------------------
+ * What dolfinx does as "loop over cells, MatSetValuesLocal(ADD_VALUES)" (demo/strong-dirichlet/flower/
+ * main.py:121-123,130-131) is turned around: every listed row walks the cells, ghost-penalty facets and
+ * one-sided entities that touch its vertex, evaluates ONLY its own row of each element tensor and keeps
+ * the row's entries in shared-memory accumulators until one plain store per CSR entry.  An entity is not
+ * named by its id: a record holds the positions, inside the row's own column list, of the entity's other
+ * vertices (uint8 each), so the CSR pattern itself is the connectivity the kernel reads.
+ * Records are stored as sliced ELLPACK over warps: slice s = listed rows [32 s, 32 s + 32), record k of
+ * lane l at rec[((ptr[s] + k) * 32 + l) * words]; ptr[] counts records per lane, pads are all-ones.
+ * Each record kind has its own list of rows (the ghost-penalty and one-sided terms touch only rows near
+ * the surface; walking them in the cell pass would leave most lanes of every warp idle). */
+typedef struct phifem_row_list {
+  int64_t n_listed;            /* rows of this list, in processing order */
+  const int32_t* rows;         /* [n_listed] row (= vertex) ids, each row at most once */
+  const uint8_t* diag_pos;     /* [n_listed] position of the diagonal entry inside the row */
+  const int32_t* ptr;          /* [ceil(n_listed / 32) + 1] */
+  const uint32_t* rec;         /* records, see phifem_rows_plan */
+} phifem_row_list;
+
+typedef struct phifem_rows_plan {
+  const int32_t* indptr;       /* [n_rows + 1] CSR row pointers */
+  const int32_t* indices;      /* [nnz] CSR column indices */
+  int32_t max_row_nnz;         /* longest row (accumulators per thread), <= 255 */
+  int32_t reserved;
+  /* every row with pattern entries; one word per record: byte j < d = position of other vertex j of a
+   * cell tagged 1/2 containing the row's vertex; bit 24: the cell is cut (tag 2).  This pass WRITES the
+   * rows (data and b); rows listed here without records are written as zeros. */
+  phifem_row_list cells;
+  /* rows touched by interior facets tagged 2/3; two words per record: word 0 byte j = position of other
+   * vertex j of the facet macro element; word 1 = role:
+   *   0: row is a facet vertex, others = [other facet vertices, opposite vertex of cell A, of cell B];
+   *   1: row is the opposite vertex of cell A, others = [facet vertices, opposite vertex of cell B].
+   * This pass ADDS to the rows written by the cell pass. */
+  phifem_row_list ghost;
+  /* rows on one-sided facets of ds(100); one word per record: byte 0 = position of the cell vertex opposite
+   * the facet, bytes 1..d-1 = the other facet vertices.  ADDS as well. */
+  phifem_row_list boundary;
+} phifem_rows_plan;
+
+/* Same operator as phifem_assemble_{cells,boundary,ghost}_p1, three launches on `stream` (cell pass, then
+ * the two surface passes).  `data` need NOT be zeroed (every entry of a listed row is written by the cell
+ * pass); b[row] is written for listed rows only. */
+int phifem_assemble_rows_p1(const phifem_mesh* mesh, const double* phi, const double* f, double sigma,
+                            const phifem_rows_plan* plan, double* data, double* b, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

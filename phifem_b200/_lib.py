@@ -44,6 +44,16 @@ class CBlockedPlan(ctypes.Structure):
                 ("n_bnd_inst", ctypes.c_int64), ("bnd_entity", _vp), ("bnd_pos", _vp)]
 
 
+class CRowList(ctypes.Structure):
+    _fields_ = [("n_listed", ctypes.c_int64), ("rows", _vp), ("diag_pos", _vp), ("ptr", _vp), ("rec", _vp)]
+
+
+class CRowsPlan(ctypes.Structure):
+    _fields_ = [("indptr", _vp), ("indices", _vp), ("max_row_nnz", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("cells", CRowList), ("ghost", CRowList),
+                ("boundary", CRowList)]
+
+
 _SIGNATURES = {
     "phifem_last_error": (ctypes.c_char_p, []),
     "phifem_abi_version": (ctypes.c_int, []),
@@ -62,6 +72,8 @@ _SIGNATURES = {
                                                 ctypes.c_double, _vp, _vp]),
     "phifem_assemble_blocked_p1": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, ctypes.c_double,
                                                   ctypes.POINTER(CBlockedPlan), _vp, _vp, _vp]),
+    "phifem_assemble_rows_p1": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, ctypes.c_double,
+                                               ctypes.POINTER(CRowsPlan), _vp, _vp, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

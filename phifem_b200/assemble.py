@@ -54,13 +54,16 @@ def ghost_macro_vertices(mesh, facets):
 class AssemblyPlan:
     """Tag-dependent symbolic data of one operator (reused for every assembly with the same tags).
 
-    method = "atomic" : fp64 reductions through the slot maps (the default: fastest at present, see
-    DESIGN.md / profiles/);
-    method = "blocked": owner-computes kernel (no atomics, no zero-fill, bitwise reproducible;
-    phifem_b200/blocked.py); falls back to "atomic" when a single row gathers more contributions than a
+    method = "rows"   : row-gather kernel, one thread per CSR row (the default: no atomics, no zero-fill,
+    bitwise reproducible; phifem_b200/rows.py); falls back to "atomic" when a row holds more than 200
+    entries;
+    method = "atomic" : one thread per entity, fp64 reductions through the entity -> CSR-slot maps;
+    method = "blocked": owner-computes CTA per row block with a shared-memory segmented reduction
+    (phifem_b200/blocked.py); falls back to "atomic" when a single row gathers more contributions than a
     shared-memory block can hold."""
 
-    def __init__(self, mesh, cell_tags8, facet_tags8, entities, method="atomic", capacity=None):
+    def __init__(self, mesh, cell_tags8, facet_tags8, entities, method="rows", capacity=None,
+                 order="natural"):
         if mesh.cell_type not in ("triangle", "tetrahedron"):
             raise NotImplementedError("P1 assembly supports triangles and tetrahedra")
         dev = mesh.device
@@ -99,16 +102,23 @@ class AssemblyPlan:
         self.indptr[1:] = torch.cumsum(counts, dim=0)
         self.indptr = self.indptr.to(torch.int32).contiguous()
         self.nnz = int(uniq.numel())
-        self.blocked, self.method = None, "atomic"
-        if method == "blocked" and self.active.numel() > 0:
+        self.blocked, self.rowsplan, self.method = None, None, "atomic"
+        if method == "rows" and self.nnz > 0:
+            from . import rows as rows_mod
+            try:
+                self.rowsplan = rows_mod.RowsPlan(self, order=order)
+                self.method = "rows"
+            except NotImplementedError:
+                self.rowsplan = None
+        elif method == "blocked" and self.active.numel() > 0:
             from . import blocked
             try:
                 self.blocked = blocked.BlockedPlan(self, capacity or blocked.DEFAULT_CAPACITY)
                 self.method = "blocked"
             except NotImplementedError:
                 self.blocked = None
-        elif method not in ("blocked", "atomic"):
-            raise ValueError("method must be 'blocked' or 'atomic'")
+        elif method not in ("rows", "blocked", "atomic"):
+            raise ValueError("method must be 'rows', 'blocked' or 'atomic'")
 
     def new_outputs(self):
         dev = self.mesh.device
@@ -116,7 +126,7 @@ class AssemblyPlan:
                 torch.zeros(self.n_rows, dtype=torch.float64, device=dev))
 
 
-def build_plan(mesh, cells_tags, facets_tags, ds=None, method="atomic", capacity=None):
+def build_plan(mesh, cells_tags, facets_tags, ds=None, method="rows", capacity=None, order="natural"):
     """Symbolic phase for `a` and `L` of the strong-Dirichlet demo.  `ds` is what the demo passes as
     `ds_bdy(100)` (main.py:64): a MeasureRestriction, a flat entity array, or None (no boundary term)."""
     c8 = getattr(cells_tags, "tags8", None)
@@ -131,7 +141,8 @@ def build_plan(mesh, cells_tags, facets_tags, ds=None, method="atomic", capacity
         ents = ds.to(mesh.device)
     else:
         ents = torch.as_tensor(np.asarray(ds, dtype=np.int32), device=mesh.device)
-    return AssemblyPlan(mesh, c8.contiguous(), f8.contiguous(), ents, method=method, capacity=capacity)
+    return AssemblyPlan(mesh, c8.contiguous(), f8.contiguous(), ents, method=method, capacity=capacity,
+                        order=order)
 
 
 def _device_vector(mesh, v):
@@ -152,6 +163,14 @@ def assemble_into(plan, phi, f, sigma, data, b, marks=None):
     invoked after the zeroing and after each kernel (bench.py records CUDA events there)."""
     marks = marks or (lambda: None)
     _lib.require_cuda(plan.mesh)
+    if getattr(plan, "rowsplan", None) is not None:
+        from . import rows as rows_mod
+        marks()
+        rows_mod.assemble_rows_into(plan.rowsplan, phi, f, sigma, data, b)
+        marks()
+        marks()
+        marks()
+        return data, b
     if getattr(plan, "blocked", None) is not None:
         from . import blocked
         marks()

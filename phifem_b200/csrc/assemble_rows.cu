@@ -1,0 +1,509 @@
+// K2+K3+K4 fused, row-gather form: strong-Dirichlet phi-FEM operator, P1 on triangles / tetrahedra,
+// one thread per CSR row.
+//
+// Forms of reference demo/strong-dirichlet/flower/main.py:104-128 (closed-form element tensors of
+// SURVEY.md Appendix B).  dolfinx loops over cells and ADDs 4x4 blocks into PETSc AIJ rows
+// (main.py:121-123); a GPU doing the same issues 20 fp64 reductions per tetrahedron, and the SM retires
+// less than one reduction lane per clock (profiles/: 1.74 ms for 19.8 M cells, fp64 pipe 14 % busy).
+// Here the loop is turned around: the thread owning row r walks the entities touching vertex r and
+// evaluates only ITS row of each element tensor (1.8x the fp64 work of the cell loop, which the idle
+// fp64 pipe absorbs), accumulating in registers (diagonal, load vector) and in a private, bank-conflict
+// free column of shared memory (off-diagonals).  One plain store per CSR entry at the end: no atomics,
+// no zero-fill, bitwise reproducible, and every rank of a multi-GPU run can own rows outright.
+//
+// Connectivity comes from the CSR pattern itself: a record holds the positions inside row r's column
+// list of the entity's other vertices, so `indices[start + pos]` names them (include/phifem_b200.h).
+#include "common.cuh"
+
+namespace phifem {
+namespace {
+
+constexpr int kRowsBlock = 128;
+constexpr uint32_t kPad = 0xffffffffu;
+
+template <int D>
+__device__ __forceinline__ double dot(const double (&a)[D], const double (&b)[D]) {
+  double s = a[0] * b[0];
+#pragma unroll
+  for (int d = 1; d < D; ++d) s += a[d] * b[d];
+  return s;
+}
+
+// gradients of the barycentric coordinates of the simplex X[0..D], det of the edge matrix
+template <int D>
+__device__ __forceinline__ void simplex_gradients(const double (&X)[D + 1][D], double (&G)[D + 1][D],
+                                                  double& det) {
+  double e[D][D];
+#pragma unroll
+  for (int k = 0; k < D; ++k)
+#pragma unroll
+    for (int d = 0; d < D; ++d) e[k][d] = X[k + 1][d] - X[0][d];
+  if constexpr (D == 2) {
+    det = e[0][0] * e[1][1] - e[1][0] * e[0][1];
+    const double inv = 1.0 / det;
+    G[1][0] = e[1][1] * inv;  G[1][1] = -e[1][0] * inv;
+    G[2][0] = -e[0][1] * inv; G[2][1] = e[0][0] * inv;
+  } else {
+    const double r1[3] = {e[1][1] * e[2][2] - e[1][2] * e[2][1], e[1][2] * e[2][0] - e[1][0] * e[2][2],
+                          e[1][0] * e[2][1] - e[1][1] * e[2][0]};
+    const double r2[3] = {e[2][1] * e[0][2] - e[2][2] * e[0][1], e[2][2] * e[0][0] - e[2][0] * e[0][2],
+                          e[2][0] * e[0][1] - e[2][1] * e[0][0]};
+    const double r3[3] = {e[0][1] * e[1][2] - e[0][2] * e[1][1], e[0][2] * e[1][0] - e[0][0] * e[1][2],
+                          e[0][0] * e[1][1] - e[0][1] * e[1][0]};
+    det = e[0][0] * r1[0] + e[0][1] * r1[1] + e[0][2] * r1[2];
+    const double inv = 1.0 / det;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      G[1][d] = r1[d] * inv;
+      G[2][d] = r2[d] * inv;
+      G[3][d] = r3[d] * inv;
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    double s = G[1][d];
+#pragma unroll
+    for (int k = 2; k <= D; ++k) s += G[k][d];
+    G[0][d] = -s;
+  }
+}
+
+template <int D>
+__device__ __forceinline__ double diameter2(const double (&X)[D + 1][D]) {
+  double h2 = 0.0;  // CellDiameter^2 = max squared vertex distance (main.py:100)
+#pragma unroll
+  for (int a = 0; a <= D; ++a)
+#pragma unroll
+    for (int b = a + 1; b <= D; ++b) {
+      double s = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const double t = X[a][d] - X[b][d];
+        s += t * t;
+      }
+      h2 = fmax(h2, s);
+    }
+  return h2;
+}
+
+template <int D> constexpr double volume_factor() { return D == 2 ? 0.5 : 1.0 / 6.0; }
+
+// Unnormalised gradients: R[k] = det * grad(lambda_k) (cofactors of the edge matrix), edges from X[0].
+template <int D>
+__device__ __forceinline__ void simplex_cofactors(const double (&X)[D + 1][D], double (&R)[D + 1][D],
+                                                  double& det) {
+  double e[D][D];
+#pragma unroll
+  for (int k = 0; k < D; ++k)
+#pragma unroll
+    for (int d = 0; d < D; ++d) e[k][d] = X[k + 1][d] - X[0][d];
+  if constexpr (D == 2) {
+    R[1][0] = e[1][1];  R[1][1] = -e[1][0];
+    R[2][0] = -e[0][1]; R[2][1] = e[0][0];
+    det = e[0][0] * e[1][1] - e[1][0] * e[0][1];
+  } else {
+    R[1][0] = e[1][1] * e[2][2] - e[1][2] * e[2][1];
+    R[1][1] = e[1][2] * e[2][0] - e[1][0] * e[2][2];
+    R[1][2] = e[1][0] * e[2][1] - e[1][1] * e[2][0];
+    R[2][0] = e[2][1] * e[0][2] - e[2][2] * e[0][1];
+    R[2][1] = e[2][2] * e[0][0] - e[2][0] * e[0][2];
+    R[2][2] = e[2][0] * e[0][1] - e[2][1] * e[0][0];
+    R[3][0] = e[0][1] * e[1][2] - e[0][2] * e[1][1];
+    R[3][1] = e[0][2] * e[1][0] - e[0][0] * e[1][2];
+    R[3][2] = e[0][0] * e[1][1] - e[0][1] * e[1][0];
+    det = e[0][0] * R[1][0] + e[0][1] * R[1][1] + e[0][2] * R[1][2];
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    double s = R[1][d];
+#pragma unroll
+    for (int k = 2; k <= D; ++k) s += R[k][d];
+    R[0][d] = -s;
+  }
+}
+
+// Row 0 of the cell tensor of simplex X (local vertex 0 = the row's vertex): dx((1,2)) stiffness,
+// dx(2) stabilisation (main.py:105,107-112) and entry 0 of the load vector (:126-128).
+// Appendix B closed forms with every gradient left scaled by det (G = R / det), so that one reciprocal
+// and ~125 fp64 operations give the row:
+//   K_j = |K|/((d+1)(d+2)) [ |g|^2 (1 + delta_0j) + a_0 (P + p_j) + (P + p_0) a_j + G_0.G_j mu ]
+//         + 4 sigma h^2 |K| a_0 a_j,     g = grad(phi), a_j = g.G_j, P = sum p, mu = P^2 + sum p^2.
+template <int D>
+__device__ __forceinline__ void cell_row(const double (&X)[D + 1][D], const double (&p)[D + 1],
+                                         const double (&fv)[D + 1], bool is_cut, double sigma,
+                                         double (&K)[D + 1], double& b0) {
+  constexpr int NV = D + 1;
+  constexpr double dfact = D == 2 ? 2.0 : 6.0;
+  double R[NV][D], det;
+  simplex_cofactors<D>(X, R, det);
+  const double inv = 1.0 / det;
+  double gR[D];  // det * grad(phi)
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    double s = (p[1] - p[0]) * R[1][d];
+#pragma unroll
+    for (int k = 2; k < NV; ++k) s += (p[k] - p[0]) * R[k][d];
+    gR[d] = s;
+  }
+  double aR[NV], c0[NV];  // det^2 * a_j, det^2 * G_0.G_j
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    aR[j] = dot<D>(gR, R[j]);
+    c0[j] = dot<D>(R[0], R[j]);
+  }
+  const double ggR = dot<D>(gR, gR);
+  double P = p[0], S2 = p[0] * p[0], F = fv[0], FP = fv[0] * p[0];
+#pragma unroll
+  for (int k = 1; k < NV; ++k) {
+    P += p[k];
+    S2 += p[k] * p[k];
+    F += fv[k];
+    FP += fv[k] * p[k];
+  }
+  const double mu = P * P + S2;
+  const double ainv = fabs(inv), adet = fabs(det);
+  const double w = ainv * (1.0 / (dfact * (D + 1) * (D + 2)));
+  const double P0 = P + p[0];
+  double sh2 = 0.0;  // sigma h_T^2 on cut cells
+  if (is_cut) sh2 = sigma * diameter2<D>(X);
+  const double sR = (4.0 / dfact) * sh2 * ainv * (inv * inv) * aR[0];  // 4 sigma h^2 |K| a_0 / det^2
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+    K[j] = w * (ggR * (j == 0 ? 2.0 : 1.0) + aR[0] * (P + p[j]) + P0 * aR[j] + c0[j] * mu) + sR * aR[j];
+  constexpr double fact_d3 = D == 2 ? 120.0 : 720.0;
+  b0 = adet * ((1.0 / fact_d3) * ((F * P + FP) + fv[0] * P + F * p[0] + 2.0 * fv[0] * p[0]) -
+               (2.0 / (dfact * NV)) * sh2 * F * aR[0] * (inv * inv));
+}
+
+__device__ __forceinline__ double alpha3(int a, int b, int c) {
+  return (double)((1 + (a == b)) * (1 + (a == c) + (b == c)));
+}
+
+// Row 0 of -int_F (grad(phi w).n) phi v (main.py:106) on the facet [X[0..D-1]] of simplex X; local
+// vertex D is the one opposite the facet, the row's vertex is facet vertex 0.  K[j] = entry (0, j).
+template <int D>
+__device__ __forceinline__ void boundary_row(const double (&X)[D + 1][D], const double (&p)[D + 1],
+                                             double (&K)[D + 1]) {
+  constexpr int NV = D + 1;
+  double G[NV][D], det;
+  simplex_gradients<D>(X, G, det);
+  const double vol = fabs(det) * volume_factor<D>();
+  const double gnorm = sqrt(dot<D>(G[D], G[D]));
+  double n[D], g[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    n[d] = -G[D][d] / gnorm;  // outward normal of THIS cell (tests/test_one_sided_integral.py pins it)
+    double s = p[0] * G[0][d];
+#pragma unroll
+    for (int k = 1; k < NV; ++k) s += p[k] * G[k][d];
+    g[d] = s;
+  }
+  const double gn = dot<D>(g, n);
+  constexpr double cfac = D == 2 ? 1.0 / 24.0 : 2.0 / 120.0;  // (d-1)!/(d+2)!
+  const double cF = D * vol * gnorm * cfac;
+  double Q = 0.0;
+#pragma unroll
+  for (int k = 0; k < D; ++k)
+#pragma unroll
+    for (int l = 0; l < D; ++l) Q += p[k] * p[l] * alpha3(l, k, 0);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    double W = 0.0;
+    if (j < D) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) W += p[k] * alpha3(j, k, 0);
+    }
+    K[j] = -cF * (gn * W + dot<D>(G[j], n) * Q);
+  }
+}
+
+// One row of sigma avg(h_T) int_F jump.jump (main.py:113-118) over the facet macro element
+// M = [facet vertices 0..D-1, opposite vertex of cell A, opposite vertex of cell B]; `arow` (0 or D) is
+// the macro index of the row's vertex.  K[m] = entry (row, M[m]).
+//
+// With N = the facet's cofactor vector (normal scaled by (D-1)! |F|, the same for both cells) the normal
+// derivative of lambda_a seen from cell s is  Gn_a = -(R_a . N) / (|det_s| |N|),  and the jump of
+// grad(phi w_m).n at facet vertex k is  delta_mk [m on F] gsum + c_m phi_k  with gsum = sum_s grad(phi).n_s,
+// c_m = sum_s Gn_m.  The facet mass matrix |F| (1 + delta_kl) / (D (D+1)) then gives the entries in closed
+// form from c, gsum, sum phi_k and sum phi_k^2.
+template <int D>
+__device__ __forceinline__ void ghost_row(const double (&M)[D + 2][D], const double (&pm)[D + 2],
+                                          int arow, double sigma, double (&K)[D + 2]) {
+  constexpr int NV = D + 1, NG = D + 2;
+  double c[NG], N[D], nn = 0.0, rn = 0.0, gsum = 0.0, hsum = 0.0;
+#pragma unroll
+  for (int m = 0; m < NG; ++m) c[m] = 0.0;
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    double X[NV][D], p[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int m = k < D ? k : D + side;
+      p[k] = pm[m];
+#pragma unroll
+      for (int d = 0; d < D; ++d) X[k][d] = M[m][d];
+    }
+    double R[NV][D], det;
+    simplex_cofactors<D>(X, R, det);
+    if (side == 0) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) N[d] = R[D][d];
+      nn = dot<D>(N, N);
+      rn = rsqrt(nn);
+    }
+    const double scale = -rn / fabs(det);
+#pragma unroll
+    for (int a = 0; a < NV; ++a) {
+      const double Gn = dot<D>(R[a], N) * scale;
+      gsum += p[a] * Gn;
+      c[a < D ? a : D + side] += Gn;
+    }
+    hsum += sqrt(diameter2<D>(X));
+  }
+  const double area = nn * rn * (D == 2 ? 1.0 : 0.5);  // |N| / (D-1)!
+  const double coef = sigma * 0.5 * hsum * area * (1.0 / (D * (D + 1)));
+  double Pf = pm[0], Sf2 = pm[0] * pm[0];
+#pragma unroll
+  for (int k = 1; k < D; ++k) {
+    Pf += pm[k];
+    Sf2 += pm[k] * pm[k];
+  }
+  const bool onf = arow == 0;  // the row's vertex is facet vertex 0, else the opposite vertex of cell A
+  const double ca = onf ? c[0] : c[D];
+  const double ga = onf ? gsum : 0.0;  // delta part of the row's jump
+  const double Jsa = ga + ca * Pf;
+#pragma unroll
+  for (int m = 0; m < NG; ++m) {
+    const double gm = m < D ? gsum : 0.0;
+    const double Jsm = gm + c[m] * Pf;
+    double cross = ca * c[m] * Sf2 + ga * c[m] * pm[0];
+    if (m < D) cross += ca * gm * pm[m];
+    if (m == 0) cross += ga * gm;
+    K[m] = coef * (Jsa * Jsm + cross);
+  }
+}
+
+template <int D>
+__device__ __forceinline__ void load_vertex(const double* __restrict__ x, const double* __restrict__ phi,
+                                            int v, double (&xv)[D], double& p) {
+#pragma unroll
+  for (int d = 0; d < D; ++d) xv[d] = __ldg(x + (int64_t)v * D + d);
+  p = __ldg(phi + v);
+}
+
+enum { kCells = 0, kGhost = 1, kBoundary = 2 };
+
+// coordinates, phi and f of the D other vertices of a cell record
+template <int D>
+struct Others {
+  double X[D][D], p[D], f[D];
+};
+
+// One pass over one row list.  KIND == kCells writes data / b of its rows, the surface passes add to them.
+template <int D, int KIND>
+__global__ void __launch_bounds__(kRowsBlock, 4) k_assemble_rows_p1(
+    const double* __restrict__ x, const double* __restrict__ phi, const double* __restrict__ f,
+    double sigma, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+    phifem_row_list rl, double* __restrict__ data, double* __restrict__ b) {
+  constexpr int NV = D + 1, NG = D + 2;
+  extern __shared__ double acc_s[];  // accumulator k of thread t at acc_s[k * kRowsBlock + t]
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t li = (int64_t)blockIdx.x * kRowsBlock + tid;
+  const int slice = (int)(li >> 5);
+  if (li >= rl.n_listed) return;  // no block-wide barrier below
+  const int r = __ldg(rl.rows + li);
+  const int start = __ldg(indptr + r);
+  const int nnz = __ldg(indptr + r + 1) - start;
+  const int dpos = __ldg(rl.diag_pos + li);
+  const int32_t* __restrict__ cols = indices + start;
+  double* acc = acc_s + tid;
+  for (int k = 0; k < nnz; ++k) acc[k * kRowsBlock] = 0.0;
+  double xr[D], pr;
+  load_vertex<D>(x, phi, r, xr, pr);
+  double diag = 0.0, br = 0.0;
+  const int kb = __ldg(rl.ptr + slice), ke = __ldg(rl.ptr + slice + 1);
+
+  if constexpr (KIND == kCells) {  // cells tagged 1 / 2 containing vertex r
+    // Four records in flight per thread, one per dependent-load level: while record k is evaluated the
+    // vertex data of record k+1 is arriving, the column indices of record k+2 have been requested and so
+    // has the word of record k+3.  The two data buffers swap roles (loop unrolled by two) so that no
+    // register-to-register copies are needed.
+    const double fr = __ldg(f + r);
+    auto fetch_rec = [&](int k) { return k < ke ? __ldg(rl.rec + (int64_t)k * 32 + lane) : kPad; };
+    auto fetch_idx = [&](uint32_t rec, int (&v)[D]) {
+      const uint32_t q = rec == kPad ? 0u : rec;  // pads gather the row's first column: harmless
+#pragma unroll
+      for (int j = 0; j < D; ++j) v[j] = __ldg(cols + ((q >> (8 * j)) & 0xff));
+    };
+    auto fetch_data = [&](const int (&v)[D], Others<D>& o) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        load_vertex<D>(x, phi, v[j], o.X[j], o.p[j]);
+        o.f[j] = __ldg(f + v[j]);
+      }
+    };
+    uint32_t w0 = fetch_rec(kb), w1 = fetch_rec(kb + 1), w2 = fetch_rec(kb + 2);
+    int v1[D];
+    Others<D> A, B;
+    if (kb < ke) {
+      fetch_idx(w0, v1);
+      fetch_data(v1, A);
+      fetch_idx(w1, v1);
+    }
+    // on entry: `cur` holds the data of record k (word w0), v1 the column indices of record k+1 (word w1),
+    // w2 the word of record k+2
+    auto body = [&](int k, const Others<D>& cur, Others<D>& nxt) {
+      fetch_data(v1, nxt);
+      fetch_idx(w2, v1);
+      const uint32_t w3 = fetch_rec(k + 3);
+      if (w0 != kPad) {
+        double X[NV][D], p[NV], fv[NV];
+#pragma unroll
+        for (int d = 0; d < D; ++d) X[0][d] = xr[d];
+        p[0] = pr;
+        fv[0] = fr;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+#pragma unroll
+          for (int d = 0; d < D; ++d) X[j + 1][d] = cur.X[j][d];
+          p[j + 1] = cur.p[j];
+          fv[j + 1] = cur.f[j];
+        }
+        double K[NV], b0;
+        cell_row<D>(X, p, fv, (w0 >> 24) & 1u, sigma, K, b0);
+        diag += K[0];
+        br += b0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) acc[((w0 >> (8 * j)) & 0xff) * kRowsBlock] += K[j + 1];
+      }
+      w0 = w1;
+      w1 = w2;
+      w2 = w3;
+    };
+    for (int k = kb; k < ke; k += 2) {
+      body(k, A, B);
+      if (k + 1 < ke) body(k + 1, B, A);
+    }
+  } else if constexpr (KIND == kGhost) {  // interior facets tagged 2 / 3 whose macro element contains r
+    for (int k = kb; k < ke; ++k) {
+      const uint2 cur = __ldg(reinterpret_cast<const uint2*>(rl.rec) + (int64_t)k * 32 + lane);
+      if (cur.y == kPad) continue;
+      const int role = (int)cur.y;
+      int pos[NV];
+      double O[NV][D], po[NV];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        pos[j] = (cur.x >> (8 * j)) & 0xff;
+        load_vertex<D>(x, phi, __ldg(cols + pos[j]), O[j], po[j]);
+      }
+      // role 0: M = [r, O0..O(D-2) | O(D-1), O(D)];  role 1: M = [O0..O(D-1) | r, O(D)]
+      double M[NG][D], pm[NG];
+#pragma unroll
+      for (int m = 0; m < NG; ++m) {
+        const int j0 = m == 0 ? 0 : m - 1;           // role 0 source (m == 0: the row's vertex)
+        const int j1 = m < D ? m : (m == D ? 0 : D);  // role 1 source (m == D: the row's vertex)
+        const bool own = role == 0 ? m == 0 : m == D;
+#pragma unroll
+        for (int d = 0; d < D; ++d) M[m][d] = own ? xr[d] : (role == 0 ? O[j0][d] : O[j1][d]);
+        pm[m] = own ? pr : (role == 0 ? po[j0] : po[j1]);
+      }
+      double K[NG];
+      ghost_row<D>(M, pm, role == 0 ? 0 : D, sigma, K);
+      if (role == 0) {
+        diag += K[0];
+#pragma unroll
+        for (int m = 1; m < NG; ++m) acc[pos[m - 1] * kRowsBlock] += K[m];
+      } else {
+        diag += K[D];
+#pragma unroll
+        for (int m = 0; m < D; ++m) acc[pos[m] * kRowsBlock] += K[m];
+        acc[pos[D] * kRowsBlock] += K[D + 1];
+      }
+    }
+  } else {  // one-sided facets of ds(100) having r as a vertex
+    for (int k = kb; k < ke; ++k) {
+      const uint32_t cur = __ldg(rl.rec + (int64_t)k * 32 + lane);
+      if (cur == kPad) continue;
+      int pos[D];
+      double X[NV][D], p[NV];
+#pragma unroll
+      for (int d = 0; d < D; ++d) X[0][d] = xr[d];
+      p[0] = pr;
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        pos[j] = (cur >> (8 * j)) & 0xff;
+        const int loc = j == 0 ? D : j;  // byte 0 names the vertex opposite the facet
+        load_vertex<D>(x, phi, __ldg(cols + pos[j]), X[loc], p[loc]);
+      }
+      double K[NV];
+      boundary_row<D>(X, p, K);
+      diag += K[0];
+      acc[pos[0] * kRowsBlock] += K[D];
+#pragma unroll
+      for (int j = 1; j < D; ++j) acc[pos[j] * kRowsBlock] += K[j];
+    }
+  }
+  acc[dpos * kRowsBlock] += diag;
+  if constexpr (KIND == kCells) {
+    for (int k = 0; k < nnz; ++k) data[start + k] = acc[k * kRowsBlock];
+    b[r] = br;
+  } else {
+    for (int k = 0; k < nnz; ++k) data[start + k] += acc[k * kRowsBlock];
+  }
+}
+
+}  // namespace
+}  // namespace phifem
+
+using namespace phifem;
+
+namespace {
+bool list_ok(const phifem_row_list& l) {
+  return l.n_listed == 0 || (l.rows && l.diag_pos && l.ptr && l.rec);
+}
+}  // namespace
+
+extern "C" int phifem_assemble_rows_p1(const phifem_mesh* mesh, const double* phi, const double* f,
+                                       double sigma, const phifem_rows_plan* plan, double* data,
+                                       double* b, void* stream) {
+  PHIFEM_CHECK_ARG(mesh != nullptr && mesh->x, "mesh is null");
+  if (mesh->cell_type != PHIFEM_TRIANGLE && mesh->cell_type != PHIFEM_TETRAHEDRON) {
+    set_error("P1 assembly supports triangles and tetrahedra, got cell type %d", mesh->cell_type);
+    return PHIFEM_ERR_UNSUPPORTED;
+  }
+  PHIFEM_CHECK_ARG(mesh->gdim == (mesh->cell_type == PHIFEM_TRIANGLE ? 2 : 3), "gdim mismatch");
+  PHIFEM_CHECK_ARG(phi && f && plan && data && b, "null pointer");
+  if (plan->cells.n_listed == 0) return PHIFEM_OK;
+  PHIFEM_CHECK_ARG(plan->indptr && plan->indices, "CSR pattern is null");
+  PHIFEM_CHECK_ARG(list_ok(plan->cells) && list_ok(plan->ghost) && list_ok(plan->boundary),
+                   "row list arrays are null");
+  PHIFEM_CHECK_ARG(plan->max_row_nnz > 0 && plan->max_row_nnz <= 255, "plan.max_row_nnz out of range");
+  const size_t smem = (size_t)plan->max_row_nnz * kRowsBlock * sizeof(double);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t err = cudaSuccess;
+  auto launch = [&](auto kernel, const phifem_row_list& rl) {
+    if (rl.n_listed == 0 || err != cudaSuccess) return;
+    if (smem > 48 * 1024)
+      err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t grid = (rl.n_listed + kRowsBlock - 1) / kRowsBlock;
+    if (err == cudaSuccess)
+      kernel<<<(unsigned)grid, kRowsBlock, smem, st>>>(mesh->x, phi, f, sigma, plan->indptr, plan->indices,
+                                                       rl, data, b);
+  };
+  if (mesh->cell_type == PHIFEM_TRIANGLE) {
+    launch(k_assemble_rows_p1<2, kCells>, plan->cells);
+    launch(k_assemble_rows_p1<2, kGhost>, plan->ghost);
+    launch(k_assemble_rows_p1<2, kBoundary>, plan->boundary);
+  } else {
+    launch(k_assemble_rows_p1<3, kCells>, plan->cells);
+    launch(k_assemble_rows_p1<3, kGhost>, plan->ghost);
+    launch(k_assemble_rows_p1<3, kBoundary>, plan->boundary);
+  }
+  if (err != cudaSuccess) {
+    set_error("phifem_assemble_rows_p1: cannot reserve %zu bytes of shared memory: %s", smem,
+              cudaGetErrorString(err));
+    return PHIFEM_ERR_CUDA;
+  }
+  PHIFEM_CHECK_LAUNCH();
+  return PHIFEM_OK;
+}

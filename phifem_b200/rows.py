@@ -1,0 +1,223 @@
+"""Symbolic phase of the row-gather assembly (csrc/assemble_rows.cu, k_assemble_rows_p1).
+
+Turns an `AssemblyPlan` (CSR pattern + entity lists + entity -> CSR-slot maps) into the arrays of
+`phifem_rows_plan` (include/phifem_b200.h): for every row with pattern entries, the list of entities
+touching its vertex, each entity written as the positions -- inside the row's own column list -- of its
+other vertices.  Three record kinds (cells, ghost-penalty facets, one-sided facets), each stored as
+sliced ELLPACK over groups of 32 consecutive listed rows so that a warp reads one coalesced 128-byte
+line per step.
+
+Sort/scatter plumbing written with torch ops; runs on the device of the mesh (CPU tensors work too,
+which is how the CPU tests check it against the oracle).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+PAD = 0xFFFFFFFF
+MAX_ROW_NNZ = 255            # positions are uint8
+MAX_SMEM_BYTES = 200 * 1024  # accumulators of one CTA (128 threads x max_row_nnz doubles)
+BLOCK = 128
+
+
+def morton_order(x, rows):
+    """Listed rows sorted along a Morton curve of their vertex coordinates (21 bits per axis)."""
+    pts = x[rows]
+    lo, hi = pts.min(dim=0).values, pts.max(dim=0).values
+    q = ((pts - lo) / (hi - lo).clamp(min=1e-300) * (2 ** 21 - 1)).long().clamp_(0, 2 ** 21 - 1)
+    d = pts.shape[1]
+    key = torch.zeros(len(rows), dtype=torch.int64, device=x.device)
+    for bit in range(21):
+        for k in range(d):
+            key |= ((q[:, k] >> bit) & 1) << (bit * d + k)
+    return rows[torch.argsort(key, stable=True)]
+
+
+class RowList:
+    """One record kind of the plan: the rows it touches (processing order), the position of each row's
+    diagonal entry, and the records as sliced ELLPACK -- record k of lane l of slice s (= listed rows
+    [32 s, 32 s + 32)) at rec[((ptr[s] + k) * 32 + l) * words]; pads are all-ones words; the records of a
+    row keep their input order."""
+
+    def __init__(self, rows, diag_slot, indptr, rec_rows, words, n_rows, balance=False):
+        """rows [L] int64 (processing order); rec_rows [m] row id of each record; words [m, w].
+        balance: re-sort the rows by record count (descending, stable) so that the 32 rows of a slice
+        carry the same number of records -- for the short surface lists, whose data stays in L2 anyway."""
+        dev = rows.device
+        i64 = dict(dtype=torch.int64, device=dev)
+        if balance and rows.numel():
+            per_row = torch.bincount(rec_rows, minlength=n_rows)[rows]
+            rows = rows[torch.argsort(per_row, descending=True, stable=True)]
+        self.n_listed = int(rows.numel())
+        self.n_slices = (self.n_listed + 31) // 32
+        self.words = w = words.shape[1]
+        self.n_records = int(rec_rows.numel())
+        self.rows = rows.to(torch.int32).contiguous()
+        self.diag_pos = (diag_slot[rows] - indptr[rows]).to(torch.uint8).contiguous()
+        ns = self.n_slices
+        li_of_row = torch.full((n_rows,), -1, **i64)
+        li_of_row[rows] = torch.arange(self.n_listed, **i64)
+        li = li_of_row[rec_rows]
+        assert self.n_records == 0 or int(li.min()) >= 0, "a record names a row outside its list"
+        counts = torch.bincount(li, minlength=ns * 32)[:ns * 32]
+        width = counts.reshape(ns, 32).max(dim=1).values if ns else torch.zeros(0, **i64)
+        ptr = torch.zeros(ns + 1, **i64)
+        ptr[1:] = torch.cumsum(width, 0)
+        total = int(ptr[-1])
+        if total * 32 * w >= 2 ** 31:
+            raise NotImplementedError("row-gather plan: record array exceeds 2^31 words")
+        rec = torch.full((max(total, 1) * 32, w), PAD, **i64)
+        if self.n_records:
+            order = torch.argsort(li, stable=True)
+            ls = li[order]
+            first = torch.cumsum(counts, 0) - counts                 # first sorted record of each row
+            k = torch.arange(ls.numel(), **i64) - first[ls]          # rank inside the row
+            rec[(ptr[ls >> 5] + k) * 32 + (ls & 31)] = words[order]
+        rec = rec.reshape(-1)
+        rec = torch.where(rec >= 2 ** 31, rec - 2 ** 32, rec).to(torch.int32)   # same bits as uint32
+        self.ptr, self.rec = ptr.to(torch.int32).contiguous(), rec.contiguous()
+
+    def c_struct(self):
+        p = _lib.ptr
+        return _lib.CRowList(self.n_listed, p(self.rows), p(self.diag_pos), p(self.ptr), p(self.rec))
+
+    def nbytes(self):
+        return int(sum(t.numel() * t.element_size() for t in (self.rows, self.diag_pos, self.ptr, self.rec)))
+
+    def padding(self):
+        """Fraction of record slots that are pads (lanes idling in the record loop)."""
+        return 1.0 - self.n_records * self.words / max(1, self.rec.numel())
+
+
+def _pack_bytes(pos):
+    """[m, k<=4] small non-negative ints -> one word per row, byte j = pos[:, j]."""
+    word = torch.zeros(pos.shape[0], dtype=torch.int64, device=pos.device)
+    for j in range(pos.shape[1]):
+        word |= pos[:, j] << (8 * j)
+    return word
+
+
+class RowsPlan:
+    def __init__(self, plan, order="natural"):
+        mesh = plan.mesh
+        dev = mesh.device
+        d = mesh.gdim
+        nv = d + 1
+        n = plan.n_rows
+        i64 = dict(dtype=torch.int64, device=dev)
+        self.plan = plan
+        indptr = plan.indptr.long()
+        row_nnz = indptr[1:] - indptr[:-1]
+        listed = torch.nonzero(row_nnz > 0).reshape(-1)
+        self.max_row_nnz = int(row_nnz.max()) if listed.numel() else 0
+        if self.max_row_nnz > MAX_ROW_NNZ or self.max_row_nnz * BLOCK * 8 > MAX_SMEM_BYTES:
+            raise NotImplementedError(
+                "row-gather assembly: a row holds %d entries (limit %d); use the atomic scatter kernels "
+                "for this mesh" % (self.max_row_nnz, min(MAX_ROW_NNZ, MAX_SMEM_BYTES // (BLOCK * 8))))
+        if order not in ("natural", "morton"):
+            raise ValueError("order must be 'natural' or 'morton'")
+        self.order = order
+
+        def ordered(rows):
+            """Unique row ids in processing order."""
+            rows = torch.unique(rows)
+            return morton_order(mesh.x, rows) if order == "morton" and rows.numel() else rows
+
+        # diagonal slot: the pattern holds (r, r) for every listed row (each entity couples its vertices
+        # with themselves)
+        cols = plan.indices.long()
+        row_of_slot = torch.repeat_interleave(torch.arange(n, **i64), row_nnz)
+        is_diag = cols == row_of_slot
+        dslot = torch.full((n,), -1, **i64)
+        dslot[row_of_slot[is_diag]] = torch.nonzero(is_diag).reshape(-1)
+        assert bool((dslot[listed] >= 0).all()), "a listed row has no diagonal entry"
+        del row_of_slot, is_diag, cols
+
+        # ---- cells: one record per (vertex of an active cell); list = every row of the pattern ------
+        cells_act = mesh.cells[plan.active.long()].long()                       # [Na, nv]
+        slots = plan.slots_cells.long().reshape(-1, nv, nv)                     # slot of (row i, col j)
+        cut = (plan.cell_tags8[plan.active.long()] == 2).long()
+        words = []
+        for i in range(nv):
+            others = [j for j in range(nv) if j != i]
+            pos = slots[:, i, others] - indptr[cells_act[:, i]][:, None]
+            words.append(_pack_bytes(pos) | (cut << 24))
+        # interleaved so that the records of a row keep cell order (deterministic summation order)
+        self.cells = RowList(ordered(listed), dslot, indptr, cells_act.reshape(-1),
+                             torch.stack(words, dim=1).reshape(-1, 1), n)
+        del slots, cells_act, words
+
+        # ---- ghost-penalty facets: one record per distinct vertex of the macro element ------------------
+        from .assemble import ghost_macro_vertices
+        ng = int(plan.ghost.numel())
+        if ng:
+            mac = ghost_macro_vertices(mesh, plan.ghost)                         # [ng, nv+1]
+            gs = plan.slots_ghost.long().reshape(-1, nv + 1, nv + 1)
+            words = []
+            for a in range(nv + 1):
+                if a < d:       # facet vertex: others = other facet vertices, opposite A, opposite B
+                    others = [j for j in range(d) if j != a] + [d, d + 1]
+                    role = 0
+                elif a == d:    # opposite vertex of cell A: others = facet vertices, opposite B
+                    others = list(range(d)) + [d + 1]
+                    role = 1
+                else:           # opposite vertex of cell B: same, with the sides swapped
+                    others = list(range(d)) + [d]
+                    role = 1
+                pos = gs[:, a, others] - indptr[mac[:, a]][:, None]
+                words.append(torch.stack([_pack_bytes(pos), torch.full((ng,), role, **i64)], dim=1))
+            rec_rows, words = mac.reshape(-1), torch.stack(words, dim=1).reshape(-1, 2)
+        else:
+            rec_rows, words = torch.zeros(0, **i64), torch.zeros((0, 2), **i64)
+        self.ghost = RowList(ordered(rec_rows), dslot, indptr, rec_rows, words, n, balance=True)
+
+        # ---- one-sided facets: one record per facet vertex of each (cell, local facet) entity --------------
+        ne = int(plan.entities.shape[0])
+        if ne:
+            ec = plan.entities[:, 0].long()
+            eo = plan.entities[:, 1].long()
+            ev = mesh.cells[ec].long()
+            bs = plan.slots_boundary.long().reshape(-1, nv, nv)
+            ar = torch.arange(ne, **i64)
+            loc = torch.arange(nv, **i64)[None, :].expand(ne, nv)
+            fac = loc[loc != eo[:, None]].reshape(ne, d)                # local ids of the facet vertices
+            rec_rows, words = [], []
+            for t in range(d):                      # t-th facet vertex = t-th local vertex != o
+                i = fac[:, t]
+                rest = fac[:, [u for u in range(d) if u != t]]
+                oth = torch.cat([eo[:, None], rest], dim=1)             # opposite vertex first
+                row = ev[ar, i]
+                pos = bs[ar[:, None], i[:, None], oth] - indptr[row][:, None]
+                words.append(_pack_bytes(pos))
+                rec_rows.append(row)
+            rec_rows = torch.stack(rec_rows, dim=1).reshape(-1)
+            words = torch.stack(words, dim=1).reshape(-1, 1)
+        else:
+            rec_rows, words = torch.zeros(0, **i64), torch.zeros((0, 1), **i64)
+        self.boundary = RowList(ordered(rec_rows), dslot, indptr, rec_rows, words, n, balance=True)
+        self._c = None
+
+    def c_struct(self):
+        if self._c is None:
+            p = _lib.ptr
+            pl = self.plan
+            self._c = _lib.CRowsPlan(p(pl.indptr), p(pl.indices), self.max_row_nnz, 0,
+                                     self.cells.c_struct(), self.ghost.c_struct(), self.boundary.c_struct())
+        return self._c
+
+    def index_bytes(self):
+        """Bytes of plan arrays one numeric pass streams besides the CSR pattern itself."""
+        return self.cells.nbytes() + self.ghost.nbytes() + self.boundary.nbytes()
+
+
+def assemble_rows_into(rplan, phi, f, sigma, data, b):
+    """Numeric phase, one launch on the current stream.  `data` needs no zero-fill; `b` must have been
+    zeroed once (rows without pattern entries are never written)."""
+    mesh = rplan.plan.mesh
+    _lib.require_cuda(mesh)
+    _lib.check(_lib.load().phifem_assemble_rows_p1(
+        _lib.c_mesh(mesh), _lib.ptr(phi), _lib.ptr(f), float(sigma), ctypes.byref(rplan.c_struct()),
+        _lib.ptr(data), _lib.ptr(b), _lib.stream()))
+    return data, b

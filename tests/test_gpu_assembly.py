@@ -38,7 +38,8 @@ def _row_scale(indptr, data):
     return scale, rows
 
 
-@pytest.mark.parametrize("method,capacity", [("blocked", None), ("blocked", 2500), ("atomic", None)])
+@pytest.mark.parametrize("method,capacity", [("rows", None), ("rows", "morton"), ("blocked", None),
+                                             ("blocked", 2500), ("atomic", None)])
 @pytest.mark.parametrize("kind,n", [("tri", 40), ("tri-unstructured", 24), ("tet", 10),
                                     ("tet-unstructured", 8)])
 def test_cuda_operator_matches_oracle(kind, n, method, capacity):
@@ -47,10 +48,13 @@ def test_cuda_operator_matches_oracle(kind, n, method, capacity):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore", RuntimeWarning)
         ctags, ftags, _, ds, _ = mesh_scripts.compute_tags_measures(mesh, fn, 1, box_mode=True)
-    plan = assemble.build_plan(mesh, ctags, ftags, ds(100), method=method, capacity=capacity)
+    order = "natural"
+    if method == "rows" and capacity:
+        order, capacity = capacity, None
+    plan = assemble.build_plan(mesh, ctags, ftags, ds(100), method=method, capacity=capacity, order=order)
     assert plan.method == method
     A, b = assemble.assemble_strong_dirichlet(plan, phi, f, stab_coef=1.0)
-    if method == "blocked":
+    if method in ("blocked", "rows"):
         # owner-computes sums in a fixed order: bitwise reproducible, and independent of what the
         # output buffers held before (no zero-fill needed for the matrix)
         data2 = torch.full_like(A.data, float("nan"))
@@ -59,6 +63,8 @@ def test_cuda_operator_matches_oracle(kind, n, method, capacity):
         assert torch.equal(data2, A.data) and torch.equal(b2, b)
         if capacity:
             assert plan.blocked.n_blocks > 4
+        if method == "rows":
+            assert plan.rowsplan.order == order and plan.rowsplan.cells.n_records > 0
 
     x = mesh.x.cpu().numpy()
     cells = mesh.cells.cpu().numpy().astype(np.int64)
@@ -150,8 +156,8 @@ def test_cuda_assembly_properties_at_scale():
     with warnings.catch_warnings():
         warnings.simplefilter("ignore", RuntimeWarning)
         ctags, ftags, _, ds, _ = mesh_scripts.compute_tags_measures(mesh, fn, 1, box_mode=True)
-    plan = assemble.build_plan(mesh, ctags, ftags, None, method="blocked")   # no one-sided term
-    assert plan.method == "blocked" and plan.blocked.n_blocks > 148
+    plan = assemble.build_plan(mesh, ctags, ftags, None, method="rows")   # no one-sided term
+    assert plan.method == "rows" and plan.rowsplan.cells.n_slices > 148
     one = torch.ones(mesh.num_vertices, dtype=torch.float64, device="cuda")
     A, b = assemble.assemble_strong_dirichlet(plan, one, one, stab_coef=1.0)
     M = A.to_scipy()
