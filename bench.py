@@ -228,7 +228,8 @@ def run_ours(args):
         ctags, ftags = MeshTags(mesh, tdim, ws.cell_tags), MeshTags(mesh, tdim - 1, ws.facet_tags)
         ctags.tags8, ftags.tags8 = ws.cell_tags8, ws.facet_tags8
         ents = mesh_scripts._integration_entities_dev(mesh, ws.cell_tags8, ws.facet_tags8, 4, (1, 2))
-        plan = assemble.build_plan(mesh, ctags, ftags, ents, method=args.scatter, capacity=args.capacity)
+        plan = assemble.build_plan(mesh, ctags, ftags, ents, method=args.scatter, capacity=args.capacity,
+                                   order=args.order)
         data, b = plan.new_outputs()
     torch.cuda.synchronize()
     symbolic_ms = (time.perf_counter() - t0) * 1e3
@@ -416,6 +417,8 @@ def main():
     ap.add_argument("--scatter", default="rows", choices=["rows", "blocked", "atomic"],
                     help="assembly strategy (row-gather / owner-computes blocks / fp64 reductions)")
     ap.add_argument("--capacity", type=int, default=None, help="contributions per block (blocked scatter)")
+    ap.add_argument("--order", default="natural", choices=["natural", "morton"],
+                    help="row processing order of the row-gather assembly")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     args = ap.parse_args()

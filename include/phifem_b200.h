@@ -81,6 +81,8 @@ enum {
   PHIFEM_CNT_EXTERIOR = 2,     /* cells tagged 3 */
   PHIFEM_CNT_UNTAGGED = 3,     /* cells with NaN ratio */
   PHIFEM_CNT_ZERO_DEN = 4,     /* cells whose dx-denominator is ~0 (RuntimeWarning, :129-133) */
+  PHIFEM_CNT_ZERO_DEN_AMBIGUOUS = 5, /* uncut cells whose ~0 test was skipped by the P1 fast path: if slot 4
+                                  is 0 and this one is not, call again with bit 1 of single_layer_cut set */
   PHIFEM_CNT_FACET_ZERO_DEN = 11, /* cells whose ds-denominator is ~0 */
   PHIFEM_CNT_FACET_CONFLICT = 12, /* facets the reference algebra would emit twice */
   PHIFEM_CNT_BOUNDARY_OWNERS = 13, /* cells owning at least one mesh-boundary facet */
@@ -99,8 +101,9 @@ int phifem_cell_points(const phifem_mesh* mesh, const double* shape, int32_t n_p
 /* Replaces `_compute_detection_vector` (:95-134) + `_tag_cells` (:284-390) for the `dx` detection
  * measure: cell_tags[n_cells] in {1 interior, 2 cut, 3 exterior, 0 untagged}; cell_tags8 is the
  * same as int8 (consumed by the facet / assembly kernels).  `counters` (int64[PHIFEM_N_COUNTERS])
- * must be zeroed by the caller; slots 0..4 are accumulated.  single_layer_cut != 0 applies
- * :349-358 and needs `vertex_scratch` (uint8[n_vertices], any content). */
+ * must be zeroed by the caller; slots 0..5 are accumulated.  single_layer_cut: bit 0 applies
+ * :349-358; bit 1 makes the P1 fast path evaluate every denominator exactly (see slot 5).  `vertex_scratch` (uint8[n_vertices + 3], any content) holds the per-vertex class bytes of
+ * the P1 classifier (sign of phi, evaluated once per vertex) and the flags of single_layer_cut. */
 int phifem_tag_cells(const phifem_mesh* mesh, const phifem_levelset* ls, int32_t single_layer_cut,
                      int32_t* cell_tags, int8_t* cell_tags8, uint8_t* vertex_scratch,
                      int64_t* counters, void* stream);

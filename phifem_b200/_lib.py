@@ -9,11 +9,11 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libphifem_b200.so")
+LIB_PATH = os.environ.get("PHIFEM_B200_LIB") or os.path.join(_HERE, "libphifem_b200.so")
 
 CELL_TYPE_ID = {"triangle": 0, "quadrilateral": 1, "tetrahedron": 2}
 N_COUNTERS = 16
-CNT_INTERIOR, CNT_CUT, CNT_EXTERIOR, CNT_UNTAGGED, CNT_ZERO_DEN = 0, 1, 2, 3, 4
+CNT_INTERIOR, CNT_CUT, CNT_EXTERIOR, CNT_UNTAGGED, CNT_ZERO_DEN, CNT_ZERO_DEN_AMBIGUOUS = 0, 1, 2, 3, 4, 5
 CNT_FACET_ZERO_DEN, CNT_FACET_CONFLICT, CNT_BOUNDARY_OWNERS = 11, 12, 13
 
 _vp = ctypes.c_void_p

@@ -19,6 +19,9 @@ namespace phifem {
 namespace {
 
 constexpr int kRowsBlock = 128;
+#ifndef PHIFEM_ROWS_MINBLOCKS
+#define PHIFEM_ROWS_MINBLOCKS 4
+#endif
 constexpr uint32_t kPad = 0xffffffffu;
 
 template <int D>
@@ -301,7 +304,7 @@ struct Others {
 
 // One pass over one row list.  KIND == kCells writes data / b of its rows, the surface passes add to them.
 template <int D, int KIND>
-__global__ void __launch_bounds__(kRowsBlock, 4) k_assemble_rows_p1(
+__global__ void __launch_bounds__(kRowsBlock, KIND == kGhost ? 3 : PHIFEM_ROWS_MINBLOCKS) k_assemble_rows_p1(
     const double* __restrict__ x, const double* __restrict__ phi, const double* __restrict__ f,
     double sigma, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
     phifem_row_list rl, double* __restrict__ data, double* __restrict__ b) {
@@ -385,17 +388,30 @@ __global__ void __launch_bounds__(kRowsBlock, 4) k_assemble_rows_p1(
       if (k + 1 < ke) body(k + 1, B, A);
     }
   } else if constexpr (KIND == kGhost) {  // interior facets tagged 2 / 3 whose macro element contains r
-    for (int k = kb; k < ke; ++k) {
-      const uint2 cur = __ldg(reinterpret_cast<const uint2*>(rl.rec) + (int64_t)k * 32 + lane);
-      if (cur.y == kPad) continue;
-      const int role = (int)cur.y;
-      int pos[NV];
-      double O[NV][D], po[NV];
+    // Same pipeline as the cell pass with a single data buffer: the role selection below copies the
+    // buffer into the macro element, after which the gathers of the next record can overwrite it.
+    const uint2* __restrict__ recs = reinterpret_cast<const uint2*>(rl.rec);
+    const uint2 pad2 = make_uint2(0u, kPad);
+    auto fetch_rec = [&](int k) { return k < ke ? __ldg(recs + (int64_t)k * 32 + lane) : pad2; };
+    auto fetch_idx = [&](uint2 rec, int (&v)[NV]) {
+      const uint32_t q = rec.y == kPad ? 0u : rec.x;
 #pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        pos[j] = (cur.x >> (8 * j)) & 0xff;
-        load_vertex<D>(x, phi, __ldg(cols + pos[j]), O[j], po[j]);
-      }
+      for (int j = 0; j < NV; ++j) v[j] = __ldg(cols + ((q >> (8 * j)) & 0xff));
+    };
+    double O[NV][D], po[NV];
+    auto fetch_data = [&](const int (&v)[NV]) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) load_vertex<D>(x, phi, v[j], O[j], po[j]);
+    };
+    uint2 w0 = fetch_rec(kb), w1 = fetch_rec(kb + 1), w2 = fetch_rec(kb + 2);
+    int v1[NV];
+    if (kb < ke) {
+      fetch_idx(w0, v1);
+      fetch_data(v1);
+      fetch_idx(w1, v1);
+    }
+    for (int k = kb; k < ke; ++k) {
+      const int role = (int)w0.y;
       // role 0: M = [r, O0..O(D-2) | O(D-1), O(D)];  role 1: M = [O0..O(D-1) | r, O(D)]
       double M[NG][D], pm[NG];
 #pragma unroll
@@ -407,17 +423,24 @@ __global__ void __launch_bounds__(kRowsBlock, 4) k_assemble_rows_p1(
         for (int d = 0; d < D; ++d) M[m][d] = own ? xr[d] : (role == 0 ? O[j0][d] : O[j1][d]);
         pm[m] = own ? pr : (role == 0 ? po[j0] : po[j1]);
       }
+      const uint2 cur = w0;
+      fetch_data(v1);
+      fetch_idx(w2, v1);
+      w0 = w1;
+      w1 = w2;
+      w2 = fetch_rec(k + 3);
+      if (cur.y == kPad) continue;
       double K[NG];
       ghost_row<D>(M, pm, role == 0 ? 0 : D, sigma, K);
       if (role == 0) {
         diag += K[0];
 #pragma unroll
-        for (int m = 1; m < NG; ++m) acc[pos[m - 1] * kRowsBlock] += K[m];
+        for (int m = 1; m < NG; ++m) acc[((cur.x >> (8 * (m - 1))) & 0xff) * kRowsBlock] += K[m];
       } else {
         diag += K[D];
 #pragma unroll
-        for (int m = 0; m < D; ++m) acc[pos[m] * kRowsBlock] += K[m];
-        acc[pos[D] * kRowsBlock] += K[D + 1];
+        for (int m = 0; m < D; ++m) acc[((cur.x >> (8 * m)) & 0xff) * kRowsBlock] += K[m];
+        acc[((cur.x >> (8 * D)) & 0xff) * kRowsBlock] += K[D + 1];
       }
     }
   } else {  // one-sided facets of ds(100) having r as a vertex

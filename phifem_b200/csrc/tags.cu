@@ -174,15 +174,49 @@ __device__ __noinline__ int tag_cell_exact(const double* __restrict__ x, int v0,
   return classify(num, den) | ((int)is_close_to_zero(den) << 8);
 }
 
+// Level-set evaluation over the vertices (= P1 dofs), one coalesced pass: a class byte per vertex
+//   bit 0: phi > 0   bit 1: phi < 0   bit 2: 1e-150 <= |phi| <= 1e150 (products cannot over/underflow)
+//   bit 3: |phi| * detj_min > 2e-8 (one such vertex puts the cell's denominator clear of the
+//          RuntimeWarning threshold of mesh_scripts.py:129, whatever the other vertices hold)
+//   bit 4: 4 |phi| * detj_max < 0.5e-8 (all vertices such: the denominator is below the threshold)
+// The cell kernel then gathers 1 byte per vertex instead of 8 (the byte array of 8.6 M vertices stays in
+// L1/L2), and reads phi itself only for the few cells the bytes cannot decide.
+__global__ void __launch_bounds__(kBlock) k_vertex_class(const double* __restrict__ phi, int64_t n,
+                                                         double detj_min, double detj_max,
+                                                         uint8_t* __restrict__ vclass) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; base < n; base += stride) {
+    unsigned int packed = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t i = base + k;
+      const double p = i < n ? __ldg(phi + i) : 0.0;
+      const double ap = fabs(p);
+      unsigned int c = (p > 0.0 ? 1u : 0u) | (p < 0.0 ? 2u : 0u);
+      c |= (ap >= 1e-150 && ap <= 1e150) ? 4u : 0u;
+      c |= (ap * detj_min > 2e-8) ? 8u : 0u;
+      c |= (4.0 * ap * detj_max < 0.5e-8) ? 16u : 0u;
+      packed |= c << (8 * k);
+    }
+    if (base + 3 < n) {
+      *reinterpret_cast<unsigned int*>(vclass + base) = packed;  // base is a multiple of 4
+    } else {
+      for (int k = 0; k < 4 && base + k < n; ++k) vclass[base + k] = (uint8_t)(packed >> (8 * k));
+    }
+  }
+}
+
 template <int CT>
 __global__ void __launch_bounds__(kBlock, 3) k_tag_cells_p1(phifem_mesh m, const double* __restrict__ phi,
-                                                            bool have_bounds, int32_t* __restrict__ tags,
+                                                            const uint8_t* __restrict__ vclass,
+                                                            bool exact_zero_den,
+                                                            int32_t* __restrict__ tags,
                                                             int8_t* __restrict__ tags8,
                                                             int64_t* counters) {
   using T = CellTraits<CT>;
-  __shared__ unsigned int scnt[5];
-  BlockCounters cnt(scnt, 5);
-  unsigned int local[5] = {0u, 0u, 0u, 0u, 0u};
+  __shared__ unsigned int scnt[6];
+  BlockCounters cnt(scnt, 6);
+  unsigned int local[6] = {0u, 0u, 0u, 0u, 0u, 0u};
   const int64_t tile = (int64_t)blockDim.x * kUnroll;
   for (int64_t base = (int64_t)blockIdx.x * tile; base < m.n_cells; base += (int64_t)gridDim.x * tile) {
     int v[kUnroll][4];
@@ -200,36 +234,38 @@ __global__ void __launch_bounds__(kBlock, 3) k_tag_cells_p1(phifem_mesh m, const
         for (int k = 0; k < T::nv; ++k) v[u][k] = __ldg(m.cells + cc * T::nv + k);
       }
     }
-    double p[kUnroll][4];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u)
-#pragma unroll
-      for (int k = 0; k < T::nv; ++k) p[u][k] = __ldg(phi + v[u][k]);
+    unsigned int all[kUnroll], any[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      bool allpos = true, allneg = true, sane = true;
-      double sumabs = 0.0;
+      all[u] = 0xffu;
+      any[u] = 0u;
 #pragma unroll
       for (int k = 0; k < T::nv; ++k) {
-        allpos &= p[u][k] > 0.0;
-        allneg &= p[u][k] < 0.0;
-        const double ap = fabs(p[u][k]);
-        sane &= (ap >= 1e-150) & (ap <= 1e150);
-        sumabs += ap;
+        const unsigned int c = __ldg(vclass + v[u][k]);
+        all[u] &= c;
+        any[u] |= c;
       }
-      bool fast = have_bounds && sane && (allpos || allneg);
-      bool zden = false;
-      if (fast) {
-        // den = sum |p| s lies in [sumabs*detj_min, sumabs*detj_max] up to rounding: decide the
-        // isclose(den, 0) flag (atol 1e-8, mesh_scripts.py:129) only when it is unambiguous
-        if (sumabs * m.detj_min > 2e-8) zden = false;
-        else if (sumabs * m.detj_max < 0.5e-8) zden = true;
-        else fast = false;
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      // same sign everywhere and no product can vanish or overflow: num == +-den bit-exactly, the tag
+      // follows from the sign.  The isclose(den, 0) flag behind the RuntimeWarning (mesh_scripts.py:129)
+      // is decided from the magnitude bits where they are conclusive; the rest is counted as ambiguous
+      // (the host re-runs with exact_zero_den only if no cell settled the warning) or evaluated exactly.
+      bool fast = (all[u] & 3u) != 0u && (all[u] & 4u) != 0u;
+      int tag = (all[u] & 1u) ? 3 : 1;
+      bool zden = false, ambiguous = false;
+      if (fast && !(any[u] & 8u)) {
+        if (all[u] & 16u) zden = true;
+        else if (exact_zero_den) fast = false;
+        else ambiguous = true;
       }
-      int tag = allpos ? 3 : 1;
       if (!fast && valid[u]) {
+        double p[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < T::nv; ++k) p[k] = __ldg(phi + v[u][k]);
         const int r = tag_cell_exact<CT>(m.x, v[u][0], v[u][1], v[u][2], T::nv == 4 ? v[u][3] : 0,
-                                         p[u][0], p[u][1], p[u][2], T::nv == 4 ? p[u][3] : 0.0);
+                                         p[0], p[1], p[2], p[3]);
         tag = r & 0xff;
         zden = (r >> 8) != 0;
       }
@@ -242,12 +278,13 @@ __global__ void __launch_bounds__(kBlock, 3) k_tag_cells_p1(phifem_mesh m, const
         local[2] += tag == 3;
         local[3] += tag == 0;
         local[4] += zden;
+        local[5] += ambiguous;
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < 5; ++i) cnt.add(local[i], i);
-  cnt.flush(counters, PHIFEM_CNT_INTERIOR, 5);
+  for (int i = 0; i < 6; ++i) cnt.add(local[i], i);
+  cnt.flush(counters, PHIFEM_CNT_INTERIOR, 6);
 }
 
 // ---- K1b: generic table-driven cell classification (P1..P3 / Q1..Q3, any detection degree) ----
@@ -617,7 +654,9 @@ extern "C" int phifem_tag_cells(const phifem_mesh* mesh, const phifem_levelset* 
   if (int rc = check_mesh(mesh, false)) return rc;
   if (int rc = check_levelset(mesh, ls, false)) return rc;
   PHIFEM_CHECK_ARG(cell_tags && cell_tags8 && counters, "output pointer is null");
-  PHIFEM_CHECK_ARG(!single_layer_cut || vertex_scratch, "single_layer_cut needs vertex_scratch");
+  PHIFEM_CHECK_ARG(vertex_scratch, "vertex_scratch is null (uint8[n_vertices + 3])");
+  const bool exact_zero_den = (single_layer_cut & 2) != 0;
+  single_layer_cut &= 1;
   if (mesh->n_cells == 0) return PHIFEM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int ct = mesh->cell_type;
@@ -630,14 +669,19 @@ extern "C" int phifem_tag_cells(const phifem_mesh* mesh, const phifem_levelset* 
   if (p1) {
     const bool have_bounds = mesh->detj_min >= 1e-150 && mesh->detj_max <= 1e150 &&
                              mesh->detj_min <= mesh->detj_max;
+    // without bounds on |det J| the magnitude bits stay clear and the denominators are evaluated exactly
+    k_vertex_class<<<grid_for((mesh->n_vertices + 3) / 4, kBlock, 8), kBlock, 0, st>>>(
+        ls->coeffs, mesh->n_vertices, have_bounds ? mesh->detj_min : 0.0,
+        have_bounds ? mesh->detj_max : 1e300, vertex_scratch);
+    const bool exact = exact_zero_den || !have_bounds;
     const int64_t tiles = (mesh->n_cells + kBlock * kUnroll - 1) / (kBlock * kUnroll);
     if (ct == PHIFEM_TRIANGLE)
       k_tag_cells_p1<PHIFEM_TRIANGLE><<<persistent_grid(k_tag_cells_p1<PHIFEM_TRIANGLE>, kBlock, tiles),
-                                        kBlock, 0, st>>>(*mesh, ls->coeffs, have_bounds, cell_tags,
+                                        kBlock, 0, st>>>(*mesh, ls->coeffs, vertex_scratch, exact, cell_tags,
                                                          cell_tags8, counters);
     else
       k_tag_cells_p1<PHIFEM_TETRAHEDRON><<<persistent_grid(k_tag_cells_p1<PHIFEM_TETRAHEDRON>, kBlock, tiles),
-                                           kBlock, 0, st>>>(*mesh, ls->coeffs, have_bounds, cell_tags,
+                                           kBlock, 0, st>>>(*mesh, ls->coeffs, vertex_scratch, exact, cell_tags,
                                                             cell_tags8, counters);
   } else {
     PHIFEM_CHECK_ARG(ls->mode != 0 || ls->cell_table != nullptr, "levelset.cell_table is null");

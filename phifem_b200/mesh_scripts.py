@@ -114,13 +114,16 @@ class TagWorkspace:
         self.vertex_scratch = None
 
 
-def classify_cells(mesh, dls, ws, single_layer_cut=False):
-    """K1 on the current stream: zero the counters, tag the cells (no host synchronisation)."""
+def classify_cells(mesh, dls, ws, single_layer_cut=False, exact_zero_den=False):
+    """K1 on the current stream: zero the counters, tag the cells (no host synchronisation).
+    exact_zero_den: evaluate the isclose(den, 0) test of reference :129 on every cell instead of
+    counting the inconclusive ones in counters[CNT_ZERO_DEN_AMBIGUOUS] (the tags do not depend on it)."""
     ws.counters.zero_()
-    if single_layer_cut and ws.vertex_scratch is None:
-        ws.vertex_scratch = torch.empty(mesh.num_vertices, dtype=torch.uint8, device=mesh.device)
+    if ws.vertex_scratch is None:   # vertex class bytes of the P1 classifier, flags of single_layer_cut
+        ws.vertex_scratch = torch.empty(mesh.num_vertices + 3, dtype=torch.uint8, device=mesh.device)
     _lib.check(_lib.load().phifem_tag_cells(
-        _lib.c_mesh(mesh), dls.c, int(bool(single_layer_cut)), _lib.ptr(ws.cell_tags),
+        _lib.c_mesh(mesh), dls.c, int(bool(single_layer_cut)) | (2 if exact_zero_den else 0),
+        _lib.ptr(ws.cell_tags),
         _lib.ptr(ws.cell_tags8), _lib.ptr(ws.vertex_scratch), _lib.ptr(ws.counters), _lib.stream()))
 
 
@@ -131,10 +134,10 @@ def classify_facets(mesh, dls, ws):
         _lib.ptr(ws.facet_tags8), _lib.ptr(ws.counters), _lib.stream()))
 
 
-def classify(mesh, dls, single_layer_cut=False, ws=None):
+def classify(mesh, dls, single_layer_cut=False, ws=None, exact_zero_den=False):
     """Run the tag kernels (cells, then facets) on the current stream; returns the workspace."""
     ws = ws or TagWorkspace(mesh)
-    classify_cells(mesh, dls, ws, single_layer_cut)
+    classify_cells(mesh, dls, ws, single_layer_cut, exact_zero_den)
     classify_facets(mesh, dls, ws)
     return ws
 
@@ -215,6 +218,10 @@ def compute_tags_measures(mesh, discrete_levelset, detection_degree, box_mode=Fa
     dls = _DeviceLevelset(mesh, discrete_levelset, detection_degree)
     ws = classify(mesh, dls, single_layer_cut)
     counters = ws.counters.cpu().numpy()          # one small D2H: warnings, debug checks
+    if counters[_lib.CNT_ZERO_DEN] == 0 and counters[_lib.CNT_ZERO_DEN_AMBIGUOUS] > 0:
+        # no cell settled the RuntimeWarning of :129-133 and some were left undecided: evaluate them
+        ws = classify(mesh, dls, single_layer_cut, ws=ws, exact_zero_den=True)
+        counters = ws.counters.cpu().numpy()
     if counters[_lib.CNT_ZERO_DEN] > 0:           # :129-133 for the dx detection
         warnings.warn(_ZERO_WARNING, RuntimeWarning)
     if counters[_lib.CNT_FACET_ZERO_DEN] > 0 or counters[_lib.CNT_BOUNDARY_OWNERS] < mesh.num_cells:
