@@ -194,7 +194,7 @@ def run_ours(args):
     t_setup = time.perf_counter()
     if world > 1:
         from phifem_b200 import dist as pdist
-        problem = pdist.SlabProblem(n, rank, world, dev)
+        problem = pdist.SlabProblem(n, rank, world, dev, mode=args.dist_mode)
         mesh, phi, f = problem.mesh, problem.phi, problem.f
     else:
         problem = None
@@ -222,7 +222,8 @@ def run_ours(args):
     from phifem_b200.mesh import MeshTags
     if problem is not None:
         plan = problem.build_plan(ws.cell_tags8, ws.facet_tags8)
-        plan.method, plan.blocked = "atomic", None
+        if args.dist_mode == "exchange":
+            plan.method, plan.blocked, plan.rowsplan = "atomic", None, None
         data, b = problem.data, problem.b_local
     else:
         ctags, ftags = MeshTags(mesh, tdim, ws.cell_tags), MeshTags(mesh, tdim - 1, ws.facet_tags)
@@ -381,11 +382,14 @@ def run_ours(args):
                            "cells_total": n_cells_total, "counts": counts,
                            "l2_policy": "inputs larger than L2 (%.1f GB streamed per step)"
                                         % (ab["total"] / 1e9),
-                           "partition": "1 slab of the global box per rank, owned CSR rows, NCCL halo "
-                                        "exchange" if world > 1 else "single GPU",
+                           "partition": ("single GPU" if world == 1 else
+                                         "1 slab of the global box per rank, owned CSR rows, "
+                                         + ("owner computes its rows from 2 redundantly classified ghost "
+                                            "layers: one 8-byte all-reduce per step, no halo exchange"
+                                            if args.dist_mode == "rows" else "NCCL halo exchange")),
                            "timed": "tag kernels + zeroing + assembly kernels; symbolic phase excluded"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-                "gpu_launches": {"rows": 6, "blocked": 4, "atomic": 6}[plan.method] * args.steps,
+                "gpu_launches": {"rows": 7, "blocked": 5, "atomic": 7}[plan.method] * args.steps,
                 "symbolic_ms": symbolic_ms, "topology_s": topo_s,
                 "scatter": {"method": plan.method,
                             **({"blocks": plan.blocked.n_blocks, "capacity": plan.blocked.capacity,
@@ -419,6 +423,8 @@ def main():
     ap.add_argument("--capacity", type=int, default=None, help="contributions per block (blocked scatter)")
     ap.add_argument("--order", default="natural", choices=["natural", "morton"],
                     help="row processing order of the row-gather assembly")
+    ap.add_argument("--dist-mode", default="rows", choices=["rows", "exchange"],
+                    help="multi-GPU numeric strategy: owner-computes rows / per-entity kernels + halo exchange")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     args = ap.parse_args()

@@ -496,7 +496,7 @@ extern "C" int phifem_assemble_rows_p1(const phifem_mesh* mesh, const double* ph
   }
   PHIFEM_CHECK_ARG(mesh->gdim == (mesh->cell_type == PHIFEM_TRIANGLE ? 2 : 3), "gdim mismatch");
   PHIFEM_CHECK_ARG(phi && f && plan && data && b, "null pointer");
-  if (plan->cells.n_listed == 0) return PHIFEM_OK;
+  if (plan->cells.n_listed == 0 && plan->ghost.n_listed == 0 && plan->boundary.n_listed == 0) return PHIFEM_OK;
   PHIFEM_CHECK_ARG(plan->indptr && plan->indices, "CSR pattern is null");
   PHIFEM_CHECK_ARG(list_ok(plan->cells) && list_ok(plan->ghost) && list_ok(plan->boundary),
                    "row list arrays are null");

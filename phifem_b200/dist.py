@@ -10,11 +10,17 @@ path shards the way SURVEY.md section 8(e) lays out:
     without communication;
   * one 8-byte all-reduce makes "is there any exterior cell" global (the facet algebra changes when
     there is none, mesh_scripts.py:469-474);
-  * every rank assembles its owned cells, the ghost-penalty facets whose first cell it owns and the
-    one-sided entities of its owned cells.  Rows are owned by the lowest rank touching them.  The
-    scatter kernels write contributions to rows owned by another rank straight into that rank's
-    send segment (the slot maps point there), so the exchange is pack-free: grouped send/recv of
-    the segments (NCCL over NVLink), then one indexed add on the owner.
+  * rows are owned by the lowest rank touching them.  Two numeric strategies:
+    mode="rows" (default of bench.py): OWNER COMPUTES -- every rank runs the row-gather kernels on the
+      rows it owns; the entities touching those rows reach at most two cell layers into the next slab
+      (a cell holding an owned boundary vertex, and its facet neighbour for the ghost penalty), so the
+      rank keeps two redundantly classified ghost layers on that side and NOTHING is exchanged in the
+      numeric phase: no halo buffers, no atomics, bitwise identical to the single-GPU rows;
+    mode="exchange": every rank assembles its owned cells, the ghost-penalty facets whose first cell it
+      owns and the one-sided entities of its owned cells with the per-entity kernels; contributions to
+      rows owned by another rank are written straight into that rank's send segment (the slot maps point
+      there), so the exchange is pack-free: grouped send/recv of the segments (NCCL over NVLink), then
+      one indexed add on the owner.
 
 The symbolic phase (pattern union across ranks, slot maps, send/recv lists) uses point-to-point
 transfers and works on the `gloo` backend too, which is how the CPU tests cover it.
@@ -59,11 +65,13 @@ class SlabProblem:
     unit cube joined by a thin tube along x, so the partition boundaries cut through active cells and
     the halo exchange carries real entries."""
 
-    def __init__(self, n, rank, world, device, group=None):
-        self.n, self.rank, self.world, self.group = n, rank, world, group
+    def __init__(self, n, rank, world, device, group=None, mode="exchange"):
+        if mode not in ("exchange", "rows"):
+            raise ValueError("mode must be 'exchange' or 'rows'")
+        self.n, self.rank, self.world, self.group, self.mode = n, rank, world, group, mode
         self.device = torch.device(device)
         gl = 1 if rank > 0 else 0
-        gr = 1 if rank < world - 1 else 0
+        gr = (min(2, n) if mode == "rows" else 1) if rank < world - 1 else 0
         nx = n + gl + gr
         i0 = rank * n - gl
         self.mesh = self._slab_mesh(nx, n, i0)
@@ -130,6 +138,8 @@ class SlabProblem:
 
     # ---- symbolic phase ----------------------------------------------------------------------------
     def build_plan(self, cell_tags8, facet_tags8):
+        if self.mode == "rows":
+            return self._build_rows_plan(cell_tags8, facet_tags8)
         mesh, dev, rank, world = self.mesh, self.device, self.rank, self.world
         NG = self.n_global_vertices
         gv = self.global_vertex
@@ -208,6 +218,39 @@ class SlabProblem:
                         for s in self.plan.b_recv_rows]
         return self.plan
 
+    def _build_rows_plan(self, cell_tags8, facet_tags8):
+        """Owner-computes plan: the single-GPU symbolic phase on the local mesh (slab + ghost layers),
+        restricted to the rows this rank owns.  The owned rows are a contiguous range of local rows."""
+        mesh = self.mesh
+        if mesh.device.type == "cuda":
+            ents = mesh_scripts._integration_entities_dev(mesh, cell_tags8, facet_tags8, 4, (1, 2))
+        else:
+            ents = self._entities_host(cell_tags8, facet_tags8)
+        owned = self.vertex_owner == self.rank
+        plan = assemble.AssemblyPlan(mesh, cell_tags8.contiguous(), facet_tags8.contiguous(),
+                                     ents.reshape(-1, 2), method="rows", row_mask=owned)
+        if plan.method != "rows":
+            raise NotImplementedError("owner-computes sharding needs the row-gather plan")
+        ov = torch.nonzero(owned).reshape(-1)
+        lo, hi = int(ov[0]), int(ov[-1]) + 1
+        assert hi - lo == ov.numel() == self.row_hi - self.row_lo, "owned rows are not contiguous"
+        plan.owned_lo, plan.owned_hi = lo, hi
+        plan.owned_vertices = ov
+        ip = plan.indptr.long()
+        plan.owned_slots = (int(ip[lo]), int(ip[hi]))      # CSR range of the owned rows (host ints: the
+        plan.owned_indptr = (ip[lo:hi + 1] - ip[lo])       # numeric phase must not synchronise)
+        plan.owned_cols = self.global_vertex[plan.indices[plan.owned_slots[0]:plan.owned_slots[1]].long()]
+        plan.send_ranges = []
+        self.plan = plan
+        self.data, self.b_local = plan.new_outputs()
+        return plan
+
+    def owned_csr(self):
+        """(indptr, global column ids, data view, b view) of the owned rows (mode="rows")."""
+        p = self.plan
+        a, b = p.owned_slots
+        return p.owned_indptr, p.owned_cols, self.data[a:b], self.b_local[p.owned_lo:p.owned_hi]
+
     def _entities_host(self, cell_tags8, facet_tags8):
         """CPU stand-in of the entity search for the gloo tests (same ordering rules, torch ops)."""
         mesh = self.mesh
@@ -228,6 +271,13 @@ class SlabProblem:
         replaces the CUDA kernels in the CPU (gloo) tests only."""
         p = self.plan
         run = local_kernels or assemble.assemble_into
+        if self.mode == "rows":
+            if local_kernels is None:
+                run(p, self.phi, self.f, sigma, self.data, self.b_local, marks=marks)
+            else:
+                run(p, self.phi, self.f, sigma, self.data, self.b_local)
+            _, _, data, b = self.owned_csr()
+            return data, b
         if local_kernels is None:
             run(p, self.phi, self.f, sigma, self.data, self.b_local, marks=marks)
         else:

@@ -100,7 +100,10 @@ def _pack_bytes(pos):
 
 
 class RowsPlan:
-    def __init__(self, plan, order="natural"):
+    """row_mask (bool [n_rows], optional): assemble only these rows -- the rows a rank owns in a multi-GPU
+    run; records of other rows are dropped (their owner evaluates them from its own halo cells)."""
+
+    def __init__(self, plan, order="natural", row_mask=None):
         mesh = plan.mesh
         dev = mesh.device
         d = mesh.gdim
@@ -110,8 +113,19 @@ class RowsPlan:
         self.plan = plan
         indptr = plan.indptr.long()
         row_nnz = indptr[1:] - indptr[:-1]
-        listed = torch.nonzero(row_nnz > 0).reshape(-1)
-        self.max_row_nnz = int(row_nnz.max()) if listed.numel() else 0
+        has = row_nnz > 0
+        if row_mask is not None:
+            has = has & row_mask.to(dev)
+        listed = torch.nonzero(has).reshape(-1)
+        self.max_row_nnz = int(row_nnz[listed].max()) if listed.numel() else 0
+
+        def owned(rec_rows, words):
+            """Drop the records of rows outside the mask."""
+            if row_mask is None or rec_rows.numel() == 0:
+                return rec_rows, words
+            keep = row_mask.to(dev)[rec_rows]
+            return rec_rows[keep], words[keep]
+
         if self.max_row_nnz > MAX_ROW_NNZ or self.max_row_nnz * BLOCK * 8 > MAX_SMEM_BYTES:
             raise NotImplementedError(
                 "row-gather assembly: a row holds %d entries (limit %d); use the atomic scatter kernels "
@@ -145,8 +159,8 @@ class RowsPlan:
             pos = slots[:, i, others] - indptr[cells_act[:, i]][:, None]
             words.append(_pack_bytes(pos) | (cut << 24))
         # interleaved so that the records of a row keep cell order (deterministic summation order)
-        self.cells = RowList(ordered(listed), dslot, indptr, cells_act.reshape(-1),
-                             torch.stack(words, dim=1).reshape(-1, 1), n)
+        rec_rows, words = owned(cells_act.reshape(-1), torch.stack(words, dim=1).reshape(-1, 1))
+        self.cells = RowList(ordered(listed), dslot, indptr, rec_rows, words, n)
         del slots, cells_act, words
 
         # ---- ghost-penalty facets: one record per distinct vertex of the macro element ------------------
@@ -171,6 +185,7 @@ class RowsPlan:
             rec_rows, words = mac.reshape(-1), torch.stack(words, dim=1).reshape(-1, 2)
         else:
             rec_rows, words = torch.zeros(0, **i64), torch.zeros((0, 2), **i64)
+        rec_rows, words = owned(rec_rows, words)
         self.ghost = RowList(ordered(rec_rows), dslot, indptr, rec_rows, words, n, balance=True)
 
         # ---- one-sided facets: one record per facet vertex of each (cell, local facet) entity --------------
@@ -196,10 +211,19 @@ class RowsPlan:
             words = torch.stack(words, dim=1).reshape(-1, 1)
         else:
             rec_rows, words = torch.zeros(0, **i64), torch.zeros((0, 1), **i64)
+        rec_rows, words = owned(rec_rows, words)
         self.boundary = RowList(ordered(rec_rows), dslot, indptr, rec_rows, words, n, balance=True)
         self._c = None
 
-    def c_struct(self):
+    def c_struct(self, passes=None):
+        """`passes`: subset of ("cells", "ghost", "boundary") to run (bench.py times them one by one);
+        the other lists are passed empty."""
+        if passes is not None:
+            p = _lib.ptr
+            empty = _lib.CRowList(0, None, None, None, None)
+            lists = [getattr(self, nm).c_struct() if nm in passes else empty
+                     for nm in ("cells", "ghost", "boundary")]
+            return _lib.CRowsPlan(p(self.plan.indptr), p(self.plan.indices), self.max_row_nnz, 0, *lists)
         if self._c is None:
             p = _lib.ptr
             pl = self.plan
@@ -212,12 +236,12 @@ class RowsPlan:
         return self.cells.nbytes() + self.ghost.nbytes() + self.boundary.nbytes()
 
 
-def assemble_rows_into(rplan, phi, f, sigma, data, b):
-    """Numeric phase, one launch on the current stream.  `data` needs no zero-fill; `b` must have been
-    zeroed once (rows without pattern entries are never written)."""
+def assemble_rows_into(rplan, phi, f, sigma, data, b, passes=None):
+    """Numeric phase on the current stream (cell pass, ghost-penalty pass, one-sided pass).  `data` needs
+    no zero-fill; `b` must have been zeroed once (rows without pattern entries are never written)."""
     mesh = rplan.plan.mesh
     _lib.require_cuda(mesh)
     _lib.check(_lib.load().phifem_assemble_rows_p1(
-        _lib.c_mesh(mesh), _lib.ptr(phi), _lib.ptr(f), float(sigma), ctypes.byref(rplan.c_struct()),
-        _lib.ptr(data), _lib.ptr(b), _lib.stream()))
+        _lib.c_mesh(mesh), _lib.ptr(phi), _lib.ptr(f), float(sigma),
+        ctypes.byref(rplan.c_struct(passes)), _lib.ptr(data), _lib.ptr(b), _lib.stream()))
     return data, b

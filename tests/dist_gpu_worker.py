@@ -17,18 +17,23 @@ from phifem_b200.mesh import MeshTags  # noqa: E402
 
 def main():
     n = int(sys.argv[1])
+    mode = sys.argv[2] if len(sys.argv) > 2 else "exchange"
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=dev)
-    prob = pdist.SlabProblem(n, rank, world, dev)
+    prob = pdist.SlabProblem(n, rank, world, dev, mode=mode)
     dls = mesh_scripts._DeviceLevelset(prob.mesh, fem.Function(fem.functionspace_p1_device(prob.mesh), prob.phi), 1)
     ws = prob.classify(dls, mesh_scripts.TagWorkspace(prob.mesh))
     plan = prob.build_plan(ws.cell_tags8, ws.facet_tags8)
     data, b = prob.assemble(1.0)
     torch.cuda.synchronize()
-    mine = dict(row_lo=prob.row_lo, row_hi=prob.row_hi, indptr=plan.indptr.cpu().numpy(),
-                indices=plan.indices.cpu().numpy(), data=data.cpu().numpy(), b=b.cpu().numpy(),
+    if mode == "rows":
+        indptr, indices, _, _ = prob.owned_csr()
+    else:
+        indptr, indices = plan.indptr, plan.indices
+    mine = dict(row_lo=prob.row_lo, row_hi=prob.row_hi, indptr=indptr.cpu().numpy(),
+                indices=indices.cpu().numpy(), data=data.cpu().numpy(), b=b.cpu().numpy(),
                 tags=ws.cell_tags[prob.cell_owned].cpu().numpy(),
                 sent=sum(hi - lo for lo, hi in plan.send_ranges))
     parts = [None] * world
@@ -53,8 +58,10 @@ def main():
             assert np.array_equal(p["indices"], ix[lo:hi])
             assert np.abs(p["data"] - dd[lo:hi]).max() <= 1e-12 * np.abs(dd).max()
             assert np.abs(p["b"] - bb[p["row_lo"]:row]).max() <= 1e-12 * np.abs(bb).max()
-        assert row == mesh.num_vertices and sum(p["sent"] for p in parts) > 0
-        print("DIST-OK world=%d cells=%d halo_entries=%d" % (world, mesh.num_cells, sum(p["sent"] for p in parts)))
+        assert row == mesh.num_vertices
+        assert (sum(p["sent"] for p in parts) > 0) == (mode == "exchange")
+        print("DIST-OK world=%d mode=%s cells=%d halo_entries=%d"
+              % (world, mode, mesh.num_cells, sum(p["sent"] for p in parts)))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -29,9 +29,10 @@ def oracle_kernels(plan, phi, f, sigma, data, b):
 
 def main():
     n, out_dir = int(sys.argv[1]), sys.argv[2]
+    mode = sys.argv[3] if len(sys.argv) > 3 else "exchange"
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
-    prob = pdist.SlabProblem(n, rank, world, "cpu")
+    prob = pdist.SlabProblem(n, rank, world, "cpu", mode=mode)
     m = prob.mesh
     x, cells = m.x.numpy(), np.ascontiguousarray(m.cells.numpy())
     ct = ON.tag_cells_p1(x, cells, prob.phi.numpy())
@@ -39,10 +40,22 @@ def main():
                           prob.phi.numpy(), ct)
     plan = prob.build_plan(torch.from_numpy(ct.astype(np.int8)), torch.from_numpy(ft.astype(np.int8)))
     data, b = prob.assemble(1.0, local_kernels=oracle_kernels)
+    if mode == "rows":     # owner computes: nothing was exchanged; the owned rows are a slice of the local CSR
+        indptr, indices, _, _ = prob.owned_csr()
+        n_send = n_halo_b = 0
+        # every record of the row-gather plan belongs to an owned row
+        rp = plan.rowsplan
+        owned = (prob.vertex_owner == rank).numpy()
+        for rl in (rp.cells, rp.ghost, rp.boundary):
+            assert owned[rl.rows.numpy()].all()
+    else:
+        indptr, indices = plan.indptr, plan.indices
+        n_send = sum(hi - lo for lo, hi in plan.send_ranges)
+        n_halo_b = sum(int(v.numel()) for v in plan.b_send_local)
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), row_lo=prob.row_lo, row_hi=prob.row_hi,
-             indptr=plan.indptr.numpy(), indices=plan.indices.numpy(), data=data.numpy(), b=b.numpy(),
-             cell_tags=ct[prob.cell_owned.numpy()], n_send=sum(hi - lo for lo, hi in plan.send_ranges),
-             n_halo_b=sum(int(v.numel()) for v in plan.b_send_local))
+             indptr=indptr.numpy(), indices=indices.numpy(), data=data.numpy(), b=b.numpy(),
+             cell_tags=ct[prob.cell_owned.numpy()], n_send=n_send, n_halo_b=n_halo_b,
+             n_local_cells=m.num_cells)
     dist.barrier()
     dist.destroy_process_group()
 

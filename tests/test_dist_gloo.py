@@ -21,7 +21,11 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def test_two_ranks_reproduce_the_single_domain_operator(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("mode", ["exchange", "rows"])
+def test_two_ranks_reproduce_the_single_domain_operator(tmp_path, mode):
     n, world = 4, 2
     port = _free_port()
     procs = []
@@ -29,7 +33,7 @@ def test_two_ranks_reproduce_the_single_domain_operator(tmp_path):
         env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
                    MASTER_PORT=str(port), OMP_NUM_THREADS="2")
         procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "dist_worker.py"), str(n),
-                                       str(tmp_path)], env=env))
+                                       str(tmp_path), mode], env=env))
     for p in procs:
         assert p.wait(timeout=300) == 0
     mesh, phi, f = pdist.SlabProblem.global_reference(n, world)
@@ -57,4 +61,7 @@ def test_two_ranks_reproduce_the_single_domain_operator(tmp_path):
         halo += int(r["n_send"]) + int(r["n_halo_b"])
     assert row == len(x)
     assert np.array_equal(np.concatenate(tags), out["cell_tags"])
-    assert halo > 0          # the partition boundary cuts through active cells: a real exchange happened
+    if mode == "exchange":   # the partition boundary cuts through active cells: a real exchange happened
+        assert halo > 0
+    else:                    # owner computes: nothing exchanged, rank 0 carries two ghost layers instead
+        assert halo == 0

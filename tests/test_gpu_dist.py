@@ -12,10 +12,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_two_gpus_match_single_gpu():
+@pytest.mark.parametrize("mode", ["rows", "exchange"])
+def test_two_gpus_match_single_gpu(mode):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29611",
-                          os.path.join(HERE, "dist_gpu_worker.py"), "12"], capture_output=True, text=True,
+                          os.path.join(HERE, "dist_gpu_worker.py"), "12", mode], capture_output=True, text=True,
                          timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
-    assert "DIST-OK world=2" in out.stdout
+    assert "DIST-OK world=2 mode=%s" % mode in out.stdout
