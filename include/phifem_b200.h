@@ -235,6 +235,51 @@ typedef struct phifem_rows_plan {
 int phifem_assemble_rows_p1(const phifem_mesh* mesh, const double* phi, const double* f, double sigma,
                             const phifem_rows_plan* plan, double* data, double* b, void* stream);
 
+/* ---- strong-Dirichlet phi-FEM operator by quadrature: Lagrange P1 / P2 trial-test space (`fe_degree`,
+ * demo/strong-dirichlet/flower/main.py:37) and P1 / P2 level set (`levelset_degree`, :39) on triangles and
+ * tetrahedra.  Same forms and ADD semantics as the *_p1 entry points; `data` and `b` zeroed by the caller. */
+typedef struct phifem_pk_space {
+  int32_t degree;              /* 1 or 2 */
+  int32_t n_dofs_per_cell;     /* nd: nv (P1) or nv + number of edges (P2) */
+  int64_t n_dofs;
+  const int32_t* dofmap;       /* [n_cells, nd], cell-local order = vertices, then edges in dolfinx local edge
+                                  order (triangle (1,2),(0,2),(0,1); tetrahedron (2,3),(1,3),(1,2),(0,3),(0,2),
+                                  (0,1)); NULL => mesh.cells (P1 with vertex dofs) */
+} phifem_pk_space;
+
+/* Quadrature tables (barycentric points, weights summing to 1); what dolfinx takes from basix for the
+ * estimated degree of each integrand: cells 2 (kw + kphi - 1), facets 2 (kw + kphi) - 1.  At most 128 points. */
+typedef struct phifem_quadrature {
+  int32_t n_cell_points;
+  int32_t n_facet_points;
+  const double* cell_points;   /* [n_cell_points, nv] */
+  const double* cell_weights;  /* [n_cell_points] */
+  const double* facet_points;  /* [n_facet_points, nv - 1], facet vertices in ascending local order */
+  const double* facet_weights; /* [n_facet_points] */
+} phifem_quadrature;
+
+/* dx((1,2)) + dx(2) terms and the load vector (:105,107-112,126-128).  slots[nd*nd, n_active]: CSR position of
+ * entry (test dof i, trial dof j) of active cell e at slots[(i*nd + j) * n_active + e] (entry-major, so that
+ * consecutive threads read consecutive words).  `f` lives in the trial/test space. */
+int phifem_assemble_cells_pk(const phifem_mesh* mesh, const phifem_pk_space* space_w,
+                             const phifem_pk_space* space_phi, const phifem_quadrature* quad,
+                             const double* phi, const double* f, const int8_t* cell_tags8,
+                             const int32_t* active, int64_t n_active, const int32_t* slots, double sigma,
+                             double* data, double* b, void* stream);
+
+/* -int_{ds(100)} (grad(phi w).n) phi v (:106); slots[nd*nd, n_entities] entry-major. */
+int phifem_assemble_boundary_pk(const phifem_mesh* mesh, const phifem_pk_space* space_w,
+                                const phifem_pk_space* space_phi, const phifem_quadrature* quad,
+                                const double* phi, const int32_t* entities, int64_t n_entities,
+                                const int32_t* slots, double* data, void* stream);
+
+/* Ghost penalty over dS((2,3)) (:113-118); macro dofs = [dofs of cell + (f2c[f][0]), dofs of cell -];
+ * slots[(2nd)^2, n_facets] entry-major. */
+int phifem_assemble_ghost_pk(const phifem_mesh* mesh, const phifem_pk_space* space_w,
+                             const phifem_pk_space* space_phi, const phifem_quadrature* quad,
+                             const double* phi, const int32_t* facets, int64_t n_facets,
+                             const int32_t* slots, double sigma, double* data, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,19 @@ class CRowsPlan(ctypes.Structure):
                 ("boundary", CRowList)]
 
 
+class CPkSpace(ctypes.Structure):
+    _fields_ = [("degree", ctypes.c_int32), ("n_dofs_per_cell", ctypes.c_int32), ("n_dofs", ctypes.c_int64),
+                ("dofmap", _vp)]
+
+
+class CQuadrature(ctypes.Structure):
+    _fields_ = [("n_cell_points", ctypes.c_int32), ("n_facet_points", ctypes.c_int32),
+                ("cell_points", _vp), ("cell_weights", _vp), ("facet_points", _vp), ("facet_weights", _vp)]
+
+
+_PK_HEAD = [ctypes.POINTER(CMesh), ctypes.POINTER(CPkSpace), ctypes.POINTER(CPkSpace),
+            ctypes.POINTER(CQuadrature)]
+
 _SIGNATURES = {
     "phifem_last_error": (ctypes.c_char_p, []),
     "phifem_abi_version": (ctypes.c_int, []),
@@ -74,6 +87,11 @@ _SIGNATURES = {
                                                   ctypes.POINTER(CBlockedPlan), _vp, _vp, _vp]),
     "phifem_assemble_rows_p1": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, ctypes.c_double,
                                                ctypes.POINTER(CRowsPlan), _vp, _vp, _vp]),
+    "phifem_assemble_cells_pk": (ctypes.c_int, _PK_HEAD + [_vp, _vp, _vp, _vp, ctypes.c_int64, _vp,
+                                                           ctypes.c_double, _vp, _vp, _vp]),
+    "phifem_assemble_boundary_pk": (ctypes.c_int, _PK_HEAD + [_vp, _vp, ctypes.c_int64, _vp, _vp, _vp]),
+    "phifem_assemble_ghost_pk": (ctypes.c_int, _PK_HEAD + [_vp, _vp, ctypes.c_int64, _vp, ctypes.c_double,
+                                                           _vp, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -126,9 +126,12 @@ class AssemblyPlan:
                 torch.zeros(self.n_rows, dtype=torch.float64, device=dev))
 
 
-def build_plan(mesh, cells_tags, facets_tags, ds=None, method="rows", capacity=None, order="natural"):
+def build_plan(mesh, cells_tags, facets_tags, ds=None, method="rows", capacity=None, order="natural",
+               V=None, V_phi=None):
     """Symbolic phase for `a` and `L` of the strong-Dirichlet demo.  `ds` is what the demo passes as
-    `ds_bdy(100)` (main.py:64): a MeasureRestriction, a flat entity array, or None (no boundary term)."""
+    `ds_bdy(100)` (main.py:64): a MeasureRestriction, a flat entity array, or None (no boundary term).
+    `V` / `V_phi`: the demo's `primal_space` / `levelset_space` (main.py:74-75); omitted or both of degree 1
+    => the closed-form P1 kernels, otherwise the quadrature kernels for P1 / P2 (phifem_b200/assemble_pk.py)."""
     c8 = getattr(cells_tags, "tags8", None)
     c8 = c8 if c8 is not None else cells_tags.values_dev.to(torch.int8)
     f8 = getattr(facets_tags, "tags8", None)
@@ -141,19 +144,29 @@ def build_plan(mesh, cells_tags, facets_tags, ds=None, method="rows", capacity=N
         ents = ds.to(mesh.device)
     else:
         ents = torch.as_tensor(np.asarray(ds, dtype=np.int32), device=mesh.device)
+    V_phi = V if V_phi is None else V_phi
+    V = V_phi if V is None else V
+    if V is not None and (V.degree != 1 or V_phi.degree != 1 or method == "pk"):
+        from .assemble_pk import PkAssemblyPlan
+        return PkAssemblyPlan(mesh, c8.contiguous(), f8.contiguous(), ents, V, V_phi)
     return AssemblyPlan(mesh, c8.contiguous(), f8.contiguous(), ents, method=method, capacity=capacity,
                         order=order)
 
 
-def _device_vector(mesh, v):
+def _device_vector(mesh, v, space=None):
+    """Coefficient vector on the device; `space` (P_k plans) names the space it must live in."""
     if isinstance(v, Function):
-        if v.function_space.degree != 1:
-            raise NotImplementedError("the CUDA assembly path implements P1 (vertex dofs)")
+        if space is None and v.function_space.degree != 1:
+            raise NotImplementedError("this plan was built for P1 (vertex dofs); pass V / V_phi to build_plan")
+        if space is not None and v.function_space.degree != space.degree:
+            raise ValueError("coefficient of degree %d given where the plan expects degree %d"
+                             % (v.function_space.degree, space.degree))
         v = v.x.array
     t = v if torch.is_tensor(v) else torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64))
     t = t.to(mesh.device, dtype=torch.float64, non_blocking=True).contiguous()
-    if t.numel() != mesh.num_vertices:
-        raise ValueError("expected one value per vertex")
+    n = mesh.num_vertices if space is None else space.num_dofs
+    if t.numel() != n:
+        raise ValueError("expected %d dof values, got %d" % (n, t.numel()))
     return t
 
 
@@ -206,6 +219,13 @@ def assemble_into(plan, phi, f, sigma, data, b, marks=None):
 def assemble_strong_dirichlet(plan, phi_h, f_h, stab_coef=1.0):
     """A (CSR) and b of reference demo/strong-dirichlet/flower/main.py:104-131."""
     mesh = plan.mesh
+    if getattr(plan, "V", None) is not None:
+        from .assemble_pk import assemble_pk_into
+        phi = _device_vector(mesh, phi_h, plan.V_phi)
+        f = _device_vector(mesh, f_h, plan.V)
+        data, b = plan.new_outputs()
+        assemble_pk_into(plan, phi, f, stab_coef, data, b)
+        return CSRMatrix(plan.indptr, plan.indices, data, (plan.n_rows, plan.n_rows)), b
     phi = _device_vector(mesh, phi_h)
     f = _device_vector(mesh, f_h)
     data, b = plan.new_outputs()

@@ -1,0 +1,124 @@
+"""Strong-Dirichlet phi-FEM operator for Lagrange P1 / P2 trial-test spaces and P1 / P2 level sets
+(`fe_degree`, `levelset_degree` of reference demo/strong-dirichlet/flower/main.py:37-41), assembled into CSR
+by the quadrature kernels of csrc/assemble_pk.cu.
+
+    V, Vphi = fem.functionspace(mesh, 2), fem.functionspace(mesh, 2)
+    plan = assemble.build_plan(mesh, cells_tags, facets_tags, ds_bdy(100), V=V, V_phi=Vphi)
+    A, b = assemble.assemble_strong_dirichlet(plan, phi_h, f_h, stab_coef=1.0)
+
+Symbolic phase (torch sort/unique on the mesh's device): CSR pattern = all dof pairs of every cell tagged
+1/2 plus all pairs among the dofs of the two cells of every interior facet tagged 2/3 (dolfinx
+create_sparsity_pattern [dep-knowledge, SURVEY.md C.3]); entity -> CSR-slot maps stored entry-major
+([nd*nd, n_entities]) so that consecutive threads read consecutive words.
+"""
+import ctypes
+
+import torch
+
+from . import _lib, quadrature
+
+
+class PkAssemblyPlan:
+    method = "pk-atomic"
+    rowsplan = None
+    blocked = None
+
+    def __init__(self, mesh, cell_tags8, facet_tags8, entities, V, V_phi):
+        if mesh.cell_type not in ("triangle", "tetrahedron"):
+            raise NotImplementedError("P_k assembly supports triangles and tetrahedra")
+        for sp in (V, V_phi):
+            if sp.mesh is not mesh:
+                raise ValueError("the function space is defined on another mesh")
+            if sp.degree not in (1, 2):
+                raise NotImplementedError("the CUDA assembly path implements Lagrange degrees 1 and 2")
+        dev = mesh.device
+        self.mesh, self.V, self.V_phi = mesh, V, V_phi
+        self.cell_tags8 = cell_tags8
+        self.n_rows = n = int(V.num_dofs)
+        self.dofmap = V.dofmap_dev
+        self.dofmap_phi = V_phi.dofmap_dev
+        nd = self.nd = int(self.dofmap.shape[1])
+        self.active = torch.nonzero((cell_tags8 == 1) | (cell_tags8 == 2)).reshape(-1).to(torch.int32)
+        interior = mesh.f2c[:, 1] >= 0
+        self.ghost = torch.nonzero(((facet_tags8 == 2) | (facet_tags8 == 3)) & interior) \
+            .reshape(-1).to(torch.int32)
+        self.entities = entities.reshape(-1, 2).to(torch.int32).contiguous()
+
+        def pair_keys(dm):  # [m, k] dofs -> [m, k*k] keys row*n+col, row-major (row = test)
+            return (dm[:, :, None] * n + dm[:, None, :]).reshape(dm.shape[0], dm.shape[1] * dm.shape[1])
+
+        keys_c = pair_keys(self.dofmap[self.active.long()].long())
+        g = self.ghost.long()
+        mac = torch.cat([self.dofmap[mesh.f2c[g, 0].long()], self.dofmap[mesh.f2c[g, 1].long()]], dim=1).long()
+        keys_g = pair_keys(mac)
+        n_c = keys_c.numel()
+        uniq, inv = torch.unique(torch.cat([keys_c.reshape(-1), keys_g.reshape(-1)]), sorted=True,
+                                 return_inverse=True)
+        del keys_c, keys_g
+        inv = inv.to(torch.int32)
+        self.slots_cells = inv[:n_c].reshape(-1, nd * nd).t().contiguous()
+        self.slots_ghost = inv[n_c:].reshape(-1, 4 * nd * nd).t().contiguous()
+        del inv
+        keys_b = pair_keys(self.dofmap[self.entities[:, 0].long()].long())
+        self.slots_boundary = torch.searchsorted(uniq, keys_b.reshape(-1)).reshape(-1, nd * nd) \
+            .to(torch.int32).t().contiguous()
+        rows = uniq // n
+        self.indices = (uniq - rows * n).to(torch.int32).contiguous()
+        counts = torch.bincount(rows, minlength=n)
+        indptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        indptr[1:] = torch.cumsum(counts, dim=0)
+        self.indptr = indptr.to(torch.int32).contiguous()
+        self.nnz = int(uniq.numel())
+
+        # quadrature tables and C structs (kept alive with the plan)
+        d = mesh.gdim
+        (cl, cw), (fl, fw) = quadrature.rules_for(d, V.degree, V_phi.degree)
+        f64 = dict(dtype=torch.float64, device=dev)
+        self._q = [torch.as_tensor(a, **f64).contiguous() for a in (cl, cw, fl, fw)]
+        self.n_cell_points, self.n_facet_points = len(cw), len(fw)
+        self._cquad = self._cw = self._cp = None
+
+    def c_structs(self):
+        if self._cquad is None:
+            p = _lib.ptr
+            q = self._q
+            self._cquad = _lib.CQuadrature(self.n_cell_points, self.n_facet_points, p(q[0]), p(q[1]), p(q[2]),
+                                           p(q[3]))
+            self._cw = _lib.CPkSpace(self.V.degree, self.nd, self.V.num_dofs, p(self.dofmap))
+            self._cp = _lib.CPkSpace(self.V_phi.degree, int(self.dofmap_phi.shape[1]), self.V_phi.num_dofs,
+                                     p(self.dofmap_phi))
+        return self._cw, self._cp, self._cquad
+
+    def new_outputs(self):
+        dev = self.mesh.device
+        return (torch.zeros(self.nnz, dtype=torch.float64, device=dev),
+                torch.zeros(self.n_rows, dtype=torch.float64, device=dev))
+
+
+def assemble_pk_into(plan, phi, f, sigma, data, b, marks=None):
+    """Numeric phase on the current stream: zero `data` / `b`, then the cell, one-sided and ghost-penalty
+    kernels.  All arguments are device tensors; nothing synchronises."""
+    marks = marks or (lambda: None)
+    mesh = plan.mesh
+    _lib.require_cuda(mesh)
+    lib = _lib.load()
+    cm = _lib.c_mesh(mesh)
+    cw, cp, cq = plan.c_structs()
+    head = (cm, ctypes.byref(cw), ctypes.byref(cp), ctypes.byref(cq))
+    st = _lib.stream()
+    data.zero_()
+    b.zero_()
+    marks()
+    _lib.check(lib.phifem_assemble_cells_pk(
+        *head, _lib.ptr(phi), _lib.ptr(f), _lib.ptr(plan.cell_tags8), _lib.ptr(plan.active),
+        plan.active.numel(), _lib.ptr(plan.slots_cells), float(sigma), _lib.ptr(data), _lib.ptr(b), st))
+    marks()
+    _lib.check(lib.phifem_assemble_boundary_pk(
+        *head, _lib.ptr(phi), _lib.ptr(plan.entities), plan.entities.shape[0],
+        _lib.ptr(plan.slots_boundary), _lib.ptr(data), st))
+    marks()
+    _lib.check(lib.phifem_assemble_ghost_pk(
+        *head, _lib.ptr(phi), _lib.ptr(plan.ghost), plan.ghost.numel(), _lib.ptr(plan.slots_ghost),
+        float(sigma), _lib.ptr(data), st))
+    marks()
+    return data, b

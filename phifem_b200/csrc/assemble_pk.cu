@@ -1,0 +1,596 @@
+// K2/K3/K4 for Lagrange P1 / P2 trial-test spaces and P1 / P2 level sets on triangles / tetrahedra:
+// the strong-Dirichlet phi-FEM operator of reference demo/strong-dirichlet/flower/main.py:104-128 with
+// `fe_degree`, `levelset_degree` in {1, 2} (main.py:37-41), evaluated by quadrature.
+//
+// dolfinx would JIT one FFCx `tabulate_tensor` per integral and call it once per entity
+// (main.py:121-123,130-131); here one thread evaluates a block of rows of one element tensor with every
+// loop over basis functions unrolled at compile time (accumulators in registers), the quadrature rule
+// staged in shared memory, and adds the entries into CSR through a precomputed entity -> slot map.
+// The rules are host-provided tables (phifem_quadrature): the symbolic side picks rules exact for the
+// polynomial degree of each integrand (2 (kw + kphi - 1) on cells, 2 (kw + kphi) - 1 on facets).
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace phifem {
+namespace {
+
+constexpr int kBlockPk = 128;
+constexpr int kMaxQuadPoints = 128;
+
+// dolfinx / basix local edge order [dep-knowledge, SURVEY.md C.7]: edge e joins vertices ev(e, 0) < ev(e, 1)
+template <int D>
+__host__ __device__ constexpr int ev(int e, int s) {
+  if (D == 2) {
+    constexpr int t[3][2] = {{1, 2}, {0, 2}, {0, 1}};
+    return t[e][s];
+  } else {
+    constexpr int t[6][2] = {{2, 3}, {1, 3}, {1, 2}, {0, 3}, {0, 2}, {0, 1}};
+    return t[e][s];
+  }
+}
+
+template <int D, int K>
+struct Space {
+  static constexpr int NV = D + 1;
+  static constexpr int NE = K == 2 ? D * (D + 1) / 2 : 0;
+  static constexpr int ND = NV + NE;
+};
+
+template <int D>
+__device__ __forceinline__ double dotd(const double (&a)[D], const double (&b)[D]) {
+  double s = a[0] * b[0];
+#pragma unroll
+  for (int d = 1; d < D; ++d) s += a[d] * b[d];
+  return s;
+}
+
+// values and gradients of the P_K Lagrange basis at barycentric point lam; G = grad(lambda)
+template <int D, int K>
+__device__ __forceinline__ void tabulate(const double (&lam)[D + 1], const double (&G)[D + 1][D],
+                                         double (&val)[Space<D, K>::ND], double (&grad)[Space<D, K>::ND][D]) {
+  constexpr int NV = D + 1;
+  if constexpr (K == 1) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      val[i] = lam[i];
+#pragma unroll
+      for (int d = 0; d < D; ++d) grad[i][d] = G[i][d];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      val[i] = lam[i] * (2.0 * lam[i] - 1.0);
+      const double c = 4.0 * lam[i] - 1.0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) grad[i][d] = c * G[i][d];
+    }
+#pragma unroll
+    for (int e = 0; e < Space<D, K>::NE; ++e) {
+      const int a = ev<D>(e, 0), b = ev<D>(e, 1);
+      val[NV + e] = 4.0 * lam[a] * lam[b];
+#pragma unroll
+      for (int d = 0; d < D; ++d) grad[NV + e][d] = 4.0 * (lam[a] * G[b][d] + lam[b] * G[a][d]);
+    }
+  }
+}
+
+// Laplacians of the basis (constant on the cell for K <= 2)
+template <int D, int K>
+__device__ __forceinline__ void laplacians(const double (&G)[D + 1][D], double (&lap)[Space<D, K>::ND]) {
+  constexpr int NV = D + 1;
+  if constexpr (K == 1) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) lap[i] = 0.0;
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) lap[i] = 4.0 * dotd<D>(G[i], G[i]);
+#pragma unroll
+    for (int e = 0; e < Space<D, K>::NE; ++e) lap[NV + e] = 8.0 * dotd<D>(G[ev<D>(e, 0)], G[ev<D>(e, 1)]);
+  }
+}
+
+// affine geometry of one simplex: vertex coordinates, grad(lambda), |K|, h_T^2
+template <int D>
+struct Geometry {
+  double X[D + 1][D], G[D + 1][D], vol, h2;
+};
+
+template <int D>
+__device__ __forceinline__ void load_geometry(const phifem_mesh& m, int64_t c, Geometry<D>& g) {
+  constexpr int NV = D + 1;
+  int v[NV];
+  if (D == 3) {
+    const int4 q = __ldg(reinterpret_cast<const int4*>(m.cells) + c);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[D] = q.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = __ldg(m.cells + c * NV + k);
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+#pragma unroll
+    for (int d = 0; d < D; ++d) g.X[k][d] = __ldg(m.x + (int64_t)v[k] * D + d);
+  double e[D][D];
+#pragma unroll
+  for (int k = 0; k < D; ++k)
+#pragma unroll
+    for (int d = 0; d < D; ++d) e[k][d] = g.X[k + 1][d] - g.X[0][d];
+  double det;
+  if constexpr (D == 2) {
+    det = e[0][0] * e[1][1] - e[1][0] * e[0][1];
+    const double inv = 1.0 / det;
+    g.G[1][0] = e[1][1] * inv;  g.G[1][1] = -e[1][0] * inv;
+    g.G[2][0] = -e[0][1] * inv; g.G[2][1] = e[0][0] * inv;
+    g.vol = 0.5 * fabs(det);
+  } else {
+    const double r1[3] = {e[1][1] * e[2][2] - e[1][2] * e[2][1], e[1][2] * e[2][0] - e[1][0] * e[2][2],
+                          e[1][0] * e[2][1] - e[1][1] * e[2][0]};
+    const double r2[3] = {e[2][1] * e[0][2] - e[2][2] * e[0][1], e[2][2] * e[0][0] - e[2][0] * e[0][2],
+                          e[2][0] * e[0][1] - e[2][1] * e[0][0]};
+    const double r3[3] = {e[0][1] * e[1][2] - e[0][2] * e[1][1], e[0][2] * e[1][0] - e[0][0] * e[1][2],
+                          e[0][0] * e[1][1] - e[0][1] * e[1][0]};
+    det = e[0][0] * r1[0] + e[0][1] * r1[1] + e[0][2] * r1[2];
+    const double inv = 1.0 / det;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      g.G[1][d] = r1[d] * inv;
+      g.G[2][d] = r2[d] * inv;
+      g.G[3][d] = r3[d] * inv;
+    }
+    g.vol = fabs(det) * (1.0 / 6.0);
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    double s = g.G[1][d];
+#pragma unroll
+    for (int k = 2; k <= D; ++k) s += g.G[k][d];
+    g.G[0][d] = -s;
+  }
+  double h2 = 0.0;  // CellDiameter^2 = max squared vertex distance (main.py:100)
+#pragma unroll
+  for (int a = 0; a <= D; ++a)
+#pragma unroll
+    for (int b = a + 1; b <= D; ++b) {
+      double s = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const double t = g.X[a][d] - g.X[b][d];
+        s += t * t;
+      }
+      h2 = fmax(h2, s);
+    }
+  g.h2 = h2;
+}
+
+// cell-local coefficients of a P_K function (dofmap NULL => vertex dofs = mesh.cells, K == 1 only)
+template <int D, int K>
+__device__ __forceinline__ void load_dofs(const phifem_mesh& m, const phifem_pk_space& sp,
+                                          const double* __restrict__ coef, int64_t c,
+                                          double (&out)[Space<D, K>::ND]) {
+  constexpr int ND = Space<D, K>::ND;
+  const int32_t* dm = sp.dofmap ? sp.dofmap + c * ND : m.cells + c * ND;
+#pragma unroll
+  for (int k = 0; k < ND; ++k) out[k] = __ldg(coef + __ldg(dm + k));
+}
+
+// phi_h, grad(phi_h) at a point from the tabulated basis (KP == KW shares the tables)
+template <int D, int KW, int KP>
+__device__ __forceinline__ void eval_phi(const double (&lam)[D + 1], const double (&G)[D + 1][D],
+                                         const double (&wv)[Space<D, KW>::ND],
+                                         const double (&wg)[Space<D, KW>::ND][D],
+                                         const double (&pc)[Space<D, KP>::ND], double& ph, double (&gph)[D]) {
+  constexpr int NDP = Space<D, KP>::ND;
+  ph = 0.0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) gph[d] = 0.0;
+  if constexpr (KP == KW) {
+#pragma unroll
+    for (int k = 0; k < NDP; ++k) {
+      ph += pc[k] * wv[k];
+#pragma unroll
+      for (int d = 0; d < D; ++d) gph[d] += pc[k] * wg[k][d];
+    }
+  } else {
+    double pv[NDP], pg[NDP][D];
+    tabulate<D, KP>(lam, G, pv, pg);
+#pragma unroll
+    for (int k = 0; k < NDP; ++k) {
+      ph += pc[k] * pv[k];
+#pragma unroll
+      for (int d = 0; d < D; ++d) gph[d] += pc[k] * pg[k][d];
+    }
+  }
+}
+
+// ---- cells: rows [I0, I1) of the symmetric element matrix (columns j >= i) and of the load vector ----
+//   A_ij = int grad(phi psi_i).grad(phi psi_j) + [cut] sigma h^2 int lap(phi psi_i) lap(phi psi_j)   (main.py:105-112)
+//   b_i  = int f phi psi_i - [cut] sigma h^2 int f lap(phi psi_i)                                     (:126-128)
+template <int D, int KW, int KP, int I0, int I1>
+__device__ __forceinline__ void cell_rows(const Geometry<D>& g, const double (&pc)[Space<D, KP>::ND],
+                                          const double (&fc)[Space<D, KW>::ND], bool is_cut, double sigma,
+                                          const double* __restrict__ qlam, const double* __restrict__ qw,
+                                          int nq, const int32_t* __restrict__ slots, int64_t stride,
+                                          const int32_t* __restrict__ dofs, double* __restrict__ data,
+                                          double* __restrict__ b) {
+  constexpr int NV = D + 1, ND = Space<D, KW>::ND, NDP = Space<D, KP>::ND, NR = I1 - I0;
+  double A[NR][ND], bv[NR];
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    bv[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < ND; ++j) A[i][j] = 0.0;
+  }
+  double wl[ND], lph = 0.0;
+  laplacians<D, KW>(g.G, wl);
+  {
+    double pl[NDP];
+    laplacians<D, KP>(g.G, pl);
+#pragma unroll
+    for (int k = 0; k < NDP; ++k) lph += pc[k] * pl[k];
+  }
+  const double sh2 = is_cut ? sigma * g.h2 : 0.0;
+  for (int q = 0; q < nq; ++q) {
+    double lam[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) lam[k] = qlam[q * NV + k];
+    const double w = qw[q] * g.vol;
+    double wv[ND], wg[ND][D];
+    tabulate<D, KW>(lam, g.G, wv, wg);
+    double ph, gph[D];
+    eval_phi<D, KW, KP>(lam, g.G, wv, wg, pc, ph, gph);
+    double fq = 0.0;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) fq += fc[k] * wv[k];
+    double gu[ND][D];
+#pragma unroll
+    for (int j = I0; j < ND; ++j)
+#pragma unroll
+      for (int d = 0; d < D; ++d) gu[j][d] = wv[j] * gph[d] + ph * wg[j][d];
+    const double wf = w * fq;
+#pragma unroll
+    for (int i = I0; i < I1; ++i) {
+      bv[i - I0] += wf * ph * wv[i];
+      double wgi[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) wgi[d] = w * gu[i][d];
+#pragma unroll
+      for (int j = i; j < ND; ++j) A[i - I0][j] += dotd<D>(wgi, gu[j]);
+    }
+    if (is_cut) {
+      double lu[ND];
+#pragma unroll
+      for (int j = I0; j < ND; ++j) lu[j] = wv[j] * lph + 2.0 * dotd<D>(gph, wg[j]) + ph * wl[j];
+      const double ws = w * sh2;
+#pragma unroll
+      for (int i = I0; i < I1; ++i) {
+        bv[i - I0] -= ws * fq * lu[i];
+        const double wli = ws * lu[i];
+#pragma unroll
+        for (int j = i; j < ND; ++j) A[i - I0][j] += wli * lu[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = I0; i < I1; ++i) {
+    atomicAdd(b + dofs[i], bv[i - I0]);
+#pragma unroll
+    for (int j = i; j < ND; ++j) {
+      const double v = A[i - I0][j];
+      atomicAdd(data + __ldg(slots + (int64_t)(i * ND + j) * stride), v);
+      if (j != i) atomicAdd(data + __ldg(slots + (int64_t)(j * ND + i) * stride), v);
+    }
+  }
+}
+
+// row ranges of the passes (blockIdx.y): the accumulators of one pass must fit the register file
+template <int ND> struct Passes { static constexpr int N = 1; };
+template <> struct Passes<10> { static constexpr int N = 3; };
+
+template <int D, int KW, int KP>
+__global__ void __launch_bounds__(kBlockPk) k_assemble_cells_pk(
+    phifem_mesh m, phifem_pk_space sw, phifem_pk_space sp, const double* __restrict__ qlam_g,
+    const double* __restrict__ qw_g, int nq, const double* __restrict__ phi, const double* __restrict__ f,
+    const int8_t* __restrict__ ctags, const int32_t* __restrict__ active, int64_t n_active,
+    const int32_t* __restrict__ slots, double sigma, double* __restrict__ data, double* __restrict__ b) {
+  constexpr int NV = D + 1, ND = Space<D, KW>::ND, NDP = Space<D, KP>::ND;
+  __shared__ double qlam[kMaxQuadPoints * NV], qw[kMaxQuadPoints];
+  for (int i = threadIdx.x; i < nq * NV; i += blockDim.x) qlam[i] = qlam_g[i];
+  for (int i = threadIdx.x; i < nq; i += blockDim.x) qw[i] = qw_g[i];
+  __syncthreads();
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_active) return;
+  const int64_t c = __ldg(active + e);
+  Geometry<D> g;
+  load_geometry<D>(m, c, g);
+  double pc[NDP], fc[ND];
+  load_dofs<D, KP>(m, sp, phi, c, pc);
+  load_dofs<D, KW>(m, sw, f, c, fc);
+  int32_t dofs[ND];
+  {
+    const int32_t* dm = sw.dofmap ? sw.dofmap + c * ND : m.cells + c * ND;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) dofs[k] = __ldg(dm + k);
+  }
+  const bool is_cut = ctags[c] == 2;
+  const int32_t* sl = slots + e;
+  if constexpr (ND == 10) {
+    if (blockIdx.y == 0)
+      cell_rows<D, KW, KP, 0, 2>(g, pc, fc, is_cut, sigma, qlam, qw, nq, sl, n_active, dofs, data, b);
+    else if (blockIdx.y == 1)
+      cell_rows<D, KW, KP, 2, 5>(g, pc, fc, is_cut, sigma, qlam, qw, nq, sl, n_active, dofs, data, b);
+    else
+      cell_rows<D, KW, KP, 5, 10>(g, pc, fc, is_cut, sigma, qlam, qw, nq, sl, n_active, dofs, data, b);
+  } else {
+    cell_rows<D, KW, KP, 0, ND>(g, pc, fc, is_cut, sigma, qlam, qw, nq, sl, n_active, dofs, data, b);
+  }
+}
+
+// barycentric point of the cell from a point of local facet o (the facet's vertices in ascending local order)
+template <int D>
+__device__ __forceinline__ void facet_to_cell(const double* __restrict__ fl, int o, double (&lam)[D + 1]) {
+#pragma unroll
+  for (int k = 0; k <= D; ++k) {
+    double v = 0.0;
+    if (k < o) v = fl[k];
+    if (k > o) v = fl[k - 1];
+    lam[k] = v;
+  }
+}
+
+template <int D>
+__device__ __forceinline__ void facet_normal(const Geometry<D>& g, int o, double (&n)[D], double& area) {
+  double Go[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) Go[d] = 0.0;
+#pragma unroll
+  for (int k = 0; k <= D; ++k)
+    if (k == o)
+#pragma unroll
+      for (int d = 0; d < D; ++d) Go[d] = g.G[k][d];
+  const double gnorm = sqrt(dotd<D>(Go, Go));
+#pragma unroll
+  for (int d = 0; d < D; ++d) n[d] = -Go[d] / gnorm;  // outward normal of THIS cell
+  area = D * g.vol * gnorm;
+}
+
+template <int N>
+__device__ __forceinline__ double pick(const double (&a)[N], int i) {
+  double v = a[0];
+#pragma unroll
+  for (int k = 1; k < N; ++k)
+    if (k == i) v = a[k];
+  return v;
+}
+
+// ---- one-sided boundary term: one thread per (entity, test dof i) ------------------------------------------
+//   A_ij = -int_F (grad(phi psi_j).n) phi psi_i    (main.py:106), n = outward normal of the entity's cell
+template <int D, int KW, int KP>
+__global__ void __launch_bounds__(kBlockPk) k_assemble_boundary_pk(
+    phifem_mesh m, phifem_pk_space sw, phifem_pk_space sp, const double* __restrict__ qlam_g,
+    const double* __restrict__ qw_g, int nq, const double* __restrict__ phi,
+    const int32_t* __restrict__ entities, int64_t n_entities, const int32_t* __restrict__ slots,
+    double* __restrict__ data) {
+  constexpr int NV = D + 1, ND = Space<D, KW>::ND, NDP = Space<D, KP>::ND;
+  __shared__ double qlam[kMaxQuadPoints * D], qw[kMaxQuadPoints];
+  for (int i = threadIdx.x; i < nq * D; i += blockDim.x) qlam[i] = qlam_g[i];
+  for (int i = threadIdx.x; i < nq; i += blockDim.x) qw[i] = qw_g[i];
+  __syncthreads();
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_entities * ND) return;
+  const int64_t e = t / ND;
+  const int i = (int)(t - e * ND);
+  const int64_t c = __ldg(entities + 2 * e);
+  const int o = __ldg(entities + 2 * e + 1);
+  Geometry<D> g;
+  load_geometry<D>(m, c, g);
+  double pc[NDP];
+  load_dofs<D, KP>(m, sp, phi, c, pc);
+  double n[D], area;
+  facet_normal<D>(g, o, n, area);
+  double A[ND];
+#pragma unroll
+  for (int j = 0; j < ND; ++j) A[j] = 0.0;
+  for (int q = 0; q < nq; ++q) {
+    double lam[NV];
+    facet_to_cell<D>(qlam + q * D, o, lam);
+    double wv[ND], wg[ND][D];
+    tabulate<D, KW>(lam, g.G, wv, wg);
+    double ph, gph[D];
+    eval_phi<D, KW, KP>(lam, g.G, wv, wg, pc, ph, gph);
+    const double gpn = dotd<D>(gph, n);
+    const double ui = -qw[q] * area * ph * pick<ND>(wv, i);
+#pragma unroll
+    for (int j = 0; j < ND; ++j) A[j] += ui * (wv[j] * gpn + ph * dotd<D>(wg[j], n));
+  }
+#pragma unroll
+  for (int j = 0; j < ND; ++j) atomicAdd(data + __ldg(slots + (int64_t)(i * ND + j) * n_entities + e), A[j]);
+}
+
+// ---- ghost penalty: one thread per (facet, macro test dof a) -----------------------------------------------
+//   E_ab = sigma avg(h_T) int_F J_a J_b,  J_a = grad(phi psi_a).n of the side dof a lives on   (main.py:113-118)
+// macro dofs = [dofs of cell + (= f2c[f][0]), dofs of cell -]: 2 ND rows/columns, shared dofs appear twice
+// and add into the same CSR entry, as in dolfinx's interior-facet assembly.
+template <int D, int KW, int KP>
+__global__ void __launch_bounds__(kBlockPk) k_assemble_ghost_pk(
+    phifem_mesh m, phifem_pk_space sw, phifem_pk_space sp, const double* __restrict__ qlam_g,
+    const double* __restrict__ qw_g, int nq, const double* __restrict__ phi,
+    const int32_t* __restrict__ facets, int64_t n_facets, const int32_t* __restrict__ slots, double sigma,
+    double* __restrict__ data) {
+  constexpr int NV = D + 1, ND = Space<D, KW>::ND, NDP = Space<D, KP>::ND, NM = 2 * ND;
+  __shared__ double qlam[kMaxQuadPoints * D], qw[kMaxQuadPoints];
+  for (int i = threadIdx.x; i < nq * D; i += blockDim.x) qlam[i] = qlam_g[i];
+  for (int i = threadIdx.x; i < nq; i += blockDim.x) qw[i] = qw_g[i];
+  __syncthreads();
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_facets * NM) return;
+  const int64_t e = t / NM;
+  const int a = (int)(t - e * NM);
+  const int32_t fct = __ldg(facets + e);
+  const int2 cc = __ldg(reinterpret_cast<const int2*>(m.f2c) + fct);
+  Geometry<D> gp, gm;
+  load_geometry<D>(m, cc.x, gp);
+  load_geometry<D>(m, cc.y, gm);
+  int op = 0, om = 0;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    if (__ldg(m.c2f + (int64_t)cc.x * NV + k) == fct) op = k;
+    if (__ldg(m.c2f + (int64_t)cc.y * NV + k) == fct) om = k;
+  }
+  double pcp[NDP], pcm[NDP];
+  load_dofs<D, KP>(m, sp, phi, cc.x, pcp);
+  load_dofs<D, KP>(m, sp, phi, cc.y, pcm);
+  double np_[D], nm_[D], area, area_m;
+  facet_normal<D>(gp, op, np_, area);
+  facet_normal<D>(gm, om, nm_, area_m);
+  const double coef = sigma * 0.5 * (sqrt(gp.h2) + sqrt(gm.h2)) * area;
+  double E[NM];
+#pragma unroll
+  for (int bb = 0; bb < NM; ++bb) E[bb] = 0.0;
+  for (int q = 0; q < nq; ++q) {
+    double lam[NV], J[NM];
+    facet_to_cell<D>(qlam + q * D, op, lam);
+    {
+      double wv[ND], wg[ND][D], ph, gph[D];
+      tabulate<D, KW>(lam, gp.G, wv, wg);
+      eval_phi<D, KW, KP>(lam, gp.G, wv, wg, pcp, ph, gph);
+      const double gpn = dotd<D>(gph, np_);
+#pragma unroll
+      for (int j = 0; j < ND; ++j) J[j] = wv[j] * gpn + ph * dotd<D>(wg[j], np_);
+    }
+    // the same physical point in the barycentric coordinates of cell -
+    double xq[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) s += lam[k] * gp.X[k][d];
+      xq[d] = s - gm.X[0][d];
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) lam[k] = (k == 0 ? 1.0 : 0.0) + dotd<D>(gm.G[k], xq);
+    {
+      double wv[ND], wg[ND][D], ph, gph[D];
+      tabulate<D, KW>(lam, gm.G, wv, wg);
+      eval_phi<D, KW, KP>(lam, gm.G, wv, wg, pcm, ph, gph);
+      const double gpn = dotd<D>(gph, nm_);
+#pragma unroll
+      for (int j = 0; j < ND; ++j) J[ND + j] = wv[j] * gpn + ph * dotd<D>(wg[j], nm_);
+    }
+    const double wa = qw[q] * coef * pick<NM>(J, a);
+#pragma unroll
+    for (int bb = 0; bb < NM; ++bb) E[bb] += wa * J[bb];
+  }
+#pragma unroll
+  for (int bb = 0; bb < NM; ++bb) atomicAdd(data + __ldg(slots + (int64_t)(a * NM + bb) * n_facets + e), E[bb]);
+}
+
+int check_pk(const phifem_mesh* m, const phifem_pk_space* sw, const phifem_pk_space* sp,
+             const double* points, const double* weights, int nq) {
+  PHIFEM_CHECK_ARG(m != nullptr && m->x && m->cells, "mesh is null");
+  if (m->cell_type != PHIFEM_TRIANGLE && m->cell_type != PHIFEM_TETRAHEDRON) {
+    set_error("P_k assembly supports triangles and tetrahedra, got cell type %d", m->cell_type);
+    return PHIFEM_ERR_UNSUPPORTED;
+  }
+  const int D = m->cell_type == PHIFEM_TRIANGLE ? 2 : 3;
+  PHIFEM_CHECK_ARG(m->gdim == D, "gdim mismatch");
+  PHIFEM_CHECK_ARG(sw && sp, "function spaces are null");
+  for (const phifem_pk_space* s : {sw, sp}) {
+    if (s->degree != 1 && s->degree != 2) {
+      set_error("P_k assembly implements degrees 1 and 2, got %d", s->degree);
+      return PHIFEM_ERR_UNSUPPORTED;
+    }
+    const int nd = s->degree == 1 ? D + 1 : (D + 1) + D * (D + 1) / 2;
+    PHIFEM_CHECK_ARG(s->n_dofs_per_cell == nd, "n_dofs_per_cell does not match the degree");
+    PHIFEM_CHECK_ARG(s->dofmap || s->degree == 1, "a P2 space needs its dofmap");
+  }
+  PHIFEM_CHECK_ARG(points && weights && nq > 0 && nq <= kMaxQuadPoints, "quadrature rule (1..128 points)");
+  return PHIFEM_OK;
+}
+
+// instantiate kernel<D, KW, KP> for the runtime (cell type, degrees)
+template <typename F>
+void dispatch(int cell_type, int kw, int kp, F&& f) {
+  auto with_d = [&](auto d) {
+    constexpr int D = decltype(d)::value;
+    if (kw == 1 && kp == 1) f(d, std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{});
+    else if (kw == 1) f(d, std::integral_constant<int, 1>{}, std::integral_constant<int, 2>{});
+    else if (kp == 1) f(d, std::integral_constant<int, 2>{}, std::integral_constant<int, 1>{});
+    else f(d, std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{});
+    (void)D;
+  };
+  if (cell_type == PHIFEM_TRIANGLE) with_d(std::integral_constant<int, 2>{});
+  else with_d(std::integral_constant<int, 3>{});
+}
+
+}  // namespace
+}  // namespace phifem
+
+using namespace phifem;
+
+extern "C" int phifem_assemble_cells_pk(const phifem_mesh* mesh, const phifem_pk_space* space_w,
+                                        const phifem_pk_space* space_phi, const phifem_quadrature* quad,
+                                        const double* phi, const double* f, const int8_t* cell_tags8,
+                                        const int32_t* active, int64_t n_active, const int32_t* slots,
+                                        double sigma, double* data, double* b, void* stream) {
+  PHIFEM_CHECK_ARG(quad != nullptr, "quadrature is null");
+  if (int rc = check_pk(mesh, space_w, space_phi, quad->cell_points, quad->cell_weights, quad->n_cell_points))
+    return rc;
+  PHIFEM_CHECK_ARG(phi && f && cell_tags8 && data && b, "null pointer");
+  PHIFEM_CHECK_ARG(n_active == 0 || (active && slots), "null active / slots");
+  if (n_active == 0) return PHIFEM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  dispatch(mesh->cell_type, space_w->degree, space_phi->degree, [&](auto d, auto kw, auto kp) {
+    constexpr int D = decltype(d)::value, KW = decltype(kw)::value, KP = decltype(kp)::value;
+    const dim3 grid((unsigned)((n_active + kBlockPk - 1) / kBlockPk), Passes<Space<D, KW>::ND>::N);
+    k_assemble_cells_pk<D, KW, KP><<<grid, kBlockPk, 0, st>>>(
+        *mesh, *space_w, *space_phi, quad->cell_points, quad->cell_weights, quad->n_cell_points, phi, f,
+        cell_tags8, active, n_active, slots, sigma, data, b);
+  });
+  PHIFEM_CHECK_LAUNCH();
+  return PHIFEM_OK;
+}
+
+extern "C" int phifem_assemble_boundary_pk(const phifem_mesh* mesh, const phifem_pk_space* space_w,
+                                           const phifem_pk_space* space_phi, const phifem_quadrature* quad,
+                                           const double* phi, const int32_t* entities, int64_t n_entities,
+                                           const int32_t* slots, double* data, void* stream) {
+  PHIFEM_CHECK_ARG(quad != nullptr, "quadrature is null");
+  if (int rc = check_pk(mesh, space_w, space_phi, quad->facet_points, quad->facet_weights, quad->n_facet_points))
+    return rc;
+  PHIFEM_CHECK_ARG(phi && data, "null pointer");
+  PHIFEM_CHECK_ARG(n_entities == 0 || (entities && slots), "null entities / slots");
+  if (n_entities == 0) return PHIFEM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  dispatch(mesh->cell_type, space_w->degree, space_phi->degree, [&](auto d, auto kw, auto kp) {
+    constexpr int D = decltype(d)::value, KW = decltype(kw)::value, KP = decltype(kp)::value;
+    const int64_t threads = n_entities * Space<D, KW>::ND;
+    k_assemble_boundary_pk<D, KW, KP><<<(unsigned)((threads + kBlockPk - 1) / kBlockPk), kBlockPk, 0, st>>>(
+        *mesh, *space_w, *space_phi, quad->facet_points, quad->facet_weights, quad->n_facet_points, phi,
+        entities, n_entities, slots, data);
+  });
+  PHIFEM_CHECK_LAUNCH();
+  return PHIFEM_OK;
+}
+
+extern "C" int phifem_assemble_ghost_pk(const phifem_mesh* mesh, const phifem_pk_space* space_w,
+                                        const phifem_pk_space* space_phi, const phifem_quadrature* quad,
+                                        const double* phi, const int32_t* facets, int64_t n_facets,
+                                        const int32_t* slots, double sigma, double* data, void* stream) {
+  PHIFEM_CHECK_ARG(quad != nullptr, "quadrature is null");
+  if (int rc = check_pk(mesh, space_w, space_phi, quad->facet_points, quad->facet_weights, quad->n_facet_points))
+    return rc;
+  PHIFEM_CHECK_ARG(phi && data && mesh->c2f && mesh->f2c, "null pointer");
+  PHIFEM_CHECK_ARG(n_facets == 0 || (facets && slots), "null facets / slots");
+  if (n_facets == 0) return PHIFEM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  dispatch(mesh->cell_type, space_w->degree, space_phi->degree, [&](auto d, auto kw, auto kp) {
+    constexpr int D = decltype(d)::value, KW = decltype(kw)::value, KP = decltype(kp)::value;
+    const int64_t threads = n_facets * 2 * Space<D, KW>::ND;
+    k_assemble_ghost_pk<D, KW, KP><<<(unsigned)((threads + kBlockPk - 1) / kBlockPk), kBlockPk, 0, st>>>(
+        *mesh, *space_w, *space_phi, quad->facet_points, quad->facet_weights, quad->n_facet_points, phi,
+        facets, n_facets, slots, sigma, data);
+  });
+  PHIFEM_CHECK_LAUNCH();
+  return PHIFEM_OK;
+}

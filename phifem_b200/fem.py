@@ -112,11 +112,40 @@ def _unique_rows(keys):
     return uniq, inv.reshape(-1)
 
 
+def simplex_dofmap_device(mesh, degree):
+    """Dofmap [Nc, nd] (int32, on the mesh's device) and dof count of P1 / P2 Lagrange on triangles /
+    tetrahedra, built with torch sort/unique where the mesh lives.  Same numbering as the host builder in
+    `FunctionSpace`: vertex dofs = vertex ids, then one dof per edge, edges numbered by the lexicographic
+    rank of their sorted vertex pair, cell-local edge order = LOCAL_EDGES."""
+    import torch
+    if degree == 1:
+        return mesh.cells, mesh.num_vertices
+    assert degree == 2 and mesh.cell_type in ("triangle", "tetrahedron")
+    nv = mesh.num_vertices
+    c = mesh.cells.long()
+    edges = LOCAL_EDGES[mesh.cell_type]
+    a = torch.stack([c[:, e[0]] for e in edges], dim=1)
+    b = torch.stack([c[:, e[1]] for e in edges], dim=1)
+    key = torch.minimum(a, b) * nv + torch.maximum(a, b)
+    del a, b
+    uniq, inv = torch.unique(key.reshape(-1), sorted=True, return_inverse=True)
+    n_edges = int(uniq.numel())
+    del uniq, key
+    dm = torch.cat([c, nv + inv.reshape(c.shape[0], len(edges))], dim=1).to(torch.int32).contiguous()
+    return dm, nv + n_edges
+
+
 class FunctionSpace:
     def __init__(self, mesh, degree):
         self.mesh = mesh
         self.element = LagrangeElement(mesh.cell_type, degree)
         self.degree = degree
+        self._dofmap_dev = None
+        if degree <= 2 and mesh.cell_type in ("triangle", "tetrahedron"):
+            # large meshes: sort/unique on the device, host copy made on first use
+            self._dofmap_dev, self.num_dofs = simplex_dofmap_device(mesh, degree)
+            self._dofmap = None
+            return
         cells = mesh.cells_host.astype(np.int64)
         nc = len(cells)
         nv = mesh.num_vertices
@@ -149,9 +178,41 @@ class FunctionSpace:
             base = offset + np.arange(nc)[:, None] * n_int
             cols.append(base + np.arange(n_int)[None, :])
             offset += nc * n_int
-        self.dofmap = np.ascontiguousarray(np.concatenate(cols, axis=1).astype(np.int32))
+        self._dofmap = np.ascontiguousarray(np.concatenate(cols, axis=1).astype(np.int32))
         self.num_dofs = int(offset)
-        assert self.dofmap.shape[1] == self.element.ndofs
+        assert self._dofmap.shape[1] == self.element.ndofs
+
+    @property
+    def dofmap(self):
+        """Host dofmap [Nc, nd] int32."""
+        if self._dofmap is None:
+            self._dofmap = np.ascontiguousarray(self._dofmap_dev.cpu().numpy())
+        return self._dofmap
+
+    @property
+    def dofmap_dev(self):
+        """Dofmap on the mesh's device (int32 [Nc, nd])."""
+        if self._dofmap_dev is None:
+            import torch
+            self._dofmap_dev = torch.from_numpy(self._dofmap).to(self.mesh.device).contiguous()
+        return self._dofmap_dev
+
+    def dof_coordinates_dev(self):
+        """Dof coordinates [num_dofs, gdim] on the mesh's device (P1 / P2 on simplices): vertices, then edge
+        midpoints -- what `tabulate_dof_coordinates` returns on the host."""
+        import torch
+        if self.degree > 2 or self.mesh.cell_type not in ("triangle", "tetrahedron"):
+            return torch.from_numpy(self.tabulate_dof_coordinates()).to(self.mesh.device)
+        mesh = self.mesh
+        if self.degree == 1:
+            return mesh.x
+        out = torch.empty((self.num_dofs, mesh.gdim), dtype=torch.float64, device=mesh.device)
+        out[:mesh.num_vertices] = mesh.x
+        nvpc = mesh.cells.shape[1]
+        dm = self.dofmap_dev.long()
+        for e, (a, b) in enumerate(LOCAL_EDGES[mesh.cell_type]):
+            out[dm[:, nvpc + e]] = 0.5 * mesh.x[dm[:, a]] + 0.5 * mesh.x[dm[:, b]]
+        return out
 
     def tabulate_dof_coordinates(self):
         """Physical coordinates of the dofs [num_dofs, gdim] (affine / bilinear push-forward of the

@@ -71,11 +71,10 @@ class _DeviceLevelset:
                 # vertex dofs, points on the vertices: identity table => fast kernel (dofmap = cells)
                 self.c.dofmap, self.c.cell_table = None, None
             else:
-                if not hasattr(V, "_dofmap_dev") or V._dofmap_dev.device != dev:
-                    V._dofmap_dev = torch.from_numpy(V.dofmap).to(dev)
+                dm = V.dofmap_dev
                 ctab = torch.as_tensor(V.element.tabulate(pts), **f64).contiguous()
-                self.c.dofmap, self.c.cell_table = _lib.ptr(V._dofmap_dev), _lib.ptr(ctab)
-                self.keep += [ctab]
+                self.c.dofmap, self.c.cell_table = _lib.ptr(dm), _lib.ptr(ctab)
+                self.keep += [ctab, dm]
         elif callable(levelset):
             vals = self._evaluate(mesh, levelset, pts)
             fvals = self._evaluate(mesh, levelset, fpts.reshape(-1, fpts.shape[-1]))
