@@ -26,6 +26,19 @@ import numpy as np  # noqa: E402
 
 METRIC = "phi-FEM cells assembled/s (tags+CSR)"
 UNIT = "cells/s"
+# 2D configurations (BASELINE.json configs[1..2]): disc in [-1, 1]^2, offsets keep |phi_v| >> ulp
+DISC_CENTER = (3.141592653589793 / 1000.0, 2.718281828459045 / 1000.0)
+DISC_RADIUS = 0.6
+CONFIGS = {   # name -> (default n, description)
+    "3d-p1": (204, "synthetic 3D P1 phi-FEM Poisson (BASELINE.json configs[4]): %d Kuhn tetrahedra per GPU "
+                   "(n=%d), sphere level set"),
+    "2d-p1": (1414, "synthetic 2D P1 phi-FEM Poisson (BASELINE.json configs[1] scale, 4 M triangles): %d "
+                    "triangles (n=%d), disc level set"),
+    "2d-p2": (2828, "synthetic 2D P2 phi-FEM Poisson (BASELINE.json configs[2], 16 M triangles): %d triangles "
+                    "(n=%d), disc level set, P2 trial/test space and P2 level set, P1 detection"),
+    "3d-p2": (64, "synthetic 3D P2 phi-FEM Poisson: %d Kuhn tetrahedra (n=%d), sphere level set, P2 trial/test "
+                  "space and P2 level set, P1 detection"),
+}
 
 
 def _peaks():
@@ -90,12 +103,15 @@ def algorithmic_bytes(counts):
     """compulsory traffic, each input read once / each output written once."""
     nc, nv, nf, gdim, nvpc = counts["Nc"], counts["Nv"], counts["Nf"], counts["gdim"], counts["nvpc"]
     na, nva, ng, nnz = counts["Na"], counts["Nv_active"], counts["Ng"], counts["nnz"]
+    nd, nrow = counts.get("nd", nvpc), counts.get("Nrow", nv)
+    ndof_a = counts.get("Ndof_active", nva)          # active dofs of the trial/test space (= of phi and f)
     b_tags_cells = 4 * nvpc * nc + 8 * nv + 4 * nc
     b_tags_facets = 4 * nvpc * nc + 4 * nf            # c2f (== f2c in size) + facet tags out
-    b_asm = (4 * nvpc * na + 8 * gdim * nva + 8 * nva + 8 * nva + 4 * na + 8 * ng + 12 * nnz
-             + 4 * (nv + 1) + 8 * nv)
+    geo = 4 * nvpc * na if nd != nvpc else 0          # P2: cell -> vertex for the geometry besides the dofmap
+    b_asm = (4 * nd * na + geo + 8 * gdim * nva + 8 * ndof_a + 8 * ndof_a + 4 * na + 8 * ng + 12 * nnz
+             + 4 * (nrow + 1) + 8 * nrow)
     # the numeric cell kernel alone: no column indices / indptr (they belong to the symbolic phase)
-    b_cells_kernel = 4 * nvpc * na + 8 * gdim * nva + 16 * nva + 4 * na + 8 * nnz + 8 * nva
+    b_cells_kernel = 4 * nd * na + geo + 8 * gdim * nva + 16 * ndof_a + 4 * na + 8 * nnz + 8 * ndof_a
     return {"tags_cells": b_tags_cells, "tags_facets": b_tags_facets, "assembly": b_asm,
             "cells_kernel": b_cells_kernel, "total": b_tags_cells + b_tags_facets + b_asm}
 
@@ -167,7 +183,7 @@ def run_reference(args):
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -198,14 +214,21 @@ def run_ours(args):
         mesh, phi, f = problem.mesh, problem.phi, problem.f
     else:
         problem = None
-        mesh = synthetic.box_mesh(n, device=dev)
-        phi = synthetic.sphere_levelset(mesh.x)
-        f = synthetic.ball_source(mesh.x)
+        if args.config.startswith("2d"):
+            mesh = synthetic.rectangle_mesh(n, device=dev)
+            ls_kw = dict(center=DISC_CENTER, radius=DISC_RADIUS)
+        else:
+            mesh = synthetic.box_mesh(n, device=dev)
+            ls_kw = {}
+        phi = synthetic.sphere_levelset(mesh.x, **ls_kw)
+        f = synthetic.ball_source(mesh.x, **({"center": DISC_CENTER} if ls_kw else {}))
     mesh.c2f  # build the facet topology (mesh-level symbolic, once per mesh)
     mesh.detj_bounds()
     torch.cuda.synchronize()
     topo_s = time.perf_counter() - t_setup
 
+    degree = 2 if args.config.endswith("p2") else 1
+    phi_asm, f_asm = phi, f
     V = fem.functionspace_p1_device(mesh)
     fn = fem.Function(V, phi)
     dls = mesh_scripts._DeviceLevelset(mesh, fn, 1)
@@ -229,8 +252,17 @@ def run_ours(args):
         ctags, ftags = MeshTags(mesh, tdim, ws.cell_tags), MeshTags(mesh, tdim - 1, ws.facet_tags)
         ctags.tags8, ftags.tags8 = ws.cell_tags8, ws.facet_tags8
         ents = mesh_scripts._integration_entities_dev(mesh, ws.cell_tags8, ws.facet_tags8, 4, (1, 2))
-        plan = assemble.build_plan(mesh, ctags, ftags, ents, method=args.scatter, capacity=args.capacity,
-                                   order=args.order)
+        if degree == 2:
+            # P2 trial/test space and P2 level set: phi_h / f_h = interpolants at the P2 nodes (main.py:85-90)
+            Vw = fem.functionspace(mesh, 2)
+            Xd = Vw.dof_coordinates_dev()
+            phi_asm = synthetic.sphere_levelset(Xd, **ls_kw)
+            f_asm = synthetic.ball_source(Xd, **({"center": DISC_CENTER} if ls_kw else {}))
+            del Xd
+            plan = assemble.build_plan(mesh, ctags, ftags, ents, V=Vw, V_phi=Vw)
+        else:
+            plan = assemble.build_plan(mesh, ctags, ftags, ents, method=args.scatter, capacity=args.capacity,
+                                       order=args.order)
         data, b = plan.new_outputs()
     torch.cuda.synchronize()
     symbolic_ms = (time.perf_counter() - t0) * 1e3
@@ -253,7 +285,7 @@ def run_ours(args):
         if problem is not None:
             problem.assemble(1.0, marks=mark)
         else:
-            assemble.assemble_into(plan, phi, f, 1.0, data, b, marks=mark)
+            assemble.assemble_into(plan, phi_asm, f_asm, 1.0, data, b, marks=mark)
         mark()
 
     for _ in range(args.warmup):
@@ -296,9 +328,13 @@ def run_ours(args):
         n_cells_total = int(t.item())
     value = n_cells_total / (ms_per_step * 1e-3)
 
+    act_v = torch.zeros(mesh.num_vertices, dtype=torch.bool, device=dev)
+    act_v[mesh.cells[plan.active.long()].long().reshape(-1)] = True
     counts = {"Nc": mesh.num_cells, "Nv": mesh.num_vertices, "Nf": mesh.num_facets, "gdim": mesh.gdim,
               "nvpc": mesh.cells.shape[1], "Na": int(plan.active.numel()), "Ng": int(plan.ghost.numel()),
-              "Nv_active": int((plan.indptr[1:] > plan.indptr[:-1]).sum()), "nnz": plan.nnz,
+              "Nv_active": int(act_v.sum()), "nnz": plan.nnz, "Nrow": plan.n_rows,
+              "nd": getattr(plan, "nd", mesh.cells.shape[1]),
+              "Ndof_active": int((plan.indptr[1:] > plan.indptr[:-1]).sum()),
               "Ne_ds100": int(plan.entities.shape[0]),
               "halo_entries_sent": (sum(hi - lo for lo, hi in plan.send_ranges) if problem is not None else 0),
               "interior": int(counters[0]), "cut": int(counters[1]), "exterior": int(counters[2])}
@@ -313,7 +349,8 @@ def run_ours(args):
     achieved = kbytes / (per[dominant] * 1e-3) / 1e9
     kernel_names = {"tag_cells": "k_tag_cells_p1", "tag_facets": "k_tag_facets",
                     "assemble_cells": {"rows": "k_assemble_rows_p1", "blocked": "k_assemble_blocked_p1",
-                                       "atomic": "k_assemble_cells_p1"}[plan.method]}
+                                       "atomic": "k_assemble_cells_p1",
+                                       "pk-atomic": "k_assemble_cells_pk"}[plan.method]}
     roofline = {"bound": "hbm", "kernel": kernel_names[dominant], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": kbytes,
@@ -332,11 +369,12 @@ def run_ours(args):
     e2e = None
     if world == 1 and not args.no_e2e:
         phi_h = phi.cpu().pin_memory()
-        f_h = f.cpu().pin_memory()
+        f_h = f_asm.cpu().pin_memory()
+        phi_asm_h = phi_asm.cpu().pin_memory() if degree == 2 else phi_h
         out_h = {"ct": torch.empty(mesh.num_cells, dtype=torch.int32).pin_memory(),
                  "ft": torch.empty(mesh.num_facets, dtype=torch.int32).pin_memory(),
                  "data": torch.empty(plan.nnz, dtype=torch.float64).pin_memory(),
-                 "b": torch.empty(mesh.num_vertices, dtype=torch.float64).pin_memory()}
+                 "b": torch.empty(plan.n_rows, dtype=torch.float64).pin_memory()}
         import warnings
 
         def e2e_step():
@@ -344,7 +382,7 @@ def run_ours(args):
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore", RuntimeWarning)
                 ct_, ft_, _, ds_, _ = mesh_scripts.compute_tags_measures(mesh, fn_h, 1, box_mode=True)
-            A_, b_ = assemble.assemble_strong_dirichlet(plan, phi_h, f_h, stab_coef=1.0)
+            A_, b_ = assemble.assemble_strong_dirichlet(plan, phi_asm_h, f_h, stab_coef=1.0)
             out_h["ct"].copy_(ct_.values_dev, non_blocking=True)
             out_h["ft"].copy_(ft_.values_dev, non_blocking=True)
             out_h["data"].copy_(A_.data, non_blocking=True)
@@ -359,14 +397,14 @@ def run_ours(args):
             e2e_step()
         dt = (time.perf_counter() - t0) / e2e_steps
         e2e = {"value": mesh.num_cells / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
-               "h2d_bytes_per_step": int(phi_h.numel() * 8 * 2 + f_h.numel() * 8),
+               "h2d_bytes_per_step": int(phi_h.numel() * 8 + phi_asm_h.numel() * 8 + f_h.numel() * 8),
                "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in out_h.values())),
                "api": "compute_tags_measures(box_mode=True) + assemble_strong_dirichlet(plan, ...) with "
                       "pinned host level set / source in and pinned host tags + CSR values + b out; "
                       "assembly plan (symbolic phase) reused"}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and args.config == "3d-p1":
         cpu = cpu_measure(args.cpu_n, 3, 1)
         cpu.pop("ms_per_step")
 
@@ -374,11 +412,10 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "synthetic 3D P1 phi-FEM Poisson (BASELINE.json configs[4]): "
-                                       "%d Kuhn tetrahedra per GPU (n=%d), sphere level set%s, tags + "
-                                       "strong-Dirichlet CSR assembly"
+                "config": {"workload": (CONFIGS[args.config][1] + "%s, tags + strong-Dirichlet CSR assembly")
                                        % (n_cells_local, n, " per unit cube joined by a thin tube across the "
                                           "partition boundaries" if world > 1 else ""),
+                           "name": args.config,
                            "cells_total": n_cells_total, "counts": counts,
                            "l2_policy": "inputs larger than L2 (%.1f GB streamed per step)"
                                         % (ab["total"] / 1e9),
@@ -389,7 +426,7 @@ def run_ours(args):
                                             if args.dist_mode == "rows" else "NCCL halo exchange")),
                            "timed": "tag kernels + zeroing + assembly kernels; symbolic phase excluded"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-                "gpu_launches": {"rows": 7, "blocked": 5, "atomic": 7}[plan.method] * args.steps,
+                "gpu_launches": {"rows": 7, "blocked": 5, "atomic": 7, "pk-atomic": 9}[plan.method] * args.steps,
                 "symbolic_ms": symbolic_ms, "topology_s": topo_s,
                 "scatter": {"method": plan.method,
                             **({"blocks": plan.blocked.n_blocks, "capacity": plan.blocked.capacity,
@@ -405,9 +442,31 @@ def run_ours(args):
                                 "lane_padding": [plan.rowsplan.cells.padding(), plan.rowsplan.ghost.padding(),
                                                  plan.rowsplan.boundary.padding()],
                                 "plan_bytes": plan.rowsplan.index_bytes()} if plan.rowsplan else {})}}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_JSON_FD = None
+
+
+def _quiet_stdout():
+    """Library chatter (e.g. "NCCL version ..." from libnccl) must not share stdout with the ONE JSON line:
+    fd 1 is pointed at stderr for the run and the line is written to the saved descriptor."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    payload = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(payload.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, payload)
 
 
 def main():
@@ -415,7 +474,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--n", type=int, default=204, help="cubes per edge (6 n^3 tetrahedra per GPU)")
+    ap.add_argument("--config", default="3d-p1", choices=sorted(CONFIGS),
+                    help="workload; the default is the configuration BASELINE.json's metric is quoted on")
+    ap.add_argument("--n", type=int, default=None,
+                    help="cells per edge (6 n^3 tetrahedra per GPU / 2 n^2 triangles); default per config")
     ap.add_argument("--cpu-n", type=int, default=80, help="size of the bounded CPU sample")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scatter", default="rows", choices=["rows", "blocked", "atomic"],
@@ -428,7 +490,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     args = ap.parse_args()
+    if args.n is None:
+        args.n = CONFIGS[args.config][0]
+    if args.config != "3d-p1" and (args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1):
+        raise SystemExit("bench.py: the multi-GPU path runs the 3d-p1 configuration")
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

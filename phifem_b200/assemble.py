@@ -174,6 +174,9 @@ def assemble_into(plan, phi, f, sigma, data, b, marks=None):
     """Numeric phase on the current stream: zero `data`/`b`, run the cell, boundary and ghost-penalty
     kernels.  All arguments are device tensors; nothing synchronises.  `marks` (optional callable) is
     invoked after the zeroing and after each kernel (bench.py records CUDA events there)."""
+    if getattr(plan, "V", None) is not None:
+        from .assemble_pk import assemble_pk_into
+        return assemble_pk_into(plan, phi, f, sigma, data, b, marks=marks)
     marks_given = marks is not None
     marks = marks or (lambda: None)
     _lib.require_cuda(plan.mesh)
