@@ -173,6 +173,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # torchrun pins OMP_NUM_THREADS=1 for its workers; the CPU arm runs on rank 0 alone and uses every
+        # host core (set before libgomp is loaded)
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     res = cpu_measure(args.cpu_n, max(1, args.steps), max(1, args.warmup))
     line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": max(1, args.steps), "warmup": max(1, args.warmup), "ms_per_step": res["ms_per_step"],
