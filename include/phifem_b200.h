@@ -280,6 +280,30 @@ int phifem_assemble_ghost_pk(const phifem_mesh* mesh, const phifem_pk_space* spa
                              const double* phi, const int32_t* facets, int64_t n_facets,
                              const int32_t* slots, double sigma, double* data, void* stream);
 
+/* ---- weak-Dirichlet (dual) phi-FEM operator on the mixed space (u, p) in P_k x P_k, k = 1, 2:
+ * demo/weak-dirichlet/flower/main.py:112-151 (`assemble_matrix(form(a))` :137-139, `assemble_vector(form(L))`
+ * :153-154).  Cell-local mixed dof order [u dofs, p dofs] (nm = 2 nd); the global mixed numbering is the
+ * caller's (`mixed_dofmap` [n_cells, nm]; phifem_b200/assemble_pk.py numbers u at scalar dof s as 2 s, p as
+ * 2 s + 1).  space_w = the scalar P_k space of u, p, f and u_D; space_phi = the level-set space.  Slot maps are
+ * entry-major over the mixed tensors: cells / one-sided entities [nm*nm, n], ghost facets [(2 nm)^2, n] with
+ * macro order [mixed dofs of cell +, mixed dofs of cell -].  ADD semantics; `data` / `b` zeroed by the caller. */
+int phifem_assemble_weak_cells_pk(const phifem_mesh* mesh, const phifem_pk_space* space_w,
+                                  const phifem_pk_space* space_phi, const phifem_quadrature* quad,
+                                  const double* phi, const double* f, const double* u_d,
+                                  const int8_t* cell_tags8, const int32_t* active, int64_t n_active,
+                                  const int32_t* slots, const int32_t* mixed_dofmap, double gamma,
+                                  double sigma, double* data, double* b, void* stream);
+
+/* -int_{ds(100)} (grad u.n) v (:114). */
+int phifem_assemble_weak_boundary_pk(const phifem_mesh* mesh, const phifem_pk_space* space_w,
+                                     const phifem_quadrature* quad, const int32_t* entities,
+                                     int64_t n_entities, const int32_t* slots, double* data, void* stream);
+
+/* sigma avg(h_T) [grad u.n][grad v.n] over dS((2,3)) (:129-134). */
+int phifem_assemble_weak_ghost_pk(const phifem_mesh* mesh, const phifem_pk_space* space_w,
+                                  const phifem_quadrature* quad, const int32_t* facets, int64_t n_facets,
+                                  const int32_t* slots, double sigma, double* data, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

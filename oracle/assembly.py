@@ -387,3 +387,207 @@ def assemble_strong_dirichlet(x, cells, dofmap, n_rows, phi, f, cell_tags, facet
 
 def to_scipy(indptr, indices, data, n):
     return sp.csr_matrix((data, indices, indptr), shape=(n, n))
+
+
+# --------------------------------------------------------------------------------------
+# weak-Dirichlet (dual) phi-FEM operator, mixed P_k x P_k space (u, p)
+# reference demo/weak-dirichlet/flower/main.py:102-154
+#   a = int_{dx(1,2)} grad u.grad v - int_ds (grad u.n) v                                   (:113-114)
+#       + gamma h^-2 int_{dx(2)} (u - h^-1 phi p)(v - h^-1 phi q)                           (:115-122)
+#       + sigma h^2 int_{dx(2)} lap u lap v + sigma int_{dS(2,3)} avg(h) [grad u.n][grad v.n]   (:123-134)
+#   L = int_{dx(1,2)} f v + gamma h^-2 int_{dx(2)} u_D (v - h^-1 phi q) - sigma h^2 int_{dx(2)} f lap v   (:142-151)
+# Cell-local mixed dof order: [u dofs of the cell, p dofs of the cell] (sub-element 0 first, as a
+# basix mixed element lays them out [dep-knowledge]); the global numbering is an input (`mixed_dofmap`).
+# Two independent restatements: brute-force quadrature (P1 / P2) and closed forms for P1 from the exact
+# integrals of barycentric monomials, int prod lambda^e = |K| d! prod e! / (d + sum e)!.
+# --------------------------------------------------------------------------------------
+def weak_cell_tensors_quadrature(x, cells, phi_dofs, f_dofs, ud_dofs, cut, gamma, sigma, kphi=1, kw=1, n=6):
+    """[n, 2nd, 2nd] matrices and [n, 2nd] vectors; phi_dofs [n, nd_phi], f_dofs / ud_dofs [n, nd]."""
+    d = x.shape[1]
+    G, vol, h = simplex_geometry(x, cells)
+    lam, W = simplex_rule(d, n)
+    out_A, out_b = [], []
+    for c in range(len(cells)):
+        wv, wg, wl = lagrange_eval(lam, G[c], kw)
+        pv, _, _ = lagrange_eval(lam, G[c], kphi)
+        nd = wv.shape[1]
+        ph = pv @ phi_dofs[c]
+        wq = W * math.factorial(d) * vol[c]
+        fq = wv @ f_dofs[c]
+        A = np.zeros((2 * nd, 2 * nd))
+        b = np.zeros(2 * nd)
+        A[:nd, :nd] = np.einsum("q,qid,qjd->ij", wq, wg, wg)
+        b[:nd] = np.einsum("q,q,qi->i", wq, fq, wv)
+        if cut[c]:
+            hh = h[c]
+            # test / trial combination  v - h^-1 phi q  over the mixed basis [psi_i, 0] and [0, psi_i]
+            T = np.concatenate([wv, -(ph / hh)[:, None] * wv], axis=1)          # [nq, 2nd]
+            A += gamma / hh ** 2 * np.einsum("q,qa,qb->ab", wq, T, T)
+            A[:nd, :nd] += sigma * hh ** 2 * np.einsum("q,i,j->ij", wq, wl, wl)
+            uq = wv @ ud_dofs[c]
+            b += gamma / hh ** 2 * np.einsum("q,q,qa->a", wq, uq, T)
+            b[:nd] -= sigma * hh ** 2 * np.einsum("q,q,i->i", wq, fq, wl)
+        out_A.append(A)
+        out_b.append(b)
+    return np.array(out_A), np.array(out_b)
+
+
+def weak_boundary_tensors_quadrature(x, cells, ents, kw=1, n=6):
+    """-int_F (grad u_j.n) v_i on (cell, local facet) pairs -> [m, 2nd, 2nd] (only the uu block is non-zero)."""
+    ents = np.asarray(ents).reshape(-1, 2)
+    d = x.shape[1]
+    G, _, _ = simplex_geometry(x, cells[ents[:, 0]])
+    nrm, area = facet_geometry(x, cells, ents)
+    out = []
+    for e, (c, o) in enumerate(ents):
+        lam, W = _facet_bary(d, o, n)
+        wv, wg, _ = lagrange_eval(lam, G[e], kw)
+        nd = wv.shape[1]
+        A = np.zeros((2 * nd, 2 * nd))
+        A[:nd, :nd] = -np.einsum("q,qj,qi->ij", W * area[e], wg @ nrm[e], wv)
+        out.append(A)
+    return np.array(out)
+
+
+def weak_ghost_tensors_quadrature(x, cells, c2f, f2c, facets, sigma, kw=1, n=6):
+    """sigma avg(h) int_F [grad u.n][grad v.n] over macro dofs [mixed dofs of cell +, mixed dofs of cell -]
+    -> [ng, 4nd, 4nd]; only u-u entries are non-zero."""
+    d = x.shape[1]
+    facets = np.asarray(facets)
+    out = []
+    for fct in facets:
+        cc = f2c[fct]
+        J, hsum = [], 0.0
+        for side, c in enumerate(cc):
+            o = int(np.nonzero(c2f[c] == fct)[0][0])
+            G, vol, h = simplex_geometry(x, cells[c:c + 1])
+            nrm, area = facet_geometry(x, cells, [(c, o)])
+            lam, W = _facet_bary(d, o, n)
+            if side == 0:
+                xq = lam @ x[cells[c]]
+                Wp, ar = W, area[0]
+            else:
+                T = np.concatenate([x[cells[c]].T, np.ones((1, d + 1))], axis=0)
+                rhs = np.concatenate([xq.T, np.ones((1, len(Wp)))], axis=0)
+                lam = np.linalg.solve(T, rhs).T
+            _, wg, _ = lagrange_eval(lam, G[0], kw)
+            Ju = wg @ nrm[0]                                   # [nq, nd]
+            J.append(np.concatenate([Ju, np.zeros_like(Ju)], axis=1))
+            hsum += h[0]
+        Jm = np.concatenate(J, axis=1)                         # [nq, 4nd]
+        out.append(sigma * 0.5 * hsum * np.einsum("q,qa,qb->ab", Wp * ar, Jm, Jm))
+    return np.array(out)
+
+
+def _bary_moment(d, idx):
+    """int lambda_{idx[0]} lambda_{idx[1]} ... / |K|."""
+    e = [idx.count(v) for v in set(idx)]
+    return math.factorial(d) * math.prod(math.factorial(v) for v in e) / math.factorial(d + len(idx))
+
+
+def weak_cell_tensors_closed_form(x, cells, phi, f, ud, cut, gamma, sigma):
+    """P1 x P1 element tensors, vertex dofs; [n, 2nv, 2nv], [n, 2nv]."""
+    d = x.shape[1]
+    nv = d + 1
+    G, vol, h = simplex_geometry(x, cells)
+    p, fv, uv = phi[cells], f[cells], ud[cells]
+    M = np.array([[_bary_moment(d, (i, j)) for j in range(nv)] for i in range(nv)])
+    T3 = np.array([[[_bary_moment(d, (k, i, j)) for j in range(nv)] for i in range(nv)] for k in range(nv)])
+    Q4 = np.array([[[[_bary_moment(d, (k, l, i, j)) for j in range(nv)] for i in range(nv)]
+                    for l in range(nv)] for k in range(nv)])
+    n = len(cells)
+    A = np.zeros((n, 2 * nv, 2 * nv))
+    b = np.zeros((n, 2 * nv))
+    A[:, :nv, :nv] = vol[:, None, None] * np.einsum("nid,njd->nij", G, G)
+    b[:, :nv] = vol[:, None] * (fv @ M)
+    c = np.where(cut, 1.0, 0.0)
+    g2 = c * gamma / h ** 2 * vol
+    A[:, :nv, :nv] += g2[:, None, None] * M[None]
+    up = -(g2 / h)[:, None, None] * np.einsum("nk,kij->nij", p, T3)     # (test v_i, trial p_j)
+    A[:, :nv, nv:] += up
+    A[:, nv:, :nv] += np.transpose(up, (0, 2, 1))
+    A[:, nv:, nv:] += (g2 / h ** 2)[:, None, None] * np.einsum("nk,nl,klij->nij", p, p, Q4)
+    b[:, :nv] += g2[:, None] * (uv @ M)
+    b[:, nv:] += -(g2 / h)[:, None] * np.einsum("nk,nl,kli->ni", uv, p, T3)
+    del sigma  # lap(P1) = 0: the h^2 lap.lap term vanishes (main.py:123-128)
+    return A, b
+
+
+def weak_boundary_tensors_closed_form(x, cells, ents):
+    ents = np.asarray(ents).reshape(-1, 2)
+    d = x.shape[1]
+    nv = d + 1
+    G, _, _ = simplex_geometry(x, cells[ents[:, 0]])
+    nrm, area = facet_geometry(x, cells, ents)
+    Gn = np.einsum("njd,nd->nj", G, nrm)
+    A = np.zeros((len(ents), 2 * nv, 2 * nv))
+    for e, (_, o) in enumerate(ents):
+        for i in range(nv):
+            if i != o:
+                A[e, i, :nv] = -Gn[e] * area[e] / d
+    return A
+
+
+def weak_ghost_tensors_closed_form(x, cells, c2f, f2c, facets, sigma):
+    d = x.shape[1]
+    nv = d + 1
+    facets = np.asarray(facets)
+    E = np.zeros((len(facets), 4 * nv, 4 * nv))
+    if len(facets) == 0:
+        return E
+    J = np.zeros((len(facets), 4 * nv))
+    hsum = np.zeros(len(facets))
+    area = None
+    for side in (0, 1):
+        cc = f2c[facets, side]
+        lf = np.argmax(c2f[cc] == facets[:, None], axis=1)
+        G, _, h = simplex_geometry(x, cells[cc])
+        nrm, ar = facet_geometry(x, cells, np.stack([cc, lf], axis=1))
+        J[:, side * 2 * nv:side * 2 * nv + nv] = np.einsum("njd,nd->nj", G, nrm)
+        hsum += h
+        if side == 0:
+            area = ar
+    return (sigma * 0.5 * hsum * area)[:, None, None] * J[:, :, None] * J[:, None, :]
+
+
+def assemble_weak_dirichlet(x, cells, dofmap, n_scalar_dofs, phi, f, ud, cell_tags, facet_tags, c2f, f2c,
+                            ds100, gamma=1.0, sigma=1.0, method="closed_form", kphi=1, kw=1,
+                            phi_dofmap=None):
+    """(indptr, indices, data, b) of the weak-Dirichlet operator in box mode.  `dofmap` [Nc, nd]: scalar P_kw
+    dofmap; the mixed space numbers u at scalar dof s as 2 s and p as 2 s + 1 (cell-local order
+    [u dofs, p dofs]).  Pattern: all mixed-dof pairs of every active cell and of every ghost-facet macro
+    element (structural zeros kept: dolfinx builds the pattern from the mixed dofmap, not from the blocks that
+    happen to be non-zero [dep-knowledge])."""
+    phi_dofmap = dofmap if phi_dofmap is None else phi_dofmap
+    mixed = np.concatenate([2 * dofmap.astype(np.int64), 2 * dofmap.astype(np.int64) + 1], axis=1)
+    n_rows = 2 * n_scalar_dofs
+    active = np.nonzero((cell_tags == 1) | (cell_tags == 2))[0]
+    ghost = np.nonzero(((facet_tags == 2) | (facet_tags == 3)) & (f2c[:, 1] >= 0))[0]
+    ents = np.asarray(ds100).reshape(-1, 2)
+    indptr, indices = sparsity_pattern(n_rows, mixed, active, ghost, f2c)
+    data = np.zeros(len(indices))
+    b = np.zeros(n_rows)
+    cut = cell_tags[active] == 2
+    if method == "closed_form":
+        assert kphi == 1 and kw == 1
+        A, be = weak_cell_tensors_closed_form(x, cells[active], phi, f, ud, cut, gamma, sigma)
+        Ab = weak_boundary_tensors_closed_form(x, cells, ents)
+        Eg = weak_ghost_tensors_closed_form(x, cells, c2f, f2c, ghost, sigma)
+    else:
+        A, be = weak_cell_tensors_quadrature(x, cells[active], phi[phi_dofmap[active]], f[dofmap[active]],
+                                             ud[dofmap[active]], cut, gamma, sigma, kphi, kw)
+        Ab = weak_boundary_tensors_quadrature(x, cells, ents, kw)
+        Eg = weak_ghost_tensors_quadrature(x, cells, c2f, f2c, ghost, sigma, kw)
+    nm = mixed.shape[1]
+    dm = mixed[active]
+    _scatter(indptr, indices, data, np.repeat(dm, nm, axis=1).ravel(), np.tile(dm, (1, nm)).ravel(), A.ravel())
+    np.add.at(b, dm.ravel(), be.ravel())
+    if len(ents):
+        dmb = mixed[ents[:, 0]]
+        _scatter(indptr, indices, data, np.repeat(dmb, nm, axis=1).ravel(), np.tile(dmb, (1, nm)).ravel(),
+                 Ab.ravel())
+    if len(ghost):
+        mac = np.concatenate([mixed[f2c[ghost, 0]], mixed[f2c[ghost, 1]]], axis=1)
+        _scatter(indptr, indices, data, np.repeat(mac, 2 * nm, axis=1).ravel(),
+                 np.tile(mac, (1, 2 * nm)).ravel(), Eg.ravel())
+    return indptr, indices, data, b

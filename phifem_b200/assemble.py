@@ -126,12 +126,8 @@ class AssemblyPlan:
                 torch.zeros(self.n_rows, dtype=torch.float64, device=dev))
 
 
-def build_plan(mesh, cells_tags, facets_tags, ds=None, method="rows", capacity=None, order="natural",
-               V=None, V_phi=None):
-    """Symbolic phase for `a` and `L` of the strong-Dirichlet demo.  `ds` is what the demo passes as
-    `ds_bdy(100)` (main.py:64): a MeasureRestriction, a flat entity array, or None (no boundary term).
-    `V` / `V_phi`: the demo's `primal_space` / `levelset_space` (main.py:74-75); omitted or both of degree 1
-    => the closed-form P1 kernels, otherwise the quadrature kernels for P1 / P2 (phifem_b200/assemble_pk.py)."""
+def _plan_inputs(mesh, cells_tags, facets_tags, ds):
+    """int8 tag arrays and the [m, 2] entity list of `ds` on the mesh's device."""
     c8 = getattr(cells_tags, "tags8", None)
     c8 = c8 if c8 is not None else cells_tags.values_dev.to(torch.int8)
     f8 = getattr(facets_tags, "tags8", None)
@@ -144,12 +140,22 @@ def build_plan(mesh, cells_tags, facets_tags, ds=None, method="rows", capacity=N
         ents = ds.to(mesh.device)
     else:
         ents = torch.as_tensor(np.asarray(ds, dtype=np.int32), device=mesh.device)
+    return c8.contiguous(), f8.contiguous(), ents
+
+
+def build_plan(mesh, cells_tags, facets_tags, ds=None, method="rows", capacity=None, order="natural",
+               V=None, V_phi=None):
+    """Symbolic phase for `a` and `L` of the strong-Dirichlet demo.  `ds` is what the demo passes as
+    `ds_bdy(100)` (main.py:64): a MeasureRestriction, a flat entity array, or None (no boundary term).
+    `V` / `V_phi`: the demo's `primal_space` / `levelset_space` (main.py:74-75); omitted or both of degree 1
+    => the closed-form P1 kernels, otherwise the quadrature kernels for P1 / P2 (phifem_b200/assemble_pk.py)."""
+    c8, f8, ents = _plan_inputs(mesh, cells_tags, facets_tags, ds)
     V_phi = V if V_phi is None else V_phi
     V = V_phi if V is None else V
     if V is not None and (V.degree != 1 or V_phi.degree != 1 or method == "pk"):
         from .assemble_pk import PkAssemblyPlan
-        return PkAssemblyPlan(mesh, c8.contiguous(), f8.contiguous(), ents, V, V_phi)
-    return AssemblyPlan(mesh, c8.contiguous(), f8.contiguous(), ents, method=method, capacity=capacity,
+        return PkAssemblyPlan(mesh, c8, f8, ents, V, V_phi)
+    return AssemblyPlan(mesh, c8, f8, ents, method=method, capacity=capacity,
                         order=order)
 
 
@@ -222,6 +228,8 @@ def assemble_into(plan, phi, f, sigma, data, b, marks=None):
 def assemble_strong_dirichlet(plan, phi_h, f_h, stab_coef=1.0):
     """A (CSR) and b of reference demo/strong-dirichlet/flower/main.py:104-131."""
     mesh = plan.mesh
+    if getattr(plan, "form", "strong") != "strong":
+        raise ValueError("the plan was built by build_plan_weak_dirichlet; call assemble_weak_dirichlet")
     if getattr(plan, "V", None) is not None:
         from .assemble_pk import assemble_pk_into
         phi = _device_vector(mesh, phi_h, plan.V_phi)
@@ -233,4 +241,29 @@ def assemble_strong_dirichlet(plan, phi_h, f_h, stab_coef=1.0):
     f = _device_vector(mesh, f_h)
     data, b = plan.new_outputs()
     assemble_into(plan, phi, f, stab_coef, data, b)
+    return CSRMatrix(plan.indptr, plan.indices, data, (plan.n_rows, plan.n_rows)), b
+
+
+def build_plan_weak_dirichlet(mesh, cells_tags, facets_tags, ds=None, V=None, V_phi=None):
+    """Symbolic phase for `a` and `L` of the weak-Dirichlet (dual) demo (reference
+    demo/weak-dirichlet/flower/main.py:112-151): mixed space `V x V` (u, p) (`mixed_space`, main.py:76-82),
+    level-set space `V_phi`; defaults: P1 on the mesh.  The mixed vector holds u at even, p at odd positions."""
+    from . import fem
+    from .assemble_pk import PkAssemblyPlan
+    V = fem.functionspace(mesh, 1) if V is None else V
+    V_phi = V if V_phi is None else V_phi
+    c8, f8, ents = _plan_inputs(mesh, cells_tags, facets_tags, ds)
+    return PkAssemblyPlan(mesh, c8, f8, ents, V, V_phi, form="weak")
+
+
+def assemble_weak_dirichlet(plan, phi_h, f_h, u_D=None, pen_coef=1.0, stab_coef=1.0):
+    """A (CSR over the mixed dofs) and b of reference demo/weak-dirichlet/flower/main.py:112-154;
+    `u_D` = Dirichlet data in the primal space (None = 0, as `dirichlet_data` of the demo)."""
+    from .assemble_pk import assemble_weak_into
+    mesh = plan.mesh
+    phi = _device_vector(mesh, phi_h, plan.V_phi)
+    f = _device_vector(mesh, f_h, plan.V)
+    ud = torch.zeros_like(f) if u_D is None else _device_vector(mesh, u_D, plan.V)
+    data, b = plan.new_outputs()
+    assemble_weak_into(plan, phi, f, ud, pen_coef, stab_coef, data, b)
     return CSRMatrix(plan.indptr, plan.indices, data, (plan.n_rows, plan.n_rows)), b

@@ -23,7 +23,13 @@ class PkAssemblyPlan:
     rowsplan = None
     blocked = None
 
-    def __init__(self, mesh, cell_tags8, facet_tags8, entities, V, V_phi):
+    def __init__(self, mesh, cell_tags8, facet_tags8, entities, V, V_phi, form="strong"):
+        """form = "strong": strong-Dirichlet operator on V; form = "weak": weak-Dirichlet (dual) operator on
+        the mixed space V x V, u at scalar dof s numbered 2 s, p numbered 2 s + 1 (cell-local order
+        [u dofs, p dofs])."""
+        if form not in ("strong", "weak"):
+            raise ValueError("form must be 'strong' or 'weak'")
+        self.form = form
         if mesh.cell_type not in ("triangle", "tetrahedron"):
             raise NotImplementedError("P_k assembly supports triangles and tetrahedra")
         for sp in (V, V_phi):
@@ -34,10 +40,16 @@ class PkAssemblyPlan:
         dev = mesh.device
         self.mesh, self.V, self.V_phi = mesh, V, V_phi
         self.cell_tags8 = cell_tags8
-        self.n_rows = n = int(V.num_dofs)
         self.dofmap = V.dofmap_dev
         self.dofmap_phi = V_phi.dofmap_dev
-        nd = self.nd = int(self.dofmap.shape[1])
+        self.nd = int(self.dofmap.shape[1])
+        if form == "weak":
+            self.pattern_dofmap = torch.cat([2 * self.dofmap, 2 * self.dofmap + 1], dim=1).contiguous()
+            self.n_rows = n = 2 * int(V.num_dofs)
+        else:
+            self.pattern_dofmap = self.dofmap
+            self.n_rows = n = int(V.num_dofs)
+        nd = int(self.pattern_dofmap.shape[1])       # dofs per cell of the assembled (possibly mixed) space
         self.active = torch.nonzero((cell_tags8 == 1) | (cell_tags8 == 2)).reshape(-1).to(torch.int32)
         interior = mesh.f2c[:, 1] >= 0
         self.ghost = torch.nonzero(((facet_tags8 == 2) | (facet_tags8 == 3)) & interior) \
@@ -47,9 +59,10 @@ class PkAssemblyPlan:
         def pair_keys(dm):  # [m, k] dofs -> [m, k*k] keys row*n+col, row-major (row = test)
             return (dm[:, :, None] * n + dm[:, None, :]).reshape(dm.shape[0], dm.shape[1] * dm.shape[1])
 
-        keys_c = pair_keys(self.dofmap[self.active.long()].long())
+        pdm = self.pattern_dofmap
+        keys_c = pair_keys(pdm[self.active.long()].long())
         g = self.ghost.long()
-        mac = torch.cat([self.dofmap[mesh.f2c[g, 0].long()], self.dofmap[mesh.f2c[g, 1].long()]], dim=1).long()
+        mac = torch.cat([pdm[mesh.f2c[g, 0].long()], pdm[mesh.f2c[g, 1].long()]], dim=1).long()
         keys_g = pair_keys(mac)
         n_c = keys_c.numel()
         uniq, inv = torch.unique(torch.cat([keys_c.reshape(-1), keys_g.reshape(-1)]), sorted=True,
@@ -59,7 +72,7 @@ class PkAssemblyPlan:
         self.slots_cells = inv[:n_c].reshape(-1, nd * nd).t().contiguous()
         self.slots_ghost = inv[n_c:].reshape(-1, 4 * nd * nd).t().contiguous()
         del inv
-        keys_b = pair_keys(self.dofmap[self.entities[:, 0].long()].long())
+        keys_b = pair_keys(pdm[self.entities[:, 0].long()].long())
         self.slots_boundary = torch.searchsorted(uniq, keys_b.reshape(-1)).reshape(-1, nd * nd) \
             .to(torch.int32).t().contiguous()
         rows = uniq // n
@@ -72,7 +85,8 @@ class PkAssemblyPlan:
 
         # quadrature tables and C structs (kept alive with the plan)
         d = mesh.gdim
-        (cl, cw), (fl, fw) = quadrature.rules_for(d, V.degree, V_phi.degree)
+        rules = quadrature.rules_for_weak if form == "weak" else quadrature.rules_for
+        (cl, cw), (fl, fw) = rules(d, V.degree, V_phi.degree)
         f64 = dict(dtype=torch.float64, device=dev)
         self._q = [torch.as_tensor(a, **f64).contiguous() for a in (cl, cw, fl, fw)]
         self.n_cell_points, self.n_facet_points = len(cw), len(fw)
@@ -121,4 +135,29 @@ def assemble_pk_into(plan, phi, f, sigma, data, b, marks=None):
         *head, _lib.ptr(phi), _lib.ptr(plan.ghost), plan.ghost.numel(), _lib.ptr(plan.slots_ghost),
         float(sigma), _lib.ptr(data), st))
     marks()
+    return data, b
+
+
+def assemble_weak_into(plan, phi, f, u_d, gamma, sigma, data, b):
+    """Numeric phase of the weak-Dirichlet operator (plan.form == "weak") on the current stream."""
+    mesh = plan.mesh
+    _lib.require_cuda(mesh)
+    if plan.form != "weak":
+        raise ValueError("the plan was built for the strong-Dirichlet operator")
+    lib = _lib.load()
+    cm = _lib.c_mesh(mesh)
+    cw, cp, cq = plan.c_structs()
+    st = _lib.stream()
+    data.zero_()
+    b.zero_()
+    _lib.check(lib.phifem_assemble_weak_cells_pk(
+        cm, ctypes.byref(cw), ctypes.byref(cp), ctypes.byref(cq), _lib.ptr(phi), _lib.ptr(f), _lib.ptr(u_d),
+        _lib.ptr(plan.cell_tags8), _lib.ptr(plan.active), plan.active.numel(), _lib.ptr(plan.slots_cells),
+        _lib.ptr(plan.pattern_dofmap), float(gamma), float(sigma), _lib.ptr(data), _lib.ptr(b), st))
+    _lib.check(lib.phifem_assemble_weak_boundary_pk(
+        cm, ctypes.byref(cw), ctypes.byref(cq), _lib.ptr(plan.entities), plan.entities.shape[0],
+        _lib.ptr(plan.slots_boundary), _lib.ptr(data), st))
+    _lib.check(lib.phifem_assemble_weak_ghost_pk(
+        cm, ctypes.byref(cw), ctypes.byref(cq), _lib.ptr(plan.ghost), plan.ghost.numel(),
+        _lib.ptr(plan.slots_ghost), float(sigma), _lib.ptr(data), st))
     return data, b

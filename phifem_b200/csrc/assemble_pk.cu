@@ -485,6 +485,201 @@ __global__ void __launch_bounds__(kBlockPk) k_assemble_ghost_pk(
   for (int bb = 0; bb < NM; ++bb) atomicAdd(data + __ldg(slots + (int64_t)(a * NM + bb) * n_facets + e), E[bb]);
 }
 
+// ==== weak-Dirichlet (dual) phi-FEM operator on the mixed space (u, p) in P_KW x P_KW ========================
+// reference demo/weak-dirichlet/flower/main.py:112-151 (BASELINE.json configs[0]):
+//   a = int_{dx(1,2)} grad u.grad v - int_ds (grad u.n) v + gamma h^-2 int_{dx(2)} (u - h^-1 phi p)(v - h^-1 phi q)
+//       + sigma h^2 int_{dx(2)} lap u lap v + sigma int_{dS(2,3)} avg(h) [grad u.n][grad v.n]
+//   L = int_{dx(1,2)} f v + gamma h^-2 int_{dx(2)} u_D (v - h^-1 phi q) - sigma h^2 int_{dx(2)} f lap v
+// Cell-local mixed dofs: [u dofs, p dofs] (NM = 2 ND); one thread per (entity, mixed test dof).
+
+template <int D, int KW, int KP>
+__global__ void __launch_bounds__(kBlockPk) k_assemble_cells_weak_pk(
+    phifem_mesh m, phifem_pk_space sw, phifem_pk_space sp, const double* __restrict__ qlam_g,
+    const double* __restrict__ qw_g, int nq, const double* __restrict__ phi, const double* __restrict__ f,
+    const double* __restrict__ ud, const int8_t* __restrict__ ctags, const int32_t* __restrict__ active,
+    int64_t n_active, const int32_t* __restrict__ slots, const int32_t* __restrict__ mixed_dofmap,
+    double gamma, double sigma, double* __restrict__ data, double* __restrict__ b) {
+  constexpr int NV = D + 1, ND = Space<D, KW>::ND, NDP = Space<D, KP>::ND, NM = 2 * ND;
+  __shared__ double qlam[kMaxQuadPoints * NV], qw[kMaxQuadPoints];
+  for (int i = threadIdx.x; i < nq * NV; i += blockDim.x) qlam[i] = qlam_g[i];
+  for (int i = threadIdx.x; i < nq; i += blockDim.x) qw[i] = qw_g[i];
+  __syncthreads();
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_active * NM) return;
+  const int64_t e = t / NM;
+  const int a = (int)(t - e * NM);
+  const bool test_q = a >= ND;  // mixed test function (0, psi_i) instead of (psi_i, 0)
+  const int i = test_q ? a - ND : a;
+  const int64_t c = __ldg(active + e);
+  const bool is_cut = ctags[c] == 2;
+  if (test_q && !is_cut) return;  // rows of q only carry the penalty term of cut cells
+  Geometry<D> g;
+  load_geometry<D>(m, c, g);
+  double pc[NDP], fc[ND], uc[ND];
+  load_dofs<D, KP>(m, sp, phi, c, pc);
+  load_dofs<D, KW>(m, sw, f, c, fc);
+  load_dofs<D, KW>(m, sw, ud, c, uc);
+  double wl[ND];
+  laplacians<D, KW>(g.G, wl);
+  const double wli = pick<ND>(wl, i);
+  const double h = sqrt(g.h2);
+  const double pen = is_cut ? gamma / g.h2 : 0.0, stab = is_cut ? sigma * g.h2 : 0.0, rh = 1.0 / h;
+  double A[NM], bv = 0.0;
+#pragma unroll
+  for (int j = 0; j < NM; ++j) A[j] = 0.0;
+  for (int q = 0; q < nq; ++q) {
+    double lam[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) lam[k] = qlam[q * NV + k];
+    const double w = qw[q] * g.vol;
+    double wv[ND], wg[ND][D];
+    tabulate<D, KW>(lam, g.G, wv, wg);
+    double ph, gph[D];
+    eval_phi<D, KW, KP>(lam, g.G, wv, wg, pc, ph, gph);
+    double fq = 0.0, uq = 0.0;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+      fq += fc[k] * wv[k];
+      uq += uc[k] * wv[k];
+    }
+    const double psi = pick<ND>(wv, i);
+    if (!test_q) {
+      double gi[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        double v = wg[0][d];
+#pragma unroll
+        for (int k = 1; k < ND; ++k)
+          if (k == i) v = wg[k][d];
+        gi[d] = v;
+      }
+      bv += w * (fq * psi - stab * fq * wli);
+#pragma unroll
+      for (int j = 0; j < ND; ++j) A[j] += w * (dotd<D>(wg[j], gi) + stab * wl[j] * wli);
+    }
+    if (is_cut) {
+      const double pr = -ph * rh;                   // p-part of the combination  u - h^-1 phi p
+      const double T = (test_q ? pr * psi : psi) * w * pen;
+      bv += uq * T;
+#pragma unroll
+      for (int j = 0; j < ND; ++j) {
+        A[j] += wv[j] * T;
+        A[ND + j] += pr * wv[j] * T;
+      }
+    }
+  }
+  atomicAdd(b + __ldg(mixed_dofmap + c * NM + a), bv);
+#pragma unroll
+  for (int j = 0; j < NM; ++j)
+    if (j < ND || is_cut) atomicAdd(data + __ldg(slots + (int64_t)(a * NM + j) * n_active + e), A[j]);
+}
+
+template <int D, int KW>
+__global__ void __launch_bounds__(kBlockPk) k_assemble_boundary_weak_pk(
+    phifem_mesh m, const double* __restrict__ qlam_g, const double* __restrict__ qw_g, int nq,
+    const int32_t* __restrict__ entities, int64_t n_entities, const int32_t* __restrict__ slots,
+    double* __restrict__ data) {
+  constexpr int NV = D + 1, ND = Space<D, KW>::ND, NM = 2 * ND;
+  __shared__ double qlam[kMaxQuadPoints * D], qw[kMaxQuadPoints];
+  for (int i = threadIdx.x; i < nq * D; i += blockDim.x) qlam[i] = qlam_g[i];
+  for (int i = threadIdx.x; i < nq; i += blockDim.x) qw[i] = qw_g[i];
+  __syncthreads();
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_entities * ND) return;
+  const int64_t e = t / ND;
+  const int i = (int)(t - e * ND);
+  const int64_t c = __ldg(entities + 2 * e);
+  const int o = __ldg(entities + 2 * e + 1);
+  Geometry<D> g;
+  load_geometry<D>(m, c, g);
+  double n[D], area;
+  facet_normal<D>(g, o, n, area);
+  double A[ND];
+#pragma unroll
+  for (int j = 0; j < ND; ++j) A[j] = 0.0;
+  for (int q = 0; q < nq; ++q) {
+    double lam[NV];
+    facet_to_cell<D>(qlam + q * D, o, lam);
+    double wv[ND], wg[ND][D];
+    tabulate<D, KW>(lam, g.G, wv, wg);
+    const double vi = -qw[q] * area * pick<ND>(wv, i);
+#pragma unroll
+    for (int j = 0; j < ND; ++j) A[j] += vi * dotd<D>(wg[j], n);
+  }
+#pragma unroll
+  for (int j = 0; j < ND; ++j) atomicAdd(data + __ldg(slots + (int64_t)(i * NM + j) * n_entities + e), A[j]);
+}
+
+template <int D, int KW>
+__global__ void __launch_bounds__(kBlockPk) k_assemble_ghost_weak_pk(
+    phifem_mesh m, const double* __restrict__ qlam_g, const double* __restrict__ qw_g, int nq,
+    const int32_t* __restrict__ facets, int64_t n_facets, const int32_t* __restrict__ slots, double sigma,
+    double* __restrict__ data) {
+  constexpr int NV = D + 1, ND = Space<D, KW>::ND, NM = 2 * ND, NU = 2 * ND;  // NU: u dofs of both sides
+  __shared__ double qlam[kMaxQuadPoints * D], qw[kMaxQuadPoints];
+  for (int i = threadIdx.x; i < nq * D; i += blockDim.x) qlam[i] = qlam_g[i];
+  for (int i = threadIdx.x; i < nq; i += blockDim.x) qw[i] = qw_g[i];
+  __syncthreads();
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_facets * NU) return;
+  const int64_t e = t / NU;
+  const int a = (int)(t - e * NU);  // u dof a of side a / ND
+  const int32_t fct = __ldg(facets + e);
+  const int2 cc = __ldg(reinterpret_cast<const int2*>(m.f2c) + fct);
+  Geometry<D> gp, gm;
+  load_geometry<D>(m, cc.x, gp);
+  load_geometry<D>(m, cc.y, gm);
+  int op = 0, om = 0;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    if (__ldg(m.c2f + (int64_t)cc.x * NV + k) == fct) op = k;
+    if (__ldg(m.c2f + (int64_t)cc.y * NV + k) == fct) om = k;
+  }
+  double np_[D], nm_[D], area, area_m;
+  facet_normal<D>(gp, op, np_, area);
+  facet_normal<D>(gm, om, nm_, area_m);
+  const double coef = sigma * 0.5 * (sqrt(gp.h2) + sqrt(gm.h2)) * area;
+  double E[NU];
+#pragma unroll
+  for (int bb = 0; bb < NU; ++bb) E[bb] = 0.0;
+  for (int q = 0; q < nq; ++q) {
+    double lam[NV], J[NU];
+    facet_to_cell<D>(qlam + q * D, op, lam);
+    {
+      double wv[ND], wg[ND][D];
+      tabulate<D, KW>(lam, gp.G, wv, wg);
+#pragma unroll
+      for (int j = 0; j < ND; ++j) J[j] = dotd<D>(wg[j], np_);
+    }
+    double xq[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) s += lam[k] * gp.X[k][d];
+      xq[d] = s - gm.X[0][d];
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) lam[k] = (k == 0 ? 1.0 : 0.0) + dotd<D>(gm.G[k], xq);
+    {
+      double wv[ND], wg[ND][D];
+      tabulate<D, KW>(lam, gm.G, wv, wg);
+#pragma unroll
+      for (int j = 0; j < ND; ++j) J[ND + j] = dotd<D>(wg[j], nm_);
+    }
+    const double wa = qw[q] * coef * pick<NU>(J, a);
+#pragma unroll
+    for (int bb = 0; bb < NU; ++bb) E[bb] += wa * J[bb];
+  }
+  // macro mixed index of u dof j of side s: s * NM + j
+  const int ma = (a / ND) * NM + (a % ND);
+#pragma unroll
+  for (int bb = 0; bb < NU; ++bb) {
+    const int mb = (bb / ND) * NM + (bb % ND);
+    atomicAdd(data + __ldg(slots + (int64_t)(ma * 2 * NM + mb) * n_facets + e), E[bb]);
+  }
+}
+
 int check_pk(const phifem_mesh* m, const phifem_pk_space* sw, const phifem_pk_space* sp,
              const double* points, const double* weights, int nq) {
   PHIFEM_CHECK_ARG(m != nullptr && m->x && m->cells, "mesh is null");
@@ -590,6 +785,74 @@ extern "C" int phifem_assemble_ghost_pk(const phifem_mesh* mesh, const phifem_pk
     k_assemble_ghost_pk<D, KW, KP><<<(unsigned)((threads + kBlockPk - 1) / kBlockPk), kBlockPk, 0, st>>>(
         *mesh, *space_w, *space_phi, quad->facet_points, quad->facet_weights, quad->n_facet_points, phi,
         facets, n_facets, slots, sigma, data);
+  });
+  PHIFEM_CHECK_LAUNCH();
+  return PHIFEM_OK;
+}
+
+// ---- weak-Dirichlet operator (demo/weak-dirichlet/flower/main.py:112-151) ---------------------------------------
+extern "C" int phifem_assemble_weak_cells_pk(const phifem_mesh* mesh, const phifem_pk_space* space_w,
+                                             const phifem_pk_space* space_phi, const phifem_quadrature* quad,
+                                             const double* phi, const double* f, const double* u_d,
+                                             const int8_t* cell_tags8, const int32_t* active, int64_t n_active,
+                                             const int32_t* slots, const int32_t* mixed_dofmap, double gamma,
+                                             double sigma, double* data, double* b, void* stream) {
+  PHIFEM_CHECK_ARG(quad != nullptr, "quadrature is null");
+  if (int rc = check_pk(mesh, space_w, space_phi, quad->cell_points, quad->cell_weights, quad->n_cell_points))
+    return rc;
+  PHIFEM_CHECK_ARG(phi && f && u_d && cell_tags8 && data && b && mixed_dofmap, "null pointer");
+  PHIFEM_CHECK_ARG(n_active == 0 || (active && slots), "null active / slots");
+  if (n_active == 0) return PHIFEM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  dispatch(mesh->cell_type, space_w->degree, space_phi->degree, [&](auto d, auto kw, auto kp) {
+    constexpr int D = decltype(d)::value, KW = decltype(kw)::value, KP = decltype(kp)::value;
+    const int64_t threads = n_active * 2 * Space<D, KW>::ND;
+    k_assemble_cells_weak_pk<D, KW, KP><<<(unsigned)((threads + kBlockPk - 1) / kBlockPk), kBlockPk, 0, st>>>(
+        *mesh, *space_w, *space_phi, quad->cell_points, quad->cell_weights, quad->n_cell_points, phi, f, u_d,
+        cell_tags8, active, n_active, slots, mixed_dofmap, gamma, sigma, data, b);
+  });
+  PHIFEM_CHECK_LAUNCH();
+  return PHIFEM_OK;
+}
+
+extern "C" int phifem_assemble_weak_boundary_pk(const phifem_mesh* mesh, const phifem_pk_space* space_w,
+                                                const phifem_quadrature* quad, const int32_t* entities,
+                                                int64_t n_entities, const int32_t* slots, double* data,
+                                                void* stream) {
+  PHIFEM_CHECK_ARG(quad != nullptr, "quadrature is null");
+  if (int rc = check_pk(mesh, space_w, space_w, quad->facet_points, quad->facet_weights, quad->n_facet_points))
+    return rc;
+  PHIFEM_CHECK_ARG(data != nullptr, "null pointer");
+  PHIFEM_CHECK_ARG(n_entities == 0 || (entities && slots), "null entities / slots");
+  if (n_entities == 0) return PHIFEM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  dispatch(mesh->cell_type, space_w->degree, 1, [&](auto d, auto kw, auto) {
+    constexpr int D = decltype(d)::value, KW = decltype(kw)::value;
+    const int64_t threads = n_entities * Space<D, KW>::ND;
+    k_assemble_boundary_weak_pk<D, KW><<<(unsigned)((threads + kBlockPk - 1) / kBlockPk), kBlockPk, 0, st>>>(
+        *mesh, quad->facet_points, quad->facet_weights, quad->n_facet_points, entities, n_entities, slots, data);
+  });
+  PHIFEM_CHECK_LAUNCH();
+  return PHIFEM_OK;
+}
+
+extern "C" int phifem_assemble_weak_ghost_pk(const phifem_mesh* mesh, const phifem_pk_space* space_w,
+                                             const phifem_quadrature* quad, const int32_t* facets,
+                                             int64_t n_facets, const int32_t* slots, double sigma, double* data,
+                                             void* stream) {
+  PHIFEM_CHECK_ARG(quad != nullptr, "quadrature is null");
+  if (int rc = check_pk(mesh, space_w, space_w, quad->facet_points, quad->facet_weights, quad->n_facet_points))
+    return rc;
+  PHIFEM_CHECK_ARG(data && mesh->c2f && mesh->f2c, "null pointer");
+  PHIFEM_CHECK_ARG(n_facets == 0 || (facets && slots), "null facets / slots");
+  if (n_facets == 0) return PHIFEM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  dispatch(mesh->cell_type, space_w->degree, 1, [&](auto d, auto kw, auto) {
+    constexpr int D = decltype(d)::value, KW = decltype(kw)::value;
+    const int64_t threads = n_facets * 2 * Space<D, KW>::ND;
+    k_assemble_ghost_weak_pk<D, KW><<<(unsigned)((threads + kBlockPk - 1) / kBlockPk), kBlockPk, 0, st>>>(
+        *mesh, quad->facet_points, quad->facet_weights, quad->n_facet_points, facets, n_facets, slots, sigma,
+        data);
   });
   PHIFEM_CHECK_LAUNCH();
   return PHIFEM_OK;

@@ -195,3 +195,10 @@ def rules_for(d, kw, kphi):
     cell_degree = max(2 * (kw + kphi - 1), 2 * kw + kphi)
     facet_degree = 2 * (kw + kphi) - 1
     return simplex_rule(d, cell_degree), simplex_rule(d - 1, facet_degree)
+
+
+def rules_for_weak(d, kw, kphi):
+    """Cell and facet rules of the weak-Dirichlet forms (demo/weak-dirichlet/flower/main.py:112-151): the
+    penalty block phi^2 p q needs degree 2 (kw + kphi) on cells; the facet terms (grad u.n) v and the gradient
+    jumps need 2 kw - 1."""
+    return simplex_rule(d, 2 * (kw + kphi)), simplex_rule(d - 1, max(1, 2 * kw - 1))
