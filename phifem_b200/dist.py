@@ -59,6 +59,20 @@ def _exchange(tensors_out, dtype, device, group=None):
     return recv
 
 
+def entities_host(mesh, cell_tags8, facet_tags8):
+    """CPU stand-in of the ds(100) entity search for the gloo tests (same ordering rules, torch ops)."""
+    f = torch.nonzero(facet_tags8 == 4).reshape(-1)
+    pairs = []
+    for col in (1, 0):                    # reversed link order (mesh_scripts.py:195-214)
+        c = mesh.f2c[f, col].long()
+        ok = c >= 0
+        ok &= ((cell_tags8[c.clamp(min=0)] == 1) | (cell_tags8[c.clamp(min=0)] == 2))
+        cc, ff = c[ok], f[ok]
+        lf = (mesh.c2f[cc].long() == ff[:, None]).long().argmax(dim=1)
+        pairs.append(torch.stack([cc, lf], dim=1))
+    return torch.cat(pairs).to(torch.int32)
+
+
 class SlabProblem:
     """Synthetic weak-scaling problem: the box [0, world] x [0,1]^2 of world*n x n x n cubes (6 Kuhn
     tetrahedra each), rank r owning the cubes of [r, r+1].  Level set: one sphere (radius 0.45) per
@@ -252,18 +266,7 @@ class SlabProblem:
         return p.owned_indptr, p.owned_cols, self.data[a:b], self.b_local[p.owned_lo:p.owned_hi]
 
     def _entities_host(self, cell_tags8, facet_tags8):
-        """CPU stand-in of the entity search for the gloo tests (same ordering rules, torch ops)."""
-        mesh = self.mesh
-        f = torch.nonzero(facet_tags8 == 4).reshape(-1)
-        pairs = []
-        for col in (1, 0):                    # reversed link order (mesh_scripts.py:195-214)
-            c = mesh.f2c[f, col].long()
-            ok = c >= 0
-            ok &= ((cell_tags8[c.clamp(min=0)] == 1) | (cell_tags8[c.clamp(min=0)] == 2))
-            cc, ff = c[ok], f[ok]
-            lf = (mesh.c2f[cc].long() == ff[:, None]).long().argmax(dim=1)
-            pairs.append(torch.stack([cc, lf], dim=1))
-        return torch.cat(pairs).to(torch.int32)
+        return entities_host(self.mesh, cell_tags8, facet_tags8)
 
     # ---- numeric phase -----------------------------------------------------------------------------
     def assemble(self, sigma=1.0, marks=None, local_kernels=None):

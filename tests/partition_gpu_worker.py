@@ -1,0 +1,69 @@
+"""torchrun worker of tests/test_gpu_dist.py::test_partitioned_gpus_*: N ranks shard an unstructured mesh along
+the Morton curve (phifem_b200/partition.py), classify and assemble their rows with the CUDA kernels; rank 0
+checks that the merged rows are BITWISE identical to the single-GPU product path."""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from phifem_b200 import assemble, fem, mesh_scripts, partition, synthetic  # noqa: E402
+
+
+def main():
+    kind, n = sys.argv[1], int(sys.argv[2])
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", device_id=dev)
+    gmesh = synthetic.rectangle_mesh(n, device=dev) if kind == "tri" else synthetic.box_mesh(n, device=dev)
+    gmesh = synthetic.unstructured_variant(gmesh, jitter=0.2, seed=11)
+    center = (0.013, -0.021) if kind == "tri" else synthetic.SPHERE_CENTER
+    phi = synthetic.sphere_levelset(gmesh.x, center=center, radius=0.61 if kind == "tri" else 0.37)
+    f = torch.from_numpy(np.random.default_rng(99).uniform(-1, 1, gmesh.num_vertices)).to(dev)
+    prob = partition.PartitionedProblem(gmesh, phi, f, rank, world)
+    dls = mesh_scripts._DeviceLevelset(prob.mesh, fem.Function(fem.functionspace_p1_device(prob.mesh), prob.phi), 1)
+    ws = prob.classify(dls, mesh_scripts.TagWorkspace(prob.mesh))
+    prob.build_plan(ws.cell_tags8, ws.facet_tags8)
+    prob.assemble(1.0)
+    torch.cuda.synchronize()
+    rows, indptr, cols, data, b = prob.owned_csr()
+    mine = dict(rows=rows.cpu().numpy(), indptr=indptr.cpu().numpy(), cols=cols.cpu().numpy(),
+                data=data.cpu().numpy(), b=b.cpu().numpy(),
+                owned_cells=prob.global_cell[prob.cell_owned].cpu().numpy(),
+                tags=ws.cell_tags[prob.cell_owned].cpu().numpy(), n_local=prob.mesh.num_cells)
+    parts = [None] * world
+    dist.gather_object(mine, parts if rank == 0 else None, dst=0)
+    if rank == 0:
+        fn = fem.Function(fem.functionspace_p1_device(gmesh), phi)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            ct, ft, _, ds, _ = mesh_scripts.compute_tags_measures(gmesh, fn, 1, box_mode=True)
+        A, bb = assemble.assemble_strong_dirichlet(assemble.build_plan(gmesh, ct, ft, ds(100)), phi, f)
+        ip, ix, dd, bb = (A.indptr.cpu().numpy(), A.indices.cpu().numpy(), A.data.cpu().numpy(), bb.cpu().numpy())
+        tags = ct.values_dev.cpu().numpy()
+        seen = np.zeros(gmesh.num_vertices, dtype=int)
+        for p in parts:
+            seen[p["rows"]] += 1
+            assert np.array_equal(p["tags"], tags[p["owned_cells"]])
+            cnt = np.diff(p["indptr"])
+            assert np.array_equal(cnt, ip[p["rows"] + 1] - ip[p["rows"]])
+            slots = np.repeat(ip[p["rows"]] - p["indptr"][:-1], cnt) + np.arange(len(p["cols"]))
+            assert np.array_equal(p["cols"], ix[slots])
+            assert np.array_equal(p["data"], dd[slots])          # same contributions, same order: bitwise
+            assert np.array_equal(p["b"], bb[p["rows"]])
+            assert p["n_local"] < gmesh.num_cells
+        assert np.all(seen == 1)
+        print("PARTITION-OK world=%d kind=%s cells=%d local=%s"
+              % (world, kind, gmesh.num_cells, [p["n_local"] for p in parts]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
