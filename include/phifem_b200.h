@@ -218,15 +218,19 @@ typedef struct phifem_rows_plan {
    * cell tagged 1/2 containing the row's vertex; bit 24: the cell is cut (tag 2).  This pass WRITES the
    * rows (data and b); rows listed here without records are written as zeros. */
   phifem_row_list cells;
-  /* rows touched by interior facets tagged 2/3; two words per record: word 0 byte j = position of other
-   * vertex j of the facet macro element; word 1 = role:
-   *   0: row is a facet vertex, others = [other facet vertices, opposite vertex of cell A, of cell B];
-   *   1: row is the opposite vertex of cell A, others = [facet vertices, opposite vertex of cell B].
-   * This pass ADDS to the rows written by the cell pass. */
+  /* rows touched by interior facets tagged 2/3.  The macro element of ghost facet g is ghost_macro[g] =
+   * [facet vertices as ordered in cell A = f2c[f][0], opposite vertex of cell A, opposite vertex of cell B].
+   * Two words per record: word 0 byte j = position of the j-th OTHER macro vertex (macro order, the row's own
+   * index skipped); word 1 = g | (macro index of the row's vertex << 28).  A facet-once kernel first writes
+   * 8 doubles per facet into ghost_work (jump coefficients, see csrc/assemble_rows.cu); this pass then
+   * ADDS each row's entries to the rows written by the cell pass. */
   phifem_row_list ghost;
   /* rows on one-sided facets of ds(100); one word per record: byte 0 = position of the cell vertex opposite
    * the facet, bytes 1..d-1 = the other facet vertices.  ADDS as well. */
   phifem_row_list boundary;
+  int64_t n_ghost_facets;      /* < 2^28 */
+  const int32_t* ghost_macro;  /* [n_ghost_facets, d + 2] vertex ids */
+  double* ghost_work;          /* [n_ghost_facets, 8] scratch (32-byte aligned), rewritten by every call */
 } phifem_rows_plan;
 
 /* Same operator as phifem_assemble_{cells,boundary,ghost}_p1, three launches on `stream` (cell pass, then

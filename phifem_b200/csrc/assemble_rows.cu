@@ -220,19 +220,44 @@ __device__ __forceinline__ void boundary_row(const double (&X)[D + 1][D], const 
   }
 }
 
-// One row of sigma avg(h_T) int_F jump.jump (main.py:113-118) over the facet macro element
-// M = [facet vertices 0..D-1, opposite vertex of cell A, opposite vertex of cell B]; `arow` (0 or D) is
-// the macro index of the row's vertex.  K[m] = entry (row, M[m]).
-//
-// With N = the facet's cofactor vector (normal scaled by (D-1)! |F|, the same for both cells) the normal
-// derivative of lambda_a seen from cell s is  Gn_a = -(R_a . N) / (|det_s| |N|),  and the jump of
-// grad(phi w_m).n at facet vertex k is  delta_mk [m on F] gsum + c_m phi_k  with gsum = sum_s grad(phi).n_s,
-// c_m = sum_s Gn_m.  The facet mass matrix |F| (1 + delta_kl) / (D (D+1)) then gives the entries in closed
-// form from c, gsum, sum phi_k and sum phi_k^2.
+// Ghost penalty sigma avg(h_T) int_F jump.jump (main.py:113-118) over the facet macro element
+// M = [facet vertices 0..D-1 (as ordered in cell A = f2c[f][0]), opposite vertex of cell A, opposite vertex of
+// cell B].  Two phases, both without atomics:
+//   facet-once (k_ghost_facets_p1): with N = the facet's cofactor vector (normal scaled by (D-1)! |F|, the same
+//     for both cells) the normal derivative of lambda_a seen from cell s is Gn_a = -(R_a . N) / (|det_s| |N|);
+//     the jump of grad(phi w_m).n at a point of F is  lambda_m [m on F] gsum + phi c_m  with
+//     gsum = sum_s grad(phi).n_s and c_m = sum_s Gn_m (sum_m c_m = 0: the barycentric gradients of a cell sum
+//     to zero).  With s = sqrt(|sigma| avg(h) |F| / (D (D+1))) the thread stores s c_0..s c_D, s gsum and phi at
+//     the facet vertices: 8 doubles = 64 bytes per facet (two 256-bit loads for a row), 93 MB for the 1.45 M
+//     ghost facets of config E;
+//   per row (k_assemble_rows_p1<D, kGhost>): the facet mass matrix |F| (1 + delta_kl) / (D (D+1)) gives
+//     entry (a, m) = sign(sigma) [ (ga + c_a Pf)(gm + c_m Pf) + c_a c_m Sf2 + ga c_m phi_a + c_a gm phi_m
+//                                  + ga gm delta_am ],  ga = s gsum if a lies on F else 0, Pf = sum phi_k,
+//     Sf2 = sum phi_k^2 over the facet vertices: ~50 fp64 operations per row instead of ~300.
+// The pass is bound by the L1 request rate of the per-lane record gathers (ncu: 6 x 128-bit loads per record
+// cost 0.20 ms, 3 x 256-bit 0.16 ms), hence the compact record.
+template <int D> constexpr int kGhostWork = 8;  // D + 1 jump coefficients, gsum, D facet values (+ pad in 2D)
+
+// sm_100 256-bit read-only load (LDG.E.256): one L1 request per 32-byte sector instead of two
+__device__ __forceinline__ void ldg256(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
 template <int D>
-__device__ __forceinline__ void ghost_row(const double (&M)[D + 2][D], const double (&pm)[D + 2],
-                                          int arow, double sigma, double (&K)[D + 2]) {
-  constexpr int NV = D + 1, NG = D + 2;
+__global__ void __launch_bounds__(kRowsBlock) k_ghost_facets_p1(
+    const double* __restrict__ x, const double* __restrict__ phi, double sigma,
+    const int32_t* __restrict__ macro, int64_t n_facets, double* __restrict__ work) {
+  constexpr int NV = D + 1, NG = D + 2, W = kGhostWork<D>;
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_facets) return;
+  double M[NG][D], pm[NG];
+#pragma unroll
+  for (int m = 0; m < NG; ++m) {
+    const int v = __ldg(macro + g * NG + m);
+#pragma unroll
+    for (int d = 0; d < D; ++d) M[m][d] = __ldg(x + (int64_t)v * D + d);
+    pm[m] = __ldg(phi + v);
+  }
   double c[NG], N[D], nn = 0.0, rn = 0.0, gsum = 0.0, hsum = 0.0;
 #pragma unroll
   for (int m = 0; m < NG; ++m) c[m] = 0.0;
@@ -264,25 +289,50 @@ __device__ __forceinline__ void ghost_row(const double (&M)[D + 2][D], const dou
     hsum += sqrt(diameter2<D>(X));
   }
   const double area = nn * rn * (D == 2 ? 1.0 : 0.5);  // |N| / (D-1)!
-  const double coef = sigma * 0.5 * hsum * area * (1.0 / (D * (D + 1)));
-  double Pf = pm[0], Sf2 = pm[0] * pm[0];
+  const double sc = sqrt(fabs(sigma) * 0.5 * hsum * area * (1.0 / (D * (D + 1))));
+  double* w = work + g * W;
+#pragma unroll
+  for (int m = 0; m <= D; ++m) w[m] = sc * c[m];
+  w[D + 1] = sc * gsum;
+#pragma unroll
+  for (int k = 0; k < D; ++k) w[D + 2 + k] = pm[k];
+  if (D == 2) w[6] = w[7] = 0.0;
+}
+
+// Row a of the macro tensor from the facet's work record; pr = phi at the row's own vertex, sg = sign(sigma).
+template <int D>
+__device__ __forceinline__ void ghost_row(const double (&wk)[kGhostWork<D>], int a, double pr, double sg,
+                                          double (&K)[D + 2]) {
+  constexpr int NG = D + 2;
+  double c[NG], csum = 0.0;
+#pragma unroll
+  for (int m = 0; m <= D; ++m) {
+    c[m] = wk[m];
+    csum += wk[m];
+  }
+  c[D + 1] = -csum;
+  const double gsum = wk[D + 1];
+  double Pf = wk[D + 2], Sf2 = wk[D + 2] * wk[D + 2];
 #pragma unroll
   for (int k = 1; k < D; ++k) {
-    Pf += pm[k];
-    Sf2 += pm[k] * pm[k];
+    Pf += wk[D + 2 + k];
+    Sf2 += wk[D + 2 + k] * wk[D + 2 + k];
   }
-  const bool onf = arow == 0;  // the row's vertex is facet vertex 0, else the opposite vertex of cell A
-  const double ca = onf ? c[0] : c[D];
-  const double ga = onf ? gsum : 0.0;  // delta part of the row's jump
-  const double Jsa = ga + ca * Pf;
+  double ca = c[0];
+#pragma unroll
+  for (int m = 1; m < NG; ++m)
+    if (m == a) ca = c[m];
+  const bool onf = a < D;  // the row's vertex lies on the facet
+  const double ga = onf ? gsum : 0.0;
+  const double Jsa = sg * (ga + ca * Pf), cs = sg * ca, gs = sg * ga;
 #pragma unroll
   for (int m = 0; m < NG; ++m) {
     const double gm = m < D ? gsum : 0.0;
     const double Jsm = gm + c[m] * Pf;
-    double cross = ca * c[m] * Sf2 + ga * c[m] * pm[0];
-    if (m < D) cross += ca * gm * pm[m];
-    if (m == 0) cross += ga * gm;
-    K[m] = coef * (Jsa * Jsm + cross);
+    double cross = cs * c[m] * Sf2 + gs * c[m] * pr;
+    if (m < D) cross += cs * gm * wk[D + 2 + m];
+    if (m == a) cross += gs * gm;
+    K[m] = Jsa * Jsm + cross;
   }
 }
 
@@ -304,10 +354,11 @@ struct Others {
 
 // One pass over one row list.  KIND == kCells writes data / b of its rows, the surface passes add to them.
 template <int D, int KIND>
-__global__ void __launch_bounds__(kRowsBlock, KIND == kGhost ? 3 : PHIFEM_ROWS_MINBLOCKS) k_assemble_rows_p1(
+__global__ void __launch_bounds__(kRowsBlock, PHIFEM_ROWS_MINBLOCKS) k_assemble_rows_p1(
     const double* __restrict__ x, const double* __restrict__ phi, const double* __restrict__ f,
     double sigma, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-    phifem_row_list rl, double* __restrict__ data, double* __restrict__ b) {
+    phifem_row_list rl, const double* __restrict__ ghost_work, double* __restrict__ data,
+    double* __restrict__ b) {
   constexpr int NV = D + 1, NG = D + 2;
   extern __shared__ double acc_s[];  // accumulator k of thread t at acc_s[k * kRowsBlock + t]
   const int tid = threadIdx.x, lane = tid & 31;
@@ -388,60 +439,50 @@ __global__ void __launch_bounds__(kRowsBlock, KIND == kGhost ? 3 : PHIFEM_ROWS_M
       if (k + 1 < ke) body(k + 1, B, A);
     }
   } else if constexpr (KIND == kGhost) {  // interior facets tagged 2 / 3 whose macro element contains r
-    // Same pipeline as the cell pass with a single data buffer: the role selection below copies the
-    // buffer into the macro element, after which the gathers of the next record can overwrite it.
+    // record = {positions of the other macro vertices (macro order, the row's own index skipped),
+    //           facet index in the plan's ghost list | macro index of the row's vertex << 28};
+    // the facet's work record (L2-resident) of record k+1 is requested before record k is evaluated
+    constexpr int W = kGhostWork<D>;
     const uint2* __restrict__ recs = reinterpret_cast<const uint2*>(rl.rec);
     const uint2 pad2 = make_uint2(0u, kPad);
     auto fetch_rec = [&](int k) { return k < ke ? __ldg(recs + (int64_t)k * 32 + lane) : pad2; };
-    auto fetch_idx = [&](uint2 rec, int (&v)[NV]) {
-      const uint32_t q = rec.y == kPad ? 0u : rec.x;
+    auto fetch_work = [&](uint2 rec, double (&wk)[W]) {
+      const int64_t g = rec.y == kPad ? 0 : (int64_t)(rec.y & 0x0fffffffu);
+      const double* src = ghost_work + g * W;
 #pragma unroll
-      for (int j = 0; j < NV; ++j) v[j] = __ldg(cols + ((q >> (8 * j)) & 0xff));
+      for (int q = 0; q < W / 4; ++q) ldg256(src + 4 * q, wk[4 * q], wk[4 * q + 1], wk[4 * q + 2], wk[4 * q + 3]);
     };
-    double O[NV][D], po[NV];
-    auto fetch_data = [&](const int (&v)[NV]) {
-#pragma unroll
-      for (int j = 0; j < NV; ++j) load_vertex<D>(x, phi, v[j], O[j], po[j]);
-    };
-    uint2 w0 = fetch_rec(kb), w1 = fetch_rec(kb + 1), w2 = fetch_rec(kb + 2);
-    int v1[NV];
-    if (kb < ke) {
-      fetch_idx(w0, v1);
-      fetch_data(v1);
-      fetch_idx(w1, v1);
-    }
-    for (int k = kb; k < ke; ++k) {
-      const int role = (int)w0.y;
-      // role 0: M = [r, O0..O(D-2) | O(D-1), O(D)];  role 1: M = [O0..O(D-1) | r, O(D)]
-      double M[NG][D], pm[NG];
-#pragma unroll
-      for (int m = 0; m < NG; ++m) {
-        const int j0 = m == 0 ? 0 : m - 1;           // role 0 source (m == 0: the row's vertex)
-        const int j1 = m < D ? m : (m == D ? 0 : D);  // role 1 source (m == D: the row's vertex)
-        const bool own = role == 0 ? m == 0 : m == D;
-#pragma unroll
-        for (int d = 0; d < D; ++d) M[m][d] = own ? xr[d] : (role == 0 ? O[j0][d] : O[j1][d]);
-        pm[m] = own ? pr : (role == 0 ? po[j0] : po[j1]);
-      }
-      const uint2 cur = w0;
-      fetch_data(v1);
-      fetch_idx(w2, v1);
+    // record words are streamed from HBM (read once): kept 5 deep so that the word naming the NEXT facet has
+    // arrived when its work record is requested
+    const double sg = sigma < 0.0 ? -1.0 : 1.0;
+    double wa[W], wb[W];
+    uint2 w0 = fetch_rec(kb), w1 = fetch_rec(kb + 1), w2 = fetch_rec(kb + 2), w3 = fetch_rec(kb + 3),
+          w4 = fetch_rec(kb + 4);
+    if (kb < ke) fetch_work(w0, wa);
+    auto body = [&](int k, const double (&cur)[W], double (&nxt)[W]) {
+      const uint2 rec = w0;
+      fetch_work(w1, nxt);
       w0 = w1;
       w1 = w2;
-      w2 = fetch_rec(k + 3);
-      if (cur.y == kPad) continue;
+      w2 = w3;
+      w3 = w4;
+      w4 = fetch_rec(k + 5);
+      if (rec.y == kPad) return;
+      const int a = (int)(rec.y >> 28);
       double K[NG];
-      ghost_row<D>(M, pm, role == 0 ? 0 : D, sigma, K);
-      if (role == 0) {
-        diag += K[0];
+      ghost_row<D>(cur, a, pr, sg, K);
+      double Ka = K[0];
 #pragma unroll
-        for (int m = 1; m < NG; ++m) acc[((cur.x >> (8 * (m - 1))) & 0xff) * kRowsBlock] += K[m];
-      } else {
-        diag += K[D];
+      for (int m = 1; m < NG; ++m)
+        if (m == a) Ka = K[m];
+      diag += Ka;
 #pragma unroll
-        for (int m = 0; m < D; ++m) acc[((cur.x >> (8 * m)) & 0xff) * kRowsBlock] += K[m];
-        acc[((cur.x >> (8 * D)) & 0xff) * kRowsBlock] += K[D + 1];
-      }
+      for (int j = 0; j < NG - 1; ++j)  // j-th other macro vertex = macro index j (j < a) or j + 1
+        acc[((rec.x >> (8 * j)) & 0xff) * kRowsBlock] += j < a ? K[j] : K[j + 1];
+    };
+    for (int k = kb; k < ke; k += 2) {
+      body(k, wa, wb);
+      if (k + 1 < ke) body(k + 1, wb, wa);
     }
   } else {  // one-sided facets of ds(100) having r as a vertex
     for (int k = kb; k < ke; ++k) {
@@ -501,6 +542,10 @@ extern "C" int phifem_assemble_rows_p1(const phifem_mesh* mesh, const double* ph
   PHIFEM_CHECK_ARG(list_ok(plan->cells) && list_ok(plan->ghost) && list_ok(plan->boundary),
                    "row list arrays are null");
   PHIFEM_CHECK_ARG(plan->max_row_nnz > 0 && plan->max_row_nnz <= 255, "plan.max_row_nnz out of range");
+  PHIFEM_CHECK_ARG(plan->ghost.n_listed == 0 ||
+                       (plan->n_ghost_facets > 0 && plan->n_ghost_facets < (1 << 28) && plan->ghost_macro &&
+                        plan->ghost_work),
+                   "ghost facet arrays (n_ghost_facets < 2^28, ghost_macro, ghost_work)");
   const size_t smem = (size_t)plan->max_row_nnz * kRowsBlock * sizeof(double);
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t err = cudaSuccess;
@@ -511,14 +556,20 @@ extern "C" int phifem_assemble_rows_p1(const phifem_mesh* mesh, const double* ph
     const int64_t grid = (rl.n_listed + kRowsBlock - 1) / kRowsBlock;
     if (err == cudaSuccess)
       kernel<<<(unsigned)grid, kRowsBlock, smem, st>>>(mesh->x, phi, f, sigma, plan->indptr, plan->indices,
-                                                       rl, data, b);
+                                                       rl, plan->ghost_work, data, b);
   };
+  const int64_t ng = plan->ghost.n_listed ? plan->n_ghost_facets : 0;
+  const unsigned ggrid = (unsigned)((ng + kRowsBlock - 1) / kRowsBlock);
   if (mesh->cell_type == PHIFEM_TRIANGLE) {
     launch(k_assemble_rows_p1<2, kCells>, plan->cells);
+    if (ng) k_ghost_facets_p1<2><<<ggrid, kRowsBlock, 0, st>>>(mesh->x, phi, sigma, plan->ghost_macro, ng,
+                                                              plan->ghost_work);
     launch(k_assemble_rows_p1<2, kGhost>, plan->ghost);
     launch(k_assemble_rows_p1<2, kBoundary>, plan->boundary);
   } else {
     launch(k_assemble_rows_p1<3, kCells>, plan->cells);
+    if (ng) k_ghost_facets_p1<3><<<ggrid, kRowsBlock, 0, st>>>(mesh->x, phi, sigma, plan->ghost_macro, ng,
+                                                              plan->ghost_work);
     launch(k_assemble_rows_p1<3, kGhost>, plan->ghost);
     launch(k_assemble_rows_p1<3, kBoundary>, plan->boundary);
   }

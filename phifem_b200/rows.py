@@ -20,6 +20,7 @@ PAD = 0xFFFFFFFF
 MAX_ROW_NNZ = 255            # positions are uint8
 MAX_SMEM_BYTES = 200 * 1024  # accumulators of one CTA (128 threads x max_row_nnz doubles)
 BLOCK = 128
+BALANCE_CHUNK = 4096         # rows per spatially compact group of the surface lists
 
 
 def morton_order(x, rows):
@@ -48,8 +49,14 @@ class RowList:
         dev = rows.device
         i64 = dict(dtype=torch.int64, device=dev)
         if balance and rows.numel():
+            # `rows` arrive in a spatially compact order (Morton curve); inside chunks of BALANCE_CHUNK rows
+            # they are re-sorted by record count, so that the 32 lanes of a slice carry (almost) the same number
+            # of records while rows that share entities are still processed close in time (L2 reuse of the
+            # facet-once records of the ghost-penalty pass)
             per_row = torch.bincount(rec_rows, minlength=n_rows)[rows]
-            rows = rows[torch.argsort(per_row, descending=True, stable=True)]
+            chunk = torch.arange(rows.numel(), **i64) // BALANCE_CHUNK
+            key = chunk * (int(per_row.max()) + 1) + (int(per_row.max()) - per_row)
+            rows = rows[torch.argsort(key, stable=True)]
         self.n_listed = int(rows.numel())
         self.n_slices = (self.n_listed + 31) // 32
         self.words = w = words.shape[1]
@@ -139,6 +146,11 @@ class RowsPlan:
             rows = torch.unique(rows)
             return morton_order(mesh.x, rows) if order == "morton" and rows.numel() else rows
 
+        def surface_ordered(rows):
+            """Rows of the surface lists along the Morton curve (then balanced chunk by chunk)."""
+            rows = torch.unique(rows)
+            return morton_order(mesh.x, rows) if rows.numel() else rows
+
         # diagonal slot: the pattern holds (r, r) for every listed row (each entity couples its vertices
         # with themselves)
         cols = plan.indices.long()
@@ -169,24 +181,24 @@ class RowsPlan:
         if ng:
             mac = ghost_macro_vertices(mesh, plan.ghost)                         # [ng, nv+1]
             gs = plan.slots_ghost.long().reshape(-1, nv + 1, nv + 1)
+            if ng >= 2 ** 28:
+                raise NotImplementedError("row-gather plan: more than 2^28 ghost-penalty facets")
             words = []
-            for a in range(nv + 1):
-                if a < d:       # facet vertex: others = other facet vertices, opposite A, opposite B
-                    others = [j for j in range(d) if j != a] + [d, d + 1]
-                    role = 0
-                elif a == d:    # opposite vertex of cell A: others = facet vertices, opposite B
-                    others = list(range(d)) + [d + 1]
-                    role = 1
-                else:           # opposite vertex of cell B: same, with the sides swapped
-                    others = list(range(d)) + [d]
-                    role = 1
+            gidx = torch.arange(ng, **i64)
+            for a in range(nv + 1):     # the row's vertex is macro vertex a; others keep the macro order
+                others = [j for j in range(nv + 1) if j != a]
                 pos = gs[:, a, others] - indptr[mac[:, a]][:, None]
-                words.append(torch.stack([_pack_bytes(pos), torch.full((ng,), role, **i64)], dim=1))
+                words.append(torch.stack([_pack_bytes(pos), gidx | (a << 28)], dim=1))
             rec_rows, words = mac.reshape(-1), torch.stack(words, dim=1).reshape(-1, 2)
+            self.ghost_macro = mac.to(torch.int32).contiguous()
         else:
             rec_rows, words = torch.zeros(0, **i64), torch.zeros((0, 2), **i64)
+            self.ghost_macro = torch.zeros((0, nv + 1), dtype=torch.int32, device=dev)
+        self.n_ghost_facets = ng
+        # facet-once scratch of the ghost-penalty pass (8 doubles = 64 bytes per facet), rewritten by every assembly
+        self.ghost_work = torch.empty((max(ng, 1), 8), dtype=torch.float64, device=dev)
         rec_rows, words = owned(rec_rows, words)
-        self.ghost = RowList(ordered(rec_rows), dslot, indptr, rec_rows, words, n, balance=True)
+        self.ghost = RowList(surface_ordered(rec_rows), dslot, indptr, rec_rows, words, n, balance=True)
 
         # ---- one-sided facets: one record per facet vertex of each (cell, local facet) entity --------------
         ne = int(plan.entities.shape[0])
@@ -212,7 +224,7 @@ class RowsPlan:
         else:
             rec_rows, words = torch.zeros(0, **i64), torch.zeros((0, 1), **i64)
         rec_rows, words = owned(rec_rows, words)
-        self.boundary = RowList(ordered(rec_rows), dslot, indptr, rec_rows, words, n, balance=True)
+        self.boundary = RowList(surface_ordered(rec_rows), dslot, indptr, rec_rows, words, n, balance=True)
         self._c = None
 
     def c_struct(self, passes=None):
@@ -223,17 +235,27 @@ class RowsPlan:
             empty = _lib.CRowList(0, None, None, None, None)
             lists = [getattr(self, nm).c_struct() if nm in passes else empty
                      for nm in ("cells", "ghost", "boundary")]
-            return _lib.CRowsPlan(p(self.plan.indptr), p(self.plan.indices), self.max_row_nnz, 0, *lists)
+            return _lib.CRowsPlan(p(self.plan.indptr), p(self.plan.indices), self.max_row_nnz, 0, *lists,
+                                  *self._ghost_fields())
         if self._c is None:
             p = _lib.ptr
             pl = self.plan
             self._c = _lib.CRowsPlan(p(pl.indptr), p(pl.indices), self.max_row_nnz, 0,
-                                     self.cells.c_struct(), self.ghost.c_struct(), self.boundary.c_struct())
+                                     self.cells.c_struct(), self.ghost.c_struct(), self.boundary.c_struct(),
+                                     *self._ghost_fields())
         return self._c
+
+    def _ghost_fields(self):
+        """Trailing fields of phifem_rows_plan: the ghost facet arrays."""
+        if self.ghost_work.device.type != "cuda":
+            return 0, None, None
+        return (self.n_ghost_facets, _lib.ptr(self.ghost_macro) if self.n_ghost_facets else None,
+                _lib.ptr(self.ghost_work))
 
     def index_bytes(self):
         """Bytes of plan arrays one numeric pass streams besides the CSR pattern itself."""
-        return self.cells.nbytes() + self.ghost.nbytes() + self.boundary.nbytes()
+        return (self.cells.nbytes() + self.ghost.nbytes() + self.boundary.nbytes()
+                + self.ghost_macro.numel() * 4 + self.ghost_work.numel() * 8)
 
 
 def assemble_rows_into(rplan, phi, f, sigma, data, b, passes=None):

@@ -68,22 +68,21 @@ def _emulate(rp, m, x, cells, phi, f, out, sigma):
         by_set = {frozenset(int(v) for v in macro[e]): e for e in range(len(ghost))}
         assert len(by_set) == len(ghost)
     seen = set()
+    gm = rp.ghost_macro.numpy()
     for r, dp, w in _records(rp.ghost, indptr, indices):
-        role = int(w[1])
+        e, a = int(w[1]) & 0x0FFFFFFF, int(w[1]) >> 28       # ghost facet index, macro index of the row's vertex
         pos = [(int(w[0]) >> (8 * j)) & 0xFF for j in range(nv)]
         others = [int(indices[indptr[r] + p]) for p in pos]
-        e = by_set[frozenset([int(r)] + others)]
+        assert e == by_set[frozenset([int(r)] + others)]
         assert (r, e) not in seen
         seen.add((r, e))
         cplus, cminus = out["f2c"][ghost[e]]
         fv = set(cells[cplus]) & set(cells[cminus])
-        assert (role == 0) == (r in fv)
-        if role == 0:     # others = other facet vertices, then the two opposite vertices
-            assert set(others[:d - 1]) | {r} == fv and not (set(others[d - 1:]) & fv)
-        else:             # others = facet vertices, then the far opposite vertex
-            assert set(others[:d]) == fv and others[d] not in fv
-            # "cell A" is the cell holding the row's vertex
-            assert r in cells[cplus] or r in cells[cminus]
+        # macro order: facet vertices as ordered in cell +, opposite vertex of cell +, of cell -
+        assert int(gm[e][a]) == r and [int(v) for k, v in enumerate(gm[e]) if k != a] == others
+        assert set(int(v) for v in gm[e][:d]) == fv
+        assert int(gm[e][d]) in cells[cplus] and int(gm[e][d + 1]) in cells[cminus]
+        assert [v for v in cells[cplus] if v in fv] == [int(v) for v in gm[e][:d]]
         mv = [int(v) for v in macro[e]]
         rsel = [k for k, v in enumerate(mv) if v == r]
         for col, p in zip([int(r)] + others, [dp] + pos):
