@@ -267,7 +267,11 @@ class MeshTags:
 
     def _materialise(self):
         if self._indices is None:
-            dense = self.values_dev.cpu().numpy()
+            # computed tags fit one byte: move the int8 copy the kernels wrote (4x fewer PCIe bytes) and
+            # widen on the host; user-overwritten tags (`tags8_exact` unset) go through the int32 array
+            t8 = getattr(self, "tags8", None)
+            src = t8 if (t8 is not None and getattr(self, "tags8_exact", False)) else self.values_dev
+            dense = src.cpu().numpy()
             idx = np.nonzero(dense)[0].astype(np.int32)
             self._indices, self._values = idx, dense[idx].astype(np.int32)
 

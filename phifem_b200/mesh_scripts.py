@@ -250,6 +250,8 @@ def compute_tags_measures(mesh, discrete_levelset, detection_degree, box_mode=Fa
         ents_in = _integration_entities_dev(mesh, cell_tags8, facet_tags8, 3, (2, 3))
         measure = Measure("ds", mesh, subdomain_data=[(100, ents_out), (101, ents_in)])
         cells_tags.tags8, facets_tags.tags8 = cell_tags8, facet_tags8
+        cells_tags.tags8_exact = "cells" not in overwrite_tags
+        facets_tags.tags8_exact = "facets" not in overwrite_tags
         return cells_tags, facets_tags, None, measure, None
 
     # submesh of Omega_h = cells tagged 1 or 2 (:635-645)
