@@ -235,7 +235,14 @@ def run_ours(args):
     phi_asm, f_asm = phi, f
     V = fem.functionspace_p1_device(mesh)
     fn = fem.Function(V, phi)
-    dls = mesh_scripts._DeviceLevelset(mesh, fn, 1)
+    if args.detection_degree > 1:
+        # tags from a P_k level set with detection_degree k (the generic table-driven classifier) instead of
+        # the demos' P1 detection level set
+        Vd = fem.functionspace(mesh, args.detection_degree)
+        phi_det = synthetic.sphere_levelset(Vd.dof_coordinates_dev(), **ls_kw)
+        dls = mesh_scripts._DeviceLevelset(mesh, fem.Function(Vd, phi_det), args.detection_degree)
+    else:
+        dls = mesh_scripts._DeviceLevelset(mesh, fn, 1)
     ws = mesh_scripts.TagWorkspace(mesh)
     if problem is not None:
         problem.classify(dls, ws)
@@ -438,7 +445,7 @@ def run_ours(args):
                                             if args.dist_mode == "rows" else "NCCL halo exchange")),
                            "timed": "tag kernels + zeroing + assembly kernels; symbolic phase excluded"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-                "gpu_launches": {"rows": 7, "blocked": 5, "atomic": 7, "pk-atomic": 9}[plan.method] * args.steps,
+                "gpu_launches": {"rows": 8, "blocked": 5, "atomic": 7, "pk-atomic": 9}[plan.method] * args.steps,
                 "symbolic_ms": symbolic_ms, "topology_s": topo_s,
                 "scatter": {"method": plan.method,
                             **({"blocks": plan.blocked.n_blocks, "capacity": plan.blocked.capacity,
@@ -499,6 +506,8 @@ def main():
                     help="row processing order of the row-gather assembly")
     ap.add_argument("--dist-mode", default="rows", choices=["rows", "exchange"],
                     help="multi-GPU numeric strategy: owner-computes rows / per-entity kernels + halo exchange")
+    ap.add_argument("--detection-degree", type=int, default=1, choices=[1, 2],
+                    help="degree of the detection level set and of the detection rule (1 = the demos' setting)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     args = ap.parse_args()

@@ -308,6 +308,12 @@ int phifem_assemble_weak_ghost_pk(const phifem_mesh* mesh, const phifem_pk_space
                                   const phifem_quadrature* quad, const int32_t* facets, int64_t n_facets,
                                   const int32_t* slots, double sigma, double* data, void* stream);
 
+/* ---- the step after the path: y = A x for the CSR operator the assembly produced.  Building
+ * block of the Jacobi-preconditioned BiCGStab in phifem_b200/solve.py, which stands where the reference calls
+ * PETSc KSP preonly + MUMPS LU (demo/strong-dirichlet/flower/main.py:138-157). */
+int phifem_csr_spmv(int64_t n_rows, const int32_t* indptr, const int32_t* indices, const double* data,
+                    const double* x, double* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,3 +97,43 @@ def ball_source(x, center=SPHERE_CENTER, radius=0.2, value=10.0):
     c = torch.tensor(center[:x.shape[1]], dtype=torch.float64, device=x.device)
     d = x - c
     return torch.where((d * d).sum(dim=1) <= radius * radius, value, 0.0).to(torch.float64)
+
+
+# ---- flower domain of the reference demos (demo/weak-dirichlet/flower/data.py:27-99, demo/strong-dirichlet/
+# flower/data.py:16-62): a disc of radius 2 with eight petals.  numpy, x of shape (gdim | 3, npoints) like a dolfinx
+# interpolation callback.  `flower_detection` is the non-smooth min used for the tags (data.py:57-82),
+# `flower_levelset` the graded smooth-min used in the forms (:27-54), `flower_source` 10 on a small disc inside the
+# first petal (:85-99).  Checked against the reference's own values in tests/golden/flower_demo.npz.
+def _flower_parts(x):
+    s = np.cos(np.pi / 8.0) + np.sin(np.pi / 8.0)
+    rp = np.sqrt(2.0) * 2.0 * s * np.sin(np.pi / 8.0)
+    yield x[0] ** 2 + x[1] ** 2 - 4.0
+    for i in range(1, 9):
+        cx, cy = 2.0 * s * np.cos(i * np.pi / 4.0), 2.0 * s * np.sin(i * np.pi / 4.0)
+        yield (x[0] - cx) ** 2 + (x[1] - cy) ** 2 - rp ** 2
+
+
+def flower_detection(x):
+    val = None
+    for part in _flower_parts(x):
+        val = part if val is None else np.minimum(val, part)
+    return val
+
+
+def flower_levelset(x):
+    r = np.sqrt(x[0] ** 2 + x[1] ** 2)
+    k = (np.pi / 2.0 - np.arctan(50.0 * (r - 2.0))) / np.pi / 2.0          # graded smoothing width in (0, 1/2)
+    val = None
+    for part in _flower_parts(x):
+        if val is None:
+            val = part
+            continue
+        lo = np.minimum(val, part)
+        val = np.maximum(k, lo) - np.sqrt(np.maximum(k - val, 0.0) ** 2 + np.maximum(k - part, 0.0) ** 2)
+    return val
+
+
+def flower_source(x):
+    s = np.cos(np.pi / 8.0) + np.sin(np.pi / 8.0)
+    r1 = np.sqrt(2.0) * 2.0 * s * np.sin(np.pi / 8.0)
+    return np.where((x[0] - 2.0 * s) ** 2 + x[1] ** 2 <= r1 ** 2 / 2.0, 10.0, 0.0)
