@@ -18,6 +18,7 @@ import torch
 
 from . import _lib
 from .fem import Function
+from .mesh import Measure
 
 
 class CSRMatrix:
@@ -134,6 +135,13 @@ def _plan_inputs(mesh, cells_tags, facets_tags, ds):
     f8 = f8 if f8 is not None else facets_tags.values_dev.to(torch.int8)
     if ds is None:
         ents = torch.zeros(0, dtype=torch.int32, device=mesh.device)
+    elif isinstance(ds, Measure) and ds.subdomain_data is None:
+        # plain `ufl.Measure("ds", domain=submesh)` of the demos' "sub" mode (main.py:66-70): every exterior facet
+        # of the mesh, seen from its only cell
+        bf = mesh.boundary_facets.long()
+        owner = mesh.f2c[bf, 0].long()
+        lf = (mesh.c2f[owner].long() == bf[:, None]).long().argmax(dim=1)
+        ents = torch.stack([owner, lf], dim=1).reshape(-1).to(torch.int32)
     elif hasattr(ds, "integration_entities_dev"):
         ents = ds.integration_entities_dev
     elif torch.is_tensor(ds):

@@ -172,3 +172,30 @@ def test_cuda_assembly_properties_at_scale():
     assert abs(float(b.sum()) - want) <= 1e-10 * want
     # sphere of radius 0.45: |Omega_h| slightly above the ball volume
     assert 0.38 < want < 0.42
+
+
+@pytest.mark.parametrize("kind,n", [("tri-unstructured", 28), ("tet-unstructured", 9)])
+def test_submesh_route_equals_box_mode(kind, n):
+    """`python main.py sub` vs `python main.py bg` of the demo (main.py:58-70): the operator assembled on the
+    submesh of Omega_h with the plain `ds` measure equals the box-mode operator restricted to the dofs of
+    Omega_h (same sparsity, same entries), and the box-mode rows outside Omega_h are empty."""
+    mesh, phi, f = _setup(kind, n)
+    fn = fem.Function(fem.functionspace(mesh, 1), phi.cpu().numpy())
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        ctags, ftags, _, ds_bdy, _ = mesh_scripts.compute_tags_measures(mesh, fn, 1, box_mode=True)
+        sct, sft, sub, ds_sub, maps = mesh_scripts.compute_tags_measures(mesh, fn, 1, box_mode=False)
+    A, b = assemble.assemble_strong_dirichlet(assemble.build_plan(mesh, ctags, ftags, ds_bdy(100)), phi, f)
+    v_map = torch.as_tensor(maps[1].astype(np.int64), device="cuda")
+    As, bs = assemble.assemble_strong_dirichlet(assemble.build_plan(sub, sct, sft, ds_sub), phi[v_map], f[v_map])
+    M, Ms = A.to_scipy().tocsr(), As.to_scipy().tocsr()
+    vm = maps[1].astype(np.int64)
+    outside = np.setdiff1d(np.arange(mesh.num_vertices), vm)
+    assert np.all(np.diff(M.indptr)[outside] == 0) and np.all(b.cpu().numpy()[outside] == 0.0)
+    R = M[vm][:, vm].tocsr()
+    R.sort_indices()
+    Ms.sort_indices()
+    assert np.array_equal(R.indptr, Ms.indptr) and np.array_equal(R.indices, Ms.indices)
+    scale = np.abs(R.data).max()
+    assert np.abs(R.data - Ms.data).max() <= 1e-12 * scale
+    assert np.abs(b.cpu().numpy()[vm] - bs.cpu().numpy()).max() <= 1e-12 * float(b.abs().max())
