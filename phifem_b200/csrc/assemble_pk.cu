@@ -288,7 +288,7 @@ template <int ND> struct Passes { static constexpr int N = 1; };
 template <> struct Passes<10> { static constexpr int N = 3; };
 
 template <int D, int KW, int KP>
-__global__ void __launch_bounds__(kBlockPk) k_assemble_cells_pk(
+__global__ void __launch_bounds__(kBlockPk, D == 2 ? 3 : 2) k_assemble_cells_pk(
     phifem_mesh m, phifem_pk_space sw, phifem_pk_space sp, const double* __restrict__ qlam_g,
     const double* __restrict__ qw_g, int nq, const double* __restrict__ phi, const double* __restrict__ f,
     const int8_t* __restrict__ ctags, const int32_t* __restrict__ active, int64_t n_active,
