@@ -78,14 +78,34 @@ def main():
         fd = np.zeros(len(f2c), dtype=np.int8)
         fd[ft.indices] = ft.values
         assert len(np.unique(ft.indices)) == len(ft.indices), "the reference emitted a facet twice"
-        return cd, fd
+        # submesh route (:635-645): the reference's `_transfer_tags` (:217-281) onto the submesh of Omega_h.
+        # dolfinx's create_submesh is not available; the submesh stand-in keeps the cells tagged 1/2 in
+        # ascending order and renumbers their vertices ascending (oracle/tags.py `submesh`)
+        keep = np.nonzero((cd == 1) | (cd == 2))[0]
+        sx, scells, _ = OT.submesh(x, cells.astype(np.int64), keep)
+        sub = Mesh(sx, scells, cell_type, device="cpu")
+        sct = ref._transfer_tags(ct, sub, keep)
+        sft = ref._transfer_tags(ft, sub, keep, source_mesh=mesh)
+        assert np.array_equal(sct.indices, np.arange(len(keep))) and np.array_equal(sft.indices,
+                                                                                    np.arange(sub.num_facets))
+        # user overlay (:561-568): tag 7 on every fifth cell, 9 on every seventh facet
+        oc = ref._overwrite_tags(mesh, ct, Tags(mesh, ct.dim, np.arange(0, mesh.num_cells, 5, dtype=np.int32),
+                                                np.full(len(range(0, mesh.num_cells, 5)), 7, dtype=np.int32)))
+        of = ref._overwrite_tags(mesh, ft, Tags(mesh, ft.dim, np.arange(0, len(f2c), 7, dtype=np.int32),
+                                                np.full(len(range(0, len(f2c), 7)), 9, dtype=np.int32)))
+        extra = {"sub_ctags": sct.values.astype(np.int8), "sub_ftags": sft.values.astype(np.int8),
+                 "ow_c_idx": oc.indices.astype(np.int32), "ow_c_val": oc.values.astype(np.int32),
+                 "ow_f_idx": of.indices.astype(np.int32), "ow_f_val": of.values.astype(np.int32)}
+        return cd, fd, extra
 
     out, names = {}, []
 
     def add(name, x, cells, cell_type, phi_v):
         for single in (False, True):
             key = name + ("_single" if single else "")
-            ct, ft = run(x, cells, cell_type, phi_v, single)
+            ct, ft, extra = run(x, cells, cell_type, phi_v, single)
+            for k, v in extra.items():
+                out[k + "_" + key] = v
             out["x_" + key], out["cells_" + key] = x, cells.astype(np.int32)
             out["type_" + key], out["phi_" + key] = np.array(cell_type), phi_v
             out["ctags_" + key], out["ftags_" + key] = ct, ft
