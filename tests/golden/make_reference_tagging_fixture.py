@@ -3,9 +3,10 @@
 Everything in those two functions downstream of the detection vector is numpy: the exact comparisons with +-1
 (:343-347), `single_layer_cut` (:349-358) and the ~30 set operations of the facet algebra (:454-496).  The only
 dolfinx-dependent piece is `_compute_detection_vector` (:95-134, two DG0 forms assembled by dolfinx).  This script
-imports the unmodified reference module with stubbed dolfinx / ufl / basix imports, replaces
-`_compute_detection_vector` alone by the oracle's detection ratio (oracle/tags.py; that piece is pinned separately
-by the reference's golden CSVs) and runs the reference's code on
+imports the unmodified reference module with stubbed dolfinx / ufl / basix imports, answers the two
+`assemble_vector` calls inside `_compute_detection_vector` with the oracle's sums (oracle/tags.py; that piece is
+pinned separately by the reference's golden CSVs) -- the ratio, its 0.5 fallback and the warning (:124-133) run for
+real -- and runs the reference's code on
 
   * the reference's triangle / quadrilateral fixture meshes (both functions), and
   * jittered, permuted, relabelled triangle and TETRAHEDRON meshes -- the reference's `_tag_cells` refuses
@@ -20,6 +21,7 @@ Output: tests/golden/reference_tagging.npz (committed; meshes included, they are
 import os
 import sys
 import types
+import warnings
 
 import numpy as np
 
@@ -65,14 +67,34 @@ def main():
         phi_facet = OT.point_values_function(phi_v, cells, ftab)
         num_c, den_c = OT.detection_sums_cells(phi_cell, OT.cell_scale(x, cells, cell_type, pts))
         num_f, den_f = OT.detection_sums_facets(phi_facet, OT.facet_scale(x, cells, cell_type), c2f, f2c)
-        vectors = {"dx": OT.detection_ratio(num_c, den_c, warn=False),
-                   "ds": OT.detection_ratio(num_f, den_f, warn=False)}
-        ref._compute_detection_vector = lambda m, ls, measure: vectors[measure.kind]
+        # `_compute_detection_vector` (:95-134) runs for real; only the two dolfinx `assemble_vector` calls inside
+        # it are answered with the oracle's sums (the UFL expression it builds is reduced to a (which, measure) key)
+        sums = {("num", "dx"): num_c, ("den", "dx"): den_c, ("num", "ds"): num_f, ("den", "ds"): den_f}
+
+        class Integrand:
+            def __init__(self, which):
+                self.which = which
+
+            def __mul__(self, measure):
+                return (self.which, measure.kind)
+
+        class LevelSet:
+            def __abs__(self):
+                return "abs"
+
+        ref.inner = lambda a, v0: Integrand("den" if a == "abs" else "num")
+        ref.element = lambda *a, **k: None
+        ref.dfx.fem = types.SimpleNamespace(functionspace=lambda m, e: None, form=lambda f: f)
+        ref.ufl.TestFunction = lambda space: "v0"
+        ref.assemble_vector = lambda form: types.SimpleNamespace(array=sums[form].copy())
         ref.ufl.Measure = lambda kind, **kw: types.SimpleNamespace(kind=kind)
+        levelset = LevelSet()
         if cell_type == "tetrahedron":       # get past the guard of :326-329 (see the module docstring)
             mesh.topology.cell_type.name = "triangle"
-        ct = ref._tag_cells(mesh, None, 1, single_layer_cut=single)
-        ft = ref._tag_facets(mesh, ct, None, 1)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)    # the ds detection warns on every mesh (:129-133)
+            ct = ref._tag_cells(mesh, levelset, 1, single_layer_cut=single)
+            ft = ref._tag_facets(mesh, ct, levelset, 1)
         cd = np.zeros(mesh.num_cells, dtype=np.int8)
         cd[ct.indices] = ct.values
         fd = np.zeros(len(f2c), dtype=np.int8)
