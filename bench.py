@@ -309,6 +309,15 @@ def run_ours(args):
         dist.barrier()
     torch.cuda.synchronize()
     sampler.start()
+    # an NVML query takes milliseconds, a step two: keep the device under the same load until the sampler has
+    # seen it (untimed steps), then time exactly `steps` steps with the sampler still running
+    t_load = time.perf_counter()
+    while len(sampler.samples) < 3 and time.perf_counter() - t_load < 0.5 and sampler.nv is not None:
+        step()
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for i in range(args.steps):
