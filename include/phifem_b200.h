@@ -199,8 +199,8 @@ int phifem_assemble_blocked_p1(const phifem_mesh* mesh, const double* phi, const
  * vertices (uint8 each), so the CSR pattern itself is the connectivity the kernel reads.
  * Records are stored as sliced ELLPACK over warps: slice s = listed rows [32 s, 32 s + 32), record k of
  * lane l at rec[((ptr[s] + k) * 32 + l) * words]; ptr[] counts records per lane, pads are all-ones.
- * Each record kind has its own list of rows (the ghost-penalty and one-sided terms touch only rows near
- * the surface; walking them in the cell pass would leave most lanes of every warp idle). */
+ * The surface terms have their own list of rows (they touch only rows near the surface; walking them in the
+ * cell pass would leave most lanes of every warp idle). */
 typedef struct phifem_row_list {
   int64_t n_listed;            /* rows of this list, in processing order */
   const int32_t* rows;         /* [n_listed] row (= vertex) ids, each row at most once */
@@ -218,23 +218,26 @@ typedef struct phifem_rows_plan {
    * cell tagged 1/2 containing the row's vertex; bit 24: the cell is cut (tag 2).  This pass WRITES the
    * rows (data and b); rows listed here without records are written as zeros. */
   phifem_row_list cells;
-  /* rows touched by interior facets tagged 2/3.  The macro element of ghost facet g is ghost_macro[g] =
-   * [facet vertices as ordered in cell A = f2c[f][0], opposite vertex of cell A, opposite vertex of cell B].
-   * Two words per record: word 0 byte j = position of the j-th OTHER macro vertex (macro order, the row's own
-   * index skipped); word 1 = g | (macro index of the row's vertex << 28).  A facet-once kernel first writes
-   * 8 doubles per facet into ghost_work (jump coefficients, see csrc/assemble_rows.cu); this pass then
-   * ADDS each row's entries to the rows written by the cell pass. */
-  phifem_row_list ghost;
-  /* rows on one-sided facets of ds(100); one word per record: byte 0 = position of the cell vertex opposite
-   * the facet, bytes 1..d-1 = the other facet vertices.  ADDS as well. */
-  phifem_row_list boundary;
-  int64_t n_ghost_facets;      /* < 2^28 */
+  /* rows touched by the surface terms: interior facets tagged 2/3 (ghost penalty) and the one-sided entities of
+   * ds(100).  A facet-once kernel first writes 8 doubles per ghost facet / entity into surface_work (jump
+   * coefficients resp. normal derivatives, see csrc/assemble_rows.cu); this pass then ADDS each row's entries to the
+   * rows written by the cell pass.  Two words per record:
+   *   ghost facet g, macro element ghost_macro[g] = [facet vertices as ordered in cell A = f2c[f][0], opposite
+   *     vertex of cell A, opposite vertex of cell B]: word 0 byte j = position of the j-th OTHER macro vertex
+   *     (macro order, the row's own index skipped); word 1 = g | (macro index of the row's vertex << 28);
+   *   one-sided entity e, entity_macro[e] = [facet vertices in ascending local order, opposite vertex]: the row's
+   *     vertex is facet vertex t; word 0 byte 0 = position of the opposite vertex, byte j = position of facet
+   *     vertex (t + j) % d; word 1 = (n_ghost_facets + e) | (t << 28) | (1 << 31). */
+  phifem_row_list surface;
+  int64_t n_ghost_facets;      /* n_ghost_facets + n_entities < 2^28 */
   const int32_t* ghost_macro;  /* [n_ghost_facets, d + 2] vertex ids */
-  double* ghost_work;          /* [n_ghost_facets, 8] scratch (32-byte aligned), rewritten by every call */
+  int64_t n_entities;
+  const int32_t* entity_macro; /* [n_entities, d + 1] vertex ids */
+  double* surface_work;        /* [n_ghost_facets + n_entities, 8] scratch (32-byte aligned), rewritten by every call */
 } phifem_rows_plan;
 
-/* Same operator as phifem_assemble_{cells,boundary,ghost}_p1, three launches on `stream` (cell pass, then
- * the two surface passes).  `data` need NOT be zeroed (every entry of a listed row is written by the cell
+/* Same operator as phifem_assemble_{cells,boundary,ghost}_p1: the facet-once kernel (forked onto an internal side
+ * stream, joined before the surface pass), the cell pass and the surface pass.  `data` need NOT be zeroed (every entry of a listed row is written by the cell
  * pass); b[row] is written for listed rows only. */
 int phifem_assemble_rows_p1(const phifem_mesh* mesh, const double* phi, const double* f, double sigma,
                             const phifem_rows_plan* plan, double* data, double* b, void* stream);

@@ -50,9 +50,9 @@ class CRowList(ctypes.Structure):
 
 class CRowsPlan(ctypes.Structure):
     _fields_ = [("indptr", _vp), ("indices", _vp), ("max_row_nnz", ctypes.c_int32),
-                ("reserved", ctypes.c_int32), ("cells", CRowList), ("ghost", CRowList),
-                ("boundary", CRowList), ("n_ghost_facets", ctypes.c_int64), ("ghost_macro", _vp),
-                ("ghost_work", _vp)]
+                ("reserved", ctypes.c_int32), ("cells", CRowList), ("surface", CRowList),
+                ("n_ghost_facets", ctypes.c_int64), ("ghost_macro", _vp), ("n_entities", ctypes.c_int64),
+                ("entity_macro", _vp), ("surface_work", _vp)]
 
 
 class CPkSpace(ctypes.Structure):

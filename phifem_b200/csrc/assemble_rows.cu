@@ -182,11 +182,17 @@ __device__ __forceinline__ double alpha3(int a, int b, int c) {
   return (double)((1 + (a == b)) * (1 + (a == c) + (b == c)));
 }
 
-// Row 0 of -int_F (grad(phi w).n) phi v (main.py:106) on the facet [X[0..D-1]] of simplex X; local
-// vertex D is the one opposite the facet, the row's vertex is facet vertex 0.  K[j] = entry (0, j).
+// One-sided term -int_F (grad(phi w).n) phi v (main.py:106) on a (cell, local facet) entity of ds(100), in the same two
+// phases as the ghost penalty.  Entity-once (k_surface_once_p1): with the cell's vertices listed as
+// [facet vertices 0..D-1, opposite vertex], n = the outward normal of THIS cell (tests/test_one_sided_integral.py pins
+// it), cF = |F| (D-1)!/(D+2)!, the thread stores cF grad(phi).n, cF grad(lambda_j).n for the D + 1 vertices and phi at
+// the facet vertices: 2 D + 2 doubles.  Per row (facet vertex t): with the facet vertices rotated so that the row's
+// vertex comes first, entry (0, j) = -[ (cF gn) W_j + (cF Gn_j) Q ],  W_j = sum_k phi_k alpha(j,k,0) for j on the
+// facet (0 for the opposite vertex), Q = sum_kl phi_k phi_l alpha(l,k,0), alpha = the multiplicity factor of
+// int lambda_a lambda_b lambda_c over the facet.
 template <int D>
-__device__ __forceinline__ void boundary_row(const double (&X)[D + 1][D], const double (&p)[D + 1],
-                                             double (&K)[D + 1]) {
+__device__ __forceinline__ void entity_record(const double (&X)[D + 1][D], const double (&p)[D + 1],
+                                              double* __restrict__ w) {
   constexpr int NV = D + 1;
   double G[NV][D], det;
   simplex_gradients<D>(X, G, det);
@@ -195,42 +201,65 @@ __device__ __forceinline__ void boundary_row(const double (&X)[D + 1][D], const 
   double n[D], g[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) {
-    n[d] = -G[D][d] / gnorm;  // outward normal of THIS cell (tests/test_one_sided_integral.py pins it)
+    n[d] = -G[D][d] / gnorm;
     double s = p[0] * G[0][d];
 #pragma unroll
     for (int k = 1; k < NV; ++k) s += p[k] * G[k][d];
     g[d] = s;
   }
-  const double gn = dot<D>(g, n);
   constexpr double cfac = D == 2 ? 1.0 / 24.0 : 2.0 / 120.0;  // (d-1)!/(d+2)!
   const double cF = D * vol * gnorm * cfac;
+  w[0] = cF * dot<D>(g, n);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) w[1 + j] = cF * dot<D>(G[j], n);
+#pragma unroll
+  for (int k = 0; k < D; ++k) w[2 + D + k] = p[k];
+  if (D == 2) w[6] = w[7] = 0.0;
+}
+
+// Row of facet vertex t from the entity's record: K[0] = diagonal, K[1..D-1] = facet vertices (t + j) % D,
+// K[D] = the opposite vertex.
+template <int D>
+__device__ __forceinline__ void entity_row(const double (&wk)[8], int t, double (&K)[D + 1]) {
+  double p[D], Gn[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) {  // rotate: index k <- (t + k) % D
+    double pv = wk[2 + D + k], gv = wk[1 + k];
+#pragma unroll
+    for (int s = 1; s < D; ++s)
+      if (t == s) {
+        pv = wk[2 + D + (k + s) % D];
+        gv = wk[1 + (k + s) % D];
+      }
+    p[k] = pv;
+    Gn[k] = gv;
+  }
   double Q = 0.0;
 #pragma unroll
   for (int k = 0; k < D; ++k)
 #pragma unroll
     for (int l = 0; l < D; ++l) Q += p[k] * p[l] * alpha3(l, k, 0);
 #pragma unroll
-  for (int j = 0; j < NV; ++j) {
+  for (int j = 0; j < D; ++j) {
     double W = 0.0;
-    if (j < D) {
 #pragma unroll
-      for (int k = 0; k < D; ++k) W += p[k] * alpha3(j, k, 0);
-    }
-    K[j] = -cF * (gn * W + dot<D>(G[j], n) * Q);
+    for (int k = 0; k < D; ++k) W += p[k] * alpha3(j, k, 0);
+    K[j] = -(wk[0] * W + Gn[j] * Q);
   }
+  K[D] = -wk[1 + D] * Q;
 }
 
 // Ghost penalty sigma avg(h_T) int_F jump.jump (main.py:113-118) over the facet macro element
 // M = [facet vertices 0..D-1 (as ordered in cell A = f2c[f][0]), opposite vertex of cell A, opposite vertex of
 // cell B].  Two phases, both without atomics:
-//   facet-once (k_ghost_facets_p1): with N = the facet's cofactor vector (normal scaled by (D-1)! |F|, the same
+//   facet-once (k_surface_once_p1): with N = the facet's cofactor vector (normal scaled by (D-1)! |F|, the same
 //     for both cells) the normal derivative of lambda_a seen from cell s is Gn_a = -(R_a . N) / (|det_s| |N|);
 //     the jump of grad(phi w_m).n at a point of F is  lambda_m [m on F] gsum + phi c_m  with
 //     gsum = sum_s grad(phi).n_s and c_m = sum_s Gn_m (sum_m c_m = 0: the barycentric gradients of a cell sum
 //     to zero).  With s = sqrt(|sigma| avg(h) |F| / (D (D+1))) the thread stores s c_0..s c_D, s gsum and phi at
 //     the facet vertices: 8 doubles = 64 bytes per facet (two 256-bit loads for a row), 93 MB for the 1.45 M
 //     ghost facets of config E;
-//   per row (k_assemble_rows_p1<D, kGhost>): the facet mass matrix |F| (1 + delta_kl) / (D (D+1)) gives
+//   per row (k_assemble_rows_p1<D, kSurface>): the facet mass matrix |F| (1 + delta_kl) / (D (D+1)) gives
 //     entry (a, m) = sign(sigma) [ (ga + c_a Pf)(gm + c_m Pf) + c_a c_m Sf2 + ga c_m phi_a + c_a gm phi_m
 //                                  + ga gm delta_am ],  ga = s gsum if a lies on F else 0, Pf = sum phi_k,
 //     Sf2 = sum phi_k^2 over the facet vertices: ~50 fp64 operations per row instead of ~300.
@@ -244,12 +273,26 @@ __device__ __forceinline__ void ldg256(const double* p, double& a, double& b, do
 }
 
 template <int D>
-__global__ void __launch_bounds__(kRowsBlock) k_ghost_facets_p1(
+__global__ void __launch_bounds__(kRowsBlock) k_surface_once_p1(
     const double* __restrict__ x, const double* __restrict__ phi, double sigma,
-    const int32_t* __restrict__ macro, int64_t n_facets, double* __restrict__ work) {
+    const int32_t* __restrict__ macro, int64_t n_facets, const int32_t* __restrict__ entity_macro,
+    int64_t n_entities, double* __restrict__ work) {
   constexpr int NV = D + 1, NG = D + 2, W = kGhostWork<D>;
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_facets) return;
+  if (g >= n_facets + n_entities) return;
+  if (g >= n_facets) {  // one-sided entity: record index n_facets + e
+    const int64_t e = g - n_facets;
+    double X[NV][D], p[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int v = __ldg(entity_macro + e * NV + k);
+#pragma unroll
+      for (int d = 0; d < D; ++d) X[k][d] = __ldg(x + (int64_t)v * D + d);
+      p[k] = __ldg(phi + v);
+    }
+    entity_record<D>(X, p, work + g * W);
+    return;
+  }
   double M[NG][D], pm[NG];
 #pragma unroll
   for (int m = 0; m < NG; ++m) {
@@ -344,7 +387,7 @@ __device__ __forceinline__ void load_vertex(const double* __restrict__ x, const 
   p = __ldg(phi + v);
 }
 
-enum { kCells = 0, kGhost = 1, kBoundary = 2 };
+enum { kCells = 0, kSurface = 1 };
 
 // coordinates, phi and f of the D other vertices of a cell record
 template <int D>
@@ -357,7 +400,7 @@ template <int D, int KIND>
 __global__ void __launch_bounds__(kRowsBlock, PHIFEM_ROWS_MINBLOCKS) k_assemble_rows_p1(
     const double* __restrict__ x, const double* __restrict__ phi, const double* __restrict__ f,
     double sigma, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-    phifem_row_list rl, const double* __restrict__ ghost_work, double* __restrict__ data,
+    phifem_row_list rl, const double* __restrict__ surface_work, double* __restrict__ data,
     double* __restrict__ b) {
   constexpr int NV = D + 1, NG = D + 2;
   extern __shared__ double acc_s[];  // accumulator k of thread t at acc_s[k * kRowsBlock + t]
@@ -438,17 +481,19 @@ __global__ void __launch_bounds__(kRowsBlock, PHIFEM_ROWS_MINBLOCKS) k_assemble_
       body(k, A, B);
       if (k + 1 < ke) body(k + 1, B, A);
     }
-  } else if constexpr (KIND == kGhost) {  // interior facets tagged 2 / 3 whose macro element contains r
-    // record = {positions of the other macro vertices (macro order, the row's own index skipped),
-    //           facet index in the plan's ghost list | macro index of the row's vertex << 28};
+  } else {  // surface pass: ghost-penalty facets and one-sided entities whose vertices include r
+    // ghost record = {positions of the other macro vertices (macro order, the row's own index skipped),
+    //                 facet index in the plan's ghost list | macro index of the row's vertex << 28};
+    // one-sided record = {positions of [opposite vertex, facet vertices (t + 1) % D, ...],
+    //                     (n_ghost_facets + entity index) | t << 28 | 1 << 31};
     // the facet's work record (L2-resident) of record k+1 is requested before record k is evaluated
     constexpr int W = kGhostWork<D>;
     const uint2* __restrict__ recs = reinterpret_cast<const uint2*>(rl.rec);
     const uint2 pad2 = make_uint2(0u, kPad);
     auto fetch_rec = [&](int k) { return k < ke ? __ldg(recs + (int64_t)k * 32 + lane) : pad2; };
     auto fetch_work = [&](uint2 rec, double (&wk)[W]) {
-      const int64_t g = rec.y == kPad ? 0 : (int64_t)(rec.y & 0x0fffffffu);
-      const double* src = ghost_work + g * W;
+      const int64_t g = rec.y == kPad ? 0 : (int64_t)(rec.y & 0x0fffffffu);  // ghost facet or n_ghost + entity
+      const double* src = surface_work + g * W;
 #pragma unroll
       for (int q = 0; q < W / 4; ++q) ldg256(src + 4 * q, wk[4 * q], wk[4 * q + 1], wk[4 * q + 2], wk[4 * q + 3]);
     };
@@ -468,6 +513,15 @@ __global__ void __launch_bounds__(kRowsBlock, PHIFEM_ROWS_MINBLOCKS) k_assemble_
       w3 = w4;
       w4 = fetch_rec(k + 5);
       if (rec.y == kPad) return;
+      if (rec.y >> 31) {  // one-sided entity: byte 0 = the opposite vertex, byte j = facet vertex (t + j) % D
+        double Kb[NV];
+        entity_row<D>(cur, (int)((rec.y >> 28) & 7u), Kb);
+        diag += Kb[0];
+        acc[(rec.x & 0xff) * kRowsBlock] += Kb[D];
+#pragma unroll
+        for (int j = 1; j < D; ++j) acc[((rec.x >> (8 * j)) & 0xff) * kRowsBlock] += Kb[j];
+        return;
+      }
       const int a = (int)(rec.y >> 28);
       double K[NG];
       ghost_row<D>(cur, a, pr, sg, K);
@@ -483,28 +537,6 @@ __global__ void __launch_bounds__(kRowsBlock, PHIFEM_ROWS_MINBLOCKS) k_assemble_
     for (int k = kb; k < ke; k += 2) {
       body(k, wa, wb);
       if (k + 1 < ke) body(k + 1, wb, wa);
-    }
-  } else {  // one-sided facets of ds(100) having r as a vertex
-    for (int k = kb; k < ke; ++k) {
-      const uint32_t cur = __ldg(rl.rec + (int64_t)k * 32 + lane);
-      if (cur == kPad) continue;
-      int pos[D];
-      double X[NV][D], p[NV];
-#pragma unroll
-      for (int d = 0; d < D; ++d) X[0][d] = xr[d];
-      p[0] = pr;
-#pragma unroll
-      for (int j = 0; j < D; ++j) {
-        pos[j] = (cur >> (8 * j)) & 0xff;
-        const int loc = j == 0 ? D : j;  // byte 0 names the vertex opposite the facet
-        load_vertex<D>(x, phi, __ldg(cols + pos[j]), X[loc], p[loc]);
-      }
-      double K[NV];
-      boundary_row<D>(X, p, K);
-      diag += K[0];
-      acc[pos[0] * kRowsBlock] += K[D];
-#pragma unroll
-      for (int j = 1; j < D; ++j) acc[pos[j] * kRowsBlock] += K[j];
     }
   }
   acc[dpos * kRowsBlock] += diag;
@@ -525,6 +557,24 @@ namespace {
 bool list_ok(const phifem_row_list& l) {
   return l.n_listed == 0 || (l.rows && l.diag_pos && l.ptr && l.rec);
 }
+// one side stream + fork / join events per device (created on first use, never destroyed)
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool ok = false;
+};
+SideStream& side_stream() {
+  static SideStream per_device[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  SideStream& s = per_device[dev & 63];
+  if (!s.stream) {
+    s.ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess;
+  }
+  return s;
+}
 }  // namespace
 
 extern "C" int phifem_assemble_rows_p1(const phifem_mesh* mesh, const double* phi, const double* f,
@@ -537,15 +587,16 @@ extern "C" int phifem_assemble_rows_p1(const phifem_mesh* mesh, const double* ph
   }
   PHIFEM_CHECK_ARG(mesh->gdim == (mesh->cell_type == PHIFEM_TRIANGLE ? 2 : 3), "gdim mismatch");
   PHIFEM_CHECK_ARG(phi && f && plan && data && b, "null pointer");
-  if (plan->cells.n_listed == 0 && plan->ghost.n_listed == 0 && plan->boundary.n_listed == 0) return PHIFEM_OK;
+  if (plan->cells.n_listed == 0 && plan->surface.n_listed == 0) return PHIFEM_OK;
   PHIFEM_CHECK_ARG(plan->indptr && plan->indices, "CSR pattern is null");
-  PHIFEM_CHECK_ARG(list_ok(plan->cells) && list_ok(plan->ghost) && list_ok(plan->boundary),
-                   "row list arrays are null");
+  PHIFEM_CHECK_ARG(list_ok(plan->cells) && list_ok(plan->surface), "row list arrays are null");
   PHIFEM_CHECK_ARG(plan->max_row_nnz > 0 && plan->max_row_nnz <= 255, "plan.max_row_nnz out of range");
-  PHIFEM_CHECK_ARG(plan->ghost.n_listed == 0 ||
-                       (plan->n_ghost_facets > 0 && plan->n_ghost_facets < (1 << 28) && plan->ghost_macro &&
-                        plan->ghost_work),
-                   "ghost facet arrays (n_ghost_facets < 2^28, ghost_macro, ghost_work)");
+  const int64_t n_once = plan->surface.n_listed ? plan->n_ghost_facets + plan->n_entities : 0;
+  PHIFEM_CHECK_ARG(plan->surface.n_listed == 0 ||
+                       (n_once > 0 && n_once < (1 << 28) && plan->surface_work &&
+                        (plan->n_ghost_facets == 0 || plan->ghost_macro) &&
+                        (plan->n_entities == 0 || plan->entity_macro)),
+                   "surface arrays (n_ghost_facets + n_entities < 2^28, ghost_macro, entity_macro, surface_work)");
   const size_t smem = (size_t)plan->max_row_nnz * kRowsBlock * sizeof(double);
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t err = cudaSuccess;
@@ -556,22 +607,34 @@ extern "C" int phifem_assemble_rows_p1(const phifem_mesh* mesh, const double* ph
     const int64_t grid = (rl.n_listed + kRowsBlock - 1) / kRowsBlock;
     if (err == cudaSuccess)
       kernel<<<(unsigned)grid, kRowsBlock, smem, st>>>(mesh->x, phi, f, sigma, plan->indptr, plan->indices,
-                                                       rl, plan->ghost_work, data, b);
+                                                       rl, plan->surface_work, data, b);
   };
-  const int64_t ng = plan->ghost.n_listed ? plan->n_ghost_facets : 0;
-  const unsigned ggrid = (unsigned)((ng + kRowsBlock - 1) / kRowsBlock);
+  // The facet-once kernel (latency-bound gathers, 2 % of the work) is forked onto a side stream so that it shares
+  // the SMs with the fp64-bound cell pass; the surface row pass waits for both.
+  SideStream& ss = side_stream();
+  const bool fork = n_once > 0 && plan->cells.n_listed > 0 && ss.ok;
+  cudaStream_t once_stream = fork ? ss.stream : st;
+  auto once = [&](auto kernel) {
+    if (n_once == 0) return;
+    if (fork) {
+      cudaEventRecord(ss.fork, st);
+      cudaStreamWaitEvent(ss.stream, ss.fork, 0);
+    }
+    kernel<<<(unsigned)((n_once + kRowsBlock - 1) / kRowsBlock), kRowsBlock, 0, once_stream>>>(
+        mesh->x, phi, sigma, plan->ghost_macro, plan->n_ghost_facets, plan->entity_macro, plan->n_entities,
+        plan->surface_work);
+    if (fork) cudaEventRecord(ss.join, ss.stream);
+  };
   if (mesh->cell_type == PHIFEM_TRIANGLE) {
+    once(k_surface_once_p1<2>);
     launch(k_assemble_rows_p1<2, kCells>, plan->cells);
-    if (ng) k_ghost_facets_p1<2><<<ggrid, kRowsBlock, 0, st>>>(mesh->x, phi, sigma, plan->ghost_macro, ng,
-                                                              plan->ghost_work);
-    launch(k_assemble_rows_p1<2, kGhost>, plan->ghost);
-    launch(k_assemble_rows_p1<2, kBoundary>, plan->boundary);
+    if (fork) cudaStreamWaitEvent(st, ss.join, 0);
+    launch(k_assemble_rows_p1<2, kSurface>, plan->surface);
   } else {
+    once(k_surface_once_p1<3>);
     launch(k_assemble_rows_p1<3, kCells>, plan->cells);
-    if (ng) k_ghost_facets_p1<3><<<ggrid, kRowsBlock, 0, st>>>(mesh->x, phi, sigma, plan->ghost_macro, ng,
-                                                              plan->ghost_work);
-    launch(k_assemble_rows_p1<3, kGhost>, plan->ghost);
-    launch(k_assemble_rows_p1<3, kBoundary>, plan->boundary);
+    if (fork) cudaStreamWaitEvent(st, ss.join, 0);
+    launch(k_assemble_rows_p1<3, kSurface>, plan->surface);
   }
   if (err != cudaSuccess) {
     set_error("phifem_assemble_rows_p1: cannot reserve %zu bytes of shared memory: %s", smem,

@@ -3,9 +3,9 @@
 Turns an `AssemblyPlan` (CSR pattern + entity lists + entity -> CSR-slot maps) into the arrays of
 `phifem_rows_plan` (include/phifem_b200.h): for every row with pattern entries, the list of entities
 touching its vertex, each entity written as the positions -- inside the row's own column list -- of its
-other vertices.  Three record kinds (cells, ghost-penalty facets, one-sided facets), each stored as
-sliced ELLPACK over groups of 32 consecutive listed rows so that a warp reads one coalesced 128-byte
-line per step.
+other vertices.  Two lists -- cells (every pattern row) and surface (ghost-penalty facets and one-sided
+entities, rows near the surface only) -- each stored as sliced ELLPACK over groups of 32 consecutive listed rows
+so that a warp reads one coalesced 128-byte line per step.
 
 Sort/scatter plumbing written with torch ops; runs on the device of the mesh (CPU tensors work too,
 which is how the CPU tests check it against the oracle).
@@ -195,13 +195,13 @@ class RowsPlan:
             rec_rows, words = torch.zeros(0, **i64), torch.zeros((0, 2), **i64)
             self.ghost_macro = torch.zeros((0, nv + 1), dtype=torch.int32, device=dev)
         self.n_ghost_facets = ng
-        # facet-once scratch of the ghost-penalty pass (8 doubles = 64 bytes per facet), rewritten by every assembly
-        self.ghost_work = torch.empty((max(ng, 1), 8), dtype=torch.float64, device=dev)
-        rec_rows, words = owned(rec_rows, words)
-        self.ghost = RowList(surface_ordered(rec_rows), dslot, indptr, rec_rows, words, n, balance=True)
+        ghost_rows, ghost_words = owned(rec_rows, words)
 
         # ---- one-sided facets: one record per facet vertex of each (cell, local facet) entity --------------
         ne = int(plan.entities.shape[0])
+        self.n_entities = ne
+        if ng + ne >= 2 ** 28:
+            raise NotImplementedError("row-gather plan: more than 2^28 surface entities")
         if ne:
             ec = plan.entities[:, 0].long()
             eo = plan.entities[:, 1].long()
@@ -211,55 +211,65 @@ class RowsPlan:
             loc = torch.arange(nv, **i64)[None, :].expand(ne, nv)
             fac = loc[loc != eo[:, None]].reshape(ne, d)                # local ids of the facet vertices
             rec_rows, words = [], []
-            for t in range(d):                      # t-th facet vertex = t-th local vertex != o
+            for t in range(d):                      # the row's vertex = t-th facet vertex
                 i = fac[:, t]
-                rest = fac[:, [u for u in range(d) if u != t]]
+                rest = fac[:, [(t + u) % d for u in range(1, d)]]       # the others, rotated: (t + 1) % d, ...
                 oth = torch.cat([eo[:, None], rest], dim=1)             # opposite vertex first
                 row = ev[ar, i]
                 pos = bs[ar[:, None], i[:, None], oth] - indptr[row][:, None]
-                words.append(_pack_bytes(pos))
+                words.append(torch.stack([_pack_bytes(pos), (ng + ar) | (t << 28) | (1 << 31)], dim=1))
                 rec_rows.append(row)
             rec_rows = torch.stack(rec_rows, dim=1).reshape(-1)
-            words = torch.stack(words, dim=1).reshape(-1, 1)
+            words = torch.stack(words, dim=1).reshape(-1, 2)
+            # vertex ids [facet vertices in ascending local order, opposite vertex]
+            self.entity_macro = torch.cat([ev.gather(1, fac), ev.gather(1, eo[:, None])], dim=1) \
+                .to(torch.int32).contiguous()
         else:
-            rec_rows, words = torch.zeros(0, **i64), torch.zeros((0, 1), **i64)
-        rec_rows, words = owned(rec_rows, words)
-        self.boundary = RowList(surface_ordered(rec_rows), dslot, indptr, rec_rows, words, n, balance=True)
+            rec_rows, words = torch.zeros(0, **i64), torch.zeros((0, 2), **i64)
+            self.entity_macro = torch.zeros((0, nv), dtype=torch.int32, device=dev)
+        ent_rows, ent_words = owned(rec_rows, words)
+        # one surface list: a row's ghost-penalty records first, then its one-sided records
+        rec_rows = torch.cat([ghost_rows, ent_rows])
+        words = torch.cat([ghost_words, ent_words])
+        self.n_ghost_records, self.n_entity_records = int(ghost_rows.numel()), int(ent_rows.numel())
+        self.surface = RowList(surface_ordered(rec_rows), dslot, indptr, rec_rows, words, n, balance=True)
+        # facet-once scratch of the surface pass (8 doubles = 64 bytes per ghost facet / entity), rewritten by
+        # every assembly
+        self.surface_work = torch.empty((max(ng + ne, 1), 8), dtype=torch.float64, device=dev)
         self._c = None
 
     def c_struct(self, passes=None):
-        """`passes`: subset of ("cells", "ghost", "boundary") to run (bench.py times them one by one);
-        the other lists are passed empty."""
+        """`passes`: subset of ("cells", "surface") to run (bench.py times them one by one); the other list is
+        passed empty."""
         if passes is not None:
             p = _lib.ptr
             empty = _lib.CRowList(0, None, None, None, None)
-            lists = [getattr(self, nm).c_struct() if nm in passes else empty
-                     for nm in ("cells", "ghost", "boundary")]
+            lists = [getattr(self, nm).c_struct() if nm in passes else empty for nm in ("cells", "surface")]
             return _lib.CRowsPlan(p(self.plan.indptr), p(self.plan.indices), self.max_row_nnz, 0, *lists,
-                                  *self._ghost_fields())
+                                  *self._surface_fields())
         if self._c is None:
             p = _lib.ptr
             pl = self.plan
             self._c = _lib.CRowsPlan(p(pl.indptr), p(pl.indices), self.max_row_nnz, 0,
-                                     self.cells.c_struct(), self.ghost.c_struct(), self.boundary.c_struct(),
-                                     *self._ghost_fields())
+                                     self.cells.c_struct(), self.surface.c_struct(), *self._surface_fields())
         return self._c
 
-    def _ghost_fields(self):
-        """Trailing fields of phifem_rows_plan: the ghost facet arrays."""
-        if self.ghost_work.device.type != "cuda":
-            return 0, None, None
+    def _surface_fields(self):
+        """Trailing fields of phifem_rows_plan: ghost facet / entity vertex lists and the facet-once scratch."""
+        if self.surface_work.device.type != "cuda":
+            return 0, None, 0, None, None
         return (self.n_ghost_facets, _lib.ptr(self.ghost_macro) if self.n_ghost_facets else None,
-                _lib.ptr(self.ghost_work))
+                self.n_entities, _lib.ptr(self.entity_macro) if self.n_entities else None,
+                _lib.ptr(self.surface_work))
 
     def index_bytes(self):
         """Bytes of plan arrays one numeric pass streams besides the CSR pattern itself."""
-        return (self.cells.nbytes() + self.ghost.nbytes() + self.boundary.nbytes()
-                + self.ghost_macro.numel() * 4 + self.ghost_work.numel() * 8)
+        return (self.cells.nbytes() + self.surface.nbytes() + self.ghost_macro.numel() * 4
+                + self.entity_macro.numel() * 4 + self.surface_work.numel() * 8)
 
 
 def assemble_rows_into(rplan, phi, f, sigma, data, b, passes=None):
-    """Numeric phase on the current stream (cell pass, ghost-penalty pass, one-sided pass).  `data` needs
+    """Numeric phase on the current stream (facet-once kernel, cell pass, surface pass).  `data` needs
     no zero-fill; `b` must have been zeroed once (rows without pattern entries are never written)."""
     mesh = rplan.plan.mesh
     _lib.require_cuda(mesh)

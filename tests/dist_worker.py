@@ -46,7 +46,7 @@ def main():
         # every record of the row-gather plan belongs to an owned row
         rp = plan.rowsplan
         owned = (prob.vertex_owner == rank).numpy()
-        for rl in (rp.cells, rp.ghost, rp.boundary):
+        for rl in (rp.cells, rp.surface):
             assert owned[rl.rows.numpy()].all()
     else:
         indptr, indices = plan.indptr, plan.indices

@@ -48,7 +48,7 @@ def main():
     rows, indptr, cols, data, b = prob.owned_csr()
     rp = prob.plan.rowsplan
     owned = prob.row_mask.numpy()
-    for rl in (rp.cells, rp.ghost, rp.boundary):          # every record belongs to an owned row
+    for rl in (rp.cells, rp.surface):          # every record belongs to an owned row
         assert owned[rl.rows.numpy()].all()
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), rows=rows.numpy(), indptr=indptr.numpy(),
              cols=cols.numpy(), data=data.numpy(), b=b.numpy(),

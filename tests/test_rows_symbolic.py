@@ -69,7 +69,27 @@ def _emulate(rp, m, x, cells, phi, f, out, sigma):
         assert len(by_set) == len(ghost)
     seen = set()
     gm = rp.ghost_macro.numpy()
-    for r, dp, w in _records(rp.ghost, indptr, indices):
+    ents = plan.entities.numpy()
+    if len(ents):
+        Bt = OA.boundary_tensors_closed_form(x, cells, phi, ents)
+        em = rp.entity_macro.numpy()
+    seen_b = set()
+    for r, dp, w in _records(rp.surface, indptr, indices):
+        if int(w[1]) >> 31:          # one-sided entity e, the row's vertex = facet vertex t
+            e, t = (int(w[1]) & 0x0FFFFFFF) - len(ghost), (int(w[1]) >> 28) & 7
+            pos = [(int(w[0]) >> (8 * j)) & 0xFF for j in range(d)]
+            others = [int(indices[indptr[r] + p]) for p in pos]
+            c, o = int(ents[e, 0]), int(ents[e, 1])
+            fac = [int(v) for k, v in enumerate(cells[c]) if k != o]         # facet vertices, ascending local order
+            assert [int(v) for v in em[e]] == fac + [int(cells[c][o])]
+            assert fac[t] == r and others == [int(cells[c][o])] + [fac[(t + u) % d] for u in range(1, d)]
+            assert (r, e) not in seen_b
+            seen_b.add((r, e))
+            i = list(cells[c]).index(r)
+            data[indptr[r] + dp] += Bt[e, i, i]
+            for p, v in zip(pos, others):
+                data[indptr[r] + p] += Bt[e, i, list(cells[c]).index(v)]
+            continue
         e, a = int(w[1]) & 0x0FFFFFFF, int(w[1]) >> 28       # ghost facet index, macro index of the row's vertex
         pos = [(int(w[0]) >> (8 * j)) & 0xFF for j in range(nv)]
         others = [int(indices[indptr[r] + p]) for p in pos]
@@ -89,26 +109,8 @@ def _emulate(rp, m, x, cells, phi, f, out, sigma):
             csel = [k for k, v in enumerate(mv) if v == col]
             data[indptr[r] + p] += G8[e][np.ix_(rsel, csel)].sum()
     assert len(seen) == (d + 2) * len(ghost)
-
-    # one-sided facets
-    ents = plan.entities.numpy()
-    if len(ents):
-        Bt = OA.boundary_tensors_closed_form(x, cells, phi, ents)
-        ent_of = {(int(c), int(o)): e for e, (c, o) in enumerate(ents)}
-    seen = set()
-    for r, dp, w in _records(rp.boundary, indptr, indices):
-        pos = [(int(w[0]) >> (8 * j)) & 0xFF for j in range(d)]
-        others = [indices[indptr[r] + p] for p in pos]
-        c = cell_of[tuple(sorted([r] + others))]
-        o = list(cells[c]).index(others[0])
-        e = ent_of[(c, o)]
-        assert (r, e) not in seen
-        seen.add((r, e))
-        i = list(cells[c]).index(r)
-        data[indptr[r] + dp] += Bt[e, i, i]
-        for p, v in zip(pos, others):
-            data[indptr[r] + p] += Bt[e, i, list(cells[c]).index(v)]
-    assert len(seen) == d * len(ents)
+    assert len(seen_b) == d * len(ents)
+    assert rp.n_ghost_records == len(seen) and rp.n_entity_records == len(seen_b)
     return data, b
 
 
@@ -138,12 +140,11 @@ def test_rows_plan_reproduces_the_oracle_operator(d, n, order):
     nnz_row = np.diff(plan.indptr.numpy())
     assert sorted(rows) == list(np.nonzero(nnz_row > 0)[0])
     assert rp.max_row_nnz == nnz_row.max()
-    assert 0 < rp.boundary.n_listed <= rp.ghost.n_listed <= rp.cells.n_listed
+    assert 0 < rp.surface.n_listed <= rp.cells.n_listed
     if order == "natural":
         assert np.all(np.diff(rows) > 0)
-    for rl in (rp.ghost, rp.boundary):      # surface lists: rows sorted by record count, descending
-        cnt = np.diff(rl.ptr.numpy())
-        assert np.all(np.diff(cnt) <= 0) and rl.padding() < 0.5
+    cnt = np.diff(rp.surface.ptr.numpy())   # surface list: rows sorted by record count, descending (one chunk here)
+    assert np.all(np.diff(cnt) <= 0) and rp.surface.padding() < 0.5
     data, b = _emulate(rp, m, x, cells, phi, f, out, 1.0)
     ip, ix, want, wb = OA.assemble_strong_dirichlet(x, cells, cells, len(x), phi, f, out["cell_tags"],
                                                     out["facet_tags"], out["c2f"], out["f2c"],
