@@ -310,12 +310,12 @@ def run_ours(args):
         dist.barrier()
     torch.cuda.synchronize()
     sampler.start()
-    # an NVML query takes milliseconds, a step two: keep the device under the same load until the sampler has
-    # seen it (untimed steps), then time exactly `steps` steps with the sampler still running
-    t_load = time.perf_counter()
-    while len(sampler.samples) < 3 and time.perf_counter() - t_load < 0.5 and sampler.nv is not None:
+    # an NVML query takes milliseconds, a step two: keep the device under the same load for a fixed number of
+    # untimed steps (the same on every rank: a step holds a collective) so that the sampler has seen it, then time
+    # exactly `steps` steps with the sampler still running
+    for _ in range(15):
         step()
-        torch.cuda.synchronize()
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
