@@ -394,7 +394,7 @@ def run_ours(args):
                                 "tag_facets": ab["tags_facets"] / per["tag_facets"] / 1e6,
                                 "assemble_cells": asm_bytes / per["assemble_cells"] / 1e6}}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(traffic_file):
+    if os.path.exists(traffic_file) and args.config == "3d-p1" and n == CONFIGS["3d-p1"][0] and world == 1:
         with open(traffic_file) as fh:
             roofline["traffic"] = json.load(fh).get(dominant)
 
