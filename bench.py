@@ -289,12 +289,13 @@ def run_ours(args):
                 events[k].record()
                 k += 1
         mark()
-        mesh_scripts.classify_cells(mesh, dls, ws)
-        if problem is not None:   # "any exterior cell" must be global before the facet algebra runs
-            dist.all_reduce(ws.counters[_lib.CNT_EXTERIOR:_lib.CNT_EXTERIOR + 1])
-        mark()
-        mesh_scripts.classify_facets(mesh, dls, ws)
-        mark()
+        if problem is not None:   # the all-reduce of "any exterior cell" overlaps the interior-facet kernel
+            problem.classify(dls, ws, mark=mark)
+        else:
+            mesh_scripts.classify_cells(mesh, dls, ws)
+            mark()
+            mesh_scripts.classify_facets(mesh, dls, ws)
+            mark()
         if problem is not None:
             problem.assemble(1.0, marks=mark if split else None)
         else:

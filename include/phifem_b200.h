@@ -114,6 +114,15 @@ int phifem_tag_cells(const phifem_mesh* mesh, const phifem_levelset* ls, int32_t
 int phifem_tag_facets(const phifem_mesh* mesh, const phifem_levelset* ls, const int8_t* cell_tags8,
                       int32_t* facet_tags, int8_t* facet_tags8, int64_t* counters, void* stream);
 
+/* The same in two separately launchable phases, for callers that must make `counters[PHIFEM_CNT_EXTERIOR]` global
+ * (an all-reduce across ranks) between the cell and facet kernels: the tags of interior facets do not depend on that
+ * flag, so PHIFEM_FACETS_INTERIOR can run while the reduction is in flight and PHIFEM_FACETS_BOUNDARY (the mesh-boundary
+ * facets, which do read it; needs mesh.boundary_facets) after it.  phases = both bits == phifem_tag_facets. */
+enum { PHIFEM_FACETS_INTERIOR = 1, PHIFEM_FACETS_BOUNDARY = 2 };
+int phifem_tag_facets_phase(const phifem_mesh* mesh, const phifem_levelset* ls, const int8_t* cell_tags8,
+                            int32_t* facet_tags, int8_t* facet_tags8, int64_t* counters, int32_t phases,
+                            void* stream);
+
 /* Candidate records of `_compute_integration_entities` (:137-192): for every facet with
  * facet_tags == facet_tag and every adjacent cell whose tag bit is set in cell_mask
  * (bit t set => cells tagged t allowed), append (key = 2*facet + column, cell, local facet) to

@@ -76,6 +76,8 @@ _SIGNATURES = {
                                         ctypes.c_int32, _vp, _vp, _vp, _vp, _vp]),
     "phifem_tag_facets": (ctypes.c_int, [ctypes.POINTER(CMesh), ctypes.POINTER(CLevelset), _vp, _vp,
                                          _vp, _vp, _vp]),
+    "phifem_tag_facets_phase": (ctypes.c_int, [ctypes.POINTER(CMesh), ctypes.POINTER(CLevelset), _vp, _vp,
+                                               _vp, _vp, ctypes.c_int32, _vp]),
     "phifem_entity_records": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, ctypes.c_int32,
                                              ctypes.c_uint32, _vp, ctypes.c_int64, _vp, _vp]),
     "phifem_assemble_cells_p1": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, _vp, _vp,

@@ -757,6 +757,13 @@ SideStream& side_stream() {
 extern "C" int phifem_tag_facets(const phifem_mesh* mesh, const phifem_levelset* ls,
                                  const int8_t* cell_tags8, int32_t* facet_tags, int8_t* facet_tags8,
                                  int64_t* counters, void* stream) {
+  return phifem_tag_facets_phase(mesh, ls, cell_tags8, facet_tags, facet_tags8, counters,
+                                 PHIFEM_FACETS_INTERIOR | PHIFEM_FACETS_BOUNDARY, stream);
+}
+
+extern "C" int phifem_tag_facets_phase(const phifem_mesh* mesh, const phifem_levelset* ls,
+                                       const int8_t* cell_tags8, int32_t* facet_tags, int8_t* facet_tags8,
+                                       int64_t* counters, int32_t phases, void* stream) {
   if (int rc = check_mesh(mesh, true)) return rc;
   if (int rc = check_levelset(mesh, ls, true)) return rc;
   PHIFEM_CHECK_ARG(cell_tags8 && facet_tags && facet_tags8 && counters, "null pointer");
@@ -764,9 +771,22 @@ extern "C" int phifem_tag_facets(const phifem_mesh* mesh, const phifem_levelset*
   const int64_t tiles = (mesh->n_facets + kBlock * kUnroll - 1) / (kBlock * kUnroll);
   cudaStream_t st = (cudaStream_t)stream;
   const bool two_pass = mesh->boundary_facets != nullptr;
+  const bool both = (phases & 3) == 3;
+  PHIFEM_CHECK_ARG((phases & 3) != 0, "phases selects nothing");
+  PHIFEM_CHECK_ARG(both || two_pass, "phases need mesh.boundary_facets");
   dispatch_cell_type(mesh->cell_type, [&](auto c) {
     constexpr int CT = decltype(c)::value;
-    if (two_pass) {
+    if (!both) {  // one phase alone, on the caller's stream (the caller orders them, e.g. around an all-reduce)
+      if (phases & PHIFEM_FACETS_INTERIOR) {
+        const int grid = persistent_grid(k_tag_facets<CT, false>, kBlock, tiles);
+        k_tag_facets<CT, false><<<grid, kBlock, 0, st>>>(*mesh, *ls, cell_tags8, facet_tags, facet_tags8,
+                                                         counters);
+      } else if (mesh->n_boundary_facets > 0) {
+        const int g2 = (int)((mesh->n_boundary_facets + kBlock - 1) / kBlock);
+        k_tag_boundary_facets<CT><<<g2, kBlock, 0, st>>>(*mesh, *ls, cell_tags8, facet_tags, facet_tags8,
+                                                         counters);
+      }
+    } else if (two_pass) {
       // The mesh-boundary facets (a chain of dependent gathers over few threads: latency-bound) run on a
       // side stream forked from / joined to the caller's stream, concurrently with the streaming kernel;
       // the two kernels write disjoint facets.

@@ -142,13 +142,10 @@ class SlabProblem:
         return synthetic.ball_source(frac)
 
     # ---- tags --------------------------------------------------------------------------------------
-    def classify(self, dls, ws):
-        """Cells, 8-byte all-reduce of the exterior-cell count, facets (all on the current stream)."""
-        mesh_scripts.classify_cells(self.mesh, dls, ws)
-        if self.world > 1:
-            dist.all_reduce(ws.counters[_lib.CNT_EXTERIOR:_lib.CNT_EXTERIOR + 1], group=self.group)
-        mesh_scripts.classify_facets(self.mesh, dls, ws)
-        return ws
+    def classify(self, dls, ws, mark=None):
+        """Cells, interior facets overlapped with the 8-byte all-reduce of the exterior-cell count, mesh-boundary
+        facets (all on the current stream; mesh_scripts.classify_sharded)."""
+        return mesh_scripts.classify_sharded(self.mesh, dls, ws, group=self.group, world=self.world, mark=mark)
 
     # ---- symbolic phase ----------------------------------------------------------------------------
     def build_plan(self, cell_tags8, facet_tags8):

@@ -126,11 +126,35 @@ def classify_cells(mesh, dls, ws, single_layer_cut=False, exact_zero_den=False):
         _lib.ptr(ws.cell_tags8), _lib.ptr(ws.vertex_scratch), _lib.ptr(ws.counters), _lib.stream()))
 
 
-def classify_facets(mesh, dls, ws):
-    """Facet tags from the cell tags of `ws` on the current stream (no host synchronisation)."""
-    _lib.check(_lib.load().phifem_tag_facets(
+FACETS_INTERIOR, FACETS_BOUNDARY = 1, 2
+
+
+def classify_facets(mesh, dls, ws, phases=FACETS_INTERIOR | FACETS_BOUNDARY):
+    """Facet tags from the cell tags of `ws` on the current stream (no host synchronisation).  `phases`: run only
+    the interior facets (independent of the global "any exterior cell" flag) or only the mesh-boundary facets
+    (which read it) -- the sharded classifiers put their all-reduce between the two."""
+    _lib.check(_lib.load().phifem_tag_facets_phase(
         _lib.c_mesh(mesh), dls.c, _lib.ptr(ws.cell_tags8), _lib.ptr(ws.facet_tags),
-        _lib.ptr(ws.facet_tags8), _lib.ptr(ws.counters), _lib.stream()))
+        _lib.ptr(ws.facet_tags8), _lib.ptr(ws.counters), int(phases), _lib.stream()))
+
+
+def classify_sharded(mesh, dls, ws, group=None, world=1, mark=None):
+    """Cells, then the interior facets WHILE the 8-byte all-reduce of the exterior-cell count is in flight, then
+    the mesh-boundary facets (reference :469-474 makes their tags depend on the global flag).  `mark` (optional
+    callable) is invoked after the cell kernel and at the end (bench.py records CUDA events there)."""
+    import torch.distributed as dist
+    mark = mark or (lambda: None)
+    classify_cells(mesh, dls, ws)
+    mark()
+    if world > 1:
+        work = dist.all_reduce(ws.counters[_lib.CNT_EXTERIOR:_lib.CNT_EXTERIOR + 1], group=group, async_op=True)
+        classify_facets(mesh, dls, ws, FACETS_INTERIOR)
+        work.wait()
+        classify_facets(mesh, dls, ws, FACETS_BOUNDARY)
+    else:
+        classify_facets(mesh, dls, ws)
+    mark()
+    return ws
 
 
 def classify(mesh, dls, single_layer_cut=False, ws=None, exact_zero_den=False):
