@@ -103,6 +103,9 @@ class AssemblyPlan:
         self.indptr[1:] = torch.cumsum(counts, dim=0)
         self.indptr = self.indptr.to(torch.int32).contiguous()
         self.nnz = int(uniq.numel())
+        if self.nnz >= 2 ** 31:
+            raise NotImplementedError("CSR pattern with %d entries: indptr / slot maps are int32 (PETSc's default "
+                                      "index width too); shard the mesh (phifem_b200/partition.py)" % self.nnz)
         self.blocked, self.rowsplan, self.method = None, None, "atomic"
         if method == "rows" and self.nnz > 0:
             from . import rows as rows_mod

@@ -82,6 +82,8 @@ class PkAssemblyPlan:
         indptr[1:] = torch.cumsum(counts, dim=0)
         self.indptr = indptr.to(torch.int32).contiguous()
         self.nnz = int(uniq.numel())
+        if self.nnz >= 2 ** 31:
+            raise NotImplementedError("CSR pattern with %d entries: indptr / slot maps are int32" % self.nnz)
 
         # quadrature tables and C structs (kept alive with the plan)
         d = mesh.gdim

@@ -581,9 +581,9 @@ extern "C" int phifem_assemble_cells_p1(const phifem_mesh* mesh, const double* p
                                         int64_t n_active, const int32_t* slots, double sigma,
                                         double* data, double* b, void* stream) {
   if (int rc = check_simplex_mesh(mesh)) return rc;
+  if (n_active == 0) return PHIFEM_OK;  // nothing to add (an empty pattern has no storage to point at)
   PHIFEM_CHECK_ARG(phi && f && cell_tags8 && data && b, "null pointer");
-  PHIFEM_CHECK_ARG(n_active == 0 || (active && slots), "null active / slots");
-  if (n_active == 0) return PHIFEM_OK;
+  PHIFEM_CHECK_ARG(active && slots, "null active / slots");
   const int grid = (int)((n_active + kBlock - 1) / kBlock);
   cudaStream_t st = (cudaStream_t)stream;
   if (mesh->cell_type == PHIFEM_TRIANGLE)
@@ -600,9 +600,9 @@ extern "C" int phifem_assemble_boundary_p1(const phifem_mesh* mesh, const double
                                            const int32_t* entities, int64_t n_entities,
                                            const int32_t* slots, double* data, void* stream) {
   if (int rc = check_simplex_mesh(mesh)) return rc;
-  PHIFEM_CHECK_ARG(phi && data, "null pointer");
-  PHIFEM_CHECK_ARG(n_entities == 0 || (entities && slots), "null entities / slots");
   if (n_entities == 0) return PHIFEM_OK;
+  PHIFEM_CHECK_ARG(phi && data, "null pointer");
+  PHIFEM_CHECK_ARG(entities && slots, "null entities / slots");
   const int grid = (int)((n_entities + kBlock - 1) / kBlock);
   cudaStream_t st = (cudaStream_t)stream;
   if (mesh->cell_type == PHIFEM_TRIANGLE)
@@ -617,9 +617,9 @@ extern "C" int phifem_assemble_ghost_p1(const phifem_mesh* mesh, const double* p
                                         const int32_t* facets, int64_t n_facets, const int32_t* slots,
                                         double sigma, double* data, void* stream) {
   if (int rc = check_simplex_mesh(mesh)) return rc;
-  PHIFEM_CHECK_ARG(phi && data && mesh->c2f && mesh->f2c, "null pointer");
-  PHIFEM_CHECK_ARG(n_facets == 0 || (facets && slots), "null facets / slots");
   if (n_facets == 0) return PHIFEM_OK;
+  PHIFEM_CHECK_ARG(phi && data && mesh->c2f && mesh->f2c, "null pointer");
+  PHIFEM_CHECK_ARG(facets && slots, "null facets / slots");
   const int grid = (int)((n_facets + kBlock - 1) / kBlock);
   cudaStream_t st = (cudaStream_t)stream;
   if (mesh->cell_type == PHIFEM_TRIANGLE)
@@ -634,7 +634,9 @@ extern "C" int phifem_assemble_blocked_p1(const phifem_mesh* mesh, const double*
                                           double sigma, const phifem_blocked_plan* plan, double* data,
                                           double* b, void* stream) {
   if (int rc = check_simplex_mesh(mesh)) return rc;
-  PHIFEM_CHECK_ARG(phi && f && plan && data && b, "null pointer");
+  PHIFEM_CHECK_ARG(plan != nullptr, "plan is null");
+  if (plan->n_blocks == 0) return PHIFEM_OK;
+  PHIFEM_CHECK_ARG(phi && f && data && b, "null pointer");
   PHIFEM_CHECK_ARG(plan->n_blocks == 0 || (plan->block_desc && plan->seg_start && plan->seg_dest),
                    "plan arrays are null");
   PHIFEM_CHECK_ARG(plan->n_ghost_inst == 0 || (mesh->c2f && mesh->f2c), "ghost facets need c2f / f2c");

@@ -731,9 +731,9 @@ extern "C" int phifem_assemble_cells_pk(const phifem_mesh* mesh, const phifem_pk
   PHIFEM_CHECK_ARG(quad != nullptr, "quadrature is null");
   if (int rc = check_pk(mesh, space_w, space_phi, quad->cell_points, quad->cell_weights, quad->n_cell_points))
     return rc;
-  PHIFEM_CHECK_ARG(phi && f && cell_tags8 && data && b, "null pointer");
-  PHIFEM_CHECK_ARG(n_active == 0 || (active && slots), "null active / slots");
   if (n_active == 0) return PHIFEM_OK;
+  PHIFEM_CHECK_ARG(phi && f && cell_tags8 && data && b, "null pointer");
+  PHIFEM_CHECK_ARG(active && slots, "null active / slots");
   cudaStream_t st = (cudaStream_t)stream;
   dispatch(mesh->cell_type, space_w->degree, space_phi->degree, [&](auto d, auto kw, auto kp) {
     constexpr int D = decltype(d)::value, KW = decltype(kw)::value, KP = decltype(kp)::value;
@@ -753,9 +753,9 @@ extern "C" int phifem_assemble_boundary_pk(const phifem_mesh* mesh, const phifem
   PHIFEM_CHECK_ARG(quad != nullptr, "quadrature is null");
   if (int rc = check_pk(mesh, space_w, space_phi, quad->facet_points, quad->facet_weights, quad->n_facet_points))
     return rc;
-  PHIFEM_CHECK_ARG(phi && data, "null pointer");
-  PHIFEM_CHECK_ARG(n_entities == 0 || (entities && slots), "null entities / slots");
   if (n_entities == 0) return PHIFEM_OK;
+  PHIFEM_CHECK_ARG(phi && data, "null pointer");
+  PHIFEM_CHECK_ARG(entities && slots, "null entities / slots");
   cudaStream_t st = (cudaStream_t)stream;
   dispatch(mesh->cell_type, space_w->degree, space_phi->degree, [&](auto d, auto kw, auto kp) {
     constexpr int D = decltype(d)::value, KW = decltype(kw)::value, KP = decltype(kp)::value;
@@ -775,9 +775,9 @@ extern "C" int phifem_assemble_ghost_pk(const phifem_mesh* mesh, const phifem_pk
   PHIFEM_CHECK_ARG(quad != nullptr, "quadrature is null");
   if (int rc = check_pk(mesh, space_w, space_phi, quad->facet_points, quad->facet_weights, quad->n_facet_points))
     return rc;
-  PHIFEM_CHECK_ARG(phi && data && mesh->c2f && mesh->f2c, "null pointer");
-  PHIFEM_CHECK_ARG(n_facets == 0 || (facets && slots), "null facets / slots");
   if (n_facets == 0) return PHIFEM_OK;
+  PHIFEM_CHECK_ARG(phi && data && mesh->c2f && mesh->f2c, "null pointer");
+  PHIFEM_CHECK_ARG(facets && slots, "null facets / slots");
   cudaStream_t st = (cudaStream_t)stream;
   dispatch(mesh->cell_type, space_w->degree, space_phi->degree, [&](auto d, auto kw, auto kp) {
     constexpr int D = decltype(d)::value, KW = decltype(kw)::value, KP = decltype(kp)::value;
@@ -800,9 +800,9 @@ extern "C" int phifem_assemble_weak_cells_pk(const phifem_mesh* mesh, const phif
   PHIFEM_CHECK_ARG(quad != nullptr, "quadrature is null");
   if (int rc = check_pk(mesh, space_w, space_phi, quad->cell_points, quad->cell_weights, quad->n_cell_points))
     return rc;
-  PHIFEM_CHECK_ARG(phi && f && u_d && cell_tags8 && data && b && mixed_dofmap, "null pointer");
-  PHIFEM_CHECK_ARG(n_active == 0 || (active && slots), "null active / slots");
   if (n_active == 0) return PHIFEM_OK;
+  PHIFEM_CHECK_ARG(phi && f && u_d && cell_tags8 && data && b && mixed_dofmap, "null pointer");
+  PHIFEM_CHECK_ARG(active && slots, "null active / slots");
   cudaStream_t st = (cudaStream_t)stream;
   dispatch(mesh->cell_type, space_w->degree, space_phi->degree, [&](auto d, auto kw, auto kp) {
     constexpr int D = decltype(d)::value, KW = decltype(kw)::value, KP = decltype(kp)::value;
@@ -822,9 +822,9 @@ extern "C" int phifem_assemble_weak_boundary_pk(const phifem_mesh* mesh, const p
   PHIFEM_CHECK_ARG(quad != nullptr, "quadrature is null");
   if (int rc = check_pk(mesh, space_w, space_w, quad->facet_points, quad->facet_weights, quad->n_facet_points))
     return rc;
-  PHIFEM_CHECK_ARG(data != nullptr, "null pointer");
-  PHIFEM_CHECK_ARG(n_entities == 0 || (entities && slots), "null entities / slots");
   if (n_entities == 0) return PHIFEM_OK;
+  PHIFEM_CHECK_ARG(data != nullptr, "null pointer");
+  PHIFEM_CHECK_ARG(entities && slots, "null entities / slots");
   cudaStream_t st = (cudaStream_t)stream;
   dispatch(mesh->cell_type, space_w->degree, 1, [&](auto d, auto kw, auto) {
     constexpr int D = decltype(d)::value, KW = decltype(kw)::value;
@@ -843,9 +843,9 @@ extern "C" int phifem_assemble_weak_ghost_pk(const phifem_mesh* mesh, const phif
   PHIFEM_CHECK_ARG(quad != nullptr, "quadrature is null");
   if (int rc = check_pk(mesh, space_w, space_w, quad->facet_points, quad->facet_weights, quad->n_facet_points))
     return rc;
-  PHIFEM_CHECK_ARG(data && mesh->c2f && mesh->f2c, "null pointer");
-  PHIFEM_CHECK_ARG(n_facets == 0 || (facets && slots), "null facets / slots");
   if (n_facets == 0) return PHIFEM_OK;
+  PHIFEM_CHECK_ARG(data && mesh->c2f && mesh->f2c, "null pointer");
+  PHIFEM_CHECK_ARG(facets && slots, "null facets / slots");
   cudaStream_t st = (cudaStream_t)stream;
   dispatch(mesh->cell_type, space_w->degree, 1, [&](auto d, auto kw, auto) {
     constexpr int D = decltype(d)::value, KW = decltype(kw)::value;

@@ -586,8 +586,9 @@ extern "C" int phifem_assemble_rows_p1(const phifem_mesh* mesh, const double* ph
     return PHIFEM_ERR_UNSUPPORTED;
   }
   PHIFEM_CHECK_ARG(mesh->gdim == (mesh->cell_type == PHIFEM_TRIANGLE ? 2 : 3), "gdim mismatch");
-  PHIFEM_CHECK_ARG(phi && f && plan && data && b, "null pointer");
+  PHIFEM_CHECK_ARG(plan != nullptr, "plan is null");
   if (plan->cells.n_listed == 0 && plan->surface.n_listed == 0) return PHIFEM_OK;
+  PHIFEM_CHECK_ARG(phi && f && data && b, "null pointer");
   PHIFEM_CHECK_ARG(plan->indptr && plan->indices, "CSR pattern is null");
   PHIFEM_CHECK_ARG(list_ok(plan->cells) && list_ok(plan->surface), "row list arrays are null");
   PHIFEM_CHECK_ARG(plan->max_row_nnz > 0 && plan->max_row_nnz <= 255, "plan.max_row_nnz out of range");

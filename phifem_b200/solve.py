@@ -21,6 +21,8 @@ def spmv(A, x, out=None):
     """y = A x for a `CSRMatrix` on the device (csrc/solve.cu, phifem_csr_spmv)."""
     if out is None:
         out = torch.empty(A.shape[0], dtype=torch.float64, device=x.device)
+    if A.data.numel() == 0:          # empty pattern (no active cell): nothing to point the kernel at
+        return out.zero_()
     _lib.check(_lib.load().phifem_csr_spmv(A.shape[0], _lib.ptr(A.indptr), _lib.ptr(A.indices),
                                            _lib.ptr(A.data), _lib.ptr(x), _lib.ptr(out), _lib.stream()))
     return out
