@@ -394,6 +394,16 @@ def run_ours(args):
                 "kernels_gbs": {"tag_cells": ab["tags_cells"] / per["tag_cells"] / 1e6,
                                 "tag_facets": ab["tags_facets"] / per["tag_facets"] / 1e6,
                                 "assemble_cells": asm_bytes / per["assemble_cells"] / 1e6}}
+    if plan.method == "rows" and mesh.gdim == 3:
+        # the cell pass is bound by fp64 issue, not by HBM: 146 fp64 instructions per (row, cell) record (SASS
+        # count of cell_row<3>) against 64 fp64 lanes per clock per SM
+        lanes = plan.rowsplan.cells.n_records * 146.0
+        peak_lanes = 148 * 64 * (clocks["sm_max_mhz"] or 1965) * 1e6
+        roofline["fp64_issue"] = {"kernel": "k_assemble_rows_p1<cells>", "fp64_instructions_per_record": 146,
+                                  "records": plan.rowsplan.cells.n_records,
+                                  "achieved_tera_lane_instr_per_s": lanes / (per["assemble_cells"] * 1e-3) / 1e12,
+                                  "peak_tera_lane_instr_per_s": peak_lanes / 1e12,
+                                  "frac": lanes / (per["assemble_cells"] * 1e-3) / peak_lanes}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file) and args.config == "3d-p1" and n == CONFIGS["3d-p1"][0] and world == 1:
         with open(traffic_file) as fh:
