@@ -146,6 +146,7 @@ class SlabProblem:
         """Cells, interior facets overlapped with the 8-byte all-reduce of the exterior-cell count, mesh-boundary
         facets (all on the current stream; mesh_scripts.classify_sharded)."""
         return mesh_scripts.classify_sharded(self.mesh, dls, ws, group=self.group, world=self.world, mark=mark)
+        # (`single_layer_cut` needs one more ghost layer: offered by partition.PartitionedProblem, not by the slabs)
 
     # ---- symbolic phase ----------------------------------------------------------------------------
     def build_plan(self, cell_tags8, facet_tags8):

@@ -138,13 +138,13 @@ def classify_facets(mesh, dls, ws, phases=FACETS_INTERIOR | FACETS_BOUNDARY):
         _lib.ptr(ws.facet_tags8), _lib.ptr(ws.counters), int(phases), _lib.stream()))
 
 
-def classify_sharded(mesh, dls, ws, group=None, world=1, mark=None):
+def classify_sharded(mesh, dls, ws, group=None, world=1, mark=None, single_layer_cut=False):
     """Cells, then the interior facets WHILE the 8-byte all-reduce of the exterior-cell count is in flight, then
     the mesh-boundary facets (reference :469-474 makes their tags depend on the global flag).  `mark` (optional
     callable) is invoked after the cell kernel and at the end (bench.py records CUDA events there)."""
     import torch.distributed as dist
     mark = mark or (lambda: None)
-    classify_cells(mesh, dls, ws)
+    classify_cells(mesh, dls, ws, single_layer_cut)
     mark()
     if world > 1:
         work = dist.all_reduce(ws.counters[_lib.CNT_EXTERIOR:_lib.CNT_EXTERIOR + 1], group=group, async_op=True)

@@ -4,8 +4,8 @@
 triangle / tetrahedron mesh the way the north star describes: cells are sorted along a space-filling
 (Morton) curve of their centroids and cut into `world` contiguous ranges; a CSR row (= vertex) is owned by
 the lowest rank owning a cell that touches it; every rank keeps its own range, the cells touching its rows and
-their facet neighbours (the reach of the ghost penalty), classifies them redundantly and runs the row-gather kernels on
-its own rows.  Nothing is exchanged in the numeric phase except the 8-byte "any exterior cell" all-reduce of
+their facet neighbours (the reach of the ghost penalty) -- plus, with `single_layer_cut`, the vertex neighbours of
+all of those --, classifies them redundantly and runs the row-gather kernels on its own rows.  Nothing is exchanged in the numeric phase except the 8-byte "any exterior cell" all-reduce of
 the facet algebra (reference src/phifem/mesh_scripts.py:469-474).
 
 The local mesh keeps the global relative order of cells, vertices and hence facets (order-preserving
@@ -57,7 +57,7 @@ class PartitionedProblem:
     Attributes: `mesh` (local), `phi`, `f` (local vertex values), `global_vertex` / `global_cell` (ids of the
     local entities, ascending), `row_mask` (local vertices whose rows this rank owns), `cell_owned`."""
 
-    def __init__(self, mesh, phi, f, rank, world, group=None, weights=None):
+    def __init__(self, mesh, phi, f, rank, world, group=None, weights=None, single_layer_cut=False):
         if mesh.cell_type not in ("triangle", "tetrahedron"):
             raise NotImplementedError("sharding supports triangles and tetrahedra")
         self.rank, self.world, self.group = rank, world, group
@@ -75,6 +75,13 @@ class PartitionedProblem:
         keep = keep.clone()
         keep[nb[nb >= 0]] = True
         keep |= cell_owner == rank     # plus the rank's own range, so that every cell's tag has one home
+        self.single_layer_cut = bool(single_layer_cut)
+        if single_layer_cut:
+            # `single_layer_cut` (reference :349-358) re-tags a cut cell from the tags of every cell sharing a VERTEX
+            # with it: one more layer, so that the cells above see all their vertex neighbours
+            vmark = torch.zeros(mesh.num_vertices, dtype=torch.bool, device=dev)
+            vmark[cells[keep].reshape(-1)] = True
+            keep = keep | vmark[cells].any(dim=1)
         gc = torch.nonzero(keep).reshape(-1)                      # ascending global cell ids
         gv = torch.unique(cells[gc].reshape(-1))                  # ascending global vertex ids
         relabel = torch.full((mesh.num_vertices,), -1, dtype=torch.int64, device=dev)
@@ -93,7 +100,8 @@ class PartitionedProblem:
     def classify(self, dls, ws, mark=None):
         """Cells, interior facets overlapped with the 8-byte all-reduce of the exterior-cell count, mesh-boundary
         facets (all on the current stream; mesh_scripts.classify_sharded)."""
-        return mesh_scripts.classify_sharded(self.mesh, dls, ws, group=self.group, world=self.world, mark=mark)
+        return mesh_scripts.classify_sharded(self.mesh, dls, ws, group=self.group, world=self.world, mark=mark,
+                                             single_layer_cut=self.single_layer_cut)
 
     # ---- symbolic phase ----------------------------------------------------------------------------
     def build_plan(self, cell_tags8, facet_tags8, entities=None):

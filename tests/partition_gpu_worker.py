@@ -17,6 +17,7 @@ from phifem_b200 import assemble, fem, mesh_scripts, partition, synthetic  # noq
 
 def main():
     kind, n = sys.argv[1], int(sys.argv[2])
+    single = len(sys.argv) > 3 and sys.argv[3] == "single"
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
     torch.cuda.set_device(dev)
@@ -25,8 +26,13 @@ def main():
     gmesh = synthetic.unstructured_variant(gmesh, jitter=0.2, seed=11)
     center = (0.013, -0.021) if kind == "tri" else synthetic.SPHERE_CENTER
     phi = synthetic.sphere_levelset(gmesh.x, center=center, radius=0.61 if kind == "tri" else 0.37)
+    if single:   # a ball around one far vertex: cut cells without interior neighbour (reference :349-358)
+        h = (2.0 if kind == "tri" else 1.0) / n
+        far = torch.argmax(torch.where(phi > 4 * h, phi, torch.full_like(phi, -1.0)))
+        phi = torch.minimum(phi, synthetic.sphere_levelset(gmesh.x, center=tuple(float(v) for v in gmesh.x[far]),
+                                                           radius=0.3 * h))
     f = torch.from_numpy(np.random.default_rng(99).uniform(-1, 1, gmesh.num_vertices)).to(dev)
-    prob = partition.PartitionedProblem(gmesh, phi, f, rank, world)
+    prob = partition.PartitionedProblem(gmesh, phi, f, rank, world, single_layer_cut=single)
     dls = mesh_scripts._DeviceLevelset(prob.mesh, fem.Function(fem.functionspace_p1_device(prob.mesh), prob.phi), 1)
     ws = prob.classify(dls, mesh_scripts.TagWorkspace(prob.mesh))
     prob.build_plan(ws.cell_tags8, ws.facet_tags8)
@@ -43,7 +49,11 @@ def main():
         fn = fem.Function(fem.functionspace_p1_device(gmesh), phi)
         with warnings.catch_warnings():
             warnings.simplefilter("ignore", RuntimeWarning)
-            ct, ft, _, ds, _ = mesh_scripts.compute_tags_measures(gmesh, fn, 1, box_mode=True)
+            ct, ft, _, ds, _ = mesh_scripts.compute_tags_measures(gmesh, fn, 1, box_mode=True,
+                                                                  single_layer_cut=single)
+            if single:
+                ct0 = mesh_scripts.compute_tags_measures(gmesh, fn, 1, box_mode=True)[0]
+                assert int((ct0.values_dev != ct.values_dev).sum()) > 0, "single_layer_cut changed nothing"
         A, bb = assemble.assemble_strong_dirichlet(assemble.build_plan(gmesh, ct, ft, ds(100)), phi, f)
         ip, ix, dd, bb = (A.indptr.cpu().numpy(), A.indices.cpu().numpy(), A.data.cpu().numpy(), bb.cpu().numpy())
         tags = ct.values_dev.cpu().numpy()
@@ -59,8 +69,8 @@ def main():
             assert np.array_equal(p["b"], bb[p["rows"]])
             assert p["n_local"] < gmesh.num_cells
         assert np.all(seen == 1)
-        print("PARTITION-OK world=%d kind=%s cells=%d local=%s"
-              % (world, kind, gmesh.num_cells, [p["n_local"] for p in parts]))
+        print("PARTITION-OK world=%d kind=%s single=%s cells=%d local=%s"
+              % (world, kind, single, gmesh.num_cells, [p["n_local"] for p in parts]))
     dist.barrier()
     dist.destroy_process_group()
 

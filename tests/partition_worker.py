@@ -17,25 +17,37 @@ from phifem_b200 import partition, synthetic  # noqa: E402
 from dist_worker import oracle_kernels  # noqa: E402
 
 
-def global_problem(kind, n):
+def global_problem(kind, n, single=False):
     mesh = synthetic.rectangle_mesh(n, device="cpu") if kind == "tri" else synthetic.box_mesh(n, device="cpu")
     mesh = synthetic.unstructured_variant(mesh, jitter=0.2, seed=11)
     center = (0.013, -0.021) if kind == "tri" else synthetic.SPHERE_CENTER
     phi = synthetic.sphere_levelset(mesh.x, center=center, radius=0.61 if kind == "tri" else 0.37)
+    if single:   # add a ball around ONE vertex far from the main body: the cells touching that vertex are cut and
+        # have no interior neighbour, so `single_layer_cut` must re-tag them
+        h = (2.0 if kind == "tri" else 1.0) / n
+        far = torch.argmax(torch.where(phi > 4 * h, phi, torch.full_like(phi, -1.0)))
+        c2 = tuple(float(v) for v in mesh.x[far])
+        phi = torch.minimum(phi, synthetic.sphere_levelset(mesh.x, center=c2, radius=0.3 * h))
     f = torch.from_numpy(np.random.default_rng(99).uniform(-1, 1, mesh.num_vertices))
     return mesh, phi, f
 
 
 def main():
     kind, n, out_dir = sys.argv[1], int(sys.argv[2]), sys.argv[3]
+    single = len(sys.argv) > 4 and sys.argv[4] == "single"
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
-    gmesh, phi, f = global_problem(kind, n)
-    prob = partition.PartitionedProblem(gmesh, phi, f, rank, world)
+    gmesh, phi, f = global_problem(kind, n, single)
+    prob = partition.PartitionedProblem(gmesh, phi, f, rank, world, single_layer_cut=single)
     m = prob.mesh
     x, cells = m.x.numpy(), np.ascontiguousarray(m.cells.numpy())
     c2f, f2c = np.ascontiguousarray(m.c2f.numpy()), np.ascontiguousarray(m.f2c.numpy())
     ct = ON.tag_cells_p1(x, cells, prob.phi.numpy())
+    if single:   # reference :349-358 on the local mesh (numpy oracle; the C port has no single-layer pass)
+        from oracle import tags as OT
+        pts = OT.cell_detection_points(m.cell_type, 1)
+        ct = OT.tag_cells(prob.phi.numpy()[cells], OT.cell_scale(x, cells.astype(np.int64), m.cell_type, pts),
+                          cells.astype(np.int64), single_layer_cut=True, warn=False)
     # "any exterior cell" is global (mesh_scripts.py:469-474): the oracle's facet pass takes it from the local
     # cell tags, so make sure every rank agrees (true here: the disc / sphere leaves exterior cells everywhere)
     flag = torch.tensor([int((ct == 3).any())])

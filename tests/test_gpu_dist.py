@@ -23,12 +23,12 @@ def test_two_gpus_match_single_gpu(mode):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("kind,n", [("tri", 48), ("tet", 12)])
-def test_partitioned_gpus_are_bitwise_identical_to_single_gpu(kind, n):
+@pytest.mark.parametrize("kind,n,single", [("tri", 48, False), ("tet", 12, False), ("tet", 12, True)])
+def test_partitioned_gpus_are_bitwise_identical_to_single_gpu(kind, n, single):
     """General Morton-curve sharding of an unstructured mesh (phifem_b200/partition.py), owner computes."""
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29613",
-                          os.path.join(HERE, "partition_gpu_worker.py"), kind, str(n)], capture_output=True,
-                         text=True, timeout=600)
+                          os.path.join(HERE, "partition_gpu_worker.py"), kind, str(n)]
+                         + (["single"] if single else []), capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
-    assert "PARTITION-OK world=2 kind=%s" % kind in out.stdout
+    assert "PARTITION-OK world=2 kind=%s single=%s" % (kind, single) in out.stdout

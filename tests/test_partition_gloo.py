@@ -17,26 +17,31 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 
 
-@pytest.mark.parametrize("kind,n,world", [("tri", 12, 2), ("tet", 5, 2), ("tet", 5, 3)])
-def test_partitioned_ranks_reproduce_the_single_domain_operator(tmp_path, kind, n, world):
+@pytest.mark.parametrize("kind,n,world,single", [("tri", 12, 2, False), ("tet", 5, 2, False), ("tet", 5, 3, False),
+                                                 ("tri", 12, 3, True), ("tet", 5, 2, True)])
+def test_partitioned_ranks_reproduce_the_single_domain_operator(tmp_path, kind, n, world, single):
     port = _free_port()
     procs = []
     for rank in range(world):
         env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
                    MASTER_PORT=str(port), OMP_NUM_THREADS="2")
         procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "partition_worker.py"), kind, str(n),
-                                       str(tmp_path)], env=env))
+                                       str(tmp_path)] + (["single"] if single else []), env=env))
     for p in procs:
         assert p.wait(timeout=300) == 0
     from partition_worker import global_problem
-    mesh, phi, f = global_problem(kind, n)
+    mesh, phi, f = global_problem(kind, n, single)
     x, cells = mesh.x.numpy(), mesh.cells.numpy().astype(np.int64)
     ph, fh = phi.numpy(), f.numpy()
     ct = mesh.cell_type
     pts = OT.cell_detection_points(ct, 1)
     ftab = np.asarray([OT.coordinate_basis(ct, p)[0] for p in OT.facet_points_in_cell(ct, 1)])
     out = OT.compute_tags_measures(x, cells, ct, ph[cells], OT.point_values_function(ph, cells, ftab),
-                                   box_mode=True, detection_points=pts)
+                                   box_mode=True, single_layer_cut=single, detection_points=pts)
+    if single:       # the small ball's cut cells were re-tagged: the case exercises :349-358
+        plain = OT.compute_tags_measures(x, cells, ct, ph[cells], OT.point_values_function(ph, cells, ftab),
+                                         box_mode=True, detection_points=pts)
+        assert (plain["cell_tags"] != out["cell_tags"]).sum() > 0
     ip, ix, data, b = OA.assemble_strong_dirichlet(x, cells, cells, len(x), ph, fh, out["cell_tags"],
                                                    out["facet_tags"], out["c2f"], out["f2c"], out["ds100"])
     want = sp.csr_matrix((data, ix, ip), shape=(len(x), len(x)))
