@@ -283,14 +283,14 @@ int phifem_assemble_cells_pk(const phifem_mesh* mesh, const phifem_pk_space* spa
                              const int32_t* active, int64_t n_active, const int32_t* slots, double sigma,
                              double* data, double* b, void* stream);
 
-/* -int_{ds(100)} (grad(phi w).n) phi v (:106); slots[nd*nd, n_entities] entry-major. */
+/* -int_{ds(100)} (grad(phi w).n) phi v (:106); slots[n_entities, nd*nd] (row = test dof). */
 int phifem_assemble_boundary_pk(const phifem_mesh* mesh, const phifem_pk_space* space_w,
                                 const phifem_pk_space* space_phi, const phifem_quadrature* quad,
                                 const double* phi, const int32_t* entities, int64_t n_entities,
                                 const int32_t* slots, double* data, void* stream);
 
 /* Ghost penalty over dS((2,3)) (:113-118); macro dofs = [dofs of cell + (f2c[f][0]), dofs of cell -];
- * slots[(2nd)^2, n_facets] entry-major. */
+ * slots[n_facets, (2nd)^2] (row = test dof). */
 int phifem_assemble_ghost_pk(const phifem_mesh* mesh, const phifem_pk_space* space_w,
                              const phifem_pk_space* space_phi, const phifem_quadrature* quad,
                              const double* phi, const int32_t* facets, int64_t n_facets,
@@ -300,9 +300,9 @@ int phifem_assemble_ghost_pk(const phifem_mesh* mesh, const phifem_pk_space* spa
  * demo/weak-dirichlet/flower/main.py:112-151 (`assemble_matrix(form(a))` :137-139, `assemble_vector(form(L))`
  * :153-154).  Cell-local mixed dof order [u dofs, p dofs] (nm = 2 nd); the global mixed numbering is the
  * caller's (`mixed_dofmap` [n_cells, nm]; phifem_b200/assemble_pk.py numbers u at scalar dof s as 2 s, p as
- * 2 s + 1).  space_w = the scalar P_k space of u, p, f and u_D; space_phi = the level-set space.  Slot maps are
- * entry-major over the mixed tensors: cells / one-sided entities [nm*nm, n], ghost facets [(2 nm)^2, n] with
- * macro order [mixed dofs of cell +, mixed dofs of cell -].  ADD semantics; `data` / `b` zeroed by the caller. */
+ * 2 s + 1).  space_w = the scalar P_k space of u, p, f and u_D; space_phi = the level-set space.  Slot maps over
+ * the mixed tensors: cells entry-major [nm*nm, n_active], one-sided entities [n, nm*nm], ghost facets
+ * [n, (2 nm)^2] with macro order [mixed dofs of cell +, mixed dofs of cell -].  ADD semantics; `data` / `b` zeroed by the caller. */
 int phifem_assemble_weak_cells_pk(const phifem_mesh* mesh, const phifem_pk_space* space_w,
                                   const phifem_pk_space* space_phi, const phifem_quadrature* quad,
                                   const double* phi, const double* f, const double* u_d,

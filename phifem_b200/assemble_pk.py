@@ -8,8 +8,9 @@ by the quadrature kernels of csrc/assemble_pk.cu.
 
 Symbolic phase (torch sort/unique on the mesh's device): CSR pattern = all dof pairs of every cell tagged
 1/2 plus all pairs among the dofs of the two cells of every interior facet tagged 2/3 (dolfinx
-create_sparsity_pattern [dep-knowledge, SURVEY.md C.3]); entity -> CSR-slot maps stored entry-major
-([nd*nd, n_entities]) so that consecutive threads read consecutive words.
+create_sparsity_pattern [dep-knowledge, SURVEY.md C.3]); entity -> CSR-slot maps stored so that consecutive threads
+read consecutive words: entry-major ([nd*nd, n_cells]) for the cell kernel (one thread per cell), entity-major
+([n, nd*nd]) for the facet kernels (the threads of one entity work on its rows).
 """
 import ctypes
 
@@ -70,11 +71,13 @@ class PkAssemblyPlan:
         del keys_c, keys_g
         inv = inv.to(torch.int32)
         self.slots_cells = inv[:n_c].reshape(-1, nd * nd).t().contiguous()
-        self.slots_ghost = inv[n_c:].reshape(-1, 4 * nd * nd).t().contiguous()
+        # cells: entry-major (one thread per cell); facets / entities: entity-major (the threads of one entity read
+        # consecutive words)
+        self.slots_ghost = inv[n_c:].reshape(-1, 4 * nd * nd).contiguous()
         del inv
         keys_b = pair_keys(pdm[self.entities[:, 0].long()].long())
         self.slots_boundary = torch.searchsorted(uniq, keys_b.reshape(-1)).reshape(-1, nd * nd) \
-            .to(torch.int32).t().contiguous()
+            .to(torch.int32).contiguous()
         rows = uniq // n
         self.indices = (uniq - rows * n).to(torch.int32).contiguous()
         counts = torch.bincount(rows, minlength=n)

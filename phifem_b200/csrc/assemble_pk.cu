@@ -404,85 +404,163 @@ __global__ void __launch_bounds__(kBlockPk) k_assemble_boundary_pk(
     for (int j = 0; j < ND; ++j) A[j] += ui * (wv[j] * gpn + ph * dotd<D>(wg[j], n));
   }
 #pragma unroll
-  for (int j = 0; j < ND; ++j) atomicAdd(data + __ldg(slots + (int64_t)(i * ND + j) * n_entities + e), A[j]);
+  for (int j = 0; j < ND; ++j) atomicAdd(data + __ldg(slots + (e * ND + i) * ND + j), A[j]);
 }
 
-// ---- ghost penalty: one thread per (facet, macro test dof a) -----------------------------------------------
+// value and gradient of ONE basis function (run-time index i) of the P_K Lagrange basis at barycentric point lam
+template <int D, int K>
+__device__ __forceinline__ void basis_one(const double (&lam)[D + 1], const double (&G)[D + 1][D], int i,
+                                          double& val, double (&grad)[D]) {
+  constexpr int NV = D + 1;
+  // vertex a (and, for an edge function, vertex b) the function belongs to
+  int a = i, b = -1;
+  if (K == 2 && i >= NV) {
+    a = 0;
+    b = 0;
+#pragma unroll
+    for (int e = 0; e < Space<D, K>::NE; ++e)
+      if (e == i - NV) {
+        a = ev<D>(e, 0);
+        b = ev<D>(e, 1);
+      }
+  }
+  double la = 0.0, lb = 0.0, Ga[D], Gb[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) Ga[d] = Gb[d] = 0.0;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    if (k == a) {
+      la = lam[k];
+#pragma unroll
+      for (int d = 0; d < D; ++d) Ga[d] = G[k][d];
+    }
+    if (k == b) {
+      lb = lam[k];
+#pragma unroll
+      for (int d = 0; d < D; ++d) Gb[d] = G[k][d];
+    }
+  }
+  if (K == 1) {
+    val = la;
+#pragma unroll
+    for (int d = 0; d < D; ++d) grad[d] = Ga[d];
+  } else if (b < 0) {
+    val = la * (2.0 * la - 1.0);
+#pragma unroll
+    for (int d = 0; d < D; ++d) grad[d] = (4.0 * la - 1.0) * Ga[d];
+  } else {
+    val = 4.0 * la * lb;
+#pragma unroll
+    for (int d = 0; d < D; ++d) grad[d] = 4.0 * (la * Gb[d] + lb * Ga[d]);
+  }
+}
+
+// phi_h and grad(phi_h) at a point, from the level set's own tabulation
+template <int D, int KP>
+__device__ __forceinline__ void eval_phi_only(const double (&lam)[D + 1], const double (&G)[D + 1][D],
+                                              const double (&pc)[Space<D, KP>::ND], double& ph, double (&gph)[D]) {
+  constexpr int NDP = Space<D, KP>::ND;
+  double pv[NDP], pg[NDP][D];
+  tabulate<D, KP>(lam, G, pv, pg);
+  ph = 0.0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) gph[d] = 0.0;
+#pragma unroll
+  for (int k = 0; k < NDP; ++k) {
+    ph += pc[k] * pv[k];
+#pragma unroll
+    for (int d = 0; d < D; ++d) gph[d] += pc[k] * pg[k][d];
+  }
+}
+
+// ---- ghost penalty: the 2 ND threads of a facet cooperate --------------------------------------------------------
 //   E_ab = sigma avg(h_T) int_F J_a J_b,  J_a = grad(phi psi_a).n of the side dof a lives on   (main.py:113-118)
 // macro dofs = [dofs of cell + (= f2c[f][0]), dofs of cell -]: 2 ND rows/columns, shared dofs appear twice
-// and add into the same CSR entry, as in dolfinx's interior-facet assembly.
+// and add into the same CSR entry, as in dolfinx's interior-facet assembly.  Thread (facet, a) tabulates ITS jump
+// J_a at every facet point into shared memory; after one barrier it accumulates row a of E from the facet's table.
+template <int D, int KW>
+struct GhostLayout {
+  static constexpr int NM = 2 * Space<D, KW>::ND;
+  static constexpr int FPB = kBlockPk / NM;      // facets per block
+  static constexpr int kMaxPoints = 32;          // facet rule of the ghost / one-sided terms (16 points for P2/P2)
+};
+
 template <int D, int KW, int KP>
 __global__ void __launch_bounds__(kBlockPk) k_assemble_ghost_pk(
     phifem_mesh m, phifem_pk_space sw, phifem_pk_space sp, const double* __restrict__ qlam_g,
     const double* __restrict__ qw_g, int nq, const double* __restrict__ phi,
     const int32_t* __restrict__ facets, int64_t n_facets, const int32_t* __restrict__ slots, double sigma,
     double* __restrict__ data) {
-  constexpr int NV = D + 1, ND = Space<D, KW>::ND, NDP = Space<D, KP>::ND, NM = 2 * ND;
-  __shared__ double qlam[kMaxQuadPoints * D], qw[kMaxQuadPoints];
+  using L = GhostLayout<D, KW>;
+  constexpr int NV = D + 1, ND = Space<D, KW>::ND, NDP = Space<D, KP>::ND, NM = L::NM, FPB = L::FPB;
+  __shared__ double qlam[L::kMaxPoints * D], qw[L::kMaxPoints];
+  __shared__ double Js[FPB][L::kMaxPoints][NM];
   for (int i = threadIdx.x; i < nq * D; i += blockDim.x) qlam[i] = qlam_g[i];
   for (int i = threadIdx.x; i < nq; i += blockDim.x) qw[i] = qw_g[i];
   __syncthreads();
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_facets * NM) return;
-  const int64_t e = t / NM;
-  const int a = (int)(t - e * NM);
-  const int32_t fct = __ldg(facets + e);
-  const int2 cc = __ldg(reinterpret_cast<const int2*>(m.f2c) + fct);
-  Geometry<D> gp, gm;
-  load_geometry<D>(m, cc.x, gp);
-  load_geometry<D>(m, cc.y, gm);
-  int op = 0, om = 0;
+  const int fl = threadIdx.x / NM, a = threadIdx.x % NM;
+  const int64_t e = (int64_t)blockIdx.x * FPB + fl;
+  const bool live = fl < FPB && e < n_facets;
+  double coef = 0.0;
+  if (live) {
+    const int32_t fct = __ldg(facets + e);
+    const int2 cc = __ldg(reinterpret_cast<const int2*>(m.f2c) + fct);
+    const bool minus = a >= ND;                 // the side this thread's dof lives on
+    Geometry<D> gp, gm;
+    load_geometry<D>(m, cc.x, gp);
+    load_geometry<D>(m, cc.y, gm);
+    int op = 0, om = 0;
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    if (__ldg(m.c2f + (int64_t)cc.x * NV + k) == fct) op = k;
-    if (__ldg(m.c2f + (int64_t)cc.y * NV + k) == fct) om = k;
+    for (int k = 0; k < NV; ++k) {
+      if (__ldg(m.c2f + (int64_t)cc.x * NV + k) == fct) op = k;
+      if (__ldg(m.c2f + (int64_t)cc.y * NV + k) == fct) om = k;
+    }
+    double pc[NDP];
+    load_dofs<D, KP>(m, sp, phi, minus ? cc.y : cc.x, pc);
+    double np_[D], nm_[D], area, area_m;
+    facet_normal<D>(gp, op, np_, area);
+    facet_normal<D>(gm, om, nm_, area_m);
+    coef = sigma * 0.5 * (sqrt(gp.h2) + sqrt(gm.h2)) * area;
+    double G[NV][D], n[D];  // geometry of this thread's side (selected value by value: stays in registers)
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+      for (int d = 0; d < D; ++d) G[k][d] = minus ? gm.G[k][d] : gp.G[k][d];
+#pragma unroll
+    for (int d = 0; d < D; ++d) n[d] = minus ? nm_[d] : np_[d];
+    for (int q = 0; q < nq; ++q) {
+      double lam[NV];
+      facet_to_cell<D>(qlam + q * D, op, lam);
+      if (minus) {  // the same physical point in the barycentric coordinates of cell -
+        double xq[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < NV; ++k) s += lam[k] * gp.X[k][d];
+          xq[d] = s - gm.X[0][d];
+        }
+#pragma unroll
+        for (int k = 0; k < NV; ++k) lam[k] = (k == 0 ? 1.0 : 0.0) + dotd<D>(gm.G[k], xq);
+      }
+      double ph, gph[D], val, grad[D];
+      eval_phi_only<D, KP>(lam, G, pc, ph, gph);
+      basis_one<D, KW>(lam, G, minus ? a - ND : a, val, grad);
+      Js[fl][q][a] = val * dotd<D>(gph, n) + ph * dotd<D>(grad, n);
+    }
   }
-  double pcp[NDP], pcm[NDP];
-  load_dofs<D, KP>(m, sp, phi, cc.x, pcp);
-  load_dofs<D, KP>(m, sp, phi, cc.y, pcm);
-  double np_[D], nm_[D], area, area_m;
-  facet_normal<D>(gp, op, np_, area);
-  facet_normal<D>(gm, om, nm_, area_m);
-  const double coef = sigma * 0.5 * (sqrt(gp.h2) + sqrt(gm.h2)) * area;
+  __syncthreads();
+  if (!live) return;
   double E[NM];
 #pragma unroll
   for (int bb = 0; bb < NM; ++bb) E[bb] = 0.0;
   for (int q = 0; q < nq; ++q) {
-    double lam[NV], J[NM];
-    facet_to_cell<D>(qlam + q * D, op, lam);
-    {
-      double wv[ND], wg[ND][D], ph, gph[D];
-      tabulate<D, KW>(lam, gp.G, wv, wg);
-      eval_phi<D, KW, KP>(lam, gp.G, wv, wg, pcp, ph, gph);
-      const double gpn = dotd<D>(gph, np_);
+    const double wa = qw[q] * coef * Js[fl][q][a];
 #pragma unroll
-      for (int j = 0; j < ND; ++j) J[j] = wv[j] * gpn + ph * dotd<D>(wg[j], np_);
-    }
-    // the same physical point in the barycentric coordinates of cell -
-    double xq[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      double s = 0.0;
-#pragma unroll
-      for (int k = 0; k < NV; ++k) s += lam[k] * gp.X[k][d];
-      xq[d] = s - gm.X[0][d];
-    }
-#pragma unroll
-    for (int k = 0; k < NV; ++k) lam[k] = (k == 0 ? 1.0 : 0.0) + dotd<D>(gm.G[k], xq);
-    {
-      double wv[ND], wg[ND][D], ph, gph[D];
-      tabulate<D, KW>(lam, gm.G, wv, wg);
-      eval_phi<D, KW, KP>(lam, gm.G, wv, wg, pcm, ph, gph);
-      const double gpn = dotd<D>(gph, nm_);
-#pragma unroll
-      for (int j = 0; j < ND; ++j) J[ND + j] = wv[j] * gpn + ph * dotd<D>(wg[j], nm_);
-    }
-    const double wa = qw[q] * coef * pick<NM>(J, a);
-#pragma unroll
-    for (int bb = 0; bb < NM; ++bb) E[bb] += wa * J[bb];
+    for (int bb = 0; bb < NM; ++bb) E[bb] += wa * Js[fl][q][bb];
   }
 #pragma unroll
-  for (int bb = 0; bb < NM; ++bb) atomicAdd(data + __ldg(slots + (int64_t)(a * NM + bb) * n_facets + e), E[bb]);
+  for (int bb = 0; bb < NM; ++bb) atomicAdd(data + __ldg(slots + (e * NM + a) * NM + bb), E[bb]);
 }
 
 // ==== weak-Dirichlet (dual) phi-FEM operator on the mixed space (u, p) in P_KW x P_KW ========================
@@ -607,7 +685,7 @@ __global__ void __launch_bounds__(kBlockPk) k_assemble_boundary_weak_pk(
     for (int j = 0; j < ND; ++j) A[j] += vi * dotd<D>(wg[j], n);
   }
 #pragma unroll
-  for (int j = 0; j < ND; ++j) atomicAdd(data + __ldg(slots + (int64_t)(i * NM + j) * n_entities + e), A[j]);
+  for (int j = 0; j < ND; ++j) atomicAdd(data + __ldg(slots + (e * NM + i) * NM + j), A[j]);
 }
 
 template <int D, int KW>
@@ -676,7 +754,7 @@ __global__ void __launch_bounds__(kBlockPk) k_assemble_ghost_weak_pk(
 #pragma unroll
   for (int bb = 0; bb < NU; ++bb) {
     const int mb = (bb / ND) * NM + (bb % ND);
-    atomicAdd(data + __ldg(slots + (int64_t)(ma * 2 * NM + mb) * n_facets + e), E[bb]);
+    atomicAdd(data + __ldg(slots + (e * 2 * NM + ma) * 2 * NM + mb), E[bb]);
   }
 }
 
@@ -778,11 +856,12 @@ extern "C" int phifem_assemble_ghost_pk(const phifem_mesh* mesh, const phifem_pk
   if (n_facets == 0) return PHIFEM_OK;
   PHIFEM_CHECK_ARG(phi && data && mesh->c2f && mesh->f2c, "null pointer");
   PHIFEM_CHECK_ARG(facets && slots, "null facets / slots");
+  PHIFEM_CHECK_ARG(quad->n_facet_points <= 32, "the ghost-penalty kernel holds at most 32 facet points");
   cudaStream_t st = (cudaStream_t)stream;
   dispatch(mesh->cell_type, space_w->degree, space_phi->degree, [&](auto d, auto kw, auto kp) {
     constexpr int D = decltype(d)::value, KW = decltype(kw)::value, KP = decltype(kp)::value;
-    const int64_t threads = n_facets * 2 * Space<D, KW>::ND;
-    k_assemble_ghost_pk<D, KW, KP><<<(unsigned)((threads + kBlockPk - 1) / kBlockPk), kBlockPk, 0, st>>>(
+    constexpr int FPB = GhostLayout<D, KW>::FPB;
+    k_assemble_ghost_pk<D, KW, KP><<<(unsigned)((n_facets + FPB - 1) / FPB), kBlockPk, 0, st>>>(
         *mesh, *space_w, *space_phi, quad->facet_points, quad->facet_weights, quad->n_facet_points, phi,
         facets, n_facets, slots, sigma, data);
   });

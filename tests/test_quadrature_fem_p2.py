@@ -87,11 +87,11 @@ def test_pk_symbolic_phase_matches_oracle_pattern(kind, n, kw):
         for j in range(nd):
             assert np.array_equal(rows[sl[i, j]], dm[:, i]) and np.array_equal(ix[sl[i, j]], dm[:, j])
     mac = np.concatenate([V.dofmap[out["f2c"][ghost, 0]], V.dofmap[out["f2c"][ghost, 1]]], axis=1)
-    sg = plan.slots_ghost.numpy().reshape(2 * nd, 2 * nd, len(ghost))
+    sg = np.moveaxis(plan.slots_ghost.numpy().reshape(len(ghost), 2 * nd, 2 * nd), 0, 2)
     for a in range(0, 2 * nd, 3):
         for b in range(2 * nd):
             assert np.array_equal(rows[sg[a, b]], mac[:, a]) and np.array_equal(ix[sg[a, b]], mac[:, b])
     eb = plan.entities.numpy()
-    sb = plan.slots_boundary.numpy().reshape(nd, nd, len(eb))
+    sb = np.moveaxis(plan.slots_boundary.numpy().reshape(len(eb), nd, nd), 0, 2)
     dmb = V.dofmap[eb[:, 0]]
     assert len(eb) > 0 and np.array_equal(rows[sb[1, 2]], dmb[:, 1]) and np.array_equal(ix[sb[1, 2]], dmb[:, 2])
