@@ -326,6 +326,27 @@ int phifem_assemble_weak_ghost_pk(const phifem_mesh* mesh, const phifem_pk_space
 int phifem_csr_spmv(int64_t n_rows, const int32_t* indptr, const int32_t* indices, const double* data,
                     const double* x, double* y, void* stream);
 
+/* ---- Neumann phi-FEM operator on the mixed space (u, y, p) in P1 x P1^d x DG0: demo/neumann/square/main.py:103-158
+ * (`assemble_matrix(form(a))` :141-143, `assemble_vector(form(L))` :160-161), triangles and tetrahedra, P1 or P2 level
+ * set.  Cell-local mixed dof order [u at the vertices, y node-major (vertex i, component c -> nv + i d + c), p]
+ * (nm = nv (1 + d) + 1); the global mixed numbering is the caller's (`mixed_dofmap` [n_cells, nm];
+ * phifem_b200/assemble_pk.py numbers u at vertex s as (d+1) s, y_c as (d+1) s + 1 + c, p of cell k as (d+1) Nv + k).
+ * `f` and `u_n` are P1 (vertex values).  Slot maps: cells entry-major [nm*nm, n_active], one-sided entities
+ * [n, nm*nm], interior facets tagged 3 [n, (2 nm)^2] (macro order [mixed dofs of cell +, of cell -]).  ADD semantics. */
+int phifem_assemble_neumann_cells(const phifem_mesh* mesh, const phifem_pk_space* space_phi,
+                                  const phifem_quadrature* quad, const double* phi, const double* f,
+                                  const double* u_n, const int8_t* cell_tags8, const int32_t* active,
+                                  int64_t n_active, const int32_t* slots, const int32_t* mixed_dofmap, double gamma,
+                                  double* data, double* b, void* stream);
+
+/* int_{ds(100)} (y.n) v (:120). */
+int phifem_assemble_neumann_boundary(const phifem_mesh* mesh, const int32_t* entities, int64_t n_entities,
+                                     const int32_t* slots, double* data, void* stream);
+
+/* sigma avg(h_T) [grad u.n][grad v.n] over dS(3) (:136-139). */
+int phifem_assemble_neumann_ghost(const phifem_mesh* mesh, const phifem_quadrature* quad, const int32_t* facets,
+                                  int64_t n_facets, const int32_t* slots, double sigma, double* data, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

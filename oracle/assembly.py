@@ -591,3 +591,201 @@ def assemble_weak_dirichlet(x, cells, dofmap, n_scalar_dofs, phi, f, ud, cell_ta
         _scatter(indptr, indices, data, np.repeat(mac, 2 * nm, axis=1).ravel(),
                  np.tile(mac, (1, 2 * nm)).ravel(), Eg.ravel())
     return indptr, indices, data, b
+
+
+# --------------------------------------------------------------------------------------
+# Neumann phi-FEM operator on the mixed space (u, y, p) in P1 x P1^d x DG0
+# reference demo/neumann/square/main.py:103-158 (BASELINE.json configs[1])
+#   a = int_{dx(1,2)} (grad u.grad v + u v) + int_ds (y.n) v                                     (:119-120)
+#       + gamma int_{dx(2)} [ (y + grad u).(z + grad v) + (div y + u)(div z + v)
+#                             + h^-2 (y.grad phi + h^-1 p phi)(z.grad phi + h^-1 q phi) ]          (:121-135)
+#       + sigma int_{dS(3)} avg(h) [grad u.n][grad v.n]                                          (:136-139)
+#   L = int_{dx(1,2)} f v + gamma int_{dx(2)} [ -h^-2 u_N |grad phi| (z.grad phi + h^-1 q phi) + f (div z + v) ]
+#                                                                                                (:146-158)
+# Cell-local mixed dof order: [u at the nv vertices, y node-major (vertex i, component c -> nv + i d + c), p].
+# Global numbering (an input of the kernels; this is the one phifem_b200 uses): u at vertex s -> (d+1) s,
+# y_c at s -> (d+1) s + 1 + c, p of cell k -> (d+1) Nv + k.  With every basis function X carrying
+# s1 = y + grad u, s2 = div y + u, s3 = y.grad phi + h^-1 p phi, the cut-cell integrand is
+# s1_b.s1_a + s2_b s2_a + h^-2 s3_b s3_a.  |grad phi_h| is not polynomial for a P2 level set: the quadrature
+# restatement is exact only for P1 phi (dolfinx would use the rule of UFL's estimated degree there).
+# --------------------------------------------------------------------------------------
+def neumann_mixed_dofmap(cells, n_vertices):
+    d = cells.shape[1] - 1
+    c = cells.astype(np.int64)
+    u = (d + 1) * c
+    y = ((d + 1) * c[:, :, None] + 1 + np.arange(d)[None, None, :]).reshape(len(c), -1)
+    p = (d + 1) * n_vertices + np.arange(len(c), dtype=np.int64)[:, None]
+    return np.concatenate([u, y, p], axis=1)
+
+
+def _neumann_fields(lam, G, pc, kphi, h):
+    """Per quadrature point and mixed basis function: u, grad u, s1, s2, s3; plus phi, grad phi."""
+    nq, nv = lam.shape
+    d = nv - 1
+    nm = nv * (1 + d) + 1
+    pv, pg, _ = lagrange_eval(lam, G, kphi)
+    ph = pv @ pc
+    gph = np.einsum("qkd,k->qd", pg, pc)
+    U = np.zeros((nq, nm))
+    GU = np.zeros((nq, nm, d))
+    S1 = np.zeros((nq, nm, d))
+    S2 = np.zeros((nq, nm))
+    S3 = np.zeros((nq, nm))
+    for j in range(nv):
+        U[:, j] = lam[:, j]
+        GU[:, j, :] = G[j][None, :]
+        S1[:, j, :] = G[j][None, :]
+        S2[:, j] = lam[:, j]
+        for c in range(d):
+            k = nv + j * d + c
+            S1[:, k, c] = lam[:, j]
+            S2[:, k] = G[j, c]
+            S3[:, k] = lam[:, j] * gph[:, c]
+    S3[:, nm - 1] = ph / h
+    return U, GU, S1, S2, S3, ph, gph
+
+
+def neumann_cell_tensors_quadrature(x, cells, phi_dofs, f_dofs, un_dofs, cut, gamma, kphi=1, n=6, rule=None):
+    """rule = (barycentric points, weights summing to 1): use this rule instead of the degree-11 one -- for a P2
+    level set the load term holds |grad phi_h| (not polynomial), so the result depends on the rule."""
+    d = x.shape[1]
+    G, vol, h = simplex_geometry(x, cells)
+    lam, W = simplex_rule(d, n)
+    if rule is not None:
+        lam, W = np.asarray(rule[0]), np.asarray(rule[1]) / math.factorial(d)
+    out_A, out_b = [], []
+    for c in range(len(cells)):
+        U, GU, S1, S2, S3, ph, gph = _neumann_fields(lam, G[c], phi_dofs[c], kphi, h[c])
+        wq = W * math.factorial(d) * vol[c]
+        fq = lam @ f_dofs[c]
+        A = np.einsum("q,qad,qbd->ab", wq, GU, GU) + np.einsum("q,qa,qb->ab", wq, U, U)
+        b = np.einsum("q,q,qa->a", wq, fq, U)
+        if cut[c]:
+            hh = h[c]
+            A += gamma * (np.einsum("q,qad,qbd->ab", wq, S1, S1) + np.einsum("q,qa,qb->ab", wq, S2, S2)
+                          + np.einsum("q,qa,qb->ab", wq, S3, S3) / hh ** 2)
+            unq = lam @ un_dofs[c]
+            ngp = np.sqrt((gph ** 2).sum(axis=1))
+            b += gamma * (-np.einsum("q,q,q,qa->a", wq, unq, ngp, S3) / hh ** 2 + np.einsum("q,q,qa->a", wq, fq, S2))
+        out_A.append(A)
+        out_b.append(b)
+    return np.array(out_A), np.array(out_b)
+
+
+def neumann_cell_tensors_closed_form(x, cells, phi, f, un, cut, gamma):
+    """P1 level set: every integrand is polynomial (grad phi constant per cell); exact monomial integrals."""
+    d = x.shape[1]
+    nv = d + 1
+    nm = nv * (1 + d) + 1
+    G, vol, h = simplex_geometry(x, cells)
+    p, fv, uv = phi[cells], f[cells], un[cells]
+    M = np.array([[_bary_moment(d, (i, j)) for j in range(nv)] for i in range(nv)])
+    m1 = 1.0 / nv
+    n = len(cells)
+    A = np.zeros((n, nm, nm))
+    b = np.zeros((n, nm))
+    GG = np.einsum("nid,njd->nij", G, G)
+    g = np.einsum("nk,nkd->nd", p, G)
+    ng = np.sqrt((g * g).sum(axis=1))
+    cg = np.where(cut, gamma, 0.0)
+    yi = lambda i, c: nv + i * d + c          # noqa: E731
+    A[:, :nv, :nv] = (vol * (1.0 + cg))[:, None, None] * (GG + M[None])
+    b[:, :nv] = (vol * (1.0 + cg))[:, None] * (fv @ M)
+    fbar = fv.mean(axis=1)                     # int f / |K|
+    for i in range(nv):
+        for c in range(d):
+            a = yi(i, c)
+            # rows of z = psi_i e_c against u_j: s1 -> psi_i dG_j/dc, s2 -> dpsi_i/dc psi_j
+            A[:, a, :nv] = (cg * vol)[:, None] * (m1 * G[:, :, c] + G[:, i, c][:, None] * m1)
+            A[:, :nv, a] = A[:, a, :nv]
+            for j in range(nv):
+                for c2 in range(d):
+                    a2 = yi(j, c2)
+                    A[:, a, a2] = cg * vol * ((M[i, j] if c == c2 else 0.0) + G[:, i, c] * G[:, j, c2]
+                                              + g[:, c] * g[:, c2] * M[i, j] / h ** 2)
+            A[:, a, nm - 1] = cg * vol * g[:, c] * (p @ M[:, i]) / h ** 3
+            A[:, nm - 1, a] = A[:, a, nm - 1]
+            b[:, a] = cg * vol * (-ng * g[:, c] * (uv @ M[:, i]) / h ** 2 + G[:, i, c] * fbar)
+    A[:, nm - 1, nm - 1] = cg * vol * np.einsum("nk,nl,kl->n", p, p, M) / h ** 4
+    b[:, nm - 1] = -cg * vol * ng * np.einsum("nk,nl,kl->n", uv, p, M) / h ** 3
+    return A, b
+
+
+def neumann_boundary_tensors(x, cells, ents):
+    """int_F (y.n) v on (cell, local facet) pairs: rows u_i (i on the facet), columns y_(j,c) (j on the facet):
+    n_c |F| (1 + delta_ij) / (d (d+1))."""
+    ents = np.asarray(ents).reshape(-1, 2)
+    d = x.shape[1]
+    nv = d + 1
+    nm = nv * (1 + d) + 1
+    nrm, area = facet_geometry(x, cells, ents)
+    A = np.zeros((len(ents), nm, nm))
+    for e, (_, o) in enumerate(ents):
+        on = [k for k in range(nv) if k != o]
+        for i in on:
+            for j in on:
+                for c in range(d):
+                    A[e, i, nv + j * d + c] = nrm[e, c] * area[e] * (2.0 if i == j else 1.0) / (d * (d + 1))
+    return A
+
+
+def neumann_ghost_tensors(x, cells, c2f, f2c, facets, sigma):
+    """sigma avg(h) int_F [grad u.n][grad v.n] over macro dofs [mixed dofs of cell +, of cell -]; u-u entries only."""
+    d = x.shape[1]
+    nv = d + 1
+    nm = nv * (1 + d) + 1
+    facets = np.asarray(facets)
+    E = np.zeros((len(facets), 2 * nm, 2 * nm))
+    if len(facets) == 0:
+        return E
+    J = np.zeros((len(facets), 2 * nm))
+    hsum = np.zeros(len(facets))
+    area = None
+    for side in (0, 1):
+        cc = f2c[facets, side]
+        lf = np.argmax(c2f[cc] == facets[:, None], axis=1)
+        G, _, h = simplex_geometry(x, cells[cc])
+        nrm, ar = facet_geometry(x, cells, np.stack([cc, lf], axis=1))
+        J[:, side * nm:side * nm + nv] = np.einsum("njd,nd->nj", G, nrm)
+        hsum += h
+        if side == 0:
+            area = ar
+    return (sigma * 0.5 * hsum * area)[:, None, None] * J[:, :, None] * J[:, None, :]
+
+
+def assemble_neumann(x, cells, phi, f, un, cell_tags, facet_tags, c2f, f2c, ds100, gamma=1.0, sigma=1.0,
+                     method="closed_form", kphi=1, phi_dofmap=None, rule=None):
+    """(indptr, indices, data, b) of the Neumann operator in box mode on the mixed numbering above."""
+    nvtx = len(x)
+    d = x.shape[1]
+    mixed = neumann_mixed_dofmap(cells, nvtx)
+    n_rows = (d + 1) * nvtx + len(cells)
+    phi_dofmap = cells if phi_dofmap is None else phi_dofmap
+    active = np.nonzero((cell_tags == 1) | (cell_tags == 2))[0]
+    ghost = np.nonzero((facet_tags == 3) & (f2c[:, 1] >= 0))[0]
+    ents = np.asarray(ds100).reshape(-1, 2)
+    indptr, indices = sparsity_pattern(n_rows, mixed, active, ghost, f2c)
+    data = np.zeros(len(indices))
+    b = np.zeros(n_rows)
+    cut = cell_tags[active] == 2
+    if method == "closed_form":
+        assert kphi == 1
+        A, be = neumann_cell_tensors_closed_form(x, cells[active], phi, f, un, cut, gamma)
+    else:
+        A, be = neumann_cell_tensors_quadrature(x, cells[active], phi[phi_dofmap[active]], f[cells[active]],
+                                                un[cells[active]], cut, gamma, kphi, rule=rule)
+    Ab = neumann_boundary_tensors(x, cells, ents)
+    Eg = neumann_ghost_tensors(x, cells, c2f, f2c, ghost, sigma)
+    nm = mixed.shape[1]
+    dm = mixed[active]
+    _scatter(indptr, indices, data, np.repeat(dm, nm, axis=1).ravel(), np.tile(dm, (1, nm)).ravel(), A.ravel())
+    np.add.at(b, dm.ravel(), be.ravel())
+    if len(ents):
+        dmb = mixed[ents[:, 0]]
+        _scatter(indptr, indices, data, np.repeat(dmb, nm, axis=1).ravel(), np.tile(dmb, (1, nm)).ravel(),
+                 Ab.ravel())
+    if len(ghost):
+        mac = np.concatenate([mixed[f2c[ghost, 0]], mixed[f2c[ghost, 1]]], axis=1)
+        _scatter(indptr, indices, data, np.repeat(mac, 2 * nm, axis=1).ravel(),
+                 np.tile(mac, (1, 2 * nm)).ravel(), Eg.ravel())
+    return indptr, indices, data, b

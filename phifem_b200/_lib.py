@@ -95,6 +95,12 @@ _SIGNATURES = {
     "phifem_assemble_boundary_pk": (ctypes.c_int, _PK_HEAD + [_vp, _vp, ctypes.c_int64, _vp, _vp, _vp]),
     "phifem_assemble_ghost_pk": (ctypes.c_int, _PK_HEAD + [_vp, _vp, ctypes.c_int64, _vp, ctypes.c_double,
                                                            _vp, _vp]),
+    "phifem_assemble_neumann_cells": (ctypes.c_int, [ctypes.POINTER(CMesh), ctypes.POINTER(CPkSpace),
+                                                     ctypes.POINTER(CQuadrature), _vp, _vp, _vp, _vp, _vp,
+                                                     ctypes.c_int64, _vp, _vp, ctypes.c_double, _vp, _vp, _vp]),
+    "phifem_assemble_neumann_boundary": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, ctypes.c_int64, _vp, _vp, _vp]),
+    "phifem_assemble_neumann_ghost": (ctypes.c_int, [ctypes.POINTER(CMesh), ctypes.POINTER(CQuadrature), _vp,
+                                                     ctypes.c_int64, _vp, ctypes.c_double, _vp, _vp]),
     "phifem_csr_spmv": (ctypes.c_int, [ctypes.c_int64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "phifem_assemble_weak_cells_pk": (ctypes.c_int, _PK_HEAD + [_vp, _vp, _vp, _vp, _vp, ctypes.c_int64, _vp, _vp,
                                                                 ctypes.c_double, ctypes.c_double, _vp, _vp, _vp]),

@@ -28,8 +28,10 @@ class PkAssemblyPlan:
         """form = "strong": strong-Dirichlet operator on V; form = "weak": weak-Dirichlet (dual) operator on
         the mixed space V x V, u at scalar dof s numbered 2 s, p numbered 2 s + 1 (cell-local order
         [u dofs, p dofs])."""
-        if form not in ("strong", "weak"):
-            raise ValueError("form must be 'strong' or 'weak'")
+        if form not in ("strong", "weak", "neumann"):
+            raise ValueError("form must be 'strong', 'weak' or 'neumann'")
+        if form == "neumann" and V.degree != 1:
+            raise NotImplementedError("the Neumann operator is implemented for P1 u and y (main.py:37-39)")
         self.form = form
         if mesh.cell_type not in ("triangle", "tetrahedron"):
             raise NotImplementedError("P_k assembly supports triangles and tetrahedra")
@@ -47,14 +49,23 @@ class PkAssemblyPlan:
         if form == "weak":
             self.pattern_dofmap = torch.cat([2 * self.dofmap, 2 * self.dofmap + 1], dim=1).contiguous()
             self.n_rows = n = 2 * int(V.num_dofs)
+        elif form == "neumann":
+            # mixed space (u, y, p) in P1 x P1^d x DG0: u at vertex s -> (d+1) s, y_c -> (d+1) s + 1 + c,
+            # p of cell k -> (d+1) Nv + k; cell-local order [u, y node-major, p]
+            d_, nvx = mesh.gdim, mesh.num_vertices
+            c = mesh.cells.long()
+            y = ((d_ + 1) * c[:, :, None] + 1 + torch.arange(d_, device=dev)[None, None, :]).reshape(c.shape[0], -1)
+            pcol = (d_ + 1) * nvx + torch.arange(mesh.num_cells, device=dev)[:, None]
+            self.pattern_dofmap = torch.cat([(d_ + 1) * c, y, pcol], dim=1).to(torch.int32).contiguous()
+            self.n_rows = n = (d_ + 1) * nvx + mesh.num_cells
         else:
             self.pattern_dofmap = self.dofmap
             self.n_rows = n = int(V.num_dofs)
         nd = int(self.pattern_dofmap.shape[1])       # dofs per cell of the assembled (possibly mixed) space
         self.active = torch.nonzero((cell_tags8 == 1) | (cell_tags8 == 2)).reshape(-1).to(torch.int32)
         interior = mesh.f2c[:, 1] >= 0
-        self.ghost = torch.nonzero(((facet_tags8 == 2) | (facet_tags8 == 3)) & interior) \
-            .reshape(-1).to(torch.int32)
+        gmask = (facet_tags8 == 3) if form == "neumann" else ((facet_tags8 == 2) | (facet_tags8 == 3))
+        self.ghost = torch.nonzero(gmask & interior).reshape(-1).to(torch.int32)   # dS(3) resp. dS((2,3))
         self.entities = entities.reshape(-1, 2).to(torch.int32).contiguous()
 
         def pair_keys(dm):  # [m, k] dofs -> [m, k*k] keys row*n+col, row-major (row = test)
@@ -90,8 +101,11 @@ class PkAssemblyPlan:
 
         # quadrature tables and C structs (kept alive with the plan)
         d = mesh.gdim
-        rules = quadrature.rules_for_weak if form == "weak" else quadrature.rules_for
-        (cl, cw), (fl, fw) = rules(d, V.degree, V_phi.degree)
+        if form == "neumann":
+            (cl, cw), (fl, fw) = quadrature.rules_for_neumann(d, V_phi.degree)
+        else:
+            rules = quadrature.rules_for_weak if form == "weak" else quadrature.rules_for
+            (cl, cw), (fl, fw) = rules(d, V.degree, V_phi.degree)
         f64 = dict(dtype=torch.float64, device=dev)
         self._q = [torch.as_tensor(a, **f64).contiguous() for a in (cl, cw, fl, fw)]
         self.n_cell_points, self.n_facet_points = len(cw), len(fw)
@@ -165,4 +179,28 @@ def assemble_weak_into(plan, phi, f, u_d, gamma, sigma, data, b):
     _lib.check(lib.phifem_assemble_weak_ghost_pk(
         cm, ctypes.byref(cw), ctypes.byref(cq), _lib.ptr(plan.ghost), plan.ghost.numel(),
         _lib.ptr(plan.slots_ghost), float(sigma), _lib.ptr(data), st))
+    return data, b
+
+
+def assemble_neumann_into(plan, phi, f, u_n, gamma, sigma, data, b):
+    """Numeric phase of the Neumann operator (plan.form == "neumann") on the current stream."""
+    mesh = plan.mesh
+    _lib.require_cuda(mesh)
+    if plan.form != "neumann":
+        raise ValueError("the plan was not built by build_plan_neumann")
+    lib = _lib.load()
+    cm = _lib.c_mesh(mesh)
+    _, cp, cq = plan.c_structs()
+    st = _lib.stream()
+    data.zero_()
+    b.zero_()
+    _lib.check(lib.phifem_assemble_neumann_cells(
+        cm, ctypes.byref(cp), ctypes.byref(cq), _lib.ptr(phi), _lib.ptr(f), _lib.ptr(u_n),
+        _lib.ptr(plan.cell_tags8), _lib.ptr(plan.active), plan.active.numel(), _lib.ptr(plan.slots_cells),
+        _lib.ptr(plan.pattern_dofmap), float(gamma), _lib.ptr(data), _lib.ptr(b), st))
+    _lib.check(lib.phifem_assemble_neumann_boundary(
+        cm, _lib.ptr(plan.entities), plan.entities.shape[0], _lib.ptr(plan.slots_boundary), _lib.ptr(data), st))
+    _lib.check(lib.phifem_assemble_neumann_ghost(
+        cm, ctypes.byref(cq), _lib.ptr(plan.ghost), plan.ghost.numel(), _lib.ptr(plan.slots_ghost), float(sigma),
+        _lib.ptr(data), st))
     return data, b

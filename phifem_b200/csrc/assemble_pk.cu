@@ -688,12 +688,12 @@ __global__ void __launch_bounds__(kBlockPk) k_assemble_boundary_weak_pk(
   for (int j = 0; j < ND; ++j) atomicAdd(data + __ldg(slots + (e * NM + i) * NM + j), A[j]);
 }
 
-template <int D, int KW>
+template <int D, int KW, int NMIX = 2 * Space<D, KW>::ND>
 __global__ void __launch_bounds__(kBlockPk) k_assemble_ghost_weak_pk(
     phifem_mesh m, const double* __restrict__ qlam_g, const double* __restrict__ qw_g, int nq,
     const int32_t* __restrict__ facets, int64_t n_facets, const int32_t* __restrict__ slots, double sigma,
     double* __restrict__ data) {
-  constexpr int NV = D + 1, ND = Space<D, KW>::ND, NM = 2 * ND, NU = 2 * ND;  // NU: u dofs of both sides
+  constexpr int NV = D + 1, ND = Space<D, KW>::ND, NM = NMIX, NU = 2 * ND;  // NU: u dofs of both sides
   __shared__ double qlam[kMaxQuadPoints * D], qw[kMaxQuadPoints];
   for (int i = threadIdx.x; i < nq * D; i += blockDim.x) qlam[i] = qlam_g[i];
   for (int i = threadIdx.x; i < nq; i += blockDim.x) qw[i] = qw_g[i];
@@ -755,6 +755,157 @@ __global__ void __launch_bounds__(kBlockPk) k_assemble_ghost_weak_pk(
   for (int bb = 0; bb < NU; ++bb) {
     const int mb = (bb / ND) * NM + (bb % ND);
     atomicAdd(data + __ldg(slots + (e * 2 * NM + ma) * 2 * NM + mb), E[bb]);
+  }
+}
+
+// ==== Neumann phi-FEM operator on the mixed space (u, y, p) in P1 x P1^D x DG0 =====================================
+// reference demo/neumann/square/main.py:103-158 (BASELINE.json configs[1]):
+//   a = int_{dx(1,2)} (grad u.grad v + u v) + int_ds (y.n) v
+//       + gamma int_{dx(2)} [ (y + grad u).(z + grad v) + (div y + u)(div z + v)
+//                             + h^-2 (y.grad phi + h^-1 p phi)(z.grad phi + h^-1 q phi) ]
+//       + sigma int_{dS(3)} avg(h) [grad u.n][grad v.n]
+//   L = int_{dx(1,2)} f v + gamma int_{dx(2)} [ -h^-2 u_N |grad phi| (z.grad phi + h^-1 q phi) + f (div z + v) ]
+// Cell-local mixed dofs: [u at the D+1 vertices, y node-major (vertex i, component c -> NV + i D + c), p]:
+// NM = (D+1)(D+1) + 1.  Every basis function X carries  s1 = y + grad u, s2 = div y + u,
+// s3 = y.grad phi + h^-1 p phi;  the cut-cell integrand is s1_b.s1_a + s2_b s2_a + h^-2 s3_b s3_a.
+// One thread per (cell, mixed test dof a).
+template <int D>
+struct NeumannSpace {
+  static constexpr int NV = D + 1;
+  static constexpr int NM = NV * (1 + D) + 1;
+};
+
+// the tuple (u, grad u, s1, s2, s3) of mixed basis function m at a point (lam = P1 basis values, G their gradients)
+template <int D>
+__device__ __forceinline__ void neumann_basis(int m, const double (&lam)[D + 1], const double (&G)[D + 1][D],
+                                              const double (&gph)[D], double ph_over_h, double& U,
+                                              double (&GU)[D], double (&S1)[D], double& S2, double& S3) {
+  constexpr int NV = D + 1, NM = NeumannSpace<D>::NM;
+  U = 0.0;
+  S2 = 0.0;
+  S3 = 0.0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) GU[d] = S1[d] = 0.0;
+  if (m == NM - 1) {  // p: piecewise constant
+    S3 = ph_over_h;
+    return;
+  }
+  const bool is_u = m < NV;
+  const int node = is_u ? m : (m - NV) / D, comp = is_u ? -1 : (m - NV) % D;
+  double lj = 0.0, Gj[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) Gj[d] = 0.0;
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+    if (k == node) {
+      lj = lam[k];
+#pragma unroll
+      for (int d = 0; d < D; ++d) Gj[d] = G[k][d];
+    }
+  if (is_u) {
+    U = lj;
+    S2 = lj;
+#pragma unroll
+    for (int d = 0; d < D; ++d) GU[d] = S1[d] = Gj[d];
+  } else {
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+      if (d == comp) {
+        S1[d] = lj;
+        S2 = Gj[d];
+        S3 = lj * gph[d];
+      }
+  }
+}
+
+template <int D, int KP>
+__global__ void __launch_bounds__(kBlockPk) k_assemble_cells_neumann(
+    phifem_mesh m, phifem_pk_space sp, const double* __restrict__ qlam_g, const double* __restrict__ qw_g, int nq,
+    const double* __restrict__ phi, const double* __restrict__ f, const double* __restrict__ un,
+    const int8_t* __restrict__ ctags, const int32_t* __restrict__ active, int64_t n_active,
+    const int32_t* __restrict__ slots, const int32_t* __restrict__ mixed_dofmap, double gamma,
+    double* __restrict__ data, double* __restrict__ b) {
+  constexpr int NV = D + 1, NDP = Space<D, KP>::ND, NM = NeumannSpace<D>::NM;
+  __shared__ double qlam[kMaxQuadPoints * NV], qw[kMaxQuadPoints];
+  for (int i = threadIdx.x; i < nq * NV; i += blockDim.x) qlam[i] = qlam_g[i];
+  for (int i = threadIdx.x; i < nq; i += blockDim.x) qw[i] = qw_g[i];
+  __syncthreads();
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_active * NM) return;
+  const int64_t e = t / NM;
+  const int a = (int)(t - e * NM);
+  const int64_t c = __ldg(active + e);
+  const bool is_cut = ctags[c] == 2;
+  if (a >= NV && !is_cut) return;  // rows of z and q only carry cut-cell terms
+  Geometry<D> g;
+  load_geometry<D>(m, c, g);
+  double pc[NDP], fc[NV], uc[NV];
+  load_dofs<D, KP>(m, sp, phi, c, pc);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int v = __ldg(m.cells + c * NV + k);
+    fc[k] = __ldg(f + v);
+    uc[k] = __ldg(un + v);
+  }
+  const double h = sqrt(g.h2), rh = 1.0 / h, rh2 = 1.0 / g.h2;
+  const double pen = is_cut ? gamma : 0.0;
+  double A[NM], bv = 0.0;
+#pragma unroll
+  for (int j = 0; j < NM; ++j) A[j] = 0.0;
+  for (int q = 0; q < nq; ++q) {
+    double lam[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) lam[k] = qlam[q * NV + k];
+    const double w = qw[q] * g.vol;
+    double ph, gph[D];
+    eval_phi_only<D, KP>(lam, g.G, pc, ph, gph);
+    double fq = 0.0, uq = 0.0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      fq += fc[k] * lam[k];
+      uq += uc[k] * lam[k];
+    }
+    double Ua, GUa[D], S1a[D], S2a, S3a;
+    neumann_basis<D>(a, lam, g.G, gph, ph * rh, Ua, GUa, S1a, S2a, S3a);
+    bv += w * (fq * Ua + pen * (fq * S2a - rh2 * uq * sqrt(dotd<D>(gph, gph)) * S3a));
+#pragma unroll
+    for (int bb = 0; bb < NM; ++bb) {
+      double Ub, GUb[D], S1b[D], S2b, S3b;
+      neumann_basis<D>(bb, lam, g.G, gph, ph * rh, Ub, GUb, S1b, S2b, S3b);
+      A[bb] += w * (dotd<D>(GUa, GUb) + Ua * Ub + pen * (dotd<D>(S1a, S1b) + S2a * S2b + rh2 * S3a * S3b));
+    }
+  }
+  atomicAdd(b + __ldg(mixed_dofmap + c * NM + a), bv);
+#pragma unroll
+  for (int bb = 0; bb < NM; ++bb)
+    if (bb < NV || is_cut) atomicAdd(data + __ldg(slots + (int64_t)(a * NM + bb) * n_active + e), A[bb]);
+}
+
+// int_{ds(100)} (y.n) v: one thread per (entity, u test dof i); columns y_(j,c)
+template <int D>
+__global__ void __launch_bounds__(kBlockPk) k_assemble_boundary_neumann(
+    phifem_mesh m, const int32_t* __restrict__ entities, int64_t n_entities, const int32_t* __restrict__ slots,
+    double* __restrict__ data) {
+  constexpr int NV = D + 1, NM = NeumannSpace<D>::NM;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_entities * NV) return;
+  const int64_t e = t / NV;
+  const int i = (int)(t - e * NV);
+  const int64_t c = __ldg(entities + 2 * e);
+  const int o = __ldg(entities + 2 * e + 1);
+  if (i == o) return;  // v_i vanishes on the facet opposite vertex i
+  Geometry<D> g;
+  load_geometry<D>(m, c, g);
+  double n[D], area;
+  facet_normal<D>(g, o, n, area);
+  const double cF = area * (1.0 / (D * (D + 1)));  // facet mass matrix |F| (1 + delta_ij) / (D (D+1))
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    if (j == o) continue;
+    const double mij = cF * (i == j ? 2.0 : 1.0);
+#pragma unroll
+    for (int cc = 0; cc < D; ++cc)
+      atomicAdd(data + __ldg(slots + (e * NM + i) * NM + NV + j * D + cc), n[cc] * mij);
   }
 }
 
@@ -933,6 +1084,72 @@ extern "C" int phifem_assemble_weak_ghost_pk(const phifem_mesh* mesh, const phif
         *mesh, quad->facet_points, quad->facet_weights, quad->n_facet_points, facets, n_facets, slots, sigma,
         data);
   });
+  PHIFEM_CHECK_LAUNCH();
+  return PHIFEM_OK;
+}
+
+// ---- Neumann operator (demo/neumann/square/main.py:103-158) --------------------------------------------------------
+extern "C" int phifem_assemble_neumann_cells(const phifem_mesh* mesh, const phifem_pk_space* space_phi,
+                                             const phifem_quadrature* quad, const double* phi, const double* f,
+                                             const double* u_n, const int8_t* cell_tags8, const int32_t* active,
+                                             int64_t n_active, const int32_t* slots, const int32_t* mixed_dofmap,
+                                             double gamma, double* data, double* b, void* stream) {
+  PHIFEM_CHECK_ARG(quad != nullptr && space_phi != nullptr, "quadrature / level-set space is null");
+  phifem_pk_space p1{1, mesh && mesh->cell_type == PHIFEM_TRIANGLE ? 3 : 4, 0, nullptr};
+  if (int rc = check_pk(mesh, &p1, space_phi, quad->cell_points, quad->cell_weights, quad->n_cell_points)) return rc;
+  if (n_active == 0) return PHIFEM_OK;
+  PHIFEM_CHECK_ARG(phi && f && u_n && cell_tags8 && data && b && mixed_dofmap && active && slots, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  dispatch(mesh->cell_type, 1, space_phi->degree, [&](auto d, auto, auto kp) {
+    constexpr int D = decltype(d)::value, KP = decltype(kp)::value;
+    const int64_t threads = n_active * NeumannSpace<D>::NM;
+    k_assemble_cells_neumann<D, KP><<<(unsigned)((threads + kBlockPk - 1) / kBlockPk), kBlockPk, 0, st>>>(
+        *mesh, *space_phi, quad->cell_points, quad->cell_weights, quad->n_cell_points, phi, f, u_n, cell_tags8,
+        active, n_active, slots, mixed_dofmap, gamma, data, b);
+  });
+  PHIFEM_CHECK_LAUNCH();
+  return PHIFEM_OK;
+}
+
+extern "C" int phifem_assemble_neumann_boundary(const phifem_mesh* mesh, const int32_t* entities,
+                                                int64_t n_entities, const int32_t* slots, double* data,
+                                                void* stream) {
+  PHIFEM_CHECK_ARG(mesh != nullptr && mesh->x && mesh->cells, "mesh is null");
+  if (mesh->cell_type != PHIFEM_TRIANGLE && mesh->cell_type != PHIFEM_TETRAHEDRON) {
+    set_error("the Neumann operator supports triangles and tetrahedra, got cell type %d", mesh->cell_type);
+    return PHIFEM_ERR_UNSUPPORTED;
+  }
+  if (n_entities == 0) return PHIFEM_OK;
+  PHIFEM_CHECK_ARG(entities && slots && data, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mesh->cell_type == PHIFEM_TRIANGLE)
+    k_assemble_boundary_neumann<2><<<(unsigned)((n_entities * 3 + kBlockPk - 1) / kBlockPk), kBlockPk, 0, st>>>(
+        *mesh, entities, n_entities, slots, data);
+  else
+    k_assemble_boundary_neumann<3><<<(unsigned)((n_entities * 4 + kBlockPk - 1) / kBlockPk), kBlockPk, 0, st>>>(
+        *mesh, entities, n_entities, slots, data);
+  PHIFEM_CHECK_LAUNCH();
+  return PHIFEM_OK;
+}
+
+extern "C" int phifem_assemble_neumann_ghost(const phifem_mesh* mesh, const phifem_quadrature* quad,
+                                             const int32_t* facets, int64_t n_facets, const int32_t* slots,
+                                             double sigma, double* data, void* stream) {
+  PHIFEM_CHECK_ARG(quad != nullptr, "quadrature is null");
+  phifem_pk_space p1{1, mesh && mesh->cell_type == PHIFEM_TRIANGLE ? 3 : 4, 0, nullptr};
+  if (int rc = check_pk(mesh, &p1, &p1, quad->facet_points, quad->facet_weights, quad->n_facet_points)) return rc;
+  if (n_facets == 0) return PHIFEM_OK;
+  PHIFEM_CHECK_ARG(data && mesh->c2f && mesh->f2c && facets && slots, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mesh->cell_type == PHIFEM_TRIANGLE) {
+    constexpr int NM = NeumannSpace<2>::NM;
+    k_assemble_ghost_weak_pk<2, 1, NM><<<(unsigned)((n_facets * 6 + kBlockPk - 1) / kBlockPk), kBlockPk, 0, st>>>(
+        *mesh, quad->facet_points, quad->facet_weights, quad->n_facet_points, facets, n_facets, slots, sigma, data);
+  } else {
+    constexpr int NM = NeumannSpace<3>::NM;
+    k_assemble_ghost_weak_pk<3, 1, NM><<<(unsigned)((n_facets * 8 + kBlockPk - 1) / kBlockPk), kBlockPk, 0, st>>>(
+        *mesh, quad->facet_points, quad->facet_weights, quad->n_facet_points, facets, n_facets, slots, sigma, data);
+  }
   PHIFEM_CHECK_LAUNCH();
   return PHIFEM_OK;
 }

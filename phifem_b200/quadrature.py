@@ -202,3 +202,10 @@ def rules_for_weak(d, kw, kphi):
     penalty block phi^2 p q needs degree 2 (kw + kphi) on cells; the facet terms (grad u.n) v and the gradient
     jumps need 2 kw - 1."""
     return simplex_rule(d, 2 * (kw + kphi)), simplex_rule(d - 1, max(1, 2 * kw - 1))
+
+
+def rules_for_neumann(d, kphi):
+    """Cell and facet rules of the Neumann forms (demo/neumann/square/main.py:117-158) for P1 u / y and a P_kphi
+    level set: the penalty block (y.grad phi + p phi / h)^2 has degree 2 (kphi + 1) at most (|grad phi_h| in the
+    load term is not polynomial for kphi = 2: integrated by the same rule); the facet terms are constant / linear."""
+    return simplex_rule(d, 2 * (kphi + 1)), simplex_rule(d - 1, 2)

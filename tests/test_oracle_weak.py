@@ -65,3 +65,41 @@ def test_weak_symbolic_phase_matches_oracle_pattern(kind, n, k):
         for b in (1, nm // 2 + 1):
             assert np.array_equal(rows[sl[a, b]], mixed[active][:, a])
             assert np.array_equal(ix[sl[a, b]], mixed[active][:, b])
+
+
+@pytest.mark.parametrize("kind,n", [("tri", 8), ("tet", 3)])
+def test_neumann_closed_form_equals_quadrature_and_symbolic_phase(kind, n):
+    """Neumann operator (demo/neumann/square/main.py:103-158): the two restatements agree; the product's symbolic
+    phase for the mixed space (u, y, p) reproduces the oracle's pattern and numbering."""
+    mesh, x, cells, ph, out = _case(kind, n)
+    rng = np.random.default_rng(0)
+    f, un = rng.uniform(-1, 1, len(x)), rng.uniform(-1, 1, len(x))
+    args = (x, cells, ph, f, un, out["cell_tags"], out["facet_tags"], out["c2f"], out["f2c"], out["ds100"])
+    a = OA.assemble_neumann(*args, gamma=1.3, sigma=0.7)
+    q = OA.assemble_neumann(*args, gamma=1.3, sigma=0.7, method="quadrature")
+    assert np.array_equal(a[0], q[0]) and np.array_equal(a[1], q[1])
+    assert np.abs(a[2] - q[2]).max() <= 1e-13 * np.abs(a[2]).max()
+    assert np.abs(a[3] - q[3]).max() <= 1e-13 * np.abs(a[3]).max()
+    d = x.shape[1]
+    nrows = (d + 1) * len(x) + len(cells)
+    M = OA.to_scipy(a[0], a[1], a[2], nrows)
+    # the cell part of the form is symmetric; only int_ds (y.n) v is not: remove it and compare
+    Ab = OA.neumann_boundary_tensors(x, cells, out["ds100"])
+    mixed = OA.neumann_mixed_dofmap(cells, len(x))
+    import scipy.sparse as sp
+    ents = np.asarray(out["ds100"]).reshape(-1, 2)
+    dmb = mixed[ents[:, 0]]
+    nm = mixed.shape[1]
+    B = sp.coo_matrix((Ab.ravel(), (np.repeat(dmb, nm, axis=1).ravel(), np.tile(dmb, (1, nm)).ravel())),
+                      shape=(nrows, nrows)).tocsr()
+    S = M - B
+    assert abs(S - S.T).max() <= 1e-13 * abs(M).max()
+    V = fem.functionspace(mesh, 1)
+    ct8 = torch.from_numpy(out["cell_tags"].astype(np.int8))
+    ft8 = torch.from_numpy(out["facet_tags"].astype(np.int8))
+    ents_t = torch.from_numpy(np.asarray(out["ds100"], dtype=np.int32))
+    plan = PkAssemblyPlan(mesh, ct8, ft8, ents_t, V, V, form="neumann")
+    assert plan.n_rows == nrows and np.array_equal(plan.pattern_dofmap.numpy(), mixed)
+    assert np.array_equal(plan.indptr.numpy(), a[0]) and np.array_equal(plan.indices.numpy(), a[1])
+    assert np.array_equal(plan.ghost.numpy(),
+                          np.nonzero((out["facet_tags"] == 3) & (out["f2c"][:, 1] >= 0))[0])
