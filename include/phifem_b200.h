@@ -331,13 +331,15 @@ int phifem_csr_spmv(int64_t n_rows, const int32_t* indptr, const int32_t* indice
  * set.  Cell-local mixed dof order [u at the vertices, y node-major (vertex i, component c -> nv + i d + c), p]
  * (nm = nv (1 + d) + 1); the global mixed numbering is the caller's (`mixed_dofmap` [n_cells, nm];
  * phifem_b200/assemble_pk.py numbers u at vertex s as (d+1) s, y_c as (d+1) s + 1 + c, p of cell k as (d+1) Nv + k).
- * `f` and `u_n` are P1 (vertex values).  Slot maps: cells entry-major [nm*nm, n_active], one-sided entities
+ * `f` and `u_n` are P1 (vertex values).  robin_coef != 0 turns the penalty combination into
+ * y.grad phi - |grad phi| robin_coef u + h^-1 p phi: the Robin operator of demo/robin/square/main.py:118-174 (u_n = the
+ * Robin data; its ghost penalty runs over dS(2): pass those facets to phifem_assemble_neumann_ghost).  Slot maps: cells entry-major [nm*nm, n_active], one-sided entities
  * [n, nm*nm], interior facets tagged 3 [n, (2 nm)^2] (macro order [mixed dofs of cell +, of cell -]).  ADD semantics. */
 int phifem_assemble_neumann_cells(const phifem_mesh* mesh, const phifem_pk_space* space_phi,
                                   const phifem_quadrature* quad, const double* phi, const double* f,
                                   const double* u_n, const int8_t* cell_tags8, const int32_t* active,
                                   int64_t n_active, const int32_t* slots, const int32_t* mixed_dofmap, double gamma,
-                                  double* data, double* b, void* stream);
+                                  double robin_coef, double* data, double* b, void* stream);
 
 /* int_{ds(100)} (y.n) v (:120). */
 int phifem_assemble_neumann_boundary(const phifem_mesh* mesh, const int32_t* entities, int64_t n_entities,

@@ -618,8 +618,9 @@ def neumann_mixed_dofmap(cells, n_vertices):
     return np.concatenate([u, y, p], axis=1)
 
 
-def _neumann_fields(lam, G, pc, kphi, h):
-    """Per quadrature point and mixed basis function: u, grad u, s1, s2, s3; plus phi, grad phi."""
+def _neumann_fields(lam, G, pc, kphi, h, kappa=0.0):
+    """Per quadrature point and mixed basis function: u, grad u, s1, s2, s3; plus phi, grad phi.  kappa = the Robin
+    coefficient (demo/robin/square/main.py:124-133: s3 = y.grad phi - |grad phi| kappa u + h^-1 p phi; 0 = Neumann)."""
     nq, nv = lam.shape
     d = nv - 1
     nm = nv * (1 + d) + 1
@@ -631,11 +632,13 @@ def _neumann_fields(lam, G, pc, kphi, h):
     S1 = np.zeros((nq, nm, d))
     S2 = np.zeros((nq, nm))
     S3 = np.zeros((nq, nm))
+    ngp = np.sqrt((gph ** 2).sum(axis=1))
     for j in range(nv):
         U[:, j] = lam[:, j]
         GU[:, j, :] = G[j][None, :]
         S1[:, j, :] = G[j][None, :]
         S2[:, j] = lam[:, j]
+        S3[:, j] = -kappa * ngp * lam[:, j]
         for c in range(d):
             k = nv + j * d + c
             S1[:, k, c] = lam[:, j]
@@ -645,7 +648,8 @@ def _neumann_fields(lam, G, pc, kphi, h):
     return U, GU, S1, S2, S3, ph, gph
 
 
-def neumann_cell_tensors_quadrature(x, cells, phi_dofs, f_dofs, un_dofs, cut, gamma, kphi=1, n=6, rule=None):
+def neumann_cell_tensors_quadrature(x, cells, phi_dofs, f_dofs, un_dofs, cut, gamma, kphi=1, n=6, rule=None,
+                                    kappa=0.0):
     """rule = (barycentric points, weights summing to 1): use this rule instead of the degree-11 one -- for a P2
     level set the load term holds |grad phi_h| (not polynomial), so the result depends on the rule."""
     d = x.shape[1]
@@ -655,7 +659,7 @@ def neumann_cell_tensors_quadrature(x, cells, phi_dofs, f_dofs, un_dofs, cut, ga
         lam, W = np.asarray(rule[0]), np.asarray(rule[1]) / math.factorial(d)
     out_A, out_b = [], []
     for c in range(len(cells)):
-        U, GU, S1, S2, S3, ph, gph = _neumann_fields(lam, G[c], phi_dofs[c], kphi, h[c])
+        U, GU, S1, S2, S3, ph, gph = _neumann_fields(lam, G[c], phi_dofs[c], kphi, h[c], kappa)
         wq = W * math.factorial(d) * vol[c]
         fq = lam @ f_dofs[c]
         A = np.einsum("q,qad,qbd->ab", wq, GU, GU) + np.einsum("q,qa,qb->ab", wq, U, U)
@@ -672,7 +676,7 @@ def neumann_cell_tensors_quadrature(x, cells, phi_dofs, f_dofs, un_dofs, cut, ga
     return np.array(out_A), np.array(out_b)
 
 
-def neumann_cell_tensors_closed_form(x, cells, phi, f, un, cut, gamma):
+def neumann_cell_tensors_closed_form(x, cells, phi, f, un, cut, gamma, kappa=0.0):
     """P1 level set: every integrand is polynomial (grad phi constant per cell); exact monomial integrals."""
     d = x.shape[1]
     nv = d + 1
@@ -708,6 +712,19 @@ def neumann_cell_tensors_closed_form(x, cells, phi, f, un, cut, gamma):
             b[:, a] = cg * vol * (-ng * g[:, c] * (uv @ M[:, i]) / h ** 2 + G[:, i, c] * fbar)
     A[:, nm - 1, nm - 1] = cg * vol * np.einsum("nk,nl,kl->n", p, p, M) / h ** 4
     b[:, nm - 1] = -cg * vol * ng * np.einsum("nk,nl,kl->n", uv, p, M) / h ** 3
+    if kappa != 0.0:   # Robin: s3 of u_j gains -kappa |g| lambda_j
+        kg = kappa * ng
+        A[:, :nv, :nv] += (cg * vol * kg * kg / h ** 2)[:, None, None] * M[None]
+        for i in range(nv):
+            for c in range(d):
+                a = yi(i, c)
+                t = -(cg * vol * kg * g[:, c] / h ** 2)[:, None] * M[i][None, :]
+                A[:, a, :nv] += t
+                A[:, :nv, a] += t
+        t = -(cg * vol * kg / h ** 3)[:, None] * (p @ M)
+        A[:, nm - 1, :nv] += t
+        A[:, :nv, nm - 1] += t
+        b[:, :nv] += (cg * vol * ng * kg / h ** 2)[:, None] * (uv @ M)
     return A, b
 
 
@@ -754,15 +771,16 @@ def neumann_ghost_tensors(x, cells, c2f, f2c, facets, sigma):
 
 
 def assemble_neumann(x, cells, phi, f, un, cell_tags, facet_tags, c2f, f2c, ds100, gamma=1.0, sigma=1.0,
-                     method="closed_form", kphi=1, phi_dofmap=None, rule=None):
-    """(indptr, indices, data, b) of the Neumann operator in box mode on the mixed numbering above."""
+                     method="closed_form", kphi=1, phi_dofmap=None, rule=None, robin_coef=0.0, ghost_tag=3):
+    """(indptr, indices, data, b) of the Neumann operator in box mode on the mixed numbering above.  robin_coef != 0
+    with ghost_tag = 2 gives the Robin operator of demo/robin/square/main.py:118-174 (`un` = the Robin data u_R)."""
     nvtx = len(x)
     d = x.shape[1]
     mixed = neumann_mixed_dofmap(cells, nvtx)
     n_rows = (d + 1) * nvtx + len(cells)
     phi_dofmap = cells if phi_dofmap is None else phi_dofmap
     active = np.nonzero((cell_tags == 1) | (cell_tags == 2))[0]
-    ghost = np.nonzero((facet_tags == 3) & (f2c[:, 1] >= 0))[0]
+    ghost = np.nonzero((facet_tags == ghost_tag) & (f2c[:, 1] >= 0))[0]
     ents = np.asarray(ds100).reshape(-1, 2)
     indptr, indices = sparsity_pattern(n_rows, mixed, active, ghost, f2c)
     data = np.zeros(len(indices))
@@ -770,10 +788,10 @@ def assemble_neumann(x, cells, phi, f, un, cell_tags, facet_tags, c2f, f2c, ds10
     cut = cell_tags[active] == 2
     if method == "closed_form":
         assert kphi == 1
-        A, be = neumann_cell_tensors_closed_form(x, cells[active], phi, f, un, cut, gamma)
+        A, be = neumann_cell_tensors_closed_form(x, cells[active], phi, f, un, cut, gamma, robin_coef)
     else:
         A, be = neumann_cell_tensors_quadrature(x, cells[active], phi[phi_dofmap[active]], f[cells[active]],
-                                                un[cells[active]], cut, gamma, kphi, rule=rule)
+                                                un[cells[active]], cut, gamma, kphi, rule=rule, kappa=robin_coef)
     Ab = neumann_boundary_tensors(x, cells, ents)
     Eg = neumann_ghost_tensors(x, cells, c2f, f2c, ghost, sigma)
     nm = mixed.shape[1]

@@ -283,30 +283,33 @@ def assemble_weak_dirichlet(plan, phi_h, f_h, u_D=None, pen_coef=1.0, stab_coef=
     return CSRMatrix(plan.indptr, plan.indices, data, (plan.n_rows, plan.n_rows)), b
 
 
-def build_plan_neumann(mesh, cells_tags, facets_tags, ds=None, V_phi=None):
+def build_plan_neumann(mesh, cells_tags, facets_tags, ds=None, V_phi=None, ghost_tag=3):
     """Symbolic phase for `a` and `L` of the Neumann demo (reference demo/neumann/square/main.py:103-158): mixed space
     (u, y, p) in P1 x P1^d x DG0 (`mixed_space`, main.py:71-79) on triangles / tetrahedra, level-set space `V_phi`
     (P1 or P2; default P1).  Mixed vector layout: u at vertex s -> (d+1) s, y_c -> (d+1) s + 1 + c, p of cell k ->
-    (d+1) Nv + k (`plan.split(x)` returns the three fields)."""
+    (d+1) Nv + k (`plan.split(x)` returns the three fields).  ghost_tag: facets of the gradient-jump term, dS(3) in the
+    Neumann demo (main.py:136-139), dS(2) in the Robin demo (demo/robin/square/main.py:143-150)."""
     from . import fem
     from .assemble_pk import PkAssemblyPlan
     V = fem.functionspace(mesh, 1)
     V_phi = V if V_phi is None else V_phi
     c8, f8, ents = _plan_inputs(mesh, cells_tags, facets_tags, ds)
-    plan = PkAssemblyPlan(mesh, c8, f8, ents, V, V_phi, form="neumann")
+    plan = PkAssemblyPlan(mesh, c8, f8, ents, V, V_phi, form="neumann", ghost_tag=ghost_tag)
     d, nv = mesh.gdim, mesh.num_vertices
     plan.split = lambda x: (x[:(d + 1) * nv].reshape(nv, d + 1)[:, 0], x[:(d + 1) * nv].reshape(nv, d + 1)[:, 1:],
                             x[(d + 1) * nv:])
     return plan
 
 
-def assemble_neumann(plan, phi_h, f_h, u_N, pen_coef=1.0, stab_coef=1.0):
-    """A (CSR over the mixed dofs) and b of reference demo/neumann/square/main.py:117-161; `f_h`, `u_N` are P1."""
+def assemble_neumann(plan, phi_h, f_h, u_N, pen_coef=1.0, stab_coef=1.0, robin_coef=0.0):
+    """A (CSR over the mixed dofs) and b of reference demo/neumann/square/main.py:117-161; `f_h`, `u_N` are P1.
+    robin_coef != 0 (with a plan built with ghost_tag=2): the Robin operator of demo/robin/square/main.py:118-174,
+    `u_N` being the Robin data u_R."""
     from .assemble_pk import assemble_neumann_into
     mesh = plan.mesh
     phi = _device_vector(mesh, phi_h, plan.V_phi)
     f = _device_vector(mesh, f_h, plan.V)
     un = _device_vector(mesh, u_N, plan.V)
     data, b = plan.new_outputs()
-    assemble_neumann_into(plan, phi, f, un, pen_coef, stab_coef, data, b)
+    assemble_neumann_into(plan, phi, f, un, pen_coef, stab_coef, data, b, robin_coef=robin_coef)
     return CSRMatrix(plan.indptr, plan.indices, data, (plan.n_rows, plan.n_rows)), b

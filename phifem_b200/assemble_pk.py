@@ -24,7 +24,7 @@ class PkAssemblyPlan:
     rowsplan = None
     blocked = None
 
-    def __init__(self, mesh, cell_tags8, facet_tags8, entities, V, V_phi, form="strong"):
+    def __init__(self, mesh, cell_tags8, facet_tags8, entities, V, V_phi, form="strong", ghost_tag=None):
         """form = "strong": strong-Dirichlet operator on V; form = "weak": weak-Dirichlet (dual) operator on
         the mixed space V x V, u at scalar dof s numbered 2 s, p numbered 2 s + 1 (cell-local order
         [u dofs, p dofs])."""
@@ -64,7 +64,10 @@ class PkAssemblyPlan:
         nd = int(self.pattern_dofmap.shape[1])       # dofs per cell of the assembled (possibly mixed) space
         self.active = torch.nonzero((cell_tags8 == 1) | (cell_tags8 == 2)).reshape(-1).to(torch.int32)
         interior = mesh.f2c[:, 1] >= 0
-        gmask = (facet_tags8 == 3) if form == "neumann" else ((facet_tags8 == 2) | (facet_tags8 == 3))
+        if form == "neumann":      # dS(3) for the Neumann demo, dS(2) for the Robin demo
+            gmask = facet_tags8 == (3 if ghost_tag is None else int(ghost_tag))
+        else:
+            gmask = (facet_tags8 == 2) | (facet_tags8 == 3)
         self.ghost = torch.nonzero(gmask & interior).reshape(-1).to(torch.int32)   # dS(3) resp. dS((2,3))
         self.entities = entities.reshape(-1, 2).to(torch.int32).contiguous()
 
@@ -182,7 +185,7 @@ def assemble_weak_into(plan, phi, f, u_d, gamma, sigma, data, b):
     return data, b
 
 
-def assemble_neumann_into(plan, phi, f, u_n, gamma, sigma, data, b):
+def assemble_neumann_into(plan, phi, f, u_n, gamma, sigma, data, b, robin_coef=0.0):
     """Numeric phase of the Neumann operator (plan.form == "neumann") on the current stream."""
     mesh = plan.mesh
     _lib.require_cuda(mesh)
@@ -197,7 +200,7 @@ def assemble_neumann_into(plan, phi, f, u_n, gamma, sigma, data, b):
     _lib.check(lib.phifem_assemble_neumann_cells(
         cm, ctypes.byref(cp), ctypes.byref(cq), _lib.ptr(phi), _lib.ptr(f), _lib.ptr(u_n),
         _lib.ptr(plan.cell_tags8), _lib.ptr(plan.active), plan.active.numel(), _lib.ptr(plan.slots_cells),
-        _lib.ptr(plan.pattern_dofmap), float(gamma), _lib.ptr(data), _lib.ptr(b), st))
+        _lib.ptr(plan.pattern_dofmap), float(gamma), float(robin_coef), _lib.ptr(data), _lib.ptr(b), st))
     _lib.check(lib.phifem_assemble_neumann_boundary(
         cm, _lib.ptr(plan.entities), plan.entities.shape[0], _lib.ptr(plan.slots_boundary), _lib.ptr(data), st))
     _lib.check(lib.phifem_assemble_neumann_ghost(

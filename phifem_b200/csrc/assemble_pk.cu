@@ -778,7 +778,7 @@ struct NeumannSpace {
 // the tuple (u, grad u, s1, s2, s3) of mixed basis function m at a point (lam = P1 basis values, G their gradients)
 template <int D>
 __device__ __forceinline__ void neumann_basis(int m, const double (&lam)[D + 1], const double (&G)[D + 1][D],
-                                              const double (&gph)[D], double ph_over_h, double& U,
+                                              const double (&gph)[D], double ph_over_h, double kappa_ngp, double& U,
                                               double (&GU)[D], double (&S1)[D], double& S2, double& S3) {
   constexpr int NV = D + 1, NM = NeumannSpace<D>::NM;
   U = 0.0;
@@ -805,6 +805,7 @@ __device__ __forceinline__ void neumann_basis(int m, const double (&lam)[D + 1],
   if (is_u) {
     U = lj;
     S2 = lj;
+    S3 = -kappa_ngp * lj;  // Robin: s3 = y.grad phi - |grad phi| kappa u + h^-1 p phi (demo/robin/square/main.py:124-133)
 #pragma unroll
     for (int d = 0; d < D; ++d) GU[d] = S1[d] = Gj[d];
   } else {
@@ -823,7 +824,7 @@ __global__ void __launch_bounds__(kBlockPk) k_assemble_cells_neumann(
     phifem_mesh m, phifem_pk_space sp, const double* __restrict__ qlam_g, const double* __restrict__ qw_g, int nq,
     const double* __restrict__ phi, const double* __restrict__ f, const double* __restrict__ un,
     const int8_t* __restrict__ ctags, const int32_t* __restrict__ active, int64_t n_active,
-    const int32_t* __restrict__ slots, const int32_t* __restrict__ mixed_dofmap, double gamma,
+    const int32_t* __restrict__ slots, const int32_t* __restrict__ mixed_dofmap, double gamma, double kappa,
     double* __restrict__ data, double* __restrict__ b) {
   constexpr int NV = D + 1, NDP = Space<D, KP>::ND, NM = NeumannSpace<D>::NM;
   __shared__ double qlam[kMaxQuadPoints * NV], qw[kMaxQuadPoints];
@@ -865,13 +866,14 @@ __global__ void __launch_bounds__(kBlockPk) k_assemble_cells_neumann(
       fq += fc[k] * lam[k];
       uq += uc[k] * lam[k];
     }
+    const double ngp = sqrt(dotd<D>(gph, gph));
     double Ua, GUa[D], S1a[D], S2a, S3a;
-    neumann_basis<D>(a, lam, g.G, gph, ph * rh, Ua, GUa, S1a, S2a, S3a);
-    bv += w * (fq * Ua + pen * (fq * S2a - rh2 * uq * sqrt(dotd<D>(gph, gph)) * S3a));
+    neumann_basis<D>(a, lam, g.G, gph, ph * rh, kappa * ngp, Ua, GUa, S1a, S2a, S3a);
+    bv += w * (fq * Ua + pen * (fq * S2a - rh2 * uq * ngp * S3a));
 #pragma unroll
     for (int bb = 0; bb < NM; ++bb) {
       double Ub, GUb[D], S1b[D], S2b, S3b;
-      neumann_basis<D>(bb, lam, g.G, gph, ph * rh, Ub, GUb, S1b, S2b, S3b);
+      neumann_basis<D>(bb, lam, g.G, gph, ph * rh, kappa * ngp, Ub, GUb, S1b, S2b, S3b);
       A[bb] += w * (dotd<D>(GUa, GUb) + Ua * Ub + pen * (dotd<D>(S1a, S1b) + S2a * S2b + rh2 * S3a * S3b));
     }
   }
@@ -1093,7 +1095,8 @@ extern "C" int phifem_assemble_neumann_cells(const phifem_mesh* mesh, const phif
                                              const phifem_quadrature* quad, const double* phi, const double* f,
                                              const double* u_n, const int8_t* cell_tags8, const int32_t* active,
                                              int64_t n_active, const int32_t* slots, const int32_t* mixed_dofmap,
-                                             double gamma, double* data, double* b, void* stream) {
+                                             double gamma, double robin_coef, double* data, double* b,
+                                             void* stream) {
   PHIFEM_CHECK_ARG(quad != nullptr && space_phi != nullptr, "quadrature / level-set space is null");
   phifem_pk_space p1{1, mesh && mesh->cell_type == PHIFEM_TRIANGLE ? 3 : 4, 0, nullptr};
   if (int rc = check_pk(mesh, &p1, space_phi, quad->cell_points, quad->cell_weights, quad->n_cell_points)) return rc;
@@ -1105,7 +1108,7 @@ extern "C" int phifem_assemble_neumann_cells(const phifem_mesh* mesh, const phif
     const int64_t threads = n_active * NeumannSpace<D>::NM;
     k_assemble_cells_neumann<D, KP><<<(unsigned)((threads + kBlockPk - 1) / kBlockPk), kBlockPk, 0, st>>>(
         *mesh, *space_phi, quad->cell_points, quad->cell_weights, quad->n_cell_points, phi, f, u_n, cell_tags8,
-        active, n_active, slots, mixed_dofmap, gamma, data, b);
+        active, n_active, slots, mixed_dofmap, gamma, robin_coef, data, b);
   });
   PHIFEM_CHECK_LAUNCH();
   return PHIFEM_OK;

@@ -21,9 +21,11 @@ def _row_scale(indptr, data):
     return scale, rows
 
 
-@pytest.mark.parametrize("kphi", [1, 2])
+@pytest.mark.parametrize("kphi,robin", [(1, 0.0), (2, 0.0), (1, 0.8), (2, 0.8)])
 @pytest.mark.parametrize("kind,n", [("tri", 14), ("tri-unstructured", 10), ("tet", 5), ("tet-unstructured", 4)])
-def test_neumann_operator_matches_oracle(kind, n, kphi):
+def test_neumann_operator_matches_oracle(kind, n, kphi, robin):
+    """robin = 0: demo/neumann (gradient jumps over dS(3)); robin != 0: demo/robin (over dS(2))."""
+    gtag = 2 if robin else 3
     if kind.startswith("tri"):
         mesh = synthetic.rectangle_mesh(n, device="cuda")
         center, radius = (0.013, -0.021), 0.61
@@ -41,8 +43,8 @@ def test_neumann_operator_matches_oracle(kind, n, kphi):
     rng = np.random.default_rng(77)
     f = torch.from_numpy(rng.uniform(-1, 1, mesh.num_vertices)).cuda()
     un = torch.from_numpy(rng.uniform(-1, 1, mesh.num_vertices)).cuda()
-    plan = assemble.build_plan_neumann(mesh, ctags, ftags, ds(100), V_phi=Vp)
-    A, b = assemble.assemble_neumann(plan, phi, f, un, pen_coef=1.3, stab_coef=0.7)
+    plan = assemble.build_plan_neumann(mesh, ctags, ftags, ds(100), V_phi=Vp, ghost_tag=gtag)
+    A, b = assemble.assemble_neumann(plan, phi, f, un, pen_coef=1.3, stab_coef=0.7, robin_coef=robin)
     d = mesh.gdim
     assert A.shape[0] == (d + 1) * mesh.num_vertices + mesh.num_cells
     assert plan.ghost.numel() > 0 and plan.entities.shape[0] > 0
@@ -55,7 +57,7 @@ def test_neumann_operator_matches_oracle(kind, n, kphi):
         method="closed_form" if kphi == 1 else "quadrature", kphi=kphi, phi_dofmap=Vp.dofmap.astype(np.int64),
         # P2 level set: |grad phi_h| in the load term is not polynomial, the value depends on the rule (dolfinx would
         # use the rule of UFL's estimated degree): compare on the kernel's rule
-        rule=quadrature.rules_for_neumann(d, 2)[0] if kphi == 2 else None)
+        rule=quadrature.rules_for_neumann(d, 2)[0] if kphi == 2 else None, robin_coef=robin, ghost_tag=gtag)
     assert np.array_equal(A.indptr.cpu().numpy(), ip) and np.array_equal(A.indices.cpu().numpy(), ix)
     scale, rows = _row_scale(ip, data)
     gs = np.abs(data).max()
