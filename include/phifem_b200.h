@@ -349,6 +349,48 @@ int phifem_assemble_neumann_boundary(const phifem_mesh* mesh, const int32_t* ent
 int phifem_assemble_neumann_ghost(const phifem_mesh* mesh, const phifem_quadrature* quad, const int32_t* facets,
                                   int64_t n_facets, const int32_t* slots, double sigma, double* data, void* stream);
 
+/* ---- interface-elasticity phi-FEM operator on the mixed space (u_in, u_out, y_in, y_out, p) in
+ * P1^d x P1^d x P1^(d x d) x P1^(d x d) x P1^d: demo/interface-elasticity/main.py:152-274 (`assemble_matrix(form(a), bcs)`
+ * :238-240, `assemble_vector(form(L))` :271, `apply_lifting` / `bc.set` :273-275), triangles and tetrahedra, P1 or P2
+ * level set.  Every field is nodal, so the mixed space has NB = 3 d + 2 d^2 dofs per vertex: global dof = NB vertex + o,
+ * o: u_in c -> c, u_out c -> d + c, y_in (r,s) -> 2d + r d + s, y_out (r,s) -> 2d + d^2 + r d + s, p c -> 2d + 2d^2 + c.
+ * The CSR matrix is the vertex graph (`vptr` [n_vertices + 1], sorted neighbour lists: vertex pairs of every tagged cell
+ * and of the macro elements of the interior facets tagged 3 / 4) with dense NB x NB blocks: entry (NB r + a, NB s + b)
+ * at NB (NB vptr[r] + a deg(r) + pos) + b, pos = rank of s among r's neighbours.  Slot maps hold `pos` per vertex pair:
+ * cells [n_cells, nv*nv], facets [n, (2 nv)^2] (macro order [vertices of cell +, of cell -]), entities [n, nv*nv]
+ * (row = test vertex).  `f` is a P1 vector field [n_vertices, d].  ADD semantics; `data` / `b` zeroed by the caller. */
+typedef struct phifem_elasticity_params {
+  double lmbda_in, mu_in;    /* Lame coefficients of data.py:5-22 */
+  double lmbda_out, mu_out;
+  double coef_in, coef_out;  /* (E_in / (E_in + E_out))^2, (E_out / (E_in + E_out))^2 (main.py:189-190) */
+  double gamma;              /* penalization_coefficient */
+  double sigma_s;            /* stabilization_coefficient */
+} phifem_elasticity_params;
+
+/* All cell integrals of `a` and `L` (dx((1,2)), dx((2,3)), dx(2)); cells with another tag are skipped. */
+int phifem_assemble_elasticity_cells(const phifem_mesh* mesh, const phifem_pk_space* space_phi,
+                                     const phifem_quadrature* quad, const double* phi, const double* f,
+                                     const int8_t* cell_tags8, const int32_t* vptr, const int32_t* pos_cells,
+                                     const phifem_elasticity_params* prm, double* data, double* b, void* stream);
+
+/* sigma_s avg(h_T) [sigma(u) n].[sigma(v) n] over the given interior facets: side 0 = sigma_in / u_in over dS(3)
+ * (:207-211), side 1 = sigma_out / u_out over dS(4) (:221-225). */
+int phifem_assemble_elasticity_facets(const phifem_mesh* mesh, const int32_t* facets, int64_t n_facets,
+                                      const int32_t* vptr, const int32_t* pos_facets, int32_t side,
+                                      const phifem_elasticity_params* prm, double* data, void* stream);
+
+/* int (y n).v over one-sided entities [cell, local facet]: side 0 = (y_in, v_in) over ds(100), side 1 = (y_out, v_out)
+ * over ds(101) (:183-184, 235-236). */
+int phifem_assemble_elasticity_boundary(const phifem_mesh* mesh, const int32_t* entities, int64_t n_entities,
+                                        const int32_t* vptr, const int32_t* pos_boundary, int32_t side, double* data,
+                                        void* stream);
+
+/* Dirichlet conditions on an assembled CSR system (dolfinx `assemble_matrix(a, bcs)` + `apply_lifting` + `bc.set`,
+ * main.py:238, 273-275): rows and columns of the marked dofs are zeroed (entries stay in the pattern), their diagonal
+ * is 1, b <- b - A g on the free rows, b = g on the marked ones.  bc_marker int8 [n_rows], bc_values [n_rows]. */
+int phifem_apply_dirichlet(int64_t n_rows, const int32_t* indptr, const int32_t* indices, const int8_t* bc_marker,
+                           const double* bc_values, double* data, double* b, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,11 @@ class CQuadrature(ctypes.Structure):
                 ("cell_points", _vp), ("cell_weights", _vp), ("facet_points", _vp), ("facet_weights", _vp)]
 
 
+class CElasticityParams(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_double) for n in ("lmbda_in", "mu_in", "lmbda_out", "mu_out", "coef_in", "coef_out",
+                                               "gamma", "sigma_s")]
+
+
 _PK_HEAD = [ctypes.POINTER(CMesh), ctypes.POINTER(CPkSpace), ctypes.POINTER(CPkSpace),
             ctypes.POINTER(CQuadrature)]
 
@@ -111,6 +116,14 @@ _SIGNATURES = {
     "phifem_assemble_weak_ghost_pk": (ctypes.c_int, [ctypes.POINTER(CMesh), ctypes.POINTER(CPkSpace),
                                                      ctypes.POINTER(CQuadrature), _vp, ctypes.c_int64, _vp,
                                                      ctypes.c_double, _vp, _vp]),
+    "phifem_assemble_elasticity_cells": (ctypes.c_int, [ctypes.POINTER(CMesh), ctypes.POINTER(CPkSpace),
+                                                        ctypes.POINTER(CQuadrature), _vp, _vp, _vp, _vp, _vp,
+                                                        ctypes.POINTER(CElasticityParams), _vp, _vp, _vp]),
+    "phifem_assemble_elasticity_facets": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, ctypes.c_int64, _vp, _vp,
+                                                         ctypes.c_int32, ctypes.POINTER(CElasticityParams), _vp, _vp]),
+    "phifem_assemble_elasticity_boundary": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, ctypes.c_int64, _vp, _vp,
+                                                           ctypes.c_int32, _vp, _vp]),
+    "phifem_apply_dirichlet": (ctypes.c_int, [ctypes.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
