@@ -335,11 +335,14 @@ int phifem_csr_spmv(int64_t n_rows, const int32_t* indptr, const int32_t* indice
  * y.grad phi - |grad phi| robin_coef u + h^-1 p phi: the Robin operator of demo/robin/square/main.py:118-174 (u_n = the
  * Robin data; its ghost penalty runs over dS(2): pass those facets to phifem_assemble_neumann_ghost).  Slot maps: cells entry-major [nm*nm, n_active], one-sided entities
  * [n, nm*nm], interior facets tagged 3 [n, (2 nm)^2] (macro order [mixed dofs of cell +, of cell -]).  ADD semantics. */
+/* `cut_positions` [n_cut]: positions in `active` of the cells tagged 2 (every term of the form, by quadrature); the
+ * other active cells carry the P1 stiffness + mass block of u only (closed form, a separate light kernel). */
 int phifem_assemble_neumann_cells(const phifem_mesh* mesh, const phifem_pk_space* space_phi,
                                   const phifem_quadrature* quad, const double* phi, const double* f,
                                   const double* u_n, const int8_t* cell_tags8, const int32_t* active,
-                                  int64_t n_active, const int32_t* slots, const int32_t* mixed_dofmap, double gamma,
-                                  double robin_coef, double* data, double* b, void* stream);
+                                  int64_t n_active, const int32_t* cut_positions, int64_t n_cut, const int32_t* slots,
+                                  const int32_t* mixed_dofmap, double gamma, double robin_coef, double* data,
+                                  double* b, void* stream);
 
 /* int_{ds(100)} (y.n) v (:120). */
 int phifem_assemble_neumann_boundary(const phifem_mesh* mesh, const int32_t* entities, int64_t n_entities,
@@ -367,10 +370,13 @@ typedef struct phifem_elasticity_params {
   double sigma_s;            /* stabilization_coefficient */
 } phifem_elasticity_params;
 
-/* All cell integrals of `a` and `L` (dx((1,2)), dx((2,3)), dx(2)); cells with another tag are skipped. */
+/* All cell integrals of `a` and `L` (dx((1,2)), dx((2,3)), dx(2)).  Cells tagged 1 / 3 (one closed-form stiffness block
+ * each) are found through cell_tags8, cells with another tag skipped; `cut_cells` [n_cut] lists the cells tagged 2, which
+ * carry every term of the form and are integrated by quadrature. */
 int phifem_assemble_elasticity_cells(const phifem_mesh* mesh, const phifem_pk_space* space_phi,
                                      const phifem_quadrature* quad, const double* phi, const double* f,
-                                     const int8_t* cell_tags8, const int32_t* vptr, const int32_t* pos_cells,
+                                     const int8_t* cell_tags8, const int32_t* cut_cells, int64_t n_cut,
+                                     const int32_t* vptr, const int32_t* pos_cells,
                                      const phifem_elasticity_params* prm, double* data, double* b, void* stream);
 
 /* sigma_s avg(h_T) [sigma(u) n].[sigma(v) n] over the given interior facets: side 0 = sigma_in / u_in over dS(3)

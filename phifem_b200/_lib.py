@@ -102,8 +102,8 @@ _SIGNATURES = {
                                                            _vp, _vp]),
     "phifem_assemble_neumann_cells": (ctypes.c_int, [ctypes.POINTER(CMesh), ctypes.POINTER(CPkSpace),
                                                      ctypes.POINTER(CQuadrature), _vp, _vp, _vp, _vp, _vp,
-                                                     ctypes.c_int64, _vp, _vp, ctypes.c_double, ctypes.c_double,
-                                                     _vp, _vp, _vp]),
+                                                     ctypes.c_int64, _vp, ctypes.c_int64, _vp, _vp, ctypes.c_double,
+                                                     ctypes.c_double, _vp, _vp, _vp]),
     "phifem_assemble_neumann_boundary": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, ctypes.c_int64, _vp, _vp, _vp]),
     "phifem_assemble_neumann_ghost": (ctypes.c_int, [ctypes.POINTER(CMesh), ctypes.POINTER(CQuadrature), _vp,
                                                      ctypes.c_int64, _vp, ctypes.c_double, _vp, _vp]),
@@ -117,8 +117,8 @@ _SIGNATURES = {
                                                      ctypes.POINTER(CQuadrature), _vp, ctypes.c_int64, _vp,
                                                      ctypes.c_double, _vp, _vp]),
     "phifem_assemble_elasticity_cells": (ctypes.c_int, [ctypes.POINTER(CMesh), ctypes.POINTER(CPkSpace),
-                                                        ctypes.POINTER(CQuadrature), _vp, _vp, _vp, _vp, _vp,
-                                                        ctypes.POINTER(CElasticityParams), _vp, _vp, _vp]),
+                                                        ctypes.POINTER(CQuadrature), _vp, _vp, _vp, _vp, ctypes.c_int64,
+                                                        _vp, _vp, ctypes.POINTER(CElasticityParams), _vp, _vp, _vp]),
     "phifem_assemble_elasticity_facets": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, ctypes.c_int64, _vp, _vp,
                                                          ctypes.c_int32, ctypes.POINTER(CElasticityParams), _vp, _vp]),
     "phifem_assemble_elasticity_boundary": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, ctypes.c_int64, _vp, _vp,

@@ -63,6 +63,8 @@ class PkAssemblyPlan:
             self.n_rows = n = int(V.num_dofs)
         nd = int(self.pattern_dofmap.shape[1])       # dofs per cell of the assembled (possibly mixed) space
         self.active = torch.nonzero((cell_tags8 == 1) | (cell_tags8 == 2)).reshape(-1).to(torch.int32)
+        # positions in `active` of the cut cells (the Neumann kernels integrate them apart from the interior cells)
+        self.cut_positions = torch.nonzero(cell_tags8[self.active.long()] == 2).reshape(-1).to(torch.int32)
         interior = mesh.f2c[:, 1] >= 0
         if form == "neumann":      # dS(3) for the Neumann demo, dS(2) for the Robin demo
             gmask = facet_tags8 == (3 if ghost_tag is None else int(ghost_tag))
@@ -199,8 +201,9 @@ def assemble_neumann_into(plan, phi, f, u_n, gamma, sigma, data, b, robin_coef=0
     b.zero_()
     _lib.check(lib.phifem_assemble_neumann_cells(
         cm, ctypes.byref(cp), ctypes.byref(cq), _lib.ptr(phi), _lib.ptr(f), _lib.ptr(u_n),
-        _lib.ptr(plan.cell_tags8), _lib.ptr(plan.active), plan.active.numel(), _lib.ptr(plan.slots_cells),
-        _lib.ptr(plan.pattern_dofmap), float(gamma), float(robin_coef), _lib.ptr(data), _lib.ptr(b), st))
+        _lib.ptr(plan.cell_tags8), _lib.ptr(plan.active), plan.active.numel(), _lib.ptr(plan.cut_positions),
+        plan.cut_positions.numel(), _lib.ptr(plan.slots_cells), _lib.ptr(plan.pattern_dofmap), float(gamma),
+        float(robin_coef), _lib.ptr(data), _lib.ptr(b), st))
     _lib.check(lib.phifem_assemble_neumann_boundary(
         cm, _lib.ptr(plan.entities), plan.entities.shape[0], _lib.ptr(plan.slots_boundary), _lib.ptr(data), st))
     _lib.check(lib.phifem_assemble_neumann_ghost(

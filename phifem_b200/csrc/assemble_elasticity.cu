@@ -17,7 +17,7 @@
 // NB (NB vptr[r] + a deg(r) + pos) + b, pos = rank of s in r's sorted vertex-neighbour list.  The only slot map
 // is therefore the scalar one (NV^2 ints per cell instead of (NV NB)^2).
 //
-// Cells: one thread per (cell, test node k, trial node j, trial offset b).  The trial function's quantities
+// Cut cells: one thread per (cell, test node k, trial node j, trial offset b).  The trial function's quantities
 // (T_in = y_in + sigma_in(u_in), T_out, R = (y_in - y_out) grad phi, S = u_in - u_out + p phi / h, div y_in, div y_out)
 // are a small runtime bundle; the NB test offsets are unrolled at compile time, so that each contraction holds only the
 // non-zero terms of its field.  Consecutive threads write consecutive CSR entries.
@@ -169,12 +169,65 @@ __device__ __forceinline__ int64_t block_address(const int32_t* __restrict__ vpt
   return (int64_t)nb * ((int64_t)nb * p0 + (int64_t)a * deg + pos) + b;
 }
 
+// Cells tagged 1 (resp. 3) carry the stiffness block of u_in (resp. u_out) and its load only, constant integrands:
+//   int sigma(u_b):eps(v_a) = |K| (lmbda G_k[c] G_j[c'] + mu (delta_cc' G_k.G_j + G_j[c] G_k[c'])),
+//   int f_c lambda_k = |K| sum_l f_l[c] (1 + delta_lk) / ((D+1)(D+2)).        One thread per (cell, k, j).
+template <int D>
+__global__ void __launch_bounds__(kBlockEl) k_elasticity_uncut(
+    phifem_mesh m, const double* __restrict__ f, const int8_t* __restrict__ ctags, const int32_t* __restrict__ vptr,
+    const int32_t* __restrict__ pos_cells, phifem_elasticity_params prm, double* __restrict__ data,
+    double* __restrict__ b) {
+  using S_ = ES<D>;
+  constexpr int NV = S_::NV, NB = S_::NB;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m.n_cells * (NV * NV)) return;
+  const int64_t c = t / (NV * NV);
+  const int rem = (int)(t - c * (NV * NV));
+  const int k = rem / NV, j = rem - k * NV;
+  const int tag = ctags[c];
+  if (tag != 1 && tag != 3) return;
+  const double lm = tag == 1 ? prm.lmbda_in : prm.lmbda_out, mu = tag == 1 ? prm.mu_in : prm.mu_out;
+  const int ou = tag == 1 ? S_::UI : S_::UO;
+  Geometry<D> g;
+  load_geometry<D>(m, c, g);
+  double Gk[D], Gj[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) Gk[d] = Gj[d] = 0.0;
+#pragma unroll
+  for (int n = 0; n < NV; ++n) {
+    if (n == k)
+#pragma unroll
+      for (int d = 0; d < D; ++d) Gk[d] = g.G[n][d];
+    if (n == j)
+#pragma unroll
+      for (int d = 0; d < D; ++d) Gj[d] = g.G[n][d];
+  }
+  const double gg = mu * dotd<D>(Gk, Gj);
+  const int vk = __ldg(m.cells + c * NV + k);
+  const int pos = __ldg(pos_cells + c * (NV * NV) + rem);
+#pragma unroll
+  for (int ca = 0; ca < D; ++ca)
+#pragma unroll
+    for (int cb = 0; cb < D; ++cb)
+      atomicAdd(data + block_address(vptr, vk, ou + ca, pos, ou + cb, NB),
+                g.vol * (lm * Gk[ca] * Gj[cb] + mu * Gj[ca] * Gk[cb] + (ca == cb ? gg : 0.0)));
+  if (j == k) {
+#pragma unroll
+    for (int ca = 0; ca < D; ++ca) {
+      double s = 0.0;
+#pragma unroll
+      for (int l = 0; l < NV; ++l) s += __ldg(f + (int64_t)__ldg(m.cells + c * NV + l) * D + ca) * (l == k ? 2.0 : 1.0);
+      atomicAdd(b + (int64_t)NB * vk + ou + ca, g.vol * s * (1.0 / ((D + 1) * (D + 2))));
+    }
+  }
+}
+
 template <int D, int KP>
 __global__ void __launch_bounds__(kBlockEl) k_elasticity_cells(
     phifem_mesh m, phifem_pk_space sp, const double* __restrict__ qlam_g, const double* __restrict__ qw_g, int nq,
-    const double* __restrict__ phi, const double* __restrict__ f, const int8_t* __restrict__ ctags,
-    const int32_t* __restrict__ vptr, const int32_t* __restrict__ pos_cells, phifem_elasticity_params prm,
-    double* __restrict__ data, double* __restrict__ b) {
+    const double* __restrict__ phi, const double* __restrict__ f, const int32_t* __restrict__ cut_cells,
+    int64_t n_cut, const int32_t* __restrict__ vptr, const int32_t* __restrict__ pos_cells,
+    phifem_elasticity_params prm, double* __restrict__ data, double* __restrict__ b) {
   using S_ = ES<D>;
   constexpr int NV = S_::NV, NB = S_::NB, NDP = Space<D, KP>::ND;
   __shared__ double qlam[kMaxQuadPoints * NV], qw[kMaxQuadPoints];
@@ -182,28 +235,24 @@ __global__ void __launch_bounds__(kBlockEl) k_elasticity_cells(
   for (int i = threadIdx.x; i < nq; i += blockDim.x) qw[i] = qw_g[i];
   __syncthreads();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= m.n_cells * (NV * NV * NB)) return;
-  const int64_t c = t / (NV * NV * NB);
-  int rem = (int)(t - c * (NV * NV * NB));
+  if (t >= n_cut * (NV * NV * NB)) return;
+  const int64_t e = t / (NV * NV * NB);
+  int rem = (int)(t - e * (NV * NV * NB));
   const int k = rem / (NV * NB);
   rem -= k * (NV * NB);
   const int j = rem / NB, ob = rem - j * NB;
-  const int tag = ctags[c];
-  if (tag < 1 || tag > 3) return;
-  const bool cut = tag == 2;
+  const int64_t c = __ldg(cut_cells + e);
   const int fld_b = S_::field(ob);
-  if (!cut && fld_b != (tag == 1 ? 0 : 1)) return;  // uncut cells carry one stiffness block only
   Geometry<D> g;
   load_geometry<D>(m, c, g);
   const double h = sqrt(g.h2);
   CellCoefs cf;
   cf.lmbda_in = prm.lmbda_in; cf.mu_in = prm.mu_in; cf.lmbda_out = prm.lmbda_out; cf.mu_out = prm.mu_out;
-  cf.w_in = tag <= 2 ? 1.0 : 0.0;
-  cf.w_out = tag >= 2 ? 1.0 : 0.0;
-  cf.pen_in = cut ? prm.gamma * prm.coef_out : 0.0;
-  cf.pen_out = cut ? prm.gamma * prm.coef_in : 0.0;
-  cf.pen_h2 = cut ? prm.gamma / g.h2 : 0.0;
-  cf.stab = cut ? prm.sigma_s * g.h2 : 0.0;
+  cf.w_in = cf.w_out = 1.0;
+  cf.pen_in = prm.gamma * prm.coef_out;
+  cf.pen_out = prm.gamma * prm.coef_in;
+  cf.pen_h2 = prm.gamma / g.h2;
+  cf.stab = prm.sigma_s * g.h2;
   double Gk[D], Gj[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) Gk[d] = Gj[d] = 0.0;
@@ -219,25 +268,18 @@ __global__ void __launch_bounds__(kBlockEl) k_elasticity_cells(
   double acc[NB];
 #pragma unroll
   for (int a = 0; a < NB; ++a) acc[a] = 0.0;
-  if (cut) {
-    double pc[NDP];
-    load_dofs<D, KP>(m, sp, phi, c, pc);
-    for (int q = 0; q < nq; ++q) {
-      double lam[NV];
+  double pc[NDP];
+  load_dofs<D, KP>(m, sp, phi, c, pc);
+  for (int q = 0; q < nq; ++q) {
+    double lam[NV];
 #pragma unroll
-      for (int n = 0; n < NV; ++n) lam[n] = qlam[q * NV + n];
-      double ph, gph[D];
-      eval_phi_only<D, KP>(lam, g.G, pc, ph, gph);
-      const double lk = pick<NV>(lam, k), lj = pick<NV>(lam, j);
-      Bundle<D> B;
-      trial_bundle<D>(ob, lj, Gj, gph, ph / h, cf, B);
-      accumulate<D>(std::make_integer_sequence<int, NB>{}, acc, qw[q] * g.vol, B, fld_b, lk, Gk, gph, ph / h, cf);
-    }
-  } else {  // constant integrand: one point at the barycentre
-    const double z[D] = {};
+    for (int n = 0; n < NV; ++n) lam[n] = qlam[q * NV + n];
+    double ph, gph[D];
+    eval_phi_only<D, KP>(lam, g.G, pc, ph, gph);
+    const double lk = pick<NV>(lam, k), lj = pick<NV>(lam, j);
     Bundle<D> B;
-    trial_bundle<D>(ob, 1.0 / NV, Gj, z, 0.0, cf, B);
-    accumulate<D>(std::make_integer_sequence<int, NB>{}, acc, g.vol, B, fld_b, 1.0 / NV, Gk, z, 0.0, cf);
+    trial_bundle<D>(ob, lj, Gj, gph, ph / h, cf, B);
+    accumulate<D>(std::make_integer_sequence<int, NB>{}, acc, qw[q] * g.vol, B, fld_b, lk, Gk, gph, ph / h, cf);
   }
   const int vk = __ldg(m.cells + c * NV + k);
   const int pos = __ldg(pos_cells + c * (NV * NV) + k * NV + j);
@@ -245,9 +287,7 @@ __global__ void __launch_bounds__(kBlockEl) k_elasticity_cells(
   const int64_t base = (int64_t)NB * ((int64_t)NB * p0 + pos) + ob;
 #pragma unroll
   for (int a = 0; a < NB; ++a) {
-    const int fa = S_::field(a);
-    const bool live = cut ? couples(fa, fld_b) : fa == fld_b;
-    if (live) atomicAdd(data + base + (int64_t)NB * a * deg, acc[a]);
+    if (couples(S_::field(a), fld_b)) atomicAdd(data + base + (int64_t)NB * a * deg, acc[a]);
   }
   // load vector: the threads with j == k own b[(k, ob)]
   if (j == k) {
@@ -265,7 +305,7 @@ __global__ void __launch_bounds__(kBlockEl) k_elasticity_cells(
       for (int l = 0; l < NV; ++l) s += __ldg(f + (int64_t)__ldg(m.cells + c * NV + l) * D + r);
       bv = cf.stab * g.vol * pick<D>(Gk, s0) * s * (1.0 / NV);
     }
-    if (fld_b <= 3 && (cut || fld_b <= 1)) atomicAdd(b + (int64_t)NB * vk + ob, bv);
+    if (fld_b <= 3) atomicAdd(b + (int64_t)NB * vk + ob, bv);
   }
 }
 
@@ -421,9 +461,10 @@ using namespace phifem;
 
 extern "C" int phifem_assemble_elasticity_cells(const phifem_mesh* mesh, const phifem_pk_space* space_phi,
                                                 const phifem_quadrature* quad, const double* phi, const double* f,
-                                                const int8_t* cell_tags8, const int32_t* vptr,
-                                                const int32_t* pos_cells, const phifem_elasticity_params* prm,
-                                                double* data, double* b, void* stream) {
+                                                const int8_t* cell_tags8, const int32_t* cut_cells, int64_t n_cut,
+                                                const int32_t* vptr, const int32_t* pos_cells,
+                                                const phifem_elasticity_params* prm, double* data, double* b,
+                                                void* stream) {
   int D = 0;
   if (int rc = check_simplex(mesh, D)) return rc;
   if (mesh->n_cells == 0) return PHIFEM_OK;
@@ -436,15 +477,24 @@ extern "C" int phifem_assemble_elasticity_cells(const phifem_mesh* mesh, const p
   PHIFEM_CHECK_ARG(quad->cell_points && quad->cell_weights && quad->n_cell_points > 0 &&
                        quad->n_cell_points <= kMaxQuadPoints, "cell quadrature rule (1..128 points)");
   PHIFEM_CHECK_ARG(phi && f && cell_tags8 && vptr && pos_cells && data && b, "null array");
+  PHIFEM_CHECK_ARG(n_cut >= 0 && (n_cut == 0 || cut_cells), "cut-cell list");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int nb = 3 * D + 2 * D * D;
-  const int64_t threads = mesh->n_cells * (int64_t)((D + 1) * (D + 1) * nb);
-  const unsigned grid = (unsigned)((threads + kBlockEl - 1) / kBlockEl);
-  PHIFEM_CHECK_ARG((threads + kBlockEl - 1) / kBlockEl < (1ll << 31), "too many cells for one launch");
-#define PHIFEM_EL_LAUNCH(DD, KK)                                                                                      \
-  k_elasticity_cells<DD, KK><<<grid, kBlockEl, 0, st>>>(*mesh, *space_phi, quad->cell_points, quad->cell_weights,       \
-                                                        quad->n_cell_points, phi, f, cell_tags8, vptr, pos_cells, *prm, \
-                                                        data, b)
+  const int nv = D + 1, nb = 3 * D + 2 * D * D;
+  {
+    const int64_t blocks = (mesh->n_cells * (int64_t)(nv * nv) + kBlockEl - 1) / kBlockEl;
+    PHIFEM_CHECK_ARG(blocks < (1ll << 31), "too many cells for one launch");
+    if (D == 2) k_elasticity_uncut<2><<<(unsigned)blocks, kBlockEl, 0, st>>>(*mesh, f, cell_tags8, vptr, pos_cells, *prm, data, b);
+    else k_elasticity_uncut<3><<<(unsigned)blocks, kBlockEl, 0, st>>>(*mesh, f, cell_tags8, vptr, pos_cells, *prm, data, b);
+    PHIFEM_CHECK_LAUNCH();
+  }
+  if (n_cut == 0) return PHIFEM_OK;
+  const int64_t blocks = (n_cut * (int64_t)(nv * nv * nb) + kBlockEl - 1) / kBlockEl;
+  PHIFEM_CHECK_ARG(blocks < (1ll << 31), "too many cut cells for one launch");
+  const unsigned grid = (unsigned)blocks;
+#define PHIFEM_EL_LAUNCH(DD, KK)                                                                                    \
+  k_elasticity_cells<DD, KK><<<grid, kBlockEl, 0, st>>>(*mesh, *space_phi, quad->cell_points, quad->cell_weights,     \
+                                                        quad->n_cell_points, phi, f, cut_cells, n_cut, vptr, pos_cells, \
+                                                        *prm, data, b)
   if (D == 2 && space_phi->degree == 1) PHIFEM_EL_LAUNCH(2, 1);
   else if (D == 2) PHIFEM_EL_LAUNCH(2, 2);
   else if (space_phi->degree == 1) PHIFEM_EL_LAUNCH(3, 1);

@@ -578,11 +578,48 @@ __device__ __forceinline__ void neumann_basis(int m, const double (&lam)[D + 1],
   }
 }
 
+// Interior cells (tag 1) carry int grad u.grad v + u v and int f v only: the P1 stiffness and mass matrices in closed
+// form, one light thread per (active cell, u test dof) -- kept apart from the cut-cell kernel, whose register footprint
+// would otherwise set the occupancy of these latency-bound threads.
+template <int D>
+__global__ void __launch_bounds__(kBlockPk) k_assemble_interior_neumann(
+    phifem_mesh m, const double* __restrict__ f, const int8_t* __restrict__ ctags, const int32_t* __restrict__ active,
+    int64_t n_active, const int32_t* __restrict__ slots, const int32_t* __restrict__ mixed_dofmap,
+    double* __restrict__ data, double* __restrict__ b) {
+  constexpr int NV = D + 1, NM = NeumannSpace<D>::NM;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_active * NV) return;
+  const int64_t e = t / NV;
+  const int a = (int)(t - e * NV);
+  const int64_t c = __ldg(active + e);
+  if (ctags[c] == 2) return;
+  Geometry<D> g;
+  load_geometry<D>(m, c, g);
+  constexpr double mm = 1.0 / ((D + 1) * (D + 2));
+  double Ga[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) Ga[d] = g.G[0][d];
+#pragma unroll
+  for (int k = 1; k < NV; ++k)
+    if (k == a)
+#pragma unroll
+      for (int d = 0; d < D; ++d) Ga[d] = g.G[k][d];
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) s += __ldg(f + __ldg(m.cells + c * NV + k)) * (k == a ? 2.0 : 1.0);
+  atomicAdd(b + __ldg(mixed_dofmap + c * NM + a), g.vol * mm * s);
+#pragma unroll
+  for (int bb = 0; bb < NV; ++bb)
+    atomicAdd(data + __ldg(slots + (int64_t)(a * NM + bb) * n_active + e),
+              g.vol * (dotd<D>(Ga, g.G[bb]) + (bb == a ? 2.0 * mm : mm)));
+}
+
+// Cut cells (tag 2): `cut_positions` [n_cut] = their positions in the active list.  One thread per (cut cell, mixed dof).
 template <int D, int KP>
 __global__ void __launch_bounds__(kBlockPk) k_assemble_cells_neumann(
     phifem_mesh m, phifem_pk_space sp, const double* __restrict__ qlam_g, const double* __restrict__ qw_g, int nq,
     const double* __restrict__ phi, const double* __restrict__ f, const double* __restrict__ un,
-    const int8_t* __restrict__ ctags, const int32_t* __restrict__ active, int64_t n_active,
+    const int32_t* __restrict__ active, int64_t n_active, const int32_t* __restrict__ cut_positions, int64_t n_cut,
     const int32_t* __restrict__ slots, const int32_t* __restrict__ mixed_dofmap, double gamma, double kappa,
     double* __restrict__ data, double* __restrict__ b) {
   constexpr int NV = D + 1, NDP = Space<D, KP>::ND, NM = NeumannSpace<D>::NM;
@@ -591,12 +628,11 @@ __global__ void __launch_bounds__(kBlockPk) k_assemble_cells_neumann(
   for (int i = threadIdx.x; i < nq; i += blockDim.x) qw[i] = qw_g[i];
   __syncthreads();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_active * NM) return;
-  const int64_t e = t / NM;
-  const int a = (int)(t - e * NM);
+  if (t >= n_cut * NM) return;
+  const int64_t ec = t / NM;
+  const int a = (int)(t - ec * NM);
+  const int64_t e = __ldg(cut_positions + ec);
   const int64_t c = __ldg(active + e);
-  const bool is_cut = ctags[c] == 2;
-  if (a >= NV && !is_cut) return;  // rows of z and q only carry cut-cell terms
   Geometry<D> g;
   load_geometry<D>(m, c, g);
   double pc[NDP], fc[NV], uc[NV];
@@ -608,7 +644,7 @@ __global__ void __launch_bounds__(kBlockPk) k_assemble_cells_neumann(
     uc[k] = __ldg(un + v);
   }
   const double h = sqrt(g.h2), rh = 1.0 / h, rh2 = 1.0 / g.h2;
-  const double pen = is_cut ? gamma : 0.0;
+  const double pen = gamma;
   double A[NM], bv = 0.0;
 #pragma unroll
   for (int j = 0; j < NM; ++j) A[j] = 0.0;
@@ -639,7 +675,7 @@ __global__ void __launch_bounds__(kBlockPk) k_assemble_cells_neumann(
   atomicAdd(b + __ldg(mixed_dofmap + c * NM + a), bv);
 #pragma unroll
   for (int bb = 0; bb < NM; ++bb)
-    if (bb < NV || is_cut) atomicAdd(data + __ldg(slots + (int64_t)(a * NM + bb) * n_active + e), A[bb]);
+    atomicAdd(data + __ldg(slots + (int64_t)(a * NM + bb) * n_active + e), A[bb]);
 }
 
 // int_{ds(100)} (y.n) v: one thread per (entity, u test dof i); columns y_(j,c)
@@ -853,21 +889,26 @@ extern "C" int phifem_assemble_weak_ghost_pk(const phifem_mesh* mesh, const phif
 extern "C" int phifem_assemble_neumann_cells(const phifem_mesh* mesh, const phifem_pk_space* space_phi,
                                              const phifem_quadrature* quad, const double* phi, const double* f,
                                              const double* u_n, const int8_t* cell_tags8, const int32_t* active,
-                                             int64_t n_active, const int32_t* slots, const int32_t* mixed_dofmap,
-                                             double gamma, double robin_coef, double* data, double* b,
-                                             void* stream) {
+                                             int64_t n_active, const int32_t* cut_positions, int64_t n_cut,
+                                             const int32_t* slots, const int32_t* mixed_dofmap, double gamma,
+                                             double robin_coef, double* data, double* b, void* stream) {
   PHIFEM_CHECK_ARG(quad != nullptr && space_phi != nullptr, "quadrature / level-set space is null");
   phifem_pk_space p1{1, mesh && mesh->cell_type == PHIFEM_TRIANGLE ? 3 : 4, 0, nullptr};
   if (int rc = check_pk(mesh, &p1, space_phi, quad->cell_points, quad->cell_weights, quad->n_cell_points)) return rc;
   if (n_active == 0) return PHIFEM_OK;
   PHIFEM_CHECK_ARG(phi && f && u_n && cell_tags8 && data && b && mixed_dofmap && active && slots, "null pointer");
+  PHIFEM_CHECK_ARG(n_cut >= 0 && n_cut <= n_active && (n_cut == 0 || cut_positions), "cut-cell positions");
   cudaStream_t st = (cudaStream_t)stream;
   dispatch(mesh->cell_type, 1, space_phi->degree, [&](auto d, auto, auto kp) {
     constexpr int D = decltype(d)::value, KP = decltype(kp)::value;
-    const int64_t threads = n_active * NeumannSpace<D>::NM;
+    const int64_t light = n_active * (D + 1);
+    k_assemble_interior_neumann<D><<<(unsigned)((light + kBlockPk - 1) / kBlockPk), kBlockPk, 0, st>>>(
+        *mesh, f, cell_tags8, active, n_active, slots, mixed_dofmap, data, b);
+    if (n_cut == 0) return;
+    const int64_t threads = n_cut * NeumannSpace<D>::NM;
     k_assemble_cells_neumann<D, KP><<<(unsigned)((threads + kBlockPk - 1) / kBlockPk), kBlockPk, 0, st>>>(
-        *mesh, *space_phi, quad->cell_points, quad->cell_weights, quad->n_cell_points, phi, f, u_n, cell_tags8,
-        active, n_active, slots, mixed_dofmap, gamma, robin_coef, data, b);
+        *mesh, *space_phi, quad->cell_points, quad->cell_weights, quad->n_cell_points, phi, f, u_n, active, n_active,
+        cut_positions, n_cut, slots, mixed_dofmap, gamma, robin_coef, data, b);
   });
   PHIFEM_CHECK_LAUNCH();
   return PHIFEM_OK;

@@ -70,6 +70,7 @@ class ElasticityPlan:
         self.n_rows = nb * nvx
         cells = mesh.cells.long()
         tagged = (cell_tags8 >= 1) & (cell_tags8 <= 3)
+        self.cut_cells = torch.nonzero(cell_tags8 == 2).reshape(-1).to(torch.int32)                   # dx(2)
         interior = mesh.f2c[:, 1] >= 0
         self.facets_in = torch.nonzero((facet_tags8 == 3) & interior).reshape(-1).to(torch.int32)     # dS(3)
         self.facets_out = torch.nonzero((facet_tags8 == 4) & interior).reshape(-1).to(torch.int32)    # dS(4)
@@ -205,8 +206,8 @@ def assemble_interface_elasticity_into(plan, phi, f, material, gamma, sigma_s, d
     data.zero_()
     b.zero_()
     _lib.check(lib.phifem_assemble_elasticity_cells(
-        cm, ctypes.byref(cp), ctypes.byref(cq), p(phi), p(f), p(plan.cell_tags8), p(plan.vptr), p(plan.pos_cells),
-        ctypes.byref(prm), p(data), p(b), st))
+        cm, ctypes.byref(cp), ctypes.byref(cq), p(phi), p(f), p(plan.cell_tags8), p(plan.cut_cells),
+        plan.cut_cells.numel(), p(plan.vptr), p(plan.pos_cells), ctypes.byref(prm), p(data), p(b), st))
     for side, (fac, pos) in enumerate(((plan.facets_in, plan.pos_facets_in), (plan.facets_out, plan.pos_facets_out))):
         _lib.check(lib.phifem_assemble_elasticity_facets(cm, p(fac), fac.numel(), p(plan.vptr), p(pos), side,
                                                          ctypes.byref(prm), p(data), st))

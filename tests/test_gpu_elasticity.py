@@ -135,3 +135,17 @@ def test_interface_elasticity_manufactured_solution_converges():
         rates = [np.log2(errs[i] / errs[i + 1]) for i in range(2)]
         print("interface-elasticity errors", E_out, errs, rates)
         assert errs[-1] < bound and min(rates) > 1.7, (E_out, errs, rates)
+
+
+def test_interface_elasticity_demo_runs_end_to_end():
+    """demo/interface_elasticity.py = `python main.py param1` of the reference demo (mesh size 0.2, uniform refinement;
+    n = 30 has a vertex at the origin, where the analytic source needs its limit)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "demo"))
+    import interface_elasticity
+    res = interface_elasticity.main(mesh_size=0.2, iterations=3, quiet=True)
+    l2, h1 = res["L2 relative error"], res["H10 relative error"]
+    assert res["dof"] == [2 * 16 * 16, 2 * 31 * 31, 2 * 61 * 61]
+    assert l2[-1] < 3e-3 and l2[0] / l2[-1] > 10.0, l2
+    assert h1[-1] < 6e-2 and h1[0] / h1[-1] > 3.0, h1
