@@ -273,7 +273,7 @@ def run_ours(args):
             plan = assemble.build_plan(mesh, ctags, ftags, ents, V=Vw, V_phi=Vw)
         else:
             plan = assemble.build_plan(mesh, ctags, ftags, ents, method=args.scatter, capacity=args.capacity,
-                                       order=args.order)
+                                       order=args.order, geometry=args.geometry)
         data, b = plan.new_outputs()
     torch.cuda.synchronize()
     symbolic_ms = (time.perf_counter() - t0) * 1e3
@@ -397,9 +397,11 @@ def run_ours(args):
     if plan.method == "rows" and mesh.gdim == 3:
         # the cell pass is bound by fp64 issue, not by HBM: 146 fp64 instructions per (row, cell) record (SASS
         # count of cell_row<3>) against 64 fp64 lanes per clock per SM
-        lanes = plan.rowsplan.cells.n_records * 146.0
+        # from the coordinates; 85 with the cached cell geometry (cell_row_geom<3>, cut-only instructions excluded)
+        per_record = 85 if plan.rowsplan.cell_geom is not None else 146
+        lanes = plan.rowsplan.cells.n_records * float(per_record)
         peak_lanes = 148 * 64 * (clocks["sm_max_mhz"] or 1965) * 1e6
-        roofline["fp64_issue"] = {"kernel": "k_assemble_rows_p1<cells>", "fp64_instructions_per_record": 146,
+        roofline["fp64_issue"] = {"kernel": "k_assemble_rows_p1<cells>", "fp64_instructions_per_record": per_record,
                                   "records": plan.rowsplan.cells.n_records,
                                   "achieved_tera_lane_instr_per_s": lanes / (per["assemble_cells"] * 1e-3) / 1e12,
                                   "peak_tera_lane_instr_per_s": peak_lanes / 1e12,
@@ -499,6 +501,8 @@ def run_ours(args):
                                                                  plan.rowsplan.n_ghost_records,
                                                                  plan.rowsplan.n_entity_records],
                                 "lane_padding": [plan.rowsplan.cells.padding(), plan.rowsplan.surface.padding()],
+                                "cell_geometry": "cached per plan (64 B per active cell)"
+                                if plan.rowsplan.cell_geom is not None else "from the vertex coordinates",
                                 "plan_bytes": plan.rowsplan.index_bytes()} if plan.rowsplan else {})}}
         emit(line)
     if world > 1:
@@ -543,6 +547,9 @@ def main():
     ap.add_argument("--capacity", type=int, default=None, help="contributions per block (blocked scatter)")
     ap.add_argument("--order", default="natural", choices=["natural", "morton"],
                     help="row processing order of the row-gather assembly")
+    ap.add_argument("--geometry", action="store_true",
+                    help="row-gather cell pass from a per-plan geometry table instead of the vertex coordinates "
+                         "(measured slower: profiles/round2_a_geometry_kernel.md)")
     ap.add_argument("--dist-mode", default="rows", choices=["rows", "exchange"],
                     help="multi-GPU numeric strategy: owner-computes rows / per-entity kernels + halo exchange")
     ap.add_argument("--detection-degree", type=int, default=1, choices=[1, 2],

@@ -243,6 +243,13 @@ typedef struct phifem_rows_plan {
   int64_t n_entities;
   const int32_t* entity_macro; /* [n_entities, d + 1] vertex ids */
   double* surface_work;        /* [n_ghost_facets + n_entities, 8] scratch (32-byte aligned), rewritten by every call */
+  /* Optional cached geometry of the cell pass (NULL: the kernel gathers the coordinates and evaluates the cofactors per
+   * record).  The forms see a cell only through its P1 stiffness matrix S_ab = |K| grad(lambda_a).grad(lambda_b), |K|
+   * and h_T^2 -- mesh data, tabulated once per plan: 8 doubles per cell (32-byte aligned) = [S_ab for a < b in
+   * lexicographic order (3 / 6 values), |K|, h_T^2, padding].  With it the records of `cells` hold TWO words: word 0 as
+   * above plus (cell-local index of the row's vertex) << 25, word 1 = the cell's index in this table; the other vertices
+   * of word 0 are in ascending cell-local order. */
+  const double* cell_geom;
 } phifem_rows_plan;
 
 /* Same operator as phifem_assemble_{cells,boundary,ghost}_p1: the facet-once kernel (forked onto an internal side

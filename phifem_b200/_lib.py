@@ -52,7 +52,7 @@ class CRowsPlan(ctypes.Structure):
     _fields_ = [("indptr", _vp), ("indices", _vp), ("max_row_nnz", ctypes.c_int32),
                 ("reserved", ctypes.c_int32), ("cells", CRowList), ("surface", CRowList),
                 ("n_ghost_facets", ctypes.c_int64), ("ghost_macro", _vp), ("n_entities", ctypes.c_int64),
-                ("entity_macro", _vp), ("surface_work", _vp)]
+                ("entity_macro", _vp), ("surface_work", _vp), ("cell_geom", _vp)]
 
 
 class CPkSpace(ctypes.Structure):

@@ -178,6 +178,88 @@ __device__ __forceinline__ void cell_row(const double (&X)[D + 1][D], const doub
                (2.0 / (dfact * NV)) * sh2 * F * aR[0] * (inv * inv));
 }
 
+// The same row from cached geometry (phifem_rows_plan.cell_geom): the forms see the cell only through its P1
+// stiffness matrix S_ab = |K| grad(lambda_a).grad(lambda_b), |K| and h_T^2, which depend on the mesh alone and are
+// tabulated once per plan: 8 doubles per active cell = [S_ab for a < b in lexicographic order, |K|, h_T^2, pad].
+// With A_j = |K| grad(phi).grad(lambda_j) = sum_k (p_k - p_j) S_kj (rows of S sum to zero) and gg = |K| |grad(phi)|^2
+// = sum_j p_j A_j:
+//   K_j = [ gg (1 + delta_0j) + A_0 (P + p_j) + (P + p_0) A_j + S_0j mu ] / ((d+1)(d+2)) + 4 sigma h^2 A_0 A_j / |K|,
+//   b_0 = |K| d!/(d+3)! [ F P + sum f_k p_k + f_0 P + F p_0 + 2 f_0 p_0 ] - 2 sigma h^2 F A_0 / (d+1),
+// ~85 fp64 instructions instead of ~146 (no cofactors, no reciprocal off the cut cells), no coordinate gathers.
+// MEASURED SLOWER on the B200 at config E (cell pass 1.74 ms against 1.20 ms; profiles/round2_a_geometry_kernel.md): the
+// fp64 pipe falls from 56 % to 17 % busy, but the warp-instruction count does not (706 M against 734 M: selects for
+// the row permutation, register moves) and the 64-byte table record of a cell -- read by D + 1 rows that run far apart in
+// time -- misses L1 (hit rate 42 % against 88 % for the coordinates, which neighbouring rows share), so every record
+// waits for an L2 round trip with one record of lead (long-scoreboard stalls 6.6 per issue against 0.9).  Requesting the
+// table line 6 records ahead with prefetch.global.L2 made it 2.05 ms.  Kept as an option of the plan
+// (`geometry=True`), off by default.
+// Slot order: slot 0 = the row's vertex = cell-local vertex i, slot s >= 1 = the (s-1)-th other vertex in ascending
+// local order (the order of the record's position bytes).
+template <int NV> __host__ __device__ constexpr int geom_slot_to_local(int i, int s) {
+  return s == 0 ? i : (s - 1 < i ? s - 1 : s);
+}
+template <int NV> __host__ __device__ constexpr int geom_stored(int x, int y) {  // index of S_xy, x != y
+  return x < y ? x * (2 * NV - x - 1) / 2 + (y - x - 1) : y * (2 * NV - y - 1) / 2 + (x - y - 1);
+}
+
+template <int D>
+__device__ __forceinline__ void cell_row_geom(const double (&g)[8], int i, const double (&p)[D + 1],
+                                              const double (&fv)[D + 1], bool is_cut, double sigma,
+                                              double (&K)[D + 1], double& b0) {
+  constexpr int NV = D + 1, NO = NV * D / 2;
+  double S[NV][NV];
+#pragma unroll
+  for (int a = 0; a < NV; ++a)
+#pragma unroll
+    for (int c = a + 1; c < NV; ++c) {
+      double v = g[geom_stored<NV>(geom_slot_to_local<NV>(0, a), geom_slot_to_local<NV>(0, c))];
+#pragma unroll
+      for (int ii = 1; ii < NV; ++ii)
+        if (i == ii) v = g[geom_stored<NV>(geom_slot_to_local<NV>(ii, a), geom_slot_to_local<NV>(ii, c))];
+      S[a][c] = v;
+    }
+  const double vol = g[NO], h2 = g[NO + 1];
+  double dp[NV][NV];  // p_a - p_c, a < c
+#pragma unroll
+  for (int a = 0; a < NV; ++a)
+#pragma unroll
+    for (int c = a + 1; c < NV; ++c) dp[a][c] = p[a] - p[c];
+  double A[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      if (k < j) s += dp[k][j] * S[k][j];
+      if (k > j) s -= dp[j][k] * S[j][k];
+    }
+    A[j] = s;
+  }
+  double gg = p[0] * A[0], P = p[0], S2 = p[0] * p[0], F = fv[0], FP = fv[0] * p[0], S00 = S[0][1];
+#pragma unroll
+  for (int k = 1; k < NV; ++k) {
+    gg += p[k] * A[k];
+    P += p[k];
+    S2 += p[k] * p[k];
+    F += fv[k];
+    FP += fv[k] * p[k];
+    if (k > 1) S00 += S[0][k];
+  }
+  const double mu = P * P + S2, P0 = P + p[0];
+  constexpr double cm = 1.0 / ((D + 1) * (D + 2));
+  constexpr double cb = D == 2 ? 1.0 / 60.0 : 1.0 / 120.0;  // d!/(d+3)!
+  double sR = 0.0, sb = 0.0;
+  if (is_cut) {
+    const double sh2 = sigma * h2;
+    sR = 4.0 * sh2 * A[0] / vol;
+    sb = (2.0 / NV) * sh2 * F * A[0];
+  }
+  K[0] = cm * (2.0 * gg + 2.0 * A[0] * P0 - S00 * mu) + sR * A[0];
+#pragma unroll
+  for (int j = 1; j < NV; ++j) K[j] = cm * (gg + A[0] * (P + p[j]) + P0 * A[j] + S[0][j] * mu) + sR * A[j];
+  b0 = vol * cb * ((F * P + FP) + fv[0] * P + F * p[0] + 2.0 * fv[0] * p[0]) - sb;
+}
+
 __device__ __forceinline__ double alpha3(int a, int b, int c) {
   return (double)((1 + (a == b)) * (1 + (a == c) + (b == c)));
 }
@@ -387,12 +469,17 @@ __device__ __forceinline__ void load_vertex(const double* __restrict__ x, const 
   p = __ldg(phi + v);
 }
 
-enum { kCells = 0, kSurface = 1 };
+enum { kCells = 0, kSurface = 1, kCellsGeom = 2 };
 
 // coordinates, phi and f of the D other vertices of a cell record
 template <int D>
 struct Others {
   double X[D][D], p[D], f[D];
+};
+// cached geometry of the record's cell, phi and f of its D other vertices
+template <int D>
+struct OthersGeom {
+  double g[8], p[D], f[D];
 };
 
 // One pass over one row list.  KIND == kCells writes data / b of its rows, the surface passes add to them.
@@ -401,7 +488,7 @@ __global__ void __launch_bounds__(kRowsBlock, PHIFEM_ROWS_MINBLOCKS) k_assemble_
     const double* __restrict__ x, const double* __restrict__ phi, const double* __restrict__ f,
     double sigma, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
     phifem_row_list rl, const double* __restrict__ surface_work, double* __restrict__ data,
-    double* __restrict__ b) {
+    double* __restrict__ b) {  // surface_work: facet-once records (kSurface) / cached cell geometry (kCellsGeom)
   constexpr int NV = D + 1, NG = D + 2;
   extern __shared__ double acc_s[];  // accumulator k of thread t at acc_s[k * kRowsBlock + t]
   const int tid = threadIdx.x, lane = tid & 31;
@@ -481,6 +568,65 @@ __global__ void __launch_bounds__(kRowsBlock, PHIFEM_ROWS_MINBLOCKS) k_assemble_
       body(k, A, B);
       if (k + 1 < ke) body(k + 1, B, A);
     }
+  } else if constexpr (KIND == kCellsGeom) {  // the cell pass on cached geometry: two words per record
+    // word 0 = position bytes | cut << 24 | (cell-local index of the row's vertex) << 25, word 1 = the cell's index
+    // in the geometry table.  Same four-deep pipeline as above; the cell's 64-byte geometry record arrives with two
+    // 256-bit loads instead of 3 D coordinate loads.
+    const double fr = __ldg(f + r);
+    const uint2* __restrict__ recs = reinterpret_cast<const uint2*>(rl.rec);
+    const uint2 pad2 = make_uint2(0u, kPad);
+    auto fetch_rec = [&](int k) { return k < ke ? __ldg(recs + (int64_t)k * 32 + lane) : pad2; };
+    auto fetch_idx = [&](uint2 rec, int (&v)[D]) {
+      const uint32_t q = rec.y == kPad ? 0u : rec.x;
+#pragma unroll
+      for (int j = 0; j < D; ++j) v[j] = __ldg(cols + ((q >> (8 * j)) & 0xff));
+    };
+    auto fetch_data = [&](const int (&v)[D], uint2 rec, OthersGeom<D>& o) {
+      const double* src = surface_work + (rec.y == kPad ? 0 : (int64_t)rec.y * 8);
+      ldg256(src, o.g[0], o.g[1], o.g[2], o.g[3]);
+      ldg256(src + 4, o.g[4], o.g[5], o.g[6], o.g[7]);
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        o.p[j] = __ldg(phi + v[j]);
+        o.f[j] = __ldg(f + v[j]);
+      }
+    };
+    uint2 w0 = fetch_rec(kb), w1 = fetch_rec(kb + 1), w2 = fetch_rec(kb + 2);
+    int v1[D];
+    OthersGeom<D> A, B;
+    if (kb < ke) {
+      fetch_idx(w0, v1);
+      fetch_data(v1, w0, A);
+      fetch_idx(w1, v1);
+    }
+    auto body = [&](int k, const OthersGeom<D>& cur, OthersGeom<D>& nxt) {
+      fetch_data(v1, w1, nxt);
+      fetch_idx(w2, v1);
+      const uint2 w3 = fetch_rec(k + 3);
+      if (w0.y != kPad) {
+        double p[NV], fv[NV];
+        p[0] = pr;
+        fv[0] = fr;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          p[j + 1] = cur.p[j];
+          fv[j + 1] = cur.f[j];
+        }
+        double K[NV], b0;
+        cell_row_geom<D>(cur.g, (int)((w0.x >> 25) & 3u), p, fv, (w0.x >> 24) & 1u, sigma, K, b0);
+        diag += K[0];
+        br += b0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) acc[((w0.x >> (8 * j)) & 0xff) * kRowsBlock] += K[j + 1];
+      }
+      w0 = w1;
+      w1 = w2;
+      w2 = w3;
+    };
+    for (int k = kb; k < ke; k += 2) {
+      body(k, A, B);
+      if (k + 1 < ke) body(k + 1, B, A);
+    }
   } else {  // surface pass: ghost-penalty facets and one-sided entities whose vertices include r
     // ghost record = {positions of the other macro vertices (macro order, the row's own index skipped),
     //                 facet index in the plan's ghost list | macro index of the row's vertex << 28};
@@ -540,7 +686,7 @@ __global__ void __launch_bounds__(kRowsBlock, PHIFEM_ROWS_MINBLOCKS) k_assemble_
     }
   }
   acc[dpos * kRowsBlock] += diag;
-  if constexpr (KIND == kCells) {
+  if constexpr (KIND != kSurface) {
     for (int k = 0; k < nnz; ++k) data[start + k] = acc[k * kRowsBlock];
     b[r] = br;
   } else {
@@ -601,15 +747,16 @@ extern "C" int phifem_assemble_rows_p1(const phifem_mesh* mesh, const double* ph
   const size_t smem = (size_t)plan->max_row_nnz * kRowsBlock * sizeof(double);
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t err = cudaSuccess;
-  auto launch = [&](auto kernel, const phifem_row_list& rl) {
+  auto launch = [&](auto kernel, const phifem_row_list& rl, const double* work) {
     if (rl.n_listed == 0 || err != cudaSuccess) return;
     if (smem > 48 * 1024)
       err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int64_t grid = (rl.n_listed + kRowsBlock - 1) / kRowsBlock;
     if (err == cudaSuccess)
       kernel<<<(unsigned)grid, kRowsBlock, smem, st>>>(mesh->x, phi, f, sigma, plan->indptr, plan->indices,
-                                                       rl, plan->surface_work, data, b);
+                                                       rl, work, data, b);
   };
+  const bool geom = plan->cell_geom != nullptr;
   // The facet-once kernel (latency-bound gathers, 2 % of the work) is forked onto a side stream so that it shares
   // the SMs with the fp64-bound cell pass; the surface row pass waits for both.
   SideStream& ss = side_stream();
@@ -628,14 +775,16 @@ extern "C" int phifem_assemble_rows_p1(const phifem_mesh* mesh, const double* ph
   };
   if (mesh->cell_type == PHIFEM_TRIANGLE) {
     once(k_surface_once_p1<2>);
-    launch(k_assemble_rows_p1<2, kCells>, plan->cells);
+    if (geom) launch(k_assemble_rows_p1<2, kCellsGeom>, plan->cells, plan->cell_geom);
+    else launch(k_assemble_rows_p1<2, kCells>, plan->cells, nullptr);
     if (fork) cudaStreamWaitEvent(st, ss.join, 0);
-    launch(k_assemble_rows_p1<2, kSurface>, plan->surface);
+    launch(k_assemble_rows_p1<2, kSurface>, plan->surface, plan->surface_work);
   } else {
     once(k_surface_once_p1<3>);
-    launch(k_assemble_rows_p1<3, kCells>, plan->cells);
+    if (geom) launch(k_assemble_rows_p1<3, kCellsGeom>, plan->cells, plan->cell_geom);
+    else launch(k_assemble_rows_p1<3, kCells>, plan->cells, nullptr);
     if (fork) cudaStreamWaitEvent(st, ss.join, 0);
-    launch(k_assemble_rows_p1<3, kSurface>, plan->surface);
+    launch(k_assemble_rows_p1<3, kSurface>, plan->surface, plan->surface_work);
   }
   if (err != cudaSuccess) {
     set_error("phifem_assemble_rows_p1: cannot reserve %zu bytes of shared memory: %s", smem,

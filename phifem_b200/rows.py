@@ -106,11 +106,52 @@ def _pack_bytes(pos):
     return word
 
 
+def cell_geometry(x, cells):
+    """[n, 8] fp64 geometry table of the cell pass (phifem_rows_plan.cell_geom): S_ab = |K| grad(lambda_a).grad(lambda_b)
+    for a < b in lexicographic order, |K|, h_T^2 (CellDiameter^2 = largest squared vertex distance), zero padding.
+    Elementwise torch ops only (one IEEE operation each, no library factorisation): the table of a cell depends on
+    its own coordinates alone, so a rank of a sharded run tabulates bit for bit what a single GPU does."""
+    n, nv = cells.shape
+    d = nv - 1
+    X = x[cells.long()]                                   # [n, nv, d]
+    e = X[:, 1:, :] - X[:, :1, :]                         # edge k = X[k + 1] - X[0]
+    if d == 2:
+        R = [None, torch.stack([e[:, 1, 1], -e[:, 1, 0]], dim=1), torch.stack([-e[:, 0, 1], e[:, 0, 0]], dim=1)]
+        det = e[:, 0, 0] * e[:, 1, 1] - e[:, 1, 0] * e[:, 0, 1]
+        dfact = 2.0
+    else:
+        def cross(a, b):
+            return torch.stack([a[:, 1] * b[:, 2] - a[:, 2] * b[:, 1], a[:, 2] * b[:, 0] - a[:, 0] * b[:, 2],
+                                a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]], dim=1)
+        R = [None, cross(e[:, 1], e[:, 2]), cross(e[:, 2], e[:, 0]), cross(e[:, 0], e[:, 1])]
+        det = e[:, 0, 0] * R[1][:, 0] + e[:, 0, 1] * R[1][:, 1] + e[:, 0, 2] * R[1][:, 2]
+        dfact = 6.0
+    R[0] = -(R[1] + R[2]) if d == 2 else -(R[1] + R[2] + R[3])
+    out = torch.zeros((n, 8), dtype=torch.float64, device=x.device)
+    scale = 1.0 / (dfact * det.abs())                     # |K| / det^2
+    k = 0
+    for a in range(nv):
+        for b in range(a + 1, nv):
+            out[:, k] = (R[a] * R[b]).sum(dim=1) * scale
+            k += 1
+    out[:, k] = det.abs() / dfact
+    h2 = torch.zeros(n, dtype=torch.float64, device=x.device)
+    for a in range(nv):
+        for b in range(a + 1, nv):
+            h2 = torch.maximum(h2, ((X[:, a] - X[:, b]) ** 2).sum(dim=1))
+    out[:, k + 1] = h2
+    return out.contiguous()
+
+
 class RowsPlan:
     """row_mask (bool [n_rows], optional): assemble only these rows -- the rows a rank owns in a multi-GPU
-    run; records of other rows are dropped (their owner evaluates them from its own halo cells)."""
+    run; records of other rows are dropped (their owner evaluates them from its own halo cells).
+    geometry: tabulate the cells' P1 stiffness entries, |K| and h_T^2 once (`cell_geom`, 64 bytes per active cell) and
+    let the cell pass read them instead of the coordinates (85 instead of 146 fp64 instructions per record; measured
+    SLOWER on the B200 -- the table misses L1 where the coordinates hit -- hence off by default, see
+    csrc/assemble_rows.cu)."""
 
-    def __init__(self, plan, order="natural", row_mask=None):
+    def __init__(self, plan, order="natural", row_mask=None, geometry=False):
         mesh = plan.mesh
         dev = mesh.device
         d = mesh.gdim
@@ -166,13 +207,17 @@ class RowsPlan:
         slots = plan.slots_cells.long().reshape(-1, nv, nv)                     # slot of (row i, col j)
         cut = (plan.cell_tags8[plan.active.long()] == 2).long()
         words = []
+        cidx = torch.arange(cells_act.shape[0], **i64)
         for i in range(nv):
             others = [j for j in range(nv) if j != i]
             pos = slots[:, i, others] - indptr[cells_act[:, i]][:, None]
-            words.append(_pack_bytes(pos) | (cut << 24))
+            w0 = _pack_bytes(pos) | (cut << 24)
+            # geometry mode: the row's cell-local index (which row of the cached matrix) and the cell's table index
+            words.append(torch.stack([w0 | (i << 25), cidx], dim=1) if geometry else w0[:, None])
         # interleaved so that the records of a row keep cell order (deterministic summation order)
-        rec_rows, words = owned(cells_act.reshape(-1), torch.stack(words, dim=1).reshape(-1, 1))
+        rec_rows, words = owned(cells_act.reshape(-1), torch.stack(words, dim=1).reshape(-1, 2 if geometry else 1))
         self.cells = RowList(ordered(listed), dslot, indptr, rec_rows, words, n)
+        self.cell_geom = cell_geometry(mesh.x, cells_act) if geometry and cells_act.shape[0] else None
         del slots, cells_act, words
 
         # ---- ghost-penalty facets: one record per distinct vertex of the macro element ------------------
@@ -255,17 +300,19 @@ class RowsPlan:
         return self._c
 
     def _surface_fields(self):
-        """Trailing fields of phifem_rows_plan: ghost facet / entity vertex lists and the facet-once scratch."""
+        """Trailing fields of phifem_rows_plan: ghost facet / entity vertex lists, the facet-once scratch, the cached
+        cell geometry."""
         if self.surface_work.device.type != "cuda":
-            return 0, None, 0, None, None
+            return 0, None, 0, None, None, None
         return (self.n_ghost_facets, _lib.ptr(self.ghost_macro) if self.n_ghost_facets else None,
                 self.n_entities, _lib.ptr(self.entity_macro) if self.n_entities else None,
-                _lib.ptr(self.surface_work))
+                _lib.ptr(self.surface_work), _lib.ptr(self.cell_geom))
 
     def index_bytes(self):
         """Bytes of plan arrays one numeric pass streams besides the CSR pattern itself."""
         return (self.cells.nbytes() + self.surface.nbytes() + self.ghost_macro.numel() * 4
-                + self.entity_macro.numel() * 4 + self.surface_work.numel() * 8)
+                + self.entity_macro.numel() * 4 + self.surface_work.numel() * 8
+                + (self.cell_geom.numel() * 8 if self.cell_geom is not None else 0))
 
 
 def assemble_rows_into(rplan, phi, f, sigma, data, b, passes=None):

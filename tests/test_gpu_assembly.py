@@ -38,8 +38,8 @@ def _row_scale(indptr, data):
     return scale, rows
 
 
-@pytest.mark.parametrize("method,capacity", [("rows", None), ("rows", "morton"), ("blocked", None),
-                                             ("blocked", 2500), ("atomic", None)])
+@pytest.mark.parametrize("method,capacity", [("rows", None), ("rows", "morton"), ("rows", "geometry"),
+                                             ("blocked", None), ("blocked", 2500), ("atomic", None)])
 @pytest.mark.parametrize("kind,n", [("tri", 40), ("tri-unstructured", 24), ("tet", 10),
                                     ("tet-unstructured", 8)])
 def test_cuda_operator_matches_oracle(kind, n, method, capacity):
@@ -48,11 +48,16 @@ def test_cuda_operator_matches_oracle(kind, n, method, capacity):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore", RuntimeWarning)
         ctags, ftags, _, ds, _ = mesh_scripts.compute_tags_measures(mesh, fn, 1, box_mode=True)
-    order = "natural"
-    if method == "rows" and capacity:
+    order, geometry = "natural", False
+    if method == "rows" and capacity == "geometry":   # cell pass from the plan's geometry table instead of the coordinates
+        geometry, capacity = True, None
+    elif method == "rows" and capacity:
         order, capacity = capacity, None
-    plan = assemble.build_plan(mesh, ctags, ftags, ds(100), method=method, capacity=capacity, order=order)
+    plan = assemble.build_plan(mesh, ctags, ftags, ds(100), method=method, capacity=capacity, order=order,
+                               geometry=geometry)
     assert plan.method == method
+    if method == "rows":
+        assert (plan.rowsplan.cell_geom is not None) == geometry
     A, b = assemble.assemble_strong_dirichlet(plan, phi, f, stab_coef=1.0)
     if method in ("blocked", "rows"):
         # owner-computes sums in a fixed order: bitwise reproducible, and independent of what the

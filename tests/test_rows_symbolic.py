@@ -55,11 +55,31 @@ def _emulate(rp, m, x, cells, phi, f, out, sigma):
         seen.add((r, c))
         At, bt = OA.cell_tensors_closed_form(x, cells[c:c + 1], phi, f, np.array([ct[c] == 2]), sigma)
         i = list(cells[c]).index(r)
+        if rp.cell_geom is not None:
+            # geometry mode: word 0 also names the row's cell-local index, word 1 the cell's entry of the geometry
+            # table; the other vertices come in ascending cell-local order
+            assert (int(w[0]) >> 25) & 3 == i and int(plan.active[int(w[1])]) == c
+            assert others == [int(v) for k, v in enumerate(cells[c]) if k != i]
+        else:
+            assert len(w) == 1
         data[indptr[r] + dp] += At[0, i, i]
         for p, v in zip(pos, others):
             data[indptr[r] + p] += At[0, i, list(cells[c]).index(v)]
         b[r] += bt[0, i]
     assert len(seen) == nv * int(np.isin(ct, (1, 2)).sum())
+    if rp.cell_geom is not None:
+        # the table: S_ab = |K| grad(lambda_a).grad(lambda_b) for a < b, |K|, h_T^2
+        act = plan.active.numpy()
+        G, vol, h = OA.simplex_geometry(x, cells[act])
+        tab = rp.cell_geom.numpy()
+        k = 0
+        for a in range(nv):
+            for c2 in range(a + 1, nv):
+                want = vol * (G[:, a] * G[:, c2]).sum(axis=1)
+                assert np.abs(tab[:, k] - want).max() <= 1e-13 * np.abs(want).max()
+                k += 1
+        assert np.allclose(tab[:, k], vol, rtol=1e-14, atol=0) and np.allclose(tab[:, k + 1], h * h, rtol=1e-14, atol=0)
+        assert np.all(tab[:, k + 2:] == 0.0)
 
     # ghost-penalty facets
     ghost = plan.ghost.numpy()
@@ -114,9 +134,9 @@ def _emulate(rp, m, x, cells, phi, f, out, sigma):
     return data, b
 
 
-@pytest.mark.parametrize("d,n,order", [(2, 12, "natural"), (2, 9, "morton"), (3, 5, "natural"),
-                                       (3, 4, "morton")])
-def test_rows_plan_reproduces_the_oracle_operator(d, n, order):
+@pytest.mark.parametrize("d,n,order,geometry", [(2, 12, "natural", True), (2, 9, "morton", False), (3, 5, "natural", True),
+                                                (3, 4, "morton", True), (3, 4, "natural", False)])
+def test_rows_plan_reproduces_the_oracle_operator(d, n, order, geometry):
     m = synthetic.rectangle_mesh(n, device="cpu") if d == 2 else synthetic.box_mesh(n, device="cpu")
     m = synthetic.unstructured_variant(m, jitter=0.15, seed=11)
     x, cells = m.x.numpy(), m.cells.numpy().astype(np.int64)
@@ -131,9 +151,10 @@ def test_rows_plan_reproduces_the_oracle_operator(d, n, order):
                                    box_mode=True, detection_points=pts)
     plan = assemble.build_plan(m, MeshTags(m, d, torch.from_numpy(out["cell_tags"])),
                                MeshTags(m, d - 1, torch.from_numpy(out["facet_tags"])), out["ds100"],
-                               method="rows", order=order)
+                               method="rows", order=order, geometry=geometry)
     rp = plan.rowsplan
-    assert plan.method == "rows" and rp.order == order
+    assert plan.method == "rows" and rp.order == order and (rp.cell_geom is not None) == geometry
+    assert rp.cells.words == (2 if geometry else 1)
     assert plan.ghost.numel() > 0 and plan.entities.shape[0] > 0
     # listed rows = rows with pattern entries, each once; slices cover them
     rows = rp.cells.rows.numpy()
