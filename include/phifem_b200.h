@@ -136,6 +136,8 @@ int phifem_entity_records(const phifem_mesh* mesh, const int8_t* cell_tags8,
  * Forms: demo/strong-dirichlet/flower/main.py:104-128.  dof = vertex.  `data` (CSR values) and `b`
  * must be zeroed by the caller; contributions are ADDED (PETSc ADD_VALUES semantics, :121-123). */
 
+/* (Slot maps are read with vector loads: pass 16-byte aligned arrays, e.g. separate cudaMalloc allocations.) */
+
 /* dx((1,2)) stiffness + dx(2) stabilisation (:105,107-112) and the load vector (:126-128).
  * active[n_active] = cells tagged 1 or 2; slots[n_active, nv*nv] = CSR position of entry
  * (row = local test vertex i, col = local trial vertex j) at slots[e*nv*nv + i*nv + j]. */
@@ -403,6 +405,31 @@ int phifem_assemble_elasticity_boundary(const phifem_mesh* mesh, const int32_t* 
  * is 1, b <- b - A g on the free rows, b = g on the marked ones.  bc_marker int8 [n_rows], bc_values [n_rows]. */
 int phifem_apply_dirichlet(int64_t n_rows, const int32_t* indptr, const int32_t* indices, const int8_t* bc_marker,
                            const double* bc_values, double* data, double* b, void* stream);
+
+/* ---- symbolic phase of the P1 strong-Dirichlet operator on the device: what dolfinx does in `create_sparsity_pattern` /
+ * `create_matrix` under `assemble_matrix(form(a))` (demo/strong-dirichlet/flower/main.py:121-123).  For hosts without
+ * Python: tags (phifem_tag_cells / phifem_tag_facets) -> phifem_pattern_create_p1 -> phifem_assemble_{cells,boundary,
+ * ghost}_p1 run the whole path with this library alone (the Python package builds the same arrays with torch sort /
+ * unique and adds the row-gather plan on top).  The pattern object owns its device arrays (cudaMalloc); the call
+ * synchronises the stream twice (two sizes come back to the host). */
+typedef struct phifem_pattern phifem_pattern;
+typedef struct phifem_pattern_view {
+  int64_t n_rows, nnz;           /* rows = vertices; nnz < 2^31 */
+  int64_t n_active, n_ghost, n_entities;
+  const int32_t* indptr;         /* [n_rows + 1] */
+  const int32_t* indices;        /* [nnz] sorted per row; structural zeros kept, rows without contributions empty */
+  const int32_t* active;         /* [n_active] cells tagged 1 / 2, ascending */
+  const int32_t* ghost;          /* [n_ghost] interior facets tagged 2 / 3, ascending */
+  const int32_t* slots_cells;    /* [n_active, nv*nv]      as phifem_assemble_cells_p1 expects */
+  const int32_t* slots_ghost;    /* [n_ghost, (nv+1)^2]    as phifem_assemble_ghost_p1 expects */
+  const int32_t* slots_boundary; /* [n_entities, nv*nv]    as phifem_assemble_boundary_p1 expects */
+} phifem_pattern_view;
+
+/* entities[n_entities, 2] = the (cell, local facet) pairs of ds(100) (may be empty). */
+int phifem_pattern_create_p1(const phifem_mesh* mesh, const int8_t* cell_tags8, const int8_t* facet_tags8,
+                             const int32_t* entities, int64_t n_entities, phifem_pattern** out, void* stream);
+int phifem_pattern_view_of(const phifem_pattern* pattern, phifem_pattern_view* out);
+void phifem_pattern_destroy(phifem_pattern* pattern);
 
 #ifdef __cplusplus
 }

@@ -65,6 +65,12 @@ class CQuadrature(ctypes.Structure):
                 ("cell_points", _vp), ("cell_weights", _vp), ("facet_points", _vp), ("facet_weights", _vp)]
 
 
+class CPatternView(ctypes.Structure):
+    _fields_ = [("n_rows", ctypes.c_int64), ("nnz", ctypes.c_int64), ("n_active", ctypes.c_int64),
+                ("n_ghost", ctypes.c_int64), ("n_entities", ctypes.c_int64), ("indptr", _vp), ("indices", _vp),
+                ("active", _vp), ("ghost", _vp), ("slots_cells", _vp), ("slots_ghost", _vp), ("slots_boundary", _vp)]
+
+
 class CElasticityParams(ctypes.Structure):
     _fields_ = [(n, ctypes.c_double) for n in ("lmbda_in", "mu_in", "lmbda_out", "mu_out", "coef_in", "coef_out",
                                                "gamma", "sigma_s")]
@@ -124,6 +130,10 @@ _SIGNATURES = {
     "phifem_assemble_elasticity_boundary": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, ctypes.c_int64, _vp, _vp,
                                                            ctypes.c_int32, _vp, _vp]),
     "phifem_apply_dirichlet": (ctypes.c_int, [ctypes.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "phifem_pattern_create_p1": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, _vp, ctypes.c_int64,
+                                                ctypes.POINTER(_vp), _vp]),
+    "phifem_pattern_view_of": (ctypes.c_int, [_vp, ctypes.POINTER(CPatternView)]),
+    "phifem_pattern_destroy": (None, [_vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
