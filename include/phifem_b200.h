@@ -430,6 +430,9 @@ int phifem_pattern_create_p1(const phifem_mesh* mesh, const int8_t* cell_tags8, 
                              const int32_t* entities, int64_t n_entities, phifem_pattern** out, void* stream);
 int phifem_pattern_view_of(const phifem_pattern* pattern, phifem_pattern_view* out);
 void phifem_pattern_destroy(phifem_pattern* pattern);
+/* The sort scratch of phifem_pattern_create_p1 (about 200 bytes per active cell) lives in a private stream-ordered memory
+ * pool that stays cached between calls; this returns it to the driver. */
+void phifem_pattern_release_scratch(void);
 
 #ifdef __cplusplus
 }

@@ -134,6 +134,7 @@ _SIGNATURES = {
                                                 ctypes.POINTER(_vp), _vp]),
     "phifem_pattern_view_of": (ctypes.c_int, [_vp, ctypes.POINTER(CPatternView)]),
     "phifem_pattern_destroy": (None, [_vp]),
+    "phifem_pattern_release_scratch": (None, []),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -108,14 +108,38 @@ __global__ void k_columns(const int64_t* __restrict__ uniq, int64_t nnz, int64_t
 
 inline unsigned blocks_for(int64_t n) { return (unsigned)((n + kBlockSym - 1) / kBlockSym); }
 
+// A private stream-ordered pool per device whose memory stays cached between calls (release threshold = max): the
+// default pool hands its memory back to the driver at every synchronisation, and re-allocating the ~10 GB of sort
+// scratch of config E costs ten times the sort.  phifem_pattern_release_scratch() trims it.
+cudaMemPool_t g_pools[64] = {};
+cudaMemPool_t scratch_pool() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaMemPool_t& pool = g_pools[dev & 63];
+  if (!pool) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) {
+      pool = nullptr;
+      return nullptr;
+    }
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  return pool;
+}
+
 struct Scratch {  // device allocations freed on scope exit (stream-ordered)
   cudaStream_t st;
+  cudaMemPool_t pool;
   void* p[16];
   int n = 0;
-  explicit Scratch(cudaStream_t s) : st(s) {}
+  Scratch(cudaStream_t s, cudaMemPool_t pl) : st(s), pool(pl) {}
   void* get(size_t bytes) {
     void* q = nullptr;
-    if (cudaMallocAsync(&q, bytes ? bytes : 1, st) != cudaSuccess) return nullptr;
+    if (cudaMallocFromPoolAsync(&q, bytes ? bytes : 1, pool, st) != cudaSuccess) return nullptr;
     p[n++] = q;
     return q;
   }
@@ -128,6 +152,12 @@ struct Scratch {  // device allocations freed on scope exit (stream-ordered)
 }  // namespace phifem
 
 using namespace phifem;
+
+extern "C" void phifem_pattern_release_scratch(void) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (g_pools[dev & 63]) cudaMemPoolTrimTo(g_pools[dev & 63], 0);
+}
 
 extern "C" void phifem_pattern_destroy(phifem_pattern* p) {
   if (!p) return;
@@ -158,7 +188,12 @@ extern "C" int phifem_pattern_create_p1(const phifem_mesh* mesh, const int8_t* c
   const int nv = mesh->cell_type == PHIFEM_TRIANGLE ? 3 : 4, nm = nv + 1;
   const int64_t n_rows = mesh->n_vertices;
   cudaStream_t st = (cudaStream_t)stream;
-  Scratch tmp(st);
+  cudaMemPool_t pool = scratch_pool();
+  if (!pool) {
+    set_error("phifem_pattern_create_p1: cannot create the scratch memory pool");
+    return PHIFEM_ERR_CUDA;
+  }
+  Scratch tmp(st, pool);
   phifem_pattern* pat = new phifem_pattern();
   pat->n_owned = 0;
   auto own = [&](size_t bytes) -> void* {

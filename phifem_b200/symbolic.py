@@ -51,8 +51,11 @@ class DevicePattern:
 
     def __del__(self):
         h = getattr(self, "_handle", None)
-        if h:
-            _lib.load().phifem_pattern_destroy(h)
+        if h and _lib is not None:       # (module globals are gone at interpreter shutdown)
+            try:
+                _lib.load().phifem_pattern_destroy(h)
+            except Exception:
+                pass
             self._handle = None
 
     def assemble(self, phi_h, f_h, stab_coef=1.0):
