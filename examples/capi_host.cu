@@ -6,8 +6,7 @@
 //        -Lphifem_b200 -lphifem_b200 -Xlinker -rpath=$PWD/phifem_b200 -o capi_host && ./capi_host 48
 //
 // Reference calls replaced: compute_tags_measures (src/phifem/mesh_scripts.py:571-653) and assemble_matrix /
-// assemble_vector of demo/strong-dirichlet/flower/main.py:121-131 (without the one-sided ds(100) term: its entity list
-// needs the host-side ordering of mesh_scripts.py:137-192, which phifem_b200/mesh_scripts.py provides).
+// assemble_vector of demo/strong-dirichlet/flower/main.py:121-131, the one-sided ds(100) term included.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -124,8 +123,15 @@ int main(int argc, char** argv) {
   int64_t cnt[PHIFEM_N_COUNTERS];
   cudaMemcpy(cnt, counters, sizeof(cnt), cudaMemcpyDeviceToHost);
 
+  // ds(100): Gamma_h facets (tag 4) seen from the cells tagged 1 / 2 (src/phifem/mesh_scripts.py:619-622)
+  int64_t n_ent = 0;
+  int32_t* ents = nullptr;
+  CHECK(phifem_integration_entities(&mesh, cell_tags8, facet_tags8, 4, (1u << 1) | (1u << 2), nullptr, 0, &n_ent, nullptr));
+  cudaMalloc(&ents, std::max<int64_t>(1, n_ent) * 2 * sizeof(int32_t));
+  CHECK(phifem_integration_entities(&mesh, cell_tags8, facet_tags8, 4, (1u << 1) | (1u << 2), ents, n_ent, &n_ent, nullptr));
+
   phifem_pattern* pat = nullptr;
-  CHECK(phifem_pattern_create_p1(&mesh, cell_tags8, facet_tags8, nullptr, 0, &pat, nullptr));
+  CHECK(phifem_pattern_create_p1(&mesh, cell_tags8, facet_tags8, ents, n_ent, &pat, nullptr));
   phifem_pattern_view v;
   CHECK(phifem_pattern_view_of(pat, &v));
   double *data, *b;
@@ -136,6 +142,7 @@ int main(int argc, char** argv) {
   if (v.n_active)
     CHECK(phifem_assemble_cells_p1(&mesh, d_phi, d_f, cell_tags8, v.active, v.n_active, v.slots_cells, 1.0, data, b,
                                    nullptr));
+  if (v.n_entities) CHECK(phifem_assemble_boundary_p1(&mesh, d_phi, ents, v.n_entities, v.slots_boundary, data, nullptr));
   if (v.n_ghost) CHECK(phifem_assemble_ghost_p1(&mesh, d_phi, v.ghost, v.n_ghost, v.slots_ghost, 1.0, data, nullptr));
   if (cudaDeviceSynchronize() != cudaSuccess) {
     std::fprintf(stderr, "CUDA error: %s\n", cudaGetErrorString(cudaGetLastError()));
@@ -153,10 +160,11 @@ int main(int argc, char** argv) {
     idx_sum += (long long)h_idx[i] * (i % 7 + 1);
   }
   for (double t : h_b) b_sum += t;
-  std::printf("interior=%lld cut=%lld exterior=%lld nnz=%lld n_active=%lld n_ghost=%lld indices_checksum=%lld "
-              "data_abs_sum=%.17g b_sum=%.17g\n",
+  std::printf("interior=%lld cut=%lld exterior=%lld nnz=%lld n_active=%lld n_ghost=%lld n_entities=%lld "
+              "indices_checksum=%lld data_abs_sum=%.17g b_sum=%.17g\n",
               (long long)cnt[PHIFEM_CNT_INTERIOR], (long long)cnt[PHIFEM_CNT_CUT], (long long)cnt[PHIFEM_CNT_EXTERIOR],
-              (long long)v.nnz, (long long)v.n_active, (long long)v.n_ghost, idx_sum, abs_sum, b_sum);
+              (long long)v.nnz, (long long)v.n_active, (long long)v.n_ghost, (long long)v.n_entities, idx_sum, abs_sum,
+              b_sum);
   phifem_pattern_destroy(pat);
   return 0;
 }

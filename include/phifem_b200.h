@@ -132,6 +132,15 @@ int phifem_entity_records(const phifem_mesh* mesh, const int8_t* cell_tags8,
                           const int8_t* facet_tags8, int32_t facet_tag, uint32_t cell_mask,
                           int64_t* records, int64_t capacity, int64_t* n_records, void* stream);
 
+/* `_compute_integration_entities` (:137-192) complete: the flat (cell, local facet) pairs of every facet tagged
+ * `facet_tag` seen from the cells whose tag bit is set in cell_mask, cells in first-appearance order, the local facets
+ * of a cell ascending -- the `subdomain_data` of ds(100) (facet_tag 4, cell_mask 1<<1 | 1<<2) and ds(101) (facet_tag 3,
+ * cell_mask 1<<2 | 1<<3), :617-626.  entities[capacity, 2] (device); *n_entities (HOST) = number of pairs; nothing is
+ * written when it exceeds capacity (call again with a larger buffer).  Synchronises the stream. */
+int phifem_integration_entities(const phifem_mesh* mesh, const int8_t* cell_tags8, const int8_t* facet_tags8,
+                                int32_t facet_tag, uint32_t cell_mask, int32_t* entities, int64_t capacity,
+                                int64_t* n_entities, void* stream);
+
 /* ---- strong-Dirichlet phi-FEM operator, P1 on triangles / tetrahedra --------------------------
  * Forms: demo/strong-dirichlet/flower/main.py:104-128.  dof = vertex.  `data` (CSR values) and `b`
  * must be zeroed by the caller; contributions are ADDED (PETSc ADD_VALUES semantics, :121-123). */

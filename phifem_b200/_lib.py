@@ -133,6 +133,8 @@ _SIGNATURES = {
     "phifem_pattern_create_p1": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, _vp, ctypes.c_int64,
                                                 ctypes.POINTER(_vp), _vp]),
     "phifem_pattern_view_of": (ctypes.c_int, [_vp, ctypes.POINTER(CPatternView)]),
+    "phifem_integration_entities": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, ctypes.c_int32, ctypes.c_uint32,
+                                                   _vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64), _vp]),
     "phifem_pattern_destroy": (None, [_vp]),
     "phifem_pattern_release_scratch": (None, []),
 }

@@ -108,6 +108,28 @@ __global__ void k_columns(const int64_t* __restrict__ uniq, int64_t nnz, int64_t
 
 inline unsigned blocks_for(int64_t n) { return (unsigned)((n + kBlockSym - 1) / kBlockSym); }
 
+// ordering of `_compute_integration_entities` (mesh_scripts.py:137-192): cells in first-appearance order of the
+// candidate records (key = 2 facet + column), the local facets of a cell ascending
+__global__ void k_entity_first_key(const int64_t* __restrict__ rec, int64_t n, unsigned long long* __restrict__ first) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) atomicMin(first + rec[3 * t + 1], (unsigned long long)rec[3 * t]);
+}
+__global__ void k_entity_sort_keys(const int64_t* __restrict__ rec, int64_t n,
+                                   const unsigned long long* __restrict__ first, int64_t* __restrict__ skey,
+                                   int64_t* __restrict__ sval) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int64_t cell = rec[3 * t + 1], lf = rec[3 * t + 2];
+  skey[t] = (int64_t)first[cell] * 8 + lf;
+  sval[t] = cell * 8 + lf;
+}
+__global__ void k_entity_unpack(const int64_t* __restrict__ sval, int64_t n, int32_t* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  out[2 * t] = (int32_t)(sval[t] >> 3);
+  out[2 * t + 1] = (int32_t)(sval[t] & 7);
+}
+
 // A private stream-ordered pool per device whose memory stays cached between calls (release threshold = max): the
 // default pool hands its memory back to the driver at every synchronisation, and re-allocating the ~10 GB of sort
 // scratch of config E costs ten times the sort.  phifem_pattern_release_scratch() trims it.
@@ -306,5 +328,58 @@ extern "C" int phifem_pattern_create_p1(const phifem_mesh* mesh, const int8_t* c
   pat->v.slots_ghost = slots_g;
   pat->v.slots_boundary = slots_b;
   *out = pat;
+  return PHIFEM_OK;
+}
+
+extern "C" int phifem_integration_entities(const phifem_mesh* mesh, const int8_t* cell_tags8, const int8_t* facet_tags8,
+                                           int32_t facet_tag, uint32_t cell_mask, int32_t* entities, int64_t capacity,
+                                           int64_t* n_entities, void* stream) {
+  PHIFEM_CHECK_ARG(mesh != nullptr && n_entities != nullptr, "null pointer");
+  PHIFEM_CHECK_ARG(capacity >= 0 && (capacity == 0 || entities), "entity buffer");
+  *n_entities = 0;
+  if (mesh->n_facets == 0) return PHIFEM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemPool_t pool = scratch_pool();
+  if (!pool) {
+    set_error("phifem_integration_entities: cannot create the scratch memory pool");
+    return PHIFEM_ERR_CUDA;
+  }
+  Scratch tmp(st, pool);
+  auto fail = [&](const char* what) {
+    set_error("phifem_integration_entities: %s: %s", what, cudaGetErrorString(cudaGetLastError()));
+    return PHIFEM_ERR_CUDA;
+  };
+  int64_t* d_n = (int64_t*)tmp.get(sizeof(int64_t));
+  if (!d_n) return fail("scratch allocation");
+  // pass 1 counts the candidates, pass 2 writes them
+  int64_t n = 0;
+  cudaMemsetAsync(d_n, 0, sizeof(int64_t), st);
+  if (int rc = phifem_entity_records(mesh, cell_tags8, facet_tags8, facet_tag, cell_mask, nullptr, 0, d_n, stream))
+    return rc;
+  if (cudaMemcpyAsync(&n, d_n, sizeof(n), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess)
+    return fail("counting");
+  *n_entities = n;
+  if (n == 0 || n > capacity) return PHIFEM_OK;  // the caller retries with a buffer of *n_entities pairs
+  int64_t* rec = (int64_t*)tmp.get(sizeof(int64_t) * 3 * n);
+  unsigned long long* first = (unsigned long long*)tmp.get(sizeof(unsigned long long) * mesh->n_cells);
+  int64_t* skey = (int64_t*)tmp.get(sizeof(int64_t) * n);
+  int64_t* sval = (int64_t*)tmp.get(sizeof(int64_t) * n);
+  int64_t* skey2 = (int64_t*)tmp.get(sizeof(int64_t) * n);
+  int64_t* sval2 = (int64_t*)tmp.get(sizeof(int64_t) * n);
+  if (!rec || !first || !skey || !sval || !skey2 || !sval2) return fail("scratch allocation");
+  cudaMemsetAsync(d_n, 0, sizeof(int64_t), st);
+  if (int rc = phifem_entity_records(mesh, cell_tags8, facet_tags8, facet_tag, cell_mask, rec, n, d_n, stream))
+    return rc;
+  cudaMemsetAsync(first, 0xff, sizeof(unsigned long long) * mesh->n_cells, st);
+  k_entity_first_key<<<blocks_for(n), kBlockSym, 0, st>>>(rec, n, first);
+  k_entity_sort_keys<<<blocks_for(n), kBlockSym, 0, st>>>(rec, n, first, skey, sval);
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, skey, skey2, sval, sval2, (int)n, 0, 40, st);
+  void* ws = tmp.get(bytes);
+  if (!ws) return fail("scratch allocation");
+  cub::DeviceRadixSort::SortPairs(ws, bytes, skey, skey2, sval, sval2, (int)n, 0, 40, st);  // keys < 2^(32 + 1 + 3)
+  k_entity_unpack<<<blocks_for(n), kBlockSym, 0, st>>>(sval2, n, entities);
+  if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) return fail("ordering kernels");
   return PHIFEM_OK;
 }

@@ -16,6 +16,7 @@ Public API (reference :571-653):
 (the stand-in for the reference's UFL expression of `SpatialCoordinate`).
 """
 import os
+import ctypes
 import warnings
 
 import numpy as np
@@ -173,26 +174,17 @@ def _integration_entities_dev(mesh, cell_tags8, facet_tags8, facet_tag, cell_tag
     mask = 0
     for t in cell_tag_values:
         mask |= 1 << int(t)
-    n_dev = torch.zeros(1, dtype=torch.int64, device=mesh.device)
+    # candidates, first-appearance ordering and the sort all happen behind the C ABI (csrc/symbolic.cu)
+    n = ctypes.c_int64(0)
     capacity = max(1024, int(4 * mesh.num_facets ** (1 - 1.0 / mesh.topology.dim)))
     while True:
-        rec = torch.empty((capacity, 3), dtype=torch.int64, device=mesh.device)
-        n_dev.zero_()
-        _lib.check(lib.phifem_entity_records(cm, _lib.ptr(cell_tags8), _lib.ptr(facet_tags8), facet_tag,
-                                             mask, _lib.ptr(rec), capacity, _lib.ptr(n_dev), _lib.stream()))
-        n = int(n_dev.item())
-        if n <= capacity:
+        ents = torch.empty((capacity, 2), dtype=torch.int32, device=mesh.device)
+        _lib.check(lib.phifem_integration_entities(cm, _lib.ptr(cell_tags8), _lib.ptr(facet_tags8), facet_tag, mask,
+                                                   _lib.ptr(ents), capacity, ctypes.byref(n), _lib.stream()))
+        if n.value <= capacity:
             break
-        capacity = n
-    rec = rec[:n]
-    if n == 0:
-        return torch.zeros(0, dtype=torch.int32, device=mesh.device)
-    key, cell, lf = rec[:, 0], rec[:, 1], rec[:, 2]
-    ucell, inv = torch.unique(cell, return_inverse=True)
-    first = torch.full((len(ucell),), torch.iinfo(torch.int64).max, dtype=torch.int64, device=mesh.device)
-    first.scatter_reduce_(0, inv, key, reduce="amin")          # first appearance of each cell
-    order = torch.argsort(first[inv] * 8 + lf)                  # then local facets ascending
-    return torch.stack([cell[order], lf[order]], dim=1).reshape(-1).to(torch.int32)
+        capacity = int(n.value)
+    return ents[:n.value].reshape(-1).contiguous()
 
 
 def _tags_from_workspace(mesh, ws):

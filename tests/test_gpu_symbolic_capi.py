@@ -95,10 +95,10 @@ def test_c_host_without_python_reproduces_the_python_path(tmp_path):
     c8 = ctags.values_dev
     assert [int(got["interior"]), int(got["cut"]), int(got["exterior"])] == \
         [int((c8 == 1).sum()), int((c8 == 2).sum()), int((c8 == 3).sum())]
-    plan = assemble.build_plan(mesh, ctags, ftags, None, method="atomic")      # the C host passes no ds(100) entities
+    plan = assemble.build_plan(mesh, ctags, ftags, ds(100), method="atomic")
     A, b = assemble.assemble_strong_dirichlet(plan, phi, f, stab_coef=1.0)
     assert int(got["nnz"]) == plan.nnz and int(got["n_active"]) == plan.active.numel()
-    assert int(got["n_ghost"]) == plan.ghost.numel()
+    assert int(got["n_ghost"]) == plan.ghost.numel() and int(got["n_entities"]) == plan.entities.shape[0] > 0
     assert int(got["indices_checksum"]) == int((plan.indices.long() * (torch.arange(plan.nnz, device="cuda") % 7 + 1)).sum())
     assert abs(float(got["data_abs_sum"]) - float(A.data.abs().sum())) <= 1e-11 * float(A.data.abs().sum())
     assert abs(float(got["b_sum"]) - float(b.sum())) <= 1e-11 * float(b.abs().sum())
