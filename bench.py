@@ -105,6 +105,9 @@ def algorithmic_bytes(counts):
     na, nva, ng, nnz = counts["Na"], counts["Nv_active"], counts["Ng"], counts["nnz"]
     nd, nrow = counts.get("nd", nvpc), counts.get("Nrow", nv)
     ndof_a = counts.get("Ndof_active", nva)          # active dofs of the trial/test space (= of phi and f)
+    # SURVEY.md section 8(d) as written: tags counted as the int32 arrays of the reference's MeshTags (4 Nc + 4 Nf).
+    # The kernels write them as one byte per entity and widen on demand, so their DRAM traffic (`roofline.traffic`,
+    # profiles/) is below this yardstick for the tag half.
     b_tags_cells = 4 * nvpc * nc + 8 * nv + 4 * nc
     b_tags_facets = 4 * nvpc * nc + 4 * nf            # c2f (== f2c in size) + facet tags out
     geo = 4 * nvpc * na if nd != nvpc else 0          # P2: cell -> vertex for the geometry besides the dofmap
@@ -550,6 +553,7 @@ def run_ours(args):
                                          + ("owner computes its rows from 2 redundantly classified ghost "
                                             "layers: one 8-byte all-reduce per step, no halo exchange"
                                             if args.dist_mode == "rows" else "NCCL halo exchange")),
+                           "tags_dtype": "int8 on the device (int32 MeshTags.values widened on demand)",
                            "timed": "tag kernels + zeroing + assembly kernels; symbolic phase excluded; "
                                     "kernels_ms: tag_* and assembly from events inside the timed region, "
                                     "the assemble_* split from an untimed pass-by-pass loop"},

@@ -100,7 +100,8 @@ int phifem_cell_points(const phifem_mesh* mesh, const double* shape, int32_t n_p
 
 /* Replaces `_compute_detection_vector` (:95-134) + `_tag_cells` (:284-390) for the `dx` detection
  * measure: cell_tags[n_cells] in {1 interior, 2 cut, 3 exterior, 0 untagged}; cell_tags8 is the
- * same as int8 (consumed by the facet / assembly kernels).  `counters` (int64[PHIFEM_N_COUNTERS])
+ * same as int8 (consumed by the facet / assembly kernels).  cell_tags may be NULL: only the int8 array is written then
+ * (a quarter of the output bytes; widen it where an int32 `MeshTags.values` is asked for).  `counters` (int64[PHIFEM_N_COUNTERS])
  * must be zeroed by the caller; slots 0..5 are accumulated.  single_layer_cut: bit 0 applies
  * :349-358; bit 1 makes the P1 fast path evaluate every denominator exactly (see slot 5).  `vertex_scratch` (uint8[n_vertices + 3], any content) holds the per-vertex class bytes of
  * the P1 classifier (sign of phi, evaluated once per vertex) and the flags of single_layer_cut. */
@@ -109,7 +110,7 @@ int phifem_tag_cells(const phifem_mesh* mesh, const phifem_levelset* ls, int32_t
                      int64_t* counters, void* stream);
 
 /* Replaces `_tag_facets` (:393-558) including its `ds` detection pass (:434-452):
- * facet_tags[n_facets] in 1..6.  Reads counters[PHIFEM_CNT_EXTERIOR] on the device (the "no exterior
+ * facet_tags[n_facets] in 1..6 (may be NULL like cell_tags: int8 output only).  Reads counters[PHIFEM_CNT_EXTERIOR] on the device (the "no exterior
  * cell" branch :469-470), accumulates slots 11..13. */
 int phifem_tag_facets(const phifem_mesh* mesh, const phifem_levelset* ls, const int8_t* cell_tags8,
                       int32_t* facet_tags, int8_t* facet_tags8, int64_t* counters, void* stream);

@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(kBlock, 3) k_tag_cells_p1(phifem_mesh m, const
       }
       if (valid[u]) {
         const int64_t c = base + (int64_t)u * blockDim.x + threadIdx.x;
-        tags[c] = tag;
+        if (tags) tags[c] = tag;
         tags8[c] = (int8_t)tag;
         local[0] += tag == 1;
         local[1] += tag == 2;
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(kBlock) k_tag_cells_generic(phifem_mesh m, phi
       }
       tag = classify(num, den);
       zden = is_close_to_zero(den);
-      tags[c] = tag;
+      if (tags) tags[c] = tag;
       tags8[c] = (int8_t)tag;
     }
     cnt.vote(tag == 1, 0);
@@ -358,7 +358,7 @@ __global__ void k_single_layer_apply(const int32_t* __restrict__ cells, int nv, 
   bool touches = false;
   for (int k = 0; k < nv; ++k) touches |= vflag[cells[c * nv + k]] != 0;
   if (!touches) {  // isolated cut cell -> exterior
-    tags[c] = 3;
+    if (tags) tags[c] = 3;
     tags8[c] = 3;
     atomicAdd(reinterpret_cast<unsigned long long*>(counters + PHIFEM_CNT_EXTERIOR), 1ull);
     atomicAdd(reinterpret_cast<unsigned long long*>(counters + PHIFEM_CNT_CUT), ~0ull);  // -1
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(kBlock) k_tag_boundary_facets(phifem_mesh m, p
     const int owner = __ldg(m.f2c + 2 * (int64_t)f);
     const int tag = tag_boundary_facet<CT>(m, ls, owner, __ldg(ctags + owner) & 3, f, anyE, n_zden,
                                            n_conflict, n_owner);
-    ftags[f] = tag;
+    if (ftags) ftags[f] = tag;
     ftags8[f] = (int8_t)tag;
   }
   cnt.add(n_zden, 0);
@@ -561,14 +561,14 @@ __global__ void __launch_bounds__(kBlock, 4) k_tag_facets(phifem_mesh m, phifem_
       out[u] = tag;
     }
     if (all_interior) {
-      *reinterpret_cast<int4*>(ftags + f0) = make_int4(out[0], out[1], out[2], out[3]);
+      if (ftags) *reinterpret_cast<int4*>(ftags + f0) = make_int4(out[0], out[1], out[2], out[3]);
       *reinterpret_cast<unsigned int*>(ftags8 + f0) =
           (unsigned)out[0] | ((unsigned)out[1] << 8) | ((unsigned)out[2] << 16) | ((unsigned)out[3] << 24);
     } else {
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u)
         if (out[u] >= 0) {
-          ftags[f0 + u] = out[u];
+          if (ftags) ftags[f0 + u] = out[u];
           ftags8[f0 + u] = (int8_t)out[u];
         }
     }
@@ -684,7 +684,7 @@ extern "C" int phifem_tag_cells(const phifem_mesh* mesh, const phifem_levelset* 
                                 uint8_t* vertex_scratch, int64_t* counters, void* stream) {
   if (int rc = check_mesh(mesh, false)) return rc;
   if (int rc = check_levelset(mesh, ls, false)) return rc;
-  PHIFEM_CHECK_ARG(cell_tags && cell_tags8 && counters, "output pointer is null");
+  PHIFEM_CHECK_ARG(cell_tags8 && counters, "output pointer is null");
   PHIFEM_CHECK_ARG(vertex_scratch, "vertex_scratch is null (uint8[n_vertices + 3])");
   const bool exact_zero_den = (single_layer_cut & 2) != 0;
   single_layer_cut &= 1;
@@ -766,7 +766,7 @@ extern "C" int phifem_tag_facets_phase(const phifem_mesh* mesh, const phifem_lev
                                        int64_t* counters, int32_t phases, void* stream) {
   if (int rc = check_mesh(mesh, true)) return rc;
   if (int rc = check_levelset(mesh, ls, true)) return rc;
-  PHIFEM_CHECK_ARG(cell_tags8 && facet_tags && facet_tags8 && counters, "null pointer");
+  PHIFEM_CHECK_ARG(cell_tags8 && facet_tags8 && counters, "null pointer");
   if (mesh->n_facets == 0) return PHIFEM_OK;
   const int64_t tiles = (mesh->n_facets + kBlock * kUnroll - 1) / (kBlock * kUnroll);
   cudaStream_t st = (cudaStream_t)stream;

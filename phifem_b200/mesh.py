@@ -248,12 +248,27 @@ class MeshTags:
     Tags live on the device (`values_dev` holds one entry per entity, 0 = untagged); the host
     views `indices` / `values` are materialised on first access (one D2H copy)."""
 
-    def __init__(self, mesh, dim, values_dev=None, indices=None, values=None):
+    def __init__(self, mesh, dim, values_dev=None, indices=None, values=None, tags8=None):
         self.mesh = mesh
         self.dim = dim
-        self.values_dev = values_dev
+        self._values_dev = values_dev
+        if tags8 is not None:     # the one-byte array the kernels wrote (computed tags fit a byte)
+            self.tags8 = tags8
+            self.tags8_exact = True
         self._indices = None if indices is None else np.ascontiguousarray(indices, dtype=np.int32)
         self._values = None if values is None else np.ascontiguousarray(values, dtype=np.int32)
+
+    @property
+    def values_dev(self):
+        """Dense int32 tags on the device (the dtype of the reference's MeshTags.values); widened from the kernels'
+        one-byte array on first access when only that was written."""
+        if self._values_dev is None:
+            self._values_dev = self.tags8.to(torch.int32)
+        return self._values_dev
+
+    @values_dev.setter
+    def values_dev(self, v):
+        self._values_dev = v
 
     @staticmethod
     def from_lists(mesh, dim, indices, values):

@@ -104,14 +104,26 @@ class _DeviceLevelset:
 class TagWorkspace:
     """Device buffers of one classification (reused across calls on the same mesh)."""
 
-    def __init__(self, mesh):
+    def __init__(self, mesh, int32=False):
+        """int32=True: the kernels also write the tags as int32 arrays (the dtype of the reference's MeshTags);
+        by default only the one-byte arrays the facet / assembly kernels consume are written -- a quarter of the output
+        bytes of the tag kernels -- and `MeshTags.values_dev` widens them when somebody asks."""
         dev = mesh.device
-        self.cell_tags = torch.empty(mesh.num_cells, dtype=torch.int32, device=dev)
+        self.cell_tags32 = torch.empty(mesh.num_cells, dtype=torch.int32, device=dev) if int32 else None
         self.cell_tags8 = torch.empty(mesh.num_cells, dtype=torch.int8, device=dev)
-        self.facet_tags = torch.empty(mesh.num_facets, dtype=torch.int32, device=dev)
+        self.facet_tags32 = torch.empty(mesh.num_facets, dtype=torch.int32, device=dev) if int32 else None
         self.facet_tags8 = torch.empty(mesh.num_facets, dtype=torch.int8, device=dev)
         self.counters = torch.zeros(_lib.N_COUNTERS, dtype=torch.int64, device=dev)
         self.vertex_scratch = None
+
+    @property
+    def cell_tags(self):
+        """int32 view of the cell tags (widened on demand when the kernels wrote int8 only)."""
+        return self.cell_tags32 if self.cell_tags32 is not None else self.cell_tags8.to(torch.int32)
+
+    @property
+    def facet_tags(self):
+        return self.facet_tags32 if self.facet_tags32 is not None else self.facet_tags8.to(torch.int32)
 
 
 def classify_cells(mesh, dls, ws, single_layer_cut=False, exact_zero_den=False):
@@ -123,7 +135,7 @@ def classify_cells(mesh, dls, ws, single_layer_cut=False, exact_zero_den=False):
         ws.vertex_scratch = torch.empty(mesh.num_vertices + 3, dtype=torch.uint8, device=mesh.device)
     _lib.check(_lib.load().phifem_tag_cells(
         _lib.c_mesh(mesh), dls.c, int(bool(single_layer_cut)) | (2 if exact_zero_den else 0),
-        _lib.ptr(ws.cell_tags),
+        _lib.ptr(ws.cell_tags32),
         _lib.ptr(ws.cell_tags8), _lib.ptr(ws.vertex_scratch), _lib.ptr(ws.counters), _lib.stream()))
 
 
@@ -135,7 +147,7 @@ def classify_facets(mesh, dls, ws, phases=FACETS_INTERIOR | FACETS_BOUNDARY):
     the interior facets (independent of the global "any exterior cell" flag) or only the mesh-boundary facets
     (which read it) -- the sharded classifiers put their all-reduce between the two."""
     _lib.check(_lib.load().phifem_tag_facets_phase(
-        _lib.c_mesh(mesh), dls.c, _lib.ptr(ws.cell_tags8), _lib.ptr(ws.facet_tags),
+        _lib.c_mesh(mesh), dls.c, _lib.ptr(ws.cell_tags8), _lib.ptr(ws.facet_tags32),
         _lib.ptr(ws.facet_tags8), _lib.ptr(ws.counters), int(phases), _lib.stream()))
 
 
@@ -189,7 +201,8 @@ def _integration_entities_dev(mesh, cell_tags8, facet_tags8, facet_tag, cell_tag
 
 def _tags_from_workspace(mesh, ws):
     tdim = mesh.topology.dim
-    return (MeshTags(mesh, tdim, ws.cell_tags), MeshTags(mesh, tdim - 1, ws.facet_tags))
+    return (MeshTags(mesh, tdim, ws.cell_tags32, tags8=ws.cell_tags8),
+            MeshTags(mesh, tdim - 1, ws.facet_tags32, tags8=ws.facet_tags8))
 
 
 def _overwrite_tags(mesh, tags_to_overwrite, new_tags):
@@ -306,9 +319,9 @@ def _tag_facets(mesh, cells_tags, discrete_levelset, detection_degree):
     ws.cell_tags8 = cells_tags.values_dev.to(torch.int8).contiguous()
     ws.counters[_lib.CNT_EXTERIOR] = int((ws.cell_tags8 == 3).sum())
     _lib.check(_lib.load().phifem_tag_facets(_lib.c_mesh(mesh), dls.c, _lib.ptr(ws.cell_tags8),
-                                             _lib.ptr(ws.facet_tags), _lib.ptr(ws.facet_tags8),
+                                             _lib.ptr(ws.facet_tags32), _lib.ptr(ws.facet_tags8),
                                              _lib.ptr(ws.counters), _lib.stream()))
-    return MeshTags(mesh, mesh.topology.dim - 1, ws.facet_tags)
+    return MeshTags(mesh, mesh.topology.dim - 1, ws.facet_tags32, tags8=ws.facet_tags8)
 
 
 def _compute_integration_entities(mesh, integration_cells, integration_facets, ind):
