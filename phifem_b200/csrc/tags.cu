@@ -148,6 +148,9 @@ struct BlockCounters {
 // sequential sum (all terms share a sign => num == +-den exactly).
 // HBM-latency bound: every thread keeps kUnroll independent cells in flight (index loads first, then
 // all gathers), counters stay in registers until the end of the grid-stride loop.
+#ifndef PHIFEM_TAG_CELLS_MINBLOCKS
+#define PHIFEM_TAG_CELLS_MINBLOCKS 3
+#endif
 constexpr int kUnroll = 4;
 
 // exact path for cells the sign test cannot decide; scalars in / packed (tag | zden << 8) out so
@@ -207,7 +210,7 @@ __global__ void __launch_bounds__(kBlock) k_vertex_class(const double* __restric
 }
 
 template <int CT>
-__global__ void __launch_bounds__(kBlock, 3) k_tag_cells_p1(phifem_mesh m, const double* __restrict__ phi,
+__global__ void __launch_bounds__(kBlock, PHIFEM_TAG_CELLS_MINBLOCKS) k_tag_cells_p1(phifem_mesh m, const double* __restrict__ phi,
                                                             const uint8_t* __restrict__ vclass,
                                                             bool exact_zero_den,
                                                             int32_t* __restrict__ tags,
