@@ -218,8 +218,18 @@ __global__ void __launch_bounds__(kBlock, PHIFEM_TAG_CELLS_MINBLOCKS) k_tag_cell
                                                             int64_t* counters) {
   using T = CellTraits<CT>;
   __shared__ unsigned int scnt[6];
-  BlockCounters cnt(scnt, 6);
+  // Cells the class bytes cannot decide (the cut cells and a few more: ~1.5 % of config E) are not evaluated where
+  // they are found -- one such lane makes its whole warp walk the exact path (coordinate gathers, |det J|, the
+  // sequential sums), which was ~40 % of the kernel's instructions -- but parked in shared memory and evaluated
+  // densely, one per thread, after the tile's barrier.  Two lists alternate between tiles; their fill counts only grow
+  // (`done` = the count every thread saw at the previous use), so one barrier per tile suffices.
+  __shared__ int s_pend[2][kBlock * kUnroll];
+  __shared__ unsigned int s_np[2];
+  if (threadIdx.x < 2) s_np[threadIdx.x] = 0u;
+  BlockCounters cnt(scnt, 6);  // (its constructor synchronises the block)
   unsigned int local[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+  unsigned int done[2] = {0u, 0u};
+  int par = 0;
   // kUnroll cells per thread, strided by the block size: every index load is one coalesced line per
   // warp (the consecutive-cells mapping with vector stores measured slower here: 0.32 vs 0.27 ms)
   const int64_t tile = (int64_t)blockDim.x * kUnroll;
@@ -265,16 +275,10 @@ __global__ void __launch_bounds__(kBlock, PHIFEM_TAG_CELLS_MINBLOCKS) k_tag_cell
         else if (exact_zero_den) fast = false;
         else ambiguous = true;
       }
-      if (!fast && valid[u]) {
-        double p[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int k = 0; k < T::nv; ++k) p[k] = __ldg(phi + v[u][k]);
-        const int r = tag_cell_exact<CT>(m.x, v[u][0], v[u][1], v[u][2], T::nv == 4 ? v[u][3] : 0,
-                                         p[0], p[1], p[2], p[3]);
-        tag = r & 0xff;
-        zden = (r >> 8) != 0;
-      }
-      if (valid[u]) {
+      if (!fast && valid[u]) {  // parked: position inside the tile
+        const unsigned int i = atomicAdd(&s_np[par], 1u) - done[par];
+        s_pend[par][i] = u * (int)blockDim.x + (int)threadIdx.x;
+      } else if (valid[u]) {
         const int64_t c = base + (int64_t)u * blockDim.x + threadIdx.x;
         if (tags) tags[c] = tag;
         tags8[c] = (int8_t)tag;
@@ -286,6 +290,29 @@ __global__ void __launch_bounds__(kBlock, PHIFEM_TAG_CELLS_MINBLOCKS) k_tag_cell
         local[5] += ambiguous;
       }
     }
+    __syncthreads();
+    const unsigned int end = s_np[par];
+    for (unsigned int i = done[par] + threadIdx.x; i < end; i += blockDim.x) {
+      const int64_t c = base + s_pend[par][i - done[par]];
+      int w[4] = {0, 0, 0, 0};
+      double p[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int k = 0; k < T::nv; ++k) {
+        w[k] = __ldg(m.cells + c * T::nv + k);
+        p[k] = __ldg(phi + w[k]);
+      }
+      const int r = tag_cell_exact<CT>(m.x, w[0], w[1], w[2], w[3], p[0], p[1], p[2], p[3]);
+      const int tag = r & 0xff;
+      if (tags) tags[c] = tag;
+      tags8[c] = (int8_t)tag;
+      local[0] += tag == 1;
+      local[1] += tag == 2;
+      local[2] += tag == 3;
+      local[3] += tag == 0;
+      local[4] += (r >> 8) != 0;
+    }
+    done[par] = end;
+    par ^= 1;
   }
 #pragma unroll
   for (int i = 0; i < 6; ++i) cnt.add(local[i], i);
