@@ -503,8 +503,11 @@ def run_ours(args):
                     keep[j] = (phi_d, f_d, ct_, ft_, A_, b_)
             torch.cuda.synchronize()
             elapsed = time.perf_counter() - t_start
-            for k in out_h:                   # both buffer sets hold the same results
-                assert torch.equal(outs[0][k], outs[1][k]), k
+            for k in out_h:                   # both buffer sets hold the same results (bit for bit where the
+                if plan.method == "rows" or outs[0][k].dtype != torch.float64:   # assembly sums in a fixed order)
+                    assert torch.equal(outs[0][k], outs[1][k]), k
+                else:
+                    assert torch.allclose(outs[0][k], outs[1][k], rtol=1e-10, atol=1e-12 * float(outs[0][k].abs().max())), k
             return elapsed / n_steps
 
         e2e_steps = max(2, min(args.steps, 5))
@@ -514,12 +517,13 @@ def run_ours(args):
         for _ in range(e2e_steps):
             e2e_step()
         dt = (time.perf_counter() - t0) / e2e_steps
-        serial_dt = dt
+        pipelined_dt = None
         if args.e2e_pipeline:
             ref_data, ref_b = out_h["data"].clone(), out_h["b"].clone()
             e2e_pipelined(4)
-            dt = e2e_pipelined(2 * e2e_steps)
-            assert torch.equal(out_h["data"], ref_data) and torch.equal(out_h["b"], ref_b)
+            pipelined_dt = e2e_pipelined(2 * e2e_steps)
+            if plan.method == "rows":
+                assert torch.equal(out_h["data"], ref_data) and torch.equal(out_h["b"], ref_b)
         e2e = {"value": mesh.num_cells / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
                "h2d_bytes_per_step": int(phi_h.numel() * 8 + (phi_asm_h.numel() * 8 if degree == 2 else 0)
                                          + f_h.numel() * 8),
@@ -527,10 +531,9 @@ def run_ours(args):
                "api": "compute_tags_measures(box_mode=True) + assemble_strong_dirichlet(plan, ...) with "
                       "pinned host level set / source in and pinned host tags (1 byte per cell / facet) + CSR values "
                       "+ b out, source-term upload overlapped with the tag kernels, tag copies with the assembly; "
-                      "assembly plan (symbolic phase) reused"
-                      + ("; two steps in flight on alternating streams with double-buffered host outputs"
-                         if args.e2e_pipeline else ""),
-               "one_step_at_a_time_ms": serial_dt * 1e3}
+                      "assembly plan (symbolic phase) reused; one step at a time"}
+        if pipelined_dt is not None:
+            e2e["two_steps_in_flight_ms"] = pipelined_dt * 1e3
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu and args.config == "3d-p1":
@@ -618,9 +621,10 @@ def main():
     ap.add_argument("--capacity", type=int, default=None, help="contributions per block (blocked scatter)")
     ap.add_argument("--order", default="natural", choices=["natural", "morton"],
                     help="row processing order of the row-gather assembly")
-    ap.add_argument("--no-e2e-pipeline", dest="e2e_pipeline", action="store_false",
-                    help="e2e one step at a time instead of two steps in flight (uploads and kernels of step i + 1 "
-                         "under the downloads of step i); the one-step figure is reported either way")
+    ap.add_argument("--e2e-pipeline", action="store_true",
+                    help="also measure e2e with two steps in flight (uploads and kernels of step i + 1 under the "
+                         "downloads of step i): reported as e2e.two_steps_in_flight_ms, the e2e value stays the "
+                         "one-step-at-a-time figure (the pipelined one varies from box to box: 14.1 / 20.5 ms seen)")
     ap.add_argument("--geometry", action="store_true",
                     help="row-gather cell pass from a per-plan geometry table instead of the vertex coordinates "
                          "(measured slower: profiles/round2_a_geometry_kernel.md)")
