@@ -78,7 +78,7 @@ class ElasticityPlan:
         self.entities_out = ents_out.reshape(-1, 2).to(torch.int32).contiguous()                      # ds(101)
 
         def pair_keys(vs):   # [m, k] vertices -> [m, k*k] keys row * Nv + col (row = test vertex)
-            return (vs[:, :, None] * nvx + vs[:, None, :]).reshape(vs.shape[0], -1)
+            return (vs[:, :, None] * nvx + vs[:, None, :]).reshape(vs.shape[0], vs.shape[1] * vs.shape[1])
 
         def macro(facets):
             g = facets.long()

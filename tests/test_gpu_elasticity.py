@@ -149,3 +149,34 @@ def test_interface_elasticity_demo_runs_end_to_end():
     assert res["dof"] == [2 * 16 * 16, 2 * 31 * 31, 2 * 61 * 61]
     assert l2[-1] < 3e-3 and l2[0] / l2[-1] > 10.0, l2
     assert h1[-1] < 6e-2 and h1[0] / h1[-1] > 3.0, h1
+
+
+@pytest.mark.parametrize("where", ["outside", "inside"])
+def test_elasticity_without_cut_cells(where):
+    """The interface misses the mesh: every cell carries one material only (tag 3 -> u_out stiffness, tag 1 -> u_in), no
+    cut cell, no interface facet, no one-sided entity; the kernels must cope with the empty lists and match the oracle."""
+    mesh = synthetic.unstructured_variant(synthetic.rectangle_mesh(7, device="cuda"), jitter=0.2, seed=3)
+    r = 0.5 if where == "outside" else 9.0
+    c = (5.0, 5.0) if where == "outside" else (0.0, 0.0)
+    phi = synthetic.sphere_levelset(mesh.x, center=c, radius=r)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        ctags, ftags, _, d_bdry, _ = mesh_scripts.compute_tags_measures(
+            mesh, fem.Function(fem.functionspace(mesh, 1), phi), 1, box_mode=True)
+    tag = 3 if where == "outside" else 1
+    assert bool((ctags.values_dev == tag).all())
+    plan = elasticity.build_plan_interface_elasticity(mesh, ctags, ftags, d_bdry)
+    assert plan.cut_cells.numel() == 0 and plan.facets_in.numel() == 0 and plan.facets_out.numel() == 0
+    f = torch.from_numpy(np.random.default_rng(5).uniform(-1, 1, (mesh.num_vertices, 2))).cuda()
+    A, b = elasticity.assemble_interface_elasticity(plan, phi, f, elasticity.Material(1.0, 0.3, 0.05, 0.27))
+    ip, ix, data, bo = OE.assemble_interface_elasticity(
+        mesh.x.cpu().numpy(), mesh.cells.cpu().numpy().astype(np.int64), phi.cpu().numpy(), f.cpu().numpy(),
+        ctags.values_dev.cpu().numpy(), ftags.values_dev.cpu().numpy(), mesh.c2f.cpu().numpy(), mesh.f2c.cpu().numpy(),
+        d_bdry(100).integration_entities, d_bdry(101).integration_entities, mat=OE.Material(1.0, 0.3, 0.05, 0.27))
+    assert np.array_equal(A.indptr.cpu().numpy(), ip) and np.array_equal(A.indices.cpu().numpy(), ix)
+    assert np.abs(A.data.cpu().numpy() - data).max() <= RTOL * np.abs(data).max()
+    assert np.abs(b.cpu().numpy() - bo).max() <= RTOL * np.abs(bo).max()
+    # only the stiffness block of the one material is populated
+    blk = np.repeat(np.arange(len(ip) - 1), np.diff(ip)) % plan.nb
+    off = plan.layout["u_out" if where == "outside" else "u_in"][0]
+    assert np.all(data[(blk < off) | (blk >= off + 2)] == 0.0) and np.abs(data).max() > 0

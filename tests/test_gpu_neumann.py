@@ -113,3 +113,29 @@ def test_neumann_manufactured_solution_converges(kphi, min_rate):
     rates = [np.log2(errs[i] / errs[i + 1]) for i in range(2)]
     print("neumann errors", kphi, errs, rates)
     assert errs[-1] < 2e-3 and min(rates) > min_rate, (errs, rates)
+
+
+def test_neumann_without_cut_cells():
+    """Every cell interior (the level set contains the mesh): only the closed-form u-u block and the load of the
+    interior kernel remain (plus the one-sided term on the mesh boundary); empty cut / ghost lists must be handled."""
+    mesh = synthetic.unstructured_variant(synthetic.rectangle_mesh(7, device="cuda"), jitter=0.2, seed=3)
+    phi = synthetic.sphere_levelset(mesh.x, center=(0.0, 0.0), radius=9.0)
+    V = fem.functionspace(mesh, 1)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        ctags, ftags, _, ds, _ = mesh_scripts.compute_tags_measures(mesh, fem.Function(V, phi), 1, box_mode=True)
+    assert bool((ctags.values_dev == 1).all())
+    rng = np.random.default_rng(2)
+    f = torch.from_numpy(rng.uniform(-1, 1, mesh.num_vertices)).cuda()
+    un = torch.from_numpy(rng.uniform(-1, 1, mesh.num_vertices)).cuda()
+    plan = assemble.build_plan_neumann(mesh, ctags, ftags, ds(100))
+    # no exterior cell: the mesh-boundary facets become Gamma_h (src/phifem/mesh_scripts.py:469-474), so ds(100) is not empty
+    assert plan.cut_positions.numel() == 0 and plan.ghost.numel() == 0 and plan.entities.shape[0] == 4 * 7
+    A, b = assemble.assemble_neumann(plan, phi, f, un)
+    ip, ix, data, bo = OA.assemble_neumann(
+        mesh.x.cpu().numpy(), mesh.cells.cpu().numpy().astype(np.int64), phi.cpu().numpy(), f.cpu().numpy(),
+        un.cpu().numpy(), ctags.values_dev.cpu().numpy(), ftags.values_dev.cpu().numpy(), mesh.c2f.cpu().numpy(),
+        mesh.f2c.cpu().numpy(), ds(100).integration_entities)
+    assert np.array_equal(A.indptr.cpu().numpy(), ip) and np.array_equal(A.indices.cpu().numpy(), ix)
+    assert np.abs(A.data.cpu().numpy() - data).max() <= RTOL * np.abs(data).max()
+    assert np.abs(b.cpu().numpy() - bo).max() <= RTOL * np.abs(bo).max()
