@@ -200,7 +200,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from phifem_b200 import _lib, assemble, fem, mesh_scripts, synthetic
+    from phifem_b200 import assemble, fem, mesh_scripts, synthetic
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

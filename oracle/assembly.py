@@ -23,7 +23,6 @@ import numpy as np
 import scipy.sparse as sp
 from scipy.special import roots_jacobi
 
-from .tags import LOCAL_FACETS
 
 # P2 local edge order of dolfinx/basix [dep-knowledge, SURVEY.md C.7]
 P2_EDGES = {2: ((1, 2), (0, 2), (0, 1)),

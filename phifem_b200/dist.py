@@ -25,13 +25,12 @@ path shards the way SURVEY.md section 8(e) lays out:
 The symbolic phase (pattern union across ranks, slot maps, send/recv lists) uses point-to-point
 transfers and works on the `gloo` backend too, which is how the CPU tests cover it.
 """
-import math
 from types import SimpleNamespace
 
 import torch
 import torch.distributed as dist
 
-from . import _lib, assemble, mesh_scripts, synthetic
+from . import assemble, mesh_scripts, synthetic
 from .mesh import Mesh
 
 TUBE_RADIUS = 0.15

@@ -19,9 +19,8 @@ tests cover it.  The reference has no counterpart: dolfinx partitions with a gra
 parallel tag transfer (src/phifem/mesh_scripts.py:264).
 """
 import torch
-import torch.distributed as dist
 
-from . import _lib, assemble, mesh_scripts
+from . import assemble, mesh_scripts
 from .mesh import Mesh
 
 
