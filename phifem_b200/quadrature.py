@@ -7,7 +7,8 @@ the same element tensors up to rounding, so the rules are chosen for point count
 
   * segments : Gauss-Legendre;
   * triangles: Dunavant's fully symmetric 12-point rule for degree <= 6 (3-, 6-, 7-point rules below that);
-  * tetrahedra: Keast's fully symmetric 24-point rule for degree <= 6 (4-, 14-point rules below that);
+  * tetrahedra: Keast's fully symmetric 24-point rule for degree 6, Walkington's 14-point rule for degrees 3-5 (1- and
+    4-point rules below that);
   * anything else: collapsed (Stroud conical product) Gauss-Jacobi rules of the required order.
 
 Every rule is checked against the exact monomial integrals at import of its first use; the orbit parameters
@@ -95,6 +96,9 @@ _SYMMETRIC = {
              ("s111", 0.082851075618374, (0.053145049844817, 0.310352451033784))],
     (3, 1): [("c", 1.0, ())],
     (3, 2): [("s31", 0.25, (0.138196601125011,))],
+    # Walkington's 14-point rule, degree 5, positive weights
+    (3, 5): [("s31", 0.112687925718016, (0.310885919263301,)), ("s31", 0.073493043116362, (0.092735250310891,)),
+             ("s22", 0.042546020777081, (0.045503704125650,))],
     (3, 6): [("s31", 0.039922750258168, (0.214602871259152,)), ("s31", 0.010077211055321, (0.040673958534611,)),
              ("s31", 0.055357181543654, (0.322337890142276,)),
              ("s211", 0.048214285714286, (0.063661001875018, 0.603005664791649))],
@@ -111,6 +115,8 @@ def _expand(d, orbits):
             base = (a,) * d + (1.0 - d * a,)
         elif kind == "s111":
             base = (par[0], par[1], 1.0 - par[0] - par[1])
+        elif kind == "s22":
+            base = (par[0], par[0], 0.5 - par[0], 0.5 - par[0])
         elif kind == "s211":
             base = (par[0], par[0], par[1], 1.0 - 2.0 * par[0] - par[1])
         else:
