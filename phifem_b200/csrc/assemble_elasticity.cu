@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(kBlockEl) k_elasticity_uncut(
 }
 
 template <int D, int KP>
-__global__ void __launch_bounds__(kBlockEl) k_elasticity_cells(
+__global__ void __launch_bounds__(kBlockEl, 3) k_elasticity_cells(
     phifem_mesh m, phifem_pk_space sp, const double* __restrict__ qlam_g, const double* __restrict__ qw_g, int nq,
     const double* __restrict__ phi, const double* __restrict__ f, const int32_t* __restrict__ cut_cells,
     int64_t n_cut, const int32_t* __restrict__ vptr, const int32_t* __restrict__ pos_cells,
