@@ -415,6 +415,13 @@ int phifem_assemble_elasticity_boundary(const phifem_mesh* mesh, const int32_t* 
  * is 1, b <- b - A g on the free rows, b = g on the marked ones.  bc_marker int8 [n_rows], bc_values [n_rows]. */
 int phifem_apply_dirichlet(int64_t n_rows, const int32_t* indptr, const int32_t* indices, const int8_t* bc_marker,
                            const double* bc_values, double* data, double* b, void* stream);
+/* The same for a structurally symmetric pattern (one space for trial and test functions: every operator here), driven
+ * by the list bc_dofs[n_bc] of the marked dofs: the mirrored entry (j, c) of every entry (c, j) of a marked row is found by
+ * binary search, so the work is the marked rows' lengths instead of a pass over the matrix.  The lifting adds into b
+ * with fp64 reductions (order not fixed). */
+int phifem_apply_dirichlet_symmetric(int64_t n_rows, const int32_t* indptr, const int32_t* indices,
+                                     const int32_t* bc_dofs, int64_t n_bc, const int8_t* bc_marker,
+                                     const double* bc_values, double* data, double* b, void* stream);
 
 /* ---- symbolic phase of the P1 strong-Dirichlet operator on the device: what dolfinx does in `create_sparsity_pattern` /
  * `create_matrix` under `assemble_matrix(form(a))` (demo/strong-dirichlet/flower/main.py:121-123).  For hosts without

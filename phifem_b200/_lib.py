@@ -130,6 +130,8 @@ _SIGNATURES = {
     "phifem_assemble_elasticity_boundary": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, ctypes.c_int64, _vp, _vp,
                                                            ctypes.c_int32, _vp, _vp]),
     "phifem_apply_dirichlet": (ctypes.c_int, [ctypes.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "phifem_apply_dirichlet_symmetric": (ctypes.c_int, [ctypes.c_int64, _vp, _vp, _vp, ctypes.c_int64, _vp, _vp, _vp,
+                                                        _vp, _vp]),
     "phifem_pattern_create_p1": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, _vp, ctypes.c_int64,
                                                 ctypes.POINTER(_vp), _vp]),
     "phifem_pattern_view_of": (ctypes.c_int, [_vp, ctypes.POINTER(CPatternView)]),

@@ -191,7 +191,7 @@ def build_plan_interface_elasticity(mesh, cells_tags, facets_tags, d_bdry, V_phi
 
 
 def assemble_interface_elasticity_into(plan, phi, f, material, gamma, sigma_s, data, b, bc_marker=None,
-                                       bc_values=None):
+                                       bc_values=None, bc_dofs=None):
     """Numeric phase on the current stream: zero `data` / `b`, cells, interface facets, one-sided entities, Dirichlet
     conditions.  All arguments are device tensors; nothing synchronises."""
     mesh = plan.mesh
@@ -215,16 +215,21 @@ def assemble_interface_elasticity_into(plan, phi, f, material, gamma, sigma_s, d
                                        (plan.entities_out, plan.pos_entities_out))):
         _lib.check(lib.phifem_assemble_elasticity_boundary(cm, p(ent), ent.shape[0], p(plan.vptr), p(pos), side,
                                                            p(data), st))
-    if bc_marker is not None:
+    if bc_marker is not None and bc_dofs is not None:   # the pattern is structurally symmetric: list-driven variant
+        _lib.check(lib.phifem_apply_dirichlet_symmetric(plan.n_rows, p(plan.indptr), p(plan.indices), p(bc_dofs),
+                                                        bc_dofs.numel(), p(bc_marker), p(bc_values), p(data), p(b), st))
+    elif bc_marker is not None:
         _lib.check(lib.phifem_apply_dirichlet(plan.n_rows, p(plan.indptr), p(plan.indices), p(bc_marker),
                                               p(bc_values), p(data), p(b), st))
     return data, b
 
 
-def assemble_interface_elasticity(plan, phi_h, f_h, material=None, pen_coef=1.0, stab_coef=1.0, bcs=None):
+def assemble_interface_elasticity(plan, phi_h, f_h, material=None, pen_coef=1.0, stab_coef=1.0, bcs=None,
+                                  symmetric_bc=False):
     """A (CSR over the mixed dofs) and b of main.py:227-275.  `f_h`: P1 vector field [Nv, d] (the demo's `f` is a UFL
     expression, :150; here its nodal interpolant).  `bcs` = (dofs, values): Dirichlet conditions as dolfinx applies them
-    (assemble_matrix(bcs=) zeroes rows / columns and sets the diagonal to 1, apply_lifting, bc.set)."""
+    (assemble_matrix(bcs=) zeroes rows / columns and sets the diagonal to 1, apply_lifting, bc.set).  symmetric_bc: use
+    the list-driven pass, whose work is the constrained rows' lengths (small-system parity only so far)."""
     mesh = plan.mesh
     _lib.require_cuda(mesh)
     material = material or Material()
@@ -233,7 +238,7 @@ def assemble_interface_elasticity(plan, phi_h, f_h, material=None, pen_coef=1.0,
     f = f.to(mesh.device, dtype=torch.float64).contiguous()
     if tuple(f.shape) != (mesh.num_vertices, mesh.gdim):
         raise ValueError("f_h must hold one vector per vertex: expected shape (%d, %d)" % (mesh.num_vertices, mesh.gdim))
-    marker = values = None
+    marker = values = bc_list = None
     if bcs is not None:
         dofs = torch.as_tensor(bcs[0], device=mesh.device).reshape(-1).long()
         vals = torch.as_tensor(bcs[1], device=mesh.device, dtype=torch.float64).reshape(-1)
@@ -243,6 +248,8 @@ def assemble_interface_elasticity(plan, phi_h, f_h, material=None, pen_coef=1.0,
         values = torch.zeros(plan.n_rows, dtype=torch.float64, device=mesh.device)
         marker[dofs] = 1
         values[dofs] = vals
+        if symmetric_bc:   # list-driven Dirichlet pass (phifem_apply_dirichlet_symmetric) instead of the full-matrix one
+            bc_list = torch.unique(dofs).to(torch.int32).contiguous()
     data, b = plan.new_outputs()
-    assemble_interface_elasticity_into(plan, phi, f, material, pen_coef, stab_coef, data, b, marker, values)
+    assemble_interface_elasticity_into(plan, phi, f, material, pen_coef, stab_coef, data, b, marker, values, bc_list)
     return CSRMatrix(plan.indptr, plan.indices, data, (plan.n_rows, plan.n_rows)), b

@@ -53,6 +53,11 @@ def test_elasticity_operator_matches_oracle(kind, n, kphi, with_bc):
         bcs = (bc_dofs, bc_vals)
         bc_dofs, bc_vals = bc_dofs.cpu().numpy(), bc_vals.cpu().numpy()
     A, b = elasticity.assemble_interface_elasticity(plan, phi, f, mat, pen_coef=1.3, stab_coef=0.7, bcs=bcs)
+    if with_bc:   # the list-driven Dirichlet pass gives the same system (its lifting sums in another order)
+        A2, b2 = elasticity.assemble_interface_elasticity(plan, phi, f, mat, pen_coef=1.3, stab_coef=0.7, bcs=bcs,
+                                                          symmetric_bc=True)
+        assert torch.allclose(A2.data, A.data, rtol=0, atol=1e-13 * float(A.data.abs().max()))
+        assert torch.allclose(b2, b, rtol=0, atol=1e-12 * float(b.abs().max()))
     assert A.shape[0] == plan.nb * mesh.num_vertices
     omat = OE.Material(1.0, 0.3, 0.05, 0.27)
     ip, ix, data, bo = OE.assemble_interface_elasticity(

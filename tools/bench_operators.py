@@ -23,6 +23,9 @@ from phifem_b200 import assemble, assemble_pk, elasticity, fem, mesh_scripts, sy
 from phifem_b200.mesh import Measure, MeshTags  # noqa: E402
 
 
+SYMMETRIC_BC = False   # --symmetric-bc: the list-driven Dirichlet pass (phifem_apply_dirichlet_symmetric)
+
+
 def _tags(mesh, phi):
     dls = mesh_scripts._DeviceLevelset(mesh, fem.Function(fem.functionspace_p1_device(mesh), phi), 1)
     ws = mesh_scripts.TagWorkspace(mesh)
@@ -83,10 +86,12 @@ def run(op, steps, warmup):
         bv = plan.boundary_vertices()
         marker = torch.zeros(plan.n_rows, dtype=torch.int8, device=dev)
         values = torch.zeros(plan.n_rows, dtype=torch.float64, device=dev)
-        marker[plan.dofs("u_in", bv).reshape(-1)] = 1
+        bc_dofs = plan.dofs("u_in", bv).reshape(-1)
+        marker[bc_dofs] = 1
+        bc_list = bc_dofs.to(torch.int32).contiguous() if SYMMETRIC_BC else None
         data, b = plan.new_outputs()
         asm = lambda: elasticity.assemble_interface_elasticity_into(plan, phi, f, mat, 1.0, 1.0, data, b,   # noqa: E731
-                                                                   marker, values)
+                                                                   marker, values, bc_list)
     torch.cuda.synchronize()
     t2 = time.perf_counter()
 
@@ -119,7 +124,9 @@ if __name__ == "__main__":
     ap.add_argument("--ops", default="neumann,elasticity-2d,elasticity-3d")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--symmetric-bc", action="store_true")
     a = ap.parse_args()
+    SYMMETRIC_BC = a.symmetric_bc
     for name in a.ops.split(","):
         run(name, a.steps, a.warmup)
         torch.cuda.empty_cache()
