@@ -52,6 +52,14 @@ def test_elasticity_closed_form_equals_quadrature(kind, n):
         r = M @ t
         rows = o.nb * np.nonzero(interior_v)[0][:, None] + np.arange(2 * d)[None, :]
         assert np.abs(r[rows]).max() <= 1e-12 * abs(M).max()
+        # ... and so are the infinitesimal rotations (zero strain): u = (-y, x) in 2D, rotations about the axes in 3D
+        pairs = [(0, 1)] if d == 2 else [(0, 1), (0, 2), (1, 2)]
+        for (a_, b_) in pairs:
+            t = np.zeros(nrows)
+            t[o.nb * np.arange(len(x)) + o.ui + a_] = -x[:, b_]
+            t[o.nb * np.arange(len(x)) + o.ui + b_] = x[:, a_]
+            r = M @ t
+            assert np.abs(r[rows]).max() <= 1e-12 * abs(M).max() * np.abs(x).max()
     # p only lives on cut cells: rows of p at vertices without a cut cell are empty of values
     cutv = np.zeros(len(x), dtype=bool)
     cutv[np.unique(cells[out["cell_tags"] == 2])] = True
