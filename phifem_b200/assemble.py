@@ -132,10 +132,11 @@ class AssemblyPlan:
 
 def _plan_inputs(mesh, cells_tags, facets_tags, ds):
     """int8 tag arrays and the [m, 2] entity list of `ds` on the mesh's device."""
+    from .mesh_scripts import _narrow_tags   # values outside 0..6 (user tags) must not wrap into 1..6
     c8 = getattr(cells_tags, "tags8", None)
-    c8 = c8 if c8 is not None else cells_tags.values_dev.to(torch.int8)
+    c8 = c8 if c8 is not None else _narrow_tags(cells_tags.values_dev)
     f8 = getattr(facets_tags, "tags8", None)
-    f8 = f8 if f8 is not None else facets_tags.values_dev.to(torch.int8)
+    f8 = f8 if f8 is not None else _narrow_tags(facets_tags.values_dev)
     if ds is None:
         ents = torch.zeros(0, dtype=torch.int32, device=mesh.device)
     elif isinstance(ds, Measure) and ds.subdomain_data is None:

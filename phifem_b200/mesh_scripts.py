@@ -199,6 +199,15 @@ def _integration_entities_dev(mesh, cell_tags8, facet_tags8, facet_tag, cell_tag
     return ents[:n.value].reshape(-1).contiguous()
 
 
+def _narrow_tags(values_dev):
+    """One-byte copy of dense int32 tags for the kernels.  The kernels and the plans only ever compare with the
+    computed values 1..6; a user tag of `overwrite_tags` may be any other integer (reference :606-615 reserves only
+    1..6 / 100 / 101), and a plain int8 cast would wrap 257 -> 1, 260 -> 4: everything outside 0..6 becomes 0
+    ("matches nothing"), exactly as `find(4)` of the reference does not match 260."""
+    v = values_dev
+    return torch.where((v >= 0) & (v <= 6), v, torch.zeros_like(v)).to(torch.int8).contiguous()
+
+
 def _tags_from_workspace(mesh, ws):
     tdim = mesh.topology.dim
     return (MeshTags(mesh, tdim, ws.cell_tags32, tags8=ws.cell_tags8),
@@ -266,13 +275,13 @@ def compute_tags_measures(mesh, discrete_levelset, detection_degree, box_mode=Fa
         if np.any(np.isin([1, 2, 3], ow.values)):
             raise ValueError("Cannot overwrite cells tags with values 1, 2 or 3.")
         cells_tags = _overwrite_tags(mesh, cells_tags, ow)
-        cell_tags8 = cells_tags.values_dev.to(torch.int8)
+        cell_tags8 = _narrow_tags(cells_tags.values_dev)
     if "facets" in overwrite_tags.keys():         # :611-615
         ow = overwrite_tags["facets"]
         if np.any(np.isin([1, 2, 3, 4, 5, 6, 100, 101], ow.values)):
             raise ValueError("Cannot overwrite facets tags with values 1, 2, 3, 4, 5, 6, 100 or 101.")
         facets_tags = _overwrite_tags(mesh, facets_tags, ow)
-        facet_tags8 = facets_tags.values_dev.to(torch.int8)
+        facet_tags8 = _narrow_tags(facets_tags.values_dev)
 
     if box_mode:                                   # :617-634
         ents_out = _integration_entities_dev(mesh, cell_tags8, facet_tags8, 4, (1, 2))
@@ -316,7 +325,7 @@ def _tag_facets(mesh, cells_tags, discrete_levelset, detection_degree):
     _lib.require_cuda(mesh)
     dls = _DeviceLevelset(mesh, discrete_levelset, detection_degree)
     ws = TagWorkspace(mesh)
-    ws.cell_tags8 = cells_tags.values_dev.to(torch.int8).contiguous()
+    ws.cell_tags8 = _narrow_tags(cells_tags.values_dev).contiguous()
     ws.counters[_lib.CNT_EXTERIOR] = int((ws.cell_tags8 == 3).sum())
     _lib.check(_lib.load().phifem_tag_facets(_lib.c_mesh(mesh), dls.c, _lib.ptr(ws.cell_tags8),
                                              _lib.ptr(ws.facet_tags32), _lib.ptr(ws.facet_tags8),

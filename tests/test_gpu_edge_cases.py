@@ -121,3 +121,35 @@ def test_no_active_cell_quadrature_and_mixed_operators():
     planw = assemble.build_plan_weak_dirichlet(mesh, ctags, ftags, ds(100), V=V)
     Aw, bw = assemble.assemble_weak_dirichlet(planw, phi, f)
     assert planw.nnz == 0 and Aw.shape == (2 * V.num_dofs, 2 * V.num_dofs) and float(bw.abs().max()) == 0.0
+
+
+def test_overwrite_values_beyond_int8_match_nothing():
+    """A facet tagged 260 must not be picked up as Gamma_h (4) by the ds(100) search, a cell tagged 257 / 258 must leave
+    Omega_h (reference :606-615 allows any value but 1..6 / 100 / 101; `find(4)` / `find(1)` do not match them)."""
+    from phifem_b200.mesh import MeshTags
+    mesh = synthetic.unstructured_variant(synthetic.rectangle_mesh(14, device="cuda"), seed=5)
+    phi = synthetic.sphere_levelset(mesh.x, center=(0.03, -0.02), radius=0.55)
+    ctags, ftags, _, ds, _ = _run(mesh, phi)
+    x, cells, ph, out = _oracle(mesh, phi)
+    g_facets = np.nonzero(out["facet_tags"] == 4)[0][::2]
+    in_cells, cut_cells = np.nonzero(out["cell_tags"] == 1)[0][::3], np.nonzero(out["cell_tags"] == 2)[0][::2]
+    assert len(g_facets) and len(in_cells) and len(cut_cells)
+    oc = MeshTags.from_lists(mesh, 2, np.concatenate([in_cells, cut_cells]),
+                             np.concatenate([np.full(len(in_cells), 257), np.full(len(cut_cells), 258)]))
+    of = MeshTags.from_lists(mesh, 1, g_facets, np.full(len(g_facets), 260))
+    fn = fem.Function(fem.functionspace(mesh, 1), phi.cpu().numpy())
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        c2, f2, _, ds2, _ = mesh_scripts.compute_tags_measures(mesh, fn, 1, box_mode=True,
+                                                               overwrite_tags={"cells": oc, "facets": of})
+        s2 = mesh_scripts.compute_tags_measures(mesh, fn, 1, box_mode=False, overwrite_tags={"cells": oc, "facets": of})
+    ct_o, ft_o = out["cell_tags"].copy(), out["facet_tags"].copy()
+    ct_o[in_cells], ct_o[cut_cells], ft_o[g_facets] = 257, 258, 260
+    assert np.array_equal(c2.values_dev.cpu().numpy(), ct_o) and np.array_equal(f2.values_dev.cpu().numpy(), ft_o)
+    want100 = OT.integration_entities(out["c2f"], out["f2c"], (ct_o == 1) | (ct_o == 2), ft_o == 4)
+    want101 = OT.integration_entities(out["c2f"], out["f2c"], (ct_o == 2) | (ct_o == 3), ft_o == 3)
+    assert np.array_equal(ds2(100).integration_entities, want100)
+    assert np.array_equal(ds2(101).integration_entities, want101)
+    assert np.array_equal(s2[4][0], np.nonzero((ct_o == 1) | (ct_o == 2))[0])      # submesh = cells still tagged 1 / 2
+    plan = assemble.build_plan(mesh, c2, f2, ds2(100))
+    assert np.array_equal(np.sort(plan.active.cpu().numpy()), np.nonzero((ct_o == 1) | (ct_o == 2))[0])

@@ -118,3 +118,13 @@ def test_lagrange_spaces_partition_of_unity_and_interpolation():
     for k in (1, 2, 3):
         V = fem.functionspace(m3, k)
         assert V.element.ndofs == {1: 4, 2: 10, 3: 20}[k]
+
+
+def test_user_tags_outside_int8_do_not_wrap_into_computed_values():
+    """`overwrite_tags` values are free apart from 1..6 / 100 / 101 (reference src/phifem/mesh_scripts.py:606-615);
+    the one-byte arrays the kernels read must not alias 257 -> 1, 260 -> 4, 200 -> -56."""
+    v = torch.tensor([0, 1, 2, 3, 4, 5, 6, 7, 100, 127, 128, 200, 255, 256, 257, 258, 260, 262, -1, 65540],
+                     dtype=torch.int32)
+    t8 = mesh_scripts._narrow_tags(v)
+    assert t8.dtype == torch.int8
+    assert t8.tolist() == [0, 1, 2, 3, 4, 5, 6] + [0] * 13
