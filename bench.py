@@ -214,6 +214,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.n
+    reorder_ms = None
     t_setup = time.perf_counter()
     if world > 1:
         from phifem_b200 import dist as pdist
@@ -227,6 +228,17 @@ def run_ours(args):
         else:
             mesh = synthetic.box_mesh(n, device=dev)
             ls_kw = {}
+        if args.mesh == "unstructured":
+            # vertex jitter +-0.2 h (seed 0), random cell permutation (seed 1), random vertex
+            # relabelling (seed 2); then -- as part of the mesh-level symbolic phase, like dolfinx's own reordering at
+            # mesh creation -- renumbered along the Morton curve.  Level set and source are interpolated on THAT mesh.
+            mesh = synthetic.unstructured_variant_device(mesh, jitter=0.2, seed=0)
+            torch.cuda.synchronize()
+            t_re = time.perf_counter()
+            if not args.no_reorder:
+                mesh = mesh.reordered()
+            torch.cuda.synchronize()
+            reorder_ms = (time.perf_counter() - t_re) * 1e3
         phi = synthetic.sphere_levelset(mesh.x, **ls_kw)
         f = synthetic.ball_source(mesh.x, **({"center": DISC_CENTER} if ls_kw else {}))
     mesh.c2f  # build the facet topology (mesh-level symbolic, once per mesh)
@@ -276,7 +288,8 @@ def run_ours(args):
             plan = assemble.build_plan(mesh, ctags, ftags, ents, V=Vw, V_phi=Vw)
         else:
             plan = assemble.build_plan(mesh, ctags, ftags, ents, method=args.scatter, capacity=args.capacity,
-                                       order=args.order, geometry=args.geometry)
+                                       order=args.order, geometry=args.geometry, cell_pass=args.cell_pass,
+                                       rows_per_tile=args.rows_per_tile)
         data, b = plan.new_outputs()
     torch.cuda.synchronize()
     symbolic_ms = (time.perf_counter() - t0) * 1e3
@@ -402,10 +415,14 @@ def run_ours(args):
         # count of cell_row<3>) against 64 fp64 lanes per clock per SM
         # from the coordinates; 85 with the cached cell geometry (cell_row_geom<3>, cut-only instructions excluded)
         per_record = 85 if plan.rowsplan.cell_geom is not None else 146
-        lanes = plan.rowsplan.cells.n_records * float(per_record)
+        tiles = plan.rowsplan.tiles
+        if tiles is not None:   # cell-once pass: ~200 fp64 instructions per cell evaluation (SASS of cell_tensor<3>)
+            per_record = 200
+        n_eval = tiles.n_cell_slots if tiles is not None else plan.rowsplan.cells.n_records
+        lanes = n_eval * float(per_record)
         peak_lanes = 148 * 64 * (clocks["sm_max_mhz"] or 1965) * 1e6
-        roofline["fp64_issue"] = {"kernel": "k_assemble_rows_p1<cells>", "fp64_instructions_per_record": per_record,
-                                  "records": plan.rowsplan.cells.n_records,
+        roofline["fp64_issue"] = {"kernel": "k_assemble_tiles_p1" if tiles is not None else "k_assemble_rows_p1<cells>",
+                                  "fp64_instructions_per_record": per_record, "records": n_eval,
                                   "achieved_tera_lane_instr_per_s": lanes / (per["assemble_cells"] * 1e-3) / 1e12,
                                   "peak_tera_lane_instr_per_s": peak_lanes / 1e12,
                                   "frac": lanes / (per["assemble_cells"] * 1e-3) / peak_lanes}
@@ -547,7 +564,10 @@ def run_ours(args):
                 "config": {"workload": (CONFIGS[args.config][1] + "%s, tags + strong-Dirichlet CSR assembly")
                                        % (n_cells_local, n, " per unit cube joined by a thin tube across the "
                                           "partition boundaries" if world > 1 else ""),
-                           "name": args.config,
+                           "name": args.config, "mesh": args.mesh + (
+                               "" if args.mesh == "structured" else
+                               (": jitter 0.2 h, cells permuted, vertices relabelled" +
+                                (", NOT renumbered" if args.no_reorder else ", renumbered along the Morton curve"))),
                            "cells_total": n_cells_total, "counts": counts,
                            "l2_policy": "inputs larger than L2 (%.1f GB streamed per step)"
                                         % (ab["total"] / 1e9),
@@ -562,16 +582,23 @@ def run_ours(args):
                                     "the assemble_* split from an untimed pass-by-pass loop"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
                 "gpu_launches": {"rows": 7, "blocked": 5, "atomic": 7, "pk-atomic": 9}[plan.method] * args.steps,
-                "symbolic_ms": symbolic_ms, "topology_s": topo_s,
+                "symbolic_ms": symbolic_ms, "topology_s": topo_s, "reorder_ms": reorder_ms,
                 "scatter": {"method": plan.method,
                             **({"blocks": plan.blocked.n_blocks, "capacity": plan.blocked.capacity,
                                 "bin_shape": plan.blocked.bin_shape,
                                 "recompute_factor": plan.blocked.redundancy,
                                 "plan_bytes": plan.blocked.index_bytes()} if plan.blocked else {}),
                             **({"order": plan.rowsplan.order, "max_row_nnz": plan.rowsplan.max_row_nnz,
-                                "rows_cells_surface": [plan.rowsplan.cells.n_listed,
+                                "cell_pass": plan.rowsplan.cell_pass,
+                                **({"rows_per_tile": plan.rowsplan.tiles.rows_per_tile,
+                                    "tiles": plan.rowsplan.tiles.n_tiles, "chunks": plan.rowsplan.tiles.n_chunks,
+                                    "cell_evaluations": plan.rowsplan.tiles.n_cell_slots,
+                                    "recompute_factor": plan.rowsplan.tiles.recompute}
+                                   if plan.rowsplan.tiles is not None else {}),
+                                "rows_cells_surface": [plan.rowsplan.tiles.n_listed if plan.rowsplan.tiles is not None
+                                                       else plan.rowsplan.cells.n_listed,
                                                        plan.rowsplan.surface.n_listed],
-                                "records_cells_ghost_onesided": [plan.rowsplan.cells.n_records,
+                                "records_cells_ghost_onesided": [plan.rowsplan.n_cell_records,
                                                                  plan.rowsplan.n_ghost_records,
                                                                  plan.rowsplan.n_entity_records],
                                 "lane_padding": [plan.rowsplan.cells.padding(), plan.rowsplan.surface.padding()],
@@ -619,7 +646,14 @@ def main():
     ap.add_argument("--scatter", default="rows", choices=["rows", "blocked", "atomic"],
                     help="assembly strategy (row-gather / owner-computes blocks / fp64 reductions)")
     ap.add_argument("--capacity", type=int, default=None, help="contributions per block (blocked scatter)")
-    ap.add_argument("--order", default="natural", choices=["natural", "morton"],
+    ap.add_argument("--mesh", default="structured", choices=["structured", "unstructured"],
+                    help="unstructured = SURVEY.md 8(d)'s variant (jitter, cell permutation, vertex relabelling), "
+                         "renumbered along the Morton curve in the mesh-level symbolic phase")
+    ap.add_argument("--no-reorder", action="store_true", help="unstructured mesh left in its random numbering")
+    ap.add_argument("--cell-pass", default="rows", choices=["rows", "tiles"],
+                    help="row-gather cell pass / cell-once tile pass (csrc/assemble_tiles.cu)")
+    ap.add_argument("--rows-per-tile", type=int, default=256, choices=[128, 256])
+    ap.add_argument("--order", default="auto", choices=["auto", "natural", "morton"],
                     help="row processing order of the row-gather assembly")
     ap.add_argument("--e2e-pipeline", action="store_true",
                     help="also measure e2e with two steps in flight (uploads and kernels of step i + 1 under the "

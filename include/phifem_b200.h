@@ -230,6 +230,31 @@ typedef struct phifem_row_list {
   const uint32_t* rec;         /* records, see phifem_rows_plan */
 } phifem_row_list;
 
+/* Cell-once form of the cell pass (csrc/assemble_tiles.cu).  The row-gather pass evaluates a cell once per vertex
+ * (the cofactors, the determinant and its reciprocal four times per tetrahedron); here a CTA owns a TILE of
+ * `rows_per_tile` consecutive listed rows, evaluates every cell touching the tile ONCE (the whole element tensor),
+ * parks the tensors of `rows_per_tile` cells (a CHUNK, one cell per thread) in shared memory and lets the thread of
+ * each row pull its own entries -- in a fixed order, without atomics.  A cell touching several tiles is evaluated
+ * once per tile (recompute factor ~1.6 for 256 spatially compact rows of a tetrahedral mesh instead of 4).
+ *   slot q = chunk * rows_per_tile + lane holds one cell: slot_verts[q] = its vertex ids (cell-local order; v[0] < 0
+ *   marks an empty slot, bit 31 of v[1] the cut cells; triangles leave v[3] unused).  The cells of a tile appear in
+ *   ascending cell index, so every row sums its cells in mesh order whatever the tiling.
+ *   Row l of the tile pulls, in chunk c, the records rec[rec_base[c] + rec_off[c][l] .. rec_base[c] + rec_off[c][l+1]):
+ *   word = slot lane (bits 0-7) | cell-local index of the row's vertex (bits 8-9) | positions, inside the row's
+ *   column list, of the cell's other vertices in ascending cell-local order (7 bits each from bit 10). */
+typedef struct phifem_cell_tiles {
+  int32_t rows_per_tile;       /* 128 or 256 (= threads per CTA = cells per chunk) */
+  int32_t n_tiles;
+  int64_t n_listed;            /* listed rows; tile t owns rows[t * rows_per_tile ...] */
+  const int32_t* rows;         /* [n_listed] row (= vertex) ids in processing order */
+  const uint8_t* diag_pos;     /* [n_listed] position of the diagonal entry inside the row */
+  const int32_t* chunk_ptr;    /* [n_tiles + 1] chunks of tile t = [chunk_ptr[t], chunk_ptr[t + 1]) */
+  const int32_t* slot_verts;   /* [n_chunks * rows_per_tile, 4] (16-byte aligned) */
+  const int32_t* rec_base;     /* [n_chunks + 1] */
+  const uint16_t* rec_off;     /* [n_chunks, rows_per_tile + 1] */
+  const uint32_t* rec;         /* [rec_base[n_chunks]] */
+} phifem_cell_tiles;
+
 typedef struct phifem_rows_plan {
   const int32_t* indptr;       /* [n_rows + 1] CSR row pointers */
   const int32_t* indices;      /* [nnz] CSR column indices */
@@ -262,6 +287,9 @@ typedef struct phifem_rows_plan {
    * above plus (cell-local index of the row's vertex) << 25, word 1 = the cell's index in this table; the other vertices
    * of word 0 are in ascending cell-local order. */
   const double* cell_geom;
+  /* Optional cell-once form of the cell pass (NULL: the row list `cells` above is walked).  When set, `cells` may be
+   * empty; the rows of tiles->rows are written (data and b) exactly as the row-gather cell pass writes its rows. */
+  const phifem_cell_tiles* tiles;
 } phifem_rows_plan;
 
 /* Same operator as phifem_assemble_{cells,boundary,ghost}_p1: the facet-once kernel (forked onto an internal side

@@ -48,11 +48,18 @@ class CRowList(ctypes.Structure):
     _fields_ = [("n_listed", ctypes.c_int64), ("rows", _vp), ("diag_pos", _vp), ("ptr", _vp), ("rec", _vp)]
 
 
+class CCellTiles(ctypes.Structure):
+    _fields_ = [("rows_per_tile", ctypes.c_int32), ("n_tiles", ctypes.c_int32), ("n_listed", ctypes.c_int64),
+                ("rows", _vp), ("diag_pos", _vp), ("chunk_ptr", _vp), ("slot_verts", _vp), ("rec_base", _vp),
+                ("rec_off", _vp), ("rec", _vp)]
+
+
 class CRowsPlan(ctypes.Structure):
     _fields_ = [("indptr", _vp), ("indices", _vp), ("max_row_nnz", ctypes.c_int32),
                 ("reserved", ctypes.c_int32), ("cells", CRowList), ("surface", CRowList),
                 ("n_ghost_facets", ctypes.c_int64), ("ghost_macro", _vp), ("n_entities", ctypes.c_int64),
-                ("entity_macro", _vp), ("surface_work", _vp), ("cell_geom", _vp)]
+                ("entity_macro", _vp), ("surface_work", _vp), ("cell_geom", _vp),
+                ("tiles", ctypes.POINTER(CCellTiles))]
 
 
 class CPkSpace(ctypes.Structure):

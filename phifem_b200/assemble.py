@@ -64,7 +64,7 @@ class AssemblyPlan:
     shared-memory block can hold."""
 
     def __init__(self, mesh, cell_tags8, facet_tags8, entities, method="rows", capacity=None,
-                 order="natural", row_mask=None, geometry=False):
+                 order="auto", row_mask=None, geometry=False, cell_pass="rows", rows_per_tile=256):
         if mesh.cell_type not in ("triangle", "tetrahedron"):
             raise NotImplementedError("P1 assembly supports triangles and tetrahedra")
         dev = mesh.device
@@ -110,7 +110,8 @@ class AssemblyPlan:
         if method == "rows" and self.nnz > 0:
             from . import rows as rows_mod
             try:
-                self.rowsplan = rows_mod.RowsPlan(self, order=order, row_mask=row_mask, geometry=geometry)
+                self.rowsplan = rows_mod.RowsPlan(self, order=order, row_mask=row_mask, geometry=geometry,
+                                                  cell_pass=cell_pass, rows_per_tile=rows_per_tile)
                 self.method = "rows"
             except NotImplementedError:
                 self.rowsplan = None
@@ -155,13 +156,14 @@ def _plan_inputs(mesh, cells_tags, facets_tags, ds):
     return c8.contiguous(), f8.contiguous(), ents
 
 
-def build_plan(mesh, cells_tags, facets_tags, ds=None, method="rows", capacity=None, order="natural",
-               V=None, V_phi=None, geometry=False):
+def build_plan(mesh, cells_tags, facets_tags, ds=None, method="rows", capacity=None, order="auto",
+               V=None, V_phi=None, geometry=False, cell_pass="rows", rows_per_tile=256):
     """Symbolic phase for `a` and `L` of the strong-Dirichlet demo.  `ds` is what the demo passes as
     `ds_bdy(100)` (main.py:64): a MeasureRestriction, a flat entity array, or None (no boundary term).
     `V` / `V_phi`: the demo's `primal_space` / `levelset_space` (main.py:74-75); omitted or both of degree 1
     => the closed-form P1 kernels, otherwise the quadrature kernels for P1 / P2 (phifem_b200/assemble_pk.py).
-    geometry (row-gather plans): tabulate the cells' geometry factors once per plan (phifem_b200/rows.py; an
+    cell_pass (row-gather plans): "rows" = one evaluation per (row, cell) record, "tiles" = the cell-once pass of
+    csrc/assemble_tiles.cu.  geometry (row-gather plans): tabulate the cells' geometry factors once per plan (phifem_b200/rows.py; an
     option kept for the record, slower than the default on the B200)."""
     c8, f8, ents = _plan_inputs(mesh, cells_tags, facets_tags, ds)
     V_phi = V if V_phi is None else V_phi
@@ -170,7 +172,7 @@ def build_plan(mesh, cells_tags, facets_tags, ds=None, method="rows", capacity=N
         from .assemble_pk import PkAssemblyPlan
         return PkAssemblyPlan(mesh, c8, f8, ents, V, V_phi)
     return AssemblyPlan(mesh, c8, f8, ents, method=method, capacity=capacity,
-                        order=order, geometry=geometry)
+                        order=order, geometry=geometry, cell_pass=cell_pass, rows_per_tile=rows_per_tile)
 
 
 def _device_vector(mesh, v, space=None):

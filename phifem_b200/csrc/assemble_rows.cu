@@ -14,6 +14,7 @@
 // Connectivity comes from the CSR pattern itself: a record holds the positions inside row r's column
 // list of the entity's other vertices, so `indices[start + pos]` names them (include/phifem_b200.h).
 #include "common.cuh"
+#include "p1_forms.cuh"
 
 namespace phifem {
 namespace {
@@ -23,107 +24,6 @@ constexpr int kRowsBlock = 128;
 #define PHIFEM_ROWS_MINBLOCKS 4
 #endif
 constexpr uint32_t kPad = 0xffffffffu;
-
-template <int D>
-__device__ __forceinline__ double dot(const double (&a)[D], const double (&b)[D]) {
-  double s = a[0] * b[0];
-#pragma unroll
-  for (int d = 1; d < D; ++d) s += a[d] * b[d];
-  return s;
-}
-
-// gradients of the barycentric coordinates of the simplex X[0..D], det of the edge matrix
-template <int D>
-__device__ __forceinline__ void simplex_gradients(const double (&X)[D + 1][D], double (&G)[D + 1][D],
-                                                  double& det) {
-  double e[D][D];
-#pragma unroll
-  for (int k = 0; k < D; ++k)
-#pragma unroll
-    for (int d = 0; d < D; ++d) e[k][d] = X[k + 1][d] - X[0][d];
-  if constexpr (D == 2) {
-    det = e[0][0] * e[1][1] - e[1][0] * e[0][1];
-    const double inv = 1.0 / det;
-    G[1][0] = e[1][1] * inv;  G[1][1] = -e[1][0] * inv;
-    G[2][0] = -e[0][1] * inv; G[2][1] = e[0][0] * inv;
-  } else {
-    const double r1[3] = {e[1][1] * e[2][2] - e[1][2] * e[2][1], e[1][2] * e[2][0] - e[1][0] * e[2][2],
-                          e[1][0] * e[2][1] - e[1][1] * e[2][0]};
-    const double r2[3] = {e[2][1] * e[0][2] - e[2][2] * e[0][1], e[2][2] * e[0][0] - e[2][0] * e[0][2],
-                          e[2][0] * e[0][1] - e[2][1] * e[0][0]};
-    const double r3[3] = {e[0][1] * e[1][2] - e[0][2] * e[1][1], e[0][2] * e[1][0] - e[0][0] * e[1][2],
-                          e[0][0] * e[1][1] - e[0][1] * e[1][0]};
-    det = e[0][0] * r1[0] + e[0][1] * r1[1] + e[0][2] * r1[2];
-    const double inv = 1.0 / det;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      G[1][d] = r1[d] * inv;
-      G[2][d] = r2[d] * inv;
-      G[3][d] = r3[d] * inv;
-    }
-  }
-#pragma unroll
-  for (int d = 0; d < D; ++d) {
-    double s = G[1][d];
-#pragma unroll
-    for (int k = 2; k <= D; ++k) s += G[k][d];
-    G[0][d] = -s;
-  }
-}
-
-template <int D>
-__device__ __forceinline__ double diameter2(const double (&X)[D + 1][D]) {
-  double h2 = 0.0;  // CellDiameter^2 = max squared vertex distance (main.py:100)
-#pragma unroll
-  for (int a = 0; a <= D; ++a)
-#pragma unroll
-    for (int b = a + 1; b <= D; ++b) {
-      double s = 0.0;
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        const double t = X[a][d] - X[b][d];
-        s += t * t;
-      }
-      h2 = fmax(h2, s);
-    }
-  return h2;
-}
-
-template <int D> constexpr double volume_factor() { return D == 2 ? 0.5 : 1.0 / 6.0; }
-
-// Unnormalised gradients: R[k] = det * grad(lambda_k) (cofactors of the edge matrix), edges from X[0].
-template <int D>
-__device__ __forceinline__ void simplex_cofactors(const double (&X)[D + 1][D], double (&R)[D + 1][D],
-                                                  double& det) {
-  double e[D][D];
-#pragma unroll
-  for (int k = 0; k < D; ++k)
-#pragma unroll
-    for (int d = 0; d < D; ++d) e[k][d] = X[k + 1][d] - X[0][d];
-  if constexpr (D == 2) {
-    R[1][0] = e[1][1];  R[1][1] = -e[1][0];
-    R[2][0] = -e[0][1]; R[2][1] = e[0][0];
-    det = e[0][0] * e[1][1] - e[1][0] * e[0][1];
-  } else {
-    R[1][0] = e[1][1] * e[2][2] - e[1][2] * e[2][1];
-    R[1][1] = e[1][2] * e[2][0] - e[1][0] * e[2][2];
-    R[1][2] = e[1][0] * e[2][1] - e[1][1] * e[2][0];
-    R[2][0] = e[2][1] * e[0][2] - e[2][2] * e[0][1];
-    R[2][1] = e[2][2] * e[0][0] - e[2][0] * e[0][2];
-    R[2][2] = e[2][0] * e[0][1] - e[2][1] * e[0][0];
-    R[3][0] = e[0][1] * e[1][2] - e[0][2] * e[1][1];
-    R[3][1] = e[0][2] * e[1][0] - e[0][0] * e[1][2];
-    R[3][2] = e[0][0] * e[1][1] - e[0][1] * e[1][0];
-    det = e[0][0] * R[1][0] + e[0][1] * R[1][1] + e[0][2] * R[1][2];
-  }
-#pragma unroll
-  for (int d = 0; d < D; ++d) {
-    double s = R[1][d];
-#pragma unroll
-    for (int k = 2; k <= D; ++k) s += R[k][d];
-    R[0][d] = -s;
-  }
-}
 
 // Row 0 of the cell tensor of simplex X (local vertex 0 = the row's vertex): dx((1,2)) stiffness,
 // dx(2) stabilisation (main.py:105,107-112) and entry 0 of the load vector (:126-128).
@@ -699,6 +599,12 @@ __global__ void __launch_bounds__(kRowsBlock, PHIFEM_ROWS_MINBLOCKS) k_assemble_
 
 using namespace phifem;
 
+namespace phifem {  // csrc/assemble_tiles.cu
+cudaError_t launch_cell_tiles_p1(const phifem_mesh* mesh, const double* phi, const double* f, double sigma,
+                                 const int32_t* indptr, const phifem_cell_tiles* tl, int max_row_nnz, double* data,
+                                 double* b, cudaStream_t st);
+}
+
 namespace {
 bool list_ok(const phifem_row_list& l) {
   return l.n_listed == 0 || (l.rows && l.diag_pos && l.ptr && l.rec);
@@ -733,7 +639,8 @@ extern "C" int phifem_assemble_rows_p1(const phifem_mesh* mesh, const double* ph
   }
   PHIFEM_CHECK_ARG(mesh->gdim == (mesh->cell_type == PHIFEM_TRIANGLE ? 2 : 3), "gdim mismatch");
   PHIFEM_CHECK_ARG(plan != nullptr, "plan is null");
-  if (plan->cells.n_listed == 0 && plan->surface.n_listed == 0) return PHIFEM_OK;
+  const phifem_cell_tiles* tiles = plan->tiles && plan->tiles->n_tiles > 0 ? plan->tiles : nullptr;
+  if (plan->cells.n_listed == 0 && plan->surface.n_listed == 0 && !tiles) return PHIFEM_OK;
   PHIFEM_CHECK_ARG(phi && f && data && b, "null pointer");
   PHIFEM_CHECK_ARG(plan->indptr && plan->indices, "CSR pattern is null");
   PHIFEM_CHECK_ARG(list_ok(plan->cells) && list_ok(plan->surface), "row list arrays are null");
@@ -757,10 +664,14 @@ extern "C" int phifem_assemble_rows_p1(const phifem_mesh* mesh, const double* ph
                                                        rl, work, data, b);
   };
   const bool geom = plan->cell_geom != nullptr;
+  auto cell_tiles = [&]() {  // cell-once form of the cell pass
+    if (err == cudaSuccess)
+      err = launch_cell_tiles_p1(mesh, phi, f, sigma, plan->indptr, tiles, plan->max_row_nnz, data, b, st);
+  };
   // The facet-once kernel (latency-bound gathers, 2 % of the work) is forked onto a side stream so that it shares
   // the SMs with the fp64-bound cell pass; the surface row pass waits for both.
   SideStream& ss = side_stream();
-  const bool fork = n_once > 0 && plan->cells.n_listed > 0 && ss.ok;
+  const bool fork = n_once > 0 && (plan->cells.n_listed > 0 || tiles) && ss.ok;
   cudaStream_t once_stream = fork ? ss.stream : st;
   auto once = [&](auto kernel) {
     if (n_once == 0) return;
@@ -775,20 +686,22 @@ extern "C" int phifem_assemble_rows_p1(const phifem_mesh* mesh, const double* ph
   };
   if (mesh->cell_type == PHIFEM_TRIANGLE) {
     once(k_surface_once_p1<2>);
-    if (geom) launch(k_assemble_rows_p1<2, kCellsGeom>, plan->cells, plan->cell_geom);
+    if (tiles) cell_tiles();
+    else if (geom) launch(k_assemble_rows_p1<2, kCellsGeom>, plan->cells, plan->cell_geom);
     else launch(k_assemble_rows_p1<2, kCells>, plan->cells, nullptr);
     if (fork) cudaStreamWaitEvent(st, ss.join, 0);
     launch(k_assemble_rows_p1<2, kSurface>, plan->surface, plan->surface_work);
   } else {
     once(k_surface_once_p1<3>);
-    if (geom) launch(k_assemble_rows_p1<3, kCellsGeom>, plan->cells, plan->cell_geom);
+    if (tiles) cell_tiles();
+    else if (geom) launch(k_assemble_rows_p1<3, kCellsGeom>, plan->cells, plan->cell_geom);
     else launch(k_assemble_rows_p1<3, kCells>, plan->cells, nullptr);
     if (fork) cudaStreamWaitEvent(st, ss.join, 0);
     launch(k_assemble_rows_p1<3, kSurface>, plan->surface, plan->surface_work);
   }
   if (err != cudaSuccess) {
-    set_error("phifem_assemble_rows_p1: cannot reserve %zu bytes of shared memory: %s", smem,
-              cudaGetErrorString(err));
+    set_error("phifem_assemble_rows_p1: launch failed (%zu bytes of shared memory per row-gather CTA%s): %s", smem,
+              tiles ? ", cell tiles" : "", cudaGetErrorString(err));
     return PHIFEM_ERR_CUDA;
   }
   PHIFEM_CHECK_LAUNCH();

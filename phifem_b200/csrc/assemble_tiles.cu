@@ -1,0 +1,201 @@
+// K2+K4, cell-once form of the cell pass: strong-Dirichlet phi-FEM operator, P1 on triangles / tetrahedra.
+//
+// Forms of reference demo/strong-dirichlet/flower/main.py:105,107-112 (bilinear, cells) and :126-128 (linear),
+// closed forms of SURVEY.md Appendix B.  The row-gather pass (csrc/assemble_rows.cu) evaluates a cell once per
+// VERTEX: cofactors, determinant and reciprocal 4 times per tetrahedron, ~146 fp64 instructions per (row, cell)
+// record = ~580 per tetrahedron against ~190 for the whole 4x4 tensor evaluated once -- and the B200 retires only 64
+// fp64 lanes per clock per SM.  Here a CTA owns a TILE of R consecutive listed rows (spatially compact: the rows are
+// listed along a space-filling curve) and works through the cells touching the tile in CHUNKS of R cells:
+//   evaluate  thread t takes the cell in slot t of the chunk, gathers its vertices, evaluates the WHOLE element
+//             tensor and load vector once and parks the (D+1)^2 + (D+1) values in shared memory, entry-major
+//             (buf[e * R + t]: conflict-free);
+//   pull      after one barrier the thread of row l walks l's records of this chunk -- (slot, cell-local index of the
+//             row's vertex, positions of the other vertices inside the row's column list) -- and adds the row of the
+//             parked tensor to its private accumulators (diagonal and load entry in registers, off-diagonals in the
+//             column acc[k * R + l] of shared memory, as in the row-gather kernel).
+// Two tensor buffers alternate, so a chunk costs ONE barrier and the rows without records in a chunk go straight to the
+// next evaluation.  A cell touching several tiles is evaluated once per tile (recompute factor ~1.6 at R = 256 on a
+// Kuhn mesh instead of 4).  No atomics, no zero-fill; the cells of a tile are listed in ascending cell index, so every
+// row sums its cells in mesh order: bitwise reproducible and independent of the tiling.
+#include "common.cuh"
+#include "p1_forms.cuh"
+
+namespace phifem {
+namespace {
+
+#ifndef PHIFEM_TILES_MINBLOCKS
+#define PHIFEM_TILES_MINBLOCKS 2
+#endif
+
+// Whole element tensor of simplex X: K[i * NV + j] at out[(i * NV + j) * stride], b[i] at out[(NV * NV + i) * stride].
+//   K_ij = |K|/((d+1)(d+2)) [ |g|^2 (1 + delta_ij) + a_i (P + p_j) + (P + p_i) a_j + G_i.G_j mu ] + 4 sigma h^2 |K| a_i a_j
+//   b_i  = |K| d!/(d+3)! [ F P + sum f_k p_k + f_i (P + 2 p_i) + F p_i ] - 2 sigma h^2 |K| mean(f) a_i
+// with g = grad(phi), a_j = g.G_j, P = sum p, mu = P^2 + sum p^2, F = sum f; every gradient is left scaled by det
+// (G = R / det) so that one reciprocal serves the cell.
+template <int D>
+__device__ __forceinline__ void cell_tensor(const double (&X)[D + 1][D], const double (&p)[D + 1],
+                                            const double (&fv)[D + 1], bool is_cut, double sigma,
+                                            double* __restrict__ out, int stride) {
+  constexpr int NV = D + 1;
+  constexpr double dfact = D == 2 ? 2.0 : 6.0;
+  double R[NV][D], det;
+  simplex_cofactors<D>(X, R, det);
+  const double inv = 1.0 / det;
+  double gR[D];  // det * grad(phi)
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    double s = (p[1] - p[0]) * R[1][d];
+#pragma unroll
+    for (int k = 2; k < NV; ++k) s += (p[k] - p[0]) * R[k][d];
+    gR[d] = s;
+  }
+  double aR[NV];  // det^2 * a_j
+#pragma unroll
+  for (int j = 0; j < NV; ++j) aR[j] = dot<D>(gR, R[j]);
+  const double ggR = dot<D>(gR, gR);
+  double P = p[0], S2 = p[0] * p[0], F = fv[0], FP = fv[0] * p[0];
+#pragma unroll
+  for (int k = 1; k < NV; ++k) {
+    P += p[k];
+    S2 += p[k] * p[k];
+    F += fv[k];
+    FP += fv[k] * p[k];
+  }
+  const double ainv = fabs(inv), adet = fabs(det);
+  const double w = ainv * (1.0 / (dfact * (D + 1) * (D + 2)));
+  const double wmu = w * (P * P + S2), wgg = w * ggR;
+  double q[NV], wa[NV], sa[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    q[j] = P + p[j];
+    wa[j] = w * aR[j];
+    sa[j] = 0.0;
+  }
+  double sh2i = 0.0;  // sigma h_T^2 / det^2 on cut cells
+  if (is_cut) {
+    sh2i = sigma * diameter2<D>(X) * (inv * inv);
+    const double sc = (4.0 / dfact) * sh2i * ainv;  // 4 sigma h^2 |K| / det^4
+#pragma unroll
+    for (int j = 0; j < NV; ++j) sa[j] = sc * aR[j];
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = i; j < NV; ++j) {
+      const double c = dot<D>(R[i], R[j]);
+      double k = fma(c, wmu, i == j ? 2.0 * wgg : wgg);
+      k = fma(wa[i], q[j], k);
+      k = fma(q[i], wa[j], k);
+      k = fma(sa[i], aR[j], k);
+      out[(i * NV + j) * stride] = k;
+      if (j != i) out[(j * NV + i) * stride] = k;
+    }
+  constexpr double fact_d3 = D == 2 ? 120.0 : 720.0;
+  const double c3 = adet * (1.0 / fact_d3), base = F * P + FP;
+  const double cs = adet * (2.0 / (dfact * NV)) * sh2i * F;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    out[(NV * NV + i) * stride] = c3 * (base + fv[i] * (P + 2.0 * p[i]) + F * p[i]) - cs * aR[i];
+}
+
+template <int D, int R>
+__global__ void __launch_bounds__(R, PHIFEM_TILES_MINBLOCKS) k_assemble_tiles_p1(
+    const double* __restrict__ x, const double* __restrict__ phi, const double* __restrict__ f, double sigma,
+    const int32_t* __restrict__ indptr, phifem_cell_tiles tl, int max_row_nnz, double* __restrict__ data,
+    double* __restrict__ b) {
+  constexpr int NV = D + 1, NE = NV * NV + NV;
+  extern __shared__ double sm[];
+  double* acc_s = sm;                                   // [max_row_nnz][R]
+  double* buf_s = sm + (size_t)max_row_nnz * R;         // [2][NE][R]
+  uint32_t* rec_s = reinterpret_cast<uint32_t*>(buf_s + 2 * NE * R);  // [2][NV * R]
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x;
+  const int64_t li = (int64_t)tile * R + tid;
+  const bool has_row = li < tl.n_listed;
+  int r = 0, start = 0, nnz = 0, dpos = 0;
+  if (has_row) {
+    r = __ldg(tl.rows + li);
+    start = __ldg(indptr + r);
+    nnz = __ldg(indptr + r + 1) - start;
+    dpos = __ldg(tl.diag_pos + li);
+  }
+  double* acc = acc_s + tid;
+  for (int k = 0; k < nnz; ++k) acc[k * R] = 0.0;
+  double diag = 0.0, br = 0.0;
+  const int c0 = __ldg(tl.chunk_ptr + tile), c1 = __ldg(tl.chunk_ptr + tile + 1);
+  const int4* __restrict__ slots = reinterpret_cast<const int4*>(tl.slot_verts);
+  for (int c = c0; c < c1; ++c) {
+    const int sel = (c - c0) & 1;
+    double* buf = buf_s + sel * (NE * R);
+    uint32_t* recs = rec_s + sel * (NV * R);
+    const int4 sv = __ldg(slots + (int64_t)c * R + tid);
+    const int rb = __ldg(tl.rec_base + c), nrec = __ldg(tl.rec_base + c + 1) - rb;
+    const uint16_t* off = tl.rec_off + (int64_t)c * (R + 1);
+    const int o0 = has_row ? (int)__ldg(off + tid) : 0, o1 = has_row ? (int)__ldg(off + tid + 1) : 0;
+    for (int j = tid; j < nrec; j += R) recs[j] = __ldg(tl.rec + rb + j);
+    if (sv.x >= 0) {
+      const int v[4] = {sv.x, sv.y & 0x7fffffff, sv.z, sv.w};
+      double X[NV][D], p[NV], fv[NV];
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) X[k][d] = __ldg(x + (int64_t)v[k] * D + d);
+        p[k] = __ldg(phi + v[k]);
+        fv[k] = __ldg(f + v[k]);
+      }
+      cell_tensor<D>(X, p, fv, sv.y < 0, sigma, buf + tid, R);
+    }
+    __syncthreads();
+    for (int k = o0; k < o1; ++k) {
+      const uint32_t w = recs[k];
+      const int s = w & 0xff, i = (w >> 8) & 3;
+      const double* t = buf + s;
+      diag += t[(i * NV + i) * R];
+      br += t[(NV * NV + i) * R];
+#pragma unroll
+      for (int m = 0; m < D; ++m) {
+        const int j = m + (m >= i);  // m-th other vertex in ascending cell-local order
+        acc[((w >> (10 + 7 * m)) & 0x7f) * R] += t[(i * NV + j) * R];
+      }
+    }
+  }
+  if (has_row) {
+    acc[dpos * R] += diag;
+    for (int k = 0; k < nnz; ++k) data[start + k] = acc[k * R];
+    b[r] = br;
+  }
+}
+
+template <int D, int R>
+cudaError_t launch(const phifem_mesh* mesh, const double* phi, const double* f, double sigma, const int32_t* indptr,
+                   const phifem_cell_tiles& tl, int max_row_nnz, double* data, double* b, cudaStream_t st) {
+  constexpr int NV = D + 1, NE = NV * NV + NV;
+  const size_t smem = ((size_t)max_row_nnz * R + 2 * NE * R) * sizeof(double) + 2 * NV * R * sizeof(uint32_t);
+  auto kernel = k_assemble_tiles_p1<D, R>;
+  cudaError_t err = cudaSuccess;
+  if (smem > 48 * 1024) err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  kernel<<<(unsigned)tl.n_tiles, R, smem, st>>>(mesh->x, phi, f, sigma, indptr, tl, max_row_nnz, data, b);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+// Cell pass over the tiles of `tl`; called by phifem_assemble_rows_p1 (csrc/assemble_rows.cu) in place of the row-gather
+// cell pass when the plan carries tiles.  Returns cudaErrorInvalidValue for a malformed plan.
+cudaError_t launch_cell_tiles_p1(const phifem_mesh* mesh, const double* phi, const double* f, double sigma,
+                                 const int32_t* indptr, const phifem_cell_tiles* tl, int max_row_nnz, double* data,
+                                 double* b, cudaStream_t st) {
+  if (tl->n_tiles <= 0) return cudaSuccess;
+  if (!(tl->rows && tl->diag_pos && tl->chunk_ptr && tl->slot_verts && tl->rec_base && tl->rec_off && tl->rec) ||
+      max_row_nnz > 128 || (tl->rows_per_tile != 128 && tl->rows_per_tile != 256))
+    return cudaErrorInvalidValue;
+  const bool tri = mesh->cell_type == PHIFEM_TRIANGLE;
+  if (tl->rows_per_tile == 128)
+    return tri ? launch<2, 128>(mesh, phi, f, sigma, indptr, *tl, max_row_nnz, data, b, st)
+               : launch<3, 128>(mesh, phi, f, sigma, indptr, *tl, max_row_nnz, data, b, st);
+  return tri ? launch<2, 256>(mesh, phi, f, sigma, indptr, *tl, max_row_nnz, data, b, st)
+             : launch<3, 256>(mesh, phi, f, sigma, indptr, *tl, max_row_nnz, data, b, st);
+}
+
+}  // namespace phifem

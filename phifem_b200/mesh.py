@@ -100,6 +100,20 @@ class _Geometry:
         return out
 
 
+def morton_keys(pts, bits=21):
+    """Morton (Z-order) key of each point: coordinates quantised to `bits` bits per axis over the bounding box, bits
+    interleaved (axis 0 least significant)."""
+    d = pts.shape[1]
+    bits = min(bits, 63 // d)
+    lo, hi = pts.min(dim=0).values, pts.max(dim=0).values
+    q = ((pts - lo) / (hi - lo).clamp(min=1e-300) * (2 ** bits - 1)).long().clamp_(0, 2 ** bits - 1)
+    key = torch.zeros(pts.shape[0], dtype=torch.int64, device=pts.device)
+    for bit in range(bits):
+        for k in range(d):
+            key |= ((q[:, k] >> bit) & 1) << (bit * d + k)
+    return key
+
+
 class Mesh:
     """Unstructured mesh of triangles, quadrilaterals or tetrahedra on one device."""
 
@@ -117,6 +131,9 @@ class Mesh:
         self.num_cells = int(self.cells.shape[0])
         self._topo = None
         self._host = {}
+        self.sfc_ordered = False            # numbered along a space-filling curve (see `reordered`)
+        self.original_cell_index = None
+        self.input_global_indices = None
         self.topology = Topology(self)
         self.geometry = _Geometry(self)
 
@@ -128,6 +145,35 @@ class Mesh:
         if cell_type == "quadrilateral":
             cells = cells[:, [0, 1, 3, 2]]
         return Mesh(x, cells, cell_type, device)
+
+    def reordered(self, curve="morton"):
+        """The same mesh renumbered along a space-filling curve: vertices by the Morton key of their coordinates, cells
+        by the Morton key of their centroid (cell-local vertex order kept, so local facets and orientations are
+        unchanged).  This is the data-locality reordering dolfinx applies when it builds a mesh (`create_mesh` reorders
+        cells and vertices and keeps `topology.original_cell_index` / `geometry.input_global_indices` [dep-knowledge]);
+        like there, everything downstream -- facet numbering, tags, dofs, CSR rows -- lives in the NEW numbering and the
+        two maps translate user data:
+            new.original_cell_index[c_new] = c_old        new.input_global_indices[v_new] = v_old
+        so per-vertex data of the old mesh becomes `data[new.input_global_indices]`."""
+        if curve != "morton":
+            raise ValueError("curve must be 'morton'")
+        vperm = torch.argsort(morton_keys(self.x), stable=True)                 # new -> old
+        vinv = torch.empty_like(vperm)
+        vinv[vperm] = torch.arange(self.num_vertices, device=self.device)
+        step = 1 << 24
+        ckey = torch.empty(self.num_cells, dtype=torch.int64, device=self.device)
+        lo, hi = self.x.min(dim=0).values, self.x.max(dim=0).values
+        box = torch.stack([lo, hi])
+        for s0 in range(0, self.num_cells, step):
+            cen = self.x[self.cells[s0:s0 + step].long()].mean(dim=1)
+            ckey[s0:s0 + step] = morton_keys(torch.cat([box, cen]))[2:]         # same bounding box for every slab
+        cperm = torch.argsort(ckey, stable=True)
+        del ckey
+        new = Mesh(self.x[vperm], vinv[self.cells[cperm].long()].to(torch.int32), self.cell_type, self.device)
+        new.sfc_ordered = True
+        new.original_cell_index = cperm
+        new.input_global_indices = vperm
+        return new
 
     # ---- host mirrors (lazy) -------------------------------------------------------------
     @property

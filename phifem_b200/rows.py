@@ -25,15 +25,8 @@ BALANCE_CHUNK = 4096         # rows per spatially compact group of the surface l
 
 def morton_order(x, rows):
     """Listed rows sorted along a Morton curve of their vertex coordinates (21 bits per axis)."""
-    pts = x[rows]
-    lo, hi = pts.min(dim=0).values, pts.max(dim=0).values
-    q = ((pts - lo) / (hi - lo).clamp(min=1e-300) * (2 ** 21 - 1)).long().clamp_(0, 2 ** 21 - 1)
-    d = pts.shape[1]
-    key = torch.zeros(len(rows), dtype=torch.int64, device=x.device)
-    for bit in range(21):
-        for k in range(d):
-            key |= ((q[:, k] >> bit) & 1) << (bit * d + k)
-    return rows[torch.argsort(key, stable=True)]
+    from .mesh import morton_keys
+    return rows[torch.argsort(morton_keys(x[rows]), stable=True)]
 
 
 class RowList:
@@ -151,7 +144,10 @@ class RowsPlan:
     SLOWER on the B200 -- the table misses L1 where the coordinates hit -- hence off by default, see
     csrc/assemble_rows.cu)."""
 
-    def __init__(self, plan, order="natural", row_mask=None, geometry=False):
+    def __init__(self, plan, order="natural", row_mask=None, geometry=False, cell_pass="rows", rows_per_tile=256):
+        """cell_pass: "rows" = the row-gather cell pass (one evaluation per (row, cell) record); "tiles" = the cell-once
+        pass of csrc/assemble_tiles.cu (phifem_b200/tiles.py), whose rows are listed along the Morton curve unless
+        `order` says otherwise or the mesh is already numbered along a space-filling curve (`mesh.sfc_ordered`)."""
         mesh = plan.mesh
         dev = mesh.device
         d = mesh.gdim
@@ -178,9 +174,16 @@ class RowsPlan:
             raise NotImplementedError(
                 "row-gather assembly: a row holds %d entries (limit %d); use the atomic scatter kernels "
                 "for this mesh" % (self.max_row_nnz, min(MAX_ROW_NNZ, MAX_SMEM_BYTES // (BLOCK * 8))))
-        if order not in ("natural", "morton"):
-            raise ValueError("order must be 'natural' or 'morton'")
+        if order not in ("natural", "morton", "auto"):
+            raise ValueError("order must be 'natural', 'morton' or 'auto'")
+        if cell_pass not in ("rows", "tiles"):
+            raise ValueError("cell_pass must be 'rows' or 'tiles'")
+        if cell_pass == "tiles" and (geometry or self.max_row_nnz > 128):
+            cell_pass = "rows"        # positions of the tile records are 7 bits
+        if order == "auto":
+            order = "morton" if cell_pass == "tiles" and not getattr(mesh, "sfc_ordered", False) else "natural"
         self.order = order
+        self.cell_pass = cell_pass
 
         def ordered(rows):
             """Unique row ids in processing order."""
@@ -216,7 +219,18 @@ class RowsPlan:
             words.append(torch.stack([w0 | (i << 25), cidx], dim=1) if geometry else w0[:, None])
         # interleaved so that the records of a row keep cell order (deterministic summation order)
         rec_rows, words = owned(cells_act.reshape(-1), torch.stack(words, dim=1).reshape(-1, 2 if geometry else 1))
-        self.cells = RowList(ordered(listed), dslot, indptr, rec_rows, words, n)
+        self.tiles = None
+        if cell_pass == "tiles":
+            from .tiles import CellTiles
+            trows = ordered(listed)
+            self.tiles = CellTiles(mesh, plan.active, cut, plan.slots_cells, indptr, trows,
+                                   (dslot[trows] - indptr[trows]).to(torch.uint8), rows_per_tile)
+            self.n_cell_records = int(rec_rows.numel())
+            empty = torch.zeros(0, **i64)
+            self.cells = RowList(empty, dslot, indptr, empty, torch.zeros((0, 1), **i64), n)
+        else:
+            self.cells = RowList(ordered(listed), dslot, indptr, rec_rows, words, n)
+            self.n_cell_records = self.cells.n_records
         self.cell_geom = cell_geometry(mesh.x, cells_act) if geometry and cells_act.shape[0] else None
         del slots, cells_act, words
 
@@ -291,7 +305,7 @@ class RowsPlan:
             empty = _lib.CRowList(0, None, None, None, None)
             lists = [getattr(self, nm).c_struct() if nm in passes else empty for nm in ("cells", "surface")]
             return _lib.CRowsPlan(p(self.plan.indptr), p(self.plan.indices), self.max_row_nnz, 0, *lists,
-                                  *self._surface_fields())
+                                  *self._surface_fields(cells="cells" in passes))
         if self._c is None:
             p = _lib.ptr
             pl = self.plan
@@ -299,18 +313,20 @@ class RowsPlan:
                                      self.cells.c_struct(), self.surface.c_struct(), *self._surface_fields())
         return self._c
 
-    def _surface_fields(self):
+    def _surface_fields(self, cells=True):
         """Trailing fields of phifem_rows_plan: ghost facet / entity vertex lists, the facet-once scratch, the cached
         cell geometry."""
         if self.surface_work.device.type != "cuda":
-            return 0, None, 0, None, None, None
+            return 0, None, 0, None, None, None, None
         return (self.n_ghost_facets, _lib.ptr(self.ghost_macro) if self.n_ghost_facets else None,
                 self.n_entities, _lib.ptr(self.entity_macro) if self.n_entities else None,
-                _lib.ptr(self.surface_work), _lib.ptr(self.cell_geom))
+                _lib.ptr(self.surface_work), _lib.ptr(self.cell_geom),
+                ctypes.pointer(self.tiles.c_struct()) if self.tiles is not None and cells else None)
 
     def index_bytes(self):
         """Bytes of plan arrays one numeric pass streams besides the CSR pattern itself."""
-        return (self.cells.nbytes() + self.surface.nbytes() + self.ghost_macro.numel() * 4
+        return (self.cells.nbytes() + (self.tiles.nbytes() if self.tiles is not None else 0)
+                + self.surface.nbytes() + self.ghost_macro.numel() * 4
                 + self.entity_macro.numel() * 4 + self.surface_work.numel() * 8
                 + (self.cell_geom.numel() * 8 if self.cell_geom is not None else 0))
 

@@ -79,6 +79,28 @@ def unstructured_variant(mesh, jitter=0.2, seed=0):
     return Mesh(xn, relabel[cells].astype(np.int32), mesh.cell_type, mesh.device)
 
 
+def unstructured_variant_device(mesh, jitter=0.2, seed=0):
+    """`unstructured_variant` with torch generators on the mesh's device (the 50 M-cell benchmark mesh is never copied
+    to the host): jitter from seed, cell permutation from seed + 1, vertex relabelling from seed + 2."""
+    dev = mesh.device
+    gens = [torch.Generator(device=dev).manual_seed(seed + k) for k in range(3)]
+    x = mesh.x.clone()
+    lo, hi = x.min(dim=0).values, x.max(dim=0).values
+    nv = mesh.num_vertices
+    n = round(nv ** (1.0 / x.shape[1])) - 1
+    h = (hi - lo) / n
+    interior = ((x > lo + 1e-12) & (x < hi - 1e-12)).all(dim=1)
+    u = torch.rand(x.shape, generator=gens[0], device=dev, dtype=torch.float64) * 2.0 - 1.0
+    x += torch.where(interior[:, None], u * (jitter * h), torch.zeros_like(u))
+    del u
+    cperm = torch.randperm(mesh.num_cells, generator=gens[1], device=dev)
+    relabel = torch.randperm(nv, generator=gens[2], device=dev)
+    xn = torch.empty_like(x)
+    xn[relabel] = x
+    cells = relabel[mesh.cells[cperm].long()].to(torch.int32)
+    return Mesh(xn, cells, mesh.cell_type, dev)
+
+
 SPHERE_CENTER = (0.5 + math.pi / 1000.0, 0.5 + math.e / 1000.0, 0.5 + math.sqrt(2.0) / 1000.0)
 SPHERE_RADIUS = 0.45
 

@@ -39,6 +39,7 @@ def _row_scale(indptr, data):
 
 
 @pytest.mark.parametrize("method,capacity", [("rows", None), ("rows", "morton"), ("rows", "geometry"),
+                                             ("rows", "tiles128"), ("rows", "tiles256"),
                                              ("blocked", None), ("blocked", 2500), ("atomic", None)])
 @pytest.mark.parametrize("kind,n", [("tri", 40), ("tri-unstructured", 24), ("tet", 10),
                                     ("tet-unstructured", 8)])
@@ -48,16 +49,19 @@ def test_cuda_operator_matches_oracle(kind, n, method, capacity):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore", RuntimeWarning)
         ctags, ftags, _, ds, _ = mesh_scripts.compute_tags_measures(mesh, fn, 1, box_mode=True)
-    order, geometry = "natural", False
-    if method == "rows" and capacity == "geometry":   # cell pass from the plan's geometry table instead of the coordinates
+    order, geometry, cell_pass, rpt = "natural", False, "rows", 256
+    if method == "rows" and str(capacity).startswith("tiles"):   # cell-once cell pass (csrc/assemble_tiles.cu)
+        order, cell_pass, rpt, capacity = "morton", "tiles", int(capacity[5:]), None
+    elif method == "rows" and capacity == "geometry":   # cell pass from the plan's geometry table instead of the coordinates
         geometry, capacity = True, None
     elif method == "rows" and capacity:
         order, capacity = capacity, None
     plan = assemble.build_plan(mesh, ctags, ftags, ds(100), method=method, capacity=capacity, order=order,
-                               geometry=geometry)
+                               geometry=geometry, cell_pass=cell_pass, rows_per_tile=rpt)
     assert plan.method == method
     if method == "rows":
         assert (plan.rowsplan.cell_geom is not None) == geometry
+        assert (plan.rowsplan.tiles is not None) == (cell_pass == "tiles")
     A, b = assemble.assemble_strong_dirichlet(plan, phi, f, stab_coef=1.0)
     if method in ("blocked", "rows"):
         # owner-computes sums in a fixed order: bitwise reproducible, and independent of what the
@@ -69,7 +73,7 @@ def test_cuda_operator_matches_oracle(kind, n, method, capacity):
         if capacity:
             assert plan.blocked.n_blocks > 4
         if method == "rows":
-            assert plan.rowsplan.order == order and plan.rowsplan.cells.n_records > 0
+            assert plan.rowsplan.order == order and plan.rowsplan.n_cell_records > 0
 
     x = mesh.x.cpu().numpy()
     cells = mesh.cells.cpu().numpy().astype(np.int64)
