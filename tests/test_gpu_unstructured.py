@@ -38,7 +38,9 @@ def problem():
     c2f, f2c = np.ascontiguousarray(host.c2f.numpy()), np.ascontiguousarray(host.f2c.numpy())
     phi_o = np.empty(len(x))
     phi_o[igi] = phi.cpu().numpy()
-    assert np.array_equal(phi_o, synthetic.sphere_levelset(host.x).numpy())      # same coordinates, same values
+    # (the level set is data of the mesh numbering: the oracle gets the SAME values, moved to the user's numbering;
+    # re-evaluating it on the host would differ in the last bit, the device contracts a*a + b into an FMA)
+    assert np.abs(phi_o - synthetic.sphere_levelset(host.x).numpy()).max() < 1e-15
     f_o = np.empty(len(x))
     f_o[igi] = f.cpu().numpy()
     ct_o = ON.tag_cells_p1(x, cells, phi_o)
