@@ -26,6 +26,9 @@ namespace {
 #ifndef PHIFEM_TILES_MINBLOCKS
 #define PHIFEM_TILES_MINBLOCKS 2
 #endif
+#ifndef PHIFEM_TILES_MINBLOCKS_128
+#define PHIFEM_TILES_MINBLOCKS_128 4
+#endif
 
 // Whole element tensor of simplex X: K[i * NV + j] at out[(i * NV + j) * stride], b[i] at out[(NV * NV + i) * stride].
 //   K_ij = |K|/((d+1)(d+2)) [ |g|^2 (1 + delta_ij) + a_i (P + p_j) + (P + p_i) a_j + G_i.G_j mu ] + 4 sigma h^2 |K| a_i a_j
@@ -98,12 +101,35 @@ __device__ __forceinline__ void cell_tensor(const double (&X)[D + 1][D], const d
     out[(NV * NV + i) * stride] = c3 * (base + fv[i] * (P + 2.0 * p[i]) + F * p[i]) - cs * aR[i];
 }
 
+// position of K_ij inside the packed symmetric tensor (i <= j: i * NV - i (i - 1) / 2 + j - i), 4 bits per (i, j)
+template <int NV> __host__ __device__ constexpr uint64_t sym_lut() {
+  uint64_t lut = 0;
+  for (int i = 0; i < NV; ++i)
+    for (int j = 0; j < NV; ++j) {
+      const int a = i < j ? i : j, c = i < j ? j : i;
+      lut |= (uint64_t)(a * NV - a * (a - 1) / 2 + c - a) << (4 * (i * 4 + j));
+    }
+  return lut;
+}
+
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Software pipeline over the chunks of a tile: while a chunk's tensors are pulled, the vertex data of the NEXT chunk's
+// cell is already on its way into registers, that chunk's records stream into shared memory with cp.async and the
+// vertex ids of the chunk after it are being fetched -- the only global latency left on the critical path of a chunk is
+// the barrier itself.
 template <int D, int R>
-__global__ void __launch_bounds__(R, PHIFEM_TILES_MINBLOCKS) k_assemble_tiles_p1(
+__global__ void __launch_bounds__(R, R == 128 ? PHIFEM_TILES_MINBLOCKS_128 : PHIFEM_TILES_MINBLOCKS) k_assemble_tiles_p1(
     const double* __restrict__ x, const double* __restrict__ phi, const double* __restrict__ f, double sigma,
     const int32_t* __restrict__ indptr, phifem_cell_tiles tl, int max_row_nnz, double* __restrict__ data,
     double* __restrict__ b) {
-  constexpr int NV = D + 1, NE = NV * NV + NV;
+  constexpr int NV = D + 1, NS = NV * (NV + 1) / 2, NE = NS + NV;   // packed symmetric tensor + load vector
+  constexpr uint64_t LUT = sym_lut<NV>();
   extern __shared__ double sm[];
   double* acc_s = sm;                                   // [max_row_nnz][R]
   double* buf_s = sm + (size_t)max_row_nnz * R;         // [2][NE][R]
@@ -124,38 +150,103 @@ __global__ void __launch_bounds__(R, PHIFEM_TILES_MINBLOCKS) k_assemble_tiles_p1
   double diag = 0.0, br = 0.0;
   const int c0 = __ldg(tl.chunk_ptr + tile), c1 = __ldg(tl.chunk_ptr + tile + 1);
   const int4* __restrict__ slots = reinterpret_cast<const int4*>(tl.slot_verts);
+  const int4 none = make_int4(-1, 0, 0, 0);
+
+  double X[NV][D], p[NV], fv[NV];
+  auto gather = [&](const int4& sv) {  // issue the loads of a cell's vertex data (no use until the next evaluation)
+    if (sv.x < 0) return;
+    const int v[4] = {sv.x, sv.y & 0x7fffffff, sv.z, sv.w};
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) X[k][d] = __ldg(x + (int64_t)v[k] * D + d);
+      p[k] = __ldg(phi + v[k]);
+      fv[k] = __ldg(f + v[k]);
+    }
+  };
+  auto stream_records = [&](int c) {   // records of chunk c -> rec_s[c & 1] (asynchronous)
+    const int rb = __ldg(tl.rec_base + c), nrec = __ldg(tl.rec_base + c + 1) - rb;
+    uint32_t* dst = rec_s + ((c - c0) & 1) * (NV * R);
+    for (int j = tid; j < nrec; j += R) cp_async4(dst + j, tl.rec + rb + j);
+    cp_async_commit();
+  };
+  auto offsets = [&](int c, int& o0, int& o1) {
+    const uint16_t* off = tl.rec_off + (int64_t)c * (R + 1);
+    o0 = has_row ? (int)__ldg(off + tid) : 0;
+    o1 = has_row ? (int)__ldg(off + tid + 1) : 0;
+  };
+
+  int4 sv = c0 < c1 ? __ldg(slots + (int64_t)c0 * R + tid) : none;           // cell evaluated in this chunk
+  int4 sv1 = c0 + 1 < c1 ? __ldg(slots + (int64_t)(c0 + 1) * R + tid) : none;  // ... in the next one
+  int o0 = 0, o1 = 0;
+  if (c0 < c1) {
+    stream_records(c0);
+    offsets(c0, o0, o1);
+    gather(sv);
+  }
   for (int c = c0; c < c1; ++c) {
     const int sel = (c - c0) & 1;
     double* buf = buf_s + sel * (NE * R);
-    uint32_t* recs = rec_s + sel * (NV * R);
-    const int4 sv = __ldg(slots + (int64_t)c * R + tid);
-    const int rb = __ldg(tl.rec_base + c), nrec = __ldg(tl.rec_base + c + 1) - rb;
-    const uint16_t* off = tl.rec_off + (int64_t)c * (R + 1);
-    const int o0 = has_row ? (int)__ldg(off + tid) : 0, o1 = has_row ? (int)__ldg(off + tid + 1) : 0;
-    for (int j = tid; j < nrec; j += R) recs[j] = __ldg(tl.rec + rb + j);
-    if (sv.x >= 0) {
-      const int v[4] = {sv.x, sv.y & 0x7fffffff, sv.z, sv.w};
-      double X[NV][D], p[NV], fv[NV];
+    const uint32_t* recs = rec_s + sel * (NV * R);
+    if (sv.x >= 0) {   // evaluate: whole tensor of this thread's cell, packed symmetric, entry-major
+      double out[NV * NV + NV];
+      cell_tensor<D>(X, p, fv, sv.y < 0, sigma, out, 1);
 #pragma unroll
-      for (int k = 0; k < NV; ++k) {
+      for (int i = 0; i < NV; ++i) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) X[k][d] = __ldg(x + (int64_t)v[k] * D + d);
-        p[k] = __ldg(phi + v[k]);
-        fv[k] = __ldg(f + v[k]);
+        for (int j = i; j < NV; ++j) buf[(int)((LUT >> (4 * (i * 4 + j))) & 0xf) * R + tid] = out[i * NV + j];
+        buf[(NS + i) * R + tid] = out[NV * NV + i];
       }
-      cell_tensor<D>(X, p, fv, sv.y < 0, sigma, buf + tid, R);
     }
+    // next chunk: vertex data into the registers just consumed, vertex ids of the chunk after it, record offsets
+    sv = sv1;
+    gather(sv);
+    sv1 = c + 2 < c1 ? __ldg(slots + (int64_t)(c + 2) * R + tid) : none;
+    const int q0 = o0, q1 = o1;
+    if (c + 1 < c1) offsets(c + 1, o0, o1);
+    cp_async_wait_all();   // this chunk's records (issued one chunk ago) have landed
     __syncthreads();
-    for (int k = o0; k < o1; ++k) {
-      const uint32_t w = recs[k];
-      const int s = w & 0xff, i = (w >> 8) & 3;
-      const double* t = buf + s;
-      diag += t[(i * NV + i) * R];
-      br += t[(NV * NV + i) * R];
+    if (c + 1 < c1) stream_records(c + 1);   // every thread is past the pull of chunk c - 1: its record buffer is free
+    // pull: this row's records of the chunk; the parked values of record k + 1 are requested before record k is added
+    int k = q0;
+    uint32_t w = 0;
+    double t[NV + 1];
+    auto fetch = [&](int kk, uint32_t& ww, double (&tt)[NV + 1]) {
+      ww = recs[kk];
+      const int s = ww & 0xff, i = (ww >> 8) & 3;
+      const double* src = buf + s;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) tt[j] = src[(int)((LUT >> (4 * (i * 4 + j))) & 0xf) * R];
+      tt[NV] = src[(NS + i) * R];
+    };
+    if (k < q1) fetch(k, w, t);
+    while (k < q1) {
+      const uint32_t wc = w;
+      double tc[NV + 1];
+#pragma unroll
+      for (int j = 0; j <= NV; ++j) tc[j] = t[j];
+      if (++k < q1) fetch(k, w, t);
+      const int i = (wc >> 8) & 3;
+      br += tc[NV];
+      double a[D];
+      double* dst[D];
+#pragma unroll
+      for (int m = 0; m < D; ++m) {   // the D other vertices of a cell sit at D distinct positions of the row
+        dst[m] = acc + ((wc >> (10 + 7 * m)) & 0x7f) * R;
+        a[m] = *dst[m];
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        if (j == i) diag += tc[j];
+      }
 #pragma unroll
       for (int m = 0; m < D; ++m) {
-        const int j = m + (m >= i);  // m-th other vertex in ascending cell-local order
-        acc[((w >> (10 + 7 * m)) & 0x7f) * R] += t[(i * NV + j) * R];
+        const int j = m + (m >= i);
+        double v = tc[0];
+#pragma unroll
+        for (int jj = 1; jj < NV; ++jj)
+          if (jj == j) v = tc[jj];
+        *dst[m] = a[m] + v;
       }
     }
   }
@@ -169,7 +260,7 @@ __global__ void __launch_bounds__(R, PHIFEM_TILES_MINBLOCKS) k_assemble_tiles_p1
 template <int D, int R>
 cudaError_t launch(const phifem_mesh* mesh, const double* phi, const double* f, double sigma, const int32_t* indptr,
                    const phifem_cell_tiles& tl, int max_row_nnz, double* data, double* b, cudaStream_t st) {
-  constexpr int NV = D + 1, NE = NV * NV + NV;
+  constexpr int NV = D + 1, NE = NV * (NV + 1) / 2 + NV;
   const size_t smem = ((size_t)max_row_nnz * R + 2 * NE * R) * sizeof(double) + 2 * NV * R * sizeof(uint32_t);
   auto kernel = k_assemble_tiles_p1<D, R>;
   cudaError_t err = cudaSuccess;
