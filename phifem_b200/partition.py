@@ -4,8 +4,8 @@
 triangle / tetrahedron mesh the way the north star describes: cells are sorted along a space-filling
 (Morton) curve of their centroids and cut into `world` contiguous ranges; a CSR row (= vertex) is owned by
 the lowest rank owning a cell that touches it; every rank keeps its own range, the cells touching its rows and
-their facet neighbours (the reach of the ghost penalty) -- plus, with `single_layer_cut`, the vertex neighbours of
-all of those --, classifies them redundantly and runs the row-gather kernels on its own rows.  Nothing is exchanged in the numeric phase except the 8-byte "any exterior cell" all-reduce of
+the cells sharing a vertex with those (which covers their facet neighbours, the reach of the ghost penalty, without a
+global facet numbering) -- plus, with `single_layer_cut`, one more such layer --, classifies them redundantly and runs the row-gather kernels on its own rows.  Nothing is exchanged in the numeric phase except the 8-byte "any exterior cell" all-reduce of
 the facet algebra (reference src/phifem/mesh_scripts.py:469-474).
 
 The local mesh keeps the global relative order of cells, vertices and hence facets (order-preserving
@@ -24,16 +24,7 @@ from . import assemble, mesh_scripts
 from .mesh import Mesh
 
 
-def morton_keys(pts):
-    """63-bit Morton keys of points [n, d] (21 bits per axis over the bounding box)."""
-    lo, hi = pts.min(dim=0).values, pts.max(dim=0).values
-    q = ((pts - lo) / (hi - lo).clamp(min=1e-300) * (2 ** 21 - 1)).long().clamp_(0, 2 ** 21 - 1)
-    d = pts.shape[1]
-    key = torch.zeros(pts.shape[0], dtype=torch.int64, device=pts.device)
-    for bit in range(21):
-        for k in range(d):
-            key |= ((q[:, k] >> bit) & 1) << (bit * d + k)
-    return key
+from .mesh import morton_keys  # noqa: E402  (63-bit Morton keys over the bounding box)
 
 
 def partition_cells(mesh, world, weights=None):
@@ -50,50 +41,121 @@ def partition_cells(mesh, world, weights=None):
     return owner
 
 
+def rank_share(mesh, cell_owner, vowner, rank, single_layer_cut=False):
+    """Global ids (ascending) of the cells and vertices rank `rank` keeps: the cells touching a row it owns, the cells
+    sharing a vertex with those (a superset of their facet neighbours -- the reach of the ghost penalty and of the
+    one-sided entities -- that needs no global facet numbering), its own range of the curve, and with
+    `single_layer_cut` (reference :349-358 re-tags a cut cell from every cell sharing a VERTEX with it) one more layer."""
+    cells = mesh.cells.long()
+    dev = mesh.device
+    owned_v = vowner == rank
+    keep = owned_v[cells].any(dim=1)
+    for _ in range(2 if single_layer_cut else 1):
+        vmark = torch.zeros(mesh.num_vertices, dtype=torch.bool, device=dev)
+        vmark[cells[keep].reshape(-1)] = True
+        keep = vmark[cells].any(dim=1)
+    keep |= cell_owner == rank             # every cell's tag has one home
+    gc = torch.nonzero(keep).reshape(-1)
+    gv = torch.unique(cells[gc].reshape(-1))
+    return gc, gv
+
+
 class PartitionedProblem:
-    """One rank's share of (mesh, phi, f): local mesh = cells touching owned rows + their facet neighbours.
+    """One rank's share of (mesh, phi, f): local mesh = cells touching owned rows + the cells around them.
 
     Attributes: `mesh` (local), `phi`, `f` (local vertex values), `global_vertex` / `global_cell` (ids of the
-    local entities, ascending), `row_mask` (local vertices whose rows this rank owns), `cell_owned`."""
+    local entities, ascending), `row_mask` (local vertices whose rows this rank owns), `cell_owned`.
+
+    Two ways in: the constructor (every rank holds the global arrays and cuts its own share: the CPU tests) and
+    `PartitionedProblem.scatter` (ONE rank holds the global mesh, computes the partition once and sends every rank its
+    share only: symbolic time and memory of a rank shrink with the number of ranks)."""
 
     def __init__(self, mesh, phi, f, rank, world, group=None, weights=None, single_layer_cut=False):
         if mesh.cell_type not in ("triangle", "tetrahedron"):
             raise NotImplementedError("sharding supports triangles and tetrahedra")
-        self.rank, self.world, self.group = rank, world, group
-        dev = mesh.device
+        cell_owner, vowner = self.ownership(mesh, world, weights)
+        self.vertex_owner_global = vowner
+        gc, gv = rank_share(mesh, cell_owner, vowner, rank, single_layer_cut)
+        self._from_share(rank, world, group, single_layer_cut, mesh.cell_type, mesh.num_vertices, gc, gv,
+                         mesh.cells[gc].long(), mesh.x[gv], phi.to(mesh.device)[gv], f.to(mesh.device)[gv],
+                         vowner[gv] == rank, cell_owner[gc] == rank)
+
+    @staticmethod
+    def ownership(mesh, world, weights=None):
+        """(cell_owner [Nc], vertex_owner [Nv]): contiguous ranges of the Morton order of the cell centroids of equal
+        weight; a vertex (= CSR row) belongs to the lowest rank owning a cell that touches it."""
         cells = mesh.cells.long()
         cell_owner = partition_cells(mesh, world, weights)
-        vowner = torch.full((mesh.num_vertices,), world, dtype=torch.int64, device=dev)
+        vowner = torch.full((mesh.num_vertices,), world, dtype=torch.int64, device=mesh.device)
         vowner.scatter_reduce_(0, cells.reshape(-1), cell_owner.repeat_interleave(cells.shape[1]), reduce="amin")
-        self.vertex_owner_global = vowner
-        owned_v = vowner == rank
-        keep = owned_v[cells].any(dim=1)                         # cells touching an owned row
-        # + their facet neighbours (ghost-penalty macro elements, tags on both sides of every relevant facet)
-        fac = mesh.c2f[keep].long().reshape(-1)
-        nb = mesh.f2c[fac].long().reshape(-1)
-        keep = keep.clone()
-        keep[nb[nb >= 0]] = True
-        keep |= cell_owner == rank     # plus the rank's own range, so that every cell's tag has one home
+        return cell_owner, vowner
+
+    def _from_share(self, rank, world, group, single_layer_cut, cell_type, n_global_vertices, gc, gv, cells_global,
+                    x, phi, f, row_mask, cell_owned):
+        dev = x.device
+        self.rank, self.world, self.group = rank, world, group
         self.single_layer_cut = bool(single_layer_cut)
-        if single_layer_cut:
-            # `single_layer_cut` (reference :349-358) re-tags a cut cell from the tags of every cell sharing a VERTEX
-            # with it: one more layer, so that the cells above see all their vertex neighbours
-            vmark = torch.zeros(mesh.num_vertices, dtype=torch.bool, device=dev)
-            vmark[cells[keep].reshape(-1)] = True
-            keep = keep | vmark[cells].any(dim=1)
-        gc = torch.nonzero(keep).reshape(-1)                      # ascending global cell ids
-        gv = torch.unique(cells[gc].reshape(-1))                  # ascending global vertex ids
-        relabel = torch.full((mesh.num_vertices,), -1, dtype=torch.int64, device=dev)
-        relabel[gv] = torch.arange(gv.numel(), device=dev)
-        self.mesh = Mesh(mesh.x[gv], relabel[cells[gc]].to(torch.int32), mesh.cell_type, dev)
+        # order-preserving relabelling: local vertex k = k-th smallest global id
+        local = torch.searchsorted(gv, cells_global.reshape(-1)).reshape(cells_global.shape)
+        self.mesh = Mesh(x, local.to(torch.int32), cell_type, dev)
         self.global_cell, self.global_vertex = gc, gv
-        self.n_global_vertices = mesh.num_vertices
-        self.row_mask = owned_v[gv]
-        self.cell_owned = cell_owner[gc] == rank
+        self.n_global_vertices = int(n_global_vertices)
+        self.row_mask = row_mask.to(torch.bool)
+        self.cell_owned = cell_owned.to(torch.bool)
         self.n_owned_cells = int(self.cell_owned.sum())
-        self.phi = phi.to(dev)[gv].contiguous()
-        self.f = f.to(dev)[gv].contiguous()
+        self.phi, self.f = phi.contiguous(), f.contiguous()
         self.plan = None
+
+    @classmethod
+    def scatter(cls, mesh, phi, f, rank, world, group=None, weights=None, single_layer_cut=False, src=0,
+                device=None):
+        """Rank `src` passes the global (mesh, phi, f) -- everybody else passes None -- computes the Morton partition
+        ONCE and sends each rank its share: global ids, cell -> global vertex, coordinates, level set, source, owned
+        rows, owned cells (point-to-point `torch.distributed` transfers: NCCL between GPUs, gloo on the CPU).  No rank
+        but `src` ever holds the global arrays, and nobody builds the global facet numbering."""
+        import torch.distributed as dist
+        dev = torch.device(device) if device is not None else mesh.device
+        i64 = dict(dtype=torch.int64, device=dev)
+        names = ("gc", "gv", "cells", "x", "phi", "f", "row_mask", "cell_owned")
+        dtypes = (torch.int64, torch.int64, torch.int64, torch.float64, torch.float64, torch.float64, torch.uint8,
+                  torch.uint8)
+        mine = None
+        if rank == src:
+            if mesh.cell_type not in ("triangle", "tetrahedron"):
+                raise NotImplementedError("sharding supports triangles and tetrahedra")
+            cell_owner, vowner = cls.ownership(mesh, world, weights)
+            nv, gdim = mesh.cells.shape[1], mesh.gdim
+            for r in range(world):
+                gc, gv = rank_share(mesh, cell_owner, vowner, r, single_layer_cut)
+                part = (gc, gv, mesh.cells[gc].long().reshape(-1), mesh.x[gv].reshape(-1), phi.to(dev)[gv],
+                        f.to(dev)[gv], (vowner[gv] == r).to(torch.uint8), (cell_owner[gc] == r).to(torch.uint8))
+                head = torch.tensor([gc.numel(), gv.numel(), mesh.num_vertices, nv, gdim], **i64)
+                if r == src:
+                    mine = (head, part)
+                    continue
+                dist.send(head, r, group=group)
+                for t in part:
+                    dist.send(t.contiguous(), r, group=group)
+                del part
+            head, part = mine
+        else:
+            head = torch.empty(5, **i64)
+            dist.recv(head, src, group=group)
+            nc, nvl, _, nv, gdim = (int(v) for v in head)
+            sizes = (nc, nvl, nc * nv, nvl * gdim, nvl, nvl, nvl, nc)
+            part = []
+            for n, dt in zip(sizes, dtypes):
+                t = torch.empty(n, dtype=dt, device=dev)
+                dist.recv(t, src, group=group)
+                part.append(t)
+        nc, nvl, n_global, nv, gdim = (int(v) for v in head)
+        p = dict(zip(names, part))
+        self = cls.__new__(cls)
+        self.vertex_owner_global = None
+        self._from_share(rank, world, group, single_layer_cut, "triangle" if nv == 3 else "tetrahedron", n_global,
+                         p["gc"], p["gv"], p["cells"].reshape(nc, nv), p["x"].reshape(nvl, gdim), p["phi"], p["f"],
+                         p["row_mask"], p["cell_owned"])
+        return self
 
     # ---- tags --------------------------------------------------------------------------------------
     def classify(self, dls, ws, mark=None):

@@ -37,8 +37,13 @@ def main():
     single = len(sys.argv) > 4 and sys.argv[4] == "single"
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
-    gmesh, phi, f = global_problem(kind, n, single)
-    prob = partition.PartitionedProblem(gmesh, phi, f, rank, world, single_layer_cut=single)
+    if os.environ.get("PHIFEM_SCATTER") == "1":
+        # only rank 0 ever builds the global problem; the others receive their share
+        gmesh, phi, f = global_problem(kind, n, single) if rank == 0 else (None, None, None)
+        prob = partition.PartitionedProblem.scatter(gmesh, phi, f, rank, world, single_layer_cut=single, device="cpu")
+    else:
+        gmesh, phi, f = global_problem(kind, n, single)
+        prob = partition.PartitionedProblem(gmesh, phi, f, rank, world, single_layer_cut=single)
     m = prob.mesh
     x, cells = m.x.numpy(), np.ascontiguousarray(m.cells.numpy())
     c2f, f2c = np.ascontiguousarray(m.c2f.numpy()), np.ascontiguousarray(m.f2c.numpy())

@@ -17,14 +17,17 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 
 
-@pytest.mark.parametrize("kind,n,world,single", [("tri", 12, 2, False), ("tet", 5, 2, False), ("tet", 5, 3, False),
-                                                 ("tri", 12, 3, True), ("tet", 5, 2, True)])
-def test_partitioned_ranks_reproduce_the_single_domain_operator(tmp_path, kind, n, world, single):
+@pytest.mark.parametrize("kind,n,world,single,scatter", [
+    ("tri", 12, 2, False, False), ("tet", 5, 2, False, False), ("tet", 5, 3, False, True), ("tri", 12, 3, True, True),
+    ("tet", 8, 2, True, False)])
+def test_partitioned_ranks_reproduce_the_single_domain_operator(tmp_path, kind, n, world, single, scatter):
+    """scatter=True: rank 0 alone holds the global mesh, computes the partition once and sends the shares
+    (`PartitionedProblem.scatter`); otherwise every rank cuts its share from the global arrays."""
     port = _free_port()
     procs = []
     for rank in range(world):
         env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
-                   MASTER_PORT=str(port), OMP_NUM_THREADS="2")
+                   MASTER_PORT=str(port), OMP_NUM_THREADS="2", PHIFEM_SCATTER="1" if scatter else "0")
         procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "partition_worker.py"), kind, str(n),
                                        str(tmp_path)] + (["single"] if single else []), env=env))
     for p in procs:
