@@ -99,22 +99,21 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def algorithmic_bytes(counts):
-    """compulsory traffic, each input read once / each output written once."""
+def algorithmic_bytes(counts, tag_bytes=1):
+    """compulsory traffic, each input read once / each output written once.  tag_bytes: width of
+    the tag arrays the kernels WRITE (1: the int8 arrays of the product path; 4: SURVEY's yardstick, the int32 arrays of
+    the reference's MeshTags, which the product widens on demand and never writes in the timed region)."""
     nc, nv, nf, gdim, nvpc = counts["Nc"], counts["Nv"], counts["Nf"], counts["gdim"], counts["nvpc"]
     na, nva, ng, nnz = counts["Na"], counts["Nv_active"], counts["Ng"], counts["nnz"]
     nd, nrow = counts.get("nd", nvpc), counts.get("Nrow", nv)
     ndof_a = counts.get("Ndof_active", nva)          # active dofs of the trial/test space (= of phi and f)
-    # SURVEY.md section 8(d) as written: tags counted as the int32 arrays of the reference's MeshTags (4 Nc + 4 Nf).
-    # The kernels write them as one byte per entity and widen on demand, so their DRAM traffic (`roofline.traffic`,
-    # profiles/) is below this yardstick for the tag half.
-    b_tags_cells = 4 * nvpc * nc + 8 * nv + 4 * nc
-    b_tags_facets = 4 * nvpc * nc + 4 * nf            # c2f (== f2c in size) + facet tags out
+    b_tags_cells = 4 * nvpc * nc + 8 * nv + tag_bytes * nc
+    b_tags_facets = 4 * nvpc * nc + tag_bytes * nf    # c2f (== f2c in size) + facet tags out
     geo = 4 * nvpc * na if nd != nvpc else 0          # P2: cell -> vertex for the geometry besides the dofmap
-    b_asm = (4 * nd * na + geo + 8 * gdim * nva + 8 * ndof_a + 8 * ndof_a + 4 * na + 8 * ng + 12 * nnz
+    b_asm = (4 * nd * na + geo + 8 * gdim * nva + 8 * ndof_a + 8 * ndof_a + tag_bytes * na + 8 * ng + 12 * nnz
              + 4 * (nrow + 1) + 8 * nrow)
     # the numeric cell kernel alone: no column indices / indptr (they belong to the symbolic phase)
-    b_cells_kernel = 4 * nd * na + geo + 8 * gdim * nva + 16 * ndof_a + 4 * na + 8 * nnz + 8 * ndof_a
+    b_cells_kernel = 4 * nd * na + geo + 8 * gdim * nva + 16 * ndof_a + tag_bytes * na + 8 * nnz + 8 * ndof_a
     return {"tags_cells": b_tags_cells, "tags_facets": b_tags_facets, "assembly": b_asm,
             "cells_kernel": b_cells_kernel, "total": b_tags_cells + b_tags_facets + b_asm}
 
@@ -123,30 +122,46 @@ def algorithmic_bytes(counts):
 # CPU arm: the oracle port on the host cores (cpu_baseline of our line, and --impl reference)
 # ------------------------------------------------------------------------------------------------
 class CpuWorkload:
-    def __init__(self, n):
+    """Tags + CSR assembly on host arrays with the C/OpenMP oracle port (oracle/csrc/phifem_oracle.c).  The symbolic
+    phase (topology, pattern, slot maps) is SETUP, excluded from the timing like `symbolic_ms` of the GPU arm; it comes
+    either from torch ops on CPU tensors (`from_size`: no GPU needed, small n) or from the arrays an already-built
+    device plan holds (`from_device`: config E itself, n = 204)."""
+
+    def __init__(self, x, cells, c2f, f2c, phi, f, plan_arrays, nnz, label):
+        from oracle import native as ON
+        self.ON = ON
+        self.x, self.cells, self.c2f, self.f2c, self.phi, self.f = x, cells, c2f, f2c, phi, f
+        self.plan, self.nnz, self.num_cells, self.label = plan_arrays, nnz, len(cells), label
+
+    @classmethod
+    def from_size(cls, n):
         import torch
         from oracle import native as ON
+        from oracle import tags as OT
         from phifem_b200 import assemble, synthetic
         from phifem_b200.mesh import MeshTags
-        self.ON, self.n = ON, n
         mesh = synthetic.box_mesh(n, device="cpu")
-        self.x = mesh.x.numpy()
-        self.cells = np.ascontiguousarray(mesh.cells.numpy())
-        self.c2f = np.ascontiguousarray(mesh.c2f.numpy())
-        self.f2c = np.ascontiguousarray(mesh.f2c.numpy())
-        self.phi = synthetic.sphere_levelset(mesh.x).numpy()
-        self.f = synthetic.ball_source(mesh.x).numpy()
-        ct = ON.tag_cells_p1(self.x, self.cells, self.phi)
-        ft = ON.tag_facets_p1(self.x, self.cells, self.c2f, self.f2c, self.phi, ct)
-        # ds(100) entities + symbolic phase through the product's host plumbing on CPU tensors
-        from oracle import tags as OT
-        ents = OT.integration_entities(self.c2f, self.f2c, (ct == 1) | (ct == 2), ft == 4)
+        x = mesh.x.numpy()
+        cells = np.ascontiguousarray(mesh.cells.numpy())
+        c2f, f2c = np.ascontiguousarray(mesh.c2f.numpy()), np.ascontiguousarray(mesh.f2c.numpy())
+        phi = synthetic.sphere_levelset(mesh.x).numpy()
+        f = synthetic.ball_source(mesh.x).numpy()
+        ct = ON.tag_cells_p1(x, cells, phi)
+        ft = ON.tag_facets_p1(x, cells, c2f, f2c, phi, ct)
+        ents = OT.integration_entities(c2f, f2c, (ct == 1) | (ct == 2), ft == 4)
         plan = assemble.build_plan(mesh, MeshTags(mesh, 3, torch.from_numpy(ct)),
-                                   MeshTags(mesh, 2, torch.from_numpy(ft)), ents)
-        self.plan = {k: np.ascontiguousarray(getattr(plan, k).numpy())
-                     for k in ("active", "slots_cells", "entities", "slots_boundary", "ghost", "slots_ghost")}
-        self.nnz = plan.nnz
-        self.num_cells = mesh.num_cells
+                                   MeshTags(mesh, 2, torch.from_numpy(ft)), ents, method="atomic")
+        arrays = {k: np.ascontiguousarray(getattr(plan, k).numpy())
+                  for k in ("active", "slots_cells", "entities", "slots_boundary", "ghost", "slots_ghost")}
+        return cls(x, cells, c2f, f2c, phi, f, arrays, plan.nnz, "n=%d Kuhn unit cube" % n)
+
+    @classmethod
+    def from_device(cls, mesh, phi, f, plan, n):
+        arrays = {k: np.ascontiguousarray(getattr(plan, k).cpu().numpy())
+                  for k in ("active", "slots_cells", "entities", "slots_boundary", "ghost", "slots_ghost")}
+        host = lambda t: np.ascontiguousarray(t.cpu().numpy())     # noqa: E731
+        return cls(host(mesh.x), host(mesh.cells), host(mesh.c2f), host(mesh.f2c), host(phi), host(f), arrays,
+                   plan.nnz, "n=%d Kuhn unit cube" % n)
 
     def step(self):
         ON, p = self.ON, self.plan
@@ -156,20 +171,48 @@ class CpuWorkload:
                        p["slots_cells"], p["entities"], p["slots_boundary"], p["ghost"],
                        p["slots_ghost"], 1.0, self.nnz)
 
+    def measure(self, steps, warmup, one_core=True):
+        ON = self.ON
+        cores = ON.num_threads()
+        for _ in range(warmup):
+            self.step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            self.step()
+        dt = (time.perf_counter() - t0) / steps
+        res = {"value": self.num_cells / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%s (%d tetrahedra), sphere level set, tags + CSR assembly (symbolic phase excluded, as for "
+                         "the GPU arm), %d step(s), C/OpenMP oracle port; dolfinx/PETSc is not installable here"
+                         % (self.label, self.num_cells, steps),
+               "ms_per_step": dt * 1e3}
+        if one_core and cores > 1:
+            ON.set_num_threads(1)
+            t0 = time.perf_counter()
+            self.step()
+            res["one_core"] = {"value": self.num_cells / (time.perf_counter() - t0), "unit": UNIT, "cores": 1}
+            ON.set_num_threads(cores)
+        return res
 
-def cpu_measure(n, steps, warmup):
-    from oracle import native as ON
-    w = CpuWorkload(n)
-    for _ in range(warmup):
-        w.step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        w.step()
-    dt = (time.perf_counter() - t0) / steps
-    return {"value": w.num_cells / dt, "unit": UNIT, "cores": ON.num_threads(), "kind": "port",
-            "sample": "n=%d Kuhn unit cube (%d tetrahedra), sphere level set, tags + CSR assembly, "
-                      "C/OpenMP oracle port; dolfinx/PETSc is not installable here" % (n, w.num_cells),
-            "ms_per_step": dt * 1e3}
+
+def _device_setup_for_cpu(n):
+    """Config E's arrays and slot maps from the device-side symbolic phase (setup of the CPU arm when a GPU is present:
+    the torch-on-CPU plumbing would take minutes at 50.9 M cells).  Nothing of this is timed."""
+    import torch
+    from phifem_b200 import assemble, fem, mesh_scripts, synthetic
+    from phifem_b200.mesh import MeshTags
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    mesh = synthetic.box_mesh(n, device=dev)
+    phi, f = synthetic.sphere_levelset(mesh.x), synthetic.ball_source(mesh.x)
+    dls = mesh_scripts._DeviceLevelset(mesh, fem.Function(fem.functionspace_p1_device(mesh), phi), 1)
+    ws = mesh_scripts.classify(mesh, dls)
+    ents = mesh_scripts._integration_entities_dev(mesh, ws.cell_tags8, ws.facet_tags8, 4, (1, 2))
+    ct, ft = MeshTags(mesh, 3, None, tags8=ws.cell_tags8), MeshTags(mesh, 2, None, tags8=ws.facet_tags8)
+    plan = assemble.build_plan(mesh, ct, ft, ents, method="atomic")
+    w = CpuWorkload.from_device(mesh, phi, f, plan, n)
+    del mesh, plan, ws, dls
+    torch.cuda.empty_cache()
+    return w
 
 
 def run_reference(args):
@@ -180,14 +223,32 @@ def run_reference(args):
         # torchrun pins OMP_NUM_THREADS=1 for its workers; the CPU arm runs on rank 0 alone and uses every
         # host core (set before libgomp is loaded)
         os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-    res = cpu_measure(args.cpu_n, max(1, args.steps), max(1, args.warmup))
+    same_config = False
+    n = args.cpu_n
+    try:
+        import torch
+        if torch.cuda.is_available() and not args.cpu_sample:
+            w = _device_setup_for_cpu(args.n)       # the configuration of the GPU arm itself
+            n, same_config = args.n, True
+        else:
+            w = CpuWorkload.from_size(n)
+    except Exception as exc:                         # noqa: BLE001 -- e.g. out of host memory: fall back to the sample
+        sys.stderr.write("bench.py --impl reference: full-size setup failed (%s); bounded sample n=%d\n" % (exc, n))
+        w = CpuWorkload.from_size(n)
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    if same_config:          # ~0.5 s per step on 16+ threads: bound the run to about a minute
+        steps, warmup = min(steps, 20), min(warmup, 2)
+    res = w.measure(steps, warmup)
     line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": max(1, args.steps), "warmup": max(1, args.warmup), "ms_per_step": res["ms_per_step"],
+            "steps": steps, "warmup": warmup, "ms_per_step": res["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": "synthetic 3D P1 phi-FEM Poisson, Kuhn tetrahedra, sphere level set "
-                                   "(bounded sample n=%d of the n=%d configuration)" % (args.cpu_n, args.n)},
-            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "config": {"workload": (CONFIGS["3d-p1"][1] + ", tags + strong-Dirichlet CSR assembly") % (w.num_cells, n)
+                       if same_config else
+                       "synthetic 3D P1 phi-FEM Poisson, Kuhn tetrahedra, sphere level set "
+                       "(bounded sample n=%d of the n=%d configuration)" % (n, args.n),
+                       "name": "3d-p1", "same_config_as_gpu_arm": same_config},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "one_core") if k in res},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -196,11 +257,491 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+class Workload:
+    """One problem resident on one device: mesh, level set, source, tag workspace, assembly plan, outputs.  `step()` is
+    one pass of the hot path: cell tags, facet tags, assembly of the operator and the load vector."""
+
+    def __init__(self, mesh, phi, f, args, problem=None, degree=1, ls_kw=None, cell_pass=None):
+        import torch
+        from phifem_b200 import assemble, fem, mesh_scripts
+        from phifem_b200.mesh import MeshTags
+        self.mesh, self.phi, self.f, self.problem, self.args = mesh, phi, f, problem, args
+        self.torch, self.assemble_mod, self.ms = torch, assemble, mesh_scripts
+        dev = mesh.device
+        t0 = time.perf_counter()
+        mesh.c2f  # facet topology (mesh-level symbolic, once per mesh)
+        mesh.detj_bounds()
+        torch.cuda.synchronize()
+        self.topology_s = time.perf_counter() - t0
+        self.phi_asm, self.f_asm = phi, f
+        self.V = fem.functionspace_p1_device(mesh)
+        fn = fem.Function(self.V, phi)
+        if args.detection_degree > 1 and problem is None:
+            from phifem_b200 import synthetic
+            Vd = fem.functionspace(mesh, args.detection_degree)
+            phi_det = synthetic.sphere_levelset(Vd.dof_coordinates_dev(), **(ls_kw or {}))
+            self.dls = mesh_scripts._DeviceLevelset(mesh, fem.Function(Vd, phi_det), args.detection_degree)
+        else:
+            self.dls = mesh_scripts._DeviceLevelset(mesh, fn, 1)
+        self.ws = mesh_scripts.TagWorkspace(mesh)
+        if problem is not None:
+            problem.classify(self.dls, self.ws)
+        else:
+            mesh_scripts.classify(mesh, self.dls, ws=self.ws)
+        torch.cuda.synchronize()
+        self.counters = self.ws.counters.cpu().numpy()
+        t0 = time.perf_counter()
+        tdim = mesh.topology.dim
+        ws = self.ws
+        if problem is not None:
+            self.plan = problem.build_plan(ws.cell_tags8, ws.facet_tags8)
+            if getattr(problem, "mode", "rows") == "exchange":
+                self.plan.method, self.plan.blocked, self.plan.rowsplan = "atomic", None, None
+            self.data, self.b = problem.data, problem.b_local
+        else:
+            ctags, ftags = MeshTags(mesh, tdim, None, tags8=ws.cell_tags8), MeshTags(mesh, tdim - 1, None,
+                                                                                      tags8=ws.facet_tags8)
+            ents = mesh_scripts._integration_entities_dev(mesh, ws.cell_tags8, ws.facet_tags8, 4, (1, 2))
+            if degree == 2:
+                # P2 trial/test space and P2 level set: phi_h / f_h = interpolants at the P2 nodes (main.py:85-90)
+                from phifem_b200 import synthetic
+                Vw = fem.functionspace(mesh, 2)
+                Xd = Vw.dof_coordinates_dev()
+                self.phi_asm = synthetic.sphere_levelset(Xd, **(ls_kw or {}))
+                self.f_asm = synthetic.ball_source(Xd, **({"center": DISC_CENTER} if ls_kw else {}))
+                del Xd
+                self.plan = assemble.build_plan(mesh, ctags, ftags, ents, V=Vw, V_phi=Vw)
+            else:
+                self.plan = assemble.build_plan(mesh, ctags, ftags, ents, method=args.scatter, capacity=args.capacity,
+                                                order=args.order, geometry=args.geometry,
+                                                cell_pass=cell_pass or args.cell_pass,
+                                                rows_per_tile=args.rows_per_tile)
+            self.data, self.b = self.plan.new_outputs()
+        torch.cuda.synchronize()
+        self.symbolic_first_call_ms = (time.perf_counter() - t0) * 1e3
+        self.symbolic_ms = self.symbolic_first_call_ms
+        if problem is None and degree == 1 and getattr(self.plan, "method", "") == "rows" and not args.no_replan:
+            # the first call of a process also grows the scratch pool and the allocator by several GB (driver work, paid
+            # once); what a time-stepping code pays whenever the cut pattern changes is the RE-plan: timed here
+            times = []
+            for _ in range(2):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                again = assemble.build_plan(mesh, ctags, ftags, ents, method=args.scatter, capacity=args.capacity,
+                                            order=args.order, geometry=args.geometry,
+                                            cell_pass=cell_pass or args.cell_pass, rows_per_tile=args.rows_per_tile)
+                torch.cuda.synchronize()
+                times.append((time.perf_counter() - t0) * 1e3)
+                del again
+            self.symbolic_ms = min(times)
+        self.graph = None
+
+    def step(self, events=None, split=False):
+        """events: CUDA events recorded at the phase boundaries.  split=True (the untimed breakdown loop) runs the
+        assembly pass by pass so that events separate its kernels."""
+        k = 0
+
+        def mark():
+            nonlocal k
+            if events is not None:
+                events[k].record()
+                k += 1
+        mark()
+        if self.problem is not None:   # the all-reduce of "any exterior cell" overlaps the interior-facet kernel
+            self.problem.classify(self.dls, self.ws, mark=mark)
+            self.problem.assemble(1.0, marks=mark if split else None)
+        else:
+            self.ms.classify_cells(self.mesh, self.dls, self.ws)
+            mark()
+            self.ms.classify_facets(self.mesh, self.dls, self.ws)
+            mark()
+            self.assemble_mod.assemble_into(self.plan, self.phi_asm, self.f_asm, 1.0, self.data, self.b,
+                                            marks=mark if split else None)
+        mark()
+
+    def capture(self):
+        """The step as ONE CUDA graph (tag kernels, the all-reduce of a sharded run, assembly kernels with their
+        side-stream forks): a strong-scaled rank has ~0.3 ms of kernels per step, less than the host needs to issue
+        them one by one."""
+        torch = self.torch
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self.step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.step()
+        torch.cuda.synchronize()
+        self.graph = g
+
+    def run(self, events=None):
+        if self.graph is not None and events is None:
+            self.graph.replay()
+        else:
+            self.step(events)
+
+    def kernel_launches_per_step(self):
+        """Kernels of libphifem_b200.so launched by one step, COUNTED with the profiler (CUPTI) on one untimed step."""
+        torch = self.torch
+        try:
+            from torch.profiler import ProfilerActivity, profile
+            torch.cuda.synchronize()
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                self.step()
+                torch.cuda.synchronize()
+            names = [e.name for e in prof.events() if getattr(e, "device_type", None) is not None
+                     and "cuda" in str(e.device_type).lower()]
+            import re
+            ours = [m.group(0) for m in (re.search(r"\bk_\w+", n) for n in names if "phifem" in n) if m]
+            if ours:
+                return len(ours), sorted(set(ours))
+        except Exception as exc:   # noqa: BLE001
+            sys.stderr.write("bench.py: kernel count through the profiler failed (%s)\n" % exc)
+        return None, None
+
+    def counts(self):
+        torch, mesh, plan = self.torch, self.mesh, self.plan
+        act_v = torch.zeros(mesh.num_vertices, dtype=torch.bool, device=mesh.device)
+        act_v[mesh.cells[plan.active.long()].long().reshape(-1)] = True
+        c = self.counters
+        return {"Nc": mesh.num_cells, "Nv": mesh.num_vertices, "Nf": mesh.num_facets, "gdim": mesh.gdim,
+                "nvpc": mesh.cells.shape[1], "Na": int(plan.active.numel()), "Ng": int(plan.ghost.numel()),
+                "Nv_active": int(act_v.sum()), "nnz": plan.nnz, "Nrow": plan.n_rows,
+                "nd": getattr(plan, "nd", mesh.cells.shape[1]),
+                "Ndof_active": int((plan.indptr[1:] > plan.indptr[:-1]).sum()),
+                "Ne_ds100": int(plan.entities.shape[0]),
+                "halo_entries_sent": (sum(hi - lo for lo, hi in getattr(plan, "send_ranges", []))
+                                      if self.problem is not None else 0),
+                "interior": int(c[0]), "cut": int(c[1]), "exterior": int(c[2])}
+
+
+def timed_steps(w, steps, world, sampler=None, presteps=15):
+    """EXACTLY `steps` steps bracketed by barrier + synchronize, device-timed, max over ranks; per-phase means from the
+    events recorded inside the timed region (eager runs) and the assembly split from a short untimed loop."""
+    import torch
+    import torch.distributed as dist
+    dev = w.mesh.device
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if sampler is not None:
+        sampler.start()
+    # an NVML query takes milliseconds, a step two: keep the device under the same load for a fixed number of
+    # untimed steps (the same on every rank: a step holds a collective) so that the sampler has seen it, then time
+    # exactly `steps` steps with the sampler still running
+    for _ in range(presteps):
+        w.run()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(steps):
+        w.run(None if w.graph is not None else evs[i])
+    stop.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if sampler is not None else None
+    total_ms = start.elapsed_time(stop)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    n_split = 5
+    evs2 = [[torch.cuda.Event(enable_timing=True) for _ in range(8)] for _ in range(n_split)]
+    for i in range(n_split):
+        w.step(evs2[i], split=True)
+    torch.cuda.synchronize()
+    names = ["tag_cells", "tag_facets", "zero", "assemble_cells", "assemble_boundary", "assemble_ghost", "exchange"]
+    src = evs2 if w.graph is not None else None
+    per = {}
+    for j, nm in enumerate(["tag_cells", "tag_facets", "assembly"]):
+        if src is None:
+            per[nm] = statistics.mean(evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(steps))
+        elif nm != "assembly":
+            per[nm] = statistics.mean(evs2[i][j].elapsed_time(evs2[i][j + 1]) for i in range(n_split))
+        else:
+            per[nm] = statistics.mean(evs2[i][2].elapsed_time(evs2[i][7]) for i in range(n_split))
+    for j, nm in enumerate(names):
+        if j >= 2:
+            per[nm] = statistics.mean(evs2[i][j].elapsed_time(evs2[i][j + 1]) for i in range(n_split))
+    if w.plan.method == "rows":
+        per["assemble_surface"] = per.pop("assemble_ghost")      # ghost penalty + one-sided term, one pass
+        per.pop("assemble_boundary")
+    return total_ms / steps, per, clocks
+
+
+def roofline_of(w, per, ms_per_step, clocks):
+    ab = algorithmic_bytes(w.counts())
+    ab_survey = algorithmic_bytes(w.counts(), tag_bytes=4)
+    plan = w.plan
+    peak, peak_src = _peaks()
+    dominant = max(("tag_cells", "tag_facets", "assemble_cells"), key=lambda k_: per[k_])
+    # the row-gather kernel is the whole assembly (cells + ghost + one-sided terms, pattern read, CSR
+    # values and b written): SURVEY.md 8(d) B_asm; the atomic cell kernel alone moves less
+    asm_bytes = ab["assembly"] if plan.method in ("rows", "blocked") else ab["cells_kernel"]
+    kbytes = {"tag_cells": ab["tags_cells"], "tag_facets": ab["tags_facets"], "assemble_cells": asm_bytes}[dominant]
+    achieved = kbytes / (per[dominant] * 1e-3) / 1e9
+    tiles = plan.rowsplan.tiles if plan.method == "rows" else None
+    kernel_names = {"tag_cells": "k_tag_cells_p1", "tag_facets": "k_tag_facets",
+                    "assemble_cells": {"rows": "k_assemble_tiles_p1" if tiles is not None else "k_assemble_rows_p1",
+                                       "blocked": "k_assemble_blocked_p1", "atomic": "k_assemble_cells_p1",
+                                       "pk-atomic": "k_assemble_cells_pk"}[plan.method]}
+    roofline = {"bound": "hbm", "kernel": kernel_names[dominant], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": kbytes,
+                "algorithmic_bytes": "SURVEY.md 8(d) with the tag arrays at the ONE byte per entity the kernels write "
+                                     "(int32 MeshTags are widened on demand outside the timed region); "
+                                     "`step_frac_survey_int32_tags` keeps the survey's 4-byte yardstick for comparison "
+                                     "with round 1",
+                "step_bytes": ab["total"],
+                "step_achieved_gbs": ab["total"] / (ms_per_step * 1e-3) / 1e9,
+                "step_frac": ab["total"] / (ms_per_step * 1e-3) / 1e9 / peak,
+                "step_frac_survey_int32_tags": ab_survey["total"] / (ms_per_step * 1e-3) / 1e9 / peak,
+                "kernels_ms": per,
+                "kernels_gbs": {"tag_cells": ab["tags_cells"] / per["tag_cells"] / 1e6,
+                                "tag_facets": ab["tags_facets"] / per["tag_facets"] / 1e6,
+                                "assemble_cells": asm_bytes / per["assemble_cells"] / 1e6}}
+    if plan.method == "rows" and w.mesh.gdim == 3:
+        # the cell pass is bound by fp64 issue, not by HBM: 146 fp64 instructions per (row, cell) record (SASS
+        # count of cell_row<3>, DESIGN.md section 4) against 64 fp64 lanes per clock per SM; 85 with the cached cell
+        # geometry (cell_row_geom<3>); ~200 per cell evaluation of the cell-once pass
+        per_record = 200 if tiles is not None else (85 if plan.rowsplan.cell_geom is not None else 146)
+        n_eval = tiles.n_cell_slots if tiles is not None else plan.rowsplan.cells.n_records
+        lanes = n_eval * float(per_record)
+        peak_lanes = 148 * 64 * ((clocks or {}).get("sm_max_mhz") or 1965) * 1e6
+        roofline["fp64_issue"] = {"kernel": kernel_names["assemble_cells"], "fp64_instructions_per_record": per_record,
+                                  "records": n_eval,
+                                  "achieved_tera_lane_instr_per_s": lanes / (per["assemble_cells"] * 1e-3) / 1e12,
+                                  "peak_tera_lane_instr_per_s": peak_lanes / 1e12,
+                                  "frac": lanes / (per["assemble_cells"] * 1e-3) / peak_lanes}
+    return roofline, ab, dominant
+
+
+def scatter_info(plan):
+    out = {"method": plan.method}
+    if getattr(plan, "blocked", None):
+        out.update({"blocks": plan.blocked.n_blocks, "capacity": plan.blocked.capacity,
+                    "bin_shape": plan.blocked.bin_shape, "recompute_factor": plan.blocked.redundancy,
+                    "plan_bytes": plan.blocked.index_bytes()})
+    rp = getattr(plan, "rowsplan", None)
+    if rp:
+        out.update({"order": rp.order, "max_row_nnz": rp.max_row_nnz, "cell_pass": rp.cell_pass})
+        if rp.tiles is not None:
+            out.update({"rows_per_tile": rp.tiles.rows_per_tile, "tiles": rp.tiles.n_tiles, "chunks": rp.tiles.n_chunks,
+                        "cell_evaluations": rp.tiles.n_cell_slots, "recompute_factor": rp.tiles.recompute})
+        out.update({"rows_cells_surface": [rp.tiles.n_listed if rp.tiles is not None else rp.cells.n_listed,
+                                           rp.surface.n_listed],
+                    "records_cells_ghost_onesided": [rp.n_cell_records, rp.n_ghost_records, rp.n_entity_records],
+                    "lane_padding": [rp.cells.padding(), rp.surface.padding()],
+                    "cell_geometry": "cached per plan (64 B per active cell)" if rp.cell_geom is not None
+                    else "from the vertex coordinates",
+                    "plan_bytes": rp.index_bytes()})
+    return out
+
+
+def measure_e2e(w, args, degree):
+    """Public API, pinned host buffers in, pinned host buffers out."""
+    import warnings
+
+    import torch
+    from phifem_b200 import assemble, fem, mesh_scripts
+    mesh, plan, dev = w.mesh, w.plan, w.mesh.device
+    phi_h = w.phi.cpu().pin_memory()
+    f_h = w.f_asm.cpu().pin_memory()
+    phi_asm_h = w.phi_asm.cpu().pin_memory() if degree == 2 else phi_h
+    out_h = {"ct": torch.empty(mesh.num_cells, dtype=torch.int8).pin_memory(),
+             "ft": torch.empty(mesh.num_facets, dtype=torch.int8).pin_memory(),
+             "data": torch.empty(plan.nnz, dtype=torch.float64).pin_memory(),
+             "b": torch.empty(plan.n_rows, dtype=torch.float64).pin_memory()}
+    side = torch.cuda.Stream()
+    tags_done = torch.cuda.Event()
+    f_done = torch.cuda.Event()
+
+    def e2e_step():
+        # host level set -> device once; the same device-resident Function feeds the tags and (for P1) the
+        # assembly, as a user holding one phi_h would write it
+        phi_d = phi_h.to(dev, non_blocking=True)
+        # the source term follows the level set over PCIe on the side stream while the tag kernels run
+        with torch.cuda.stream(side):
+            f_d = f_h.to(dev, non_blocking=True)
+            f_done.record()
+        fn_h = fem.Function(w.V, phi_d)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            ct_, ft_, _, ds_, _ = mesh_scripts.compute_tags_measures(mesh, fn_h, 1, box_mode=True)
+        # the tags (one byte per entity, as the kernels write them; MeshTags widens to int32 on the host)
+        # leave on a side stream while the assembly runs
+        tags_done.record()
+        with torch.cuda.stream(side):
+            side.wait_event(tags_done)
+            out_h["ct"].copy_(ct_.tags8, non_blocking=True)
+            out_h["ft"].copy_(ft_.tags8, non_blocking=True)
+        torch.cuda.current_stream().wait_event(f_done)
+        A_, b_ = assemble.assemble_strong_dirichlet(plan, phi_d if degree == 1 else phi_asm_h, f_d, stab_coef=1.0)
+        f_d.record_stream(torch.cuda.current_stream())
+        out_h["data"].copy_(A_.data, non_blocking=True)
+        out_h["b"].copy_(b_, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(2):
+        e2e_step()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    dt = (time.perf_counter() - t0) / e2e_steps
+    return {"value": mesh.num_cells / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
+            "h2d_bytes_per_step": int(phi_h.numel() * 8 + (phi_asm_h.numel() * 8 if degree == 2 else 0)
+                                      + f_h.numel() * 8),
+            "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in out_h.values())),
+            "api": "compute_tags_measures(box_mode=True) + assemble_strong_dirichlet(plan, ...) with "
+                   "pinned host level set / source in and pinned host tags (1 byte per cell / facet) + CSR values "
+                   "+ b out, source-term upload overlapped with the tag kernels, tag copies with the assembly; "
+                   "assembly plan (symbolic phase) reused; one step at a time"}
+
+
+def time_to_solution(w):
+    """tags + assembly + the solve that follows them in the demos (reference
+    demo/strong-dirichlet/flower/main.py:138-157 hands the system to MUMPS), here Jacobi-BiCGStab on the CSR operator
+    in HBM.  One run, wall clock with synchronisation on both sides."""
+    import torch
+    from phifem_b200 import solve
+    from phifem_b200.assemble import CSRMatrix
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    w.step()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    A = CSRMatrix(w.plan.indptr, w.plan.indices, w.data, (w.plan.n_rows, w.plan.n_rows))
+    x, info = solve.bicgstab(A, w.b, rtol=1e-8, maxiter=4000)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    return {"total_ms": (t2 - t0) * 1e3, "tags_and_assembly_ms": (t1 - t0) * 1e3, "solve_ms": (t2 - t1) * 1e3,
+            "solver": "Jacobi-BiCGStab, rtol 1e-8 (phifem_b200/solve.py, SpMV kernel csrc/solve.cu)",
+            "iterations": info.iterations, "residual": info.residual, "converged": bool(info.converged),
+            "unknowns": info.n_active}
+
+
+def multi_gpu_parity(dev, rank, world, n=12):
+    """A small problem through the SAME sharded code path (scatter from rank 0, sharded tags with the all-reduce,
+    owner-computes assembly), merged on rank 0 and compared BITWISE with rank 0's single-GPU operator."""
+    import torch
+    import torch.distributed as dist
+    from phifem_b200 import assemble, fem, mesh_scripts, partition, synthetic
+    from phifem_b200.mesh import MeshTags
+    ref = None
+    gmesh = gphi = gf = None
+    if rank == 0:
+        gmesh = synthetic.box_mesh(n, device=dev)
+        gphi = synthetic.sphere_levelset(gmesh.x, radius=0.37)
+        gf = torch.from_numpy(np.random.default_rng(7).uniform(-1, 1, gmesh.num_vertices)).to(dev)
+        dls = mesh_scripts._DeviceLevelset(gmesh, fem.Function(fem.functionspace_p1_device(gmesh), gphi), 1)
+        ws = mesh_scripts.classify(gmesh, dls)
+        ents = mesh_scripts._integration_entities_dev(gmesh, ws.cell_tags8, ws.facet_tags8, 4, (1, 2))
+        plan = assemble.build_plan(gmesh, MeshTags(gmesh, 3, None, tags8=ws.cell_tags8),
+                                   MeshTags(gmesh, 2, None, tags8=ws.facet_tags8), ents)
+        data, b = plan.new_outputs()
+        assemble.assemble_into(plan, gphi, gf, 1.0, data, b)
+        ref = (plan.indptr.cpu().numpy(), plan.indices.cpu().numpy(), data.cpu().numpy(), b.cpu().numpy(),
+               ws.cell_tags8.cpu().numpy())
+    prob = partition.PartitionedProblem.scatter(gmesh, gphi, gf, rank, world, device=dev)
+    dls = mesh_scripts._DeviceLevelset(prob.mesh, fem.Function(fem.functionspace_p1_device(prob.mesh), prob.phi), 1)
+    ws = mesh_scripts.TagWorkspace(prob.mesh)
+    prob.classify(dls, ws)
+    prob.build_plan(ws.cell_tags8, ws.facet_tags8)
+    prob.assemble(1.0)
+    rows, indptr, cols, data, b = (t.cpu().numpy() for t in prob.owned_csr())
+    mine = (rows, indptr, cols, data, b, prob.global_cell[prob.cell_owned].cpu().numpy(),
+            ws.cell_tags8[prob.cell_owned].cpu().numpy())
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    ok = None
+    if rank == 0:
+        ip, ix, dd, bb, ct = ref
+        seen = np.zeros(len(bb), dtype=np.int64)
+        seen_c = np.zeros(len(ct), dtype=np.int64)
+        ok = True
+        for rows, indptr, cols, data, b, cells_owned, tags in parts:
+            seen[rows] += 1
+            seen_c[cells_owned] += 1
+            ok &= bool(np.array_equal(tags, ct[cells_owned]))
+            ok &= bool(np.array_equal(np.diff(indptr), ip[rows + 1] - ip[rows]))
+            if not ok:
+                break
+            sl = np.concatenate([np.arange(ip[r], ip[r + 1]) for r in rows]) if len(rows) else np.zeros(0, dtype=np.int64)
+            ok &= bool(np.array_equal(cols, ix[sl]) and np.array_equal(data, dd[sl]) and np.array_equal(b, bb[rows]))
+        ok &= bool(np.all(seen == 1) and np.all(seen_c == 1))
+    flag = torch.tensor([1 if (ok or ok is None) else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(flag.item())
+
+
+def strong_scaling(args, dev, rank, world):
+    """Config E itself -- ONE 6 n^3-tetrahedra mesh -- cut along the Morton curve into `world` ranges of equal WEIGHT
+    (exterior 1, interior 3, cut 10: SURVEY.md 8e), partition computed once on rank 0 and scattered; every rank
+    classifies its share (redundant halo included) and assembles the rows it owns; the step is one CUDA graph."""
+    import torch
+    import torch.distributed as dist
+    from phifem_b200 import partition, synthetic
+    t0 = time.perf_counter()
+    gmesh = gphi = gf = weights = None
+    n_cells = 6 * args.n ** 3
+    if rank == 0:
+        gmesh = synthetic.box_mesh(args.n, device=dev)
+        gphi, gf = synthetic.sphere_levelset(gmesh.x), synthetic.ball_source(gmesh.x)
+        neg = (gphi < 0)[gmesh.cells.long()]
+        inside, outside = neg.all(dim=1), (~neg).all(dim=1)
+        weights = torch.where(inside, 3.0, torch.where(outside, 1.0, 10.0)).to(torch.float64)
+        del neg, inside, outside
+    prob = partition.PartitionedProblem.scatter(gmesh, gphi, gf, rank, world, weights=weights, device=dev)
+    del gmesh, gphi, gf, weights
+    torch.cuda.empty_cache()
+    torch.cuda.synchronize()
+    scatter_s = time.perf_counter() - t0
+    w = Workload(prob.mesh, prob.phi, prob.f, args, problem=prob)
+    graph = False
+    if not args.no_graph:
+        try:
+            w.capture()
+            graph = True
+        except Exception as exc:   # noqa: BLE001
+            sys.stderr.write("bench.py: CUDA-graph capture of the sharded step failed (%s); eager launches\n" % exc)
+            w.graph = None
+    graph_all = torch.tensor([1 if graph else 0], device=dev)
+    dist.all_reduce(graph_all, op=dist.ReduceOp.MIN)
+    if not bool(graph_all.item()):
+        w.graph, graph = None, False
+    ms, per, _ = timed_steps(w, args.steps, world, presteps=5)
+    stats = torch.tensor([prob.mesh.num_cells, prob.n_owned_cells, w.symbolic_ms, w.topology_s * 1e3,
+                          per["tag_cells"] + per["tag_facets"], per["assembly"]], dtype=torch.float64, device=dev)
+    allst = [torch.empty_like(stats) for _ in range(world)]
+    dist.all_gather(allst, stats)
+    allst = torch.stack(allst).cpu().numpy()
+    owned_total = int(allst[:, 1].sum())
+    assert owned_total == n_cells, "the ranks' owned cells do not partition the mesh"
+    return {"n_gpus": world, "cells_total": n_cells, "ms_per_step": ms, "value": n_cells / (ms * 1e-3), "unit": UNIT,
+            "cuda_graph": graph, "scatter_s": scatter_s,
+            "partition": "Morton curve of the cell centroids, ranges of equal weight (exterior 1 / interior 3 / cut 10), "
+                         "computed once on rank 0 and scattered; rows owned by the lowest rank touching them; "
+                         "redundantly classified halo (cells sharing a vertex with a cell touching an owned row); one "
+                         "8-byte all-reduce per step, no halo exchange",
+            "local_cells": [int(v) for v in allst[:, 0]], "owned_cells": [int(v) for v in allst[:, 1]],
+            "symbolic_ms_max": float(allst[:, 2].max()), "topology_ms_max": float(allst[:, 3].max()),
+            "tags_ms": [float(v) for v in allst[:, 4]], "assembly_ms": [float(v) for v in allst[:, 5]]}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from phifem_b200 import assemble, fem, mesh_scripts, synthetic
+    from phifem_b200 import synthetic
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -214,21 +755,19 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.n
+    degree = 2 if args.config.endswith("p2") else 1
+    ls_kw = {}
     reorder_ms = None
-    t_setup = time.perf_counter()
-    if world > 1:
-        from phifem_b200 import dist as pdist
-        problem = pdist.SlabProblem(n, rank, world, dev, mode=args.dist_mode)
-        mesh, phi, f = problem.mesh, problem.phi, problem.f
-    else:
-        problem = None
+    problem = None
+
+    def make_mesh(kind):
+        nonlocal reorder_ms
         if args.config.startswith("2d"):
             mesh = synthetic.rectangle_mesh(n, device=dev)
-            ls_kw = dict(center=DISC_CENTER, radius=DISC_RADIUS)
+            ls_kw.update(center=DISC_CENTER, radius=DISC_RADIUS)
         else:
             mesh = synthetic.box_mesh(n, device=dev)
-            ls_kw = {}
-        if args.mesh == "unstructured":
+        if kind == "unstructured":
             # vertex jitter +-0.2 h (seed 0), random cell permutation (seed 1), random vertex
             # relabelling (seed 2); then -- as part of the mesh-level symbolic phase, like dolfinx's own reordering at
             # mesh creation -- renumbered along the Morton curve.  Level set and source are interpolated on THAT mesh.
@@ -241,134 +780,28 @@ def run_ours(args):
             reorder_ms = (time.perf_counter() - t_re) * 1e3
         phi = synthetic.sphere_levelset(mesh.x, **ls_kw)
         f = synthetic.ball_source(mesh.x, **({"center": DISC_CENTER} if ls_kw else {}))
-    mesh.c2f  # build the facet topology (mesh-level symbolic, once per mesh)
-    mesh.detj_bounds()
-    torch.cuda.synchronize()
-    topo_s = time.perf_counter() - t_setup
+        return mesh, phi, f
 
-    degree = 2 if args.config.endswith("p2") else 1
-    phi_asm, f_asm = phi, f
-    V = fem.functionspace_p1_device(mesh)
-    fn = fem.Function(V, phi)
-    if args.detection_degree > 1:
-        # tags from a P_k level set with detection_degree k (the generic table-driven classifier) instead of
-        # the demos' P1 detection level set
-        Vd = fem.functionspace(mesh, args.detection_degree)
-        phi_det = synthetic.sphere_levelset(Vd.dof_coordinates_dev(), **ls_kw)
-        dls = mesh_scripts._DeviceLevelset(mesh, fem.Function(Vd, phi_det), args.detection_degree)
+    parity_ok = strong = None
+    if world > 1:
+        from phifem_b200 import dist as pdist
+        if not args.no_parity:
+            parity_ok = multi_gpu_parity(dev, rank, world)
+        if args.scaling == "strong" or not args.no_strong:
+            strong = strong_scaling(args, dev, rank, world)
+            torch.cuda.empty_cache()
+        problem = pdist.SlabProblem(n, rank, world, dev, mode=args.dist_mode)
+        mesh, phi, f = problem.mesh, problem.phi, problem.f
     else:
-        dls = mesh_scripts._DeviceLevelset(mesh, fn, 1)
-    ws = mesh_scripts.TagWorkspace(mesh)
-    if problem is not None:
-        problem.classify(dls, ws)
-    else:
-        mesh_scripts.classify(mesh, dls, ws=ws)
-    torch.cuda.synchronize()
-    counters = ws.counters.cpu().numpy()
-
-    t0 = time.perf_counter()
-    tdim = mesh.topology.dim
-    from phifem_b200.mesh import MeshTags
-    if problem is not None:
-        plan = problem.build_plan(ws.cell_tags8, ws.facet_tags8)
-        if args.dist_mode == "exchange":
-            plan.method, plan.blocked, plan.rowsplan = "atomic", None, None
-        data, b = problem.data, problem.b_local
-    else:
-        ctags, ftags = MeshTags(mesh, tdim, ws.cell_tags), MeshTags(mesh, tdim - 1, ws.facet_tags)
-        ctags.tags8, ftags.tags8 = ws.cell_tags8, ws.facet_tags8
-        ents = mesh_scripts._integration_entities_dev(mesh, ws.cell_tags8, ws.facet_tags8, 4, (1, 2))
-        if degree == 2:
-            # P2 trial/test space and P2 level set: phi_h / f_h = interpolants at the P2 nodes (main.py:85-90)
-            Vw = fem.functionspace(mesh, 2)
-            Xd = Vw.dof_coordinates_dev()
-            phi_asm = synthetic.sphere_levelset(Xd, **ls_kw)
-            f_asm = synthetic.ball_source(Xd, **({"center": DISC_CENTER} if ls_kw else {}))
-            del Xd
-            plan = assemble.build_plan(mesh, ctags, ftags, ents, V=Vw, V_phi=Vw)
-        else:
-            plan = assemble.build_plan(mesh, ctags, ftags, ents, method=args.scatter, capacity=args.capacity,
-                                       order=args.order, geometry=args.geometry, cell_pass=args.cell_pass,
-                                       rows_per_tile=args.rows_per_tile)
-        data, b = plan.new_outputs()
-    torch.cuda.synchronize()
-    symbolic_ms = (time.perf_counter() - t0) * 1e3
-
-    def step(events=None, split=False):
-        """One pass of the hot path.  events: CUDA events recorded at the phase boundaries.  split=True (the
-        untimed breakdown loop) runs the assembly pass by pass so that events separate its kernels."""
-        k = 0
-
-        def mark():
-            nonlocal k
-            if events is not None:
-                events[k].record()
-                k += 1
-        mark()
-        if problem is not None:   # the all-reduce of "any exterior cell" overlaps the interior-facet kernel
-            problem.classify(dls, ws, mark=mark)
-        else:
-            mesh_scripts.classify_cells(mesh, dls, ws)
-            mark()
-            mesh_scripts.classify_facets(mesh, dls, ws)
-            mark()
-        if problem is not None:
-            problem.assemble(1.0, marks=mark if split else None)
-        else:
-            assemble.assemble_into(plan, phi_asm, f_asm, 1.0, data, b, marks=mark if split else None)
-        mark()
+        mesh, phi, f = make_mesh(args.mesh)
+    w = Workload(mesh, phi, f, args, problem=problem, degree=degree, ls_kw=ls_kw)
+    plan = w.plan
+    _sym = (w.symbolic_ms, w.topology_s, w.symbolic_first_call_ms, getattr(plan, "symbolic", None))
 
     for _ in range(args.warmup):
-        step()
+        w.step()
     torch.cuda.synchronize()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
-    sampler = ClockSampler(local_rank)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler.start()
-    # an NVML query takes milliseconds, a step two: keep the device under the same load for a fixed number of
-    # untimed steps (the same on every rank: a step holds a collective) so that the sampler has seen it, then time
-    # exactly `steps` steps with the sampler still running
-    for _ in range(15):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    start.record()
-    for i in range(args.steps):
-        step(evs[i])
-    stop.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    clocks = sampler.stop()
-    total_ms = start.elapsed_time(stop)
-    if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-
-    # phase durations from the events recorded inside the timed region (the assembly is ONE call there: its
-    # facet-once kernel overlaps the cell pass on a side stream) ...
-    per = {nm: statistics.mean(evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(args.steps))
-           for j, nm in enumerate(["tag_cells", "tag_facets", "assembly"])}
-    # ... and the assembly pass by pass from a short untimed loop
-    n_split = 5
-    evs2 = [[torch.cuda.Event(enable_timing=True) for _ in range(8)] for _ in range(n_split)]
-    for i in range(n_split):
-        step(evs2[i], split=True)
-    torch.cuda.synchronize()
-    names = ["tag_cells", "tag_facets", "zero", "assemble_cells", "assemble_boundary", "assemble_ghost", "exchange"]
-    for j, nm in enumerate(names):
-        if j >= 2:
-            per[nm] = statistics.mean(evs2[i][j].elapsed_time(evs2[i][j + 1]) for i in range(n_split))
-    if plan.method == "rows":
-        per["assemble_surface"] = per.pop("assemble_ghost")      # ghost penalty + one-sided term, one pass
-        per.pop("assemble_boundary")
+    ms_per_step, per, clocks = timed_steps(w, args.steps, world, sampler=ClockSampler(local_rank))
 
     n_cells_local = problem.n_owned_cells if problem is not None else mesh.num_cells
     n_cells_total = n_cells_local
@@ -377,185 +810,61 @@ def run_ours(args):
         dist.all_reduce(t)
         n_cells_total = int(t.item())
     value = n_cells_total / (ms_per_step * 1e-3)
-
-    act_v = torch.zeros(mesh.num_vertices, dtype=torch.bool, device=dev)
-    act_v[mesh.cells[plan.active.long()].long().reshape(-1)] = True
-    counts = {"Nc": mesh.num_cells, "Nv": mesh.num_vertices, "Nf": mesh.num_facets, "gdim": mesh.gdim,
-              "nvpc": mesh.cells.shape[1], "Na": int(plan.active.numel()), "Ng": int(plan.ghost.numel()),
-              "Nv_active": int(act_v.sum()), "nnz": plan.nnz, "Nrow": plan.n_rows,
-              "nd": getattr(plan, "nd", mesh.cells.shape[1]),
-              "Ndof_active": int((plan.indptr[1:] > plan.indptr[:-1]).sum()),
-              "Ne_ds100": int(plan.entities.shape[0]),
-              "halo_entries_sent": (sum(hi - lo for lo, hi in plan.send_ranges) if problem is not None else 0),
-              "interior": int(counters[0]), "cut": int(counters[1]), "exterior": int(counters[2])}
-    ab = algorithmic_bytes(counts)
-    peak, peak_src = _peaks()
-    dominant = max(("tag_cells", "tag_facets", "assemble_cells"), key=lambda k_: per[k_])
-    # the row-gather kernel is the whole assembly (cells + ghost + one-sided terms, pattern read, CSR
-    # values and b written): SURVEY.md 8(d) B_asm; the atomic cell kernel alone moves less
-    asm_bytes = ab["assembly"] if plan.method in ("rows", "blocked") else ab["cells_kernel"]
-    kbytes = {"tag_cells": ab["tags_cells"], "tag_facets": ab["tags_facets"],
-              "assemble_cells": asm_bytes}[dominant]
-    achieved = kbytes / (per[dominant] * 1e-3) / 1e9
-    kernel_names = {"tag_cells": "k_tag_cells_p1", "tag_facets": "k_tag_facets",
-                    "assemble_cells": {"rows": "k_assemble_rows_p1", "blocked": "k_assemble_blocked_p1",
-                                       "atomic": "k_assemble_cells_p1",
-                                       "pk-atomic": "k_assemble_cells_pk"}[plan.method]}
-    roofline = {"bound": "hbm", "kernel": kernel_names[dominant], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": kbytes,
-                "step_achieved_gbs": ab["total"] / (ms_per_step * 1e-3) / 1e9,
-                "step_frac": ab["total"] / (ms_per_step * 1e-3) / 1e9 / peak,
-                "kernels_ms": per,
-                "kernels_gbs": {"tag_cells": ab["tags_cells"] / per["tag_cells"] / 1e6,
-                                "tag_facets": ab["tags_facets"] / per["tag_facets"] / 1e6,
-                                "assemble_cells": asm_bytes / per["assemble_cells"] / 1e6}}
-    if plan.method == "rows" and mesh.gdim == 3:
-        # the cell pass is bound by fp64 issue, not by HBM: 146 fp64 instructions per (row, cell) record (SASS
-        # count of cell_row<3>) against 64 fp64 lanes per clock per SM
-        # from the coordinates; 85 with the cached cell geometry (cell_row_geom<3>, cut-only instructions excluded)
-        per_record = 85 if plan.rowsplan.cell_geom is not None else 146
-        tiles = plan.rowsplan.tiles
-        if tiles is not None:   # cell-once pass: ~200 fp64 instructions per cell evaluation (SASS of cell_tensor<3>)
-            per_record = 200
-        n_eval = tiles.n_cell_slots if tiles is not None else plan.rowsplan.cells.n_records
-        lanes = n_eval * float(per_record)
-        peak_lanes = 148 * 64 * (clocks["sm_max_mhz"] or 1965) * 1e6
-        roofline["fp64_issue"] = {"kernel": "k_assemble_tiles_p1" if tiles is not None else "k_assemble_rows_p1<cells>",
-                                  "fp64_instructions_per_record": per_record, "records": n_eval,
-                                  "achieved_tera_lane_instr_per_s": lanes / (per["assemble_cells"] * 1e-3) / 1e12,
-                                  "peak_tera_lane_instr_per_s": peak_lanes / 1e12,
-                                  "frac": lanes / (per["assemble_cells"] * 1e-3) / peak_lanes}
+    counts = w.counts()
+    roofline, ab, dominant = roofline_of(w, per, ms_per_step, clocks)
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(traffic_file) and args.config == "3d-p1" and n == CONFIGS["3d-p1"][0] and world == 1:
+    if os.path.exists(traffic_file) and args.config == "3d-p1" and n == CONFIGS["3d-p1"][0] and world == 1 \
+            and args.mesh == "structured" and plan.method == "rows" and plan.rowsplan.tiles is None:
         with open(traffic_file) as fh:
-            roofline["traffic"] = json.load(fh).get(dominant)
+            tr = json.load(fh)
+        roofline["traffic"] = tr.get(dominant)
+        roofline["traffic_source"] = tr.get("source", "profiles/traffic.json (ncu --set full capture of this command)")
+    launches, launch_names = w.kernel_launches_per_step()
 
-    # ---- e2e: public API, pinned host buffers in, pinned host buffers out ---------------------------
-    e2e = None
-    if world == 1 and not args.no_e2e:
-        phi_h = phi.cpu().pin_memory()
-        f_h = f_asm.cpu().pin_memory()
-        phi_asm_h = phi_asm.cpu().pin_memory() if degree == 2 else phi_h
-        out_h = {"ct": torch.empty(mesh.num_cells, dtype=torch.int8).pin_memory(),
-                 "ft": torch.empty(mesh.num_facets, dtype=torch.int8).pin_memory(),
-                 "data": torch.empty(plan.nnz, dtype=torch.float64).pin_memory(),
-                 "b": torch.empty(plan.n_rows, dtype=torch.float64).pin_memory()}
-        import warnings
-        side = torch.cuda.Stream()
-        tags_done = torch.cuda.Event()
-        f_done = torch.cuda.Event()
-
-        def e2e_step():
-            # host level set -> device once; the same device-resident Function feeds the tags and (for P1) the
-            # assembly, as a user holding one phi_h would write it
-            phi_d = phi_h.to(dev, non_blocking=True)
-            # the source term follows the level set over PCIe on the side stream while the tag kernels run
-            with torch.cuda.stream(side):
-                f_d = f_h.to(dev, non_blocking=True)
-                f_done.record()
-            fn_h = fem.Function(V, phi_d)
-            with warnings.catch_warnings():
-                warnings.simplefilter("ignore", RuntimeWarning)
-                ct_, ft_, _, ds_, _ = mesh_scripts.compute_tags_measures(mesh, fn_h, 1, box_mode=True)
-            # the tags (one byte per entity, as the kernels write them; MeshTags widens to int32 on the host)
-            # leave on a side stream while the assembly runs
-            tags_done.record()
-            with torch.cuda.stream(side):
-                side.wait_event(tags_done)
-                out_h["ct"].copy_(ct_.tags8, non_blocking=True)
-                out_h["ft"].copy_(ft_.tags8, non_blocking=True)
-            torch.cuda.current_stream().wait_event(f_done)
-            A_, b_ = assemble.assemble_strong_dirichlet(plan, phi_d if degree == 1 else phi_asm_h, f_d,
-                                                        stab_coef=1.0)
-            f_d.record_stream(torch.cuda.current_stream())
-            out_h["data"].copy_(A_.data, non_blocking=True)
-            out_h["b"].copy_(b_, non_blocking=True)
-            torch.cuda.synchronize()
-
-        def e2e_pipelined(n_steps):
-            """The same calls with two steps in flight: step i runs on stream i % 2 with its own pinned output
-            buffers, so that the uploads, tag kernels and assembly of step i + 1 proceed under the device->host
-            copies of step i (PCIe is full duplex; the D2H direction bounds the step).  One host thread; every step
-            still uploads its inputs and downloads its results inside the timed region."""
-            mains = [torch.cuda.Stream(), torch.cuda.Stream()]
-            sides = [torch.cuda.Stream(), torch.cuda.Stream()]
-            outs = [out_h, {k: torch.empty_like(v).pin_memory() for k, v in out_h.items()}]
-            done, keep, asm_done = [None, None], [None, None], None
-            torch.cuda.synchronize()
-            t_start = time.perf_counter()
-            for i in range(n_steps):
-                j = i & 1
-                if done[j] is not None:      # results of step i - 2 are on the host: its buffers may be reused
-                    done[j].synchronize()
-                    keep[j] = None
-                s, sd, o = mains[j], sides[j], outs[j]
-                with torch.cuda.stream(s):
-                    phi_d = phi_h.to(dev, non_blocking=True)
-                    f_ev, t_ev = torch.cuda.Event(), torch.cuda.Event()
-                    with torch.cuda.stream(sd):
-                        f_d = f_h.to(dev, non_blocking=True)
-                        f_ev.record()
-                    fn_h = fem.Function(V, phi_d)
-                    with warnings.catch_warnings():
-                        warnings.simplefilter("ignore", RuntimeWarning)
-                        ct_, ft_, _, ds_, _ = mesh_scripts.compute_tags_measures(mesh, fn_h, 1, box_mode=True)
-                    t_ev.record()
-                    with torch.cuda.stream(sd):
-                        sd.wait_event(t_ev)
-                        o["ct"].copy_(ct_.tags8, non_blocking=True)
-                        o["ft"].copy_(ft_.tags8, non_blocking=True)
-                    s.wait_event(f_ev)
-                    if asm_done is not None:  # the plan's facet-once scratch is shared by consecutive assemblies
-                        s.wait_event(asm_done)
-                    A_, b_ = assemble.assemble_strong_dirichlet(plan, phi_d if degree == 1 else phi_asm_h, f_d,
-                                                                stab_coef=1.0)
-                    asm_done = torch.cuda.Event()
-                    asm_done.record()
-                    o["data"].copy_(A_.data, non_blocking=True)
-                    o["b"].copy_(b_, non_blocking=True)
-                    s.wait_stream(sd)
-                    done[j] = torch.cuda.Event()
-                    done[j].record()
-                    keep[j] = (phi_d, f_d, ct_, ft_, A_, b_)
-            torch.cuda.synchronize()
-            elapsed = time.perf_counter() - t_start
-            for k in out_h:                   # both buffer sets hold the same results (bit for bit where the
-                if plan.method == "rows" or outs[0][k].dtype != torch.float64:   # assembly sums in a fixed order)
-                    assert torch.equal(outs[0][k], outs[1][k]), k
-                else:
-                    assert torch.allclose(outs[0][k], outs[1][k], rtol=1e-10, atol=1e-12 * float(outs[0][k].abs().max())), k
-            return elapsed / n_steps
-
-        e2e_steps = max(2, min(args.steps, 5))
-        for _ in range(2):
-            e2e_step()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        dt = (time.perf_counter() - t0) / e2e_steps
-        pipelined_dt = None
-        if args.e2e_pipeline:
-            ref_data, ref_b = out_h["data"].clone(), out_h["b"].clone()
-            e2e_pipelined(4)
-            pipelined_dt = e2e_pipelined(2 * e2e_steps)
-            if plan.method == "rows":
-                assert torch.equal(out_h["data"], ref_data) and torch.equal(out_h["b"], ref_b)
-        e2e = {"value": mesh.num_cells / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
-               "h2d_bytes_per_step": int(phi_h.numel() * 8 + (phi_asm_h.numel() * 8 if degree == 2 else 0)
-                                         + f_h.numel() * 8),
-               "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in out_h.values())),
-               "api": "compute_tags_measures(box_mode=True) + assemble_strong_dirichlet(plan, ...) with "
-                      "pinned host level set / source in and pinned host tags (1 byte per cell / facet) + CSR values "
-                      "+ b out, source-term upload overlapped with the tag kernels, tag copies with the assembly; "
-                      "assembly plan (symbolic phase) reused; one step at a time"}
-        if pipelined_dt is not None:
-            e2e["two_steps_in_flight_ms"] = pipelined_dt * 1e3
+    e2e = measure_e2e(w, args, degree) if (world == 1 and not args.no_e2e) else None
+    tts = None
+    if world == 1 and degree == 1 and not args.no_solve and plan.method == "rows":
+        try:
+            tts = time_to_solution(w)
+        except Exception as exc:   # noqa: BLE001
+            tts = {"error": str(exc)}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu and args.config == "3d-p1":
-        cpu = cpu_measure(args.cpu_n, 3, 1)
+    if rank == 0 and world == 1 and not args.no_cpu and args.config == "3d-p1" and args.mesh == "structured":
+        if args.cpu_sample or plan.method != "rows":
+            cpu = CpuWorkload.from_size(args.cpu_n).measure(3, 1)
+        else:       # the configuration itself: arrays and slot maps of the plan just timed, copied to the host
+            cpu = CpuWorkload.from_device(mesh, phi, f, plan, n).measure(3, 1)
         cpu.pop("ms_per_step")
+
+    # ---- the unstructured variant of the same configuration (VERDICT round 1, row "star") ----------------------
+    unstructured = None
+    if world == 1 and args.config == "3d-p1" and args.mesh == "structured" and not args.no_unstructured:
+        structured_ms = ms_per_step
+        del w
+        torch.cuda.empty_cache()
+        try:
+            umesh, uphi, uf = make_mesh("unstructured")
+            uw = Workload(umesh, uphi, uf, args)
+            for _ in range(args.warmup):
+                uw.step()
+            ums, uper, _ = timed_steps(uw, args.steps, 1, presteps=3)
+            uroof, _, _ = roofline_of(uw, uper, ums, clocks)
+            unstructured = {"mesh": "SURVEY.md 8(d) variant of the same configuration: vertex jitter +-0.2 h (seed 0), "
+                                    "cells permuted (seed 1), vertices relabelled (seed 2), then renumbered along the "
+                                    "Morton curve (Mesh.reordered, timed as reorder_ms); level set and source "
+                                    "interpolated on that mesh",
+                            "cells": umesh.num_cells, "ms_per_step": ums, "value": umesh.num_cells / (ums * 1e-3),
+                            "unit": UNIT, "ratio_to_structured": ums / structured_ms,
+                            "step_frac": uroof["step_frac"], "kernels_ms": uper, "reorder_ms": reorder_ms,
+                            "symbolic_ms": uw.symbolic_ms, "topology_s": uw.topology_s,
+                            "counts": {k: v for k, v in uw.counts().items() if k in ("interior", "cut", "exterior",
+                                                                                    "nnz", "Na", "Ng")}}
+            del uw, umesh, uphi, uf
+        except Exception as exc:   # noqa: BLE001
+            unstructured = {"error": str(exc)}
+        torch.cuda.empty_cache()
+        w = None
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -581,30 +890,27 @@ def run_ours(args):
                                     "kernels_ms: tag_* and assembly from events inside the timed region, "
                                     "the assemble_* split from an untimed pass-by-pass loop"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-                "gpu_launches": {"rows": 7, "blocked": 5, "atomic": 7, "pk-atomic": 9}[plan.method] * args.steps,
-                "symbolic_ms": symbolic_ms, "topology_s": topo_s, "reorder_ms": reorder_ms,
-                "scatter": {"method": plan.method,
-                            **({"blocks": plan.blocked.n_blocks, "capacity": plan.blocked.capacity,
-                                "bin_shape": plan.blocked.bin_shape,
-                                "recompute_factor": plan.blocked.redundancy,
-                                "plan_bytes": plan.blocked.index_bytes()} if plan.blocked else {}),
-                            **({"order": plan.rowsplan.order, "max_row_nnz": plan.rowsplan.max_row_nnz,
-                                "cell_pass": plan.rowsplan.cell_pass,
-                                **({"rows_per_tile": plan.rowsplan.tiles.rows_per_tile,
-                                    "tiles": plan.rowsplan.tiles.n_tiles, "chunks": plan.rowsplan.tiles.n_chunks,
-                                    "cell_evaluations": plan.rowsplan.tiles.n_cell_slots,
-                                    "recompute_factor": plan.rowsplan.tiles.recompute}
-                                   if plan.rowsplan.tiles is not None else {}),
-                                "rows_cells_surface": [plan.rowsplan.tiles.n_listed if plan.rowsplan.tiles is not None
-                                                       else plan.rowsplan.cells.n_listed,
-                                                       plan.rowsplan.surface.n_listed],
-                                "records_cells_ghost_onesided": [plan.rowsplan.n_cell_records,
-                                                                 plan.rowsplan.n_ghost_records,
-                                                                 plan.rowsplan.n_entity_records],
-                                "lane_padding": [plan.rowsplan.cells.padding(), plan.rowsplan.surface.padding()],
-                                "cell_geometry": "cached per plan (64 B per active cell)"
-                                if plan.rowsplan.cell_geom is not None else "from the vertex coordinates",
-                                "plan_bytes": plan.rowsplan.index_bytes()} if plan.rowsplan else {})}}
+                "gpu_launches": (launches if launches is not None else
+                                 {"rows": 7, "blocked": 5, "atomic": 7, "pk-atomic": 9}[plan.method]) * args.steps,
+                "gpu_launches_per_step": launches, "gpu_kernels": launch_names,
+                "gpu_launches_source": "counted with the CUPTI profiler on one untimed step" if launches is not None
+                else "table (profiler unavailable)",
+                "symbolic_ms": _sym[0], "topology_s": _sym[1], "symbolic_first_call_ms": _sym[2],
+                "symbolic": {"builder": _sym[3], "symbolic_ms": "re-plan (pattern + row lists) on a warm process, best of "
+                             "2; symbolic_first_call_ms also grows the allocator / scratch pool by several GB"},
+                "cold_step_ms": _sym[0] + ms_per_step,
+                "reorder_ms": reorder_ms if args.mesh == "unstructured" else None,
+                "scatter": scatter_info(plan)}
+        if unstructured is not None:
+            line["unstructured"] = unstructured
+        if tts is not None:
+            line["time_to_solution_ms"] = tts
+        if world > 1:
+            line["parity_ok"] = parity_ok
+            line["parity"] = ("n=12 problem through PartitionedProblem.scatter + sharded tags + owner-computes assembly on "
+                              "%d ranks, merged owned rows BITWISE equal to rank 0's single-GPU operator" % world)
+            if strong is not None:
+                line["strong"] = strong
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -655,10 +961,6 @@ def main():
     ap.add_argument("--rows-per-tile", type=int, default=256, choices=[128, 256])
     ap.add_argument("--order", default="auto", choices=["auto", "natural", "morton"],
                     help="row processing order of the row-gather assembly")
-    ap.add_argument("--e2e-pipeline", action="store_true",
-                    help="also measure e2e with two steps in flight (uploads and kernels of step i + 1 under the "
-                         "downloads of step i): reported as e2e.two_steps_in_flight_ms, the e2e value stays the "
-                         "one-step-at-a-time figure (the pipelined one varies from box to box: 14.1 / 20.5 ms seen)")
     ap.add_argument("--geometry", action="store_true",
                     help="row-gather cell pass from a per-plan geometry table instead of the vertex coordinates "
                          "(measured slower: profiles/round2_a_geometry_kernel.md)")
@@ -667,6 +969,17 @@ def main():
     ap.add_argument("--detection-degree", type=int, default=1, choices=[1, 2],
                     help="degree of the detection level set and of the detection rule (1 = the demos' setting)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-sample", action="store_true",
+                    help="CPU arm on the bounded n = --cpu-n sample instead of the configuration itself")
+    ap.add_argument("--no-unstructured", action="store_true", help="skip the unstructured variant (extra key)")
+    ap.add_argument("--no-solve", action="store_true", help="skip time_to_solution_ms (extra key)")
+    ap.add_argument("--no-replan", action="store_true", help="skip the warm re-plan timing (symbolic_ms = first call)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="multi-GPU: the headline value is always the weak-scaling slab problem; the strong-scaling "
+                         "run of config E through the Morton partitioner is reported under the key `strong`")
+    ap.add_argument("--no-strong", action="store_true", help="multi-GPU: skip the strong-scaling run")
+    ap.add_argument("--no-parity", action="store_true", help="multi-GPU: skip the parity check (parity_ok)")
+    ap.add_argument("--no-graph", action="store_true", help="strong scaling: eager launches instead of one CUDA graph")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     args = ap.parse_args()
     if args.n is None:

@@ -1,5 +1,7 @@
 // A host without Python: cut-cell tags, CSR pattern and assembly of the strong-Dirichlet phi-FEM operator through the C
-// ABI of libphifem_b200.so alone (include/phifem_b200.h).  Stand-in for what a C++ / PETSc code base would do with the
+// ABI of libphifem_b200.so alone (include/phifem_b200.h) -- twice: with the per-entity kernels over slot maps
+// (phifem_pattern_create_p1 + phifem_assemble_{cells,boundary,ghost}_p1) and with the benchmarked row-gather path
+// (phifem_rows_plan_create + phifem_assemble_rows_p1).  Stand-in for what a C++ / PETSc code base would do with the
 // arrays of its own mesh; here the mesh is a unit square of 2 n^2 triangles built on the host.
 //
 //   nvcc -O2 -std=c++17 -gencode arch=compute_100a,code=sm_100a examples/capi_host.cu -Iinclude \
@@ -160,11 +162,44 @@ int main(int argc, char** argv) {
     idx_sum += (long long)h_idx[i] * (i % 7 + 1);
   }
   for (double t : h_b) b_sum += t;
+  // The benchmarked path: the row-gather plan built on the device (phifem_rows_plan_create) and the row-gather kernels
+  // (phifem_assemble_rows_p1: no atomics, no zero-fill).  Same pattern, same operator as the per-entity kernels above.
+  phifem_rows_plan_handle* rh = nullptr;
+  CHECK(phifem_rows_plan_create(&mesh, cell_tags8, facet_tags8, ents, n_ent, nullptr, 0, &rh, nullptr));
+  phifem_rows_plan rplan;
+  phifem_rows_plan_info rinfo;
+  CHECK(phifem_rows_plan_view(rh, &rplan, &rinfo));
+  double *data2, *b2;
+  cudaMalloc(&data2, std::max<int64_t>(1, rinfo.nnz) * sizeof(double));
+  cudaMalloc(&b2, rinfo.n_rows * sizeof(double));
+  cudaMemset(data2, 0xff, rinfo.nnz * sizeof(double));  // NaNs: every entry must be written by the kernels
+  cudaMemset(b2, 0, rinfo.n_rows * sizeof(double));
+  CHECK(phifem_assemble_rows_p1(&mesh, d_phi, d_f, 1.0, &rplan, data2, b2, nullptr));
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    std::fprintf(stderr, "CUDA error: %s\n", cudaGetErrorString(cudaGetLastError()));
+    return 1;
+  }
+  std::vector<double> r_data(rinfo.nnz), r_b(rinfo.n_rows);
+  std::vector<int32_t> r_idx(rinfo.nnz);
+  cudaMemcpy(r_data.data(), data2, rinfo.nnz * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaMemcpy(r_b.data(), b2, rinfo.n_rows * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaMemcpy(r_idx.data(), rplan.indices, rinfo.nnz * sizeof(int32_t), cudaMemcpyDeviceToHost);
+  double rows_abs_sum = 0.0, rows_b_sum = 0.0, max_diff = 0.0, max_abs = 0.0;
+  int same_pattern = rinfo.nnz == v.nnz;
+  for (int64_t i = 0; same_pattern && i < v.nnz; ++i) {
+    same_pattern = r_idx[i] == h_idx[i];
+    rows_abs_sum += std::fabs(r_data[i]);
+    max_diff = std::max(max_diff, std::fabs(r_data[i] - h_data[i]));
+    max_abs = std::max(max_abs, std::fabs(h_data[i]));
+  }
+  for (double t : r_b) rows_b_sum += t;
   std::printf("interior=%lld cut=%lld exterior=%lld nnz=%lld n_active=%lld n_ghost=%lld n_entities=%lld "
-              "indices_checksum=%lld data_abs_sum=%.17g b_sum=%.17g\n",
+              "indices_checksum=%lld data_abs_sum=%.17g b_sum=%.17g rows_same_pattern=%d rows_data_abs_sum=%.17g "
+              "rows_b_sum=%.17g rows_max_rel_diff=%.3e\n",
               (long long)cnt[PHIFEM_CNT_INTERIOR], (long long)cnt[PHIFEM_CNT_CUT], (long long)cnt[PHIFEM_CNT_EXTERIOR],
               (long long)v.nnz, (long long)v.n_active, (long long)v.n_ghost, (long long)v.n_entities, idx_sum, abs_sum,
-              b_sum);
+              b_sum, same_pattern, rows_abs_sum, rows_b_sum, max_diff / (max_abs > 0 ? max_abs : 1.0));
+  phifem_rows_plan_destroy(rh);
   phifem_pattern_destroy(pat);
   return 0;
 }

@@ -479,6 +479,33 @@ void phifem_pattern_destroy(phifem_pattern* pattern);
  * pool that stays cached between calls; this returns it to the driver. */
 void phifem_pattern_release_scratch(void);
 
+/* ---- the row-gather plan itself, built on the device (csrc/rows_plan.cu): CSR pattern (indptr, indices), active cells,
+ * ghost facets and the two row lists of phifem_rows_plan, from the vertex -> cell adjacency (one radix sort of
+ * n_active * nv keys, per-row merges) instead of one key per coupled vertex pair.  Every array equals what
+ * phifem_b200/assemble.py + rows.py build with torch ops, bit for bit.  The handle owns its device arrays (cudaMalloc);
+ * the call synchronises the stream a few times (sizes come back to the host).
+ *   row_mask      optional [n_vertices] bytes: list only these rows (the rows a rank owns); NULL = every row;
+ *   morton_cells  != 0: the rows of the cell pass are listed along the Morton curve of their vertices instead of
+ *                 ascending (the surface rows always are, then balanced by record count in chunks of 4096). */
+typedef struct phifem_rows_plan_handle phifem_rows_plan_handle;
+typedef struct phifem_rows_plan_info {
+  int64_t n_rows, nnz;
+  int64_t n_active, n_ghost, n_entities;
+  const int32_t* active;            /* [n_active] cells tagged 1 / 2, ascending */
+  const int32_t* ghost;             /* [n_ghost] interior facets tagged 2 / 3, ascending */
+  int64_t n_cell_records;           /* n_active * nv (records of unlisted rows included) */
+  int64_t n_surface_records;        /* records of the surface list */
+  int64_t cells_record_slots;       /* words of plan.cells.rec (pads included) */
+  int64_t surface_record_slots;     /* uint2 slots of plan.surface.rec (pads included) */
+} phifem_rows_plan_info;
+
+int phifem_rows_plan_create(const phifem_mesh* mesh, const int8_t* cell_tags8, const int8_t* facet_tags8,
+                            const int32_t* entities, int64_t n_entities, const uint8_t* row_mask, int32_t morton_cells,
+                            phifem_rows_plan_handle** out, void* stream);
+/* plan: ready for phifem_assemble_rows_p1 (its pointers stay valid until the handle is destroyed). */
+int phifem_rows_plan_view(const phifem_rows_plan_handle* handle, phifem_rows_plan* plan, phifem_rows_plan_info* info);
+void phifem_rows_plan_destroy(phifem_rows_plan_handle* handle);
+
 #ifdef __cplusplus
 }
 #endif

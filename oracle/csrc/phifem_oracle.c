@@ -31,6 +31,15 @@ int oracle_num_threads(void) {
 #endif
 }
 
+/* threads of the following calls (the CPU baseline is reported on 1 core and on all cores) */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 static double detj_abs(const double* x, int gdim, const int32_t* v) {
   if (gdim == 2) {
     const double* p0 = x + 2 * (int64_t)v[0];

@@ -22,6 +22,8 @@ def load():
             subprocess.run(["make", "-s", "-C", _HERE], check=True)
         lib = ctypes.CDLL(_LIB)
         lib.oracle_num_threads.restype = _int
+        lib.oracle_set_num_threads.argtypes = [_int]
+        lib.oracle_set_num_threads.restype = None
         lib.oracle_tag_cells_p1.argtypes = [_d, _int, _i, _i64, _d, _i]
         lib.oracle_tag_facets_p1.argtypes = [_d, _int, _i, _i, _i, _i64, _i64, _d, _i, _i]
         lib.oracle_assemble_cells_p1.argtypes = [_d, _int, _i, _d, _d, _i, _i, _i64, _i, _dbl, _d, _d]
@@ -36,6 +38,10 @@ def load():
 
 def num_threads():
     return load().oracle_num_threads()
+
+
+def set_num_threads(n):
+    load().oracle_set_num_threads(int(n))
 
 
 def tag_cells_p1(x, cells, phi):

@@ -62,6 +62,13 @@ class CRowsPlan(ctypes.Structure):
                 ("tiles", ctypes.POINTER(CCellTiles))]
 
 
+class CRowsPlanInfo(ctypes.Structure):
+    _fields_ = [("n_rows", ctypes.c_int64), ("nnz", ctypes.c_int64), ("n_active", ctypes.c_int64),
+                ("n_ghost", ctypes.c_int64), ("n_entities", ctypes.c_int64), ("active", _vp), ("ghost", _vp),
+                ("n_cell_records", ctypes.c_int64), ("n_surface_records", ctypes.c_int64),
+                ("cells_record_slots", ctypes.c_int64), ("surface_record_slots", ctypes.c_int64)]
+
+
 class CPkSpace(ctypes.Structure):
     _fields_ = [("degree", ctypes.c_int32), ("n_dofs_per_cell", ctypes.c_int32), ("n_dofs", ctypes.c_int64),
                 ("dofmap", _vp)]
@@ -145,6 +152,10 @@ _SIGNATURES = {
     "phifem_integration_entities": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, ctypes.c_int32, ctypes.c_uint32,
                                                    _vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64), _vp]),
     "phifem_pattern_destroy": (None, [_vp]),
+    "phifem_rows_plan_create": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, _vp, ctypes.c_int64, _vp,
+                                               ctypes.c_int32, ctypes.POINTER(_vp), _vp]),
+    "phifem_rows_plan_view": (ctypes.c_int, [_vp, ctypes.POINTER(CRowsPlan), ctypes.POINTER(CRowsPlanInfo)]),
+    "phifem_rows_plan_destroy": (None, [_vp]),
     "phifem_pattern_release_scratch": (None, []),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -193,6 +204,27 @@ def ptr(t):
 
 def stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+class _DeviceArray:
+    """Zero-copy view of device memory owned by a C handle (`__cuda_array_interface__`)."""
+
+    def __init__(self, pointer, shape, typestr, owner):
+        self.owner = owner      # torch keeps THIS object alive for as long as the tensor lives, hence the handle too
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(pointer), False),
+                                         "version": 2, "strides": None}
+
+
+def device_view(pointer, shape, dtype, device, owner=None):
+    """torch tensor over `pointer` (no copy).  `owner`: the object whose destruction frees the memory; the tensor keeps
+    it alive (a CSRMatrix outlives the plan it came from)."""
+    typestr = {torch.int32: "<i4", torch.uint8: "|u1", torch.float64: "<f8", torch.int8: "|i1"}[dtype]
+    n = 1
+    for k in shape:
+        n *= int(k)
+    if n == 0 or not pointer:
+        return torch.zeros(tuple(shape), dtype=dtype, device=device)
+    return torch.as_tensor(_DeviceArray(pointer, shape, typestr, owner), device=device)
 
 
 def require_cuda(mesh):

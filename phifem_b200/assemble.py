@@ -64,7 +64,10 @@ class AssemblyPlan:
     shared-memory block can hold."""
 
     def __init__(self, mesh, cell_tags8, facet_tags8, entities, method="rows", capacity=None,
-                 order="auto", row_mask=None, geometry=False, cell_pass="rows", rows_per_tile=256):
+                 order="auto", row_mask=None, geometry=False, cell_pass="rows", rows_per_tile=256, symbolic="auto"):
+        """symbolic: "torch" = sort / unique passes with torch ops (any device: the CPU tests); "native" = the device
+        builder behind the C ABI (csrc/rows_plan.cu: same arrays, bit for bit, from the vertex -> cell adjacency);
+        "auto" = native for a row-gather plan on a CUDA mesh, torch otherwise."""
         if mesh.cell_type not in ("triangle", "tetrahedron"):
             raise NotImplementedError("P1 assembly supports triangles and tetrahedra")
         dev = mesh.device
@@ -73,6 +76,30 @@ class AssemblyPlan:
         n = mesh.num_vertices
         nv = mesh.cells.shape[1]
         self.n_rows = n
+        if symbolic not in ("auto", "torch", "native"):
+            raise ValueError("symbolic must be 'auto', 'torch' or 'native'")
+        native_ok = (method == "rows" and cell_pass == "rows" and not geometry and dev.type == "cuda")
+        if symbolic == "native" and not native_ok:
+            raise ValueError("the native symbolic phase builds row-gather plans (method='rows', cell_pass='rows') on "
+                             "CUDA meshes")
+        self._slots = None
+        if native_ok and symbolic in ("auto", "native"):
+            from . import rows as rows_mod
+            try:
+                if order == "auto":
+                    order = "natural"
+                rp = rows_mod.NativeRowsPlan(mesh, cell_tags8, facet_tags8, entities, order=order, row_mask=row_mask)
+            except NotImplementedError:
+                if symbolic == "native":
+                    raise
+                rp = None                      # e.g. a row longer than 255 entries: the torch path decides
+            if rp is not None:
+                self.entities = entities.reshape(-1, 2).to(torch.int32).contiguous()
+                self.active, self.ghost, self.indptr, self.indices, self.nnz = rp.active, rp.ghost, rp.indptr, \
+                    rp.indices, rp.nnz
+                self.blocked, self.rowsplan, self.method, self.symbolic = None, rp, "rows", "native"
+                return
+        self.symbolic = "torch"
         self.active = torch.nonzero((cell_tags8 == 1) | (cell_tags8 == 2)).reshape(-1).to(torch.int32)
         interior = mesh.f2c[:, 1] >= 0
         self.ghost = torch.nonzero(((facet_tags8 == 2) | (facet_tags8 == 3)) & interior) \
@@ -90,12 +117,13 @@ class AssemblyPlan:
         uniq, inv = torch.unique(torch.cat([keys_c.reshape(-1), keys_g.reshape(-1)]), sorted=True,
                                  return_inverse=True)
         del keys_c, keys_g
-        self.slots_cells = inv[:n_c].reshape(-1, nv * nv).to(torch.int32).contiguous()
-        self.slots_ghost = inv[n_c:].reshape(-1, (nv + 1) ** 2).to(torch.int32).contiguous()
+        slots_cells = inv[:n_c].reshape(-1, nv * nv).to(torch.int32).contiguous()
+        slots_ghost = inv[n_c:].reshape(-1, (nv + 1) ** 2).to(torch.int32).contiguous()
         del inv
         keys_b = pair_keys(mesh.cells[self.entities[:, 0].long()].long())
-        self.slots_boundary = torch.searchsorted(uniq, keys_b.reshape(-1)).reshape(-1, nv * nv) \
+        slots_boundary = torch.searchsorted(uniq, keys_b.reshape(-1)).reshape(-1, nv * nv) \
             .to(torch.int32).contiguous()
+        self._slots = (slots_cells, slots_ghost, slots_boundary)
         rows = uniq // n
         self.indices = (uniq - rows * n).to(torch.int32).contiguous()
         counts = torch.bincount(rows, minlength=n)
@@ -124,6 +152,28 @@ class AssemblyPlan:
                 self.blocked = None
         elif method not in ("rows", "blocked", "atomic"):
             raise ValueError("method must be 'rows', 'blocked' or 'atomic'")
+
+    # entity -> CSR-slot maps of the per-entity (atomic) kernels and of the CPU arm: built with the torch pattern, or on
+    # first use from a natively built pattern (position of the key row * n + col in the sorted key list)
+    def _slot_maps(self):
+        if self._slots is None:
+            n, nv = self.n_rows, self.mesh.cells.shape[1]
+            ip = self.indptr.long()
+            rows = torch.repeat_interleave(torch.arange(n, device=self.mesh.device), ip[1:] - ip[:-1])
+            keys = rows * n + self.indices.long()
+            del rows
+
+            def slots(dm):
+                k = (dm[:, :, None] * n + dm[:, None, :]).reshape(-1)
+                return torch.searchsorted(keys, k).reshape(dm.shape[0], -1).to(torch.int32).contiguous()
+            cells = self.mesh.cells
+            self._slots = (slots(cells[self.active.long()].long()), slots(ghost_macro_vertices(self.mesh, self.ghost)),
+                           slots(cells[self.entities[:, 0].long()].long()))
+        return self._slots
+
+    slots_cells = property(lambda self: self._slot_maps()[0])
+    slots_ghost = property(lambda self: self._slot_maps()[1])
+    slots_boundary = property(lambda self: self._slot_maps()[2])
 
     def new_outputs(self):
         dev = self.mesh.device
@@ -157,7 +207,7 @@ def _plan_inputs(mesh, cells_tags, facets_tags, ds):
 
 
 def build_plan(mesh, cells_tags, facets_tags, ds=None, method="rows", capacity=None, order="auto",
-               V=None, V_phi=None, geometry=False, cell_pass="rows", rows_per_tile=256):
+               V=None, V_phi=None, geometry=False, cell_pass="rows", rows_per_tile=256, symbolic="auto"):
     """Symbolic phase for `a` and `L` of the strong-Dirichlet demo.  `ds` is what the demo passes as
     `ds_bdy(100)` (main.py:64): a MeasureRestriction, a flat entity array, or None (no boundary term).
     `V` / `V_phi`: the demo's `primal_space` / `levelset_space` (main.py:74-75); omitted or both of degree 1
@@ -172,7 +222,8 @@ def build_plan(mesh, cells_tags, facets_tags, ds=None, method="rows", capacity=N
         from .assemble_pk import PkAssemblyPlan
         return PkAssemblyPlan(mesh, c8, f8, ents, V, V_phi)
     return AssemblyPlan(mesh, c8, f8, ents, method=method, capacity=capacity,
-                        order=order, geometry=geometry, cell_pass=cell_pass, rows_per_tile=rows_per_tile)
+                        order=order, geometry=geometry, cell_pass=cell_pass, rows_per_tile=rows_per_tile,
+                        symbolic=symbolic)
 
 
 def _device_vector(mesh, v, space=None):

@@ -22,6 +22,29 @@ struct phifem_pattern {
 };
 
 namespace phifem {
+// A private stream-ordered pool per device whose memory stays cached between calls (release threshold = max): the
+// default pool hands its memory back to the driver at every synchronisation, and re-allocating the ~10 GB of sort
+// scratch of config E costs ten times the sort.  phifem_pattern_release_scratch() trims it.
+cudaMemPool_t g_pools[64] = {};
+cudaMemPool_t scratch_pool() {  // also used by csrc/rows_plan.cu
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaMemPool_t& pool = g_pools[dev & 63];
+  if (!pool) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) {
+      pool = nullptr;
+      return nullptr;
+    }
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  return pool;
+}
+
 namespace {
 
 constexpr int kBlockSym = 256;
@@ -128,29 +151,6 @@ __global__ void k_entity_unpack(const int64_t* __restrict__ sval, int64_t n, int
   if (t >= n) return;
   out[2 * t] = (int32_t)(sval[t] >> 3);
   out[2 * t + 1] = (int32_t)(sval[t] & 7);
-}
-
-// A private stream-ordered pool per device whose memory stays cached between calls (release threshold = max): the
-// default pool hands its memory back to the driver at every synchronisation, and re-allocating the ~10 GB of sort
-// scratch of config E costs ten times the sort.  phifem_pattern_release_scratch() trims it.
-cudaMemPool_t g_pools[64] = {};
-cudaMemPool_t scratch_pool() {
-  int dev = 0;
-  cudaGetDevice(&dev);
-  cudaMemPool_t& pool = g_pools[dev & 63];
-  if (!pool) {
-    cudaMemPoolProps props = {};
-    props.allocType = cudaMemAllocationTypePinned;
-    props.location.type = cudaMemLocationTypeDevice;
-    props.location.id = dev;
-    if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) {
-      pool = nullptr;
-      return nullptr;
-    }
-    uint64_t keep = UINT64_MAX;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-  }
-  return pool;
 }
 
 struct Scratch {  // device allocations freed on scope exit (stream-ordered)

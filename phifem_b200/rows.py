@@ -331,10 +331,114 @@ class RowsPlan:
                 + (self.cell_geom.numel() * 8 if self.cell_geom is not None else 0))
 
 
+class _NativeList:
+    """A row list of a natively built plan, with the attributes of `RowList` that callers read."""
+
+    def __init__(self, c_list, n_records, slots, words, device, keep):
+        self.c = c_list
+        self.n_listed = int(c_list.n_listed)
+        self.n_slices = (self.n_listed + 31) // 32
+        self.words, self.n_records, self._slots = words, int(n_records), int(slots)
+        def dv(*a):
+            return _lib.device_view(*a, owner=keep)
+        self.rows = dv(c_list.rows, (self.n_listed,), torch.int32, device)
+        self.diag_pos = dv(c_list.diag_pos, (self.n_listed,), torch.uint8, device)
+        self.ptr = dv(c_list.ptr, (self.n_slices + 1,), torch.int32, device)
+        self.rec = dv(c_list.rec, (max(self._slots, 32) * words,), torch.int32, device)
+        self._keep = keep
+
+    def c_struct(self):
+        return self.c
+
+    def nbytes(self):
+        return self.n_listed * 5 + (self.n_slices + 1) * 4 + max(self._slots, 32) * self.words * 4
+
+    def padding(self):
+        return 1.0 - self.n_records / max(1, self._slots)
+
+
+class _Handle:
+    def __init__(self, pointer):
+        self.pointer = pointer
+
+    def __del__(self):
+        try:
+            if self.pointer:
+                _lib.load().phifem_rows_plan_destroy(self.pointer)
+        except Exception:   # interpreter shutdown
+            pass
+        self.pointer = None
+
+
+class NativeRowsPlan:
+    """The arrays of `RowsPlan` built on the device behind the C ABI (csrc/rows_plan.cu, phifem_rows_plan_create): the
+    CSR pattern and both row lists from the vertex -> cell adjacency, bit for bit what the torch passes of
+    `AssemblyPlan` + `RowsPlan` produce (tests/test_gpu_rows_plan_capi.py)."""
+
+    def __init__(self, mesh, cell_tags8, facet_tags8, entities, order="natural", row_mask=None):
+        _lib.require_cuda(mesh)
+        lib = _lib.load()
+        dev = mesh.device
+        ents = entities.reshape(-1, 2).to(torch.int32).contiguous()
+        mask = None if row_mask is None else row_mask.to(dev).to(torch.uint8).contiguous()
+        out = ctypes.c_void_p()
+        _lib.check(lib.phifem_rows_plan_create(_lib.c_mesh(mesh), _lib.ptr(cell_tags8), _lib.ptr(facet_tags8),
+                                               _lib.ptr(ents) if ents.numel() else None, ents.shape[0],
+                                               _lib.ptr(mask), 1 if order == "morton" else 0, ctypes.byref(out),
+                                               _lib.stream()))
+        self._handle = _Handle(out.value)
+        self._c, info = _lib.CRowsPlan(), _lib.CRowsPlanInfo()
+        _lib.check(lib.phifem_rows_plan_view(out.value, ctypes.byref(self._c), ctypes.byref(info)))
+        self.info = info
+        self.mesh, self.order, self.cell_pass, self.tiles, self.cell_geom = mesh, order, "rows", None, None
+        nv = mesh.cells.shape[1]
+
+        def dv(*a):
+            return _lib.device_view(*a, owner=self._handle)
+        self.n_rows, self.nnz = int(info.n_rows), int(info.nnz)
+        self.indptr = dv(self._c.indptr, (self.n_rows + 1,), torch.int32, dev)
+        self.indices = dv(self._c.indices, (self.nnz,), torch.int32, dev)
+        self.active = dv(info.active, (int(info.n_active),), torch.int32, dev)
+        self.ghost = dv(info.ghost, (int(info.n_ghost),), torch.int32, dev)
+        self.max_row_nnz = int(self._c.max_row_nnz)
+        self.n_ghost_facets, self.n_entities = int(info.n_ghost), int(info.n_entities)
+        self.ghost_macro = dv(self._c.ghost_macro, (self.n_ghost_facets, nv + 1), torch.int32, dev)
+        self.entity_macro = dv(self._c.entity_macro, (self.n_entities, nv), torch.int32, dev)
+        self.surface_work = dv(self._c.surface_work, (max(self.n_ghost_facets + self.n_entities, 1), 8), torch.float64,
+                               dev)
+        n_cell_rec = int(info.n_cell_records)
+        if mask is not None:     # records of the listed rows only
+            cnt = (self.indptr[1:] > self.indptr[:-1]) & mask.bool()
+            deg = torch.bincount(mesh.cells[self.active.long()].long().reshape(-1), minlength=self.n_rows)
+            n_cell_rec = int(deg[cnt].sum())
+        self.n_cell_records = n_cell_rec
+        self.cells = _NativeList(self._c.cells, n_cell_rec, info.cells_record_slots, 1, dev, self._handle)
+        self.surface = _NativeList(self._c.surface, info.n_surface_records, info.surface_record_slots, 2, dev,
+                                   self._handle)
+        self.n_ghost_records = self.n_ghost_facets * (nv + 1) if mask is None else None
+        self.n_entity_records = self.n_entities * (nv - 1) if mask is None else None
+
+    def c_struct(self, passes=None):
+        if passes is None:
+            return self._c
+        c = _lib.CRowsPlan()
+        ctypes.pointer(c)[0] = self._c
+        empty = _lib.CRowList(0, None, None, None, None)
+        if "cells" not in passes:
+            c.cells = empty
+        if "surface" not in passes:
+            c.surface = empty
+        return c
+
+    def index_bytes(self):
+        return (self.cells.nbytes() + self.surface.nbytes() + self.ghost_macro.numel() * 4
+                + self.entity_macro.numel() * 4 + self.surface_work.numel() * 8)
+
+
 def assemble_rows_into(rplan, phi, f, sigma, data, b, passes=None):
     """Numeric phase on the current stream (facet-once kernel, cell pass, surface pass).  `data` needs
     no zero-fill; `b` must have been zeroed once (rows without pattern entries are never written)."""
-    mesh = rplan.plan.mesh
+    mesh = rplan.mesh if isinstance(rplan, NativeRowsPlan) else rplan.plan.mesh
     _lib.require_cuda(mesh)
     _lib.check(_lib.load().phifem_assemble_rows_p1(
         _lib.c_mesh(mesh), _lib.ptr(phi), _lib.ptr(f), float(sigma),

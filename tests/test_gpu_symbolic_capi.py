@@ -102,3 +102,9 @@ def test_c_host_without_python_reproduces_the_python_path(tmp_path):
     assert int(got["indices_checksum"]) == int((plan.indices.long() * (torch.arange(plan.nnz, device="cuda") % 7 + 1)).sum())
     assert abs(float(got["data_abs_sum"]) - float(A.data.abs().sum())) <= 1e-11 * float(A.data.abs().sum())
     assert abs(float(got["b_sum"]) - float(b.sum())) <= 1e-11 * float(b.abs().sum())
+    # the benchmarked row-gather path from the same C++ host: same pattern, same operator
+    assert int(got["rows_same_pattern"]) == 1 and float(got["rows_max_rel_diff"]) <= 1e-12
+    rows_plan = assemble.build_plan(mesh, ctags, ftags, ds(100))
+    A2, b2 = assemble.assemble_strong_dirichlet(rows_plan, phi, f, stab_coef=1.0)
+    assert abs(float(got["rows_data_abs_sum"]) - float(A2.data.abs().sum())) <= 1e-13 * float(A2.data.abs().sum())
+    assert abs(float(got["rows_b_sum"]) - float(b2.sum())) <= 1e-12 * float(b2.abs().sum())
