@@ -629,7 +629,7 @@ def time_to_solution(w):
             "unknowns": info.n_active}
 
 
-def multi_gpu_parity(dev, rank, world, n=12):
+def multi_gpu_parity(dev, rank, world, n=12, peer=True):
     """A small problem through the SAME sharded code path (scatter from rank 0, sharded tags with the all-reduce,
     owner-computes assembly), merged on rank 0 and compared BITWISE with rank 0's single-GPU operator."""
     import torch
@@ -652,6 +652,8 @@ def multi_gpu_parity(dev, rank, world, n=12):
         ref = (plan.indptr.cpu().numpy(), plan.indices.cpu().numpy(), data.cpu().numpy(), b.cpu().numpy(),
                ws.cell_tags8.cpu().numpy())
     prob = partition.PartitionedProblem.scatter(gmesh, gphi, gf, rank, world, device=dev)
+    if peer:
+        prob.enable_peer_flags()
     dls = mesh_scripts._DeviceLevelset(prob.mesh, fem.Function(fem.functionspace_p1_device(prob.mesh), prob.phi), 1)
     ws = mesh_scripts.TagWorkspace(prob.mesh)
     prob.classify(dls, ws)
@@ -701,6 +703,7 @@ def strong_scaling(args, dev, rank, world):
         weights = torch.where(inside, 3.0, torch.where(outside, 1.0, 10.0)).to(torch.float64)
         del neg, inside, outside
     prob = partition.PartitionedProblem.scatter(gmesh, gphi, gf, rank, world, weights=weights, device=dev)
+    peer = (not args.no_peer) and prob.enable_peer_flags()
     del gmesh, gphi, gf, weights
     torch.cuda.empty_cache()
     torch.cuda.synchronize()
@@ -728,6 +731,8 @@ def strong_scaling(args, dev, rank, world):
     assert owned_total == n_cells, "the ranks' owned cells do not partition the mesh"
     return {"n_gpus": world, "cells_total": n_cells, "ms_per_step": ms, "value": n_cells / (ms * 1e-3), "unit": UNIT,
             "cuda_graph": graph, "scatter_s": scatter_s,
+            "exchange": "exterior-cell counts stored into the peers' HBM over NVLink (csrc/peer.cu)" if peer else
+                        "8-byte NCCL all-reduce",
             "partition": "Morton curve of the cell centroids, ranges of equal weight (exterior 1 / interior 3 / cut 10), "
                          "computed once on rank 0 and scattered; rows owned by the lowest rank touching them; "
                          "redundantly classified halo (cells sharing a vertex with a cell touching an owned row); one "
@@ -786,11 +791,13 @@ def run_ours(args):
     if world > 1:
         from phifem_b200 import dist as pdist
         if not args.no_parity:
-            parity_ok = multi_gpu_parity(dev, rank, world)
+            parity_ok = multi_gpu_parity(dev, rank, world, peer=not args.no_peer)
         if args.scaling == "strong" or not args.no_strong:
             strong = strong_scaling(args, dev, rank, world)
             torch.cuda.empty_cache()
         problem = pdist.SlabProblem(n, rank, world, dev, mode=args.dist_mode)
+        if not args.no_peer:
+            problem.enable_peer_flags()
         mesh, phi, f = problem.mesh, problem.phi, problem.f
     else:
         mesh, phi, f = make_mesh(args.mesh)
@@ -884,7 +891,9 @@ def run_ours(args):
                                          "1 slab of the global box per rank, owned CSR rows, "
                                          + ("owner computes its rows from 2 redundantly classified ghost "
                                             "layers: one 8-byte all-reduce per step, no halo exchange"
-                                            if args.dist_mode == "rows" else "NCCL halo exchange")),
+                                            if args.dist_mode == "rows" else "NCCL halo exchange")
+                                         + ("; the 8 bytes travel as stores into the peers' HBM over NVLink (csrc/peer.cu)"
+                                            if getattr(problem, "peer", None) is not None else "")),
                            "tags_dtype": "int8 on the device (int32 MeshTags.values widened on demand)",
                            "timed": "tag kernels + zeroing + assembly kernels; symbolic phase excluded; "
                                     "kernels_ms: tag_* and assembly from events inside the timed region, "
@@ -979,6 +988,8 @@ def main():
                          "run of config E through the Morton partitioner is reported under the key `strong`")
     ap.add_argument("--no-strong", action="store_true", help="multi-GPU: skip the strong-scaling run")
     ap.add_argument("--no-parity", action="store_true", help="multi-GPU: skip the parity check (parity_ok)")
+    ap.add_argument("--no-peer", action="store_true",
+                    help="multi-GPU: exchange the exterior-cell counts with an NCCL all-reduce instead of peer memory")
     ap.add_argument("--no-graph", action="store_true", help="strong scaling: eager launches instead of one CUDA graph")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     args = ap.parse_args()

@@ -506,6 +506,25 @@ int phifem_rows_plan_create(const phifem_mesh* mesh, const int8_t* cell_tags8, c
 int phifem_rows_plan_view(const phifem_rows_plan_handle* handle, phifem_rows_plan* plan, phifem_rows_plan_info* info);
 void phifem_rows_plan_destroy(phifem_rows_plan_handle* handle);
 
+/* ---- the exchange step of a sharded classification over NVLink peer memory (csrc/peer.cu).  `_tag_facets` needs
+ * "is there any exterior cell" GLOBALLY (reference src/phifem/mesh_scripts.py:469-474): every rank publishes its count of
+ * tag-3 cells after phifem_tag_cells by storing (epoch, count) into a slot of every peer's memory (CUDA IPC mapping, one
+ * 8-byte store per peer), runs phifem_tag_facets_phase(PHIFEM_FACETS_INTERIOR), then collects the sum from the slots in
+ * its own memory and runs the PHIFEM_FACETS_BOUNDARY phase.  One process per GPU on one node, world <= 64.
+ *   create   allocates the rank's slots and returns their 64-byte IPC handle;
+ *   connect  takes the handles of ALL ranks ([world][64] bytes, gathered by the host code, e.g. MPI_Allgather) and maps them;
+ *   publish  value: device pointer to the rank's count; every call starts a new epoch (kept in device memory: the two
+ *            calls can be captured in a CUDA graph and replayed);
+ *   collect  value_out (device) = sum over ranks of the counts of the current epoch (each clamped to 2^32 - 1); waits
+ *            for peers that are late, gives up after ~1 s (phifem_peer_flags_error then returns 1). */
+typedef struct phifem_peer_flags phifem_peer_flags;
+int phifem_peer_flags_create(int32_t world, int32_t rank, phifem_peer_flags** out, void* handle64);
+int phifem_peer_flags_connect(phifem_peer_flags* flags, const void* handles);
+int phifem_peer_flags_publish(phifem_peer_flags* flags, const int64_t* value, void* stream);
+int phifem_peer_flags_collect(phifem_peer_flags* flags, int64_t* value_out, void* stream);
+int phifem_peer_flags_error(phifem_peer_flags* flags);
+void phifem_peer_flags_destroy(phifem_peer_flags* flags);
+
 #ifdef __cplusplus
 }
 #endif

@@ -156,6 +156,12 @@ _SIGNATURES = {
                                                ctypes.c_int32, ctypes.POINTER(_vp), _vp]),
     "phifem_rows_plan_view": (ctypes.c_int, [_vp, ctypes.POINTER(CRowsPlan), ctypes.POINTER(CRowsPlanInfo)]),
     "phifem_rows_plan_destroy": (None, [_vp]),
+    "phifem_peer_flags_create": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(_vp), _vp]),
+    "phifem_peer_flags_connect": (ctypes.c_int, [_vp, _vp]),
+    "phifem_peer_flags_publish": (ctypes.c_int, [_vp, _vp, _vp]),
+    "phifem_peer_flags_collect": (ctypes.c_int, [_vp, _vp, _vp]),
+    "phifem_peer_flags_error": (ctypes.c_int, [_vp]),
+    "phifem_peer_flags_destroy": (None, [_vp]),
     "phifem_pattern_release_scratch": (None, []),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

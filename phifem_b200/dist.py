@@ -105,6 +105,7 @@ class SlabProblem:
         self.phi = self._levelset(self.mesh.x)
         self.f = self._source(self.mesh.x)
         self.plan = None
+        self.peer = None
 
     @classmethod
     def global_reference(cls, n, world, device="cpu"):
@@ -144,8 +145,15 @@ class SlabProblem:
     def classify(self, dls, ws, mark=None):
         """Cells, interior facets overlapped with the 8-byte all-reduce of the exterior-cell count, mesh-boundary
         facets (all on the current stream; mesh_scripts.classify_sharded)."""
-        return mesh_scripts.classify_sharded(self.mesh, dls, ws, group=self.group, world=self.world, mark=mark)
+        return mesh_scripts.classify_sharded(self.mesh, dls, ws, group=self.group, world=self.world, mark=mark,
+                                             peer=getattr(self, "peer", None))
         # (`single_layer_cut` needs one more ghost layer: offered by partition.PartitionedProblem, not by the slabs)
+
+    def enable_peer_flags(self):
+        """Exterior-cell counts through NVLink peer memory instead of an all-reduce (phifem_b200/peer.py)."""
+        from . import peer
+        self.peer = peer.try_create(self.rank, self.world, self.group)
+        return self.peer is not None
 
     # ---- symbolic phase ----------------------------------------------------------------------------
     def build_plan(self, cell_tags8, facet_tags8):

@@ -151,16 +151,25 @@ def classify_facets(mesh, dls, ws, phases=FACETS_INTERIOR | FACETS_BOUNDARY):
         _lib.ptr(ws.facet_tags8), _lib.ptr(ws.counters), int(phases), _lib.stream()))
 
 
-def classify_sharded(mesh, dls, ws, group=None, world=1, mark=None, single_layer_cut=False):
-    """Cells, then the interior facets WHILE the 8-byte all-reduce of the exterior-cell count is in flight, then
-    the mesh-boundary facets (reference :469-474 makes their tags depend on the global flag).  `mark` (optional
-    callable) is invoked after the cell kernel and at the end (bench.py records CUDA events there)."""
+def classify_sharded(mesh, dls, ws, group=None, world=1, mark=None, single_layer_cut=False, peer=None):
+    """Cells, then the interior facets WHILE the exterior-cell counts of the ranks travel, then the mesh-boundary facets
+    (reference :469-474 makes their tags depend on the global "any exterior cell" flag).  The exchange is either
+    `peer` (phifem_b200/peer.py: 8-byte stores into the peers' HBM over NVLink after the cell kernel, a read of the own
+    slots before the boundary kernel -- nothing that needs an SM while the persistent facet kernel runs) or, without it,
+    an 8-byte `torch.distributed` all-reduce.  `mark` (optional callable) is invoked after the cell kernel and at the
+    end (bench.py records CUDA events there)."""
     import torch.distributed as dist
     mark = mark or (lambda: None)
     classify_cells(mesh, dls, ws, single_layer_cut)
     mark()
-    if world > 1:
-        work = dist.all_reduce(ws.counters[_lib.CNT_EXTERIOR:_lib.CNT_EXTERIOR + 1], group=group, async_op=True)
+    count = ws.counters[_lib.CNT_EXTERIOR:_lib.CNT_EXTERIOR + 1]
+    if world > 1 and peer is not None:
+        peer.publish(count)
+        classify_facets(mesh, dls, ws, FACETS_INTERIOR)
+        peer.collect(count)
+        classify_facets(mesh, dls, ws, FACETS_BOUNDARY)
+    elif world > 1:
+        work = dist.all_reduce(count, group=group, async_op=True)
         classify_facets(mesh, dls, ws, FACETS_INTERIOR)
         work.wait()
         classify_facets(mesh, dls, ws, FACETS_BOUNDARY)

@@ -105,6 +105,7 @@ class PartitionedProblem:
         self.n_owned_cells = int(self.cell_owned.sum())
         self.phi, self.f = phi.contiguous(), f.contiguous()
         self.plan = None
+        self.peer = None
 
     @classmethod
     def scatter(cls, mesh, phi, f, rank, world, group=None, weights=None, single_layer_cut=False, src=0,
@@ -162,7 +163,14 @@ class PartitionedProblem:
         """Cells, interior facets overlapped with the 8-byte all-reduce of the exterior-cell count, mesh-boundary
         facets (all on the current stream; mesh_scripts.classify_sharded)."""
         return mesh_scripts.classify_sharded(self.mesh, dls, ws, group=self.group, world=self.world, mark=mark,
-                                             single_layer_cut=self.single_layer_cut)
+                                             single_layer_cut=self.single_layer_cut, peer=getattr(self, "peer", None))
+
+    def enable_peer_flags(self):
+        """Exchange the exterior-cell counts through NVLink peer memory (phifem_b200/peer.py) instead of an all-reduce;
+        returns False (and keeps the all-reduce) where peer mapping is unavailable.  Collective: every rank calls it."""
+        from . import peer
+        self.peer = peer.try_create(self.rank, self.world, self.group)
+        return self.peer is not None
 
     # ---- symbolic phase ----------------------------------------------------------------------------
     def build_plan(self, cell_tags8, facet_tags8, entities=None):

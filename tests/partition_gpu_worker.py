@@ -18,6 +18,8 @@ from phifem_b200 import assemble, fem, mesh_scripts, partition, synthetic  # noq
 def main():
     kind, n = sys.argv[1], int(sys.argv[2])
     single = len(sys.argv) > 3 and sys.argv[3] == "single"
+    halfspace = len(sys.argv) > 3 and sys.argv[3] == "halfspace"
+    use_peer = os.environ.get("PHIFEM_PEER") == "1"
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
     torch.cuda.set_device(dev)
@@ -31,13 +33,31 @@ def main():
         far = torch.argmax(torch.where(phi > 4 * h, phi, torch.full_like(phi, -1.0)))
         phi = torch.minimum(phi, synthetic.sphere_levelset(gmesh.x, center=tuple(float(v) for v in gmesh.x[far]),
                                                            radius=0.3 * h))
+    if halfspace:
+        # Omega = {x_last < 0.6}: the first half of the Morton curve (x_last < 0.5) holds interior cells only, so that
+        # rank has NO exterior cell of its own while the mesh has: its mesh-boundary facets are tagged 1 only if the
+        # global flag of reference :469-474 reaches it (tag 4 = Gamma_h otherwise, which changes ds(100) and the operator)
+        last = gmesh.x[:, -1]
+        lo, hi = float(last.min()), float(last.max())
+        phi = ((last - lo) / (hi - lo) - 0.6 - 1e-3 * torch.sin(7.0 * gmesh.x[:, 0])).contiguous()
     f = torch.from_numpy(np.random.default_rng(99).uniform(-1, 1, gmesh.num_vertices)).to(dev)
     prob = partition.PartitionedProblem(gmesh, phi, f, rank, world, single_layer_cut=single)
+    if use_peer:
+        assert prob.enable_peer_flags(), "peer mapping unavailable"
     dls = mesh_scripts._DeviceLevelset(prob.mesh, fem.Function(fem.functionspace_p1_device(prob.mesh), prob.phi), 1)
-    ws = prob.classify(dls, mesh_scripts.TagWorkspace(prob.mesh))
+    ws = mesh_scripts.TagWorkspace(prob.mesh)
+    for _ in range(3 if use_peer else 1):        # several epochs: the slots alternate
+        prob.classify(dls, ws)
+    if halfspace:
+        n_ext = int((ws.cell_tags8[prob.cell_owned] == 3).sum())
+        flags = [None] * world
+        dist.all_gather_object(flags, n_ext)
+        assert min(flags) == 0 and max(flags) > 0, "the case needs a rank without exterior cells: %s" % flags
     prob.build_plan(ws.cell_tags8, ws.facet_tags8)
     prob.assemble(1.0)
     torch.cuda.synchronize()
+    if use_peer:
+        assert not prob.peer.timed_out()
     rows, indptr, cols, data, b = prob.owned_csr()
     mine = dict(rows=rows.cpu().numpy(), indptr=indptr.cpu().numpy(), cols=cols.cpu().numpy(),
                 data=data.cpu().numpy(), b=b.cpu().numpy(),
@@ -69,8 +89,8 @@ def main():
             assert np.array_equal(p["b"], bb[p["rows"]])
             assert p["n_local"] < gmesh.num_cells
         assert np.all(seen == 1)
-        print("PARTITION-OK world=%d kind=%s single=%s cells=%d local=%s"
-              % (world, kind, single, gmesh.num_cells, [p["n_local"] for p in parts]))
+        print("PARTITION-OK world=%d kind=%s single=%s cells=%d local=%s peer=%s halfspace=%s"
+              % (world, kind, single, gmesh.num_cells, [p["n_local"] for p in parts], use_peer, halfspace))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -32,3 +32,18 @@ def test_partitioned_gpus_are_bitwise_identical_to_single_gpu(kind, n, single):
                          + (["single"] if single else []), capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert "PARTITION-OK world=2 kind=%s single=%s" % (kind, single) in out.stdout
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("peer", [False, True])
+def test_global_exterior_flag_reaches_a_rank_without_exterior_cells(peer):
+    """One rank holds interior cells only while the mesh has exterior cells: its mesh-boundary facets (and with them
+    ds(100) and the operator) are right only if the "any exterior cell" flag of reference :469-474 is exchanged --
+    through the all-reduce (peer=False) or through NVLink peer memory (csrc/peer.cu, three epochs)."""
+    env = dict(os.environ, PHIFEM_PEER="1" if peer else "0")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29615",
+                          os.path.join(HERE, "partition_gpu_worker.py"), "tet", "10", "halfspace"],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert "PARTITION-OK world=2 kind=tet single=False" in out.stdout and "peer=%s halfspace=True" % peer in out.stdout

@@ -17,10 +17,10 @@ s = d.get("strong")
 print("strong", {k: s[k] for k in ("ms_per_step", "value", "cuda_graph", "scatter_s", "local_cells", "owned_cells", "symbolic_ms_max", "topology_ms_max", "tags_ms", "assembly_ms")} if s else None)
 PY
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
-  bench.py --gpus $N --steps 20 --warmup 3 --no-graph --no-parity > gpurun_out/e_bench_${N}_eager.json 2> gpurun_out/e_bench_${N}_eager.err
+  bench.py --gpus $N --steps 20 --warmup 3 --no-peer --no-parity > gpurun_out/e_bench_${N}_eager.json 2> gpurun_out/e_bench_${N}_eager.err
 python - <<PY
 import json
 d = json.load(open("gpurun_out/e_bench_${N}_eager.json"))
 s = d.get("strong")
-print("strong eager", {k: s[k] for k in ("ms_per_step", "value", "cuda_graph")} if s else None)
+print("strong nccl all-reduce", {k: s[k] for k in ("ms_per_step", "value", "cuda_graph")} if s else None)
 PY
