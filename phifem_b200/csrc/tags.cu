@@ -11,6 +11,8 @@
 // thread per cell / facet, coalesced index loads, gathers that hit L2, warp-ballot counters.
 #include <type_traits>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace phifem {
@@ -784,6 +786,17 @@ SideStream& side_stream() {
 }
 }  // namespace
 
+namespace {
+bool facet_grid_full() {  // PHIFEM_FACETS_GRID=full: one tile per CTA instead of the persistent grid (tuning sweeps;
+  // measured slower at config E: 0.320 against 0.231 ms for the facet phase)
+  static const int v = [] {
+    const char* e = getenv("PHIFEM_FACETS_GRID");
+    return (e && e[0] == 'f') ? 1 : 0;
+  }();
+  return v != 0;
+}
+}  // namespace
+
 extern "C" int phifem_tag_facets(const phifem_mesh* mesh, const phifem_levelset* ls,
                                  const int8_t* cell_tags8, int32_t* facet_tags, int8_t* facet_tags8,
                                  int64_t* counters, void* stream) {
@@ -830,7 +843,7 @@ extern "C" int phifem_tag_facets_phase(const phifem_mesh* mesh, const phifem_lev
                                                                 facet_tags8, counters);
         cudaEventRecord(ss.join, ss.stream);
       }
-      const int grid = persistent_grid(k_tag_facets<CT, false>, kBlock, tiles);
+      const int grid = fork && facet_grid_full() ? (int)tiles : persistent_grid(k_tag_facets<CT, false>, kBlock, tiles);
       k_tag_facets<CT, false><<<grid, kBlock, 0, st>>>(*mesh, *ls, cell_tags8, facet_tags, facet_tags8,
                                                        counters);
       if (fork) {

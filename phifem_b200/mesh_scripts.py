@@ -155,8 +155,8 @@ def classify_sharded(mesh, dls, ws, group=None, world=1, mark=None, single_layer
     """Cells, then the interior facets WHILE the exterior-cell counts of the ranks travel, then the mesh-boundary facets
     (reference :469-474 makes their tags depend on the global "any exterior cell" flag).  The exchange is either
     `peer` (phifem_b200/peer.py: 8-byte stores into the peers' HBM over NVLink after the cell kernel, a read of the own
-    slots before the boundary kernel -- nothing that needs an SM while the persistent facet kernel runs) or, without it,
-    an 8-byte `torch.distributed` all-reduce.  `mark` (optional callable) is invoked after the cell kernel and at the
+    slots before the facet kernels: two one-warp kernels) or, without it, an 8-byte `torch.distributed` all-reduce
+    overlapped with the interior-facet kernel.  `mark` (optional callable) is invoked after the cell kernel and at the
     end (bench.py records CUDA events there)."""
     import torch.distributed as dist
     mark = mark or (lambda: None)
@@ -164,10 +164,11 @@ def classify_sharded(mesh, dls, ws, group=None, world=1, mark=None, single_layer
     mark()
     count = ws.counters[_lib.CNT_EXTERIOR:_lib.CNT_EXTERIOR + 1]
     if world > 1 and peer is not None:
+        # the ranks run in lockstep, so the peers' stores are there (or microseconds away) when this rank's cell kernel
+        # ends: collect at once and let the two facet kernels overlap on their fork / join streams as on one GPU
         peer.publish(count)
-        classify_facets(mesh, dls, ws, FACETS_INTERIOR)
         peer.collect(count)
-        classify_facets(mesh, dls, ws, FACETS_BOUNDARY)
+        classify_facets(mesh, dls, ws)
     elif world > 1:
         work = dist.all_reduce(count, group=group, async_op=True)
         classify_facets(mesh, dls, ws, FACETS_INTERIOR)
