@@ -19,9 +19,18 @@
 namespace phifem {
 namespace {
 
-constexpr int kRowsBlock = 128;
+#ifndef PHIFEM_ROWS_BLOCK
+#define PHIFEM_ROWS_BLOCK 128
+#endif
+constexpr int kRowsBlock = PHIFEM_ROWS_BLOCK;
 #ifndef PHIFEM_ROWS_MINBLOCKS
 #define PHIFEM_ROWS_MINBLOCKS 4
+#endif
+#ifndef PHIFEM_SURF_MINBLOCKS
+#define PHIFEM_SURF_MINBLOCKS PHIFEM_ROWS_MINBLOCKS
+#endif
+#ifndef PHIFEM_ONCE_MINBLOCKS
+#define PHIFEM_ONCE_MINBLOCKS 1
 #endif
 constexpr uint32_t kPad = 0xffffffffu;
 
@@ -255,7 +264,7 @@ __device__ __forceinline__ void ldg256(const double* p, double& a, double& b, do
 }
 
 template <int D>
-__global__ void __launch_bounds__(kRowsBlock) k_surface_once_p1(
+__global__ void __launch_bounds__(kRowsBlock, PHIFEM_ONCE_MINBLOCKS) k_surface_once_p1(
     const double* __restrict__ x, const double* __restrict__ phi, double sigma,
     const int32_t* __restrict__ macro, int64_t n_facets, const int32_t* __restrict__ entity_macro,
     int64_t n_entities, double* __restrict__ work) {
@@ -384,7 +393,7 @@ struct OthersGeom {
 
 // One pass over one row list.  KIND == kCells writes data / b of its rows, the surface passes add to them.
 template <int D, int KIND>
-__global__ void __launch_bounds__(kRowsBlock, PHIFEM_ROWS_MINBLOCKS) k_assemble_rows_p1(
+__global__ void __launch_bounds__(kRowsBlock, KIND == 1 ? PHIFEM_SURF_MINBLOCKS : PHIFEM_ROWS_MINBLOCKS) k_assemble_rows_p1(
     const double* __restrict__ x, const double* __restrict__ phi, const double* __restrict__ f,
     double sigma, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
     phifem_row_list rl, const double* __restrict__ surface_work, double* __restrict__ data,

@@ -39,7 +39,8 @@ cudaMemPool_t scratch_pool() {  // also used by csrc/rows_plan.cu
       pool = nullptr;
       return nullptr;
     }
-    uint64_t keep = UINT64_MAX;
+    uint64_t keep = 6ull << 30;  // cached between calls up to 6 GiB (the row-gather plan of 50 M tetrahedra needs ~3);
+                                 // anything above goes back to the driver at the next synchronisation
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
   return pool;

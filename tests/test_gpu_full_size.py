@@ -101,3 +101,33 @@ def test_full_size_operator_properties(problem):
     energy = float(u @ _spmv(plan0, A.data, u))
     assert abs(energy - 6.0 * vol) <= 1e-9 * 6.0 * vol
     assert abs(vol - 4.0 / 3.0 * np.pi * 0.45 ** 3) < 0.02                 # slightly above the ball volume
+
+
+def test_full_size_submesh_route(problem):
+    """`box_mode=False` at the benchmark size (reference src/phifem/mesh_scripts.py:635-645): the submesh of Omega_h
+    (19.8 M cells), tags transferred onto it, and the operator assembled on it with the plain `ds` measure -- the
+    submesh keeps the relative order of cells and vertices, so its CSR values are the box-mode values, entry by entry."""
+    mesh, phi, ctags, ftags, ds = problem
+    fn = fem.Function(fem.functionspace_p1_device(mesh), phi)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        sct, sft, sub, ds_sub, maps = mesh_scripts.compute_tags_measures(mesh, fn, 1, box_mode=False)
+    assert sub.num_cells == 19081700 + 725850
+    cmap = torch.as_tensor(maps[0].astype(np.int64), device="cuda")
+    vmap = torch.as_tensor(maps[1].astype(np.int64), device="cuda")
+    assert torch.equal(sct.values_dev, ctags.values_dev[cmap])                    # _transfer_tags, cells (:244)
+    assert torch.equal(sft.values_dev[sub.c2f.long()], ftags.values_dev[mesh.c2f[cmap].long()])   # ... facets (:244-260)
+    assert torch.equal(sub.x, mesh.x[vmap])
+    f = synthetic.ball_source(mesh.x)
+    box = assemble.build_plan(mesh, ctags, ftags, ds(100))
+    A, b = assemble.assemble_strong_dirichlet(box, phi, f, stab_coef=1.0)
+    splan = assemble.build_plan(sub, sct, sft, ds_sub)
+    As, bs = assemble.assemble_strong_dirichlet(splan, phi[vmap], f[vmap], stab_coef=1.0)
+    assert splan.nnz == box.nnz and splan.n_rows == vmap.numel()
+    rows_nnz = (box.indptr[1:] - box.indptr[:-1])
+    assert torch.equal(rows_nnz[vmap], splan.indptr[1:] - splan.indptr[:-1])       # rows outside Omega_h are empty
+    assert int(rows_nnz.sum()) == int(rows_nnz[vmap].sum())
+    assert torch.equal(vmap[As.indices.long()].to(torch.int32), A.indices)
+    scale = float(A.data.abs().max())
+    assert float((As.data - A.data).abs().max()) <= 1e-12 * scale
+    assert float((bs - b[vmap]).abs().max()) <= 1e-12 * float(b.abs().max())
