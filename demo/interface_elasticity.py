@@ -104,6 +104,8 @@ def main(mesh_size=0.2, iterations=4, solver="direct", pen_coef=1.0, stab_coef=1
                                                         stab_coef=stab_coef, bcs=bcs)
         if solver == "bicgstab":
             sol, info = solve.bicgstab(A, b, rtol=1e-9, maxiter=20000)
+            if not info.converged:
+                raise RuntimeError("the linear solve did not converge (%r): use --solver direct" % info)
             sol = sol.cpu()
         else:
             import scipy.sparse.linalg as spla

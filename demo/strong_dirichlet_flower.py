@@ -49,6 +49,8 @@ def main(n=200, degree=1, quiet=False):
     A, b = assemble.assemble_strong_dirichlet(plan, phi_h, f_h, stab_coef=1.0)
     lap("assembly (numeric)")
     w_h, info = solve.bicgstab(A, b, rtol=1e-10)
+    if not info.converged:
+        raise RuntimeError("the linear solve did not converge: %r" % info)
     lap("Jacobi-BiCGStab")
     phi_dev = torch.as_tensor(phi_h.x.array, device=w_h.device)
     u_h = w_h * phi_dev                      # main.py:165 (same space for w, phi and u here)

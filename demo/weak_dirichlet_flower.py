@@ -35,6 +35,8 @@ def main(n=200, quiet=False):
     plan = assemble.build_plan_weak_dirichlet(bg_mesh, cells_tags, facets_tags, ds_bdy(100), V=V)
     A, b = assemble.assemble_weak_dirichlet(plan, phi_h, f_h, u_D, pen_coef=1.0, stab_coef=1.0)
     sol, info = solve.bicgstab(A, b, rtol=1e-10)
+    if not info.converged:
+        raise RuntimeError("the linear solve did not converge: %r" % info)
     torch.cuda.synchronize()
     u_h = sol[0::2]
     if not quiet:

@@ -446,7 +446,10 @@ int phifem_apply_dirichlet(int64_t n_rows, const int32_t* indptr, const int32_t*
 /* The same for a structurally symmetric pattern (one space for trial and test functions: every operator here), driven
  * by the list bc_dofs[n_bc] of the marked dofs: the mirrored entry (j, c) of every entry (c, j) of a marked row is found by
  * binary search, so the work is the marked rows' lengths instead of a pass over the matrix.  The lifting adds into b
- * with fp64 reductions (order not fixed). */
+ * with fp64 reductions (order not fixed).
+ * PRECONDITIONS the call does not check: column indices sorted inside every row (the bisection), a structurally
+ * symmetric pattern (entry (j, c) exists whenever (c, j) does), and bc_dofs free of duplicates (two warps on the same
+ * row would lift twice; the Python wrapper passes torch.unique(bc_dofs)).  Opt-in: parity-tested on small systems only. */
 int phifem_apply_dirichlet_symmetric(int64_t n_rows, const int32_t* indptr, const int32_t* indices,
                                      const int32_t* bc_dofs, int64_t n_bc, const int8_t* bc_marker,
                                      const double* bc_values, double* data, double* b, void* stream);

@@ -76,6 +76,14 @@ class AssemblyPlan:
         n = mesh.num_vertices
         nv = mesh.cells.shape[1]
         self.n_rows = n
+        ents2 = entities.reshape(-1, 2)
+        if ents2.shape[0]:
+            # a one-sided entity must lie in a cell of dx((1,2)): its dof pairs are looked up in the pattern of those
+            # cells, and an entity of ds(101) or of another tag set would silently land in a neighbouring CSR slot
+            t = cell_tags8[ents2[:, 0].long()]
+            if not bool(((t == 1) | (t == 2)).all()):
+                raise ValueError("a (cell, local facet) entity names a cell that is not tagged 1 or 2: the strong-/weak-"
+                                 "Dirichlet plans take the entities of ds(100) (Gamma_h seen from Omega_h)")
         if symbolic not in ("auto", "torch", "native"):
             raise ValueError("symbolic must be 'auto', 'torch' or 'native'")
         native_ok = (method == "rows" and cell_pass == "rows" and not geometry and dev.type == "cuda")

@@ -48,13 +48,20 @@ class SolveInfo:
             self.iterations, self.residual, self.converged, self.n_active)
 
 
-def bicgstab(A, b, rtol=1e-10, maxiter=10000, check_every=10, x0=None):
+def bicgstab(A, b, rtol=1e-10, maxiter=10000, check_every=10, x0=None, pivot_tol=1e-14):
     """Solve A x = b on the rows with a non-zero diagonal (x = 0 elsewhere).  Returns (x, SolveInfo);
-    `residual` is |b - A x| / |b| over the active rows."""
+    `residual` is |b - A x| / |b| over the active rows.  pivot_tol: a row is a null pivot when |a_rr| <= pivot_tol * max_c |a_rc|.
+    Callers must check `info.converged` (the demos raise when it is False)."""
     if not b.is_cuda:
         raise RuntimeError("phifem_b200.solve: tensors must live on a CUDA device (no CPU fallback)")
     d = diagonal(A)
-    active = d != 0
+    # null pivots (MUMPS ICNTL(24)): rows without a diagonal entry or with one that is zero RELATIVE to the row -- a
+    # diagonal of 1e-300 beside entries of order one would otherwise turn the Jacobi scaling into 1e300
+    counts = (A.indptr[1:] - A.indptr[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(A.shape[0], device=b.device), counts)
+    rmax = torch.zeros_like(d).scatter_reduce_(0, rows, A.data.abs(), reduce="amax", include_self=True)
+    del rows
+    active = d.abs() > pivot_tol * rmax
     minv = torch.where(active, 1.0 / torch.where(active, d, torch.ones_like(d)), torch.zeros_like(d))
     mask = active.to(torch.float64)
     bm = b * mask
