@@ -559,17 +559,27 @@ def measure_e2e(w, args, degree):
     out_h = {"ct": torch.empty(mesh.num_cells, dtype=torch.int8).pin_memory(),
              "ft": torch.empty(mesh.num_facets, dtype=torch.int8).pin_memory(),
              "data": torch.empty(plan.nnz, dtype=torch.float64).pin_memory(),
-             "b": torch.empty(plan.n_rows, dtype=torch.float64).pin_memory()}
+             "b": torch.empty(0, dtype=torch.float64)}
+    # box mode keeps the rows of every vertex of the background mesh; 61 % of them (config E) are empty -- no cell of
+    # Omega_h touches the vertex -- and their entry of b is a structural zero: the load vector crosses PCIe compacted to
+    # the rows of the pattern (the index list is part of the plan, fetched once)
+    active_rows = torch.nonzero(plan.indptr[1:] > plan.indptr[:-1]).reshape(-1)
+    out_h["b"] = torch.empty(active_rows.numel(), dtype=torch.float64).pin_memory()
+    rows_h = active_rows.to(torch.int32).cpu()
     side = torch.cuda.Stream()
     tags_done = torch.cuda.Event()
     f_done = torch.cuda.Event()
+    phi_up = torch.cuda.Event()
 
     def e2e_step():
         # host level set -> device once; the same device-resident Function feeds the tags and (for P1) the
         # assembly, as a user holding one phi_h would write it
         phi_d = phi_h.to(dev, non_blocking=True)
-        # the source term follows the level set over PCIe on the side stream while the tag kernels run
+        phi_up.record()
+        # the source term FOLLOWS the level set over PCIe (side stream, after the level set has landed: two uploads
+        # at once share the link and delay the tag kernels) while the tag kernels run
         with torch.cuda.stream(side):
+            side.wait_event(phi_up)
             f_d = f_h.to(dev, non_blocking=True)
             f_done.record()
         fn_h = fem.Function(w.V, phi_d)
@@ -587,7 +597,7 @@ def measure_e2e(w, args, degree):
         A_, b_ = assemble.assemble_strong_dirichlet(plan, phi_d if degree == 1 else phi_asm_h, f_d, stab_coef=1.0)
         f_d.record_stream(torch.cuda.current_stream())
         out_h["data"].copy_(A_.data, non_blocking=True)
-        out_h["b"].copy_(b_, non_blocking=True)
+        out_h["b"].copy_(b_.index_select(0, active_rows), non_blocking=True)
         torch.cuda.synchronize()
 
     e2e_steps = max(2, min(args.steps, 5))
@@ -603,7 +613,7 @@ def measure_e2e(w, args, degree):
             "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in out_h.values())),
             "api": "compute_tags_measures(box_mode=True) + assemble_strong_dirichlet(plan, ...) with "
                    "pinned host level set / source in and pinned host tags (1 byte per cell / facet) + CSR values "
-                   "+ b out, source-term upload overlapped with the tag kernels, tag copies with the assembly; "
+                   "+ b on the %d non-empty rows of the %d out," % (rows_h.numel(), plan.n_rows) + " source-term upload overlapped with the tag kernels, tag copies with the assembly; "
                    "assembly plan (symbolic phase) reused; one step at a time"}
 
 

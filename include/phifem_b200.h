@@ -53,6 +53,14 @@ typedef struct phifem_mesh {
   double detj_max;        /* lets the P1 classifier skip the coordinate gather on uncut cells */
   const int32_t* boundary_facets; /* optional [n_boundary_facets]: facets with one cell, ascending; */
   int64_t n_boundary_facets;      /* lets the facet classifier run its ds detection as a second pass */
+  /* optional, filled once per mesh by phifem_boundary_records (both or neither): what the ds detection of
+   * mesh_scripts.py:434-452 needs of the mesh, so that the per-step pass over the mesh-boundary facets only gathers
+   * the level set.  boundary_owner[i] = {owner cell of boundary_facets[i], meta}; meta = n | lf_0 << 4 | lf_1 << 6 |
+   * lf_2 << 8 | lf_3 << 10 | first << 12 with n = number of mesh-boundary facets of the owner, lf_k their local
+   * indices in ascending facet index, first = 1 iff boundary_facets[i] is the smallest of them;
+   * boundary_scale[i][k] = integration scale (edge length / twice the triangle area) of local facet lf_k. */
+  const uint32_t* boundary_owner; /* [n_boundary_facets, 2] */
+  const double* boundary_scale;   /* [n_boundary_facets, 4] */
 } phifem_mesh;
 
 /* Discrete level set as seen by the detection forms (src/phifem/mesh_scripts.py:95-134).
@@ -86,6 +94,8 @@ enum {
   PHIFEM_CNT_FACET_ZERO_DEN = 11, /* cells whose ds-denominator is ~0 */
   PHIFEM_CNT_FACET_CONFLICT = 12, /* facets the reference algebra would emit twice */
   PHIFEM_CNT_BOUNDARY_OWNERS = 13, /* cells owning at least one mesh-boundary facet */
+  PHIFEM_CNT_CALLER0 = 14,     /* slots 14, 15: never written by the tag kernels; the Python host parks the two */
+  PHIFEM_CNT_CALLER1 = 15,     /* one-sided entity counts here so that ONE device -> host copy returns everything */
   PHIFEM_N_COUNTERS = 16
 };
 
@@ -120,6 +130,12 @@ int phifem_tag_facets(const phifem_mesh* mesh, const phifem_levelset* ls, const 
  * flag, so PHIFEM_FACETS_INTERIOR can run while the reduction is in flight and PHIFEM_FACETS_BOUNDARY (the mesh-boundary
  * facets, which do read it; needs mesh.boundary_facets) after it.  phases = both bits == phifem_tag_facets. */
 enum { PHIFEM_FACETS_INTERIOR = 1, PHIFEM_FACETS_BOUNDARY = 2 };
+
+/* Once per mesh: the static part of the ds detection on the mesh-boundary facets (mesh.boundary_owner /
+ * mesh.boundary_scale, see phifem_mesh; needs mesh.boundary_facets).  The scales are computed by the same device
+ * function, in the same operation order, as the pass that evaluates them on the fly: tags and counters do not depend
+ * on whether the records are present. */
+int phifem_boundary_records(const phifem_mesh* mesh, uint32_t* boundary_owner, double* boundary_scale, void* stream);
 int phifem_tag_facets_phase(const phifem_mesh* mesh, const phifem_levelset* ls, const int8_t* cell_tags8,
                             int32_t* facet_tags, int8_t* facet_tags8, int64_t* counters, int32_t phases,
                             void* stream);
@@ -141,6 +157,14 @@ int phifem_entity_records(const phifem_mesh* mesh, const int8_t* cell_tags8,
 int phifem_integration_entities(const phifem_mesh* mesh, const int8_t* cell_tags8, const int8_t* facet_tags8,
                                 int32_t facet_tag, uint32_t cell_mask, int32_t* entities, int64_t capacity,
                                 int64_t* n_entities, void* stream);
+
+/* The two halves of phifem_integration_entities WITHOUT host synchronisation, for callers that read several counts
+ * (and the tag counters) back with one device -> host copy: _count writes the number of pairs to *n_entities_dev
+ * (DEVICE, int64); _fill writes exactly n pairs, n being that count as read back by the caller. */
+int phifem_integration_entities_count(const phifem_mesh* mesh, const int8_t* cell_tags8, const int8_t* facet_tags8,
+                                      int32_t facet_tag, uint32_t cell_mask, int64_t* n_entities_dev, void* stream);
+int phifem_integration_entities_fill(const phifem_mesh* mesh, const int8_t* cell_tags8, const int8_t* facet_tags8,
+                                     int32_t facet_tag, uint32_t cell_mask, int32_t* entities, int64_t n, void* stream);
 
 /* ---- strong-Dirichlet phi-FEM operator, P1 on triangles / tetrahedra --------------------------
  * Forms: demo/strong-dirichlet/flower/main.py:104-128.  dof = vertex.  `data` (CSR values) and `b`

@@ -15,6 +15,7 @@ CELL_TYPE_ID = {"triangle": 0, "quadrilateral": 1, "tetrahedron": 2}
 N_COUNTERS = 16
 CNT_INTERIOR, CNT_CUT, CNT_EXTERIOR, CNT_UNTAGGED, CNT_ZERO_DEN, CNT_ZERO_DEN_AMBIGUOUS = 0, 1, 2, 3, 4, 5
 CNT_FACET_ZERO_DEN, CNT_FACET_CONFLICT, CNT_BOUNDARY_OWNERS = 11, 12, 13
+CNT_CALLER0, CNT_CALLER1 = 14, 15
 
 _vp = ctypes.c_void_p
 
@@ -25,7 +26,8 @@ class CMesh(ctypes.Structure):
                 ("n_facets", ctypes.c_int64),
                 ("x", _vp), ("cells", _vp), ("c2f", _vp), ("f2c", _vp),
                 ("detj_min", ctypes.c_double), ("detj_max", ctypes.c_double),
-                ("boundary_facets", _vp), ("n_boundary_facets", ctypes.c_int64)]
+                ("boundary_facets", _vp), ("n_boundary_facets", ctypes.c_int64),
+                ("boundary_owner", _vp), ("boundary_scale", _vp)]
 
 
 class CLevelset(ctypes.Structure):
@@ -101,6 +103,7 @@ _SIGNATURES = {
                                         ctypes.c_int32, _vp, _vp, _vp, _vp, _vp]),
     "phifem_tag_facets": (ctypes.c_int, [ctypes.POINTER(CMesh), ctypes.POINTER(CLevelset), _vp, _vp,
                                          _vp, _vp, _vp]),
+    "phifem_boundary_records": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, _vp]),
     "phifem_tag_facets_phase": (ctypes.c_int, [ctypes.POINTER(CMesh), ctypes.POINTER(CLevelset), _vp, _vp,
                                                _vp, _vp, ctypes.c_int32, _vp]),
     "phifem_entity_records": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, ctypes.c_int32,
@@ -151,6 +154,10 @@ _SIGNATURES = {
     "phifem_pattern_view_of": (ctypes.c_int, [_vp, ctypes.POINTER(CPatternView)]),
     "phifem_integration_entities": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, ctypes.c_int32, ctypes.c_uint32,
                                                    _vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64), _vp]),
+    "phifem_integration_entities_count": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, ctypes.c_int32,
+                                                         ctypes.c_uint32, _vp, _vp]),
+    "phifem_integration_entities_fill": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, ctypes.c_int32,
+                                                        ctypes.c_uint32, _vp, ctypes.c_int64, _vp]),
     "phifem_pattern_destroy": (None, [_vp]),
     "phifem_rows_plan_create": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, _vp, ctypes.c_int64, _vp,
                                                ctypes.c_int32, ctypes.POINTER(_vp), _vp]),
@@ -241,11 +248,15 @@ def require_cuda(mesh):
     load()
 
 
-def c_mesh(mesh, with_facets=True):
+def c_mesh(mesh, with_facets=True, with_records=True):
     require_cuda(mesh)
     lo, hi = mesh.detj_bounds() if mesh.cell_type != "quadrilateral" else (0.0, 0.0)
+    owner = scale = None
+    if with_facets and with_records and mesh.cell_type != "quadrilateral":
+        owner, scale = mesh.boundary_records()
     return CMesh(CELL_TYPE_ID[mesh.cell_type], mesh.gdim, mesh.num_vertices, mesh.num_cells,
                  mesh.num_facets if with_facets else 0, ptr(mesh.x), ptr(mesh.cells),
                  ptr(mesh.c2f) if with_facets else None, ptr(mesh.f2c) if with_facets else None,
                  lo, hi, ptr(mesh.boundary_facets) if with_facets else None,
-                 mesh.boundary_facets.numel() if with_facets else 0)
+                 mesh.boundary_facets.numel() if with_facets else 0,
+                 ptr(owner) if owner is not None else None, ptr(scale) if scale is not None else None)

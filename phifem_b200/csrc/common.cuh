@@ -54,6 +54,40 @@ template <> struct CellTraits<PHIFEM_TETRAHEDRON> {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// ---- TMA 1-D bulk copies global -> shared with mbarrier completion (sm_90+; SASS UBLKCP / SYNCS) -------------------
+// The streaming kernels stage their contiguous index arrays (cells, f2c) through shared memory with these: one elected
+// thread posts whole tiles several stages ahead, so the bytes in flight per SM no longer depend on how many warps
+// are resident or on which phase of their loop they are in.
+namespace tma {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// makes the freshly initialised barriers visible to the async proxy (the TMA unit)
+__device__ __forceinline__ void fence_init() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// dst, src and bytes multiples of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t ok = 0;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+}  // namespace tma
+
 // Persistent grid-stride kernels: exactly one resident wave (SMs x occupancy), never more CTAs than tiles.
 template <typename K>
 inline int persistent_grid(K kernel, int block, int64_t n_tiles) {

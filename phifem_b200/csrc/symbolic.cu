@@ -332,6 +332,57 @@ extern "C" int phifem_pattern_create_p1(const phifem_mesh* mesh, const int8_t* c
   return PHIFEM_OK;
 }
 
+extern "C" int phifem_integration_entities_count(const phifem_mesh* mesh, const int8_t* cell_tags8,
+                                                 const int8_t* facet_tags8, int32_t facet_tag, uint32_t cell_mask,
+                                                 int64_t* n_entities_dev, void* stream) {
+  PHIFEM_CHECK_ARG(mesh != nullptr && n_entities_dev != nullptr, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(n_entities_dev, 0, sizeof(int64_t), st);
+  if (mesh->n_facets == 0) return PHIFEM_OK;
+  return phifem_entity_records(mesh, cell_tags8, facet_tags8, facet_tag, cell_mask, nullptr, 0, n_entities_dev, stream);
+}
+
+extern "C" int phifem_integration_entities_fill(const phifem_mesh* mesh, const int8_t* cell_tags8,
+                                                const int8_t* facet_tags8, int32_t facet_tag, uint32_t cell_mask,
+                                                int32_t* entities, int64_t n, void* stream) {
+  PHIFEM_CHECK_ARG(mesh != nullptr, "null pointer");
+  PHIFEM_CHECK_ARG(n >= 0 && (n == 0 || entities), "entity buffer");
+  if (n == 0 || mesh->n_facets == 0) return PHIFEM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemPool_t pool = scratch_pool();
+  if (!pool) {
+    set_error("phifem_integration_entities_fill: cannot create the scratch memory pool");
+    return PHIFEM_ERR_CUDA;
+  }
+  Scratch tmp(st, pool);
+  auto fail = [&](const char* what) {
+    set_error("phifem_integration_entities_fill: %s: %s", what, cudaGetErrorString(cudaGetLastError()));
+    return PHIFEM_ERR_CUDA;
+  };
+  int64_t* d_n = (int64_t*)tmp.get(sizeof(int64_t));
+  int64_t* rec = (int64_t*)tmp.get(sizeof(int64_t) * 3 * n);
+  unsigned long long* first = (unsigned long long*)tmp.get(sizeof(unsigned long long) * mesh->n_cells);
+  int64_t* skey = (int64_t*)tmp.get(sizeof(int64_t) * n);
+  int64_t* sval = (int64_t*)tmp.get(sizeof(int64_t) * n);
+  int64_t* skey2 = (int64_t*)tmp.get(sizeof(int64_t) * n);
+  int64_t* sval2 = (int64_t*)tmp.get(sizeof(int64_t) * n);
+  if (!d_n || !rec || !first || !skey || !sval || !skey2 || !sval2) return fail("scratch allocation");
+  cudaMemsetAsync(d_n, 0, sizeof(int64_t), st);
+  if (int rc = phifem_entity_records(mesh, cell_tags8, facet_tags8, facet_tag, cell_mask, rec, n, d_n, stream))
+    return rc;
+  cudaMemsetAsync(first, 0xff, sizeof(unsigned long long) * mesh->n_cells, st);
+  k_entity_first_key<<<blocks_for(n), kBlockSym, 0, st>>>(rec, n, first);
+  k_entity_sort_keys<<<blocks_for(n), kBlockSym, 0, st>>>(rec, n, first, skey, sval);
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, skey, skey2, sval, sval2, (int)n, 0, 40, st);
+  void* ws = tmp.get(bytes);
+  if (!ws) return fail("scratch allocation");
+  cub::DeviceRadixSort::SortPairs(ws, bytes, skey, skey2, sval, sval2, (int)n, 0, 40, st);  // keys < 2^(32 + 1 + 3)
+  k_entity_unpack<<<blocks_for(n), kBlockSym, 0, st>>>(sval2, n, entities);
+  if (cudaGetLastError() != cudaSuccess) return fail("ordering kernels");
+  return PHIFEM_OK;
+}
+
 extern "C" int phifem_integration_entities(const phifem_mesh* mesh, const int8_t* cell_tags8, const int8_t* facet_tags8,
                                            int32_t facet_tag, uint32_t cell_mask, int32_t* entities, int64_t capacity,
                                            int64_t* n_entities, void* stream) {
@@ -345,42 +396,29 @@ extern "C" int phifem_integration_entities(const phifem_mesh* mesh, const int8_t
     set_error("phifem_integration_entities: cannot create the scratch memory pool");
     return PHIFEM_ERR_CUDA;
   }
-  Scratch tmp(st, pool);
-  auto fail = [&](const char* what) {
-    set_error("phifem_integration_entities: %s: %s", what, cudaGetErrorString(cudaGetLastError()));
-    return PHIFEM_ERR_CUDA;
-  };
-  int64_t* d_n = (int64_t*)tmp.get(sizeof(int64_t));
-  if (!d_n) return fail("scratch allocation");
-  // pass 1 counts the candidates, pass 2 writes them
   int64_t n = 0;
-  cudaMemsetAsync(d_n, 0, sizeof(int64_t), st);
-  if (int rc = phifem_entity_records(mesh, cell_tags8, facet_tags8, facet_tag, cell_mask, nullptr, 0, d_n, stream))
-    return rc;
-  if (cudaMemcpyAsync(&n, d_n, sizeof(n), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-      cudaStreamSynchronize(st) != cudaSuccess)
-    return fail("counting");
+  {
+    Scratch tmp(st, pool);
+    int64_t* d_n = (int64_t*)tmp.get(sizeof(int64_t));
+    if (!d_n) {
+      set_error("phifem_integration_entities: scratch allocation: %s", cudaGetErrorString(cudaGetLastError()));
+      return PHIFEM_ERR_CUDA;
+    }
+    if (int rc = phifem_integration_entities_count(mesh, cell_tags8, facet_tags8, facet_tag, cell_mask, d_n, stream))
+      return rc;
+    if (cudaMemcpyAsync(&n, d_n, sizeof(n), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+      set_error("phifem_integration_entities: counting: %s", cudaGetErrorString(cudaGetLastError()));
+      return PHIFEM_ERR_CUDA;
+    }
+  }
   *n_entities = n;
   if (n == 0 || n > capacity) return PHIFEM_OK;  // the caller retries with a buffer of *n_entities pairs
-  int64_t* rec = (int64_t*)tmp.get(sizeof(int64_t) * 3 * n);
-  unsigned long long* first = (unsigned long long*)tmp.get(sizeof(unsigned long long) * mesh->n_cells);
-  int64_t* skey = (int64_t*)tmp.get(sizeof(int64_t) * n);
-  int64_t* sval = (int64_t*)tmp.get(sizeof(int64_t) * n);
-  int64_t* skey2 = (int64_t*)tmp.get(sizeof(int64_t) * n);
-  int64_t* sval2 = (int64_t*)tmp.get(sizeof(int64_t) * n);
-  if (!rec || !first || !skey || !sval || !skey2 || !sval2) return fail("scratch allocation");
-  cudaMemsetAsync(d_n, 0, sizeof(int64_t), st);
-  if (int rc = phifem_entity_records(mesh, cell_tags8, facet_tags8, facet_tag, cell_mask, rec, n, d_n, stream))
+  if (int rc = phifem_integration_entities_fill(mesh, cell_tags8, facet_tags8, facet_tag, cell_mask, entities, n, stream))
     return rc;
-  cudaMemsetAsync(first, 0xff, sizeof(unsigned long long) * mesh->n_cells, st);
-  k_entity_first_key<<<blocks_for(n), kBlockSym, 0, st>>>(rec, n, first);
-  k_entity_sort_keys<<<blocks_for(n), kBlockSym, 0, st>>>(rec, n, first, skey, sval);
-  size_t bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, skey, skey2, sval, sval2, (int)n, 0, 40, st);
-  void* ws = tmp.get(bytes);
-  if (!ws) return fail("scratch allocation");
-  cub::DeviceRadixSort::SortPairs(ws, bytes, skey, skey2, sval, sval2, (int)n, 0, 40, st);  // keys < 2^(32 + 1 + 3)
-  k_entity_unpack<<<blocks_for(n), kBlockSym, 0, st>>>(sval2, n, entities);
-  if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) return fail("ordering kernels");
+  if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+    set_error("phifem_integration_entities: ordering kernels: %s", cudaGetErrorString(cudaGetLastError()));
+    return PHIFEM_ERR_CUDA;
+  }
   return PHIFEM_OK;
 }

@@ -47,6 +47,11 @@ __device__ __forceinline__ int classify(double num, double den) {
 
 __device__ __forceinline__ bool is_close_to_zero(double den) { return fabs(den) <= 1e-8; }
 
+// sm_100 256-bit read-only load (LDG.E.256)
+__device__ __forceinline__ void ldg256(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
 template <int CT>
 __device__ __forceinline__ void load_cell(const phifem_mesh& m, int64_t c, int (&v)[4],
                                           double (&xc)[4][3]) {
@@ -316,6 +321,191 @@ __global__ void __launch_bounds__(kBlock, PHIFEM_TAG_CELLS_MINBLOCKS) k_tag_cell
     done[par] = end;
     par ^= 1;
   }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) cnt.add(local[i], i);
+  cnt.flush(counters, PHIFEM_CNT_INTERIOR, 6);
+}
+
+// The same classifier with `cells` staged through shared memory by TMA bulk copies (the default).  A tile is
+// kBlock * kUnroll cells (16 KB of tetrahedra, 12 KB of triangles); thread 0 keeps kCellStages tiles in flight per CTA, so
+// the 0.8 GB index stream -- the only HBM traffic of the kernel that matters -- is requested as whole tiles several tiles
+// ahead instead of by per-thread LDG.128s whose number in flight follows the resident warps' loop phase, and a warp no
+// longer waits out a DRAM round trip before it can issue its class-byte gathers.  The cell -> thread mapping stays the
+// strided one (slot u of thread t = cell t + 256 u of the tile: a gather instruction of a warp covers 32 consecutive
+// cells, i.e. a handful of sectors of the class array); the tag bytes of a tile are collected in shared memory and leave
+// as one coalesced 32-bit word per thread AFTER the next tile's barrier, when the exact path has filled in the parked
+// cells (three 1 KB output buffers rotate so that one barrier per tile suffices).
+#ifndef PHIFEM_TAG_CELLS_STAGES
+#define PHIFEM_TAG_CELLS_STAGES 2
+#endif
+#ifndef PHIFEM_TAG_CELLS_STAGED_MINBLOCKS
+#define PHIFEM_TAG_CELLS_STAGED_MINBLOCKS 4
+#endif
+constexpr int kCellStages = PHIFEM_TAG_CELLS_STAGES;
+constexpr int kCellTile = kBlock * kUnroll;
+template <int CT> constexpr size_t staged_cells_smem() {
+  return (size_t)kCellStages * kCellTile * CellTraits<CT>::nv * sizeof(int32_t);
+}
+
+template <int CT>
+__global__ void __launch_bounds__(kBlock, PHIFEM_TAG_CELLS_STAGED_MINBLOCKS) k_tag_cells_p1_staged(
+    phifem_mesh m, const double* __restrict__ phi, const uint8_t* __restrict__ vclass, bool exact_zero_den,
+    int32_t* __restrict__ tags, int8_t* __restrict__ tags8, int64_t* counters) {
+  using T = CellTraits<CT>;
+  constexpr int NV = T::nv;
+  extern __shared__ __align__(128) int32_t s_cells[];  // [kCellStages][kCellTile * NV]
+  __shared__ alignas(8) uint64_t s_bar[kCellStages];
+  __shared__ unsigned int scnt[6];
+  __shared__ int s_pend[2][kCellTile];
+  __shared__ unsigned int s_np[2];
+  __shared__ alignas(16) unsigned int s_out[3][kCellTile / 4];
+  if (threadIdx.x < 2) s_np[threadIdx.x] = 0u;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kCellStages; ++s) tma::mbar_init(&s_bar[s], 1);
+    tma::fence_init();
+  }
+  BlockCounters cnt(scnt, 6);  // (its constructor synchronises the block)
+  unsigned int local[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+  unsigned int done[2] = {0u, 0u};
+  int par = 0, ob = 0;
+  constexpr uint32_t kTileBytes = kCellTile * NV * 4;
+  const int64_t n_full = m.n_cells / kCellTile;
+  auto post = [&](int64_t t, int s) {
+    tma::mbar_expect_tx(&s_bar[s], kTileBytes);
+    tma::bulk_g2s(s_cells + (size_t)s * kCellTile * NV, m.cells + t * kCellTile * NV, kTileBytes, &s_bar[s]);
+  };
+  if (threadIdx.x == 0)
+    for (int s = 0; s < kCellStages; ++s) {
+      const int64_t t = blockIdx.x + (int64_t)s * gridDim.x;
+      if (t < n_full) post(t, s);
+    }
+  auto decide = [&](const int (&v)[kUnroll][4], const bool (&valid)[kUnroll], int64_t base) {
+    unsigned int all[kUnroll], any[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      all[u] = 0xffu;
+      any[u] = 0u;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const unsigned int c = __ldg(vclass + v[u][k]);
+        all[u] &= c;
+        any[u] |= c;
+      }
+    }
+    uint8_t* out = reinterpret_cast<uint8_t*>(s_out[ob]);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int pos = u * kBlock + (int)threadIdx.x;
+      bool fast = (all[u] & 3u) != 0u && (all[u] & 4u) != 0u;
+      const int tag = (all[u] & 1u) ? 3 : 1;
+      bool zden = false, ambiguous = false;
+      if (fast && !(any[u] & 8u)) {
+        if (all[u] & 16u) zden = true;
+        else if (exact_zero_den) fast = false;
+        else ambiguous = true;
+      }
+      if (!valid[u]) continue;
+      if (!fast) {  // parked: position inside the tile
+        const unsigned int i = atomicAdd(&s_np[par], 1u) - done[par];
+        s_pend[par][i] = pos;
+        continue;
+      }
+      out[pos] = (uint8_t)tag;
+      if (tags) tags[base + pos] = tag;
+      local[0] += tag == 1;
+      local[2] += tag == 3;
+      local[4] += zden;
+      local[5] += ambiguous;
+    }
+  };
+  auto exact_pass = [&](int64_t base) {  // after the tile's barrier: the parked cells, one per thread
+    uint8_t* out = reinterpret_cast<uint8_t*>(s_out[ob]);
+    const unsigned int end = s_np[par];
+    for (unsigned int i = done[par] + threadIdx.x; i < end; i += blockDim.x) {
+      const int pos = s_pend[par][i - done[par]];
+      const int64_t c = base + pos;
+      int w[4] = {0, 0, 0, 0};
+      double p[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        w[k] = __ldg(m.cells + c * NV + k);
+        p[k] = __ldg(phi + w[k]);
+      }
+      const int r = tag_cell_exact<CT>(m.x, w[0], w[1], w[2], w[3], p[0], p[1], p[2], p[3]);
+      const int tag = r & 0xff;
+      if (tags) tags[c] = tag;
+      out[pos] = (uint8_t)tag;
+      local[0] += tag == 1;
+      local[1] += tag == 2;
+      local[2] += tag == 3;
+      local[3] += tag == 0;
+      local[4] += (r >> 8) != 0;
+    }
+    done[par] = end;
+    par ^= 1;
+  };
+  auto flush = [&](int buf, int64_t base) {  // the tags of a finished tile: one word per thread
+    const int64_t c0 = base + (int64_t)threadIdx.x * 4;
+    const unsigned int w = s_out[buf][threadIdx.x];
+    if (c0 + 3 < m.n_cells) {
+      *reinterpret_cast<unsigned int*>(tags8 + c0) = w;
+    } else {
+      for (int q = 0; q < 4; ++q)
+        if (c0 + q < m.n_cells) tags8[c0 + q] = (int8_t)(w >> (8 * q));
+    }
+  };
+  int64_t prev_base = -1;
+  auto finish_tile = [&](int64_t base) {  // called by every thread right after the tile's barrier
+    if (prev_base >= 0) flush(ob == 0 ? 2 : ob - 1, prev_base);
+    exact_pass(base);
+    prev_base = base;
+    ob = ob == 2 ? 0 : ob + 1;
+  };
+  int k = 0;
+  for (int64_t t = blockIdx.x; t < n_full; t += gridDim.x, ++k) {
+    const int s = k % kCellStages;
+    tma::mbar_wait(&s_bar[s], (uint32_t)(k / kCellStages) & 1u);
+    const int32_t* tile = s_cells + (size_t)s * kCellTile * NV;
+    int v[kUnroll][4];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int pos = u * kBlock + (int)threadIdx.x;
+      if constexpr (NV == 4) {
+        const int4 q = reinterpret_cast<const int4*>(tile)[pos];
+        v[u][0] = q.x; v[u][1] = q.y; v[u][2] = q.z; v[u][3] = q.w;
+      } else {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) v[u][q] = tile[pos * NV + q];
+        v[u][3] = 0;
+      }
+    }
+    const bool valid[kUnroll] = {true, true, true, true};
+    decide(v, valid, t * kCellTile);
+    __syncthreads();  // parked list and output bytes complete, every thread done with the stage
+    if (threadIdx.x == 0) {
+      const int64_t tn = t + (int64_t)kCellStages * gridDim.x;
+      if (tn < n_full) post(tn, s);
+    }
+    finish_tile(t * kCellTile);
+  }
+  if (blockIdx.x == (unsigned)(n_full % gridDim.x) && n_full * kCellTile < m.n_cells) {  // the ragged end
+    const int64_t base = n_full * kCellTile;
+    int v[kUnroll][4];
+    bool valid[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t c = base + u * kBlock + (int64_t)threadIdx.x;
+      valid[u] = c < m.n_cells;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[u][q] = (valid[u] && q < NV) ? __ldg(m.cells + c * NV + q) : 0;
+    }
+    decide(v, valid, base);
+    __syncthreads();
+    finish_tile(base);
+  }
+  __syncthreads();  // the last tile's exact path has written its bytes
+  if (prev_base >= 0) flush(ob == 0 ? 2 : ob - 1, prev_base);
 #pragma unroll
   for (int i = 0; i < 6; ++i) cnt.add(local[i], i);
   cnt.flush(counters, PHIFEM_CNT_INTERIOR, 6);
@@ -611,6 +801,244 @@ __global__ void __launch_bounds__(kBlock, 4) k_tag_facets(phifem_mesh m, phifem_
   cnt.flush(counters, PHIFEM_CNT_FACET_ZERO_DEN, 3);
 }
 
+// ---- mesh-boundary facets from per-mesh records ----------------------------------------------------------------------
+// k_tag_boundary_facets walks c2f -> f2c -> coordinates for every mesh-boundary facet on every step: five levels of
+// dependent gathers over 0.25 M threads, 66 us at config E that do not overlap with the streaming kernel (the facet phase
+// measured 0.236 ms = 0.174 + 0.068).  Which facets of the owner lie on the mesh boundary, in which order they are
+// summed, whether this facet is the owner's first, and the integration scales are properties of the MESH: tabulated once
+// (k_boundary_records), they leave the per-step pass with one level of gathers (the owner's level-set values).
+template <int CT>
+__global__ void __launch_bounds__(kBlock) k_boundary_records(phifem_mesh m, uint32_t* __restrict__ owner_meta,
+                                                             double* __restrict__ scale) {
+  using T = CellTraits<CT>;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m.n_boundary_facets) return;
+  const int32_t f = __ldg(m.boundary_facets + i);
+  const int c = __ldg(m.f2c + 2 * (int64_t)f);
+  int v[4];
+  double xc[4][3];
+  load_cell<CT>(m, c, v, xc);
+  int32_t fid[4];
+  bool isb[4];
+  int32_t smallest = INT32_MAX;
+#pragma unroll
+  for (int j = 0; j < T::nf; ++j) {
+    fid[j] = __ldg(m.c2f + (int64_t)c * T::nf + j);
+    isb[j] = __ldg(m.f2c + 2 * (int64_t)fid[j] + 1) < 0;
+    if (isb[j] && fid[j] < smallest) smallest = fid[j];
+  }
+  uint32_t meta = smallest == f ? (1u << 12) : 0u;
+  double sc[4] = {0.0, 0.0, 0.0, 0.0};
+  int n = 0;
+  int32_t last = -1;
+  for (int round = 0; round < T::nf; ++round) {  // ascending facet index, as owner_is_ds_cut sums them
+    int lf = -1;
+    int32_t best = INT32_MAX;
+#pragma unroll
+    for (int j = 0; j < T::nf; ++j)
+      if (isb[j] && fid[j] > last && fid[j] < best) {
+        best = fid[j];
+        lf = j;
+      }
+    if (lf < 0) break;
+    last = best;
+    if constexpr (CT != PHIFEM_QUADRILATERAL) sc[n] = facet_scale<CT>(xc, lf);
+    meta |= (uint32_t)lf << (4 + 2 * n);
+    ++n;
+  }
+  meta |= (uint32_t)n;
+  owner_meta[2 * i] = (uint32_t)c;
+  owner_meta[2 * i + 1] = meta;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) scale[4 * i + q] = sc[q];
+}
+
+template <int CT>
+__global__ void __launch_bounds__(kBlock) k_tag_boundary_facets_rec(phifem_mesh m, phifem_levelset ls,
+                                                                    const int8_t* __restrict__ ctags,
+                                                                    int32_t* __restrict__ ftags,
+                                                                    int8_t* __restrict__ ftags8,
+                                                                    int64_t* counters) {
+  using T = CellTraits<CT>;
+  __shared__ unsigned int scnt[4];
+  BlockCounters cnt(scnt, 3);
+  unsigned int n_zden = 0, n_conflict = 0, n_owner = 0;
+  const bool anyE = *reinterpret_cast<volatile int64_t*>(counters + PHIFEM_CNT_EXTERIOR) > 0;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m.n_boundary_facets) {
+    const int32_t f = __ldg(m.boundary_facets + i);
+    const uint2 om = __ldg(reinterpret_cast<const uint2*>(m.boundary_owner) + i);
+    double sc[4];
+    ldg256(m.boundary_scale + 4 * i, sc[0], sc[1], sc[2], sc[3]);
+    const int64_t c = (int64_t)om.x;
+    const uint32_t meta = om.y;
+    const int t0 = __ldg(ctags + c) & 3;
+    const int nq = ls.n_facet_points, nd = ls.n_dofs_per_cell;
+    double cd[kMaxDofs];
+    if (ls.mode == 0) {
+      int v[4] = {0, 0, 0, 0};
+      if (ls.dofmap == nullptr) {
+#pragma unroll
+        for (int k = 0; k < T::nv; ++k) v[k] = __ldg(m.cells + c * T::nv + k);
+      }
+      load_coeffs(m, ls, T::nv, c, v, cd);
+    }
+    double num = 0.0, den = 0.0;
+    const int n = (int)(meta & 0xfu);
+    for (int r = 0; r < n; ++r) {
+      const int lf = (int)((meta >> (4 + 2 * r)) & 3u);
+      double s = sc[0];
+#pragma unroll
+      for (int q = 1; q < 4; ++q)
+        if (r == q) s = sc[q];
+      double fn = 0.0, fd = 0.0;
+      for (int q = 0; q < nq; ++q) {
+        const double ph = ls.mode == 0
+                              ? seq_dot(ls.facet_table + ((int64_t)lf * nq + q) * nd, 1, cd, 1, nd)
+                              : __ldg(ls.facet_values + (c * T::nf + lf) * nq + q);
+        const double t = ph * s;
+        fn = fn + t;
+        fd = fd + fabs(t);
+      }
+      num = num + fn;
+      den = den + fd;
+    }
+    const double d = (den > 0.0) ? num / den : 0.5;
+    const bool k = d > -1.0 && d < 1.0;
+    const bool first = (meta >> 12) & 1u;
+    const int rr = facet_algebra(t0, 0, true, k, anyE);
+    n_conflict += rr >> 8;
+    n_zden += first && is_close_to_zero(den);
+    n_owner += first;
+    const int tag = rr & 0xf;
+    if (ftags) ftags[f] = tag;
+    ftags8[f] = (int8_t)tag;
+  }
+  cnt.add(n_zden, 0);
+  cnt.add(n_conflict, 1);
+  cnt.add(n_owner, 2);
+  cnt.flush(counters, PHIFEM_CNT_FACET_ZERO_DEN, 3);
+}
+
+// The interior-facet pass with f2c staged through shared memory by TMA bulk copies (the default when the mesh carries
+// its list of mesh-boundary facets, which k_tag_boundary_facets finishes).  A tile is kBlock * kUnroll facets = 8 KB of
+// f2c; thread 0 keeps kFacetStages tiles in flight per CTA (mbarrier expect_tx / complete_tx), every thread takes 4
+// CONSECUTIVE facets out of the landed tile (two 16-byte shared-memory reads), gathers the 8 cell tags and writes its 4
+// facet tags as one 32-bit word.  Against the per-thread LDG.128 loop of k_tag_facets (each warp instruction touching 32
+// half-used sectors, bytes in flight tied to the resident warps' loop phase) the requests for f2c leave the SM as whole
+// 8 KB copies issued three tiles ahead.
+#ifndef PHIFEM_TAG_FACETS_STAGES
+#define PHIFEM_TAG_FACETS_STAGES 4
+#endif
+#ifndef PHIFEM_TAG_FACETS_MINBLOCKS
+#define PHIFEM_TAG_FACETS_MINBLOCKS 5
+#endif
+constexpr int kFacetStages = PHIFEM_TAG_FACETS_STAGES;
+constexpr int kFacetTile = kBlock * kUnroll;
+
+template <int CT>
+__global__ void __launch_bounds__(kBlock, PHIFEM_TAG_FACETS_MINBLOCKS) k_tag_facets_staged(
+    phifem_mesh m, const int8_t* __restrict__ ctags, int32_t* __restrict__ ftags, int8_t* __restrict__ ftags8,
+    int64_t* counters) {
+  constexpr unsigned long long kTagLut = interior_facet_lut(false);
+  constexpr unsigned long long kConflictLut = interior_facet_lut(true);
+  __shared__ alignas(128) int4 s_f2c[kFacetStages][kFacetTile / 2];
+  __shared__ alignas(8) uint64_t s_bar[kFacetStages];
+  __shared__ unsigned int scnt[4];
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kFacetStages; ++s) tma::mbar_init(&s_bar[s], 1);
+    tma::fence_init();
+  }
+  BlockCounters cnt(scnt, 1);  // (its constructor synchronises the block)
+  unsigned int n_conflict = 0;
+  constexpr uint32_t kTileBytes = kFacetTile * 8;
+  const int64_t n_full = m.n_facets / kFacetTile;  // whole tiles go through TMA, the ragged end through plain loads
+  const int2* __restrict__ f2c2 = reinterpret_cast<const int2*>(m.f2c);
+  auto post = [&](int64_t t, int s) {
+    tma::mbar_expect_tx(&s_bar[s], kTileBytes);
+    tma::bulk_g2s(&s_f2c[s][0], f2c2 + t * kFacetTile, kTileBytes, &s_bar[s]);
+  };
+  if (threadIdx.x == 0)
+    for (int s = 0; s < kFacetStages; ++s) {
+      const int64_t t = blockIdx.x + (int64_t)s * gridDim.x;
+      if (t < n_full) post(t, s);
+    }
+  // gather: the 8 cell tags of 4 facets; finish: decision table and stores
+  auto gather = [&](const int2 (&cc)[kUnroll], int (&t0)[kUnroll], int (&t1)[kUnroll]) {
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      t0[u] = __ldg(ctags + cc[u].x);
+      t1[u] = cc[u].y < 0 ? 0 : __ldg(ctags + cc[u].y);
+    }
+  };
+  auto finish = [&](const int2 (&cc)[kUnroll], const int (&t0)[kUnroll], const int (&t1)[kUnroll],
+                    const bool (&valid)[kUnroll], int64_t f0) {
+    int out[kUnroll];
+    bool all_interior = valid[kUnroll - 1];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      out[u] = -1;
+      if (!valid[u]) continue;
+      if (cc[u].y < 0) {  // tagged by k_tag_boundary_facets
+        all_interior = false;
+        continue;
+      }
+      const int sh = 4 * ((t0[u] & 3) * 4 + (t1[u] & 3));
+      n_conflict += (unsigned int)((kConflictLut >> sh) & 1ull);
+      out[u] = (int)((kTagLut >> sh) & 0xfull);
+    }
+    if (all_interior) {
+      if (ftags) *reinterpret_cast<int4*>(ftags + f0) = make_int4(out[0], out[1], out[2], out[3]);
+      *reinterpret_cast<unsigned int*>(ftags8 + f0) =
+          (unsigned)out[0] | ((unsigned)out[1] << 8) | ((unsigned)out[2] << 16) | ((unsigned)out[3] << 24);
+    } else {
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+        if (out[u] >= 0) {
+          if (ftags) ftags[f0 + u] = out[u];
+          ftags8[f0 + u] = (int8_t)out[u];
+        }
+    }
+  };
+  static_assert(kUnroll == 4, "4 facets = two int4 per thread");
+  int k = 0;
+  for (int64_t t = blockIdx.x; t < n_full; t += gridDim.x, ++k) {
+    const int s = k % kFacetStages;
+    tma::mbar_wait(&s_bar[s], (uint32_t)(k / kFacetStages) & 1u);
+    const int4 a = s_f2c[s][2 * threadIdx.x], b = s_f2c[s][2 * threadIdx.x + 1];
+    const int2 cc[kUnroll] = {make_int2(a.x, a.y), make_int2(a.z, a.w), make_int2(b.x, b.y), make_int2(b.z, b.w)};
+    int t0[kUnroll], t1[kUnroll];
+    // The gathers are issued BEFORE the barrier: their addresses need the facet's cells, so every thread's shared-memory
+    // reads have returned when it arrives -- the bulk copy that refills the stage runs in the async proxy and is not
+    // ordered behind reads still queued in the load/store unit (a barrier alone let 2 360 of 102 M facets at config E
+    // see the next tile's f2c).
+    gather(cc, t0, t1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int64_t tn = t + (int64_t)kFacetStages * gridDim.x;
+      if (tn < n_full) post(tn, s);
+    }
+    const bool valid[kUnroll] = {true, true, true, true};
+    finish(cc, t0, t1, valid, t * kFacetTile + (int64_t)threadIdx.x * kUnroll);
+  }
+  if (blockIdx.x == (unsigned)(n_full % gridDim.x) && n_full * kFacetTile < m.n_facets) {  // the ragged end
+    const int64_t f0 = n_full * kFacetTile + (int64_t)threadIdx.x * kUnroll;
+    int2 cc[kUnroll];
+    bool valid[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      valid[u] = f0 + u < m.n_facets;
+      cc[u] = valid[u] ? __ldg(f2c2 + f0 + u) : make_int2(0, -1);
+    }
+    int t0[kUnroll], t1[kUnroll];
+    gather(cc, t0, t1);
+    if (valid[0]) finish(cc, t0, t1, valid, f0);
+  }
+  cnt.add(n_conflict, 0);
+  cnt.flush(counters, PHIFEM_CNT_FACET_CONFLICT, 1);
+}
+
 // ---- candidate records of the one-sided measures (mesh_scripts.py:137-192) -------------------------
 __global__ void k_entity_records(phifem_mesh m, int nf_per_cell, const int8_t* __restrict__ ctags,
                                  const int8_t* __restrict__ ftags, int facet_tag, unsigned int cell_mask,
@@ -711,6 +1139,23 @@ extern "C" int phifem_cell_points(const phifem_mesh* mesh, const double* shape, 
   return PHIFEM_OK;
 }
 
+namespace {
+// PHIFEM_FACETS_KERNEL=ldg / PHIFEM_CELLS_KERNEL=ldg select the per-thread vector-load kernels (A/B runs; read at
+// every call so that one process can compare the two)
+bool facet_kernel_staged() {
+  const char* e = getenv("PHIFEM_FACETS_KERNEL");
+  return !(e && e[0] == 'l');
+}
+bool boundary_kernel_records() {  // PHIFEM_BOUNDARY_KERNEL=walk: ignore the per-mesh records (A/B runs, tests)
+  const char* e = getenv("PHIFEM_BOUNDARY_KERNEL");
+  return !(e && e[0] == 'w');
+}
+bool cell_kernel_staged() {
+  const char* e = getenv("PHIFEM_CELLS_KERNEL");
+  return !(e && e[0] == 'l');
+}
+}  // namespace
+
 extern "C" int phifem_tag_cells(const phifem_mesh* mesh, const phifem_levelset* ls,
                                 int32_t single_layer_cut, int32_t* cell_tags, int8_t* cell_tags8,
                                 uint8_t* vertex_scratch, int64_t* counters, void* stream) {
@@ -738,7 +1183,32 @@ extern "C" int phifem_tag_cells(const phifem_mesh* mesh, const phifem_levelset* 
         have_bounds ? mesh->detj_max : 1e300, vertex_scratch);
     const bool exact = exact_zero_den || !have_bounds;
     const int64_t tiles = (mesh->n_cells + kBlock * kUnroll - 1) / (kBlock * kUnroll);
-    if (ct == PHIFEM_TRIANGLE)
+    const bool staged = cell_kernel_staged() && (reinterpret_cast<uintptr_t>(mesh->cells) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(cell_tags8) & 3) == 0;
+    auto launch_staged = [&](auto c) {
+      constexpr int CT = decltype(c)::value;
+      constexpr size_t smem = staged_cells_smem<CT>();
+      auto kernel = k_tag_cells_p1_staged<CT>;
+      static bool attr_set[64] = {};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (!attr_set[dev & 63]) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set[dev & 63] = true;
+      }
+      int per_sm = 0, sms = kNumSMs;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+      const int64_t cap = (int64_t)sms * per_sm;
+      const int grid = (int)(tiles < cap ? tiles : cap);
+      kernel<<<grid, kBlock, smem, st>>>(*mesh, ls->coeffs, vertex_scratch, exact, cell_tags, cell_tags8, counters);
+    };
+    if (staged && ct == PHIFEM_TRIANGLE)
+      launch_staged(std::integral_constant<int, PHIFEM_TRIANGLE>());
+    else if (staged)
+      launch_staged(std::integral_constant<int, PHIFEM_TETRAHEDRON>());
+    else if (ct == PHIFEM_TRIANGLE)
       k_tag_cells_p1<PHIFEM_TRIANGLE><<<persistent_grid(k_tag_cells_p1<PHIFEM_TRIANGLE>, kBlock, tiles),
                                         kBlock, 0, st>>>(*mesh, ls->coeffs, vertex_scratch, exact, cell_tags,
                                                          cell_tags8, counters);
@@ -786,16 +1256,6 @@ SideStream& side_stream() {
 }
 }  // namespace
 
-namespace {
-bool facet_grid_full() {  // PHIFEM_FACETS_GRID=full: one tile per CTA instead of the persistent grid (tuning sweeps;
-  // measured slower at config E: 0.320 against 0.231 ms for the facet phase)
-  static const int v = [] {
-    const char* e = getenv("PHIFEM_FACETS_GRID");
-    return (e && e[0] == 'f') ? 1 : 0;
-  }();
-  return v != 0;
-}
-}  // namespace
 
 extern "C" int phifem_tag_facets(const phifem_mesh* mesh, const phifem_levelset* ls,
                                  const int8_t* cell_tags8, int32_t* facet_tags, int8_t* facet_tags8,
@@ -817,17 +1277,33 @@ extern "C" int phifem_tag_facets_phase(const phifem_mesh* mesh, const phifem_lev
   const bool both = (phases & 3) == 3;
   PHIFEM_CHECK_ARG((phases & 3) != 0, "phases selects nothing");
   PHIFEM_CHECK_ARG(both || two_pass, "phases need mesh.boundary_facets");
+  // interior facets of a mesh that lists its boundary facets: f2c staged by TMA (needs a 16-byte aligned f2c; the
+  // per-thread vector-load kernel otherwise, or with PHIFEM_FACETS_KERNEL=ldg for A/B runs)
+  auto launch_interior = [&](auto c) {
+    constexpr int CT = decltype(c)::value;
+    if (facet_kernel_staged() && (reinterpret_cast<uintptr_t>(mesh->f2c) & 15) == 0) {
+      const int grid = persistent_grid(k_tag_facets_staged<CT>, kBlock, tiles);
+      k_tag_facets_staged<CT><<<grid, kBlock, 0, st>>>(*mesh, cell_tags8, facet_tags, facet_tags8, counters);
+    } else {
+      const int grid = persistent_grid(k_tag_facets<CT, false>, kBlock, tiles);
+      k_tag_facets<CT, false><<<grid, kBlock, 0, st>>>(*mesh, *ls, cell_tags8, facet_tags, facet_tags8, counters);
+    }
+  };
+  auto launch_boundary = [&](auto c, cudaStream_t bs) {
+    constexpr int CT = decltype(c)::value;
+    const int g2 = (int)((mesh->n_boundary_facets + kBlock - 1) / kBlock);
+    if (mesh->boundary_owner && mesh->boundary_scale && CT != PHIFEM_QUADRILATERAL && boundary_kernel_records())
+      k_tag_boundary_facets_rec<CT><<<g2, kBlock, 0, bs>>>(*mesh, *ls, cell_tags8, facet_tags, facet_tags8, counters);
+    else
+      k_tag_boundary_facets<CT><<<g2, kBlock, 0, bs>>>(*mesh, *ls, cell_tags8, facet_tags, facet_tags8, counters);
+  };
   dispatch_cell_type(mesh->cell_type, [&](auto c) {
     constexpr int CT = decltype(c)::value;
     if (!both) {  // one phase alone, on the caller's stream (the caller orders them, e.g. around an all-reduce)
       if (phases & PHIFEM_FACETS_INTERIOR) {
-        const int grid = persistent_grid(k_tag_facets<CT, false>, kBlock, tiles);
-        k_tag_facets<CT, false><<<grid, kBlock, 0, st>>>(*mesh, *ls, cell_tags8, facet_tags, facet_tags8,
-                                                         counters);
+        launch_interior(c);
       } else if (mesh->n_boundary_facets > 0) {
-        const int g2 = (int)((mesh->n_boundary_facets + kBlock - 1) / kBlock);
-        k_tag_boundary_facets<CT><<<g2, kBlock, 0, st>>>(*mesh, *ls, cell_tags8, facet_tags, facet_tags8,
-                                                         counters);
+        launch_boundary(c, st);
       }
     } else if (two_pass) {
       // The mesh-boundary facets (a chain of dependent gathers over few threads: latency-bound) run on a
@@ -838,26 +1314,35 @@ extern "C" int phifem_tag_facets_phase(const phifem_mesh* mesh, const phifem_lev
       if (fork) {
         cudaEventRecord(ss.fork, st);
         cudaStreamWaitEvent(ss.stream, ss.fork, 0);
-        const int g2 = (int)((mesh->n_boundary_facets + kBlock - 1) / kBlock);
-        k_tag_boundary_facets<CT><<<g2, kBlock, 0, ss.stream>>>(*mesh, *ls, cell_tags8, facet_tags,
-                                                                facet_tags8, counters);
+        launch_boundary(c, ss.stream);
         cudaEventRecord(ss.join, ss.stream);
       }
-      const int grid = fork && facet_grid_full() ? (int)tiles : persistent_grid(k_tag_facets<CT, false>, kBlock, tiles);
-      k_tag_facets<CT, false><<<grid, kBlock, 0, st>>>(*mesh, *ls, cell_tags8, facet_tags, facet_tags8,
-                                                       counters);
+      launch_interior(c);
       if (fork) {
         cudaStreamWaitEvent(st, ss.join, 0);
       } else if (mesh->n_boundary_facets > 0) {
-        const int g2 = (int)((mesh->n_boundary_facets + kBlock - 1) / kBlock);
-        k_tag_boundary_facets<CT><<<g2, kBlock, 0, st>>>(*mesh, *ls, cell_tags8, facet_tags, facet_tags8,
-                                                         counters);
+        launch_boundary(c, st);
       }
     } else {
       const int grid = persistent_grid(k_tag_facets<CT, true>, kBlock, tiles);
       k_tag_facets<CT, true><<<grid, kBlock, 0, st>>>(*mesh, *ls, cell_tags8, facet_tags, facet_tags8,
                                                       counters);
     }
+  });
+  PHIFEM_CHECK_LAUNCH();
+  return PHIFEM_OK;
+}
+
+extern "C" int phifem_boundary_records(const phifem_mesh* mesh, uint32_t* boundary_owner, double* boundary_scale,
+                                       void* stream) {
+  if (int rc = check_mesh(mesh, true)) return rc;
+  PHIFEM_CHECK_ARG(mesh->n_boundary_facets == 0 || mesh->boundary_facets, "mesh.boundary_facets is null");
+  PHIFEM_CHECK_ARG(mesh->n_boundary_facets == 0 || (boundary_owner && boundary_scale), "output pointer is null");
+  if (mesh->n_boundary_facets == 0) return PHIFEM_OK;
+  const int g = (int)((mesh->n_boundary_facets + kBlock - 1) / kBlock);
+  dispatch_cell_type(mesh->cell_type, [&](auto c) {
+    k_boundary_records<decltype(c)::value><<<g, kBlock, 0, (cudaStream_t)stream>>>(*mesh, boundary_owner,
+                                                                                  boundary_scale);
   });
   PHIFEM_CHECK_LAUNCH();
   return PHIFEM_OK;

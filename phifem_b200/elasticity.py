@@ -225,11 +225,12 @@ def assemble_interface_elasticity_into(plan, phi, f, material, gamma, sigma_s, d
 
 
 def assemble_interface_elasticity(plan, phi_h, f_h, material=None, pen_coef=1.0, stab_coef=1.0, bcs=None,
-                                  symmetric_bc=False):
+                                  symmetric_bc=True):
     """A (CSR over the mixed dofs) and b of main.py:227-275.  `f_h`: P1 vector field [Nv, d] (the demo's `f` is a UFL
     expression, :150; here its nodal interpolant).  `bcs` = (dofs, values): Dirichlet conditions as dolfinx applies them
-    (assemble_matrix(bcs=) zeroes rows / columns and sets the diagonal to 1, apply_lifting, bc.set).  symmetric_bc: use
-    the list-driven pass, whose work is the constrained rows' lengths (small-system parity only so far)."""
+    (assemble_matrix(bcs=) zeroes rows / columns and sets the diagonal to 1, apply_lifting, bc.set).  symmetric_bc
+    (default): the list-driven pass, whose work is the constrained rows' lengths -- the plan's pattern is structurally
+    symmetric with sorted rows by construction; False = the pass over the whole matrix (bitwise reproducible lifting)."""
     mesh = plan.mesh
     _lib.require_cuda(mesh)
     material = material or Material()

@@ -217,6 +217,23 @@ class Mesh:
             self._host["bfacets"] = torch.nonzero(self.f2c[:, 1] < 0).reshape(-1).to(torch.int32).contiguous()
         return self._host["bfacets"]
 
+    def boundary_records(self):
+        """(owner + meta [nb, 2] uint32 as int32 storage, scales [nb, 4]) of the mesh-boundary facets, cached: the static
+        part of the ds detection of reference mesh_scripts.py:434-452 (csrc/tags.cu, k_boundary_records).  CUDA meshes
+        only; None on the host."""
+        if "brec" not in self._host:
+            if self.device.type != "cuda":
+                self._host["brec"] = (None, None)
+            else:
+                from . import _lib
+                nb = int(self.boundary_facets.numel())
+                owner = torch.zeros((max(nb, 1), 2), dtype=torch.int32, device=self.device)
+                scale = torch.zeros((max(nb, 1), 4), dtype=torch.float64, device=self.device)
+                _lib.check(_lib.load().phifem_boundary_records(
+                    _lib.c_mesh(self, with_records=False), _lib.ptr(owner), _lib.ptr(scale), _lib.stream()))
+                self._host["brec"] = (owner, scale)
+        return self._host["brec"]
+
     def detj_bounds(self):
         """(min, max) of |det J| over the simplices of the mesh, cached.  A property of the mesh
         alone: lets the P1 classifier decide uncut cells from the signs of phi without gathering

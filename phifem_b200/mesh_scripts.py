@@ -188,15 +188,42 @@ def classify(mesh, dls, single_layer_cut=False, ws=None, exact_zero_den=False):
     return ws
 
 
-def _integration_entities_dev(mesh, cell_tags8, facet_tags8, facet_tag, cell_tag_values):
-    """Device version of `_compute_integration_entities` (reference :137-192): flat int32
-    [cell, local_facet, ...] tensor, cells in first-appearance order, local facets ascending."""
-    lib = _lib.load()
-    cm = _lib.c_mesh(mesh)
+def _cell_mask(cell_tag_values):
     mask = 0
     for t in cell_tag_values:
         mask |= 1 << int(t)
+    return mask
+
+
+# the two one-sided measures of box mode (reference :617-626): (facet tag, cell tags, counter slot of the count)
+_DS_OUT = (4, (1, 2), _lib.CNT_CALLER0)
+_DS_IN = (3, (2, 3), _lib.CNT_CALLER1)
+
+
+def _count_entities(mesh, ws, cell_tags8, facet_tags8):
+    """Queue the counting passes of ds(100) / ds(101) behind the tag kernels; the counts land in the two caller slots
+    of the counter block, so that the ONE device -> host copy that fetches the counters brings them along."""
+    lib = _lib.load()
+    cm = _lib.c_mesh(mesh)
+    for facet_tag, cell_values, slot in (_DS_OUT, _DS_IN):
+        _lib.check(lib.phifem_integration_entities_count(
+            cm, _lib.ptr(cell_tags8), _lib.ptr(facet_tags8), facet_tag, _cell_mask(cell_values),
+            ws.counters.data_ptr() + 8 * slot, _lib.stream()))
+
+
+def _integration_entities_dev(mesh, cell_tags8, facet_tags8, facet_tag, cell_tag_values, n_known=None):
+    """Device version of `_compute_integration_entities` (reference :137-192): flat int32
+    [cell, local_facet, ...] tensor, cells in first-appearance order, local facets ascending.
+    n_known: the number of pairs when the caller has already read it back (no host synchronisation then)."""
+    lib = _lib.load()
+    cm = _lib.c_mesh(mesh)
+    mask = _cell_mask(cell_tag_values)
     # candidates, first-appearance ordering and the sort all happen behind the C ABI (csrc/symbolic.cu)
+    if n_known is not None:
+        ents = torch.empty((int(n_known), 2), dtype=torch.int32, device=mesh.device)
+        _lib.check(lib.phifem_integration_entities_fill(cm, _lib.ptr(cell_tags8), _lib.ptr(facet_tags8), facet_tag,
+                                                        mask, _lib.ptr(ents), int(n_known), _lib.stream()))
+        return ents.reshape(-1)
     n = ctypes.c_int64(0)
     capacity = max(1024, int(4 * mesh.num_facets ** (1 - 1.0 / mesh.topology.dim)))
     while True:
@@ -264,10 +291,17 @@ def compute_tags_measures(mesh, discrete_levelset, detection_degree, box_mode=Fa
     _lib.require_cuda(mesh)
     dls = _DeviceLevelset(mesh, discrete_levelset, detection_degree)
     ws = classify(mesh, dls, single_layer_cut)
-    counters = ws.counters.cpu().numpy()          # one small D2H: warnings, debug checks
+    # box mode without user tags: the counting passes of ds(100) / ds(101) go behind the tag kernels, and the single
+    # device -> host copy below (warnings, debug checks) returns their counts too -- ONE host synchronisation per call
+    counted = box_mode and not overwrite_tags
+    if counted:
+        _count_entities(mesh, ws, ws.cell_tags8, ws.facet_tags8)
+    counters = ws.counters.cpu().numpy()
     if counters[_lib.CNT_ZERO_DEN] == 0 and counters[_lib.CNT_ZERO_DEN_AMBIGUOUS] > 0:
         # no cell settled the RuntimeWarning of :129-133 and some were left undecided: evaluate them
         ws = classify(mesh, dls, single_layer_cut, ws=ws, exact_zero_den=True)
+        if counted:
+            _count_entities(mesh, ws, ws.cell_tags8, ws.facet_tags8)
         counters = ws.counters.cpu().numpy()
     if counters[_lib.CNT_ZERO_DEN] > 0:           # :129-133 for the dx detection
         warnings.warn(_ZERO_WARNING, RuntimeWarning)
@@ -294,8 +328,10 @@ def compute_tags_measures(mesh, discrete_levelset, detection_degree, box_mode=Fa
         facet_tags8 = _narrow_tags(facets_tags.values_dev)
 
     if box_mode:                                   # :617-634
-        ents_out = _integration_entities_dev(mesh, cell_tags8, facet_tags8, 4, (1, 2))
-        ents_in = _integration_entities_dev(mesh, cell_tags8, facet_tags8, 3, (2, 3))
+        ents_out = _integration_entities_dev(mesh, cell_tags8, facet_tags8, *_DS_OUT[:2],
+                                             n_known=counters[_DS_OUT[2]] if counted else None)
+        ents_in = _integration_entities_dev(mesh, cell_tags8, facet_tags8, *_DS_IN[:2],
+                                            n_known=counters[_DS_IN[2]] if counted else None)
         measure = Measure("ds", mesh, subdomain_data=[(100, ents_out), (101, ents_in)])
         cells_tags.tags8, facets_tags.tags8 = cell_tags8, facet_tags8
         cells_tags.tags8_exact = "cells" not in overwrite_tags

@@ -53,9 +53,10 @@ def test_elasticity_operator_matches_oracle(kind, n, kphi, with_bc):
         bcs = (bc_dofs, bc_vals)
         bc_dofs, bc_vals = bc_dofs.cpu().numpy(), bc_vals.cpu().numpy()
     A, b = elasticity.assemble_interface_elasticity(plan, phi, f, mat, pen_coef=1.3, stab_coef=0.7, bcs=bcs)
-    if with_bc:   # the list-driven Dirichlet pass gives the same system (its lifting sums in another order)
+    if with_bc:   # the full-matrix Dirichlet pass gives the same system (the default, list-driven one sums its lifting
+        # in another order)
         A2, b2 = elasticity.assemble_interface_elasticity(plan, phi, f, mat, pen_coef=1.3, stab_coef=0.7, bcs=bcs,
-                                                          symmetric_bc=True)
+                                                          symmetric_bc=False)
         assert torch.allclose(A2.data, A.data, rtol=0, atol=1e-13 * float(A.data.abs().max()))
         assert torch.allclose(b2, b, rtol=0, atol=1e-12 * float(b.abs().max()))
     assert A.shape[0] == plan.nb * mesh.num_vertices
@@ -185,3 +186,27 @@ def test_elasticity_without_cut_cells(where):
     blk = np.repeat(np.arange(len(ip) - 1), np.diff(ip)) % plan.nb
     off = plan.layout["u_out" if where == "outside" else "u_in"][0]
     assert np.all(data[(blk < off) | (blk >= off + 2)] == 0.0) and np.abs(data).max() > 0
+
+
+def test_list_driven_dirichlet_pass_on_a_large_pattern():
+    """The default (list-driven) Dirichlet pass against the pass over the whole matrix on 180 000 triangles
+    (1.26 M mixed dofs, 1.2e8 pattern entries): same matrix, same lifted load vector."""
+    mesh = synthetic.rectangle_mesh(300, lo=(-1.5, -1.5), hi=(1.5, 1.5), device="cuda")
+    V1 = fem.functionspace(mesh, 1)
+    phi = synthetic.sphere_levelset(mesh.x, center=(0.0, 0.0), radius=1.0)
+    det = fem.Function(V1, phi.cpu().numpy())
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        ctags, ftags, _, d_bdry, _ = mesh_scripts.compute_tags_measures(mesh, det, 1, box_mode=True)
+    plan = elasticity.build_plan_interface_elasticity(mesh, ctags, ftags, d_bdry, V_phi=V1)
+    rng = np.random.default_rng(5)
+    f = torch.from_numpy(rng.uniform(-1, 1, (mesh.num_vertices, 2))).cuda()
+    bc_dofs = plan.dofs("u_out", plan.boundary_vertices()).reshape(-1)
+    bcs = (bc_dofs, torch.from_numpy(rng.uniform(-1, 1, bc_dofs.numel())).cuda())
+    mat = elasticity.Material(1.0, 0.3, 0.05, 0.27)
+    A1, b1 = elasticity.assemble_interface_elasticity(plan, phi, f, mat, bcs=bcs)
+    A2, b2 = elasticity.assemble_interface_elasticity(plan, phi, f, mat, bcs=bcs, symmetric_bc=False)
+    assert plan.nnz > 1.0e8
+    assert torch.equal(A1.data, A2.data)
+    assert torch.allclose(b1, b2, rtol=0, atol=1e-12 * float(b2.abs().max()))
+    assert bool((b1[bc_dofs.long()] == bcs[1]).all())

@@ -23,7 +23,7 @@ from phifem_b200 import assemble, assemble_pk, elasticity, fem, mesh_scripts, sy
 from phifem_b200.mesh import Measure, MeshTags  # noqa: E402
 
 
-SYMMETRIC_BC = False   # --symmetric-bc: the list-driven Dirichlet pass (phifem_apply_dirichlet_symmetric)
+SYMMETRIC_BC = True   # --full-bc: the pass over the whole matrix instead of the list-driven one (phifem_apply_dirichlet_symmetric)
 
 
 def _tags(mesh, phi):
@@ -114,6 +114,7 @@ def run(op, steps, warmup):
                        "interior": int((c8 == 1).sum()), "cut": int((c8 == 2).sum()), "exterior": int((c8 == 3).sum()),
                        "rows": plan.n_rows, "nnz": plan.nnz},
             "csr_write_gbs": 8.0 * plan.nnz / (ms_asm * 1e-3) / 1e9,
+            "dirichlet_pass": ("list" if SYMMETRIC_BC else "full") if op.startswith("elasticity") else None,
             "topology_s": t1 - t0, "symbolic_s": t2 - t1}
     print(json.dumps(line), flush=True)
     return line
@@ -124,9 +125,9 @@ if __name__ == "__main__":
     ap.add_argument("--ops", default="neumann,elasticity-2d,elasticity-3d")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--symmetric-bc", action="store_true")
+    ap.add_argument("--full-bc", action="store_true")
     a = ap.parse_args()
-    SYMMETRIC_BC = a.symmetric_bc
+    SYMMETRIC_BC = not a.full_bc
     for name in a.ops.split(","):
         run(name, a.steps, a.warmup)
         torch.cuda.empty_cache()
