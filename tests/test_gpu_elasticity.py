@@ -207,6 +207,12 @@ def test_list_driven_dirichlet_pass_on_a_large_pattern():
     A1, b1 = elasticity.assemble_interface_elasticity(plan, phi, f, mat, bcs=bcs)
     A2, b2 = elasticity.assemble_interface_elasticity(plan, phi, f, mat, bcs=bcs, symmetric_bc=False)
     assert plan.nnz > 1.0e8
-    assert torch.equal(A1.data, A2.data)
+    # (the cut-cell kernels accumulate with fp64 reductions: two assemblies differ in the last bits)
+    assert torch.allclose(A1.data, A2.data, rtol=0, atol=1e-13 * float(A2.data.abs().max()))
+    free = torch.ones(plan.n_rows, dtype=torch.bool, device="cuda")
+    free[bc_dofs.long()] = False
+    rows = torch.repeat_interleave(torch.arange(plan.n_rows, device="cuda"), (plan.indptr[1:] - plan.indptr[:-1]).long())
+    cols = plan.indices.long()
+    assert bool((A1.data[~free[rows] | ~free[cols]] == (rows == cols)[~free[rows] | ~free[cols]].double()).all())
     assert torch.allclose(b1, b2, rtol=0, atol=1e-12 * float(b2.abs().max()))
     assert bool((b1[bc_dofs.long()] == bcs[1]).all())
