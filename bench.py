@@ -813,6 +813,8 @@ def run_ours(args):
         mesh, phi, f = make_mesh(args.mesh)
     w = Workload(mesh, phi, f, args, problem=problem, degree=degree, ls_kw=ls_kw)
     plan = w.plan
+    peer_halo = (problem is not None and args.dist_mode == "exchange" and not args.no_peer
+                 and problem.enable_peer_halo())
     _sym = (w.symbolic_ms, w.topology_s, w.symbolic_first_call_ms, getattr(plan, "symbolic", None))
 
     for _ in range(args.warmup):
@@ -901,7 +903,10 @@ def run_ours(args):
                                          "1 slab of the global box per rank, owned CSR rows, "
                                          + ("owner computes its rows from 2 redundantly classified ghost "
                                             "layers: one 8-byte all-reduce per step, no halo exchange"
-                                            if args.dist_mode == "rows" else "NCCL halo exchange")
+                                            if args.dist_mode == "rows" else
+                                            ("halo contributions pushed into the owners' HBM over NVLink and added "
+                                             "there by the same kernel (phifem_halo_exchange)" if peer_halo else
+                                             "NCCL halo exchange (grouped send / recv + index_add_)"))
                                          + ("; the 8 bytes travel as stores into the peers' HBM over NVLink (csrc/peer.cu)"
                                             if getattr(problem, "peer", None) is not None else "")),
                            "tags_dtype": "int8 on the device (int32 MeshTags.values widened on demand)",

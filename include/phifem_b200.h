@@ -552,6 +552,31 @@ int phifem_peer_flags_collect(phifem_peer_flags* flags, int64_t* value_out, void
 int phifem_peer_flags_error(phifem_peer_flags* flags);
 void phifem_peer_flags_destroy(phifem_peer_flags* flags);
 
+/* ---- halo exchange of CSR / load-vector contributions over NVLink peer memory (csrc/peer.cu): SURVEY.md 8(b) export (5).
+ * The reference's only parallel hook is the MPI communicator of its mesh (demo/strong-dirichlet/flower/main.py:49): PETSc
+ * adds off-process contributions to their owner's rows inside `assemble_matrix` / `assemble_vector` + ghost updates
+ * (main.py:121-131).  Here a rank that assembled contributions to rows owned by a peer pushes them into that peer's
+ * receive buffer (CUDA IPC mapping, remote stores), publishes an epoch flag, waits for the flags of its own peers and
+ * adds what it received into `dst` through a slot list -- ONE kernel, no pack, no collective library, CUDA-graph
+ * capturable.  One process per GPU on one node.
+ *   create   allocates the receive buffer ([2][capacity] doubles, capacity the same on every rank) and returns its
+ *            64-byte CUDA IPC handle in handle64 (HOST);
+ *   connect  handles (HOST) = the world handles in rank order; remote_offset[q] (HOST) = where this rank's values start
+ *            inside peer q's receive buffer; send_ptr[world + 1] (HOST) = value range of peer q in this rank's send
+ *            list; send_src[q] (HOST) = first element of peer q's CONTIGUOUS segment of `src` (used when the exchange is
+ *            called without a send_index); n_recv = values this rank receives per exchange;
+ *   exchange value j of peer q = src[send_index[send_ptr[q] + j]] (send_index DEVICE, may be NULL: src[send_src[q] + j]);
+ *            on arrival dst[recv_index[i]] += received[i] (recv_index DEVICE [n_recv], fp64 reductions);
+ *   error    synchronises; 1 = a receive waited ~1 s for a peer that never pushed. */
+typedef struct phifem_halo phifem_halo;
+int phifem_halo_create(int32_t world, int32_t rank, int64_t capacity, phifem_halo** out, void* handle64);
+int phifem_halo_connect(phifem_halo* halo, const void* handles, const int64_t* remote_offset, const int64_t* send_ptr,
+                        const int64_t* send_src, int64_t n_recv);
+int phifem_halo_exchange(phifem_halo* halo, const double* src, const int64_t* send_index, const int64_t* recv_index,
+                         double* dst, void* stream);
+int phifem_halo_error(phifem_halo* halo);
+void phifem_halo_destroy(phifem_halo* halo);
+
 #ifdef __cplusplus
 }
 #endif

@@ -169,6 +169,12 @@ _SIGNATURES = {
     "phifem_peer_flags_collect": (ctypes.c_int, [_vp, _vp, _vp]),
     "phifem_peer_flags_error": (ctypes.c_int, [_vp]),
     "phifem_peer_flags_destroy": (None, [_vp]),
+    "phifem_halo_create": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, ctypes.POINTER(_vp), _vp]),
+    "phifem_halo_connect": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
+                                           ctypes.POINTER(ctypes.c_int64), ctypes.c_int64]),
+    "phifem_halo_exchange": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "phifem_halo_error": (ctypes.c_int, [_vp]),
+    "phifem_halo_destroy": (None, [_vp]),
     "phifem_pattern_release_scratch": (None, []),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

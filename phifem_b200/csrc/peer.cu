@@ -165,3 +165,203 @@ extern "C" void phifem_peer_flags_destroy(phifem_peer_flags* p) {
   cudaFree(p->error);
   delete p;
 }
+
+// ---- halo exchange of CSR / load-vector contributions over NVLink peer memory ------------------------------------------
+// The "halo-row contributions are exchanged ... over NVLink" step of a sharded assembly whose ranks assemble their own
+// CELLS (per-entity kernels, mode "exchange" of phifem_b200/dist.py) instead of their own ROWS: contributions to rows of
+// another rank accumulate in a send segment and must be added into that rank's CSR values.  One kernel does the whole
+// exchange -- no pack, no collective library, no host:
+//   push     every CTA copies its share of the send values straight into the owners' receive buffers (remote stores
+//            through the CUDA IPC mapping: NVLink), fences, and takes a ticket; the CTA with the last ticket stores the
+//            epoch into this rank's flag slot on every peer;
+//   receive  every CTA waits until the flags of all peers carry the epoch (they are stores into THIS rank's memory), then
+//            adds its share of the received values into the destination array through the precomputed slot list
+//            (fp64 reductions: two peers may contribute to the same entry).
+// Receive buffers and flags alternate with the epoch's parity, as the exterior-cell slots above do: a rank cannot be two
+// exchanges ahead of a peer.  The epoch lives in device memory (a one-thread kernel advances it), so the pair of
+// launches replays inside a CUDA graph.
+struct phifem_halo {
+  int world, rank;
+  int64_t capacity;                // doubles per receive buffer (the same on every rank)
+  int64_t n_recv, n_send;          // values this rank receives / sends per exchange
+  char* base;                      // local allocation: [2][64] flags (8 bytes each), then [2][capacity] doubles
+  char* peers[64];                 // the same allocation of every rank (peers[rank] == base)
+  bool opened[64];
+  char** table;                    // device copy of `peers`
+  int64_t* remote_offset;          // device [world]: where this rank's values start in peer q's receive buffer
+  int64_t* send_ptr;               // device [world + 1]: value range of peer q in the send list
+  int64_t* send_src;               // device [world]: first element of peer q's contiguous segment (send_index == NULL)
+  unsigned int* epoch;             // device
+  unsigned int* ticket;            // device
+  int* error;                      // device
+};
+
+namespace phifem {
+namespace {
+constexpr size_t kHaloFlagBytes = 2 * 64 * sizeof(unsigned long long);
+
+__global__ void k_halo_begin(unsigned int* epoch, unsigned int* ticket) {
+  *epoch += 1u;
+  *ticket = 0u;
+}
+
+__global__ void __launch_bounds__(256) k_halo_exchange(char* const* __restrict__ peers, int world, int rank,
+                                                       int64_t capacity, const unsigned int* __restrict__ epoch,
+                                                       unsigned int* __restrict__ ticket,
+                                                       const int64_t* __restrict__ remote_offset,
+                                                       const int64_t* __restrict__ send_ptr,
+                                                       const int64_t* __restrict__ send_src,
+                                                       const double* __restrict__ src,
+                                                       const int64_t* __restrict__ send_index,
+                                                       const int64_t* __restrict__ recv_index, int64_t n_recv,
+                                                       double* __restrict__ dst, int* __restrict__ error) {
+  const unsigned int e = *epoch;
+  const int par = (int)(e & 1u);
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  // push
+  for (int q = 0; q < world; ++q) {
+    if (q == rank) continue;
+    const int64_t lo = send_ptr[q], n = send_ptr[q + 1] - lo;
+    double* out = reinterpret_cast<double*>(peers[q] + kHaloFlagBytes) + (size_t)par * capacity + remote_offset[q];
+    const int64_t s0 = send_src[q];
+    for (int64_t j = tid; j < n; j += nth) out[j] = send_index ? src[send_index[lo + j]] : src[s0 + j];
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last) {  // every CTA of this rank has pushed and fenced: tell the peers
+    __threadfence();
+    if (threadIdx.x < world && (int)threadIdx.x != rank) {
+      volatile unsigned long long* flag =
+          reinterpret_cast<unsigned long long*>(peers[threadIdx.x]) + (size_t)par * 64 + rank;
+      *flag = (unsigned long long)e;
+    }
+    __threadfence_system();
+  }
+  // receive
+  if (threadIdx.x < world && (int)threadIdx.x != rank) {
+    const volatile unsigned long long* flag =
+        reinterpret_cast<const unsigned long long*>(peers[rank]) + (size_t)par * 64 + threadIdx.x;
+    int spins = 0;
+    while ((unsigned int)*flag != e) {
+      if (++spins > (1 << 21)) {  // ~1 s: a peer never pushed this epoch
+        *error = 1;
+        break;
+      }
+      __nanosleep(400);
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  const double* in = reinterpret_cast<const double*>(peers[rank] + kHaloFlagBytes) + (size_t)par * capacity;
+  for (int64_t i = tid; i < n_recv; i += nth) atomicAdd(dst + recv_index[i], __ldcv(in + i));  // .cv: not from a stale L1 line
+}
+}  // namespace
+}  // namespace phifem
+
+extern "C" int phifem_halo_create(int32_t world, int32_t rank, int64_t capacity, phifem_halo** out, void* handle64) {
+  PHIFEM_CHECK_ARG(out && handle64, "null pointer");
+  PHIFEM_CHECK_ARG(world >= 1 && world <= 64 && rank >= 0 && rank < world && capacity >= 0, "world / rank / capacity");
+  phifem_halo* h = new phifem_halo();
+  memset(h, 0, sizeof(*h));
+  h->world = world;
+  h->rank = rank;
+  h->capacity = capacity;
+  const size_t bytes = kHaloFlagBytes + 2 * (size_t)(capacity > 0 ? capacity : 1) * sizeof(double);
+  bool ok = cudaMalloc(&h->base, bytes) == cudaSuccess && cudaMalloc(&h->epoch, sizeof(unsigned int)) == cudaSuccess &&
+            cudaMalloc(&h->ticket, sizeof(unsigned int)) == cudaSuccess && cudaMalloc(&h->error, sizeof(int)) == cudaSuccess &&
+            cudaMalloc(&h->table, sizeof(char*) * 64) == cudaSuccess &&
+            cudaMalloc(&h->remote_offset, sizeof(int64_t) * 64) == cudaSuccess &&
+            cudaMalloc(&h->send_ptr, sizeof(int64_t) * 65) == cudaSuccess &&
+            cudaMalloc(&h->send_src, sizeof(int64_t) * 64) == cudaSuccess;
+  if (ok) {
+    cudaMemset(h->base, 0, bytes);
+    cudaMemset(h->epoch, 0, sizeof(unsigned int));
+    cudaMemset(h->ticket, 0, sizeof(unsigned int));
+    cudaMemset(h->error, 0, sizeof(int));
+    h->peers[rank] = h->base;
+    cudaIpcMemHandle_t ipc;
+    ok = cudaIpcGetMemHandle(&ipc, h->base) == cudaSuccess;
+    if (ok) memcpy(handle64, &ipc, 64);
+  }
+  if (!ok || cudaDeviceSynchronize() != cudaSuccess) {
+    set_error("phifem_halo_create: %s", cudaGetErrorString(cudaGetLastError()));
+    delete h;
+    return PHIFEM_ERR_CUDA;
+  }
+  *out = h;
+  return PHIFEM_OK;
+}
+
+extern "C" int phifem_halo_connect(phifem_halo* h, const void* handles, const int64_t* remote_offset,
+                                   const int64_t* send_ptr, const int64_t* send_src, int64_t n_recv) {
+  PHIFEM_CHECK_ARG(h && handles && remote_offset && send_ptr && send_src, "null pointer");
+  PHIFEM_CHECK_ARG(n_recv >= 0 && n_recv <= h->capacity, "n_recv exceeds the capacity agreed at creation");
+  for (int q = 0; q < h->world; ++q) {
+    if (q == h->rank) continue;
+    PHIFEM_CHECK_ARG(remote_offset[q] >= 0 && remote_offset[q] + (send_ptr[q + 1] - send_ptr[q]) <= h->capacity,
+                     "a send segment does not fit the peer's receive buffer");
+    cudaIpcMemHandle_t ipc;
+    memcpy(&ipc, (const char*)handles + 64 * q, 64);
+    void* ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, ipc, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      set_error("phifem_halo_connect: rank %d cannot map the receive buffer of rank %d: %s", h->rank, q,
+                cudaGetErrorString(cudaGetLastError()));
+      return PHIFEM_ERR_CUDA;
+    }
+    h->peers[q] = (char*)ptr;
+    h->opened[q] = true;
+  }
+  h->n_recv = n_recv;
+  h->n_send = send_ptr[h->world];
+  if (cudaMemcpy(h->table, h->peers, sizeof(char*) * 64, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(h->remote_offset, remote_offset, sizeof(int64_t) * h->world, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(h->send_ptr, send_ptr, sizeof(int64_t) * (h->world + 1), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(h->send_src, send_src, sizeof(int64_t) * h->world, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("phifem_halo_connect: %s", cudaGetErrorString(cudaGetLastError()));
+    return PHIFEM_ERR_CUDA;
+  }
+  return PHIFEM_OK;
+}
+
+extern "C" int phifem_halo_exchange(phifem_halo* h, const double* src, const int64_t* send_index,
+                                    const int64_t* recv_index, double* dst, void* stream) {
+  PHIFEM_CHECK_ARG(h && h->table, "create and connect first");
+  PHIFEM_CHECK_ARG((h->n_send == 0 || src) && (h->n_recv == 0 || (recv_index && dst)), "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t work = h->n_send > h->n_recv ? h->n_send : h->n_recv;
+  int64_t grid = (work + 256 * 4 - 1) / (256 * 4);
+  if (grid < 1) grid = 1;
+  if (grid > 2 * kNumSMs) grid = 2 * kNumSMs;  // all CTAs resident: the receive phase spins on the peers' flags
+  k_halo_begin<<<1, 1, 0, st>>>(h->epoch, h->ticket);
+  k_halo_exchange<<<(unsigned)grid, 256, 0, st>>>(h->table, h->world, h->rank, h->capacity, h->epoch, h->ticket,
+                                                  h->remote_offset, h->send_ptr, h->send_src, src, send_index, recv_index,
+                                                  h->n_recv, dst, h->error);
+  PHIFEM_CHECK_LAUNCH();
+  return PHIFEM_OK;
+}
+
+extern "C" int phifem_halo_error(phifem_halo* h) {  // synchronises; 1 = a receive timed out
+  if (!h) return 0;
+  int e = 0;
+  cudaMemcpy(&e, h->error, sizeof(int), cudaMemcpyDeviceToHost);
+  return e;
+}
+
+extern "C" void phifem_halo_destroy(phifem_halo* h) {
+  if (!h) return;
+  cudaDeviceSynchronize();
+  for (int q = 0; q < h->world; ++q)
+    if (h->opened[q]) cudaIpcCloseMemHandle(h->peers[q]);
+  cudaFree(h->base);
+  cudaFree(h->table);
+  cudaFree(h->remote_offset);
+  cudaFree(h->send_ptr);
+  cudaFree(h->send_src);
+  cudaFree(h->epoch);
+  cudaFree(h->ticket);
+  cudaFree(h->error);
+  delete h;
+}

@@ -295,9 +295,51 @@ class SlabProblem:
         self.exchange()
         return self.data[:p.nnz], self.b_owned()
 
+    def enable_peer_halo(self):
+        """mode "exchange": the halo contributions travel as stores into the owners' HBM over NVLink and are added there
+        by the same kernel (phifem_b200/peer.py HaloExchange, csrc/peer.cu) instead of grouped NCCL send / recv + eager
+        index_add_.  Call after build_plan; returns False where peer mapping is not available (every rank agrees)."""
+        from . import peer
+        if self.world == 1 or self.mode != "exchange" or self.plan is None or self.device.type != "cuda":
+            return False
+        p, world, rank = self.plan, self.world, self.rank
+        try:
+            halo_a = peer.HaloExchange(rank, world,
+                                       [hi - lo for lo, hi in p.send_ranges],
+                                       [0 if s is None else s.numel() for s in p.recv_slots],
+                                       send_src=[lo for lo, _ in p.send_ranges], group=self.group)
+            halo_b = peer.HaloExchange(rank, world, [t.numel() for t in p.b_send_local],
+                                       [0 if s is None else s.numel() for s in p.b_recv_rows], group=self.group)
+            ok = 1
+        except Exception:   # noqa: BLE001 -- every rank must agree, see below
+            halo_a = halo_b = None
+            ok = 0
+        t = torch.tensor([ok], device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        if int(t.item()) == 0:
+            for h in (halo_a, halo_b):
+                if h is not None:
+                    h.close()
+            return False
+        empty = torch.zeros(0, dtype=torch.int64, device=self.device)
+        self._halo = SimpleNamespace(
+            a=halo_a, b=halo_b,
+            a_recv=torch.cat([s for s in p.recv_slots if s is not None] or [empty]).contiguous(),
+            b_send=torch.cat([t_ for t_ in p.b_send_local] or [empty]).contiguous(),
+            b_recv=torch.cat([s for s in p.b_recv_rows if s is not None] or [empty]).contiguous())
+        return True
+
     def exchange(self):
-        """Halo rows -> owners: grouped send/recv of the send segments, indexed add on arrival."""
+        """Halo rows -> owners: over NVLink peer memory when enable_peer_halo() succeeded, else a grouped send/recv of
+        the send segments and an indexed add on arrival."""
         if self.world == 1:
+            return
+        halo = getattr(self, "_halo", None)
+        if halo is not None:
+            p = self.plan
+            self._b_owned = self.b_local[p.owned_vertices].clone()
+            halo.a.exchange(self.data, halo.a_recv, self.data)
+            halo.b.exchange(self.b_local, halo.b_recv, self._b_owned, send_index=halo.b_send)
             return
         p, ops, bsend = self.plan, [], []
         for q in range(self.world):

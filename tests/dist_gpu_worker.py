@@ -18,6 +18,8 @@ from phifem_b200.mesh import MeshTags  # noqa: E402
 def main():
     n = int(sys.argv[1])
     mode = sys.argv[2] if len(sys.argv) > 2 else "exchange"
+    peer_halo = mode == "exchange-peer"      # the same numeric path, halo over NVLink peer memory (csrc/peer.cu)
+    mode = "exchange" if peer_halo else mode
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
@@ -26,8 +28,15 @@ def main():
     dls = mesh_scripts._DeviceLevelset(prob.mesh, fem.Function(fem.functionspace_p1_device(prob.mesh), prob.phi), 1)
     ws = prob.classify(dls, mesh_scripts.TagWorkspace(prob.mesh))
     plan = prob.build_plan(ws.cell_tags8, ws.facet_tags8)
+    if peer_halo:
+        assert prob.enable_peer_halo(), "peer mapping of the halo buffers failed"
     data, b = prob.assemble(1.0)
     torch.cuda.synchronize()
+    if peer_halo:   # two more exchanges: both parities of the receive buffers, a reused epoch slot
+        for _ in range(2):
+            data, b = prob.assemble(1.0)
+        torch.cuda.synchronize()
+        assert not prob._halo.a.timed_out() and not prob._halo.b.timed_out()
     if mode == "rows":
         indptr, indices, _, _ = prob.owned_csr()
     else:
@@ -61,7 +70,7 @@ def main():
         assert row == mesh.num_vertices
         assert (sum(p["sent"] for p in parts) > 0) == (mode == "exchange")
         print("DIST-OK world=%d mode=%s cells=%d halo_entries=%d"
-              % (world, mode, mesh.num_cells, sum(p["sent"] for p in parts)))
+              % (world, mode + ("-peer" if peer_halo else ""), mesh.num_cells, sum(p["sent"] for p in parts)))
     dist.barrier()
     dist.destroy_process_group()
 
