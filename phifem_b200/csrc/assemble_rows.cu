@@ -29,6 +29,9 @@ constexpr int kRowsBlock = PHIFEM_ROWS_BLOCK;
 #ifndef PHIFEM_SURF_MINBLOCKS
 #define PHIFEM_SURF_MINBLOCKS PHIFEM_ROWS_MINBLOCKS
 #endif
+#ifndef PHIFEM_SURF_DEPTH
+#define PHIFEM_SURF_DEPTH 2
+#endif
 #ifndef PHIFEM_ONCE_MINBLOCKS
 #define PHIFEM_ONCE_MINBLOCKS 1
 #endif
@@ -555,18 +558,7 @@ __global__ void __launch_bounds__(kRowsBlock, KIND == 1 ? PHIFEM_SURF_MINBLOCKS 
     // record words are streamed from HBM (read once): kept 5 deep so that the word naming the NEXT facet has
     // arrived when its work record is requested
     const double sg = sigma < 0.0 ? -1.0 : 1.0;
-    double wa[W], wb[W];
-    uint2 w0 = fetch_rec(kb), w1 = fetch_rec(kb + 1), w2 = fetch_rec(kb + 2), w3 = fetch_rec(kb + 3),
-          w4 = fetch_rec(kb + 4);
-    if (kb < ke) fetch_work(w0, wa);
-    auto body = [&](int k, const double (&cur)[W], double (&nxt)[W]) {
-      const uint2 rec = w0;
-      fetch_work(w1, nxt);
-      w0 = w1;
-      w1 = w2;
-      w2 = w3;
-      w3 = w4;
-      w4 = fetch_rec(k + 5);
+    auto evaluate = [&](const uint2 rec, const double (&cur)[W]) {
       if (rec.y == kPad) return;
       if (rec.y >> 31) {  // one-sided entity: byte 0 = the opposite vertex, byte j = facet vertex (t + j) % D
         double Kb[NV];
@@ -589,10 +581,52 @@ __global__ void __launch_bounds__(kRowsBlock, KIND == 1 ? PHIFEM_SURF_MINBLOCKS 
       for (int j = 0; j < NG - 1; ++j)  // j-th other macro vertex = macro index j (j < a) or j + 1
         acc[((rec.x >> (8 * j)) & 0xff) * kRowsBlock] += j < a ? K[j] : K[j + 1];
     };
+#if PHIFEM_SURF_DEPTH == 3
+    // three work buffers: the records of facets k + 1 and k + 2 are in flight while record k is evaluated (the pass is
+    // bound by the latency of these L2 gathers: long-scoreboard stalls 7.6 per issue with two buffers)
+    double wa[W], wb[W], wc[W];
+    uint2 w0 = fetch_rec(kb), w1 = fetch_rec(kb + 1), w2 = fetch_rec(kb + 2), w3 = fetch_rec(kb + 3),
+          w4 = fetch_rec(kb + 4), w5 = fetch_rec(kb + 5);
+    if (kb < ke) {
+      fetch_work(w0, wa);
+      fetch_work(w1, wb);
+    }
+    auto body = [&](int k, const double (&cur)[W], double (&nxt)[W]) {
+      const uint2 rec = w0;
+      fetch_work(w2, nxt);
+      w0 = w1;
+      w1 = w2;
+      w2 = w3;
+      w3 = w4;
+      w4 = w5;
+      w5 = fetch_rec(k + 6);
+      evaluate(rec, cur);
+    };
+    for (int k = kb; k < ke; k += 3) {
+      body(k, wa, wc);
+      if (k + 1 < ke) body(k + 1, wb, wa);
+      if (k + 2 < ke) body(k + 2, wc, wb);
+    }
+#else
+    double wa[W], wb[W];
+    uint2 w0 = fetch_rec(kb), w1 = fetch_rec(kb + 1), w2 = fetch_rec(kb + 2), w3 = fetch_rec(kb + 3),
+          w4 = fetch_rec(kb + 4);
+    if (kb < ke) fetch_work(w0, wa);
+    auto body = [&](int k, const double (&cur)[W], double (&nxt)[W]) {
+      const uint2 rec = w0;
+      fetch_work(w1, nxt);
+      w0 = w1;
+      w1 = w2;
+      w2 = w3;
+      w3 = w4;
+      w4 = fetch_rec(k + 5);
+      evaluate(rec, cur);
+    };
     for (int k = kb; k < ke; k += 2) {
       body(k, wa, wb);
       if (k + 1 < ke) body(k + 1, wb, wa);
     }
+#endif
   }
   acc[dpos * kRowsBlock] += diag;
   if constexpr (KIND != kSurface) {
