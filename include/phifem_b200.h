@@ -61,6 +61,9 @@ typedef struct phifem_mesh {
    * boundary_scale[i][k] = integration scale (edge length / twice the triangle area) of local facet lf_k. */
   const uint32_t* boundary_owner; /* [n_boundary_facets, 2] */
   const double* boundary_scale;   /* [n_boundary_facets, 4] */
+  /* optional (tetrahedra): the coordinates padded to 4 doubles per vertex, 32-byte aligned -- the row-gather cell pass
+   * then fetches a vertex with one 256-bit load (one address, one sector) instead of three 64-bit ones */
+  const double* x4;               /* [n_vertices, 4] = {x, y, z, 0} */
 } phifem_mesh;
 
 /* Discrete level set as seen by the detection forms (src/phifem/mesh_scripts.py:95-134).

@@ -13,6 +13,8 @@
 //
 // Connectivity comes from the CSR pattern itself: a record holds the positions inside row r's column
 // list of the entity's other vertices, so `indices[start + pos]` names them (include/phifem_b200.h).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "p1_forms.cuh"
 
@@ -373,15 +375,22 @@ __device__ __forceinline__ void ghost_row(const double (&wk)[kGhostWork<D>], int
   }
 }
 
-template <int D>
+// X4: x is the mesh's padded coordinate table (phifem_mesh.x4, 4 doubles per vertex, 32-byte aligned): one 256-bit
+// gather and one address per vertex instead of three 64-bit ones, and a vertex never straddles two sectors
+template <int D, bool X4 = false>
 __device__ __forceinline__ void load_vertex(const double* __restrict__ x, const double* __restrict__ phi,
                                             int v, double (&xv)[D], double& p) {
+  if constexpr (X4 && D == 3) {
+    double pad;
+    ldg256(x + (int64_t)v * 4, xv[0], xv[1], xv[2], pad);
+  } else {
 #pragma unroll
-  for (int d = 0; d < D; ++d) xv[d] = __ldg(x + (int64_t)v * D + d);
+    for (int d = 0; d < D; ++d) xv[d] = __ldg(x + (int64_t)v * D + d);
+  }
   p = __ldg(phi + v);
 }
 
-enum { kCells = 0, kSurface = 1, kCellsGeom = 2 };
+enum { kCells = 0, kSurface = 1, kCellsGeom = 2, kCellsX4 = 3 };
 
 // coordinates, phi and f of the D other vertices of a cell record
 template <int D>
@@ -415,11 +424,11 @@ __global__ void __launch_bounds__(kRowsBlock, KIND == 1 ? PHIFEM_SURF_MINBLOCKS 
   double* acc = acc_s + tid;
   for (int k = 0; k < nnz; ++k) acc[k * kRowsBlock] = 0.0;
   double xr[D], pr;
-  load_vertex<D>(x, phi, r, xr, pr);
+  load_vertex<D, KIND == kCellsX4>(x, phi, r, xr, pr);
   double diag = 0.0, br = 0.0;
   const int kb = __ldg(rl.ptr + slice), ke = __ldg(rl.ptr + slice + 1);
 
-  if constexpr (KIND == kCells) {  // cells tagged 1 / 2 containing vertex r
+  if constexpr (KIND == kCells || KIND == kCellsX4) {  // cells tagged 1 / 2 containing vertex r
     // Four records in flight per thread, one per dependent-load level: while record k is evaluated the
     // vertex data of record k+1 is arriving, the column indices of record k+2 have been requested and so
     // has the word of record k+3.  The two data buffers swap roles (loop unrolled by two) so that no
@@ -434,7 +443,7 @@ __global__ void __launch_bounds__(kRowsBlock, KIND == 1 ? PHIFEM_SURF_MINBLOCKS 
     auto fetch_data = [&](const int (&v)[D], Others<D>& o) {
 #pragma unroll
       for (int j = 0; j < D; ++j) {
-        load_vertex<D>(x, phi, v[j], o.X[j], o.p[j]);
+        load_vertex<D, KIND == kCellsX4>(x, phi, v[j], o.X[j], o.p[j]);
         o.f[j] = __ldg(f + v[j]);
       }
     };
@@ -697,15 +706,18 @@ extern "C" int phifem_assemble_rows_p1(const phifem_mesh* mesh, const double* ph
   const size_t smem = (size_t)plan->max_row_nnz * kRowsBlock * sizeof(double);
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t err = cudaSuccess;
-  auto launch = [&](auto kernel, const phifem_row_list& rl, const double* work) {
+  auto launch = [&](auto kernel, const phifem_row_list& rl, const double* work, const double* coords = nullptr) {
     if (rl.n_listed == 0 || err != cudaSuccess) return;
     if (smem > 48 * 1024)
       err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int64_t grid = (rl.n_listed + kRowsBlock - 1) / kRowsBlock;
     if (err == cudaSuccess)
-      kernel<<<(unsigned)grid, kRowsBlock, smem, st>>>(mesh->x, phi, f, sigma, plan->indptr, plan->indices,
-                                                       rl, work, data, b);
+      kernel<<<(unsigned)grid, kRowsBlock, smem, st>>>(coords ? coords : mesh->x, phi, f, sigma, plan->indptr,
+                                                       plan->indices, rl, work, data, b);
   };
+  // the padded coordinate table is an option of the mesh (NULL by default: -2 % on the structured mesh, +2 % on the
+  // renumbered unstructured one at config E)
+  const bool use_x4 = mesh->x4 != nullptr;
   const bool geom = plan->cell_geom != nullptr;
   auto cell_tiles = [&]() {  // cell-once form of the cell pass
     if (err == cudaSuccess)
@@ -738,6 +750,7 @@ extern "C" int phifem_assemble_rows_p1(const phifem_mesh* mesh, const double* ph
     once(k_surface_once_p1<3>);
     if (tiles) cell_tiles();
     else if (geom) launch(k_assemble_rows_p1<3, kCellsGeom>, plan->cells, plan->cell_geom);
+    else if (use_x4) launch(k_assemble_rows_p1<3, kCellsX4>, plan->cells, nullptr, mesh->x4);
     else launch(k_assemble_rows_p1<3, kCells>, plan->cells, nullptr);
     if (fork) cudaStreamWaitEvent(st, ss.join, 0);
     launch(k_assemble_rows_p1<3, kSurface>, plan->surface, plan->surface_work);

@@ -217,6 +217,16 @@ class Mesh:
             self._host["bfacets"] = torch.nonzero(self.f2c[:, 1] < 0).reshape(-1).to(torch.int32).contiguous()
         return self._host["bfacets"]
 
+    @property
+    def x4(self):
+        """Coordinates padded to 4 doubles per vertex (tetrahedra, cached): one 256-bit gather per vertex in the row-gather
+        cell pass (phifem_mesh.x4)."""
+        if "x4" not in self._host:
+            x4 = torch.zeros((self.num_vertices, 4), dtype=torch.float64, device=self.device)
+            x4[:, :self.gdim] = self.x
+            self._host["x4"] = x4
+        return self._host["x4"]
+
     def boundary_records(self):
         """(owner + meta [nb, 2] uint32 as int32 storage, scales [nb, 4]) of the mesh-boundary facets, cached: the static
         part of the ds detection of reference mesh_scripts.py:434-452 (csrc/tags.cu, k_boundary_records).  CUDA meshes
