@@ -30,10 +30,62 @@ struct phifem_rows_plan_handle {
   phifem_rows_plan_info info;
   void* owned[40];
   int n_owned;
+  size_t owned_bytes[40];
+  int device;
 };
 
 namespace phifem {
 cudaMemPool_t scratch_pool();  // csrc/symbolic.cu: private stream-ordered pool, cached between calls
+
+// The arrays a plan OWNS (pattern, row lists, records: 0.55 GB at config E) are cudaMalloc blocks; a destroyed plan parks
+// them here and the next plan takes the blocks that fit, so that re-planning -- what a moving interface pays whenever the
+// cut pattern changes -- makes no driver allocation at all (73 -> 14 ms at config E; taking them from the stream-ordered
+// pool instead made the FIRST plan of a process 0.5-0.9 s: the pool grows by one mapping per array).
+// phifem_pattern_release_scratch() empties the cache.
+namespace {
+struct BlockCache {
+  static constexpr int kMax = 96;
+  void* ptr[kMax];
+  size_t bytes[kMax];
+  int n = 0;
+  size_t total = 0;
+};
+BlockCache g_block_cache[64];
+constexpr size_t kBlockCacheLimit = 4ull << 30;
+}  // namespace
+
+void* plan_block_take(int dev, size_t bytes) {
+  BlockCache& c = g_block_cache[dev & 63];
+  int best = -1;
+  for (int i = 0; i < c.n; ++i)
+    if (c.bytes[i] >= bytes && c.bytes[i] <= bytes + bytes / 4 + 4096 && (best < 0 || c.bytes[i] < c.bytes[best])) best = i;
+  if (best < 0) return nullptr;
+  void* q = c.ptr[best];
+  c.total -= c.bytes[best];
+  c.ptr[best] = c.ptr[c.n - 1];
+  c.bytes[best] = c.bytes[c.n - 1];
+  --c.n;
+  return q;
+}
+void plan_block_give(int dev, void* q, size_t bytes) {
+  BlockCache& c = g_block_cache[dev & 63];
+  if (c.n >= BlockCache::kMax || c.total + bytes > kBlockCacheLimit) {
+    cudaFree(q);
+    return;
+  }
+  c.ptr[c.n] = q;
+  c.bytes[c.n] = bytes;
+  ++c.n;
+  c.total += bytes;
+}
+void plan_block_cache_release() {  // called by phifem_pattern_release_scratch (csrc/symbolic.cu)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  BlockCache& c = g_block_cache[dev & 63];
+  for (int i = 0; i < c.n; ++i) cudaFree(c.ptr[i]);
+  c.n = 0;
+  c.total = 0;
+}
 namespace {
 
 constexpr int kB = 256;
@@ -407,7 +459,9 @@ using namespace phifem;
 
 extern "C" void phifem_rows_plan_destroy(phifem_rows_plan_handle* h) {
   if (!h) return;
-  for (int i = 0; i < h->n_owned; ++i) cudaFree(h->owned[i]);
+  // kernels reading the arrays may still be in flight on any stream; the blocks are parked for the next plan
+  if (h->n_owned) cudaDeviceSynchronize();
+  for (int i = 0; i < h->n_owned; ++i) plan_block_give(h->device, h->owned[i], h->owned_bytes[i]);
   delete h;
 }
 
@@ -444,9 +498,15 @@ extern "C" int phifem_rows_plan_create(const phifem_mesh* mesh, const int8_t* ce
   Tmp tmp(st, pool);
   phifem_rows_plan_handle* h = new phifem_rows_plan_handle();
   h->n_owned = 0;
+  h->device = 0;
+  cudaGetDevice(&h->device);
   auto own = [&](size_t bytes) -> void* {
-    void* q = nullptr;
-    if (h->n_owned >= 40 || cudaMalloc(&q, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    if (bytes == 0) bytes = 1;
+    if (h->n_owned >= 40) return nullptr;
+    void* q = plan_block_take(h->device, bytes);  // (a parked block may be up to 25 % larger; it is given back under
+                                                  // the requested size, never a larger one)
+    if (!q && cudaMalloc(&q, bytes) != cudaSuccess) return nullptr;
+    h->owned_bytes[h->n_owned] = bytes;
     h->owned[h->n_owned++] = q;
     return q;
   };

@@ -176,10 +176,14 @@ struct Scratch {  // device allocations freed on scope exit (stream-ordered)
 
 using namespace phifem;
 
+namespace phifem {
+void plan_block_cache_release();  // csrc/rows_plan.cu: parked arrays of destroyed row-gather plans
+}
 extern "C" void phifem_pattern_release_scratch(void) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (g_pools[dev & 63]) cudaMemPoolTrimTo(g_pools[dev & 63], 0);
+  plan_block_cache_release();
 }
 
 extern "C" void phifem_pattern_destroy(phifem_pattern* p) {
