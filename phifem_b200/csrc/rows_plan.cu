@@ -15,6 +15,7 @@
 //   4. surface records (ghost-penalty macro elements, one-sided entities): one sort by (row, sequence), rows ordered
 //      along the Morton curve and balanced by record count inside chunks of 4096 rows, as phifem_b200/rows.py does.
 // Every array equals the torch-built plan bit for bit (tests/test_gpu_rows_plan_capi.py).
+#include <mutex>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_reduce.cuh>
 #include <cub/device/device_run_length_encode.cuh>
@@ -51,10 +52,12 @@ struct BlockCache {
   size_t total = 0;
 };
 BlockCache g_block_cache[64];
+std::mutex g_block_cache_mutex;  // plans may be created / destroyed from several host threads
 constexpr size_t kBlockCacheLimit = 4ull << 30;
 }  // namespace
 
 void* plan_block_take(int dev, size_t bytes) {
+  std::lock_guard<std::mutex> lock(g_block_cache_mutex);
   BlockCache& c = g_block_cache[dev & 63];
   int best = -1;
   for (int i = 0; i < c.n; ++i)
@@ -68,6 +71,7 @@ void* plan_block_take(int dev, size_t bytes) {
   return q;
 }
 void plan_block_give(int dev, void* q, size_t bytes) {
+  std::lock_guard<std::mutex> lock(g_block_cache_mutex);
   BlockCache& c = g_block_cache[dev & 63];
   if (c.n >= BlockCache::kMax || c.total + bytes > kBlockCacheLimit) {
     cudaFree(q);
@@ -81,6 +85,7 @@ void plan_block_give(int dev, void* q, size_t bytes) {
 void plan_block_cache_release() {  // called by phifem_pattern_release_scratch (csrc/symbolic.cu)
   int dev = 0;
   cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_block_cache_mutex);
   BlockCache& c = g_block_cache[dev & 63];
   for (int i = 0; i < c.n; ++i) cudaFree(c.ptr[i]);
   c.n = 0;
