@@ -95,6 +95,15 @@ int main(int argc, char** argv) {
   mesh.f2c = to_device(f2c);
   mesh.boundary_facets = to_device(bfacets);
   mesh.n_boundary_facets = (int64_t)bfacets.size();
+  {  // once per mesh: the static part of the ds detection on the mesh-boundary facets (mesh_scripts.py:434-452)
+    uint32_t* owner = nullptr;
+    double* scale = nullptr;
+    cudaMalloc(&owner, std::max<size_t>(1, bfacets.size()) * 2 * sizeof(uint32_t));
+    cudaMalloc(&scale, std::max<size_t>(1, bfacets.size()) * 4 * sizeof(double));
+    CHECK(phifem_boundary_records(&mesh, owner, scale, nullptr));
+    mesh.boundary_owner = owner;
+    mesh.boundary_scale = scale;
+  }
   double* d_phi = to_device(phi);
   double* d_f = to_device(f);
 
