@@ -790,7 +790,7 @@ def run_ours(args):
             torch.cuda.synchronize()
             t_re = time.perf_counter()
             if not args.no_reorder:
-                mesh = mesh.reordered()
+                mesh = mesh.reordered(args.curve)
             torch.cuda.synchronize()
             reorder_ms = (time.perf_counter() - t_re) * 1e3
         phi = synthetic.sphere_levelset(mesh.x, **ls_kw)
@@ -870,9 +870,14 @@ def run_ours(args):
             ums, uper, _ = timed_steps(uw, args.steps, 1, presteps=3)
             uroof, _, _ = roofline_of(uw, uper, ums, clocks)
             unstructured = {"mesh": "SURVEY.md 8(d) variant of the same configuration: vertex jitter +-0.2 h (seed 0), "
-                                    "cells permuted (seed 1), vertices relabelled (seed 2), then renumbered along the "
-                                    "Morton curve (Mesh.reordered, timed as reorder_ms); level set and source "
+                                    "cells permuted (seed 1), vertices relabelled (seed 2), then renumbered "
+                                    + ("along the Morton curve" if getattr(umesh, "reorder_curve", "") == "morton" else
+                                       "in count-balanced pencils (slabs of equal vertex count along x, pencils of equal "
+                                       "count along y, sorted along z: parameter-free; chosen by curve=auto for meshes "
+                                       "with grid connectivity, the Morton curve otherwise)")
+                                    + " (Mesh.reordered, timed as reorder_ms); level set and source "
                                     "interpolated on that mesh",
+                            "curve": getattr(umesh, "reorder_curve", args.curve),
                             "cells": umesh.num_cells, "ms_per_step": ums, "value": umesh.num_cells / (ums * 1e-3),
                             "unit": UNIT, "ratio_to_structured": ums / structured_ms,
                             "step_frac": uroof["step_frac"], "kernels_ms": uper, "reorder_ms": reorder_ms,
@@ -895,7 +900,8 @@ def run_ours(args):
                            "name": args.config, "mesh": args.mesh + (
                                "" if args.mesh == "structured" else
                                (": jitter 0.2 h, cells permuted, vertices relabelled" +
-                                (", NOT renumbered" if args.no_reorder else ", renumbered along the Morton curve"))),
+                                (", NOT renumbered" if args.no_reorder else
+                                 ", renumbered (Mesh.reordered, curve=%s)" % args.curve))),
                            "cells_total": n_cells_total, "counts": counts,
                            "l2_policy": "inputs larger than L2 (%.1f GB streamed per step)"
                                         % (ab["total"] / 1e9),
@@ -980,6 +986,9 @@ def main():
                     help="unstructured = SURVEY.md 8(d)'s variant (jitter, cell permutation, vertex relabelling), "
                          "renumbered along the Morton curve in the mesh-level symbolic phase")
     ap.add_argument("--no-reorder", action="store_true", help="unstructured mesh left in its random numbering")
+    ap.add_argument("--curve", default="auto", choices=["auto", "morton", "pencil"],
+                    help="renumbering of the unstructured mesh (Mesh.reordered): Morton curve / count-balanced pencils / "
+                         "auto = pencils when the mesh has the connectivity of a grid")
     ap.add_argument("--cell-pass", default="rows", choices=["rows", "tiles"],
                     help="row-gather cell pass / cell-once tile pass (csrc/assemble_tiles.cu)")
     ap.add_argument("--rows-per-tile", type=int, default=256, choices=[128, 256])

@@ -146,17 +146,35 @@ class Mesh:
             cells = cells[:, [0, 1, 3, 2]]
         return Mesh(x, cells, cell_type, device)
 
-    def reordered(self, curve="morton"):
-        """The same mesh renumbered along a space-filling curve: vertices by the Morton key of their coordinates, cells
-        by the Morton key of their centroid (cell-local vertex order kept, so local facets and orientations are
-        unchanged).  This is the data-locality reordering dolfinx applies when it builds a mesh (`create_mesh` reorders
+    def structured_fraction(self):
+        """Share of the vertices that have the most common number of cells around them, relative to the interior share of
+        a grid with as many vertices: ~1 for a mesh with the connectivity of a tensor grid (whatever its numbering and
+        however its vertices were moved), ~0.1 for a Delaunay mesh.  Decides the renumbering of `reordered(curve="auto")`."""
+        val = torch.bincount(self.cells.reshape(-1).long(), minlength=self.num_vertices)
+        modal = float(torch.bincount(val).max()) / max(1, self.num_vertices)
+        # the vertices on the boundary of a grid have fewer cells: compare with the interior share of an m^d grid
+        m = max(3.0, self.num_vertices ** (1.0 / self.gdim))
+        return min(1.0, modal / ((m - 2.0) / m) ** self.gdim)
+
+    def reordered(self, curve="auto"):
+        """The same mesh renumbered for data locality: curve="morton": vertices by the Morton key of their coordinates,
+        cells by the Morton key of their centroid; curve="pencil": count-balanced slabs / pencils / lines (see
+        `_reordered_pencils`); curve="auto" (default): pencils for a mesh with grid connectivity (`structured_fraction`
+        >= 0.8), the Morton curve otherwise -- measured on the B200: scrambled grid of config E 1.86 ms
+        per step in pencils against 2.16 ms along the Morton curve, Delaunay mesh of a random point cloud 0.242 ms against
+        0.219 ms for the cell pass.  The cell-local vertex order is kept, so local facets and orientations are
+        unchanged.  This is the data-locality reordering dolfinx applies when it builds a mesh (`create_mesh` reorders
         cells and vertices and keeps `topology.original_cell_index` / `geometry.input_global_indices` [dep-knowledge]);
         like there, everything downstream -- facet numbering, tags, dofs, CSR rows -- lives in the NEW numbering and the
         two maps translate user data:
             new.original_cell_index[c_new] = c_old        new.input_global_indices[v_new] = v_old
         so per-vertex data of the old mesh becomes `data[new.input_global_indices]`."""
-        if curve != "morton":
-            raise ValueError("curve must be 'morton'")
+        if curve not in ("auto", "morton", "pencil"):
+            raise ValueError("curve must be 'auto', 'morton' or 'pencil'")
+        if curve == "auto":
+            curve = "pencil" if self.structured_fraction() >= 0.8 else "morton"
+        if curve == "pencil":
+            return self._reordered_pencils()
         vperm = torch.argsort(morton_keys(self.x), stable=True)                 # new -> old
         vinv = torch.empty_like(vperm)
         vinv[vperm] = torch.arange(self.num_vertices, device=self.device)
@@ -171,6 +189,43 @@ class Mesh:
         del ckey
         new = Mesh(self.x[vperm], vinv[self.cells[cperm].long()].to(torch.int32), self.cell_type, self.device)
         new.sfc_ordered = True
+        new.reorder_curve = "morton"
+        new.original_cell_index = cperm
+        new.input_global_indices = vperm
+        return new
+
+    def _reordered_pencils(self):
+        """curve="pencil": vertices in slabs of equal COUNT along axis 0, each slab in pencils of equal count along axis
+        1 (3D), each pencil sorted along the last axis; cells by their lowest new vertex.  Parameter-free (no mesh size
+        enters) and, on a mesh whose vertices sit near the points of a tensor grid (the jittered variant of SURVEY.md
+        8d: jitter below half a spacing), exactly the lexicographic numbering of that grid -- the numbering under which
+        the rows of a warp of the row-gather kernels are neighbours along a line and their gathers coalesce (cell pass at
+        config E: 1.20 ms lexicographic, 1.55 ms Morton)."""
+        nv, d, dev = self.num_vertices, self.gdim, self.device
+        m = max(1, round(nv ** (1.0 / d)))
+        per = [m ** (d - 1 - k) if m ** d == nv else int(-(-nv ** ((d - 1 - k) / d) // 1)) for k in range(d - 1)]
+        group = torch.zeros(nv, dtype=torch.int64, device=dev)     # slab, then (slab, pencil) index of each vertex
+        for k in range(d - 1):
+            rank = torch.empty(nv, dtype=torch.int64, device=dev)
+            rank[torch.argsort(self.x[:, k], stable=True)] = torch.arange(nv, device=dev)
+            order = torch.argsort(group * nv + rank)                # vertices grouped, sorted along axis k inside
+            start = torch.zeros(int(group.max()) + 2, dtype=torch.int64, device=dev)
+            start[1:] = torch.cumsum(torch.bincount(group, minlength=start.numel() - 1), dim=0)
+            pos = torch.empty(nv, dtype=torch.int64, device=dev)
+            pos[order] = torch.arange(nv, device=dev)
+            sub = (pos - start[group]) // max(1, per[k])
+            width = int(sub.max()) + 1
+            group = group * width + sub
+        rank = torch.empty(nv, dtype=torch.int64, device=dev)
+        rank[torch.argsort(self.x[:, d - 1], stable=True)] = torch.arange(nv, device=dev)
+        vperm = torch.argsort(group * nv + rank)                    # new -> old
+        vinv = torch.empty_like(vperm)
+        vinv[vperm] = torch.arange(nv, device=dev)
+        cells_new = vinv[self.cells.long()]
+        cperm = torch.argsort(cells_new.min(dim=1).values, stable=True)
+        new = Mesh(self.x[vperm], cells_new[cperm].to(torch.int32), self.cell_type, self.device)
+        new.sfc_ordered = True
+        new.reorder_curve = "pencil"
         new.original_cell_index = cperm
         new.input_global_indices = vperm
         return new

@@ -128,3 +128,22 @@ def test_user_tags_outside_int8_do_not_wrap_into_computed_values():
     t8 = mesh_scripts._narrow_tags(v)
     assert t8.dtype == torch.int8
     assert t8.tolist() == [0, 1, 2, 3, 4, 5, 6] + [0] * 13
+
+
+@pytest.mark.parametrize("kind,curve", [("tet", "pencil"), ("tri", "pencil"), ("tet", "morton"), ("tri", "morton")])
+def test_mesh_renumbering_maps_and_pencil_order(kind, curve):
+    """Mesh.reordered: the two maps translate cells and vertices, local vertex order is kept; curve="pencil" on the
+    scrambled variant of SURVEY.md 8(d) (jitter below half a spacing) is the lexicographic numbering of the grid."""
+    base = synthetic.box_mesh(7, device="cpu") if kind == "tet" else synthetic.rectangle_mesh(11, device="cpu")
+    scr = synthetic.unstructured_variant(base, jitter=0.2, seed=5)
+    new = scr.reordered(curve)
+    assert torch.equal(new.x, scr.x[new.input_global_indices])
+    old_cells = scr.cells[new.original_cell_index].long()
+    assert torch.equal(new.input_global_indices[new.cells.long()], old_cells)       # same cells, same local order
+    assert torch.equal(torch.sort(new.input_global_indices).values, torch.arange(scr.num_vertices))
+    assert torch.equal(torch.sort(new.original_cell_index).values, torch.arange(scr.num_cells))
+    if curve == "pencil":
+        n = 7 if kind == "tet" else 11
+        h = float((base.x.max() - base.x.min()) / n)
+        assert float((new.x - base.x).abs().max()) <= 0.2 * h + 1e-12             # vertex i of the grid is vertex i again
+        assert torch.equal(new.cells.min(dim=1).values, base.cells.min(dim=1).values)   # cells grouped by their cube
