@@ -17,6 +17,27 @@ namespace phifem {
 using namespace pk;
 namespace {
 
+#ifndef PHIFEM_PK_SINGLE_STORES
+#define PHIFEM_PK_SINGLE_STORES 1
+#endif
+// Does exactly ONE cell of a conforming simplicial mesh contribute to the CSR entry (dof i, dof j) of a cell?  True when
+// the vertices the two dofs sit on (a vertex dof: itself; a P2 edge dof: the edge's two vertices) are all D + 1 vertices
+// of the cell between them AND no facet contains them all -- in 2D: two different edge dofs, or a vertex dof and the
+// dof of the opposite edge (12 of the 36 entries of a P2 triangle); in 3D: the dofs of two opposite edges (6 of 100).
+// Such entries are written with a plain store after the zero-fill instead of an fp64 reduction: the P2 cell kernel of
+// config C is bound by the rate of its reductions (42 per triangle), not by occupancy (8 or 12 warps per SM: same time).
+template <int D, int K>
+__host__ __device__ constexpr bool single_contributor(int i, int j) {
+  constexpr int NV = D + 1;
+  unsigned mask = 0;
+  for (int t = 0; t < 2; ++t) {
+    const int dof = t == 0 ? i : j;
+    if (dof < NV) mask |= 1u << dof;
+    else if (K == 2) mask |= (1u << ev<D>(dof - NV, 0)) | (1u << ev<D>(dof - NV, 1));
+  }
+  return mask == (1u << NV) - 1u;   // all vertices of the simplex: no facet (a proper subset of them) holds both dofs
+}
+
 // ---- cells: rows [I0, I1) of the symmetric element matrix (columns j >= i) and of the load vector ----
 //   A_ij = int grad(phi psi_i).grad(phi psi_j) + [cut] sigma h^2 int lap(phi psi_i) lap(phi psi_j)   (main.py:105-112)
 //   b_i  = int f phi psi_i - [cut] sigma h^2 int f lap(phi psi_i)                                     (:126-128)
@@ -91,8 +112,13 @@ __device__ __forceinline__ void cell_rows(const Geometry<D>& g, const double (&p
 #pragma unroll
     for (int j = i; j < ND; ++j) {
       const double v = A[i - I0][j];
-      atomicAdd(data + __ldg(slots + (int64_t)(i * ND + j) * stride), v);
-      if (j != i) atomicAdd(data + __ldg(slots + (int64_t)(j * ND + i) * stride), v);
+      if (PHIFEM_PK_SINGLE_STORES && single_contributor<D, KW>(i, j)) {
+        data[__ldg(slots + (int64_t)(i * ND + j) * stride)] = v;
+        data[__ldg(slots + (int64_t)(j * ND + i) * stride)] = v;
+      } else {
+        atomicAdd(data + __ldg(slots + (int64_t)(i * ND + j) * stride), v);
+        if (j != i) atomicAdd(data + __ldg(slots + (int64_t)(j * ND + i) * stride), v);
+      }
     }
   }
 }
@@ -101,8 +127,21 @@ __device__ __forceinline__ void cell_rows(const Geometry<D>& g, const double (&p
 template <int ND> struct Passes { static constexpr int N = 1; };
 template <> struct Passes<10> { static constexpr int N = 3; };
 
+// measured on the B200 at config C (16 M P2 triangles, cell kernel): 128 threads x 3 CTAs per SM 1.252 ms, x 2 CTAs 1.252,
+// x 4 CTAs (spills) 1.268; 64 threads x 6 CTAs 1.214; + the slot lines prefetched into L1 before the quadrature loop 1.188
+#ifndef PHIFEM_PK_CELLS_MINBLOCKS_2D
+#define PHIFEM_PK_CELLS_MINBLOCKS_2D 6
+#endif
+#ifndef PHIFEM_PK_CELLS_BLOCK
+#define PHIFEM_PK_CELLS_BLOCK 64
+#endif
+#ifndef PHIFEM_PK_PREFETCH_SLOTS
+#define PHIFEM_PK_PREFETCH_SLOTS 1
+#endif
+constexpr int kBlockPkCells = PHIFEM_PK_CELLS_BLOCK;
+
 template <int D, int KW, int KP>
-__global__ void __launch_bounds__(kBlockPk, D == 2 ? 3 : 2) k_assemble_cells_pk(
+__global__ void __launch_bounds__(kBlockPkCells, D == 2 ? PHIFEM_PK_CELLS_MINBLOCKS_2D : 256 / kBlockPkCells) k_assemble_cells_pk(
     phifem_mesh m, phifem_pk_space sw, phifem_pk_space sp, const double* __restrict__ qlam_g,
     const double* __restrict__ qw_g, int nq, const double* __restrict__ phi, const double* __restrict__ f,
     const int8_t* __restrict__ ctags, const int32_t* __restrict__ active, int64_t n_active,
@@ -128,6 +167,14 @@ __global__ void __launch_bounds__(kBlockPk, D == 2 ? 3 : 2) k_assemble_cells_pk(
   }
   const bool is_cut = ctags[c] == 2;
   const int32_t* sl = slots + e;
+#if PHIFEM_PK_PREFETCH_SLOTS
+  // the slot lines of the final scatter (entry-major: one coalesced line per entry and warp) are requested now, so that
+  // the ND^2 dependent load -> reduction pairs at the end find them in L1
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < ND * ND; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(sl + (int64_t)k * n_active));
+  }
+#endif
   if constexpr (ND == 10) {
     if (blockIdx.y == 0)
       cell_rows<D, KW, KP, 0, 2>(g, pc, fc, is_cut, sigma, qlam, qw, nq, sl, n_active, dofs, data, b);
@@ -763,8 +810,8 @@ extern "C" int phifem_assemble_cells_pk(const phifem_mesh* mesh, const phifem_pk
   cudaStream_t st = (cudaStream_t)stream;
   dispatch(mesh->cell_type, space_w->degree, space_phi->degree, [&](auto d, auto kw, auto kp) {
     constexpr int D = decltype(d)::value, KW = decltype(kw)::value, KP = decltype(kp)::value;
-    const dim3 grid((unsigned)((n_active + kBlockPk - 1) / kBlockPk), Passes<Space<D, KW>::ND>::N);
-    k_assemble_cells_pk<D, KW, KP><<<grid, kBlockPk, 0, st>>>(
+    const dim3 grid((unsigned)((n_active + kBlockPkCells - 1) / kBlockPkCells), Passes<Space<D, KW>::ND>::N);
+    k_assemble_cells_pk<D, KW, KP><<<grid, kBlockPkCells, 0, st>>>(
         *mesh, *space_w, *space_phi, quad->cell_points, quad->cell_weights, quad->n_cell_points, phi, f,
         cell_tags8, active, n_active, slots, sigma, data, b);
   });
