@@ -298,20 +298,30 @@ __global__ void __launch_bounds__(kBlockPk) k_assemble_ghost_pk(
     const int32_t* __restrict__ facets, int64_t n_facets, const int32_t* __restrict__ slots, double sigma,
     double* __restrict__ data) {
   using L = GhostLayout<D, KW>;
-  constexpr int NV = D + 1, ND = Space<D, KW>::ND, NDP = Space<D, KP>::ND, NM = L::NM, FPB = L::FPB;
-  __shared__ double qlam[L::kMaxPoints * D], qw[L::kMaxPoints];
-  __shared__ double Js[FPB][L::kMaxPoints][NM];
+  constexpr int NV = D + 1, ND = Space<D, KW>::ND, NDP = Space<D, KP>::ND, NM = L::NM, FPB = L::FPB, NP = NV + 2;
+  // dynamic shared memory: the rule, the jumps Js[FPB][nq][NM] and -- evaluated ONCE per (facet, side, point) instead of
+  // once per thread -- the point in the side's barycentric coordinates, phi and grad(phi).n there: Pq[FPB][2][nq][NV + 2]
+  // (the P2 tetrahedron: 20 threads per facet each re-evaluated the 10 P2 basis functions of phi at 16 points;
+  // 1.30 -> 1.04 ms for the 141 750 ghost facets of the 3d-p2 configuration -- what remains is the scatter: 400 fp64
+  // reductions per facet, 196 of them onto entries another thread of the same facet also adds to)
+  extern __shared__ double sm_ghost[];
+  double* qlam = sm_ghost;
+  double* qw = qlam + nq * D;
+  double* Js = qw + nq;
+  double* Pq = Js + (size_t)FPB * nq * NM;
   for (int i = threadIdx.x; i < nq * D; i += blockDim.x) qlam[i] = qlam_g[i];
   for (int i = threadIdx.x; i < nq; i += blockDim.x) qw[i] = qw_g[i];
   __syncthreads();
   const int fl = threadIdx.x / NM, a = threadIdx.x % NM;
   const int64_t e = (int64_t)blockIdx.x * FPB + fl;
   const bool live = fl < FPB && e < n_facets;
+  const bool minus = a >= ND;                 // the side this thread's dof lives on
+  const int al = minus ? a - ND : a;          // its index among the side's dofs
   double coef = 0.0;
+  double G[NV][D], n[D];  // geometry of this thread's side (selected value by value: stays in registers)
   if (live) {
     const int32_t fct = __ldg(facets + e);
     const int2 cc = __ldg(reinterpret_cast<const int2*>(m.f2c) + fct);
-    const bool minus = a >= ND;                 // the side this thread's dof lives on
     Geometry<D> gp, gm;
     load_geometry<D>(m, cc.x, gp);
     load_geometry<D>(m, cc.y, gm);
@@ -327,14 +337,15 @@ __global__ void __launch_bounds__(kBlockPk) k_assemble_ghost_pk(
     facet_normal<D>(gp, op, np_, area);
     facet_normal<D>(gm, om, nm_, area_m);
     coef = sigma * 0.5 * (sqrt(gp.h2) + sqrt(gm.h2)) * area;
-    double G[NV][D], n[D];  // geometry of this thread's side (selected value by value: stays in registers)
 #pragma unroll
     for (int k = 0; k < NV; ++k)
 #pragma unroll
       for (int d = 0; d < D; ++d) G[k][d] = minus ? gm.G[k][d] : gp.G[k][d];
 #pragma unroll
     for (int d = 0; d < D; ++d) n[d] = minus ? nm_[d] : np_[d];
-    for (int q = 0; q < nq; ++q) {
+    // phase 0: the ND threads of a side share the side's nq points
+    double* pq_side = Pq + ((size_t)(fl * 2 + (minus ? 1 : 0)) * nq) * NP;
+    for (int q = al; q < nq; q += ND) {
       double lam[NV];
       facet_to_cell<D>(qlam + q * D, op, lam);
       if (minus) {  // the same physical point in the barycentric coordinates of cell -
@@ -349,10 +360,24 @@ __global__ void __launch_bounds__(kBlockPk) k_assemble_ghost_pk(
 #pragma unroll
         for (int k = 0; k < NV; ++k) lam[k] = (k == 0 ? 1.0 : 0.0) + dotd<D>(gm.G[k], xq);
       }
-      double ph, gph[D], val, grad[D];
+      double ph, gph[D];
       eval_phi_only<D, KP>(lam, G, pc, ph, gph);
-      basis_one<D, KW>(lam, G, minus ? a - ND : a, val, grad);
-      Js[fl][q][a] = val * dotd<D>(gph, n) + ph * dotd<D>(grad, n);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) pq_side[q * NP + k] = lam[k];
+      pq_side[q * NP + NV] = ph;
+      pq_side[q * NP + NV + 1] = dotd<D>(gph, n);
+    }
+  }
+  __syncthreads();
+  if (live) {  // phase 1: this thread's jump at every point
+    const double* pq_side = Pq + ((size_t)(fl * 2 + (minus ? 1 : 0)) * nq) * NP;
+    for (int q = 0; q < nq; ++q) {
+      double lam[NV];
+#pragma unroll
+      for (int k = 0; k < NV; ++k) lam[k] = pq_side[q * NP + k];
+      double val, grad[D];
+      basis_one<D, KW>(lam, G, al, val, grad);
+      Js[((size_t)fl * nq + q) * NM + a] = val * pq_side[q * NP + NV + 1] + pq_side[q * NP + NV] * dotd<D>(grad, n);
     }
   }
   __syncthreads();
@@ -361,9 +386,10 @@ __global__ void __launch_bounds__(kBlockPk) k_assemble_ghost_pk(
 #pragma unroll
   for (int bb = 0; bb < NM; ++bb) E[bb] = 0.0;
   for (int q = 0; q < nq; ++q) {
-    const double wa = qw[q] * coef * Js[fl][q][a];
+    const double* jq = Js + ((size_t)fl * nq + q) * NM;
+    const double wa = qw[q] * coef * jq[a];
 #pragma unroll
-    for (int bb = 0; bb < NM; ++bb) E[bb] += wa * Js[fl][q][bb];
+    for (int bb = 0; bb < NM; ++bb) E[bb] += wa * jq[bb];
   }
 #pragma unroll
   for (int bb = 0; bb < NM; ++bb) atomicAdd(data + __ldg(slots + (e * NM + a) * NM + bb), E[bb]);
@@ -855,8 +881,12 @@ extern "C" int phifem_assemble_ghost_pk(const phifem_mesh* mesh, const phifem_pk
   cudaStream_t st = (cudaStream_t)stream;
   dispatch(mesh->cell_type, space_w->degree, space_phi->degree, [&](auto d, auto kw, auto kp) {
     constexpr int D = decltype(d)::value, KW = decltype(kw)::value, KP = decltype(kp)::value;
-    constexpr int FPB = GhostLayout<D, KW>::FPB;
-    k_assemble_ghost_pk<D, KW, KP><<<(unsigned)((n_facets + FPB - 1) / FPB), kBlockPk, 0, st>>>(
+    constexpr int FPB = GhostLayout<D, KW>::FPB, NM = GhostLayout<D, KW>::NM;
+    const int nq = quad->n_facet_points;
+    const size_t smem = sizeof(double) * ((size_t)nq * (D + 1) + (size_t)FPB * nq * (NM + 2 * (D + 3)));
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(k_assemble_ghost_pk<D, KW, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_assemble_ghost_pk<D, KW, KP><<<(unsigned)((n_facets + FPB - 1) / FPB), kBlockPk, smem, st>>>(
         *mesh, *space_w, *space_phi, quad->facet_points, quad->facet_weights, quad->n_facet_points, phi,
         facets, n_facets, slots, sigma, data);
   });
