@@ -617,6 +617,66 @@ def measure_e2e(w, args, degree):
                    "assembly plan (symbolic phase) reused; one step at a time"}
 
 
+def measure_e2e_dist(w, args, world):
+    """The end-to-end leg of a multi-GPU run: every rank uploads the level set and the source term of ITS slab from
+    pinned host memory, runs the sharded classification (with its exchange) and the assembly of its owned rows, and
+    downloads its tags, owned CSR values and owned load-vector entries -- each GPU over its own PCIe link.  Time = the
+    maximum over the ranks of the wall clock around K synchronised steps; value = all owned cells / that time."""
+    import torch
+    import torch.distributed as dist
+    prob, mesh, dev = w.problem, w.mesh, w.mesh.device
+    phi_h = prob.phi.cpu().pin_memory()
+    f_h = prob.f.cpu().pin_memory()
+    data0, b0 = prob.assemble(1.0)
+    out_h = {"ct": torch.empty(mesh.num_cells, dtype=torch.int8).pin_memory(),
+             "ft": torch.empty(mesh.num_facets, dtype=torch.int8).pin_memory(),
+             "data": torch.empty(data0.numel(), dtype=torch.float64).pin_memory(),
+             "b": torch.empty(b0.numel(), dtype=torch.float64).pin_memory()}
+    side = torch.cuda.Stream()
+    tags_done, f_done, phi_up = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+
+    def e2e_step():
+        prob.phi.copy_(phi_h, non_blocking=True)      # (the classifier and the plan read these device arrays in place)
+        phi_up.record()
+        with torch.cuda.stream(side):
+            side.wait_event(phi_up)
+            prob.f.copy_(f_h, non_blocking=True)
+            f_done.record()
+        prob.classify(w.dls, w.ws)
+        tags_done.record()
+        with torch.cuda.stream(side):
+            side.wait_event(tags_done)
+            out_h["ct"].copy_(w.ws.cell_tags8, non_blocking=True)
+            out_h["ft"].copy_(w.ws.facet_tags8, non_blocking=True)
+        torch.cuda.current_stream().wait_event(f_done)
+        data, b = prob.assemble(1.0)
+        out_h["data"].copy_(data, non_blocking=True)
+        out_h["b"].copy_(b, non_blocking=True)
+        torch.cuda.synchronize()
+
+    steps = max(2, min(args.steps, 5))
+    for _ in range(2):
+        e2e_step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_step()
+    dt = torch.tensor([(time.perf_counter() - t0) / steps], dtype=torch.float64, device=dev)
+    cells = torch.tensor([prob.n_owned_cells], dtype=torch.int64, device=dev)
+    h2d = torch.tensor([phi_h.numel() * 8 + f_h.numel() * 8], dtype=torch.int64, device=dev)
+    d2h = torch.tensor([sum(t.numel() * t.element_size() for t in out_h.values())], dtype=torch.int64, device=dev)
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    for t in (cells, h2d, d2h):
+        dist.all_reduce(t)
+    return {"value": int(cells.item()) / float(dt.item()), "unit": UNIT, "ms_per_step": float(dt.item()) * 1e3,
+            "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(d2h.item()),
+            "api": "per rank: pinned host level set / source of its slab in, SlabProblem.classify (sharded tags with "
+                   "their exchange) + SlabProblem.assemble (owned rows), pinned host tags (1 byte per local cell / "
+                   "facet) + owned CSR values + owned b out; every GPU over its own PCIe link; max over the %d ranks, "
+                   "bytes summed over the ranks; one step at a time" % world}
+
+
 def time_to_solution(w):
     """tags + assembly + the solve that follows them in the demos (reference
     demo/strong-dirichlet/flower/main.py:138-157 hands the system to MUMPS), here Jacobi-BiCGStab on the CSR operator
@@ -840,7 +900,9 @@ def run_ours(args):
         roofline["traffic_source"] = tr.get("source", "profiles/traffic.json (ncu --set full capture of this command)")
     launches, launch_names = w.kernel_launches_per_step()
 
-    e2e = measure_e2e(w, args, degree) if (world == 1 and not args.no_e2e) else None
+    e2e = None
+    if not args.no_e2e:
+        e2e = measure_e2e(w, args, degree) if world == 1 else measure_e2e_dist(w, args, world)
     tts = None
     if world == 1 and degree == 1 and not args.no_solve and plan.method == "rows":
         try:
