@@ -9,8 +9,12 @@ demo/strong-dirichlet/flower/main.py:
           + sigma int_{dS(2,3)} avg(h_T) jump(grad(phi w),n) jump(grad(phi v),n)   (:113-118)
   L(v)   =  int_{dx(1,2)} f phi v - sigma h_T^2 int_{dx(2)} f div grad(phi v)      (:126-128)
 
-PARITY UNPINNED: the reference holds no golden matrix/vector and dolfinx/FFCx/PETSc are not
-installable here.  Two independent restatements live in this file and must agree to ~1e-14:
+PARITY PARTIALLY PINNED: the reference holds no golden matrix/vector and dolfinx/FFCx/PETSc are not
+installable here, so no dolfinx-produced number backs this file.  What does: the element tensors of every operator
+below (strong / weak Dirichlet, Neumann / Robin) -- both restatements -- are held to exact sympy integrals of the
+literal integrands (tests/test_oracle_sympy.py); the dolfinx conventions of the global assembly ('+' side of dS, the
+cell owning ds(100), the pattern) stay unpinned until baseline/dolfinx_reference.py has been run.
+Two independent restatements live in this file and must agree to ~1e-14:
   * `*_closed_form`  -- exact element tensors for P1 phi, P1 w/v, P1 f (SURVEY.md Appendix B);
   * `*_quadrature`   -- brute-force Gauss-Jacobi quadrature (exact to degree 11) for P1 or P2.
 Matrix convention: row = test dof (v), column = trial dof (w), like PETSc's assembled A.

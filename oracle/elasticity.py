@@ -26,9 +26,12 @@ Mixed numbering (ours; an input convention of the kernels): NB = 3 d + 2 d^2 dof
 o: u_in c -> c, u_out c -> d + c, y_in (r, s) -> 2 d + r d + s, y_out (r, s) -> 2 d + d^2 + r d + s, p c -> 2 d + 2 d^2 + c.
 Cell-local order: node-major (local vertex k, offset o) -> k NB + o.
 
-PARITY UNPINNED (no golden matrix in the reference, dolfinx not installable here): two independent restatements,
-`*_quadrature` (the UFL expressions evaluated field by field at brute-force quadrature points) and `*_closed_form`
-(entry formulas from the exact integrals of barycentric monomials, P1 level set), must agree to ~1e-14.
+PARITY PARTIALLY PINNED (no golden matrix in the reference, dolfinx not installable here): two independent
+restatements, `*_quadrature` (the UFL expressions evaluated field by field at brute-force quadrature points) and
+`*_closed_form` (entry formulas from the exact integrals of barycentric monomials, P1 level set), must agree to ~1e-14,
+and BOTH are held to exact sympy integrals of the literal integrands (tests/test_oracle_sympy.py: cell tensors, load
+vectors, one-sided and stress-jump facet tensors).  The dolfinx conventions of the global assembly (pattern, '+' side,
+lifting) stay unpinned until baseline/dolfinx_reference.py has been run.
 """
 import math
 

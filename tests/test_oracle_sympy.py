@@ -5,6 +5,10 @@ derivations FROM THE INTEGRANDS of the reference's forms (tests/sympy_forms.py):
   demo/strong-dirichlet/flower/main.py:104-128   cells (stiffness + stabilisation), one-sided boundary term, ghost penalty,
                                                  load vector (+ stabilisation)
   demo/weak-dirichlet/flower/main.py:112-151     the mixed (u, p) operator and right-hand side
+  demo/neumann/square/main.py:113-158            the mixed (u, y, p) operator, P1 level set; demo/robin/square/main.py:121-172
+                                                 with the robin_coef terms (oracle/assembly.py neumann_*)
+  demo/interface-elasticity/main.py:183-269      the 5-field operator: cut / uncut cell tensors, load vectors, (y n).v on
+                                                 ds(100) / ds(101), stress-jump penalties on dS(3) / dS(4) (oracle/elasticity.py)
 
 on random rational simplices (d = 2, 3), random rational coefficients, random cell-local vertex orders, both sides of a
 shared facet.  Tolerance: 1e-13 of the tensor's largest entry (the oracle is fp64, the derivation exact).
@@ -208,3 +212,108 @@ def test_strong_dirichlet_p2_tensors_from_the_integrands():
     Eq = OA.ghost_tensors_quadrature(x, cells, ph, np.array([phi_m], dtype=float), c2f, f2c, [fct], float(sigma),
                                      kphi=2, kw=2)
     _close(Eq[0], SF.to_float(E), "P2 ghost-penalty macro matrix")
+
+
+@pytest.mark.parametrize("d", [2, 3])
+@pytest.mark.parametrize("cut,kappa", [(False, 0), (True, 0), (True, sp.Rational(3, 4))])
+def test_neumann_robin_cell_tensors_from_the_integrands(d, cut, kappa):
+    """Mixed P1 x P1^d x DG0 operator of demo/neumann (kappa = 0) and demo/robin (kappa = robin_coef), P1 level set:
+    both oracle forms against the exact integrals of the literal integrands."""
+    rng = random.Random(1300 + 10 * d + cut + int(4 * kappa))
+    verts = _simplex(rng, d)
+    phi, f, un = ([_rat(rng) for _ in range(d + 1)] for _ in range(3))
+    gamma = sp.Rational(rng.randint(1, 9), 2)
+    A, b = SF.neumann_cell(verts, phi, f, un, cut, gamma, kappa)
+    A, b = SF.to_float(A), SF.to_float(b)[:, 0]
+    x = np.array(verts, dtype=float)
+    cells = np.arange(d + 1)[None, :]
+    ph, fv, uv = (np.array(v, dtype=float) for v in (phi, f, un))
+    Ac, bc = OA.neumann_cell_tensors_closed_form(x, cells, ph, fv, uv, np.array([cut]), float(gamma), float(kappa))
+    Aq, bq = OA.neumann_cell_tensors_quadrature(x, cells, ph[cells], fv[cells], uv[cells], np.array([cut]),
+                                                float(gamma), kappa=float(kappa))
+    _close(Ac[0], A, "closed-form Neumann / Robin cell matrix")
+    _close(Aq[0], A, "quadrature Neumann / Robin cell matrix")
+    _close(bc[0], b, "closed-form Neumann / Robin cell vector")
+    _close(bq[0], b, "quadrature Neumann / Robin cell vector")
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_neumann_facet_tensors_from_the_integrands(d):
+    rng = random.Random(1700 + d)
+    pts, plus, minus = _pair(rng, d)
+    x, cells, c2f, f2c, fct, op, om = _mesh_of_pair(pts, plus, minus, d)
+    vp, vm = [pts[k] for k in plus], [pts[k] for k in minus]
+    sigma = sp.Rational(rng.randint(1, 9), 4)
+    for o in range(d + 1):
+        B = SF.to_float(SF.neumann_boundary(vp, o))
+        _close(OA.neumann_boundary_tensors(x, cells, np.array([[0, o]]))[0], B, "Neumann one-sided matrix (y.n) v")
+    E = SF.to_float(SF.neumann_ghost(vp, vm, op, om, sigma))
+    _close(OA.neumann_ghost_tensors(x, cells, c2f, f2c, [fct], float(sigma))[0], E, "Neumann ghost penalty")
+
+
+@pytest.mark.parametrize("d,tag", [(2, 2), (2, 1), (2, 3), (3, 2)])
+def test_interface_elasticity_cell_tensors_from_the_integrands(d, tag):
+    """5-field operator of demo/interface-elasticity (BASELINE configs[3]), P1 level set: entries of both oracle forms
+    against the exact integrals of the literal integrands -- every entry in 2D for a cut cell, a random sample of 260
+    entries (and the whole load vector) otherwise."""
+    from oracle import elasticity as OE
+    rng = random.Random(2100 + 10 * d + tag)
+    verts = _simplex(rng, d)
+    nv = d + 1
+    nb = OE.Offsets(d).nb
+    nm = nv * nb
+    phi = [_rat(rng) for _ in range(nv)]
+    fd = [[_rat(rng) for _ in range(d)] for _ in range(nv)]
+    Ei, Eo = sp.Rational(rng.randint(2, 9), 2), sp.Rational(rng.randint(1, 5), 7)
+    nui, nuo = sp.Rational(3, 10), sp.Rational(1, 4)
+    lame = lambda E, nu: (E * nu / (1 + nu) / (1 - 2 * nu), E / 2 / (1 + nu))      # noqa: E731  data.py:5-10
+    (li, mi), (lo, mo) = lame(Ei, nui), lame(Eo, nuo)
+    ci, co = (Ei / (Ei + Eo)) ** 2, (Eo / (Ei + Eo)) ** 2
+    gamma, sigma_s = sp.Rational(rng.randint(1, 9), 2), sp.Rational(rng.randint(1, 9), 4)
+    if d == 2 and tag == 2:
+        pairs = [(i, j) for i in range(nm) for j in range(i, nm)]
+    else:
+        pairs = [(rng.randrange(nm), rng.randrange(nm)) for _ in range(260)]
+    ent, b = SF.elasticity_cell_entries(verts, phi, fd, tag, li, mi, lo, mo, ci, co, gamma, sigma_s, pairs)
+    mat = OE.Material(float(Ei), float(nui), float(Eo), float(nuo))
+    x = np.array(verts, dtype=float)
+    cells = np.arange(nv)[None, :]
+    ph = np.array(phi, dtype=float)
+    fv = np.array(fd, dtype=float)
+    Ac, bc = OE.cell_tensors_closed_form(x, cells, ph, fv, np.array([tag]), mat, float(gamma), float(sigma_s))
+    Aq, bq = OE.cell_tensors_quadrature(x, cells, ph[cells], fv[cells], np.array([tag]), mat, float(gamma),
+                                        float(sigma_s))
+    want = np.array([float(sp.N(ent[pq], 30)) for pq in pairs])
+    scale = max(np.abs(want).max(), 1e-300)
+    for A, what in ((Ac[0], "closed form"), (Aq[0], "quadrature")):
+        got = np.array([A[i, j] for (i, j) in pairs])
+        assert np.abs(got - want).max() <= 1e-11 * scale, what
+        assert np.abs(A - A.T).max() <= 1e-12 * scale, what + " (symmetry)"
+    bw = np.array([float(sp.N(v, 30)) for v in b])
+    for bb, what in ((bc[0], "closed form"), (bq[0], "quadrature")):
+        assert np.abs(bb - bw).max() <= 1e-11 * max(np.abs(bw).max(), 1e-300), what + " load vector"
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_interface_elasticity_facet_tensors_from_the_integrands(d):
+    from oracle import elasticity as OE
+    rng = random.Random(2500 + d)
+    pts, plus, minus = _pair(rng, d)
+    x, cells, c2f, f2c, fct, op, om = _mesh_of_pair(pts, plus, minus, d)
+    vp, vm = [pts[k] for k in plus], [pts[k] for k in minus]
+    Ei, Eo, nui, nuo = sp.Rational(7, 2), sp.Rational(3, 7), sp.Rational(3, 10), sp.Rational(1, 4)
+    lame = lambda E, nu: (E * nu / (1 + nu) / (1 - 2 * nu), E / 2 / (1 + nu))      # noqa: E731
+    mat = OE.Material(float(Ei), float(nui), float(Eo), float(nuo))
+    sigma_s = sp.Rational(rng.randint(1, 9), 4)
+    for side, (E_, nu_) in (("in", (Ei, nui)), ("out", (Eo, nuo))):
+        o = rng.randrange(d + 1)
+        B = SF.to_float(SF.elasticity_boundary(vp, o, side))
+        ents = np.array([[0, o]])
+        _close(OE.boundary_tensors_closed_form(x, cells, ents, side)[0], B, "closed-form (y n).v, side " + side)
+        _close(OE.boundary_tensors_quadrature(x, cells, ents, side)[0], B, "quadrature (y n).v, side " + side)
+        lm, mu = lame(E_, nu_)
+        E = SF.to_float(SF.elasticity_facet(vp, vm, op, om, side, lm, mu, sigma_s))
+        _close(OE.facet_tensors_closed_form(x, cells, c2f, f2c, [fct], side, mat, float(sigma_s))[0], E,
+               "closed-form stress-jump penalty, side " + side)
+        _close(OE.facet_tensors_quadrature(x, cells, c2f, f2c, [fct], side, mat, float(sigma_s))[0], E,
+               "quadrature stress-jump penalty, side " + side)
