@@ -21,12 +21,14 @@
 namespace phifem {
 namespace {
 
+// 64 threads x 8 CTAs per SM (the same 16 warps and 128 registers as 128 x 4): cell pass 1.200 -> 1.174 ms at config E
+// (profiles/round2_i_rows_variants.md, tools/r3_run_h.sh) -- half the accumulator slab per CTA, finer-grained tail
 #ifndef PHIFEM_ROWS_BLOCK
-#define PHIFEM_ROWS_BLOCK 128
+#define PHIFEM_ROWS_BLOCK 64
 #endif
 constexpr int kRowsBlock = PHIFEM_ROWS_BLOCK;
 #ifndef PHIFEM_ROWS_MINBLOCKS
-#define PHIFEM_ROWS_MINBLOCKS 4
+#define PHIFEM_ROWS_MINBLOCKS (512 / PHIFEM_ROWS_BLOCK)
 #endif
 #ifndef PHIFEM_SURF_MINBLOCKS
 #define PHIFEM_SURF_MINBLOCKS PHIFEM_ROWS_MINBLOCKS
