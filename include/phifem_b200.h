@@ -317,6 +317,12 @@ typedef struct phifem_rows_plan {
   /* Optional cell-once form of the cell pass (NULL: the row list `cells` above is walked).  When set, `cells` may be
    * empty; the rows of tiles->rows are written (data and b) exactly as the row-gather cell pass writes its rows. */
   const phifem_cell_tiles* tiles;
+  /* Optional [n_ghost_facets + n_entities, 8], filled once per plan by phifem_surface_static_p1: the part of the
+   * facet-once records that depends on the mesh alone -- per ghost facet s0 c_0 .. s0 c_{d+1} (jump coefficients of the
+   * macro vertices, s0 = sqrt(avg(h) |F| / (d (d+1))), sigma left out), per one-sided entity cF grad(lambda_j).n for the
+   * d + 1 vertices of entity_macro.  The per-step records are then LINEAR in the level set with these coefficients and a
+   * light kernel builds them (no coordinate gathers); NULL: they are evaluated from the coordinates at every call. */
+  double* surface_static;
 } phifem_rows_plan;
 
 /* Same operator as phifem_assemble_{cells,boundary,ghost}_p1: the facet-once kernel (forked onto an internal side
@@ -528,6 +534,9 @@ typedef struct phifem_rows_plan_info {
   int64_t cells_record_slots;       /* words of plan.cells.rec (pads included) */
   int64_t surface_record_slots;     /* uint2 slots of plan.surface.rec (pads included) */
 } phifem_rows_plan_info;
+
+/* Once per plan (after its ghost_macro / entity_macro lists exist): fills plan->surface_static. */
+int phifem_surface_static_p1(const phifem_mesh* mesh, const phifem_rows_plan* plan, void* stream);
 
 int phifem_rows_plan_create(const phifem_mesh* mesh, const int8_t* cell_tags8, const int8_t* facet_tags8,
                             const int32_t* entities, int64_t n_entities, const uint8_t* row_mask, int32_t morton_cells,

@@ -61,7 +61,7 @@ class CRowsPlan(ctypes.Structure):
                 ("reserved", ctypes.c_int32), ("cells", CRowList), ("surface", CRowList),
                 ("n_ghost_facets", ctypes.c_int64), ("ghost_macro", _vp), ("n_entities", ctypes.c_int64),
                 ("entity_macro", _vp), ("surface_work", _vp), ("cell_geom", _vp),
-                ("tiles", ctypes.POINTER(CCellTiles))]
+                ("tiles", ctypes.POINTER(CCellTiles)), ("surface_static", _vp)]
 
 
 class CRowsPlanInfo(ctypes.Structure):
@@ -159,6 +159,7 @@ _SIGNATURES = {
     "phifem_integration_entities_fill": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, ctypes.c_int32,
                                                         ctypes.c_uint32, _vp, ctypes.c_int64, _vp]),
     "phifem_pattern_destroy": (None, [_vp]),
+    "phifem_surface_static_p1": (ctypes.c_int, [ctypes.POINTER(CMesh), ctypes.POINTER(CRowsPlan), _vp]),
     "phifem_rows_plan_create": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, _vp, _vp, ctypes.c_int64, _vp,
                                                ctypes.c_int32, ctypes.POINTER(_vp), _vp]),
     "phifem_rows_plan_view": (ctypes.c_int, [_vp, ctypes.POINTER(CRowsPlan), ctypes.POINTER(CRowsPlanInfo)]),

@@ -15,6 +15,8 @@
 // list of the entity's other vertices, so `indices[start + pos]` names them (include/phifem_b200.h).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "p1_forms.cuh"
 
@@ -335,6 +337,118 @@ __global__ void __launch_bounds__(kRowsBlock, PHIFEM_ONCE_MINBLOCKS) k_surface_o
 #pragma unroll
   for (int m = 0; m <= D; ++m) w[m] = sc * c[m];
   w[D + 1] = sc * gsum;
+#pragma unroll
+  for (int k = 0; k < D; ++k) w[D + 2 + k] = pm[k];
+  if (D == 2) w[6] = w[7] = 0.0;
+}
+
+// ---- the facet-once records from a per-plan STATIC table ---------------------------------------------------------------
+// Everything k_surface_once_p1 computes from the coordinates is a property of the mesh and the tags: the jump
+// coefficients c_m of a ghost facet and the scale sqrt(avg(h) |F| / (D (D+1))), the normal derivatives cF grad(lambda_j).n
+// of a one-sided entity.  What depends on the level set is LINEAR in it with exactly these coefficients:
+//   s gsum = sum_m phi_m (s c_m)  (grad(phi).n on a side = sum_a phi_a grad(lambda_a).n),   cF grad(phi).n = sum_j phi_j (cF Gn_j).
+// k_surface_static_p1 tabulates the coefficients once per plan (8 doubles per facet / entity, sigma left out);
+// k_surface_fill_p1 then builds the work record of a step from one 64-byte read, the vertex list and D + 2 gathers of phi
+// -- no coordinate gathers, no cofactors, no square roots: 83 -> ~15 us for the 1.7 M records of config E.
+template <int D>
+__global__ void __launch_bounds__(kRowsBlock) k_surface_static_p1(
+    const double* __restrict__ x, const int32_t* __restrict__ macro, int64_t n_facets,
+    const int32_t* __restrict__ entity_macro, int64_t n_entities, double* __restrict__ table) {
+  constexpr int NV = D + 1, NG = D + 2, W = kGhostWork<D>;
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_facets + n_entities) return;
+  double* t = table + g * W;
+  if (g >= n_facets) {  // one-sided entity: cF grad(lambda_j).n, j = 0..D (entity_record with phi = 0 writes them)
+    const int64_t e = g - n_facets;
+    double X[NV][D], p[NV], w[W];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int v = __ldg(entity_macro + e * NV + k);
+#pragma unroll
+      for (int d = 0; d < D; ++d) X[k][d] = __ldg(x + (int64_t)v * D + d);
+      p[k] = 0.0;
+    }
+    entity_record<D>(X, p, w);
+#pragma unroll
+    for (int j = 0; j < W; ++j) t[j] = j < NV ? w[1 + j] : 0.0;
+    return;
+  }
+  double M[NG][D];
+#pragma unroll
+  for (int m = 0; m < NG; ++m) {
+    const int v = __ldg(macro + g * NG + m);
+#pragma unroll
+    for (int d = 0; d < D; ++d) M[m][d] = __ldg(x + (int64_t)v * D + d);
+  }
+  double c[NG], N[D], nn = 0.0, rn = 0.0, hsum = 0.0;
+#pragma unroll
+  for (int m = 0; m < NG; ++m) c[m] = 0.0;
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    double X[NV][D];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int m = k < D ? k : D + side;
+#pragma unroll
+      for (int d = 0; d < D; ++d) X[k][d] = M[m][d];
+    }
+    double R[NV][D], det;
+    simplex_cofactors<D>(X, R, det);
+    if (side == 0) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) N[d] = R[D][d];
+      nn = dot<D>(N, N);
+      rn = rsqrt(nn);
+    }
+    const double scale = -rn / fabs(det);
+#pragma unroll
+    for (int a = 0; a < NV; ++a) c[a < D ? a : D + side] += dot<D>(R[a], N) * scale;
+    hsum += sqrt(diameter2<D>(X));
+  }
+  const double area = nn * rn * (D == 2 ? 1.0 : 0.5);  // |N| / (D-1)!
+  const double s0 = sqrt(0.5 * hsum * area * (1.0 / (D * (D + 1))));
+#pragma unroll
+  for (int j = 0; j < W; ++j) t[j] = j < NG ? s0 * c[j] : 0.0;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kRowsBlock) k_surface_fill_p1(
+    const double* __restrict__ phi, double sigma, const int32_t* __restrict__ macro, int64_t n_facets,
+    const int32_t* __restrict__ entity_macro, int64_t n_entities, const double* __restrict__ table,
+    double* __restrict__ work) {
+  constexpr int NV = D + 1, NG = D + 2, W = kGhostWork<D>;
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_facets + n_entities) return;
+  double t[W];
+  ldg256(table + g * W, t[0], t[1], t[2], t[3]);
+  ldg256(table + g * W + 4, t[4], t[5], t[6], t[7]);
+  double* w = work + g * W;
+  if (g >= n_facets) {
+    const int64_t e = g - n_facets;
+    double p[NV], gn = 0.0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      p[k] = __ldg(phi + __ldg(entity_macro + e * NV + k));
+      gn += p[k] * t[k];
+    }
+    w[0] = gn;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) w[1 + j] = t[j];
+#pragma unroll
+    for (int k = 0; k < D; ++k) w[2 + D + k] = p[k];
+    if (D == 2) w[6] = w[7] = 0.0;
+    return;
+  }
+  const double sq = sqrt(fabs(sigma));
+  double pm[NG], gs = 0.0;
+#pragma unroll
+  for (int m = 0; m < NG; ++m) {
+    pm[m] = __ldg(phi + __ldg(macro + g * NG + m));
+    gs += pm[m] * t[m];
+  }
+#pragma unroll
+  for (int m = 0; m <= D; ++m) w[m] = sq * t[m];
+  w[D + 1] = sq * gs;
 #pragma unroll
   for (int k = 0; k < D; ++k) w[D + 2 + k] = pm[k];
   if (D == 2) w[6] = w[7] = 0.0;
@@ -730,26 +844,33 @@ extern "C" int phifem_assemble_rows_p1(const phifem_mesh* mesh, const double* ph
   SideStream& ss = side_stream();
   const bool fork = n_once > 0 && (plan->cells.n_listed > 0 || tiles) && ss.ok;
   cudaStream_t once_stream = fork ? ss.stream : st;
-  auto once = [&](auto kernel) {
+  auto once = [&](auto dim) {
+    constexpr int D = decltype(dim)::value;
     if (n_once == 0) return;
     if (fork) {
       cudaEventRecord(ss.fork, st);
       cudaStreamWaitEvent(ss.stream, ss.fork, 0);
     }
-    kernel<<<(unsigned)((n_once + kRowsBlock - 1) / kRowsBlock), kRowsBlock, 0, once_stream>>>(
-        mesh->x, phi, sigma, plan->ghost_macro, plan->n_ghost_facets, plan->entity_macro, plan->n_entities,
-        plan->surface_work);
+    const unsigned grid = (unsigned)((n_once + kRowsBlock - 1) / kRowsBlock);
+    if (plan->surface_static)  // coefficients tabulated once per plan (phifem_surface_static_p1): the light kernel
+      k_surface_fill_p1<D><<<grid, kRowsBlock, 0, once_stream>>>(phi, sigma, plan->ghost_macro, plan->n_ghost_facets,
+                                                                 plan->entity_macro, plan->n_entities,
+                                                                 plan->surface_static, plan->surface_work);
+    else
+      k_surface_once_p1<D><<<grid, kRowsBlock, 0, once_stream>>>(mesh->x, phi, sigma, plan->ghost_macro,
+                                                                 plan->n_ghost_facets, plan->entity_macro,
+                                                                 plan->n_entities, plan->surface_work);
     if (fork) cudaEventRecord(ss.join, ss.stream);
   };
   if (mesh->cell_type == PHIFEM_TRIANGLE) {
-    once(k_surface_once_p1<2>);
+    once(std::integral_constant<int, 2>());
     if (tiles) cell_tiles();
     else if (geom) launch(k_assemble_rows_p1<2, kCellsGeom>, plan->cells, plan->cell_geom);
     else launch(k_assemble_rows_p1<2, kCells>, plan->cells, nullptr);
     if (fork) cudaStreamWaitEvent(st, ss.join, 0);
     launch(k_assemble_rows_p1<2, kSurface>, plan->surface, plan->surface_work);
   } else {
-    once(k_surface_once_p1<3>);
+    once(std::integral_constant<int, 3>());
     if (tiles) cell_tiles();
     else if (geom) launch(k_assemble_rows_p1<3, kCellsGeom>, plan->cells, plan->cell_geom);
     else if (use_x4) launch(k_assemble_rows_p1<3, kCellsX4>, plan->cells, nullptr, mesh->x4);
@@ -762,6 +883,29 @@ extern "C" int phifem_assemble_rows_p1(const phifem_mesh* mesh, const double* ph
               tiles ? ", cell tiles" : "", cudaGetErrorString(err));
     return PHIFEM_ERR_CUDA;
   }
+  PHIFEM_CHECK_LAUNCH();
+  return PHIFEM_OK;
+}
+
+extern "C" int phifem_surface_static_p1(const phifem_mesh* mesh, const phifem_rows_plan* plan, void* stream) {
+  PHIFEM_CHECK_ARG(mesh != nullptr && mesh->x && plan != nullptr, "mesh / plan is null");
+  if (mesh->cell_type != PHIFEM_TRIANGLE && mesh->cell_type != PHIFEM_TETRAHEDRON) {
+    set_error("P1 assembly supports triangles and tetrahedra, got cell type %d", mesh->cell_type);
+    return PHIFEM_ERR_UNSUPPORTED;
+  }
+  const int64_t n_once = plan->n_ghost_facets + plan->n_entities;
+  if (n_once == 0) return PHIFEM_OK;
+  PHIFEM_CHECK_ARG(plan->surface_static != nullptr, "plan.surface_static is null");
+  PHIFEM_CHECK_ARG((plan->n_ghost_facets == 0 || plan->ghost_macro) && (plan->n_entities == 0 || plan->entity_macro),
+                   "ghost_macro / entity_macro");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((n_once + kRowsBlock - 1) / kRowsBlock);
+  if (mesh->cell_type == PHIFEM_TRIANGLE)
+    k_surface_static_p1<2><<<grid, kRowsBlock, 0, st>>>(mesh->x, plan->ghost_macro, plan->n_ghost_facets,
+                                                        plan->entity_macro, plan->n_entities, plan->surface_static);
+  else
+    k_surface_static_p1<3><<<grid, kRowsBlock, 0, st>>>(mesh->x, plan->ghost_macro, plan->n_ghost_facets,
+                                                        plan->entity_macro, plan->n_entities, plan->surface_static);
   PHIFEM_CHECK_LAUNCH();
   return PHIFEM_OK;
 }

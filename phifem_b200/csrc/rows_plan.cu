@@ -554,7 +554,8 @@ extern "C" int phifem_rows_plan_create(const phifem_mesh* mesh, const int8_t* ce
   int32_t* macro = (int32_t*)own(sizeof(int32_t) * ng * nm);
   int32_t* emacro = (int32_t*)own(sizeof(int32_t) * ne * nv);
   double* work = (double*)own(sizeof(double) * 8 * (ng + ne > 0 ? ng + ne : 1));
-  if (!active || !ghost || !macro || !emacro || !work) return fail("output allocation");
+  double* work_static = (double*)own(sizeof(double) * 8 * (ng + ne > 0 ? ng + ne : 1));
+  if (!active || !ghost || !macro || !emacro || !work || !work_static) return fail("output allocation");
   cudaMemcpyAsync(active, active_full, sizeof(int32_t) * na, cudaMemcpyDeviceToDevice, st);
   cudaMemcpyAsync(ghost, ghost_full, sizeof(int32_t) * ng, cudaMemcpyDeviceToDevice, st);
   if (ng) k_macro<<<nblk(ng), kB, 0, st>>>(*mesh, nv, ghost, ng, macro);
@@ -808,6 +809,11 @@ extern "C" int phifem_rows_plan_create(const phifem_mesh* mesh, const int8_t* ce
   p.surface_work = work;
   p.cell_geom = nullptr;
   p.tiles = nullptr;
+  p.surface_static = work_static;
+  if (int rc = phifem_surface_static_p1(mesh, &p, stream)) {  // mesh-only part of the facet-once records, once per plan
+    phifem_rows_plan_destroy(h);
+    return rc;
+  }
   phifem_rows_plan_info& info = h->info;
   info.n_rows = n_rows;
   info.nnz = nnz;

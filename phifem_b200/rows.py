@@ -295,7 +295,13 @@ class RowsPlan:
         # facet-once scratch of the surface pass (8 doubles = 64 bytes per ghost facet / entity), rewritten by
         # every assembly
         self.surface_work = torch.empty((max(ng + ne, 1), 8), dtype=torch.float64, device=dev)
+        # mesh-only part of those records (csrc/assemble_rows.cu k_surface_static_p1), tabulated once below
+        self.surface_static = torch.zeros((max(ng + ne, 1), 8), dtype=torch.float64, device=dev) if dev.type == "cuda" \
+            else None
         self._c = None
+        if self.surface_static is not None and ng + ne > 0:
+            _lib.check(_lib.load().phifem_surface_static_p1(_lib.c_mesh(mesh), ctypes.byref(self.c_struct()),
+                                                            _lib.stream()))
 
     def c_struct(self, passes=None):
         """`passes`: subset of ("cells", "surface") to run (bench.py times them one by one); the other list is
@@ -317,17 +323,19 @@ class RowsPlan:
         """Trailing fields of phifem_rows_plan: ghost facet / entity vertex lists, the facet-once scratch, the cached
         cell geometry."""
         if self.surface_work.device.type != "cuda":
-            return 0, None, 0, None, None, None, None
+            return 0, None, 0, None, None, None, None, None
         return (self.n_ghost_facets, _lib.ptr(self.ghost_macro) if self.n_ghost_facets else None,
                 self.n_entities, _lib.ptr(self.entity_macro) if self.n_entities else None,
                 _lib.ptr(self.surface_work), _lib.ptr(self.cell_geom),
-                ctypes.pointer(self.tiles.c_struct()) if self.tiles is not None and cells else None)
+                ctypes.pointer(self.tiles.c_struct()) if self.tiles is not None and cells else None,
+                _lib.ptr(self.surface_static))
 
     def index_bytes(self):
         """Bytes of plan arrays one numeric pass streams besides the CSR pattern itself."""
         return (self.cells.nbytes() + (self.tiles.nbytes() if self.tiles is not None else 0)
                 + self.surface.nbytes() + self.ghost_macro.numel() * 4
                 + self.entity_macro.numel() * 4 + self.surface_work.numel() * 8
+                + (self.surface_static.numel() * 8 if self.surface_static is not None else 0)
                 + (self.cell_geom.numel() * 8 if self.cell_geom is not None else 0))
 
 
@@ -406,6 +414,8 @@ class NativeRowsPlan:
         self.entity_macro = dv(self._c.entity_macro, (self.n_entities, nv), torch.int32, dev)
         self.surface_work = dv(self._c.surface_work, (max(self.n_ghost_facets + self.n_entities, 1), 8), torch.float64,
                                dev)
+        self.surface_static = dv(self._c.surface_static, (max(self.n_ghost_facets + self.n_entities, 1), 8),
+                                 torch.float64, dev)
         n_cell_rec = int(info.n_cell_records)
         if mask is not None:     # records of the listed rows only
             cnt = (self.indptr[1:] > self.indptr[:-1]) & mask.bool()
@@ -432,7 +442,7 @@ class NativeRowsPlan:
 
     def index_bytes(self):
         return (self.cells.nbytes() + self.surface.nbytes() + self.ghost_macro.numel() * 4
-                + self.entity_macro.numel() * 4 + self.surface_work.numel() * 8)
+                + self.entity_macro.numel() * 4 + self.surface_work.numel() * 8 + self.surface_static.numel() * 8)
 
 
 def assemble_rows_into(rplan, phi, f, sigma, data, b, passes=None):
