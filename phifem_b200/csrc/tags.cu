@@ -1299,10 +1299,19 @@ extern "C" int phifem_tag_facets_phase(const phifem_mesh* mesh, const phifem_lev
   PHIFEM_CHECK_ARG(both || two_pass, "phases need mesh.boundary_facets");
   // interior facets of a mesh that lists its boundary facets: f2c staged by TMA (needs a 16-byte aligned f2c; the
   // per-thread vector-load kernel otherwise, or with PHIFEM_FACETS_KERNEL=ldg for A/B runs)
-  auto launch_interior = [&](auto c) {
+  auto launch_interior = [&](auto c, bool beside_boundary = false) {
     constexpr int CT = decltype(c)::value;
     if (facet_kernel_staged() && (reinterpret_cast<uintptr_t>(mesh->f2c) & 15) == 0) {
-      const int grid = persistent_grid(k_tag_facets_staged<CT>, kBlock, tiles);
+      int grid = persistent_grid(k_tag_facets_staged<CT>, kBlock, tiles);
+      // Beside the forked mesh-boundary kernel the persistent grid gives up one CTA per SM (5 of 6): the streaming
+      // kernel alone is 7 % slower that way (0.161 against 0.150 ms at config E) but the latency-bound boundary kernel
+      // then runs entirely under it: both phases 0.168 against 0.178 ms (tools/r3_run_x.sh; 4 per SM: 0.187).
+      int per_sm = grid / kNumSMs;
+      if (beside_boundary && per_sm >= 4 && grid % kNumSMs == 0) grid -= kNumSMs;
+      if (const char* e = getenv("PHIFEM_FACETS_CTAS_PER_SM")) {  // tuning runs
+        const int64_t cap = (int64_t)kNumSMs * atoi(e);
+        if (cap > 0) grid = (int)(cap < tiles ? cap : tiles);
+      }
       k_tag_facets_staged<CT><<<grid, kBlock, 0, st>>>(*mesh, cell_tags8, facet_tags, facet_tags8, counters);
     } else {
       const int grid = persistent_grid(k_tag_facets<CT, false>, kBlock, tiles);
@@ -1337,7 +1346,7 @@ extern "C" int phifem_tag_facets_phase(const phifem_mesh* mesh, const phifem_lev
         launch_boundary(c, ss.stream);
         cudaEventRecord(ss.join, ss.stream);
       }
-      launch_interior(c);
+      launch_interior(c, fork);
       if (fork) {
         cudaStreamWaitEvent(st, ss.join, 0);
       } else if (mesh->n_boundary_facets > 0) {
