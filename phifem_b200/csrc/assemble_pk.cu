@@ -17,6 +17,9 @@ namespace phifem {
 using namespace pk;
 namespace {
 
+#ifndef PHIFEM_PK_UNROLL_Q
+#define PHIFEM_PK_UNROLL_Q 1
+#endif
 #ifndef PHIFEM_PK_SINGLE_STORES
 #define PHIFEM_PK_SINGLE_STORES 1
 #endif
@@ -65,6 +68,9 @@ __device__ __forceinline__ void cell_rows(const Geometry<D>& g, const double (&p
     for (int k = 0; k < NDP; ++k) lph += pc[k] * pl[k];
   }
   const double sh2 = is_cut ? sigma * g.h2 : 0.0;
+#if PHIFEM_PK_UNROLL_Q == 2
+#pragma unroll 2
+#endif
   for (int q = 0; q < nq; ++q) {
     double lam[NV];
 #pragma unroll
@@ -128,9 +134,10 @@ template <int ND> struct Passes { static constexpr int N = 1; };
 template <> struct Passes<10> { static constexpr int N = 3; };
 
 // measured on the B200 at config C (16 M P2 triangles, cell kernel): 128 threads x 3 CTAs per SM 1.252 ms, x 2 CTAs 1.252,
-// x 4 CTAs (spills) 1.268; 64 threads x 6 CTAs 1.214; + the slot lines prefetched into L1 before the quadrature loop 1.188
+// x 4 CTAs (spills) 1.268; 64 threads x 6 CTAs 1.214; + the slot lines prefetched into L1 before the quadrature loop 1.188;
+// 64 x 4 (226 registers, nothing spilled) 1.174; the quadrature loop unrolled by two: 1.172 (64 x 4), 1.274 (64 x 6)
 #ifndef PHIFEM_PK_CELLS_MINBLOCKS_2D
-#define PHIFEM_PK_CELLS_MINBLOCKS_2D 6
+#define PHIFEM_PK_CELLS_MINBLOCKS_2D 4
 #endif
 #ifndef PHIFEM_PK_CELLS_BLOCK
 #define PHIFEM_PK_CELLS_BLOCK 64
