@@ -406,6 +406,29 @@ int phifem_assemble_weak_ghost_pk(const phifem_mesh* mesh, const phifem_pk_space
 int phifem_csr_spmv(int64_t n_rows, const int32_t* indptr, const int32_t* indices, const double* data,
                     const double* x, double* y, void* stream);
 
+/* The Krylov iteration itself, fused (csrc/solve.cu): Jacobi-preconditioned BiCGStab on the ACTIVE rows of an assembled
+ * CSR system (rows with a usable diagonal; the others are MUMPS's null pivots, ICNTL(24), main.py:150-157).
+ *   nnz           entries of the matrix (picks the lanes per row of the product); rows [n_act]  the active rows (ascending); cols [nnz] the matrix's column ids in the compact numbering, inactive
+ *                 columns -> n_act; indptr / data: the matrix as assembled (read in place);
+ *   vectors       length n_act (minv = 1 / diagonal, rhat = the shadow residual, x, r, p, v, s, t) and n_act + 1 with
+ *                 a trailing 0 (y, z: what the products multiply);
+ *   state [8]     {rho, alpha, omega, beta, r.r, rho_new, -, -}: {1, 1, 1, 0, ...} before the first call; state[4] = |r|^2
+ *                 of the current iterate after every call;
+ *   partials      2 * 8 * 148 doubles; on entry its first *n_partials pairs hold partial sums of (rhat.r, r.r)
+ *                 (first call: one pair); *n_partials (HOST) is updated for a continuation.
+ * No host synchronisation; five kernels and three one-block scalar updates per iteration, bitwise reproducible. */
+/* Set-up passes of the solve: diag[r] = a_rr (0 when the pattern has no diagonal entry) and rowmax[r] = max_c |a_rc| of
+ * every row; cols[k] = cmap[indices[k]] (the column ids in the compact numbering of the active rows). */
+int phifem_csr_row_scan(int64_t n_rows, const int32_t* indptr, const int32_t* indices, const double* data, double* diag,
+                        double* rowmax, void* stream);
+int phifem_remap_columns(int64_t nnz, const int32_t* indices, const int32_t* cmap, int32_t* cols, void* stream);
+int phifem_csr_spmv_rows(int64_t n_act, int64_t nnz, const int32_t* rows, const int32_t* indptr, const int32_t* cols,
+                         const double* data, const double* x, double* y, double* partials, void* stream);
+int phifem_bicgstab_iterate(int64_t n_act, int64_t nnz, const int32_t* rows, const int32_t* indptr, const int32_t* cols,
+                            const double* data, const double* minv, const double* rhat, double* x, double* r, double* p,
+                            double* v, double* s, double* t, double* y, double* z, double* state, double* partials,
+                            int32_t* n_partials, int32_t iterations, void* stream);
+
 /* ---- Neumann phi-FEM operator on the mixed space (u, y, p) in P1 x P1^d x DG0: demo/neumann/square/main.py:103-158
  * (`assemble_matrix(form(a))` :141-143, `assemble_vector(form(L))` :160-161), triangles and tetrahedra, P1 or P2 level
  * set.  Cell-local mixed dof order [u at the vertices, y node-major (vertex i, component c -> nv + i d + c), p]

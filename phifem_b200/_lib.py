@@ -131,6 +131,11 @@ _SIGNATURES = {
     "phifem_assemble_neumann_ghost": (ctypes.c_int, [ctypes.POINTER(CMesh), ctypes.POINTER(CQuadrature), _vp,
                                                      ctypes.c_int64, _vp, ctypes.c_double, _vp, _vp]),
     "phifem_csr_spmv": (ctypes.c_int, [ctypes.c_int64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "phifem_csr_row_scan": (ctypes.c_int, [ctypes.c_int64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "phifem_remap_columns": (ctypes.c_int, [ctypes.c_int64, _vp, _vp, _vp, _vp]),
+    "phifem_csr_spmv_rows": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "phifem_bicgstab_iterate": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int64] + [_vp] * 16 + [ctypes.POINTER(ctypes.c_int32),
+                                                                          ctypes.c_int32, _vp]),
     "phifem_assemble_weak_cells_pk": (ctypes.c_int, _PK_HEAD + [_vp, _vp, _vp, _vp, _vp, ctypes.c_int64, _vp, _vp,
                                                                 ctypes.c_double, ctypes.c_double, _vp, _vp, _vp]),
     "phifem_assemble_weak_boundary_pk": (ctypes.c_int, [ctypes.POINTER(CMesh), ctypes.POINTER(CPkSpace),
