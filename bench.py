@@ -490,7 +490,8 @@ def roofline_of(w, per, ms_per_step, clocks):
     achieved = kbytes / (per[dominant] * 1e-3) / 1e9
     tiles = plan.rowsplan.tiles if plan.method == "rows" else None
     kernel_names = {"tag_cells": "k_tag_cells_p1", "tag_facets": "k_tag_facets",
-                    "assemble_cells": {"rows": "k_assemble_tiles_p1" if tiles is not None else "k_assemble_rows_p1",
+                    "assemble_cells": {"rows": ("k_assemble_push_p1" if tiles.push is not None else "k_assemble_tiles_p1")
+                                       if tiles is not None else "k_assemble_rows_p1",
                                        "blocked": "k_assemble_blocked_p1", "atomic": "k_assemble_cells_p1",
                                        "pk-atomic": "k_assemble_cells_pk"}[plan.method]}
     roofline = {"bound": "hbm", "kernel": kernel_names[dominant], "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -1055,7 +1056,7 @@ def main():
     ap.add_argument("--curve", default="auto", choices=["auto", "morton", "pencil"],
                     help="renumbering of the unstructured mesh (Mesh.reordered): Morton curve / count-balanced pencils / "
                          "auto = pencils when the mesh has the connectivity of a grid")
-    ap.add_argument("--cell-pass", default="rows", choices=["rows", "tiles"],
+    ap.add_argument("--cell-pass", default="rows", choices=["rows", "tiles", "push"],
                     help="row-gather cell pass / cell-once tile pass (csrc/assemble_tiles.cu)")
     ap.add_argument("--rows-per-tile", type=int, default=256, choices=[128, 256])
     ap.add_argument("--order", default="auto", choices=["auto", "natural", "morton"],

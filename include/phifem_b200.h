@@ -280,6 +280,13 @@ typedef struct phifem_cell_tiles {
   const int32_t* rec_base;     /* [n_chunks + 1] */
   const uint16_t* rec_off;     /* [n_chunks, rows_per_tile + 1] */
   const uint32_t* rec;         /* [rec_base[n_chunks]] */
+  /* Optional [n_chunks * rows_per_tile, 4] (16-byte aligned): PUSH form of the pass.  When set, the thread that
+   * evaluated the cell of slot q adds the tensor's rows to the tile's shared-memory accumulators itself (fp64
+   * shared-memory atomics; rec_base / rec_off / rec are not read): push[q][i], i = cell-local vertex: bit 8 = the
+   * vertex's row belongs to this tile, bits 0-7 = its index inside the tile, 7 bits from bit 10 + 7 m = position,
+   * inside that row's column list, of the cell's m-th other vertex (ascending cell-local order).  The sum of a row is
+   * then not in mesh order: equal to the pull form to rounding, not bit for bit. */
+  const uint32_t* push;
 } phifem_cell_tiles;
 
 typedef struct phifem_rows_plan {

@@ -53,7 +53,7 @@ class CRowList(ctypes.Structure):
 class CCellTiles(ctypes.Structure):
     _fields_ = [("rows_per_tile", ctypes.c_int32), ("n_tiles", ctypes.c_int32), ("n_listed", ctypes.c_int64),
                 ("rows", _vp), ("diag_pos", _vp), ("chunk_ptr", _vp), ("slot_verts", _vp), ("rec_base", _vp),
-                ("rec_off", _vp), ("rec", _vp)]
+                ("rec_off", _vp), ("rec", _vp), ("push", _vp)]
 
 
 class CRowsPlan(ctypes.Structure):

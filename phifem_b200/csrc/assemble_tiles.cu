@@ -29,6 +29,9 @@ namespace {
 #ifndef PHIFEM_TILES_MINBLOCKS_128
 #define PHIFEM_TILES_MINBLOCKS_128 4
 #endif
+#ifndef PHIFEM_PUSH_BATCH
+#define PHIFEM_PUSH_BATCH 1
+#endif
 
 // Whole element tensor of simplex X: K[i * NV + j] at out[(i * NV + j) * stride], b[i] at out[(NV * NV + i) * stride].
 //   K_ij = |K|/((d+1)(d+2)) [ |g|^2 (1 + delta_ij) + a_i (P + p_j) + (P + p_i) a_j + G_i.G_j mu ] + 4 sigma h^2 |K| a_i a_j
@@ -257,6 +260,136 @@ __global__ void __launch_bounds__(R, R == 128 ? PHIFEM_TILES_MINBLOCKS_128 : PHI
   }
 }
 
+// Cell-once PUSH form (plan option cell_pass="push"): same tiles, same cell list, but no parked tensors and no pull.
+// The thread that evaluated a cell adds the rows of the tensor that belong to the tile's own rows straight into the
+// tile's accumulators in shared memory -- acc[pos * R + l] for row l of the tile, its diagonal in dacc[l], its load
+// entry in bacc[l].  A tile's cells share vertices, so the updates are shared-memory fp64 atomics (a compare-and-swap
+// loop on sm_100: conflicts are rare, the loop usually runs once); nothing orders them, so the sum of a row is NOT in
+// mesh order: results agree with the row-gather pass to rounding, not bit for bit.  No barrier between the cells of a
+// tile: a thread walks slots tid, tid + R, ... with the next slot's vertex data in flight while it pushes.
+//   push[q][i] (one word per cell-local vertex i of slot q): bit 8 = the vertex's row belongs to this tile,
+//   bits 0-7 = its index l in the tile, 7 bits from bit 10 + 7 m = position inside row l's column list of the cell's
+//   m-th OTHER vertex (ascending cell-local order).
+template <int D, int R>
+__global__ void __launch_bounds__(R, R == 128 ? PHIFEM_TILES_MINBLOCKS_128 : PHIFEM_TILES_MINBLOCKS) k_assemble_push_p1(
+    const double* __restrict__ x, const double* __restrict__ phi, const double* __restrict__ f, double sigma,
+    const int32_t* __restrict__ indptr, phifem_cell_tiles tl, int max_row_nnz, double* __restrict__ data,
+    double* __restrict__ b) {
+  constexpr int NV = D + 1;
+  extern __shared__ double sm[];
+  double* acc_s = sm;                                   // [max_row_nnz][R]
+  double* dacc = sm + (size_t)max_row_nnz * R;          // [R] diagonal entries
+  double* bacc = dacc + R;                              // [R] load vector
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x;
+  const int64_t li = (int64_t)tile * R + tid;
+  const bool has_row = li < tl.n_listed;
+  int r = 0, start = 0, nnz = 0, dpos = 0;
+  if (has_row) {
+    r = __ldg(tl.rows + li);
+    start = __ldg(indptr + r);
+    nnz = __ldg(indptr + r + 1) - start;
+    dpos = __ldg(tl.diag_pos + li);
+  }
+  for (int k = 0; k < nnz; ++k) acc_s[k * R + tid] = 0.0;
+  dacc[tid] = 0.0;
+  bacc[tid] = 0.0;
+  const int64_t q0 = (int64_t)__ldg(tl.chunk_ptr + tile) * R, q1 = (int64_t)__ldg(tl.chunk_ptr + tile + 1) * R;
+  const int4* __restrict__ slots = reinterpret_cast<const int4*>(tl.slot_verts);
+  const uint4* __restrict__ pushw = reinterpret_cast<const uint4*>(tl.push);
+  const int4 none = make_int4(-1, 0, 0, 0);
+
+  double X[NV][D], p[NV], fv[NV];
+  auto gather = [&](const int4& sv) {
+    if (sv.x < 0) return;
+    const int v[4] = {sv.x, sv.y & 0x7fffffff, sv.z, sv.w};
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) X[k][d] = __ldg(x + (int64_t)v[k] * D + d);
+      p[k] = __ldg(phi + v[k]);
+      fv[k] = __ldg(f + v[k]);
+    }
+  };
+  int64_t q = q0 + tid;
+  int4 sv = q < q1 ? __ldg(slots + q) : none;
+  int4 sv1 = q + R < q1 ? __ldg(slots + q + R) : none;
+  uint4 pw = q < q1 ? __ldg(pushw + q) : make_uint4(0, 0, 0, 0);
+  gather(sv);
+  __syncthreads();   // accumulators are zero
+  for (; q < q1; q += R) {
+    const bool live = sv.x >= 0;
+    const bool is_cut = sv.y < 0;
+    double out[NV * NV + NV];
+    if (live) cell_tensor<D>(X, p, fv, is_cut, sigma, out, 1);
+    const uint4 pc = pw;
+    // next slot: vertex data into the registers just consumed, ids of the slot after it, its push words
+    sv = sv1;
+    gather(sv);
+    sv1 = q + 2 * R < q1 ? __ldg(slots + q + 2 * R) : none;
+    if (q + R < q1) pw = __ldg(pushw + q + R);
+    if (live) {
+      const uint32_t w4[4] = {pc.x, pc.y, pc.z, pc.w};
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const uint32_t w = w4[i];
+        if (w & 0x100u) {
+          const int l = w & 0xff;
+          double* dst[D + 2];
+          double v[D + 2];
+          dst[0] = dacc + l;
+          v[0] = out[i * NV + i];
+          dst[1] = bacc + l;
+          v[1] = out[NV * NV + i];
+#pragma unroll
+          for (int m = 0; m < D; ++m) {
+            const int j = m + (m >= i);
+            dst[2 + m] = acc_s + ((w >> (10 + 7 * m)) & 0x7f) * R + l;
+            v[2 + m] = out[i * NV + j];
+          }
+#if PHIFEM_PUSH_BATCH
+          // the D + 2 updates of a row as ONE batch: loads, sums, compare-and-swaps issued back to back (a
+          // compiler-generated atomicAdd is a dependent LDS -> DADD -> CAS chain each); the rare loser retries alone
+          unsigned long long seen[D + 2], want[D + 2];
+#pragma unroll
+          for (int e = 0; e < D + 2; ++e) seen[e] = *reinterpret_cast<volatile unsigned long long*>(dst[e]);
+#pragma unroll
+          for (int e = 0; e < D + 2; ++e) want[e] = __double_as_longlong(__longlong_as_double(seen[e]) + v[e]);
+#pragma unroll
+          for (int e = 0; e < D + 2; ++e)
+            want[e] = atomicCAS(reinterpret_cast<unsigned long long*>(dst[e]), seen[e], want[e]);
+#pragma unroll
+          for (int e = 0; e < D + 2; ++e)
+            if (want[e] != seen[e]) atomicAdd(dst[e], v[e]);
+#else
+#pragma unroll
+          for (int e = 0; e < D + 2; ++e) atomicAdd(dst[e], v[e]);
+#endif
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (has_row) {
+    double* acc = acc_s + tid;
+    acc[dpos * R] += dacc[tid];
+    for (int k = 0; k < nnz; ++k) data[start + k] = acc[k * R];
+    b[r] = bacc[tid];
+  }
+}
+
+template <int D, int R>
+cudaError_t launch_push(const phifem_mesh* mesh, const double* phi, const double* f, double sigma, const int32_t* indptr,
+                        const phifem_cell_tiles& tl, int max_row_nnz, double* data, double* b, cudaStream_t st) {
+  const size_t smem = ((size_t)max_row_nnz * R + 2 * R) * sizeof(double);
+  auto kernel = k_assemble_push_p1<D, R>;
+  cudaError_t err = cudaSuccess;
+  if (smem > 48 * 1024) err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  kernel<<<(unsigned)tl.n_tiles, R, smem, st>>>(mesh->x, phi, f, sigma, indptr, tl, max_row_nnz, data, b);
+  return cudaGetLastError();
+}
+
 template <int D, int R>
 cudaError_t launch(const phifem_mesh* mesh, const double* phi, const double* f, double sigma, const int32_t* indptr,
                    const phifem_cell_tiles& tl, int max_row_nnz, double* data, double* b, cudaStream_t st) {
@@ -278,10 +411,18 @@ cudaError_t launch_cell_tiles_p1(const phifem_mesh* mesh, const double* phi, con
                                  const int32_t* indptr, const phifem_cell_tiles* tl, int max_row_nnz, double* data,
                                  double* b, cudaStream_t st) {
   if (tl->n_tiles <= 0) return cudaSuccess;
-  if (!(tl->rows && tl->diag_pos && tl->chunk_ptr && tl->slot_verts && tl->rec_base && tl->rec_off && tl->rec) ||
+  if (!(tl->rows && tl->diag_pos && tl->chunk_ptr && tl->slot_verts &&
+        (tl->push || (tl->rec_base && tl->rec_off && tl->rec))) ||
       max_row_nnz > 128 || (tl->rows_per_tile != 128 && tl->rows_per_tile != 256))
     return cudaErrorInvalidValue;
   const bool tri = mesh->cell_type == PHIFEM_TRIANGLE;
+  if (tl->push) {   // push form: atomics into the tile's shared-memory accumulators
+    if (tl->rows_per_tile == 128)
+      return tri ? launch_push<2, 128>(mesh, phi, f, sigma, indptr, *tl, max_row_nnz, data, b, st)
+                 : launch_push<3, 128>(mesh, phi, f, sigma, indptr, *tl, max_row_nnz, data, b, st);
+    return tri ? launch_push<2, 256>(mesh, phi, f, sigma, indptr, *tl, max_row_nnz, data, b, st)
+               : launch_push<3, 256>(mesh, phi, f, sigma, indptr, *tl, max_row_nnz, data, b, st);
+  }
   if (tl->rows_per_tile == 128)
     return tri ? launch<2, 128>(mesh, phi, f, sigma, indptr, *tl, max_row_nnz, data, b, st)
                : launch<3, 128>(mesh, phi, f, sigma, indptr, *tl, max_row_nnz, data, b, st);

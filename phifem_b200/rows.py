@@ -176,12 +176,12 @@ class RowsPlan:
                 "for this mesh" % (self.max_row_nnz, min(MAX_ROW_NNZ, MAX_SMEM_BYTES // (BLOCK * 8))))
         if order not in ("natural", "morton", "auto"):
             raise ValueError("order must be 'natural', 'morton' or 'auto'")
-        if cell_pass not in ("rows", "tiles"):
-            raise ValueError("cell_pass must be 'rows' or 'tiles'")
-        if cell_pass == "tiles" and (geometry or self.max_row_nnz > 128):
+        if cell_pass not in ("rows", "tiles", "push"):
+            raise ValueError("cell_pass must be 'rows', 'tiles' or 'push'")
+        if cell_pass in ("tiles", "push") and (geometry or self.max_row_nnz > 128):
             cell_pass = "rows"        # positions of the tile records are 7 bits
         if order == "auto":
-            order = "morton" if cell_pass == "tiles" and not getattr(mesh, "sfc_ordered", False) else "natural"
+            order = "morton" if cell_pass in ("tiles", "push") and not getattr(mesh, "sfc_ordered", False) else "natural"
         self.order = order
         self.cell_pass = cell_pass
 
@@ -220,11 +220,12 @@ class RowsPlan:
         # interleaved so that the records of a row keep cell order (deterministic summation order)
         rec_rows, words = owned(cells_act.reshape(-1), torch.stack(words, dim=1).reshape(-1, 2 if geometry else 1))
         self.tiles = None
-        if cell_pass == "tiles":
+        if cell_pass in ("tiles", "push"):
             from .tiles import CellTiles
             trows = ordered(listed)
             self.tiles = CellTiles(mesh, plan.active, cut, plan.slots_cells, indptr, trows,
-                                   (dslot[trows] - indptr[trows]).to(torch.uint8), rows_per_tile)
+                                   (dslot[trows] - indptr[trows]).to(torch.uint8), rows_per_tile,
+                                   push=cell_pass == "push")
             self.n_cell_records = int(rec_rows.numel())
             empty = torch.zeros(0, **i64)
             self.cells = RowList(empty, dslot, indptr, empty, torch.zeros((0, 1), **i64), n)

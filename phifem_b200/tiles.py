@@ -5,6 +5,8 @@ threads per CTA); a tile's cells = the active cells touching one of its rows, in
 a record per (row, cell) names the cell's slot in its chunk and where the cell's other vertices sit in the row's column
 list.  Sort / scatter plumbing with torch ops on the mesh's device (CPU tensors work: tests/test_tiles_symbolic.py).
 """
+import os
+
 import torch
 
 from . import _lib
@@ -14,13 +16,17 @@ MAX_ROW_NNZ = 128            # positions are 7 bits
 
 
 class CellTiles:
-    def __init__(self, mesh, active, cut, slots_cells, indptr, rows, diag_pos, rows_per_tile=ROWS_PER_TILE):
+    def __init__(self, mesh, active, cut, slots_cells, indptr, rows, diag_pos, rows_per_tile=ROWS_PER_TILE, push=False,
+                 interleave=None):
         """active [Na] int: active cells ascending; cut [Na] 0/1; slots_cells [Na, nv*nv] CSR slot of (row i, col j);
         indptr [n+1] int64; rows [L] int64 listed rows in processing order; diag_pos [L] uint8."""
         if rows_per_tile not in (128, 256):
             raise ValueError("rows_per_tile must be 128 or 256")
         dev = rows.device
         i64 = dict(dtype=torch.int64, device=dev)
+        if interleave is None:
+            interleave = os.environ.get("PHIFEM_PUSH_INTERLEAVE", "0") == "1"
+        self.interleave = bool(push and interleave)
         R = self.rows_per_tile = int(rows_per_tile)
         nv = mesh.cells.shape[1]
         n = indptr.numel() - 1
@@ -47,7 +53,13 @@ class CellTiles:
         self.n_cell_slots = int(ukey.numel())                             # cell evaluations per pass
         self.n_active = na
         first = torch.cumsum(cnt, 0) - cnt
-        slot = chunk_ptr[pt] * R + (torch.arange(ukey.numel(), **i64) - first[pt])
+        rank = torch.arange(ukey.numel(), **i64) - first[pt]
+        if push and interleave:
+            # lanes of a warp take cells `stride` apart in the tile's list instead of neighbours (which share vertices
+            # and collide on the same accumulators): rank -> (rank % stride) * 32 + rank // stride, stride = ceil(cnt / 32)
+            stride = ((cnt + 31) // 32).clamp(min=1)[pt]
+            rank = (rank % stride) * 32 + rank // stride
+        slot = chunk_ptr[pt] * R + rank
         sv = torch.full((max(nch, 1) * R, 4), -1, **i64)
         verts = cells_act[pa]
         if nv == 3:
@@ -56,6 +68,27 @@ class CellTiles:
         verts[:, 1] |= cut.long()[pa] << 31
         sv[slot] = verts
         sv = torch.where(sv >= 2 ** 31, sv - 2 ** 32, sv).to(torch.int32)  # same bits as uint32
+        # ---- push words (cell_pass="push"): per slot and cell-local vertex, where the tensor's row goes -----------
+        self.push = None
+        if push:
+            sl = slots_cells.long().reshape(na, nv, nv)
+            rows_s = cells_act[pa]                                         # [S, nv] row of each local vertex
+            li_s = li[pa]
+            mine = (li_s >= 0) & ((li_s // R) == pt[:, None])
+            words = torch.zeros((max(nch, 1) * R, 4), **i64)
+            for i in range(nv):
+                w = (li_s[:, i] % R) | (1 << 8)
+                m = 0
+                for j in range(nv):
+                    if j == i:
+                        continue
+                    pos = sl[pa, i, j] - indptr[rows_s[:, i]]
+                    assert pos.numel() == 0 or (int(pos.min()) >= 0 and int(pos.max()) < MAX_ROW_NNZ)
+                    w = w | (pos << (10 + 7 * m))
+                    m += 1
+                words[slot, i] = torch.where(mine[:, i], w, torch.zeros_like(w))
+            self.push = words.to(torch.int32).contiguous()                 # bits 0..30 only
+            del sl, rows_s, li_s, mine, words
         # ---- records ------------------------------------------------------------------------------------------
         gslot = slot[torch.searchsorted(ukey, key)]                        # slot of the record's cell in ITS tile
         chunk, lane = gslot // R, gslot % R
@@ -95,12 +128,13 @@ class CellTiles:
 
     def nbytes(self):
         return int(sum(t.numel() * t.element_size() for t in (self.rows, self.diag_pos, self.chunk_ptr, self.slot_verts,
-                                                             self.rec_base, self.rec_off, self.rec)))
+                                                             self.rec_base, self.rec_off, self.rec) + (
+                                                                 (self.push,) if self.push is not None else ())))
 
     def c_struct(self):
         if self._c is None:
             p = _lib.ptr
             self._c = _lib.CCellTiles(self.rows_per_tile, self.n_tiles, self.n_listed, p(self.rows), p(self.diag_pos),
                                       p(self.chunk_ptr), p(self.slot_verts), p(self.rec_base), p(self.rec_off),
-                                      p(self.rec))
+                                      p(self.rec), p(self.push) if self.push is not None else None)
         return self._c

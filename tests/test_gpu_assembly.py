@@ -40,6 +40,7 @@ def _row_scale(indptr, data):
 
 @pytest.mark.parametrize("method,capacity", [("rows", None), ("rows", "morton"), ("rows", "geometry"),
                                              ("rows", "tiles128"), ("rows", "tiles256"),
+                                             ("rows", "push128"), ("rows", "push256"),
                                              ("blocked", None), ("blocked", 2500), ("atomic", None)])
 @pytest.mark.parametrize("kind,n", [("tri", 40), ("tri-unstructured", 24), ("tet", 10),
                                     ("tet-unstructured", 8)])
@@ -52,6 +53,8 @@ def test_cuda_operator_matches_oracle(kind, n, method, capacity):
     order, geometry, cell_pass, rpt = "natural", False, "rows", 256
     if method == "rows" and str(capacity).startswith("tiles"):   # cell-once cell pass (csrc/assemble_tiles.cu)
         order, cell_pass, rpt, capacity = "morton", "tiles", int(capacity[5:]), None
+    elif method == "rows" and str(capacity).startswith("push"):   # cell-once pass, push form (shared-memory atomics)
+        order, cell_pass, rpt, capacity = "morton", "push", int(capacity[4:]), None
     elif method == "rows" and capacity == "geometry":   # cell pass from the plan's geometry table instead of the coordinates
         geometry, capacity = True, None
     elif method == "rows" and capacity:
@@ -61,7 +64,8 @@ def test_cuda_operator_matches_oracle(kind, n, method, capacity):
     assert plan.method == method
     if method == "rows":
         assert (plan.rowsplan.cell_geom is not None) == geometry
-        assert (plan.rowsplan.tiles is not None) == (cell_pass == "tiles")
+        assert (plan.rowsplan.tiles is not None) == (cell_pass in ("tiles", "push"))
+        assert (plan.rowsplan.tiles is not None and plan.rowsplan.tiles.push is not None) == (cell_pass == "push")
     A, b = assemble.assemble_strong_dirichlet(plan, phi, f, stab_coef=1.0)
     if method in ("blocked", "rows"):
         # owner-computes sums in a fixed order: bitwise reproducible, and independent of what the
@@ -69,7 +73,12 @@ def test_cuda_operator_matches_oracle(kind, n, method, capacity):
         data2 = torch.full_like(A.data, float("nan"))
         b2 = torch.zeros_like(b)
         assemble.assemble_into(plan, phi, f, 1.0, data2, b2)
-        assert torch.equal(data2, A.data) and torch.equal(b2, b)
+        if cell_pass == "push":   # unordered shared-memory atomics: equal to rounding; still no zero-fill needed
+            assert not torch.isnan(data2).any()
+            assert (data2 - A.data).abs().max() <= 1e-14 * A.data.abs().max()
+            assert (b2 - b).abs().max() <= 1e-14 * b.abs().max()
+        else:
+            assert torch.equal(data2, A.data) and torch.equal(b2, b)
         if capacity:
             assert plan.blocked.n_blocks > 4
         if method == "rows":

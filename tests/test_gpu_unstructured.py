@@ -77,7 +77,7 @@ def test_unstructured_tags_equal_the_oracle(problem):
     assert sorted(map(tuple, got_old)) == sorted(map(tuple, ents_o.reshape(-1, 2)))
 
 
-@pytest.mark.parametrize("cell_pass", ["rows", "tiles"])
+@pytest.mark.parametrize("cell_pass", ["rows", "tiles", "push"])
 def test_unstructured_operator_equals_the_oracle(problem, cell_pass):
     p = problem
     mesh = p["mesh"]
@@ -85,7 +85,10 @@ def test_unstructured_operator_equals_the_oracle(problem, cell_pass):
     assert plan.method == "rows" and plan.rowsplan.order == "natural"          # the mesh is already SFC-numbered
     A, b = assemble.assemble_strong_dirichlet(plan, p["phi"], p["f"], stab_coef=1.0)
     A2, b2 = assemble.assemble_strong_dirichlet(plan, p["phi"], p["f"], stab_coef=1.0)
-    assert torch.equal(A.data, A2.data) and torch.equal(b, b2)                  # fixed summation order
+    if cell_pass == "push":                                                     # unordered shared-memory atomics
+        assert (A.data - A2.data).abs().max() <= 1e-14 * A.data.abs().max()
+    else:
+        assert torch.equal(A.data, A2.data) and torch.equal(b, b2)              # fixed summation order
     # oracle operator on the user's numbering (slot maps from the product's host plumbing on CPU tensors, which
     # tests/test_host_logic.py holds to the oracle's pattern)
     host = p["host"]

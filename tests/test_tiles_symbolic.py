@@ -128,3 +128,90 @@ def test_cell_tiles_with_a_row_mask_list_only_owned_rows():
     data, b, seen = _emulate_cell_pass(tl, plan, x, cells, phi, f, out["cell_tags"], 1.0)
     act = np.isin(out["cell_tags"], (1, 2))
     assert len(seen) == int(mask.numpy()[cells[act]].sum())
+
+
+def _emulate_push_pass(tl, plan, x, cells, phi, f, ct, sigma):
+    """k_assemble_push_p1 from the plan arrays: the cell of every slot is evaluated once and its rows are added to the
+    accumulators of the tile's own rows through the push words."""
+    R, nv = tl.rows_per_tile, cells.shape[1]
+    indptr, indices = plan.indptr.numpy().astype(np.int64), plan.indices.numpy().astype(np.int64)
+    rows, dpos = tl.rows.numpy().astype(np.int64), tl.diag_pos.numpy().astype(np.int64)
+    chunk_ptr, sv = tl.chunk_ptr.numpy(), tl.slot_verts.numpy().view(np.uint32).reshape(-1, 4)
+    push = tl.push.numpy().view(np.uint32).reshape(-1, 4)
+    assert push.shape == sv.shape
+    cell_of = {tuple(c): i for i, c in enumerate(cells)}
+    data = np.full(plan.nnz, np.nan)
+    b = np.zeros(len(x))
+    seen = set()
+    for t in range(tl.n_tiles):
+        mine = rows[t * R:(t + 1) * R]
+        for r in mine:
+            data[indptr[r]:indptr[r + 1]] = 0.0
+        for q in range(chunk_ptr[t] * R, chunk_ptr[t + 1] * R):
+            v = sv[q]
+            if v[0] == 0xFFFFFFFF:
+                assert not push[q].any()
+                continue
+            verts = [int(v[0]), int(v[1] & 0x7FFFFFFF)] + [int(u) for u in v[2:nv]]
+            k = cell_of[tuple(verts)]
+            _, At, bt = (k,) + OA.cell_tensors_closed_form(x, cells[k:k + 1], phi, f, np.array([ct[k] == 2]), sigma)
+            pushed = 0
+            for i in range(nv):
+                w = int(push[q, i])
+                r = verts[i]
+                if not (w >> 8) & 1:
+                    assert w == 0 and r not in set(mine), "a row of the tile is always pushed"
+                    continue
+                l = w & 0xFF
+                assert mine[l] == r and (r, k) not in seen
+                seen.add((r, k))
+                pushed += 1
+                assert indices[indptr[r] + dpos[t * R + l]] == r
+                data[indptr[r] + dpos[t * R + l]] += At[0, i, i]
+                b[r] += bt[0, i]
+                for m in range(nv - 1):
+                    j = m + (m >= i)
+                    p = (w >> (10 + 7 * m)) & 0x7F
+                    assert indices[indptr[r] + p] == verts[j]
+                    data[indptr[r] + p] += At[0, i, j]
+            assert pushed >= 1, "a slot holds a cell touching the tile"
+            assert not push[q, nv:].any()
+    return data, b, seen
+
+
+@pytest.mark.parametrize("d,n,R,order", [(2, 14, 128, "natural"), (2, 20, 256, "morton"), (3, 5, 128, "morton"),
+                                         (3, 6, 256, "auto")])
+def test_push_words_reproduce_the_oracle_cell_operator(d, n, R, order):
+    m, x, cells, phi, f, out = _problem(d, n)
+    plan = assemble.build_plan(m, MeshTags(m, d, torch.from_numpy(out["cell_tags"])),
+                               MeshTags(m, d - 1, torch.from_numpy(out["facet_tags"])), out["ds100"],
+                               method="rows", order=order, cell_pass="push", rows_per_tile=R)
+    rp = plan.rowsplan
+    tl = rp.tiles
+    assert rp.cell_pass == "push" and tl.push is not None and rp.cells.n_listed == 0
+    ct = out["cell_tags"]
+    data, b, seen = _emulate_push_pass(tl, plan, x, cells, phi, f, ct, 1.0)
+    na = int(np.isin(ct, (1, 2)).sum())
+    assert len(seen) == (d + 1) * na
+    ft0 = np.where(np.isin(out["facet_tags"], (2, 3)), 1, out["facet_tags"])
+    ip, ix, want, wb = OA.assemble_strong_dirichlet(x, cells, cells, len(x), phi, f, ct, ft0, out["c2f"], out["f2c"],
+                                                    np.zeros(0, dtype=np.int32), sigma=1.0)
+    import scipy.sparse as sp
+    assert not np.isnan(data).any()
+    full = sp.csr_matrix((data, plan.indices.numpy(), plan.indptr.numpy()), shape=(len(x), len(x)))
+    cellop = sp.csr_matrix((want, ix, ip), shape=(len(x), len(x)))
+    assert abs(full - cellop).max() <= 1e-13 * np.abs(want).max()
+    assert np.abs(b - wb).max() <= 1e-13 * np.abs(wb).max()
+
+
+def test_push_words_with_a_row_mask_push_only_owned_rows():
+    m, x, cells, phi, f, out = _problem(3, 5, seed=3)
+    mask = torch.zeros(m.num_vertices, dtype=torch.bool)
+    mask[: m.num_vertices // 2] = True
+    from phifem_b200.assemble import AssemblyPlan, _plan_inputs
+    c8, f8, ents = _plan_inputs(m, MeshTags(m, 3, torch.from_numpy(out["cell_tags"])),
+                                MeshTags(m, 2, torch.from_numpy(out["facet_tags"])), out["ds100"])
+    plan = AssemblyPlan(m, c8, f8, ents, row_mask=mask, cell_pass="push", rows_per_tile=128)
+    data, b, seen = _emulate_push_pass(plan.rowsplan.tiles, plan, x, cells, phi, f, out["cell_tags"], 1.0)
+    act = np.isin(out["cell_tags"], (1, 2))
+    assert len(seen) == int(mask.numpy()[cells[act]].sum())
