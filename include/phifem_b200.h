@@ -105,6 +105,14 @@ enum {
 const char* phifem_last_error(void);
 int phifem_abi_version(void);
 
+/* n_words (<= 4096) 64-bit words of device memory -> page-locked host memory (cudaHostAlloc / cudaHostRegister'ed,
+ * device-mapped: every such allocation is under unified addressing), written by a kernel over PCIe instead of a copy
+ * engine: the counter block of phifem_tag_cells / phifem_tag_facets reaches the host without queueing behind a large
+ * download issued on another stream.  Complete once an event recorded on `stream` after the call has completed.
+ * Replaces the implicit device -> host reads of the reference's numpy views (src/phifem/mesh_scripts.py:129-133,
+ * :360-374: warnings and debug checks on assembled arrays). */
+int phifem_post_to_host(const int64_t* device_words, int64_t* pinned_host_words, int32_t n_words, void* stream);
+
 /* Physical coordinates of reference points in every cell: out[n_cells, n_points, gdim].
  * `shape` [n_points, nvpc] = coordinate-element basis at the points.  Used to evaluate an
  * expression level set where the reference evaluates a UFL expression of SpatialCoordinate. */

@@ -98,6 +98,7 @@ _PK_HEAD = [ctypes.POINTER(CMesh), ctypes.POINTER(CPkSpace), ctypes.POINTER(CPkS
 _SIGNATURES = {
     "phifem_last_error": (ctypes.c_char_p, []),
     "phifem_abi_version": (ctypes.c_int, []),
+    "phifem_post_to_host": (ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp]),
     "phifem_cell_points": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, ctypes.c_int32, _vp, _vp]),
     "phifem_tag_cells": (ctypes.c_int, [ctypes.POINTER(CMesh), ctypes.POINTER(CLevelset),
                                         ctypes.c_int32, _vp, _vp, _vp, _vp, _vp]),

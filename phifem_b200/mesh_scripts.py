@@ -17,6 +17,7 @@ Public API (reference :571-653):
 """
 import os
 import ctypes
+import threading
 import warnings
 
 import numpy as np
@@ -124,6 +125,27 @@ class TagWorkspace:
     @property
     def facet_tags(self):
         return self.facet_tags32 if self.facet_tags32 is not None else self.facet_tags8.to(torch.int32)
+
+
+_host_counters = threading.local()
+
+
+def _read_counters(ws):
+    """The counter block on the host: THE host synchronisation of a `compute_tags_measures` call.  A kernel posts the
+    128 bytes into page-locked host memory (`phifem_post_to_host`) and the host waits for an event on the calling
+    stream only -- a `counters.cpu()` would be a copy-engine transfer, which queues behind whatever download another
+    stream has in flight (the CSR values of the previous step, in a pipeline with two steps in flight)."""
+    key = ws.counters.device.index
+    bufs = getattr(_host_counters, "bufs", None)
+    if bufs is None:
+        bufs = _host_counters.bufs = {}
+    if key not in bufs:
+        bufs[key] = (torch.zeros(_lib.N_COUNTERS, dtype=torch.int64).pin_memory(), torch.cuda.Event())
+    host, event = bufs[key]
+    _lib.check(_lib.load().phifem_post_to_host(_lib.ptr(ws.counters), host.data_ptr(), _lib.N_COUNTERS, _lib.stream()))
+    event.record()
+    event.synchronize()
+    return host.numpy().copy()
 
 
 def classify_cells(mesh, dls, ws, single_layer_cut=False, exact_zero_den=False):
@@ -296,13 +318,13 @@ def compute_tags_measures(mesh, discrete_levelset, detection_degree, box_mode=Fa
     counted = box_mode and not overwrite_tags
     if counted:
         _count_entities(mesh, ws, ws.cell_tags8, ws.facet_tags8)
-    counters = ws.counters.cpu().numpy()
+    counters = _read_counters(ws)
     if counters[_lib.CNT_ZERO_DEN] == 0 and counters[_lib.CNT_ZERO_DEN_AMBIGUOUS] > 0:
         # no cell settled the RuntimeWarning of :129-133 and some were left undecided: evaluate them
         ws = classify(mesh, dls, single_layer_cut, ws=ws, exact_zero_den=True)
         if counted:
             _count_entities(mesh, ws, ws.cell_tags8, ws.facet_tags8)
-        counters = ws.counters.cpu().numpy()
+        counters = _read_counters(ws)
     if counters[_lib.CNT_ZERO_DEN] > 0:           # :129-133 for the dx detection
         warnings.warn(_ZERO_WARNING, RuntimeWarning)
     if counters[_lib.CNT_FACET_ZERO_DEN] > 0 or counters[_lib.CNT_BOUNDARY_OWNERS] < mesh.num_cells:
