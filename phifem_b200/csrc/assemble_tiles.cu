@@ -32,6 +32,9 @@ namespace {
 #ifndef PHIFEM_PUSH_BATCH
 #define PHIFEM_PUSH_BATCH 1
 #endif
+#ifndef PHIFEM_PUSH_RACY
+#define PHIFEM_PUSH_RACY 0
+#endif
 
 // Whole element tensor of simplex X: K[i * NV + j] at out[(i * NV + j) * stride], b[i] at out[(NV * NV + i) * stride].
 //   K_ij = |K|/((d+1)(d+2)) [ |g|^2 (1 + delta_ij) + a_i (P + p_j) + (P + p_i) a_j + G_i.G_j mu ] + 4 sigma h^2 |K| a_i a_j
@@ -347,7 +350,15 @@ __global__ void __launch_bounds__(R, R == 128 ? PHIFEM_TILES_MINBLOCKS_128 : PHI
             dst[2 + m] = acc_s + ((w >> (10 + 7 * m)) & 0x7f) * R + l;
             v[2 + m] = out[i * NV + j];
           }
-#if PHIFEM_PUSH_BATCH
+#if PHIFEM_PUSH_RACY
+          // TIMING EXPERIMENT ONLY (wrong results): plain load / add / store -- what the pass would cost if the cells
+          // running concurrently never shared a row (a vertex-disjoint colouring of each tile's cells)
+          double cur[D + 2];
+#pragma unroll
+          for (int e = 0; e < D + 2; ++e) cur[e] = *reinterpret_cast<volatile double*>(dst[e]);
+#pragma unroll
+          for (int e = 0; e < D + 2; ++e) *reinterpret_cast<volatile double*>(dst[e]) = cur[e] + v[e];
+#elif PHIFEM_PUSH_BATCH
           // the D + 2 updates of a row as ONE batch: loads, sums, compare-and-swaps issued back to back (a
           // compiler-generated atomicAdd is a dependent LDS -> DADD -> CAS chain each); the rare loser retries alone
           unsigned long long seen[D + 2], want[D + 2];
