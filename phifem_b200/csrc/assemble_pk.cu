@@ -44,7 +44,7 @@ __host__ __device__ constexpr bool single_contributor(int i, int j) {
 // ---- cells: rows [I0, I1) of the symmetric element matrix (columns j >= i) and of the load vector ----
 //   A_ij = int grad(phi psi_i).grad(phi psi_j) + [cut] sigma h^2 int lap(phi psi_i) lap(phi psi_j)   (main.py:105-112)
 //   b_i  = int f phi psi_i - [cut] sigma h^2 int f lap(phi psi_i)                                     (:126-128)
-template <int D, int KW, int KP, int I0, int I1>
+template <int D, int KW, int KP, int I0, int I1, bool SLOTS_SHARED = false>
 __device__ __forceinline__ void cell_rows(const Geometry<D>& g, const double (&pc)[Space<D, KP>::ND],
                                           const double (&fc)[Space<D, KW>::ND], bool is_cut, double sigma,
                                           const double* __restrict__ qlam, const double* __restrict__ qw,
@@ -118,12 +118,14 @@ __device__ __forceinline__ void cell_rows(const Geometry<D>& g, const double (&p
 #pragma unroll
     for (int j = i; j < ND; ++j) {
       const double v = A[i - I0][j];
+      const int32_t sij = SLOTS_SHARED ? slots[(i * ND + j) * stride] : __ldg(slots + (int64_t)(i * ND + j) * stride);
+      const int32_t sji = SLOTS_SHARED ? slots[(j * ND + i) * stride] : __ldg(slots + (int64_t)(j * ND + i) * stride);
       if (PHIFEM_PK_SINGLE_STORES && single_contributor<D, KW>(i, j)) {
-        data[__ldg(slots + (int64_t)(i * ND + j) * stride)] = v;
-        data[__ldg(slots + (int64_t)(j * ND + i) * stride)] = v;
+        data[sij] = v;
+        data[sji] = v;
       } else {
-        atomicAdd(data + __ldg(slots + (int64_t)(i * ND + j) * stride), v);
-        if (j != i) atomicAdd(data + __ldg(slots + (int64_t)(j * ND + i) * stride), v);
+        atomicAdd(data + sij, v);
+        if (j != i) atomicAdd(data + sji, v);
       }
     }
   }
@@ -192,6 +194,147 @@ __global__ void __launch_bounds__(kBlockPkCells, D == 2 ? PHIFEM_PK_CELLS_MINBLO
   } else {
     cell_rows<D, KW, KP, 0, ND>(g, pc, fc, is_cut, sigma, qlam, qw, nq, sl, n_active, dofs, data, b);
   }
+}
+
+// ---- the same cells as a PERSISTENT, software-pipelined kernel (single-pass spaces: ND <= 6) --------------------------
+// The kernel above spends 30 % of its stall samples in the prologue (active[e] -> cell / dof ids -> coordinates and
+// coefficients: three dependent global loads before the first fp64 instruction) and 17 % in the final scatter (ND^2
+// slot load -> reduction pairs), with 8 warps per SM to hide them (226 registers).  Here a thread walks cells
+// e, e + T, e + 2 T, ... (T = threads of the grid) and the loads of the NEXT cells travel while the current one is
+// integrated, through per-thread shared-memory slots filled by cp.async (no registers held across the quadrature loop):
+//   top of iteration k:  wait for what iteration k-1 issued -> coordinates / coefficients of cell k into registers;
+//                        active[e_(k+3)] -> register; ids of cell k+2 (cp.async, 4 B); coordinates, coefficients and
+//                        the ND^2 slots of cell k+1 (cp.async, 8 / 4 B; addresses from the ids that landed last time);
+//   then the quadrature loop of cell k and its scatter with the slots read from shared memory.
+// MEASURED at config C (16 M P2 triangles, profiles/round2_r4d_bench_*.json): 1.331 ms against 1.175 ms for the kernel
+// above (3 CTAs per SM 1.328, 5 CTAs 1.638) -- hiding the prologue and the slot loads buys nothing, the 60 cp.async and
+// their shared-memory reads per cell cost 13 %: the kernel is bound by the NUMBER of its scattered L2 reductions (42
+// per triangle), not by the latency in front of them.  Parity green (tests/test_gpu_assembly_pk.py with
+// -DPHIFEM_PK_PIPE=1); off by default.
+#ifndef PHIFEM_PK_PIPE
+#define PHIFEM_PK_PIPE 0
+#endif
+#ifndef PHIFEM_PK_PIPE_MINBLOCKS
+#define PHIFEM_PK_PIPE_MINBLOCKS 4
+#endif
+__device__ __forceinline__ void pk_cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem)
+               : "memory");
+}
+__device__ __forceinline__ void pk_cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem)
+               : "memory");
+}
+
+template <int D, int KW, int KP>
+__global__ void __launch_bounds__(kBlockPkCells, PHIFEM_PK_PIPE_MINBLOCKS) k_assemble_cells_pk_pipe(
+    phifem_mesh m, phifem_pk_space sw, phifem_pk_space sp, const double* __restrict__ qlam_g,
+    const double* __restrict__ qw_g, int nq, const double* __restrict__ phi, const double* __restrict__ f,
+    const int8_t* __restrict__ ctags, const int32_t* __restrict__ active, int64_t n_active,
+    const int32_t* __restrict__ slots, double sigma, double* __restrict__ data, double* __restrict__ b) {
+  constexpr int NV = D + 1, ND = Space<D, KW>::ND, NDP = Space<D, KP>::ND, B = kBlockPkCells;
+  constexpr int NVAL = NV * D + NDP + ND;   // coordinates, level-set coefficients, source coefficients
+  constexpr int NID = NV + ND + NDP;        // vertex ids, dof ids of the two spaces
+  static_assert(ND <= 6, "single-pass spaces only");
+  __shared__ double qlam[kMaxQuadPoints * NV], qw[kMaxQuadPoints];
+  __shared__ double val_s[NVAL * B];
+  __shared__ int32_t slot_s[2][ND * ND * B];
+  __shared__ int32_t id_s[2][NID * B];
+  for (int i = threadIdx.x; i < nq * NV; i += blockDim.x) qlam[i] = qlam_g[i];
+  for (int i = threadIdx.x; i < nq; i += blockDim.x) qw[i] = qw_g[i];
+  __syncthreads();
+  const int tid = threadIdx.x;
+  const int64_t T = (int64_t)gridDim.x * B;
+  const int64_t e0 = (int64_t)blockIdx.x * B + tid;
+  const int32_t* __restrict__ dmw = sw.dofmap ? sw.dofmap : m.cells;
+  const int32_t* __restrict__ dmp = sp.dofmap ? sp.dofmap : m.cells;
+
+  auto issue_ids = [&](int64_t c, int buf) {   // ids of cell c -> id_s[buf]
+    int32_t* dst = id_s[buf] + tid;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) pk_cp_async4(dst + k * B, m.cells + c * NV + k);
+#pragma unroll
+    for (int k = 0; k < ND; ++k) pk_cp_async4(dst + (NV + k) * B, dmw + c * ND + k);
+#pragma unroll
+    for (int k = 0; k < NDP; ++k) pk_cp_async4(dst + (NV + ND + k) * B, dmp + c * NDP + k);
+  };
+  auto issue_values = [&](int64_t e, int buf) {   // coordinates / coefficients of the cell whose ids sit in id_s[buf], slots of e
+    const int32_t* ids = id_s[buf] + tid;
+    double* dst = val_s + tid;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int64_t v = ids[k * B];
+#pragma unroll
+      for (int d = 0; d < D; ++d) pk_cp_async8(dst + (k * D + d) * B, m.x + v * D + d);
+    }
+#pragma unroll
+    for (int k = 0; k < NDP; ++k) pk_cp_async8(dst + (NV * D + k) * B, phi + ids[(NV + ND + k) * B]);
+#pragma unroll
+    for (int k = 0; k < ND; ++k) pk_cp_async8(dst + (NV * D + NDP + k) * B, f + ids[(NV + k) * B]);
+    int32_t* sl = slot_s[buf] + tid;
+#pragma unroll
+    for (int k = 0; k < ND * ND; ++k) pk_cp_async4(sl + k * B, slots + (int64_t)k * n_active + e);
+  };
+  auto commit = [] { asm volatile("cp.async.commit_group;" ::: "memory"); };
+  auto wait_all = [] { asm volatile("cp.async.wait_all;" ::: "memory"); };
+
+  // prime the pipeline: ids of cells 0 and 1, values of cell 0, active[] of cells 2 and 3
+  int64_t c2 = -1, c3 = -1;   // active[e_(k+2)], active[e_(k+3)] at the top of iteration k
+  int cut0 = 0, cut1 = 0, cut2 = 0;   // cell tags of cells k, k + 1, k + 2 (compared where they are used)
+  if (e0 < n_active) {
+    const int64_t c = __ldg(active + e0);
+    cut0 = ctags[c];
+    issue_ids(c, 0);
+  }
+  if (e0 + T < n_active) {
+    const int64_t c = __ldg(active + e0 + T);
+    cut1 = ctags[c];
+    issue_ids(c, 1);
+  }
+  if (e0 + 2 * T < n_active) c2 = __ldg(active + e0 + 2 * T);
+  if (e0 + 3 * T < n_active) c3 = __ldg(active + e0 + 3 * T);
+  commit();
+  wait_all();
+  if (e0 < n_active) issue_values(e0, 0);
+  commit();
+
+  int k = 0;
+  for (int64_t e = e0; e < n_active; e += T, ++k) {
+    const int buf = k & 1;
+    wait_all();   // values / slots of cell k, ids of cell k + 1
+    Geometry<D> g;
+    double pc[NDP], fc[ND];
+    int32_t dofs[ND];
+    {
+      const double* src = val_s + tid;
+#pragma unroll
+      for (int a = 0; a < NV; ++a)
+#pragma unroll
+        for (int d = 0; d < D; ++d) g.X[a][d] = src[(a * D + d) * B];
+#pragma unroll
+      for (int a = 0; a < NDP; ++a) pc[a] = src[(NV * D + a) * B];
+#pragma unroll
+      for (int a = 0; a < ND; ++a) fc[a] = src[(NV * D + NDP + a) * B];
+      const int32_t* ids = id_s[buf] + tid;
+#pragma unroll
+      for (int a = 0; a < ND; ++a) dofs[a] = ids[(NV + a) * B];
+    }
+    const bool is_cut = cut0 == 2;
+    // the loads of the next cells
+    if (c2 >= 0) {
+      cut2 = ctags[c2];
+      issue_ids(c2, buf);                         // ids of cell k + 2 (the ids of cell k are in registers now)
+    }
+    if (e + T < n_active) issue_values(e + T, buf ^ 1);
+    commit();
+    c2 = c3;
+    c3 = e + 4 * T < n_active ? (int64_t)__ldg(active + e + 4 * T) : -1;
+    cut0 = cut1;
+    cut1 = cut2;
+    geometry_from_vertices<D>(g);
+    cell_rows<D, KW, KP, 0, ND, true>(g, pc, fc, is_cut, sigma, qlam, qw, nq, slot_s[buf] + tid, B, dofs, data, b);
+  }
+  wait_all();
 }
 
 // ---- one-sided boundary term: one thread per (entity, test dof i) ------------------------------------------
@@ -843,6 +986,14 @@ extern "C" int phifem_assemble_cells_pk(const phifem_mesh* mesh, const phifem_pk
   cudaStream_t st = (cudaStream_t)stream;
   dispatch(mesh->cell_type, space_w->degree, space_phi->degree, [&](auto d, auto kw, auto kp) {
     constexpr int D = decltype(d)::value, KW = decltype(kw)::value, KP = decltype(kp)::value;
+    if constexpr (PHIFEM_PK_PIPE && Space<D, KW>::ND <= 6) {
+      auto kernel = k_assemble_cells_pk_pipe<D, KW, KP>;
+      const int grid = persistent_grid(kernel, kBlockPkCells, (n_active + kBlockPkCells - 1) / kBlockPkCells);
+      kernel<<<grid, kBlockPkCells, 0, st>>>(*mesh, *space_w, *space_phi, quad->cell_points, quad->cell_weights,
+                                            quad->n_cell_points, phi, f, cell_tags8, active, n_active, slots, sigma,
+                                            data, b);
+      return;
+    }
     const dim3 grid((unsigned)((n_active + kBlockPkCells - 1) / kBlockPkCells), Passes<Space<D, KW>::ND>::N);
     k_assemble_cells_pk<D, KW, KP><<<grid, kBlockPkCells, 0, st>>>(
         *mesh, *space_w, *space_phi, quad->cell_points, quad->cell_weights, quad->n_cell_points, phi, f,

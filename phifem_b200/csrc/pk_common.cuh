@@ -88,6 +88,9 @@ struct Geometry {
 };
 
 template <int D>
+__device__ __forceinline__ void geometry_from_vertices(Geometry<D>& g);
+
+template <int D>
 __device__ __forceinline__ void load_geometry(const phifem_mesh& m, int64_t c, Geometry<D>& g) {
   constexpr int NV = D + 1;
   int v[NV];
@@ -102,6 +105,12 @@ __device__ __forceinline__ void load_geometry(const phifem_mesh& m, int64_t c, G
   for (int k = 0; k < NV; ++k)
 #pragma unroll
     for (int d = 0; d < D; ++d) g.X[k][d] = __ldg(m.x + (int64_t)v[k] * D + d);
+  geometry_from_vertices<D>(g);
+}
+
+// grad(lambda), |K|, h_T^2 from the vertex coordinates g.X
+template <int D>
+__device__ __forceinline__ void geometry_from_vertices(Geometry<D>& g) {
   double e[D][D];
 #pragma unroll
   for (int k = 0; k < D; ++k)
