@@ -682,49 +682,105 @@ def measure_e2e_dist(w, args, world):
              "ft": torch.empty(mesh.num_facets, dtype=torch.int8).pin_memory(),
              "data": torch.empty(data0.numel(), dtype=torch.float64).pin_memory(),
              "b": torch.empty(b0.numel(), dtype=torch.float64).pin_memory()}
-    side = torch.cuda.Stream()
-    tags_done, f_done, phi_up = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+    upload = torch.cuda.Stream()
+    f_done, phi_up = torch.cuda.Event(), torch.cuda.Event()
 
-    def e2e_step():
+    class Slot:
+        """Host buffers of one step in flight, device staging copies of its results (the problem's own tag / value
+        arrays are rewritten by the next step while this step's download is still running), its copy stream."""
+
+        def __init__(self, outputs, staged):
+            self.out, self.copy, self.staged = outputs, torch.cuda.Stream(), staged
+            self.dev = ({k_: torch.empty(v.shape, dtype=v.dtype, device=dev) for k_, v in outputs.items()}
+                        if staged else None)
+            self.tags_done, self.asm_done, self.done = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+            self.pending = False
+
+        def wait(self):
+            if self.pending:
+                self.done.synchronize()
+                self.pending = False
+
+    def issue(sl):
+        main = torch.cuda.current_stream()
         prob.phi.copy_(phi_h, non_blocking=True)      # (the classifier and the plan read these device arrays in place)
         phi_up.record()
-        with torch.cuda.stream(side):
-            side.wait_event(phi_up)
+        with torch.cuda.stream(upload):
+            upload.wait_event(phi_up)
             prob.f.copy_(f_h, non_blocking=True)
             f_done.record()
         prob.classify(w.dls, w.ws)
-        tags_done.record()
-        with torch.cuda.stream(side):
-            side.wait_event(tags_done)
-            out_h["ct"].copy_(w.ws.cell_tags8, non_blocking=True)
-            out_h["ft"].copy_(w.ws.facet_tags8, non_blocking=True)
-        torch.cuda.current_stream().wait_event(f_done)
+        ct, ft = w.ws.cell_tags8, w.ws.facet_tags8
+        if sl.staged:
+            sl.dev["ct"].copy_(ct, non_blocking=True)
+            sl.dev["ft"].copy_(ft, non_blocking=True)
+            ct, ft = sl.dev["ct"], sl.dev["ft"]
+        sl.tags_done.record()
+        with torch.cuda.stream(sl.copy):
+            sl.copy.wait_event(sl.tags_done)
+            sl.out["ct"].copy_(ct, non_blocking=True)
+            sl.out["ft"].copy_(ft, non_blocking=True)
+        main.wait_event(f_done)
         data, b = prob.assemble(1.0)
-        out_h["data"].copy_(data, non_blocking=True)
-        out_h["b"].copy_(b, non_blocking=True)
+        if sl.staged:
+            sl.dev["data"].copy_(data, non_blocking=True)
+            sl.dev["b"].copy_(b, non_blocking=True)
+            data, b = sl.dev["data"], sl.dev["b"]
+        sl.asm_done.record()
+        with torch.cuda.stream(sl.copy):
+            sl.copy.wait_event(sl.asm_done)
+            sl.out["data"].copy_(data, non_blocking=True)
+            sl.out["b"].copy_(b, non_blocking=True)
+            sl.done.record()
+        if not sl.staged:
+            main.wait_event(sl.done)      # one step at a time: the next step rewrites the arrays being downloaded
+        sl.pending = True
+
+    def run(depth, nsteps):
+        slots = [Slot(out_h, depth > 1)] + [Slot({k_: torch.empty_like(v).pin_memory() for k_, v in out_h.items()}, True)
+                                            for _ in range(depth - 1)]
+        for k_ in range(2 * depth):
+            slots[k_ % depth].wait()
+            issue(slots[k_ % depth])
+        for sl in slots:
+            sl.wait()
         torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k_ in range(nsteps):
+            sl = slots[k_ % depth]
+            sl.wait()
+            issue(sl)
+        for sl in slots:
+            sl.wait()
+        torch.cuda.synchronize()
+        t = torch.tensor([(time.perf_counter() - t0) / nsteps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     steps = max(2, min(args.steps, 5))
-    for _ in range(2):
-        e2e_step()
-    dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        e2e_step()
-    dt = torch.tensor([(time.perf_counter() - t0) / steps], dtype=torch.float64, device=dev)
+    dt1 = run(1, steps)
+    dt2 = None if getattr(args, "no_e2e_pipeline", False) else run(2, 2 * steps)
+    dt = dt1 if dt2 is None or dt1 <= dt2 else dt2
     cells = torch.tensor([prob.n_owned_cells], dtype=torch.int64, device=dev)
     h2d = torch.tensor([phi_h.numel() * 8 + f_h.numel() * 8], dtype=torch.int64, device=dev)
     d2h = torch.tensor([sum(t.numel() * t.element_size() for t in out_h.values())], dtype=torch.int64, device=dev)
-    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     for t in (cells, h2d, d2h):
         dist.all_reduce(t)
-    return {"value": int(cells.item()) / float(dt.item()), "unit": UNIT, "ms_per_step": float(dt.item()) * 1e3,
-            "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(d2h.item()),
-            "api": "per rank: pinned host level set / source of its slab in, SlabProblem.classify (sharded tags with "
-                   "their exchange) + SlabProblem.assemble (owned rows), pinned host tags (1 byte per local cell / "
-                   "facet) + owned CSR values + owned b out; every GPU over its own PCIe link; max over the %d ranks, "
-                   "bytes summed over the ranks; one step at a time" % world}
+    out = {"value": int(cells.item()) / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
+           "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(d2h.item()),
+           "one_step_at_a_time_ms": dt1 * 1e3,
+           "api": "per rank: pinned host level set / source of its slab in, SlabProblem.classify (sharded tags with "
+                  "their exchange) + SlabProblem.assemble (owned rows), pinned host tags (1 byte per local cell / "
+                  "facet) + owned CSR values + owned b out; every GPU over its own PCIe link; max over the %d ranks, "
+                  "bytes summed over the ranks; %s" % (world, "one step at a time" if dt is dt1 else
+                                                       "TWO steps in flight (results staged in a second device buffer, "
+                                                       "pinned output buffers double-buffered, every step's copies "
+                                                       "inside the timed region)")}
+    if dt2 is not None:
+        out["two_steps_in_flight_ms"] = dt2 * 1e3
+    return out
 
 
 def time_to_solution(w):
@@ -864,6 +920,38 @@ def strong_scaling(args, dev, rank, world):
             "local_cells": [int(v) for v in allst[:, 0]], "owned_cells": [int(v) for v in allst[:, 1]],
             "symbolic_ms_max": float(allst[:, 2].max()), "topology_ms_max": float(allst[:, 3].max()),
             "tags_ms": [float(v) for v in allst[:, 4]], "assembly_ms": [float(v) for v in allst[:, 5]]}
+
+
+def other_config(name, args, dev, clocks):
+    """Device-resident step of another BASELINE.json configuration (same metric, same timing rules, fewer keys)."""
+    import copy
+
+    import torch
+    from phifem_b200 import synthetic
+    n = CONFIGS[name][0]
+    a = copy.copy(args)
+    a.config, a.n, a.no_replan = name, n, True
+    ls_kw = {}
+    if name.startswith("2d"):
+        mesh = synthetic.rectangle_mesh(n, device=dev)
+        ls_kw.update(center=DISC_CENTER, radius=DISC_RADIUS)
+    else:
+        mesh = synthetic.box_mesh(n, device=dev)
+    phi = synthetic.sphere_levelset(mesh.x, **ls_kw)
+    f = synthetic.ball_source(mesh.x, **({"center": DISC_CENTER} if ls_kw else {}))
+    w = Workload(mesh, phi, f, a, degree=2 if name.endswith("p2") else 1, ls_kw=ls_kw)
+    for _ in range(a.warmup):
+        w.step()
+    torch.cuda.synchronize()
+    ms, per, _ = timed_steps(w, a.steps, 1, presteps=3)
+    roof, ab, dominant = roofline_of(w, per, ms, clocks)
+    c = w.counts()
+    return {"workload": CONFIGS[name][1] % (mesh.num_cells, n), "cells": mesh.num_cells, "ms_per_step": ms,
+            "value": mesh.num_cells / (ms * 1e-3), "unit": UNIT, "kernels_ms": per, "step_frac": roof["step_frac"],
+            "dominant_kernel": roof["kernel"], "dominant_frac": roof["frac"],
+            "counts": {k: v for k, v in c.items() if k in ("interior", "cut", "exterior", "nnz", "Na", "Ng",
+                                                           "Ndof_active")},
+            "method": w.plan.method}
 
 
 def run_ours(args):
@@ -1006,6 +1094,19 @@ def run_ours(args):
         torch.cuda.empty_cache()
         w = None
 
+    # ---- the other configurations of BASELINE.json: one short measurement each --------
+    others = None
+    if world == 1 and args.config == "3d-p1" and args.mesh == "structured" and not args.no_others:
+        w = None
+        torch.cuda.empty_cache()
+        others = {}
+        for name in ("2d-p1", "2d-p2", "3d-p2"):
+            try:
+                others[name] = other_config(name, args, dev, clocks)
+            except Exception as exc:   # noqa: BLE001
+                others[name] = {"error": str(exc)}
+            torch.cuda.empty_cache()
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -1051,6 +1152,8 @@ def run_ours(args):
             line["unstructured"] = unstructured
         if tts is not None:
             line["time_to_solution_ms"] = tts
+        if others is not None:
+            line["other_configs"] = others
         if world > 1:
             line["parity_ok"] = parity_ok
             line["parity"] = ("n=12 problem through PartitionedProblem.scatter + sharded tags + owner-computes assembly on "
@@ -1105,6 +1208,8 @@ def main():
     ap.add_argument("--curve", default="auto", choices=["auto", "morton", "pencil"],
                     help="renumbering of the unstructured mesh (Mesh.reordered): Morton curve / count-balanced pencils / "
                          "auto = pencils when the mesh has the connectivity of a grid")
+    ap.add_argument("--no-others", action="store_true",
+                    help="skip the short measurements of the other BASELINE.json configurations (2d-p1, 2d-p2, 3d-p2)")
     ap.add_argument("--no-e2e-pipeline", action="store_true",
                     help="end-to-end leg: one step at a time only (default: also two steps in flight, the faster "
                          "of the two is e2e.value, both are reported)")
