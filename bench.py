@@ -1187,7 +1187,7 @@ def emit(line):
         os.write(_JSON_FD, payload)
 
 
-def main():
+def parser():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -1240,6 +1240,11 @@ def main():
                     help="multi-GPU: exchange the exterior-cell counts with an NCCL all-reduce instead of peer memory")
     ap.add_argument("--no-graph", action="store_true", help="strong scaling: eager launches instead of one CUDA graph")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    return ap
+
+
+def main():
+    ap = parser()
     args = ap.parse_args()
     if args.n is None:
         args.n = CONFIGS[args.config][0]

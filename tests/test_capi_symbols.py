@@ -35,6 +35,14 @@ def test_argument_errors_do_not_need_a_gpu():
     assert rc == -3 and b"unsupported cell type" in lib.phifem_last_error()
 
 
+def test_post_to_host_rejects_bad_arguments_without_a_gpu():
+    lib = _lib.load()
+    assert lib.phifem_post_to_host(None, None, 16, None) == -1 and b"null pointer" in lib.phifem_last_error()
+    buf = (ctypes.c_int64 * 4)()
+    assert lib.phifem_post_to_host(ctypes.addressof(buf), ctypes.addressof(buf), 0, None) == -1
+    assert b"between 1 and 4096" in lib.phifem_last_error()
+
+
 def test_hot_path_refuses_cpu_meshes():
     import numpy as np
     import pytest

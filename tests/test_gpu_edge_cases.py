@@ -153,3 +153,28 @@ def test_overwrite_values_beyond_int8_match_nothing():
     assert np.array_equal(s2[4][0], np.nonzero((ct_o == 1) | (ct_o == 2))[0])      # submesh = cells still tagged 1 / 2
     plan = assemble.build_plan(mesh, c2, f2, ds2(100))
     assert np.array_equal(np.sort(plan.active.cpu().numpy()), np.nonzero((ct_o == 1) | (ct_o == 2))[0])
+
+
+def test_counters_posted_to_the_host_equal_a_copy_and_ignore_other_streams():
+    """`phifem_post_to_host` (the one host synchronisation of compute_tags_measures): the words a kernel stores into
+    pinned host memory equal a device -> host copy of the counter block, from a side stream too; a destination the
+    device cannot address is refused."""
+    from phifem_b200 import _lib
+    mesh = synthetic.box_mesh(12, device="cuda")
+    phi = synthetic.sphere_levelset(mesh.x)
+    dls = mesh_scripts._DeviceLevelset(mesh, fem.Function(fem.functionspace_p1_device(mesh), phi), 1)
+    ws = mesh_scripts.classify(mesh, dls)
+    want = ws.counters.cpu().numpy()
+    assert np.array_equal(mesh_scripts._read_counters(ws), want) and want[:3].sum() == mesh.num_cells
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ws2 = mesh_scripts.classify(mesh, dls)
+        assert np.array_equal(mesh_scripts._read_counters(ws2), want)
+    pageable = np.zeros(_lib.N_COUNTERS, dtype=np.int64)
+    rc = _lib.load().phifem_post_to_host(_lib.ptr(ws.counters), pageable.ctypes.data, _lib.N_COUNTERS, _lib.stream())
+    torch.cuda.synchronize()
+    if rc == 0:      # a system that lets the device address pageable memory: the words arrive all the same
+        assert np.array_equal(pageable, want)
+    else:
+        assert rc == -1 and b"page-locked" in _lib.load().phifem_last_error()
