@@ -23,6 +23,13 @@ namespace {
 #ifndef PHIFEM_PK_SINGLE_STORES
 #define PHIFEM_PK_SINGLE_STORES 1
 #endif
+// k_assemble_ghost_pk: add the facet's duplicate entries up in shared memory before the reductions (400 -> 196 per P2
+// tetrahedron facet).  MEASURED at the 3d-p2 configuration: 1.253 ms against 1.040 ms for the plain scatter (2d-p2: 0.043
+// against 0.039): three more barriers and the strided shared-memory rows cost more than 204 same-address reductions.
+// Parity green (tests/test_gpu_assembly_pk.py with -DPHIFEM_PK_GHOST_DEDUPE=1); off by default.
+#ifndef PHIFEM_PK_GHOST_DEDUPE
+#define PHIFEM_PK_GHOST_DEDUPE 0
+#endif
 // Does exactly ONE cell of a conforming simplicial mesh contribute to the CSR entry (dof i, dof j) of a cell?  True when
 // the vertices the two dofs sit on (a vertex dof: itself; a P2 edge dof: the edge's two vertices) are all D + 1 vertices
 // of the cell between them AND no facet contains them all -- in 2D: two different edge dofs, or a vertex dof and the
@@ -531,18 +538,69 @@ __global__ void __launch_bounds__(kBlockPk) k_assemble_ghost_pk(
     }
   }
   __syncthreads();
-  if (!live) return;
   double E[NM];
 #pragma unroll
   for (int bb = 0; bb < NM; ++bb) E[bb] = 0.0;
-  for (int q = 0; q < nq; ++q) {
-    const double* jq = Js + ((size_t)fl * nq + q) * NM;
-    const double wa = qw[q] * coef * jq[a];
+  if (live) {
+    for (int q = 0; q < nq; ++q) {
+      const double* jq = Js + ((size_t)fl * nq + q) * NM;
+      const double wa = qw[q] * coef * jq[a];
 #pragma unroll
-    for (int bb = 0; bb < NM; ++bb) E[bb] += wa * jq[bb];
+      for (int bb = 0; bb < NM; ++bb) E[bb] += wa * jq[bb];
+    }
   }
+#if PHIFEM_PK_GHOST_DEDUPE
+  // The dofs on the facet appear on both sides of the macro element: of the NM^2 entries of E only (NM - NF)^2 land on
+  // distinct CSR entries (196 of 400 for the P2 tetrahedron), the others are 2 or 4 contributions of THIS facet to one
+  // entry -- same-address reductions issued by neighbouring threads at the same moment.  They are added up in shared
+  // memory first: twin rows / columns are recognised by their slots (row a and row a' are the same dof iff their
+  // entries in column 0 share a slot), every thread folds the twin columns of its own row, the first of two twin rows
+  // takes the other one in, and only the distinct entries go to memory.
+  constexpr int LD = NM + 1;                                            // padded row of Es
+  double* Es = Pq + (size_t)FPB * 2 * nq * NP;                           // [FPB][NM][LD]
+  int* twin = reinterpret_cast<int*>(Es + (size_t)FPB * NM * LD);        // [FPB][4][NM]: row sig, col sig, row twin, col twin
+  int* sig_r = twin + (size_t)(fl < FPB ? fl : 0) * 4 * NM;
+  int* sig_c = sig_r + NM, *tw_r = sig_c + NM, *tw_c = tw_r + NM;
+  double* row = Es + ((size_t)(fl < FPB ? fl : 0) * NM + a) * LD;
+  const int32_t* sl = slots + e * NM * NM;
+  if (live) {
+    sig_r[a] = __ldg(sl + a * NM);      // slot of (a, column 0)
+    sig_c[a] = __ldg(sl + a);           // slot of (row 0, a)
+#pragma unroll
+    for (int bb = 0; bb < NM; ++bb) row[bb] = E[bb];
+  }
+  __syncthreads();
+  if (live) {
+    int tr = a, tc = a;
+    for (int k = a - 1; k >= 0; --k) {
+      if (sig_r[k] == sig_r[a]) tr = k;
+      if (sig_c[k] == sig_c[a]) tc = k;
+    }
+    tw_r[a] = tr;
+    tw_c[a] = tc;
+  }
+  __syncthreads();
+  if (live) {
+    for (int bb = 0; bb < NM; ++bb) {   // fold the twin columns of this row (ascending: a twin points to a smaller index)
+      const int t = tw_c[bb];
+      if (t != bb) row[t] += row[bb];
+    }
+  }
+  __syncthreads();
+  if (live && tw_r[a] == a) {
+    for (int k = a + 1; k < NM; ++k)
+      if (tw_r[k] == a) {               // the other side's copy of this dof
+        const double* other = Es + ((size_t)fl * NM + k) * LD;
+        for (int bb = 0; bb < NM; ++bb) row[bb] += other[bb];
+      }
+    for (int bb = 0; bb < NM; ++bb)
+      if (tw_c[bb] == bb) atomicAdd(data + __ldg(sl + a * NM + bb), row[bb]);
+  }
+#else
+  if (!live) return;
 #pragma unroll
   for (int bb = 0; bb < NM; ++bb) atomicAdd(data + __ldg(slots + (e * NM + a) * NM + bb), E[bb]);
+#endif
 }
 
 // ==== weak-Dirichlet (dual) phi-FEM operator on the mixed space (u, p) in P_KW x P_KW ========================
@@ -1041,7 +1099,10 @@ extern "C" int phifem_assemble_ghost_pk(const phifem_mesh* mesh, const phifem_pk
     constexpr int D = decltype(d)::value, KW = decltype(kw)::value, KP = decltype(kp)::value;
     constexpr int FPB = GhostLayout<D, KW>::FPB, NM = GhostLayout<D, KW>::NM;
     const int nq = quad->n_facet_points;
-    const size_t smem = sizeof(double) * ((size_t)nq * (D + 1) + (size_t)FPB * nq * (NM + 2 * (D + 3)));
+    size_t smem = sizeof(double) * ((size_t)nq * (D + 1) + (size_t)FPB * nq * (NM + 2 * (D + 3)));
+#if PHIFEM_PK_GHOST_DEDUPE
+    smem += sizeof(double) * (size_t)FPB * NM * (NM + 1) + sizeof(int) * (size_t)FPB * 4 * NM;
+#endif
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(k_assemble_ghost_pk<D, KW, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_assemble_ghost_pk<D, KW, KP><<<(unsigned)((n_facets + FPB - 1) / FPB), kBlockPk, smem, st>>>(
