@@ -224,6 +224,7 @@ __global__ void __launch_bounds__(kBlockPkCells, D == 2 ? PHIFEM_PK_CELLS_MINBLO
 #ifndef PHIFEM_PK_PIPE_MINBLOCKS
 #define PHIFEM_PK_PIPE_MINBLOCKS 4
 #endif
+#if PHIFEM_PK_PIPE
 __device__ __forceinline__ void pk_cp_async4(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem)
                : "memory");
@@ -344,6 +345,8 @@ __global__ void __launch_bounds__(kBlockPkCells, PHIFEM_PK_PIPE_MINBLOCKS) k_ass
   wait_all();
 }
 
+#endif  // PHIFEM_PK_PIPE
+
 // ---- one-sided boundary term: one thread per (entity, test dof i) ------------------------------------------
 //   A_ij = -int_F (grad(phi psi_j).n) phi psi_i    (main.py:106), n = outward normal of the entity's cell
 template <int D, int KW, int KP>
@@ -444,8 +447,7 @@ __device__ __forceinline__ void basis_one(const double (&lam)[D + 1], const doub
 template <int D, int KW>
 struct GhostLayout {
   static constexpr int NM = 2 * Space<D, KW>::ND;
-  static constexpr int FPB = kBlockPk / NM;      // facets per block
-  static constexpr int kMaxPoints = 32;          // facet rule of the ghost / one-sided terms (16 points for P2/P2)
+  static constexpr int FPB = kBlockPk / NM;      // facets per block (the facet rule holds at most 32 points: 16 for P2 / P2)
 };
 
 template <int D, int KW, int KP>
@@ -1044,7 +1046,8 @@ extern "C" int phifem_assemble_cells_pk(const phifem_mesh* mesh, const phifem_pk
   cudaStream_t st = (cudaStream_t)stream;
   dispatch(mesh->cell_type, space_w->degree, space_phi->degree, [&](auto d, auto kw, auto kp) {
     constexpr int D = decltype(d)::value, KW = decltype(kw)::value, KP = decltype(kp)::value;
-    if constexpr (PHIFEM_PK_PIPE && Space<D, KW>::ND <= 6) {
+#if PHIFEM_PK_PIPE
+    if constexpr (Space<D, KW>::ND <= 6) {
       auto kernel = k_assemble_cells_pk_pipe<D, KW, KP>;
       const int grid = persistent_grid(kernel, kBlockPkCells, (n_active + kBlockPkCells - 1) / kBlockPkCells);
       kernel<<<grid, kBlockPkCells, 0, st>>>(*mesh, *space_w, *space_phi, quad->cell_points, quad->cell_weights,
@@ -1052,6 +1055,7 @@ extern "C" int phifem_assemble_cells_pk(const phifem_mesh* mesh, const phifem_pk
                                             data, b);
       return;
     }
+#endif
     const dim3 grid((unsigned)((n_active + kBlockPkCells - 1) / kBlockPkCells), Passes<Space<D, KW>::ND>::N);
     k_assemble_cells_pk<D, KW, KP><<<grid, kBlockPkCells, 0, st>>>(
         *mesh, *space_w, *space_phi, quad->cell_points, quad->cell_weights, quad->n_cell_points, phi, f,
