@@ -1041,6 +1041,17 @@ def run_ours(args):
         roofline["traffic"] = tr.get(dominant)
         roofline["traffic_source"] = tr.get("source", "profiles/traffic.json (ncu --set full capture of this command)")
     launches, launch_names = w.kernel_launches_per_step()
+    plan_check_ms = None
+    if world == 1 and hasattr(plan, "matches"):
+        # what a moving-interface loop pays after every re-tag to learn whether the plan can be reused
+        from phifem_b200.mesh import MeshTags
+        tdim = mesh.topology.dim
+        tags_now = (MeshTags(mesh, tdim, None, tags8=w.ws.cell_tags8), MeshTags(mesh, tdim - 1, None, tags8=w.ws.facet_tags8))
+        assert plan.matches(*tags_now), "the plan of the timed steps is not the plan of their tags"
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        plan.matches(*tags_now)
+        plan_check_ms = (time.perf_counter() - t0) * 1e3
 
     e2e = None
     if not args.no_e2e:
@@ -1146,6 +1157,7 @@ def run_ours(args):
                 "symbolic": {"builder": _sym[3], "symbolic_ms": "re-plan (pattern + row lists) on a warm process, best of "
                              "2; symbolic_first_call_ms also grows the allocator / scratch pool by several GB"},
                 "cold_step_ms": _sym[0] + ms_per_step,
+                "plan_check_ms": plan_check_ms,
                 "reorder_ms": reorder_ms if args.mesh == "unstructured" else None,
                 "scatter": scatter_info(plan)}
         if unstructured is not None:

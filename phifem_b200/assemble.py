@@ -73,6 +73,9 @@ class AssemblyPlan:
         dev = mesh.device
         self.mesh = mesh
         self.cell_tags8 = cell_tags8
+        # what the plan depends on, kept as copies (the caller may rewrite its tag arrays in place): `matches`
+        self._sig_cells = cell_tags8.clone()
+        self._sig_facets = _facet_classes(facet_tags8)
         n = mesh.num_vertices
         nv = mesh.cells.shape[1]
         self.n_rows = n
@@ -187,6 +190,21 @@ class AssemblyPlan:
         dev = self.mesh.device
         return (torch.zeros(self.nnz, dtype=torch.float64, device=dev),
                 torch.zeros(self.n_rows, dtype=torch.float64, device=dev))
+
+    def matches(self, cells_tags, facets_tags):
+        """Is this plan (pattern, row lists, slot maps) still the plan of these tags?  True iff the cells of dx((1,2)),
+        the cut cells dx(2), the ghost-penalty facets dS((2,3)) and Gamma_h (facet tag 4, hence ds(100)) are the ones
+        the plan was built from -- what a moving-interface loop asks after every `compute_tags_measures` before it
+        either reuses the plan or pays the re-plan (reference demos rebuild everything at every refinement step,
+        demo/strong-dirichlet/flower/main.py:59-66,121-123).  Two passes over the tag bytes and one host
+        synchronisation."""
+        c8, f8, _ = _plan_inputs(self.mesh, cells_tags, facets_tags, None)
+        return bool(torch.equal(c8, self._sig_cells)) and bool(torch.equal(_facet_classes(f8), self._sig_facets))
+
+
+def _facet_classes(facet_tags8):
+    """What a plan sees of a facet tag: 1 = ghost-penalty facet (tags 2 and 3 alike), 2 = Gamma_h (tag 4), 0 otherwise."""
+    return ((facet_tags8 == 2) | (facet_tags8 == 3)).to(torch.int8) + 2 * (facet_tags8 == 4).to(torch.int8)
 
 
 def _plan_inputs(mesh, cells_tags, facets_tags, ds):

@@ -147,3 +147,44 @@ def test_mesh_renumbering_maps_and_pencil_order(kind, curve):
         h = float((base.x.max() - base.x.min()) / n)
         assert float((new.x - base.x).abs().max()) <= 0.2 * h + 1e-12             # vertex i of the grid is vertex i again
         assert torch.equal(new.cells.min(dim=1).values, base.cells.min(dim=1).values)   # cells grouped by their cube
+
+
+def test_plan_matches_says_when_the_tags_need_a_new_plan():
+    """`AssemblyPlan.matches`: True for the tags the plan was built from (also after the caller rewrote its arrays in place
+    with the same values, and whatever happens to facet tags the plan never looks at), False as soon as a cell enters or
+    leaves dx((1,2)) / dx(2) or a facet enters or leaves dS((2,3)) / Gamma_h."""
+    m = synthetic.unstructured_variant(synthetic.rectangle_mesh(12, device="cpu"), jitter=0.1, seed=5)
+    x, cells = m.x.numpy(), m.cells.numpy().astype(np.int64)
+
+    def tags_of(radius):
+        phi = ((x - np.array([0.1, 0.05])) ** 2).sum(axis=1) - radius * radius
+        pts = OT.cell_detection_points("triangle", 1)
+        ftab = np.asarray([OT.coordinate_basis("triangle", p)[0] for p in OT.facet_points_in_cell("triangle", 1)])
+        return OT.compute_tags_measures(x, cells, "triangle", phi[cells], OT.point_values_function(phi, cells, ftab),
+                                        box_mode=True, detection_points=pts)
+
+    out = tags_of(0.6)
+    c8, f8 = torch.from_numpy(out["cell_tags"]).to(torch.int8), torch.from_numpy(out["facet_tags"]).to(torch.int8)
+    ctags, ftags = MeshTags(m, 2, None, tags8=c8), MeshTags(m, 1, None, tags8=f8)
+    plan = assemble.build_plan(m, ctags, ftags, out["ds100"])
+    assert plan.matches(ctags, ftags)
+    assert plan.matches(MeshTags(m, 2, torch.from_numpy(out["cell_tags"])), MeshTags(m, 1, torch.from_numpy(out["facet_tags"])))
+    # facet tags 1 / 5 / 6 are not part of any integral of the operator
+    f_other = f8.clone()
+    f_other[f_other == 5] = 6
+    assert plan.matches(ctags, MeshTags(m, 1, None, tags8=f_other))
+    # the interface moved: other cut cells, other ghost facets
+    out2 = tags_of(0.63)
+    assert not np.array_equal(out2["cell_tags"], out["cell_tags"])
+    moved_c = MeshTags(m, 2, torch.from_numpy(out2["cell_tags"]))
+    moved_f = MeshTags(m, 1, torch.from_numpy(out2["facet_tags"]))
+    assert not plan.matches(moved_c, moved_f) and not plan.matches(moved_c, ftags) and not plan.matches(ctags, moved_f)
+    # the caller's arrays rewritten in place: the plan kept its own copy of what it depends on
+    c8.copy_(torch.from_numpy(out2["cell_tags"]).to(torch.int8))
+    assert not plan.matches(ctags, ftags)
+    c8.copy_(torch.from_numpy(out["cell_tags"]).to(torch.int8))
+    assert plan.matches(ctags, ftags)
+    # one facet leaving Gamma_h is enough
+    f_one = f8.clone()
+    f_one[torch.nonzero(f_one == 4)[0]] = 5
+    assert not plan.matches(ctags, MeshTags(m, 1, None, tags8=f_one))
