@@ -113,6 +113,16 @@ int phifem_abi_version(void);
  * :360-374: warnings and debug checks on assembled arrays). */
 int phifem_post_to_host(const int64_t* device_words, int64_t* pinned_host_words, int32_t n_words, void* stream);
 
+/* Do these tags still belong to an assembly plan?  `cell_signature` = a copy of the one-byte cell tags the plan was
+ * built from, `facet_signature` = the facet classes it depends on (1 = facet tag 2 or 3: ghost penalty, 2 = tag 4:
+ * Gamma_h, 0 otherwise).  One pass; *mismatches (device int64, zeroed by the call) is non-zero afterwards iff a cell
+ * tag or a facet class differs.  What a moving-interface loop asks after every classification before it reuses the
+ * plan; the reference rebuilds its forms and matrices at every step (demo/strong-dirichlet/flower/main.py:59-66,
+ * 121-123). */
+int phifem_tags_match(const int8_t* cell_tags8, const int8_t* cell_signature, int64_t n_cells,
+                      const int8_t* facet_tags8, const int8_t* facet_signature, int64_t n_facets,
+                      int64_t* mismatches, void* stream);
+
 /* Physical coordinates of reference points in every cell: out[n_cells, n_points, gdim].
  * `shape` [n_points, nvpc] = coordinate-element basis at the points.  Used to evaluate an
  * expression level set where the reference evaluates a UFL expression of SpatialCoordinate. */

@@ -99,6 +99,7 @@ _SIGNATURES = {
     "phifem_last_error": (ctypes.c_char_p, []),
     "phifem_abi_version": (ctypes.c_int, []),
     "phifem_post_to_host": (ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp]),
+    "phifem_tags_match": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp, _vp, ctypes.c_int64, _vp, _vp]),
     "phifem_cell_points": (ctypes.c_int, [ctypes.POINTER(CMesh), _vp, ctypes.c_int32, _vp, _vp]),
     "phifem_tag_cells": (ctypes.c_int, [ctypes.POINTER(CMesh), ctypes.POINTER(CLevelset),
                                         ctypes.c_int32, _vp, _vp, _vp, _vp, _vp]),

@@ -197,8 +197,15 @@ class AssemblyPlan:
         the plan was built from -- what a moving-interface loop asks after every `compute_tags_measures` before it
         either reuses the plan or pays the re-plan (reference demos rebuild everything at every refinement step,
         demo/strong-dirichlet/flower/main.py:59-66,121-123).  Two passes over the tag bytes and one host
-        synchronisation."""
+        synchronisation (CPU tensors, as in the host-logic tests: torch passes)."""
         c8, f8, _ = _plan_inputs(self.mesh, cells_tags, facets_tags, None)
+        if c8.numel() != self._sig_cells.numel() or f8.numel() != self._sig_facets.numel():
+            return False
+        if c8.is_cuda:      # one fused pass behind the C ABI (csrc/capi.cu phifem_tags_match)
+            bad = torch.empty(1, dtype=torch.int64, device=c8.device)
+            _lib.check(_lib.load().phifem_tags_match(_lib.ptr(c8), _lib.ptr(self._sig_cells), c8.numel(), _lib.ptr(f8),
+                                                     _lib.ptr(self._sig_facets), f8.numel(), _lib.ptr(bad), _lib.stream()))
+            return int(bad.item()) == 0
         return bool(torch.equal(c8, self._sig_cells)) and bool(torch.equal(_facet_classes(f8), self._sig_facets))
 
 

@@ -178,3 +178,42 @@ def test_counters_posted_to_the_host_equal_a_copy_and_ignore_other_streams():
         assert np.array_equal(pageable, want)
     else:
         assert rc == -1 and b"page-locked" in _lib.load().phifem_last_error()
+
+
+def test_plan_matches_on_the_device():
+    """`AssemblyPlan.matches` through `phifem_tags_match`: same answers as the torch passes of the CPU path -- for the
+    plan's own tags, for tags that differ in one cell / one facet class at the very end of the arrays, and for
+    unaligned views (the byte path of the kernel)."""
+    from phifem_b200 import _lib
+    from phifem_b200.mesh import MeshTags
+    mesh = synthetic.box_mesh(11, device="cuda")
+    phi = synthetic.sphere_levelset(mesh.x, radius=0.37)
+    ctags, ftags, _, ds, _ = _run(mesh, phi)
+    plan = assemble.build_plan(mesh, ctags, ftags, ds(100))
+    assert plan.matches(ctags, ftags)
+    c8, f8 = ctags.tags8.clone(), ftags.tags8.clone()
+    assert plan.matches(MeshTags(mesh, 3, None, tags8=c8), MeshTags(mesh, 2, None, tags8=f8))
+    other = f8.clone()
+    other[other == 5] = 6                                  # a tag no integral looks at
+    assert plan.matches(ctags, MeshTags(mesh, 2, None, tags8=other))
+    last_c = c8.clone()
+    last_c[-1] = 1 if int(last_c[-1]) != 1 else 3
+    assert not plan.matches(MeshTags(mesh, 3, None, tags8=last_c), ftags)
+    last_f = f8.clone()
+    last_f[-1] = 4 if int(last_f[-1]) != 4 else 5
+    assert not plan.matches(ctags, MeshTags(mesh, 2, None, tags8=last_f))
+    ctags2, ftags2, _, _, _ = _run(mesh, synthetic.sphere_levelset(mesh.x, radius=0.40))
+    assert not plan.matches(ctags2, ftags2)
+    # the kernel on unaligned arrays
+    lib, bad = _lib.load(), torch.empty(1, dtype=torch.int64, device="cuda")
+    sig_f = ((f8 == 2) | (f8 == 3)).to(torch.int8) + 2 * (f8 == 4).to(torch.int8)
+    for shift, want in ((1, 0), (3, 0)):
+        a, b, c, d = c8[shift:], c8.clone()[shift:], f8[shift:], sig_f[shift:]
+        _lib.check(lib.phifem_tags_match(a.data_ptr(), b.data_ptr(), a.numel(), c.data_ptr(), d.data_ptr(), c.numel(),
+                                         _lib.ptr(bad), _lib.stream()))
+        assert int(bad.item()) == want
+    d2 = sig_f.clone()
+    d2[5] = (int(d2[5]) + 1) % 3
+    _lib.check(lib.phifem_tags_match(c8[1:].data_ptr(), c8[1:].data_ptr(), c8.numel() - 1, f8[1:].data_ptr(),
+                                     d2[1:].data_ptr(), f8.numel() - 1, _lib.ptr(bad), _lib.stream()))
+    assert int(bad.item()) > 0
