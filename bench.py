@@ -954,6 +954,24 @@ def other_config(name, args, dev, clocks):
             "method": w.plan.method}
 
 
+def _bind_to_gpu_cores(index):
+    """One process per GPU: run on the host cores NVML lists as local to this GPU, so that the pinned buffers of the
+    end-to-end leg are first touched on the memory node the GPU's PCIe root hangs off (on a two-socket host the copies of
+    the ranks bound to the far socket otherwise cross the inter-socket link).  A no-op where the mask does not narrow the
+    process's own (single-node hosts and VMs)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        words = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index), 16)
+        local = {64 * i + b for i, w_ in enumerate(words) for b in range(64) if (int(w_) >> b) & 1}
+        mine = os.sched_getaffinity(0)
+        if local & mine and (local & mine) != mine:
+            os.sched_setaffinity(0, local & mine)
+            sys.stderr.write("bench.py: rank on GPU %d bound to host cores %s\n" % (index, sorted(local & mine)))
+    except Exception as exc:   # noqa: BLE001
+        sys.stderr.write("bench.py: no GPU-local core binding (%s)\n" % exc)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -970,6 +988,7 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        _bind_to_gpu_cores(local_rank)
 
     n = args.n
     degree = 2 if args.config.endswith("p2") else 1
